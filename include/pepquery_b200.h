@@ -1,0 +1,237 @@
+/*
+ * pepquery_b200.h — C ABI of the B200-native PepQuery pair-scoring path.
+ *
+ * This is the drop-in boundary.  The reference (PepQuery 2.0.4,
+ * 100 % Java) has no FFI seam; the seam is created at its batch fan-out loops.
+ * Every entry point below names the reference loop it replaces (file:line under
+ * /root/reference/src/main/java/).  A Java host binds these through JNI or
+ * Panama FFM; tests bind them through ctypes.
+ *
+ * Rules of the boundary
+ *   - plain C: pointers, sizes, POD structs; no C++/torch types;
+ *   - the caller owns every input and output buffer; the library copies inputs to
+ *     the device during the call and never keeps a host pointer after return;
+ *   - every function returns int32 (PQ_OK = 0, <0 = pq_status); text through
+ *     pq_last_error(); nothing throws or exits across the boundary;
+ *   - there is NO CPU fallback: without a CUDA device pq_create fails with
+ *     PQ_ERR_NO_DEVICE;
+ *   - one pq_ctx per GPU; calls on one ctx are serialised by the caller; every call
+ *     is synchronous at return.
+ */
+#ifndef PEPQUERY_B200_H
+#define PEPQUERY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PQ_VERSION_MAJOR 0
+#define PQ_VERSION_MINOR 1
+
+#define PQ_MAX_ISOTOPE 8
+#define PQ_MAX_MODS 8
+#define PQ_MAX_PEP_LEN 63      /* residues per peptide form handled on device (reference default max 45) */
+#define PQ_MAX_FORM_MODS 16    /* modification matches carried per peptide form */
+
+typedef enum pq_status {
+    PQ_OK = 0,
+    PQ_ERR_BAD_ARG = -1,
+    PQ_ERR_CAPACITY = -2,     /* caller buffer too small; required size returned through the size out-param */
+    PQ_ERR_CUDA = -3,
+    PQ_ERR_NO_DEVICE = -4,    /* no CUDA device: there is no CPU fallback */
+    PQ_ERR_STATE = -5,        /* call order violated (e.g. step3 before step2) */
+    PQ_ERR_UNSUPPORTED = -6,
+    PQ_ERR_NOMEM = -7
+} pq_status;
+
+/* Where a modification may sit.  Mirrors compomics ModificationType as used by
+ * ModificationUtils.getPossibleModificationSites (call sites pg/PeptideInput.java:127,224,515;
+ * OpenModificationSearch/ModificationDB.java:284). */
+typedef enum pq_mod_position {
+    PQ_MOD_ANYWHERE = 0,        /* modaa: every listed residue, site = 1-based residue index   */
+    PQ_MOD_PEP_NTERM = 1,       /* modn_peptide: site 0                                         */
+    PQ_MOD_PEP_CTERM = 2,       /* modc_peptide: site L+1                                       */
+    PQ_MOD_PEP_NTERM_AA = 3,    /* modnaa_peptide: site 1 if residue 1 is listed                */
+    PQ_MOD_PEP_CTERM_AA = 4,    /* modcaa_peptide: site L if residue L is listed                */
+    PQ_MOD_PROT_NTERM = 5,      /* protein-terminal types: never placed on digest peptides here */
+    PQ_MOD_PROT_CTERM = 6,
+    PQ_MOD_PROT_NTERM_AA = 7,
+    PQ_MOD_PROT_CTERM_AA = 8
+} pq_mod_position;
+
+/* A resolved modification: what pg/ModificationGear.java:100-132 hands to the search
+ * (the Java host keeps the id -> name mapping; the shim only needs residue, mass, loss). */
+typedef struct pq_mod {
+    int32_t id;                 /* caller's id (e.g. the -fixMod/-varMod number); echoed in results    */
+    int32_t position;           /* pq_mod_position                                                     */
+    char    residues[24];       /* NUL-terminated residue letters for residue-specific positions       */
+    double  delta;              /* monoisotopic mass shift                                             */
+    double  neutral_loss;       /* mass of the modification-defined neutral loss (0 = none); only the
+                                   MVH predicted-peak count uses it (PSMMatch/MVHMatch.java:150-199)   */
+} pq_mod;
+
+/* POD mirror of the pg/CParameter.java statics the hot path reads. */
+typedef struct pq_params {
+    double  tol;                /* precursor tolerance (CParameter.tol, default 10)                    */
+    int32_t tol_ppm;            /* 1 = ppm (CParameter.tolu "ppm"), 0 = Da                             */
+    int32_t score_method;       /* 1 = hyperscore, 2 = MVH (CParameter.scoreMethod)                    */
+    double  itol;               /* fragment tolerance in Da (CParameter.itol, default 0.6)             */
+    double  min_score;          /* CParameter.minScore, default 12                                     */
+    int32_t min_peaks;          /* CParameter.minPeaks, default 10: spectra with <= this are skipped   */
+    int32_t n_isotope;          /* entries of isotope[]; {0} by default (CParameter.isotope_error)     */
+    int32_t isotope[PQ_MAX_ISOTOPE];
+    int32_t max_var_mods;       /* CParameter.maxVarMods, default 3                                    */
+    int32_t max_mods_per_aa;    /* CParameter.maxModsPerAA, default 1                                  */
+    int32_t fast;               /* CParameter.fast_model                                               */
+    int32_t hc;                 /* CParameter.unrestrictedSearchWithEqualAndBetterScore (-hc)          */
+    int32_t n_random;           /* CParameter.nRandomPeptides (-n), reference default 10000            */
+    int32_t enzyme;             /* 1 = trypsin (K/R not before P), 0 = non-specific unsupported        */
+    int32_t max_missed;         /* CParameter.maxMissedCleavages, default 2                            */
+    int32_t min_len, max_len;   /* 7 / 45                                                              */
+    double  min_mass, max_mass; /* 500 / 10000 (digest mass window)                                    */
+    int64_t shuffle_seed;       /* 12457 (pg/PeptideInput.java:433)                                    */
+    int64_t mod_seed;           /* 2022  (pg/PeptideInput.java:500)                                    */
+    int32_t n_fixed, n_var;
+    pq_mod  fixed[PQ_MAX_MODS];
+    pq_mod  var[PQ_MAX_MODS];
+    int32_t device;             /* CUDA device ordinal                                                 */
+    int32_t reserved;
+} pq_params;
+
+/* One peptide form (sequence + placed modifications) as the caller sees it. */
+typedef struct pq_form {
+    int32_t seq_index;          /* index of the parent sequence in the table it came from              */
+    int32_t length;
+    double  mass;               /* H2O + residues + mods                                               */
+    int32_t n_mods;
+    uint8_t mod_site[PQ_MAX_FORM_MODS];   /* 0 = N-term, 1..L residues, L+1 = C-term                   */
+    int8_t  mod_index[PQ_MAX_FORM_MODS];  /* >=0: var[idx]; <0: fixed[-idx-1]; in reference list order  */
+    char    seq[PQ_MAX_PEP_LEN + 1];
+} pq_form;
+
+/* One target PSM and everything Steps 2-5 attach to it.  Field names follow the columns of
+ * psm.txt / psm_rank.txt (pg/PeptideSearchMT.java:1634, pg/RankPSM.java:80, PSMT:1007). */
+typedef struct pq_psm {
+    int32_t spectrum;           /* index in the caller's spectrum order (pq_load_spectra)              */
+    int32_t form;               /* target form index (pq_get_target_forms order)                       */
+    double  score;              /* hyperscore or MVH                                                   */
+    double  exp_mass;           /* precursor neutral mass (isotope-corrected mass that matched)        */
+    double  pep_mass;
+    double  tol_ppm;            /* signed, CParameter.get_mass_error                                   */
+    int32_t isotope_error;
+    int32_t count_b;            /* hyperscore: matched b / y ions; MVH: matched peaks / predicted      */
+    int32_t count_y;
+    int32_t n_db;               /* Step 3: reference forms scoring >= best target score of the spectrum */
+    int32_t total_db;           /* Step 3: reference forms inside the precursor window                 */
+    int32_t n_random;           /* Step 4: shuffles scoring >= target; -1 = not evaluated              */
+    int32_t total_random;       /* Step 4: distinct shuffles produced; -1 = not evaluated              */
+    int32_t valid;              /* 0 once Step 3 found a better reference match                        */
+    double  p_value;            /* (n_random+1)/(total_random+1); 100 = not evaluated                  */
+    int32_t rank;               /* pg/RankPSM.java:36-148, 1-based within the spectrum                 */
+    int32_t n_ptm;              /* Step 5: PTM forms scoring > (>= with hc) the target; -1 = not run   */
+    int32_t confident;          /* CParameter.passed_psm_validation(len,p,n_db,rank,n_ptm)             */
+    int32_t reserved;
+} pq_psm;
+
+/* Row of detail.txt / ptm.txt: a competitor that matched a target spectrum. */
+typedef struct pq_competitor {
+    int32_t spectrum;
+    int32_t ref_form;           /* reference form index (pq_get_reference_forms order)                 */
+    int32_t ptm;                /* Step 5: index into the PTM table, -1 for Step 3 rows                */
+    int32_t ptm_site;           /* Step 5: site carrying the PTM                                       */
+    double  score;
+    double  pep_mass;
+} pq_competitor;
+
+/* Unimod-like PTM specificity for Step 5 (OpenModificationSearch/ModificationDB.java:334-533). */
+typedef struct pq_ptm {
+    int32_t id;
+    int32_t position;           /* pq_mod_position                                                     */
+    char    residue;            /* 0 for terminal-only specificities                                   */
+    char    pad[7];
+    double  delta;
+} pq_ptm;
+
+/* Work and time counters (what the Java log lines at PSMT:476,574,589 report). */
+typedef struct pq_counters {
+    uint64_t pairs_step2, pairs_step3, pairs_step4, pairs_step5;   /* scorePeptide2Spectrum calls the
+                                                                       reference would have made       */
+    uint64_t spectra_loaded, spectra_usable, spectra_prepared;
+    uint64_t target_forms, reference_sequences, reference_forms, psms;
+    uint64_t score_kernel_launches, other_kernel_launches;
+    uint64_t score_algorithmic_bytes;   /* sum over scored pairs of 16*P_s + 64 + 32   */
+    double   ms_prepare, ms_window, ms_score, ms_shuffle, ms_total; /* CUDA-event time on the ctx stream */
+    uint64_t h2d_bytes, d2h_bytes;
+} pq_counters;
+
+typedef struct pq_ctx pq_ctx;
+
+int32_t     pq_version(void);
+const char* pq_last_error(const pq_ctx* ctx);          /* ctx may be NULL: error of the last failed pq_create */
+void        pq_default_params(pq_params* p);           /* defaults of pg/CParameter.java:84-463 with -n 1000   */
+
+int32_t pq_create(const pq_params* params, pq_ctx** out);
+int32_t pq_destroy(pq_ctx* ctx);
+
+/* Spectrum loader.  Replaces the MGF->task loop of pg/SpectraInput.java:142-198 (readMSMSfast):
+ * packs peak lists into precursor-mass-sorted CSR device arrays with a 0.1-Da bucket index.
+ * Peaks may be in any order; spectra with n_peaks <= min_peaks are kept but never scored
+ * (SpectraInput.java:183).  charge[i] must be >= 1. */
+int32_t pq_load_spectra(pq_ctx* ctx, int64_t n_spectra, const double* precursor_mz, const int32_t* charge,
+                        const uint64_t* peak_offset /* n+1 */, const double* mz, const double* intensity);
+
+/* Target peptides.  Replaces CreatePeptideInputWorker -> PeptideInput.calcPeptideIsoforms
+ * (pg/PeptideInput.java:114-237): expands each sequence into its modification forms. */
+int32_t pq_set_targets(pq_ctx* ctx, int32_t n_seq, const uint32_t* seq_offset /* n+1 */, const char* residues);
+int32_t pq_get_target_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int64_t* n_forms);
+
+/* Reference database.  Replaces DatabaseInput.generate_reference_peptide_index
+ * (pg/DatabaseInput.java:402-556) + DigestProteinWorker.run (OpenModificationSearch/DigestProteinWorker.java:64-137)
+ * + GeneratePeptideformWorker.run (:25-52): digest, I->L, unique, minus targets, isoforms, mass window,
+ * mass-sorted device table with 0.1-Da buckets.  Call after pq_step2 (the mass window is taken from the
+ * matched spectra, GeneratePeptideformWorker.set_mass_range). */
+int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* seq_offset /* n+1 */, const char* residues);
+int32_t pq_get_reference_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int64_t* n_forms);
+
+/* Step 2.  Replaces FindCandidateSpectraAndScoreWorker.run (pg/FindCandidateSpectraAndScoreWorker.java:33-100):
+ * every usable spectrum x every target form in its precursor window; keeps score > min_score. */
+int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms);
+/* Step 3.  Replaces DBSearchWorker.run (pg/DBSearchWorker.java:25-113) driven by DatabaseInput.db_search
+ * (pg/DatabaseInput.java:672-758): n_db / total_db per matched spectrum, valid flags. */
+int32_t pq_step3_competitors(pq_ctx* ctx);
+/* Step 4.  Replaces StatisticScoreCalc.run (pg/StatisticScoreCalc.java:19-63) + StatisticScoreWorker.run
+ * (pg/StatisticScoreWorker.java:36-63) + PeptideInput.generateRandomPeptidesFast / getModificationPeptide
+ * (pg/PeptideInput.java:376-557). */
+int32_t pq_step4_shuffles(pq_ctx* ctx);
+/* Rank + accept.  pg/RankPSM.java:36-148 and CParameter.passed_psm_validation (pg/CParameter.java:913-940). */
+int32_t pq_rank_and_validate(pq_ctx* ctx);
+/* Step 5.  Replaces ModificationDB.doPTMValidation (OpenModificationSearch/ModificationDB.java:1320-1466)
+ * -> ModPepQueryAndScoringWorker.do_score (ModPepQueryAndScoringWorker.java:149-276). */
+int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms);
+
+int32_t pq_get_psms(pq_ctx* ctx, pq_psm* out, int64_t capacity, int64_t* n_psms);
+int32_t pq_get_competitors(pq_ctx* ctx, int32_t step /* 3 or 5 */, pq_competitor* out, int64_t capacity, int64_t* n_rows);
+/* Shuffled sequences of one target sequence, in generation order (for parity checks of the RNG stream). */
+int32_t pq_get_shuffles(pq_ctx* ctx, int32_t target_seq, char* out /* n * (L+1) bytes, NUL separated */,
+                        int64_t capacity, int32_t* n_shuffles);
+
+/* Per-pair entry.  Replaces PeptideSearchMT.scorePeptide2Spectrum (pg/PeptideSearchMT.java:1144-1251) for
+ * callers that score an explicit list (pg/ScoreWorker.java:26-45, plot/, msio/).  forms[i] is scored
+ * against spectrum_index[i]; outputs score and the two counts. */
+int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_index, const pq_form* forms,
+                       double* score, int32_t* count_a, int32_t* count_b);
+
+int32_t pq_get_counters(pq_ctx* ctx, pq_counters* out);
+int32_t pq_reset_counters(pq_ctx* ctx);
+
+/* Host-side text front end: single-pass MGF parser into CSR buffers.  Two-call pattern:
+ * first call with NULL outputs returns the required sizes. */
+int32_t pq_parse_mgf(const char* text, uint64_t n_bytes, int64_t* n_spectra, uint64_t* n_peaks,
+                     double* precursor_mz, int32_t* charge, uint64_t* peak_offset, double* mz, double* intensity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEPQUERY_B200_H */

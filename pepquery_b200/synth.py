@@ -1,0 +1,97 @@
+"""Synthetic proteins / target peptides / spectra of the shape SURVEY.md §8d names.
+
+Thin numpy wrapper over tools/libpq_synth.so (C++, deterministic per-index RNG streams).  Test and bench
+infrastructure; not part of the scoring path.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+
+def build():
+    src = os.path.join(_ROOT, "tools", "pq_synth.cpp")
+    out = os.path.join(_ROOT, "tools", "libpq_synth.so")
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", out, src])
+    return out
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_ROOT, "tools", "libpq_synth.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.syn_proteins.restype = C.c_int64
+        L.syn_proteins.argtypes = [C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64]
+        L.syn_targets.restype = C.c_int64
+        L.syn_targets.argtypes = [C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64]
+        L.syn_mass_bounds.restype = C.c_int32
+        L.syn_mass_bounds.argtypes = [C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.syn_spectra.restype = C.c_int64
+        L.syn_spectra.argtypes = [C.c_int64, C.c_uint64, C.c_int64, C.c_double, C.c_double,
+                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def proteins(n, seed=20240101):
+    """-> (offsets uint64[n+1], residues uint8[total])"""
+    L = _lib()
+    off = np.zeros(n + 1, dtype=np.uint64)
+    total = L.syn_proteins(n, seed, _p(off), None, 0)
+    res = np.zeros(total, dtype=np.uint8)
+    L.syn_proteins(n, seed, _p(off), _p(res), total)
+    return off, res
+
+
+def targets(n, seed=7):
+    """-> (offsets uint32[n+1], residues uint8[total])"""
+    L = _lib()
+    off = np.zeros(n + 1, dtype=np.uint32)
+    total = L.syn_targets(n, seed, _p(off), None, 0)
+    res = np.zeros(total, dtype=np.uint8)
+    L.syn_targets(n, seed, _p(off), _p(res), total)
+    return off, res
+
+
+def mass_bounds(shards, tgt, prot, seed=99):
+    toff, tres = tgt
+    poff, pres = prot
+    b = np.zeros(shards + 1, dtype=np.float64)
+    _lib().syn_mass_bounds(seed, shards, len(toff) - 1, _p(toff), _p(tres), len(poff) - 1, _p(poff), _p(pres), _p(b))
+    return b
+
+
+def spectra(n, tgt, prot, seed=99, itol=0.6, first_index=0, mass_lo=0.0, mass_hi=1e9, threads=0, pinned=None):
+    """-> dict(prec_mz f64[n], charge i32[n], peak_off u64[n+1], mz f64[P], inten f64[P]).
+
+    pinned: optional callable (nbytes) -> numpy float64 array backed by pinned memory, for the peak arrays."""
+    L = _lib()
+    toff, tres = tgt
+    poff, pres = prot
+    prec = np.zeros(n, dtype=np.float64)
+    chg = np.zeros(n, dtype=np.int32)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    args = (n, seed, first_index, mass_lo, mass_hi, len(toff) - 1, _p(toff), _p(tres), len(poff) - 1, _p(poff), _p(pres), itol)
+    total = L.syn_spectra(*args, _p(prec), _p(chg), _p(off), None, None, threads)
+    if pinned is not None:
+        mz = pinned(total)
+        inten = pinned(total)
+    else:
+        mz = np.zeros(total, dtype=np.float64)
+        inten = np.zeros(total, dtype=np.float64)
+    L.syn_spectra(*args, _p(prec), _p(chg), _p(off), _p(mz), _p(inten), threads)
+    return dict(prec_mz=prec, charge=chg, peak_off=off, mz=mz, inten=inten)
