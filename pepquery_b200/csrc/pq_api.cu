@@ -1,0 +1,882 @@
+// pq_api.cu — the C ABI of libpepquery_b200.so (include/pepquery_b200.h): context, device residency, step drivers.
+// No CPU fallback: every scoring entry point launches CUDA kernels or fails.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "pq_host.h"
+
+using namespace pq;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { if (p) cudaFree(p); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; } return *this; }
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PeptideTable {               // a mass-sorted candidate table resident on the device
+    std::vector<std::string> seqs;  // parent sequences
+    std::vector<FormRec> forms;     // mass ascending
+    DevBuf rows, mass, pred;
+    std::vector<double> h_mass;     // host copy for range searches
+    size_t n() const { return forms.size(); }
+};
+
+struct TargetOrder { std::vector<uint32_t> row_of_form, form_of_row; };   // public (generation) order <-> device (mass) order
+
+struct HostPsm {
+    int32_t spectrum_sorted, spectrum, form; uint32_t blob;
+    double score, exp_mass, pep_mass; int32_t iso, ca, cb, charge;
+    int32_t n_db = 0, total_db = 0, n_random = -1, total_random = -1, valid = 1;
+    double p_value = 100.0; int32_t rank = 0, n_ptm = -1, confident = 0;
+};
+
+}  // namespace
+
+struct pq_ctx {
+    pq_params P;
+    Codes codes;
+    std::string err;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    pq_counters cnt;
+    // constant tables
+    DevBuf d_mods, d_l10, d_lnf, d_shufmods;
+    std::vector<double> ln_fact; double log10_fact[65];
+    // spectra
+    int64_t nS = 0; uint32_t max_peaks = 0;
+    DevBuf s_prec, s_charge, s_mass, s_off, s_mz, s_in, s_caller;
+    std::vector<int32_t> h_caller; std::vector<double> h_mass; std::vector<int32_t> h_charge; std::vector<uint32_t> h_npeaks;
+    SpectraView view() const {
+        SpectraView v; v.n = nS; v.prec_mz = s_prec.as<double>(); v.charge = s_charge.as<int32_t>(); v.mass = s_mass.as<double>();
+        v.off = s_off.as<uint64_t>(); v.mz = s_mz.as<double>(); v.inten = s_in.as<double>(); v.caller_index = s_caller.as<int32_t>();
+        return v;
+    }
+    // prepared spectra
+    DevBuf blobs, blob_off, prep_id, prep_list, need, scratch, scan_tmp;
+    uint32_t n_prepared = 0; uint32_t max_blob = 0;
+    // tables
+    PeptideTable targets, reference;
+    TargetOrder order;
+    bool have_targets = false, have_reference = false;
+    int step_done = 0;
+    // work buffers
+    DevBuf jobs, results, hits, hit_count, njobs;
+    // shuffles
+    DevBuf sh_seqs, sh_forms, sh_raw, sh_kidx, sh_kcnt, sh_rows;
+    std::vector<ShuffleSeq> h_sh_seqs; std::vector<uint32_t> h_kept; std::vector<int32_t> sh_slot_of_seq;
+    // results
+    std::vector<HostPsm> psms;
+    std::vector<pq_competitor> comp3, comp5;
+};
+
+namespace {
+
+int32_t fail(pq_ctx* c, int32_t code, const std::string& msg) { if (c) c->err = msg; else g_create_error = msg; return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, PQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct Timer {
+    pq_ctx* c; double* acc;
+    Timer(pq_ctx* c_, double* a) : c(c_), acc(a) { cudaEventRecord(c->ev0, c->st); }
+    ~Timer() { cudaEventRecord(c->ev1, c->st); cudaEventSynchronize(c->ev1); float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); *acc += ms; c->cnt.ms_total += ms; }
+};
+
+int32_t upload_table(pq_ctx* ctx, PeptideTable& T) {
+    const size_t n = T.n();
+    std::vector<uint8_t> rows(n * kRowBytes);
+    T.h_mass.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        if (!ctx->codes.encode_row(T.seqs[(size_t)T.forms[i].seq], T.forms[i], rows.data() + i * kRowBytes))
+            return fail(ctx, PQ_ERR_UNSUPPORTED, "peptide form cannot be encoded (length > 60 or two modifications on one site): " + T.seqs[(size_t)T.forms[i].seq]);
+        T.h_mass[i] = T.forms[i].mass;
+    }
+    CU(T.rows.reserve(std::max<size_t>(rows.size(), 64)));
+    CU(T.mass.reserve(std::max<size_t>(n * 8, 64)));
+    CU(cudaMemcpyAsync(T.rows.p, rows.data(), rows.size(), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(T.mass.p, T.h_mass.data(), n * 8, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->cnt.h2d_bytes += rows.size() + n * 8;
+    return PQ_OK;
+}
+
+ScoreConfig score_config(const pq_ctx* c, int check_window) {
+    ScoreConfig s; s.itol = c->P.itol; s.tol = c->P.tol; s.tol_ppm = c->P.tol_ppm; s.method = c->P.score_method;
+    s.min_score = c->P.min_score; s.fast = c->P.fast; s.hc = c->P.hc;
+    s.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (c->P.itol * 2.0));
+    s.check_window = check_window;
+    return s;
+}
+
+// run K1 over a job list that already sits in ctx->jobs; fills results (+hits)
+int32_t run_score(pq_ctx* ctx, JobKind kind, uint32_t n_jobs, const PeptideTable* T, const uint8_t* rows, const double* row_mass,
+                  uint32_t hit_capacity, int check_window) {
+    CU(ctx->results.reserve(std::max<size_t>((size_t)n_jobs * sizeof(JobResult), 64)));
+    CU(ctx->hits.reserve(std::max<size_t>((size_t)hit_capacity * sizeof(Hit), 64)));
+    CU(ctx->hit_count.reserve(64));
+    CU(cudaMemsetAsync(ctx->hit_count.p, 0, 4, ctx->st));
+    ScoreLaunch L; memset(&L, 0, sizeof L);
+    L.kind = kind; L.jobs = ctx->jobs.as<Job>(); L.n_jobs = n_jobs;
+    L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>();
+    L.rows = rows; L.row_mass = row_mass; L.mods = ctx->d_mods.as<ModTable>();
+    L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>();
+    L.row_pred = T ? T->pred.as<int32_t>() : nullptr;
+    L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>();
+    L.hit_capacity = hit_capacity; L.max_blob_bytes = ctx->max_blob;
+    ScoreConfig cfg = score_config(ctx, check_window);
+    {
+        Timer t(ctx, &ctx->cnt.ms_score);
+        ctx->cnt.score_kernel_launches += (uint64_t)launch_score(L, cfg, ctx->st);
+    }
+    CU(cudaGetLastError());
+    return PQ_OK;
+}
+
+template <class T> int32_t scan_exclusive(pq_ctx* ctx, const T* in, T* out, int n) {
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, ctx->st);
+    CU(ctx->scan_tmp.reserve(tmp + 64));
+    CU(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp, in, out, n, ctx->st));
+    return PQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t pq_version(void) { return PQ_VERSION_MAJOR * 100 + PQ_VERSION_MINOR; }
+const char* pq_last_error(const pq_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void pq_default_params(pq_params* p) {
+    memset(p, 0, sizeof *p);
+    p->tol = 10.0; p->tol_ppm = 1; p->score_method = 1; p->itol = 0.6; p->min_score = 12.0; p->min_peaks = 10;
+    p->n_isotope = 1; p->isotope[0] = 0; p->max_var_mods = 3; p->max_mods_per_aa = 1; p->n_random = 1000;
+    p->enzyme = 1; p->max_missed = 2; p->min_len = 7; p->max_len = 45; p->min_mass = 500.0; p->max_mass = 10000.0;
+    p->shuffle_seed = 12457; p->mod_seed = 2022;
+    p->n_fixed = 1; p->fixed[0].id = 1; p->fixed[0].position = PQ_MOD_ANYWHERE; strcpy(p->fixed[0].residues, "C"); p->fixed[0].delta = 57.02146372057;
+    p->n_var = 1; p->var[0].id = 2; p->var[0].position = PQ_MOD_ANYWHERE; strcpy(p->var[0].residues, "M"); p->var[0].delta = 15.99491461956;
+    p->var[0].neutral_loss = 63.99828574784;
+}
+
+int32_t pq_create(const pq_params* params, pq_ctx** out) {
+    pq_ctx* ctx = nullptr;
+    if (!params || !out) return fail(nullptr, PQ_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) return fail(nullptr, PQ_ERR_NO_DEVICE, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (params->device < 0 || params->device >= ndev) return fail(nullptr, PQ_ERR_BAD_ARG, "device ordinal out of range");
+    if (params->score_method != 1 && params->score_method != 2) return fail(nullptr, PQ_ERR_BAD_ARG, "score_method must be 1 (hyperscore) or 2 (MVH)");
+    if (params->n_isotope < 1 || params->n_isotope > PQ_MAX_ISOTOPE) return fail(nullptr, PQ_ERR_BAD_ARG, "n_isotope out of range");
+    { bool has0 = false; for (int i = 0; i < params->n_isotope; ++i) has0 |= params->isotope[i] == 0; if (!has0) return fail(nullptr, PQ_ERR_BAD_ARG, "isotope error list must contain 0 (CParameter.java:436-446)"); }
+    if (!(params->itol > 0) || !(params->tol >= 0)) return fail(nullptr, PQ_ERR_BAD_ARG, "tolerances must be positive");
+    if (params->enzyme != 1) return fail(nullptr, PQ_ERR_UNSUPPORTED, "only enzyme 1 (trypsin) is implemented");
+    if (params->max_len > kMaxLen) return fail(nullptr, PQ_ERR_UNSUPPORTED, "max_len > 60");
+    ctx = new pq_ctx();
+    ctx->P = *params;
+    memset(&ctx->cnt, 0, sizeof ctx->cnt);
+    std::string err;
+    if (!ctx->codes.init(*params, err)) { delete ctx; return fail(nullptr, PQ_ERR_UNSUPPORTED, err); }
+    if (cudaSetDevice(params->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx; return fail(nullptr, PQ_ERR_CUDA, "cannot initialise device");
+    }
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    int bins = (int)jround((double)(int)(2000.0 - 200.0) / (params->itol * 2.0));
+    factorial_tables(ctx->log10_fact, ctx->ln_fact, std::max(bins + 512, 4096));
+    bool ok = ctx->d_mods.reserve(sizeof(ModTable)) == cudaSuccess && ctx->d_l10.reserve(65 * 8) == cudaSuccess &&
+              ctx->d_lnf.reserve(ctx->ln_fact.size() * 8) == cudaSuccess && ctx->d_shufmods.reserve(sizeof(ShuffleMods)) == cudaSuccess;
+    if (ok) {
+        cudaMemcpy(ctx->d_mods.p, &ctx->codes.table, sizeof(ModTable), cudaMemcpyHostToDevice);
+        cudaMemcpy(ctx->d_l10.p, ctx->log10_fact, 65 * 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(ctx->d_lnf.p, ctx->ln_fact.data(), ctx->ln_fact.size() * 8, cudaMemcpyHostToDevice);
+        ok = cudaMemcpy(ctx->d_shufmods.p, &ctx->codes.shuffle, sizeof(ShuffleMods), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (!ok) { delete ctx; return fail(nullptr, PQ_ERR_CUDA, "device allocation failed"); }
+    *out = ctx;
+    return PQ_OK;
+}
+
+int32_t pq_destroy(pq_ctx* ctx) {
+    if (!ctx) return PQ_OK;
+    cudaSetDevice(ctx->P.device);
+    cudaStreamSynchronize(ctx->st);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    cudaStream_t st = ctx->st;
+    delete ctx;
+    if (st) cudaStreamDestroy(st);
+    return PQ_OK;
+}
+
+int32_t pq_get_counters(pq_ctx* ctx, pq_counters* out) { if (!ctx || !out) return PQ_ERR_BAD_ARG; *out = ctx->cnt; return PQ_OK; }
+int32_t pq_reset_counters(pq_ctx* ctx) {
+    if (!ctx) return PQ_ERR_BAD_ARG;
+    pq_counters k = ctx->cnt; memset(&ctx->cnt, 0, sizeof ctx->cnt);
+    ctx->cnt.spectra_loaded = k.spectra_loaded; ctx->cnt.spectra_usable = k.spectra_usable; ctx->cnt.target_forms = k.target_forms;
+    ctx->cnt.reference_sequences = k.reference_sequences; ctx->cnt.reference_forms = k.reference_forms;
+    return PQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int32_t* charge, const uint64_t* off,
+                        const double* mz, const double* inten) {
+    if (!ctx || n < 0 || (n > 0 && (!prec_mz || !charge || !off || !mz || !inten))) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
+    if (n > 0x7fffffffLL / PQ_MAX_ISOTOPE) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many spectra for one context");
+    cudaSetDevice(ctx->P.device);
+    uint64_t total = n ? off[n] : 0;
+    uint32_t maxp = 0; uint64_t usable = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (off[i + 1] < off[i]) return fail(ctx, PQ_ERR_BAD_ARG, "peak offsets must be non-decreasing");
+        uint64_t c = off[i + 1] - off[i];
+        if (c > 4096) return fail(ctx, PQ_ERR_UNSUPPORTED, "more than 4096 peaks in one spectrum");
+        if (charge[i] < 1) return fail(ctx, PQ_ERR_BAD_ARG, "charge must be >= 1");
+        if (c > maxp) maxp = (uint32_t)c;
+        if ((int64_t)c > (int64_t)ctx->P.min_peaks) ++usable;
+    }
+    ctx->nS = n; ctx->max_peaks = maxp; ctx->step_done = 0; ctx->psms.clear(); ctx->n_prepared = 0;
+    ctx->cnt.spectra_loaded = (uint64_t)n; ctx->cnt.spectra_usable = usable;
+    if (n == 0) return PQ_OK;
+    DevBuf in_prec, in_charge, in_off, in_mz, in_in, in_mass, key, key2, idx;
+    CU(in_prec.reserve(n * 8)); CU(in_charge.reserve(n * 4)); CU(in_off.reserve((n + 1) * 8));
+    CU(in_mz.reserve(std::max<uint64_t>(total, 1) * 8)); CU(in_in.reserve(std::max<uint64_t>(total, 1) * 8));
+    CU(in_mass.reserve(n * 8)); CU(key.reserve(n * 8)); CU(key2.reserve(n * 8)); CU(idx.reserve(n * 4));
+    CU(ctx->s_prec.reserve(n * 8)); CU(ctx->s_charge.reserve(n * 4)); CU(ctx->s_mass.reserve(n * 8)); CU(ctx->s_off.reserve((n + 1) * 8));
+    CU(ctx->s_mz.reserve(std::max<uint64_t>(total, 1) * 8)); CU(ctx->s_in.reserve(std::max<uint64_t>(total, 1) * 8)); CU(ctx->s_caller.reserve(n * 4));
+    CU(ctx->scratch.reserve((n + 1) * 8));
+    cudaStream_t st = ctx->st;
+    CU(cudaMemcpyAsync(in_prec.p, prec_mz, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(in_charge.p, charge, n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(in_off.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(in_mz.p, mz, total * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(in_in.p, inten, total * 8, cudaMemcpyHostToDevice, st));
+    ctx->cnt.h2d_bytes += (uint64_t)n * 28 + 8 + total * 16;
+    {
+        Timer t(ctx, &ctx->cnt.ms_prepare);
+        int k = 0;
+        k += launch_precursor_mass(n, in_prec.as<double>(), in_charge.as<int32_t>(), in_mass.as<double>(), key.as<uint64_t>(), idx.as<int32_t>(), st);
+        size_t tmp = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, key.as<uint64_t>(), key2.as<uint64_t>(), idx.as<int32_t>(), ctx->s_caller.as<int32_t>(), (int)n, 0, 64, st);
+        CU(ctx->scan_tmp.reserve(tmp + 64));
+        CU(cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, tmp, key.as<uint64_t>(), key2.as<uint64_t>(), idx.as<int32_t>(), ctx->s_caller.as<int32_t>(), (int)n, 0, 64, st));
+        uint64_t* counts = ctx->scratch.as<uint64_t>();
+        k += launch_gather_meta(n, ctx->s_caller.as<int32_t>(), in_prec.as<double>(), in_charge.as<int32_t>(), in_mass.as<double>(), in_off.as<uint64_t>(),
+                                ctx->s_prec.as<double>(), ctx->s_charge.as<int32_t>(), ctx->s_mass.as<double>(), counts, st);
+        CU(cudaMemsetAsync(counts + n, 0, 8, st));
+        int32_t rc = scan_exclusive(ctx, counts, ctx->s_off.as<uint64_t>(), (int)n + 1);
+        if (rc) return rc;
+        k += launch_gather_peaks(n, ctx->s_caller.as<int32_t>(), in_off.as<uint64_t>(), ctx->s_off.as<uint64_t>(), in_mz.as<double>(), in_in.as<double>(),
+                                 ctx->s_mz.as<double>(), ctx->s_in.as<double>(), st);
+        ctx->cnt.other_kernel_launches += (uint64_t)k + 4;
+    }
+    CU(cudaGetLastError());
+    ctx->h_caller.resize(n); ctx->h_mass.resize(n); ctx->h_charge.resize(n); ctx->h_npeaks.resize(n);
+    CU(cudaMemcpyAsync(ctx->h_caller.data(), ctx->s_caller.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_mass.data(), ctx->s_mass.p, n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_charge.data(), ctx->s_charge.p, n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->cnt.d2h_bytes += (uint64_t)n * 16;
+    for (int64_t i = 0; i < n; ++i) { int32_t c = ctx->h_caller[i]; ctx->h_npeaks[i] = (uint32_t)(off[c + 1] - off[c]); }
+    return PQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+static void sort_table(PeptideTable& T) {
+    // mass ascending; equal masses keep (sequence, form) generation order (stable)
+    std::stable_sort(T.forms.begin(), T.forms.end(), [](const FormRec& a, const FormRec& b) { return a.mass < b.mass; });
+}
+
+int32_t pq_set_targets(pq_ctx* ctx, int32_t n_seq, const uint32_t* off, const char* res) {
+    if (!ctx || n_seq < 0 || (n_seq > 0 && (!off || !res))) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
+    cudaSetDevice(ctx->P.device);
+    PeptideTable& T = ctx->targets;
+    T.seqs.clear(); T.forms.clear();
+    for (int32_t i = 0; i < n_seq; ++i) {
+        std::string s(res + off[i], res + off[i + 1]);
+        if (s.size() < 2 || s.size() > (size_t)kMaxLen) return fail(ctx, PQ_ERR_UNSUPPORTED, "target length must be 2..60: " + s);
+        for (char c : s) if (c < 'A' || c > 'Z' || ctx->codes.residue_mass[c - 'A'] == 0.0) return fail(ctx, PQ_ERR_BAD_ARG, "target has a non-standard residue: " + s);
+        T.seqs.push_back(s);
+        ctx->codes.expand_forms(s, i, T.forms);
+    }
+    // caller-visible form order = generation order (sequence order, then calcPeptideIsoforms order); the device table is
+    // the same forms sorted by mass; table_of_form / form_of_row translate.
+    ctx->cnt.target_forms = T.forms.size();
+    ctx->order.form_of_row.clear(); ctx->order.row_of_form.clear();
+    ctx->have_targets = true; ctx->step_done = 0; ctx->psms.clear();
+    return PQ_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// target forms keep two orders: public (generation) and device (mass-sorted)
+int32_t finalize_targets(pq_ctx* ctx) {
+    PeptideTable& T = ctx->targets;
+    TargetOrder& O = ctx->order;
+    if (!O.form_of_row.empty() && O.form_of_row.size() == T.forms.size() && T.rows.p) return PQ_OK;
+    const size_t n = T.forms.size();
+    std::vector<uint32_t> ord(n);
+    std::iota(ord.begin(), ord.end(), 0u);
+    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return T.forms[a].mass < T.forms[b].mass; });
+    O.form_of_row = ord; O.row_of_form.assign(n, 0);
+    for (size_t r = 0; r < n; ++r) O.row_of_form[ord[r]] = (uint32_t)r;
+    PeptideTable S;     // temp sorted copy for upload
+    S.seqs = T.seqs; S.forms.resize(n);
+    for (size_t r = 0; r < n; ++r) S.forms[r] = T.forms[ord[r]];
+    std::swap(S.rows, T.rows); std::swap(S.mass, T.mass);
+    int32_t rc = upload_table(ctx, S);
+    std::swap(S.rows, T.rows); std::swap(S.mass, T.mass);
+    T.h_mass = S.h_mass;    // sorted masses (row order)
+    return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int32_t pq_get_target_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int64_t* n_forms) {
+    if (!ctx || !n_forms) return PQ_ERR_BAD_ARG;
+    PeptideTable& T = ctx->targets;
+    *n_forms = (int64_t)T.forms.size();
+    if (!out) return PQ_OK;
+    if (capacity < *n_forms) return fail(ctx, PQ_ERR_CAPACITY, "form buffer too small");
+    for (size_t i = 0; i < T.forms.size(); ++i) ctx->codes.to_public(T.seqs[(size_t)T.forms[i].seq], T.forms[i], out + i);
+    return PQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
+    if (!ctx) return PQ_ERR_BAD_ARG;
+    if (!ctx->have_targets) return fail(ctx, PQ_ERR_STATE, "pq_set_targets first");
+    cudaSetDevice(ctx->P.device);
+    int32_t rc = finalize_targets(ctx);
+    if (rc) return rc;
+    ctx->psms.clear(); ctx->step_done = 0; ctx->n_prepared = 0;
+    if (n_psms) *n_psms = 0;
+    const int64_t n = ctx->nS;
+    PeptideTable& T = ctx->targets;
+    if (n == 0 || T.n() == 0) { ctx->step_done = 2; return PQ_OK; }
+    cudaStream_t st = ctx->st;
+    const uint32_t job_cap = (uint32_t)(n * ctx->P.n_isotope);
+    CU(ctx->jobs.reserve((size_t)job_cap * sizeof(Job)));
+    CU(ctx->njobs.reserve(64));
+    CU(ctx->need.reserve((size_t)(n + 1) * 4));
+    CU(ctx->prep_id.reserve((size_t)(n + 1) * 4));
+    CU(ctx->prep_list.reserve((size_t)(n + 1) * 4));
+    CU(cudaMemsetAsync(ctx->njobs.p, 0, 8, st));
+    CU(cudaMemsetAsync(ctx->need.p, 0, (size_t)(n + 1) * 4, st));
+    WindowConfig W; W.tol = ctx->P.tol; W.tol_ppm = ctx->P.tol_ppm; W.n_isotope = ctx->P.n_isotope; W.min_peaks = ctx->P.min_peaks;
+    for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) W.isotope[i] = ctx->P.isotope[i];
+    SpectraView sp = ctx->view();
+    uint32_t h_njobs = 0; int32_t h_nprep = 0;
+    {
+        Timer t(ctx, &ctx->cnt.ms_window);
+        int k = launch_enumerate_targets(sp, T.mass.as<double>(), (uint32_t)T.n(), W, ctx->jobs.as<Job>(), ctx->njobs.as<uint32_t>(), ctx->need.as<int32_t>(), st);
+        rc = scan_exclusive(ctx, ctx->need.as<int32_t>(), ctx->prep_id.as<int32_t>(), (int)n + 1);
+        if (rc) return rc;
+        ctx->cnt.other_kernel_launches += (uint64_t)k + 1;
+    }
+    CU(cudaMemcpyAsync(&h_njobs, ctx->njobs.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&h_nprep, ctx->prep_id.as<int32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->cnt.d2h_bytes += 8;
+    if (h_njobs == 0) { ctx->step_done = 2; return PQ_OK; }
+    // list of spectra to prepare (ascending sorted index) + blob offsets
+    {
+        Timer t(ctx, &ctx->cnt.ms_prepare);
+        size_t tmp = 0;
+        cub::CountingInputIterator<int32_t> iota(0);
+        cub::DeviceSelect::Flagged(nullptr, tmp, iota, ctx->need.as<int32_t>(), ctx->prep_list.as<int32_t>(), ctx->njobs.as<uint32_t>() + 1, (int)n, st);
+        CU(ctx->scan_tmp.reserve(tmp + 64));
+        CU(cub::DeviceSelect::Flagged(ctx->scan_tmp.p, tmp, iota, ctx->need.as<int32_t>(), ctx->prep_list.as<int32_t>(), ctx->njobs.as<uint32_t>() + 1, (int)n, st));
+        CU(ctx->scratch.reserve((size_t)(h_nprep + 2) * 8));
+        CU(ctx->blob_off.reserve((size_t)(h_nprep + 2) * 8));
+        launch_blob_sizes(sp, ctx->prep_list.as<int32_t>(), h_nprep, ctx->scratch.as<uint64_t>(), st);
+        rc = scan_exclusive(ctx, ctx->scratch.as<uint64_t>(), ctx->blob_off.as<uint64_t>(), h_nprep + 1);
+        if (rc) return rc;
+        uint64_t total_blob = 0;
+        CU(cudaMemcpyAsync(&total_blob, ctx->blob_off.as<uint64_t>() + h_nprep, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(ctx->blobs.reserve(total_blob + 256));
+        PrepConfig pc; pc.itol = ctx->P.itol; pc.method = ctx->P.score_method;
+        pc.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (ctx->P.itol * 2.0));
+        int k = launch_prepare(sp, ctx->prep_list.as<int32_t>(), h_nprep, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(), ctx->max_peaks, st);
+        k += launch_fix_job_blobs(ctx->jobs.as<Job>(), h_njobs, ctx->prep_id.as<int32_t>(), st);
+        ctx->cnt.other_kernel_launches += (uint64_t)k + 3;
+        ctx->n_prepared = (uint32_t)h_nprep; ctx->cnt.spectra_prepared = (uint64_t)h_nprep;
+        ctx->max_blob = blob_bytes((ctx->max_peaks + 3u) & ~3u);
+    }
+    CU(cudaGetLastError());
+    // hits capacity: every candidate could pass
+    std::vector<Job> hj(h_njobs);
+    CU(cudaMemcpyAsync(hj.data(), ctx->jobs.p, (size_t)h_njobs * sizeof(Job), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->cnt.d2h_bytes += (uint64_t)h_njobs * sizeof(Job);
+    uint64_t cand = 0; for (auto& j : hj) cand += j.cand_count;
+    if (cand > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-2 candidates for one launch");
+    rc = run_score(ctx, kJobTargets, h_njobs, &T, T.rows.as<uint8_t>(), T.mass.as<double>(), (uint32_t)cand, 1);
+    if (rc) return rc;
+    std::vector<JobResult> hr(h_njobs);
+    uint32_t nh = 0;
+    CU(cudaMemcpyAsync(hr.data(), ctx->results.p, (size_t)h_njobs * sizeof(JobResult), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&nh, ctx->hit_count.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::vector<Hit> hh(nh);
+    if (nh) { CU(cudaMemcpyAsync(hh.data(), ctx->hits.p, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
+    ctx->cnt.d2h_bytes += (uint64_t)h_njobs * sizeof(JobResult) + (uint64_t)nh * sizeof(Hit) + 4;
+    if (getenv("PQ_DEBUG")) {
+        uint64_t nin = 0; for (auto& r : hr) nin += r.n_in_window;
+        fprintf(stderr, "[pq] step2: jobs %u prepared %d candidates %llu in-window %llu hits %u max_blob %u\n", h_njobs, h_nprep,
+                (unsigned long long)cand, (unsigned long long)nin, nh, ctx->max_blob);
+        for (size_t j = 0; j < hj.size() && j < 4; ++j)
+            fprintf(stderr, "[pq]   job %zu: spec %d blob %u cand %u+%u mass %.6f -> in %u best %.4f\n", j, hj[j].spectrum, hj[j].blob, hj[j].cand_begin,
+                    hj[j].cand_count, hj[j].mass, hr[j].n_in_window, hr[j].best_score);
+    }
+    for (size_t j = 0; j < hj.size(); ++j) {
+        ctx->cnt.pairs_step2 += hr[j].n_in_window;
+        ctx->cnt.score_algorithmic_bytes += (uint64_t)hr[j].n_in_window * (16ull * ctx->h_npeaks[(size_t)hj[j].spectrum] + 96ull);
+    }
+    const TargetOrder& O = ctx->order;
+    ctx->psms.reserve(nh);
+    for (const Hit& h : hh) {
+        HostPsm p;
+        p.spectrum_sorted = h.spectrum; p.spectrum = ctx->h_caller[(size_t)h.spectrum]; p.form = (int32_t)O.form_of_row[h.cand]; p.blob = h.blob;
+        p.score = h.score; p.exp_mass = h.mass; p.pep_mass = T.h_mass[h.cand]; p.iso = h.iso; p.ca = h.count_a; p.cb = h.count_b;
+        p.charge = ctx->h_charge[(size_t)h.spectrum];
+        ctx->psms.push_back(p);
+    }
+    std::sort(ctx->psms.begin(), ctx->psms.end(), [](const HostPsm& a, const HostPsm& b) { return a.spectrum != b.spectrum ? a.spectrum < b.spectrum : a.form < b.form; });
+    ctx->cnt.psms = ctx->psms.size();
+    ctx->step_done = 2;
+    if (n_psms) *n_psms = (int64_t)ctx->psms.size();
+    return PQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off, const char* res) {
+    if (!ctx || n_proteins < 0 || (n_proteins > 0 && (!off || !res))) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
+    if (ctx->step_done < 2) return fail(ctx, PQ_ERR_STATE, "pq_step2_match_targets first (the reference mass window comes from the matched spectra)");
+    cudaSetDevice(ctx->P.device);
+    PeptideTable& R = ctx->reference;
+    R.seqs.clear(); R.forms.clear();
+    int threads = (int)std::thread::hardware_concurrency(); if (threads < 1) threads = 1; if (threads > 32) threads = 32;
+    digest_proteins(ctx->P, ctx->codes.residue_mass, n_proteins, off, res, R.seqs, threads);
+    {   // DatabaseInput.protein_digest(db, target_peptides) removes the target sequences (:480-488)
+        std::vector<std::string> t(ctx->targets.seqs); std::sort(t.begin(), t.end());
+        R.seqs.erase(std::remove_if(R.seqs.begin(), R.seqs.end(), [&](const std::string& s) { return std::binary_search(t.begin(), t.end(), s); }), R.seqs.end());
+    }
+    // GeneratePeptideformWorker.set_mass_range over the matched spectra (GeneratePeptideformWorker.java:40-52)
+    double mn = 1.7976931348623157e308, mx = 0.0;
+    for (const HostPsm& p : ctx->psms) { double m = ctx->h_mass[(size_t)p.spectrum_sorted]; mn = std::min(mn, m); mx = std::max(mx, m); }
+    const double lo = mn - 250.0 - 5.0, hi = mx + 250.0 + 5.0;
+    {
+        std::vector<std::vector<FormRec>> part((size_t)threads);
+        std::vector<std::thread> th;
+        const size_t ns = R.seqs.size();
+        for (int t = 0; t < threads; ++t) th.emplace_back([&, t]() {
+            std::vector<FormRec> tmp;
+            size_t a = ns * (size_t)t / (size_t)threads, b = ns * (size_t)(t + 1) / (size_t)threads;
+            for (size_t i = a; i < b; ++i) {
+                tmp.clear();
+                ctx->codes.expand_forms(R.seqs[i], (int32_t)i, tmp);
+                for (const FormRec& f : tmp) if (f.mass > lo && f.mass < hi) part[(size_t)t].push_back(f);
+            }
+        });
+        for (auto& t : th) t.join();
+        size_t tot = 0; for (auto& p : part) tot += p.size();
+        R.forms.reserve(tot);
+        for (auto& p : part) R.forms.insert(R.forms.end(), p.begin(), p.end());
+    }
+    sort_table(R);
+    int32_t rc = upload_table(ctx, R);
+    if (rc) return rc;
+    ctx->cnt.reference_sequences = R.seqs.size(); ctx->cnt.reference_forms = R.forms.size();
+    ctx->have_reference = true;
+    return PQ_OK;
+}
+
+int32_t pq_get_reference_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int64_t* n_forms) {
+    if (!ctx || !n_forms) return PQ_ERR_BAD_ARG;
+    PeptideTable& T = ctx->reference;
+    *n_forms = (int64_t)T.forms.size();
+    if (!out) return PQ_OK;
+    if (capacity < *n_forms) return fail(ctx, PQ_ERR_CAPACITY, "form buffer too small");
+    for (size_t i = 0; i < T.forms.size(); ++i) ctx->codes.to_public(T.seqs[(size_t)T.forms[i].seq], T.forms[i], out + i);
+    return PQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t pq_step3_competitors(pq_ctx* ctx) {
+    if (!ctx) return PQ_ERR_BAD_ARG;
+    if (ctx->step_done < 2 || !ctx->have_reference) return fail(ctx, PQ_ERR_STATE, "pq_step2_match_targets and pq_build_reference first");
+    cudaSetDevice(ctx->P.device);
+    ctx->comp3.clear();
+    PeptideTable& R = ctx->reference;
+    cudaStream_t st = ctx->st;
+    // DatabaseInput.get_spectra2score(..., "max") (:637-669)
+    struct Spec { int32_t sorted; uint32_t blob; double best; int32_t charge; };
+    std::vector<Spec> specs;
+    {
+        std::unordered_map<int32_t, size_t> at;
+        for (const HostPsm& p : ctx->psms) {
+            auto it = at.find(p.spectrum_sorted);
+            if (it == at.end()) { at[p.spectrum_sorted] = specs.size(); specs.push_back({p.spectrum_sorted, p.blob, p.score, p.charge}); }
+            else if (specs[it->second].best < p.score) specs[it->second].best = p.score;
+        }
+        std::sort(specs.begin(), specs.end(), [](const Spec& a, const Spec& b) { return a.sorted < b.sorted; });
+    }
+    std::vector<Job> hj;
+    const bool plain = ctx->P.n_isotope == 1 && ctx->P.isotope[0] == 0;
+    uint64_t cand = 0;
+    for (size_t si = 0; si < specs.size(); ++si) {
+        for (int ii = 0; ii < ctx->P.n_isotope; ++ii) {
+            double m = ctx->h_mass[(size_t)specs[si].sorted];
+            if (!plain) m = m - (double)ctx->P.isotope[ii] * kIsotope;
+            double w = ctx->P.tol_ppm ? ctx->P.tol * 1e-6 * (std::fabs(m) + 1.0) * 1.01 + 1e-6 : ctx->P.tol * 1.01 + 1e-6;
+            if (w > 0.2) w = 0.2;
+            size_t lo = std::lower_bound(R.h_mass.begin(), R.h_mass.end(), m - w) - R.h_mass.begin();
+            size_t hi = std::lower_bound(R.h_mass.begin(), R.h_mass.end(), m + w) - R.h_mass.begin();
+            if (hi <= lo) continue;
+            Job J; J.blob = specs[si].blob; J.cand_begin = (uint32_t)lo; J.cand_count = (uint32_t)(hi - lo); J.out = (uint32_t)si;
+            J.mass = m; J.ref_score = specs[si].best; J.charge = specs[si].charge; J.iso = plain ? 0 : ctx->P.isotope[ii];
+            J.spectrum = specs[si].sorted; J.aux = 0;
+            hj.push_back(J); cand += J.cand_count;
+        }
+    }
+    std::vector<JobResult> hr(hj.size());
+    std::vector<Hit> hh;
+    if (!hj.empty()) {
+        if (cand > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-3 candidates for one launch");
+        CU(ctx->jobs.reserve(hj.size() * sizeof(Job)));
+        CU(cudaMemcpyAsync(ctx->jobs.p, hj.data(), hj.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
+        ctx->cnt.h2d_bytes += hj.size() * sizeof(Job);
+        int32_t rc = run_score(ctx, kJobCompetitors, (uint32_t)hj.size(), &R, R.rows.as<uint8_t>(), R.mass.as<double>(), (uint32_t)cand, 1);
+        if (rc) return rc;
+        uint32_t nh = 0;
+        CU(cudaMemcpyAsync(hr.data(), ctx->results.p, hj.size() * sizeof(JobResult), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&nh, ctx->hit_count.p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        hh.resize(nh);
+        if (nh) { CU(cudaMemcpyAsync(hh.data(), ctx->hits.p, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
+        ctx->cnt.d2h_bytes += hj.size() * sizeof(JobResult) + (uint64_t)nh * sizeof(Hit) + 4;
+    }
+    struct Agg { int32_t matched = 0, better = 0; double best = -1.0; uint32_t best_row = 0xffffffffu; };
+    std::vector<Agg> agg(specs.size());
+    for (size_t j = 0; j < hj.size(); ++j) {
+        Agg& a = agg[hj[j].out];
+        a.matched += (int32_t)hr[j].n_in_window; a.better += (int32_t)hr[j].n_better;
+        if (hr[j].best_score > a.best) { a.best = hr[j].best_score; a.best_row = hr[j].best_cand; }     // isotope order, strict '<' (:63-65)
+        ctx->cnt.pairs_step3 += hr[j].n_in_window;
+        ctx->cnt.score_algorithmic_bytes += (uint64_t)hr[j].n_in_window * (16ull * ctx->h_npeaks[(size_t)hj[j].spectrum] + 96ull);
+    }
+    // detail rows: better-or-equal competitors with score >= 20, plus the best competitor when its score > 0 (:71-76, :93-98)
+    for (const Hit& h : hh) ctx->comp3.push_back({ctx->h_caller[(size_t)h.spectrum], (int32_t)h.cand, -1, -1, h.score, R.h_mass[h.cand]});
+    for (size_t si = 0; si < specs.size(); ++si) {
+        const Agg& a = agg[si];
+        if (a.best > 0 && a.best_row != 0xffffffffu) {
+            int32_t sp = ctx->h_caller[(size_t)specs[si].sorted];
+            bool dup = false;
+            for (const Hit& h : hh) if (h.spectrum == specs[si].sorted && h.cand == a.best_row) { dup = true; break; }
+            if (!dup) ctx->comp3.push_back({sp, (int32_t)a.best_row, -1, -1, a.best, R.h_mass[a.best_row]});
+        }
+    }
+    std::sort(ctx->comp3.begin(), ctx->comp3.end(), [](const pq_competitor& a, const pq_competitor& b) { return a.spectrum != b.spectrum ? a.spectrum < b.spectrum : a.ref_form < b.ref_form; });
+    std::unordered_map<int32_t, size_t> at;
+    for (size_t si = 0; si < specs.size(); ++si) at[specs[si].sorted] = si;
+    for (HostPsm& p : ctx->psms) {
+        const Agg& a = agg[at[p.spectrum_sorted]];
+        p.total_db = a.matched; p.n_db = a.better;
+        if (a.better >= 1) p.valid = 0;                                    // DatabaseInput.java:745-750
+    }
+    ctx->step_done = 3;
+    return PQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t pq_step4_shuffles(pq_ctx* ctx) {
+    if (!ctx) return PQ_ERR_BAD_ARG;
+    if (ctx->step_done < 2) return fail(ctx, PQ_ERR_STATE, "pq_step2_match_targets first");
+    cudaSetDevice(ctx->P.device);
+    cudaStream_t st = ctx->st;
+    PeptideTable& T = ctx->targets;
+    // StatisticScoreCalc.run (:22-41): sequences with at least one still-valid PSM get shuffles
+    std::vector<int32_t> slot_of_seq(T.seqs.size(), -1), slot_of_form(T.forms.size(), -1);
+    std::vector<ShuffleSeq> seqs; std::vector<ShuffleForm> forms;
+    uint32_t raw_rows = 0, out_rows = 0, max_num = 1;
+    for (const HostPsm& p : ctx->psms) {
+        if (!p.valid) continue;
+        int32_t sq = T.forms[(size_t)p.form].seq;
+        if (slot_of_seq[(size_t)sq] < 0) {
+            ShuffleSeq S; shuffle_plan(T.seqs[(size_t)sq], ctx->P.n_random, S);
+            S.out_base = raw_rows; raw_rows += S.num; if (S.num > max_num) max_num = S.num;
+            slot_of_seq[(size_t)sq] = (int32_t)seqs.size(); seqs.push_back(S);
+        }
+        if (slot_of_form[(size_t)p.form] < 0) {
+            const FormRec& f = T.forms[(size_t)p.form];
+            ShuffleForm F; memset(&F, 0, sizeof F);
+            F.seq_slot = (uint32_t)slot_of_seq[(size_t)sq]; F.row_base = out_rows; out_rows += seqs[F.seq_slot].num;
+            F.n_mods = f.n; for (int i = 0; i < f.n; ++i) F.mod[i] = f.mod[i];
+            slot_of_form[(size_t)p.form] = (int32_t)forms.size(); forms.push_back(F);
+        }
+    }
+    ctx->h_sh_seqs = seqs; ctx->sh_slot_of_seq = slot_of_seq;
+    ctx->h_kept.assign(seqs.size(), 0);
+    if (seqs.empty()) { ctx->step_done = 4; return PQ_OK; }
+    CU(ctx->sh_seqs.reserve(seqs.size() * sizeof(ShuffleSeq))); CU(ctx->sh_forms.reserve(forms.size() * sizeof(ShuffleForm)));
+    CU(ctx->sh_raw.reserve((size_t)std::max(raw_rows, 1u) * kRowBytes)); CU(ctx->sh_kidx.reserve((size_t)std::max(raw_rows, 1u) * 4));
+    CU(ctx->sh_kcnt.reserve(seqs.size() * 4)); CU(ctx->sh_rows.reserve((size_t)std::max(out_rows, 1u) * kRowBytes));
+    CU(cudaMemcpyAsync(ctx->sh_seqs.p, seqs.data(), seqs.size() * sizeof(ShuffleSeq), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->sh_forms.p, forms.data(), forms.size() * sizeof(ShuffleForm), cudaMemcpyHostToDevice, st));
+    ctx->cnt.h2d_bytes += seqs.size() * sizeof(ShuffleSeq) + forms.size() * sizeof(ShuffleForm);
+    {
+        Timer t(ctx, &ctx->cnt.ms_shuffle);
+        int k = launch_shuffles(ctx->sh_seqs.as<ShuffleSeq>(), (uint32_t)seqs.size(), ctx->sh_forms.as<ShuffleForm>(), (uint32_t)forms.size(),
+                                ctx->d_shufmods.as<ShuffleMods>(), ctx->sh_raw.as<uint8_t>(), ctx->sh_kidx.as<uint32_t>(), ctx->sh_kcnt.as<uint32_t>(),
+                                ctx->sh_rows.as<uint8_t>(), max_num, ctx->P.shuffle_seed, st);
+        ctx->cnt.other_kernel_launches += (uint64_t)k;
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->h_kept.data(), ctx->sh_kcnt.p, seqs.size() * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->cnt.d2h_bytes += seqs.size() * 4;
+    // one job per valid PSM (StatisticScoreWorker), ordered by form so consecutive CTAs share shuffle rows in L2
+    std::vector<size_t> order;
+    for (size_t i = 0; i < ctx->psms.size(); ++i) if (ctx->psms[i].valid) order.push_back(i);
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ctx->psms[a].form < ctx->psms[b].form; });
+    std::vector<Job> hj(order.size());
+    for (size_t k = 0; k < order.size(); ++k) {
+        const HostPsm& p = ctx->psms[order[k]];
+        const ShuffleForm& F = forms[(size_t)slot_of_form[(size_t)p.form]];
+        Job J; J.blob = p.blob; J.cand_begin = F.row_base; J.cand_count = ctx->h_kept[F.seq_slot]; J.out = (uint32_t)k;
+        J.mass = p.exp_mass; J.ref_score = p.score; J.charge = p.charge; J.iso = p.iso; J.spectrum = p.spectrum_sorted; J.aux = p.form;
+        hj[k] = J;
+    }
+    std::vector<JobResult> hr(hj.size());
+    if (!hj.empty()) {
+        CU(ctx->jobs.reserve(hj.size() * sizeof(Job)));
+        CU(cudaMemcpyAsync(ctx->jobs.p, hj.data(), hj.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
+        ctx->cnt.h2d_bytes += hj.size() * sizeof(Job);
+        int32_t rc = run_score(ctx, kJobShuffles, (uint32_t)hj.size(), nullptr, ctx->sh_rows.as<uint8_t>(), nullptr, 1, 0);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(hr.data(), ctx->results.p, hj.size() * sizeof(JobResult), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        ctx->cnt.d2h_bytes += hj.size() * sizeof(JobResult);
+    }
+    for (size_t k = 0; k < order.size(); ++k) {
+        HostPsm& p = ctx->psms[order[k]];
+        int32_t N = (int32_t)hj[k].cand_count;
+        if (N < 1) continue;        // the reference exits with "There is no random peptide!" (StatisticScoreWorker.java:59-62)
+        p.n_random = (int32_t)hr[k].n_better; p.total_random = N;
+        p.p_value = 1.0 * (p.n_random + 1) / (N + 1);
+        ctx->cnt.pairs_step4 += hr[k].n_in_window;
+        ctx->cnt.score_algorithmic_bytes += (uint64_t)hr[k].n_in_window * (16ull * ctx->h_npeaks[(size_t)p.spectrum_sorted] + 96ull);
+    }
+    ctx->step_done = 4;
+    return PQ_OK;
+}
+
+int32_t pq_get_shuffles(pq_ctx* ctx, int32_t target_seq, char* out, int64_t capacity, int32_t* n_shuffles) {
+    if (!ctx || !n_shuffles) return PQ_ERR_BAD_ARG;
+    *n_shuffles = 0;
+    if (target_seq < 0 || (size_t)target_seq >= ctx->sh_slot_of_seq.size() || ctx->sh_slot_of_seq[(size_t)target_seq] < 0) return PQ_OK;
+    cudaSetDevice(ctx->P.device);
+    size_t slot = (size_t)ctx->sh_slot_of_seq[(size_t)target_seq];
+    const ShuffleSeq& S = ctx->h_sh_seqs[slot];
+    uint32_t nk = ctx->h_kept[slot];
+    *n_shuffles = (int32_t)nk;
+    if (!out) return PQ_OK;
+    int64_t L1 = (int64_t)S.len + 1;
+    if (capacity < (int64_t)nk * L1) return fail(ctx, PQ_ERR_CAPACITY, "shuffle buffer too small");
+    std::vector<uint8_t> raw((size_t)S.num * kRowBytes); std::vector<uint32_t> kidx(S.num);
+    CU(cudaMemcpy(raw.data(), ctx->sh_raw.as<uint8_t>() + (size_t)S.out_base * kRowBytes, raw.size(), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(kidx.data(), ctx->sh_kidx.as<uint32_t>() + S.out_base, (size_t)S.num * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t k = 0; k < nk; ++k) {
+        const uint8_t* r = raw.data() + (size_t)kidx[k] * kRowBytes;
+        for (uint32_t i = 0; i < S.len; ++i) out[k * L1 + i] = (char)('A' + r[kRowHeader + i]);
+        out[k * L1 + S.len] = 0;
+    }
+    return PQ_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+static std::string mod_string(const pq_ctx* ctx, const FormRec& f) {
+    if (f.n == 0) return "-";
+    std::string s; char buf[96];
+    for (int i = 0; i < f.n; ++i) {
+        snprintf(buf, sizeof buf, "%d@%d[%.4f]", ctx->codes.mods[(size_t)f.mod[i]].id, (int)f.site[i], ctx->codes.mods[(size_t)f.mod[i]].delta);
+        if (i) s += ";";
+        s += buf;
+    }
+    return s;
+}
+static double tol_ppm_of(const HostPsm& p) { return (1.0e6) * (p.pep_mass - p.exp_mass) / p.pep_mass; }
+
+int32_t pq_rank_and_validate(pq_ctx* ctx) {
+    if (!ctx) return PQ_ERR_BAD_ARG;
+    PeptideTable& T = ctx->targets;
+    // psms are sorted by (spectrum, form): rank inside each spectrum run (pg/RankPSM.java:107-149)
+    size_t i = 0;
+    while (i < ctx->psms.size()) {
+        size_t j = i;
+        while (j < ctx->psms.size() && ctx->psms[j].spectrum == ctx->psms[i].spectrum) ++j;
+        std::vector<size_t> v(j - i); std::iota(v.begin(), v.end(), i);
+        std::stable_sort(v.begin(), v.end(), [&](size_t ia, size_t ib) {
+            const HostPsm& a = ctx->psms[ia]; const HostPsm& b = ctx->psms[ib];
+            if (a.score != b.score) return a.score > b.score;
+            if (a.p_value != b.p_value) return a.p_value < b.p_value;
+            double ta = std::fabs(tol_ppm_of(a)), tb = std::fabs(tol_ppm_of(b));
+            if (ta != tb) return ta < tb;
+            const FormRec& fa = T.forms[(size_t)a.form]; const FormRec& fb = T.forms[(size_t)b.form];
+            return T.seqs[(size_t)fa.seq] + "|" + mod_string(ctx, fa) < T.seqs[(size_t)fb.seq] + "|" + mod_string(ctx, fb);
+        });
+        for (size_t r = 0; r < v.size(); ++r) ctx->psms[v[r]].rank = (int32_t)r + 1;
+        i = j;
+    }
+    for (HostPsm& p : ctx->psms) {     // CParameter.passed_psm_validation (pg/CParameter.java:913-940)
+        int len = (int)T.seqs[(size_t)T.forms[(size_t)p.form].seq].size();
+        bool pv = (len <= 8 && p.p_value <= 0.05) || (len > 8 && p.p_value <= 0.01);
+        bool ok = pv && p.n_db == 0 && p.rank == 1;
+        if (p.n_ptm >= 0) ok = ok && p.n_ptm == 0;
+        p.confident = ok ? 1 : 0;
+    }
+    return PQ_OK;
+}
+
+int32_t pq_get_psms(pq_ctx* ctx, pq_psm* out, int64_t capacity, int64_t* n_psms) {
+    if (!ctx || !n_psms) return PQ_ERR_BAD_ARG;
+    *n_psms = (int64_t)ctx->psms.size();
+    if (!out) return PQ_OK;
+    if (capacity < *n_psms) return fail(ctx, PQ_ERR_CAPACITY, "psm buffer too small");
+    for (size_t i = 0; i < ctx->psms.size(); ++i) {
+        const HostPsm& p = ctx->psms[i]; pq_psm& q = out[i]; memset(&q, 0, sizeof q);
+        q.spectrum = p.spectrum; q.form = p.form; q.score = p.score; q.exp_mass = p.exp_mass; q.pep_mass = p.pep_mass; q.tol_ppm = tol_ppm_of(p);
+        q.isotope_error = p.iso; q.count_b = p.ca; q.count_y = p.cb; q.n_db = p.n_db; q.total_db = p.total_db; q.n_random = p.n_random;
+        q.total_random = p.total_random; q.valid = p.valid; q.p_value = p.p_value; q.rank = p.rank; q.n_ptm = p.n_ptm; q.confident = p.confident;
+    }
+    return PQ_OK;
+}
+
+int32_t pq_get_competitors(pq_ctx* ctx, int32_t step, pq_competitor* out, int64_t capacity, int64_t* n_rows) {
+    if (!ctx || !n_rows) return PQ_ERR_BAD_ARG;
+    auto& v = step == 5 ? ctx->comp5 : ctx->comp3;
+    *n_rows = (int64_t)v.size();
+    if (!out) return PQ_OK;
+    if (capacity < *n_rows) return fail(ctx, PQ_ERR_CAPACITY, "competitor buffer too small");
+    if (!v.empty()) memcpy(out, v.data(), v.size() * sizeof(pq_competitor));
+    return PQ_OK;
+}
+
+int32_t pq_step5_ptm(pq_ctx* ctx, int32_t, const pq_ptm*) { return fail(ctx, PQ_ERR_UNSUPPORTED, "Step 5 (unrestricted modification search) is not implemented yet"); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_index, const pq_form* forms, double* score,
+                       int32_t* count_a, int32_t* count_b) {
+    if (!ctx || n_pairs < 0 || (n_pairs > 0 && (!spectrum_index || !forms || !score))) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
+    if (n_pairs == 0) return PQ_OK;
+    if (n_pairs > 0x7ffffff0LL) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many pairs for one call");
+    cudaSetDevice(ctx->P.device);
+    cudaStream_t st = ctx->st;
+    const int64_t n = ctx->nS;
+    // caller index -> sorted index
+    std::vector<int32_t> sorted_of(n, -1);
+    for (int64_t i = 0; i < n; ++i) sorted_of[(size_t)ctx->h_caller[i]] = (int32_t)i;
+    // group pairs by spectrum; rows in that order
+    std::vector<uint32_t> order((size_t)n_pairs);
+    std::iota(order.begin(), order.end(), 0u);
+    for (int64_t i = 0; i < n_pairs; ++i) if (spectrum_index[i] < 0 || spectrum_index[i] >= n) return fail(ctx, PQ_ERR_BAD_ARG, "spectrum index out of range");
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return sorted_of[(size_t)spectrum_index[a]] < sorted_of[(size_t)spectrum_index[b]]; });
+    std::vector<uint8_t> rows((size_t)n_pairs * kRowBytes);
+    std::vector<int32_t> pred;
+    std::string seq; FormRec fr;
+    for (int64_t k = 0; k < n_pairs; ++k) {
+        if (!ctx->codes.from_public(forms[order[(size_t)k]], seq, fr) || !ctx->codes.encode_row(seq, fr, rows.data() + (size_t)k * kRowBytes))
+            return fail(ctx, PQ_ERR_BAD_ARG, "pair " + std::to_string(order[(size_t)k]) + ": form cannot be encoded");
+    }
+    // spectra to prepare = distinct spectra of the list
+    std::vector<int32_t> list; std::vector<Job> hj;
+    for (int64_t k = 0; k < n_pairs;) {
+        int32_t s = sorted_of[(size_t)spectrum_index[order[(size_t)k]]];
+        int64_t e = k;
+        while (e < n_pairs && sorted_of[(size_t)spectrum_index[order[(size_t)e]]] == s) ++e;
+        Job J; J.blob = (uint32_t)list.size(); J.cand_begin = (uint32_t)k; J.cand_count = (uint32_t)(e - k); J.out = (uint32_t)k;
+        J.mass = ctx->h_mass[(size_t)s]; J.ref_score = 0; J.charge = ctx->h_charge[(size_t)s]; J.iso = 0; J.spectrum = s; J.aux = 0;
+        hj.push_back(J); list.push_back(s);
+        k = e;
+    }
+    DevBuf d_rows, d_score, d_a, d_b, d_list, d_pred;
+    CU(d_rows.reserve(rows.size())); CU(d_score.reserve((size_t)n_pairs * 8)); CU(d_a.reserve((size_t)n_pairs * 4)); CU(d_b.reserve((size_t)n_pairs * 4));
+    CU(d_list.reserve(list.size() * 4 + 8));
+    CU(cudaMemcpyAsync(d_rows.p, rows.data(), rows.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_list.p, list.data(), list.size() * 4, cudaMemcpyHostToDevice, st));
+    SpectraView sp = ctx->view();
+    // this call owns the prepared-spectrum pool: invalidate the step pipeline's blobs
+    ctx->step_done = std::min(ctx->step_done, 1); ctx->n_prepared = 0;
+    CU(ctx->scratch.reserve((list.size() + 2) * 8)); CU(ctx->blob_off.reserve((list.size() + 2) * 8));
+    launch_blob_sizes(sp, d_list.as<int32_t>(), (int32_t)list.size(), ctx->scratch.as<uint64_t>(), st);
+    int32_t rc = scan_exclusive(ctx, ctx->scratch.as<uint64_t>(), ctx->blob_off.as<uint64_t>(), (int)list.size() + 1);
+    if (rc) return rc;
+    uint64_t total_blob = 0;
+    CU(cudaMemcpyAsync(&total_blob, ctx->blob_off.as<uint64_t>() + list.size(), 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(ctx->blobs.reserve(total_blob + 256));
+    PrepConfig pc; pc.itol = ctx->P.itol; pc.method = ctx->P.score_method;
+    pc.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (ctx->P.itol * 2.0));
+    {
+        Timer t(ctx, &ctx->cnt.ms_prepare);
+        ctx->cnt.other_kernel_launches += (uint64_t)launch_prepare(sp, d_list.as<int32_t>(), (int32_t)list.size(), pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(), ctx->max_peaks, st) + 2;
+    }
+    ctx->max_blob = blob_bytes((ctx->max_peaks + 3u) & ~3u);
+    CU(ctx->jobs.reserve(hj.size() * sizeof(Job)));
+    CU(cudaMemcpyAsync(ctx->jobs.p, hj.data(), hj.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
+    CU(ctx->results.reserve(hj.size() * sizeof(JobResult))); CU(ctx->hits.reserve(64)); CU(ctx->hit_count.reserve(64));
+    CU(cudaMemsetAsync(ctx->hit_count.p, 0, 4, st));
+    ScoreLaunch L; memset(&L, 0, sizeof L);
+    L.kind = kJobPairs; L.jobs = ctx->jobs.as<Job>(); L.n_jobs = (uint32_t)hj.size();
+    L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>(); L.rows = d_rows.as<uint8_t>(); L.row_mass = nullptr;
+    L.mods = ctx->d_mods.as<ModTable>(); L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>(); L.row_pred = nullptr;
+    L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>(); L.hit_capacity = 0;
+    L.pair_score = d_score.as<double>(); L.pair_a = d_a.as<int32_t>(); L.pair_b = d_b.as<int32_t>(); L.max_blob_bytes = ctx->max_blob;
+    if (ctx->P.score_method == 2) return fail(ctx, PQ_ERR_UNSUPPORTED, "pq_score_pairs with MVH needs predicted-peak counts (not implemented yet)");
+    ScoreConfig cfg = score_config(ctx, 0);
+    {
+        Timer t(ctx, &ctx->cnt.ms_score);
+        ctx->cnt.score_kernel_launches += (uint64_t)launch_score(L, cfg, st);
+    }
+    CU(cudaGetLastError());
+    std::vector<double> hs((size_t)n_pairs); std::vector<int32_t> ha((size_t)n_pairs), hb((size_t)n_pairs);
+    CU(cudaMemcpyAsync(hs.data(), d_score.p, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ha.data(), d_a.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hb.data(), d_b.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int64_t k = 0; k < n_pairs; ++k) {
+        uint32_t o = order[(size_t)k];
+        score[o] = hs[(size_t)k]; if (count_a) count_a[o] = ha[(size_t)k]; if (count_b) count_b[o] = hb[(size_t)k];
+    }
+    return PQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+// pq_host.h — host-side peptide logic of libpepquery_b200.so: modification codes, form expansion, digestion,
+// shuffle group order.  Written independently of oracle/ (the oracle is only ever a test-side checker).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "pq_internal.h"
+
+namespace pq {
+
+struct HostMod {
+    int32_t id, position;
+    uint32_t residue_mask;   // bit (letter - 'A')
+    double delta, loss;
+};
+
+// Compact form record (host): parent sequence, mass and the (modification, site) list in reference list order.
+struct FormRec {
+    int32_t seq;
+    double mass;
+    uint8_t n;
+    uint8_t site[PQ_MAX_FORM_MODS];
+    int8_t mod[PQ_MAX_FORM_MODS];      // index into Codes::mods (var first, then fixed)
+};
+
+struct Codes {
+    std::vector<HostMod> mods;          // var mods then fixed mods
+    int n_var = 0, n_fixed = 0;
+    int max_var = 3, max_per_aa = 1;
+    ModTable table;                     // device copy is made from this
+    ShuffleMods shuffle;                // K2 view
+    int n_codes = 26;
+    double residue_mass[26];
+    bool init(const pq_params& p, std::string& err);
+    // sites a modification may occupy on a sequence, ascending (compomics ModificationUtils.getPossibleModificationSites, A9)
+    void possible_sites(const std::string& seq, int mod, std::vector<int>& out) const;
+    // PeptideInput.calcPeptideIsoforms + addFixedModification (pg/PeptideInput.java:114-237)
+    void expand_forms(const std::string& seq, int32_t seq_index, std::vector<FormRec>& out) const;
+    double form_mass(const std::string& seq, const FormRec& f) const;
+    bool encode_row(const std::string& seq, const FormRec& f, uint8_t* row) const;   // 64-byte device row
+    void to_public(const std::string& seq, const FormRec& f, pq_form* o) const;
+    bool from_public(const pq_form& f, std::string& seq, FormRec& out) const;
+};
+
+// DigestProteinWorker.run (OpenModificationSearch/DigestProteinWorker.java:64-137) over all proteins; returns the unique
+// I->L sequences in lexicographic order.
+void digest_proteins(const pq_params& p, const double* residue_mass, int32_t n_proteins, const uint64_t* off, const char* res,
+                     std::vector<std::string>& out, int threads);
+
+// Group order + round count of PeptideInput.generateRandomPeptidesFast (pg/PeptideInput.java:387-422).
+void shuffle_plan(const std::string& seq, int n_random, ShuffleSeq& out);
+
+// commons-math 2 MathUtils tables (A12): log10(n!) for n <= 64 and ln(n!) for n < count
+void factorial_tables(double* log10_fact65, std::vector<double>& ln_fact, int count);
+
+}  // namespace pq

@@ -1,0 +1,143 @@
+// pq_internal.h — device views and kernel launchers shared between the translation units of libpepquery_b200.so.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "pq_common.h"
+
+namespace pq {
+
+// Spectra as they sit in HBM: CSR peak arrays in precursor-mass order (SURVEY.md §8 a15 / north_star item 1).
+struct SpectraView {
+    int64_t n;                    // spectra
+    const double* prec_mz;        // [n] sorted by neutral mass
+    const int32_t* charge;        // [n]
+    const double* mass;           // [n] neutral precursor mass  mz*z - z*proton, ascending
+    const uint64_t* off;          // [n+1] peak offsets
+    const double* mz;             // peaks, file order inside a spectrum
+    const double* inten;
+    const int32_t* caller_index;  // [n] sorted position -> index in the caller's order
+};
+
+struct PrepConfig {
+    double itol;
+    int32_t method;               // 1 hyperscore, 2 MVH
+    int32_t mvh_bins;             // round(1800 / (2*itol))
+};
+
+// One unit of scoring work: one spectrum x a run of candidate peptide rows.
+struct Job {
+    uint32_t blob;                // prepared-spectrum id
+    uint32_t cand_begin;          // first candidate row (in the table the launch names)
+    uint32_t cand_count;
+    uint32_t out;                 // result slot of the job
+    double   mass;                // precursor neutral mass this job matches against (isotope-corrected)
+    double   ref_score;           // Step 3: best target score of the spectrum; Step 4: the PSM's score
+    int32_t  charge;              // precursor charge
+    int32_t  iso;                 // isotope error of `mass`
+    int32_t  spectrum;            // sorted spectrum index
+    int32_t  aux;                 // Step 4: target form; Step 5: ptm index
+};
+
+// What a launch does with the scores of a job.
+enum JobKind : int32_t { kJobTargets = 2, kJobCompetitors = 3, kJobShuffles = 4, kJobPtm = 5, kJobPairs = 1 };
+
+struct JobResult {            // per job, reduced in the CTA
+    uint32_t n_in_window;     // candidates passing the precursor window (= pairs scored)
+    uint32_t n_better;        // Step 3: score >= ref_score; Step 4: score >= ref_score; Step 5: better per -hc rule
+    double   best_score;      // max score over the job (-1 if none)
+    uint32_t best_cand;       // lowest candidate row attaining it
+    uint32_t pad;
+};
+
+struct Hit {                  // appended rows (Step 2 PSMs, Step 3 detail rows, Step 5 ptm rows)
+    int32_t  spectrum;        // sorted spectrum index
+    uint32_t cand;            // candidate row
+    double   score;
+    double   mass;            // precursor mass of the job
+    int32_t  count_a, count_b;
+    int32_t  iso;
+    int32_t  aux;             // Step 5: (ptm << 8) | site
+    uint32_t blob;            // prepared-spectrum id of the job
+    uint32_t pad;
+};
+
+struct ScoreConfig {
+    double itol;
+    double tol;
+    int32_t tol_ppm;
+    int32_t method;
+    double min_score;
+    int32_t fast, hc;
+    int32_t mvh_bins;
+    int32_t check_window;     // candidates must pass the bucket + tolerance predicate (Steps 2, 3, 5)
+};
+
+struct ScoreLaunch {
+    JobKind kind;
+    const Job* jobs; uint32_t n_jobs;
+    const uint8_t* blobs; const uint64_t* blob_off;       // prepared spectra
+    const uint8_t* rows; const double* row_mass;           // candidate table (64-byte rows) + masses (may be null)
+    const ModTable* mods;
+    const double* log10_fact;                              // [65]  log10(n!)
+    const double* ln_fact;                                 // [n]   ln(n!)  (MVH)
+    const int32_t* row_pred;                               // MVH: predicted-peak counts per row, [2*row]: maxc 1 / 2
+    JobResult* results;                                    // [n_jobs]
+    Hit* hits; uint32_t* hit_count; uint32_t hit_capacity; // appended rows
+    double* pair_score; int32_t* pair_a; int32_t* pair_b;  // kJobPairs: per-candidate outputs
+    uint32_t max_blob_bytes;
+    // Step 5
+    double ptm_delta; int32_t ptm_position; int32_t ptm_residue_code;
+};
+
+// kernel launchers (each returns the number of kernels it launched; errors via cudaGetLastError by the caller)
+int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, const PrepConfig& cfg, uint8_t* blobs,
+                   const uint64_t* blob_off, uint32_t max_peaks, cudaStream_t st);
+int launch_score(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st);
+
+// Step-2 window enumeration on device: for every usable spectrum x isotope error, the run of target rows whose mass
+// can fall in the precursor window.  Fills jobs (capacity n_spectra * n_isotope) and returns the count through d_n_jobs.
+struct WindowConfig { double tol; int32_t tol_ppm; int32_t n_isotope; int32_t isotope[PQ_MAX_ISOTOPE]; int32_t min_peaks; };
+int launch_enumerate_targets(const SpectraView& sp, const double* table_mass, uint32_t n_rows, const WindowConfig& cfg,
+                             Job* jobs, uint32_t* d_n_jobs, int32_t* need_prepare /* [n] flags */, cudaStream_t st);
+
+// Shuffle generation (K2): replays java.util.Random per target sequence, de-duplicates, then places the
+// modifications of each target form on each shuffle (second Random stream) and writes candidate rows.
+struct ShuffleSeq {            // one per target sequence that needs shuffles
+    uint32_t len;              // L
+    uint32_t n_groups;
+    uint32_t num;              // rounds to run (min(n_random, nComb))
+    uint32_t out_base;         // first raw-shuffle slot
+    uint8_t  group_code[32];   // residue letter code (0..25) per group, in the reference's group order
+    uint8_t  group_count[32];
+    uint8_t  seq[kMaxLen + 4]; // target letters (codes 0..25)
+};
+struct ShuffleForm {           // one per target form that needs shuffles
+    uint32_t seq_slot;         // index into ShuffleSeq[]
+    uint32_t row_base;         // first output row
+    uint32_t n_mods;
+    int8_t   mod[PQ_MAX_FORM_MODS];   // modification ids (index into ShuffleMods), target list order
+};
+struct ShuffleMods {           // the search's modifications as K2 needs them
+    int32_t n_mods;            // var then fixed
+    int32_t n_var;
+    int32_t position[2 * PQ_MAX_MODS];
+    uint32_t residue_mask[2 * PQ_MAX_MODS];    // bit r set: letter code r is a target residue
+    uint8_t  code_of[2 * PQ_MAX_MODS][26];     // residue code for (mod, letter)
+    uint8_t  term_code[2 * PQ_MAX_MODS];       // terminal code for site-0 / site-L+1 modifications
+    int64_t shuffle_seed, mod_seed;
+};
+int launch_shuffles(const ShuffleSeq* seqs, uint32_t n_seqs, const ShuffleForm* forms, uint32_t n_forms,
+                    const ShuffleMods* mods, uint8_t* raw /* n_seqs*num*64 */, uint32_t* kept_index, uint32_t* kept_count,
+                    uint8_t* rows, uint32_t max_num, int64_t shuffle_seed, cudaStream_t st);
+
+// packing helpers (k3_window.cu)
+int launch_precursor_mass(int64_t n, const double* prec_mz, const int32_t* charge, double* mass, uint64_t* key, int32_t* idx, cudaStream_t st);
+int launch_gather_meta(int64_t n, const int32_t* order, const double* prec_mz_in, const int32_t* charge_in, const double* mass_in,
+                       const uint64_t* off_in, double* prec_mz, int32_t* charge, double* mass, uint64_t* count, cudaStream_t st);
+int launch_gather_peaks(int64_t n, const int32_t* order, const uint64_t* off_in, const uint64_t* off_out, const double* mz_in,
+                        const double* in_in, double* mz_out, double* in_out, cudaStream_t st);
+int launch_blob_sizes(const SpectraView& sp, const int32_t* list, int32_t n_list, uint64_t* sizes, cudaStream_t st);
+int launch_fix_job_blobs(Job* jobs, uint32_t n_jobs, const int32_t* prep_id, cudaStream_t st);
+
+}  // namespace pq

@@ -1,0 +1,250 @@
+"""Host-side mirror of the reference's entry points for the pair-scoring path, on top of the C ABI.
+
+Reference (Java) call site                                   -> here
+  pg/CParameter.java statics                                 -> CParameter (builds a pq_params)
+  SpectraInput.readMSMSfast        (pg/SpectraInput.java:91)  -> Search.readMSMSfast(spectra)   [load + Step 2]
+  DatabaseInput.db_search          (pg/DatabaseInput.java:672)-> Search.db_search(proteins)     [index + Step 3]
+  StatisticScoreCalc.run           (pg/StatisticScoreCalc.java:19) -> Search.statistic_score()  [Step 4]
+  RankPSM.rankPSMs + passed_psm_validation                   -> Search.rank_psms()
+  ModificationDB.doPTMValidation   (ModificationDB.java:1320) -> Search.do_ptm_validation(ptms) [Step 5]
+  PeptideSearchMT.scorePeptide2Spectrum (PSMT:1144)           -> scorePeptide2Spectrum / Search.score_pairs
+
+Error behaviour: the reference calls System.exit on bad input; here every failure raises PepQueryError carrying the
+pq_status code and pq_last_error() text.  A missing CUDA library or GPU is an error, never a fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+
+_ROOT = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class PepQueryError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pepquery_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def library_path():
+    return os.path.join(_ROOT, "libpepquery_b200.so")
+
+
+def load_library():
+    """Loads libpepquery_b200.so (built in-tree by __graft_entry__.build()).  Raises if it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise PepQueryError(_abi.PQ_ERR_NO_DEVICE, "CUDA library %s is not built; there is no CPU fallback "
+                            "(run `python -c 'import __graft_entry__ as g; g.build()'`)" % path)
+    L = C.CDLL(path)
+    L.pq_last_error.restype = C.c_char_p
+    L.pq_last_error.argtypes = [C.c_void_p]
+    L.pq_version.restype = C.c_int32
+    for name in EXPORTS:
+        if name not in ("pq_last_error", "pq_version", "pq_default_params"):
+            getattr(L, name).restype = C.c_int32
+    _LIB = L
+    return L
+
+
+# every symbol include/pepquery_b200.h declares
+EXPORTS = ["pq_version", "pq_last_error", "pq_default_params", "pq_create", "pq_destroy", "pq_load_spectra",
+           "pq_set_targets", "pq_get_target_forms", "pq_build_reference", "pq_get_reference_forms",
+           "pq_step2_match_targets", "pq_step3_competitors", "pq_step4_shuffles", "pq_rank_and_validate",
+           "pq_step5_ptm", "pq_get_psms", "pq_get_competitors", "pq_get_shuffles", "pq_score_pairs",
+           "pq_get_counters", "pq_reset_counters", "pq_parse_mgf"]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def CParameter(**kw):
+    """pq_params with the defaults of pg/CParameter.java:84-463 (and -n 1000); keyword overrides by field name."""
+    return _abi.default_params(**kw)
+
+
+def psm_dtype():
+    m = {C.c_int32: np.int32, C.c_double: np.float64}
+    return np.dtype([(n, m[t]) for n, t in _abi.pq_psm._fields_])
+
+
+def competitor_dtype():
+    m = {C.c_int32: np.int32, C.c_double: np.float64}
+    return np.dtype([(n, m[t]) for n, t in _abi.pq_competitor._fields_])
+
+
+class Search:
+    """One pq_ctx = one search on one GPU."""
+
+    def __init__(self, params=None, device=None):
+        self.L = load_library()
+        self.params = params if params is not None else CParameter()
+        if device is not None:
+            self.params.device = int(device)
+        self.h = C.c_void_p()
+        rc = self.L.pq_create(C.byref(self.params), C.byref(self.h))
+        if rc != 0:
+            raise PepQueryError(rc, (self.L.pq_last_error(None) or b"").decode())
+
+    # -- plumbing ----------------------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise PepQueryError(rc, (self.L.pq_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pq_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- raw ABI calls -------------------------------------------------------------------------------------------
+    def load_spectra(self, sp):
+        n = len(sp["prec_mz"])
+        self._ck(self.L.pq_load_spectra(self.h, C.c_int64(n), _p(sp["prec_mz"]), _p(sp["charge"]), _p(sp["peak_off"]),
+                                        _p(sp["mz"]), _p(sp["inten"])))
+
+    def set_targets(self, off, res):
+        self._ck(self.L.pq_set_targets(self.h, C.c_int32(len(off) - 1), _p(off), _p(res)))
+
+    def _forms(self, fn):
+        n = C.c_int64()
+        self._ck(fn(self.h, None, C.c_int64(0), C.byref(n)))
+        arr = (_abi.pq_form * max(1, n.value))()
+        self._ck(fn(self.h, arr, C.c_int64(n.value), C.byref(n)))
+        return arr, n.value
+
+    def target_forms(self):
+        return self._forms(self.L.pq_get_target_forms)
+
+    def reference_forms(self):
+        return self._forms(self.L.pq_get_reference_forms)
+
+    def build_reference(self, off, res):
+        self._ck(self.L.pq_build_reference(self.h, C.c_int32(len(off) - 1), _p(off), _p(res)))
+
+    def step2(self):
+        n = C.c_int64()
+        self._ck(self.L.pq_step2_match_targets(self.h, C.byref(n)))
+        return n.value
+
+    def step3(self):
+        self._ck(self.L.pq_step3_competitors(self.h))
+
+    def step4(self):
+        self._ck(self.L.pq_step4_shuffles(self.h))
+
+    def rank(self):
+        self._ck(self.L.pq_rank_and_validate(self.h))
+
+    def step5(self, ptms):
+        arr = (_abi.pq_ptm * max(1, len(ptms)))(*ptms)
+        self._ck(self.L.pq_step5_ptm(self.h, C.c_int32(len(ptms)), arr))
+
+    def psms(self):
+        n = C.c_int64()
+        self._ck(self.L.pq_get_psms(self.h, None, C.c_int64(0), C.byref(n)))
+        arr = (_abi.pq_psm * max(1, n.value))()
+        self._ck(self.L.pq_get_psms(self.h, arr, C.c_int64(n.value), C.byref(n)))
+        return np.frombuffer(arr, dtype=psm_dtype(), count=n.value).copy()
+
+    def competitors(self, step=3):
+        n = C.c_int64()
+        self._ck(self.L.pq_get_competitors(self.h, C.c_int32(step), None, C.c_int64(0), C.byref(n)))
+        arr = (_abi.pq_competitor * max(1, n.value))()
+        self._ck(self.L.pq_get_competitors(self.h, C.c_int32(step), arr, C.c_int64(n.value), C.byref(n)))
+        return np.frombuffer(arr, dtype=competitor_dtype(), count=n.value).copy()
+
+    def shuffles(self, target_seq, length):
+        n = C.c_int32()
+        self._ck(self.L.pq_get_shuffles(self.h, C.c_int32(target_seq), None, C.c_int64(0), C.byref(n)))
+        cap = max(1, n.value) * (length + 1)
+        buf = C.create_string_buffer(cap)
+        self._ck(self.L.pq_get_shuffles(self.h, C.c_int32(target_seq), buf, C.c_int64(cap), C.byref(n)))
+        L1 = length + 1
+        return [buf.raw[i * L1:i * L1 + length].decode() for i in range(n.value)]
+
+    def score_pairs(self, spectrum_index, forms, n=None):
+        n = len(spectrum_index) if n is None else n
+        si = np.ascontiguousarray(spectrum_index, dtype=np.int32)
+        score = np.zeros(n, dtype=np.float64)
+        ca = np.zeros(n, dtype=np.int32)
+        cb = np.zeros(n, dtype=np.int32)
+        self._ck(self.L.pq_score_pairs(self.h, C.c_int64(n), _p(si), forms, _p(score), _p(ca), _p(cb)))
+        return score, ca, cb
+
+    def counters(self):
+        c = _abi.pq_counters()
+        self._ck(self.L.pq_get_counters(self.h, C.byref(c)))
+        return c
+
+    def reset_counters(self):
+        self._ck(self.L.pq_reset_counters(self.h))
+
+    # -- the reference's names -------------------------------------------------------------------------------------
+    def readMSMSfast(self, spectra, target_off, target_res):
+        """SpectraInput.readMSMSfast (pg/SpectraInput.java:91-279): load spectra, score targets in window."""
+        self.load_spectra(spectra)
+        self.set_targets(target_off, target_res)
+        return self.step2()
+
+    def db_search(self, prot_off, prot_res):
+        """DatabaseInput.db_search (pg/DatabaseInput.java:672-758)."""
+        self.build_reference(prot_off, prot_res)
+        self.step3()
+
+    def statistic_score(self):
+        """StatisticScoreCalc.run (pg/StatisticScoreCalc.java:19-63)."""
+        self.step4()
+
+    def rank_psms(self):
+        """RankPSM.rankPSMs (pg/RankPSM.java:36) + CParameter.passed_psm_validation (pg/CParameter.java:913)."""
+        self.rank()
+        return self.psms()
+
+    def do_ptm_validation(self, ptms):
+        """ModificationDB.doPTMValidation (OpenModificationSearch/ModificationDB.java:1320-1466)."""
+        self.step5(ptms)
+        return self.psms()
+
+
+def scorePeptide2Spectrum(search, form, spectrum_index):
+    """PeptideSearchMT.scorePeptide2Spectrum (pg/PeptideSearchMT.java:1144-1251) for one pair -> (score, a, b)."""
+    arr = (_abi.pq_form * 1)(form)
+    s, a, b = search.score_pairs([spectrum_index], arr, 1)
+    return float(s[0]), int(a[0]), int(b[0])
+
+
+def parse_mgf(text):
+    """MGF text -> CSR dict (pq_parse_mgf; replaces compomics MgfFileIterator, SpectraInput.java:150)."""
+    L = load_library()
+    raw = text if isinstance(text, (bytes, bytearray)) else text.encode()
+    ns = C.c_int64(0)
+    npk = C.c_uint64(0)
+    rc = L.pq_parse_mgf(raw, C.c_uint64(len(raw)), C.byref(ns), C.byref(npk), None, None, None, None, None)
+    if rc != 0:
+        raise PepQueryError(rc, "pq_parse_mgf")
+    sp = dict(prec_mz=np.zeros(ns.value), charge=np.zeros(ns.value, dtype=np.int32),
+              peak_off=np.zeros(ns.value + 1, dtype=np.uint64), mz=np.zeros(npk.value), inten=np.zeros(npk.value))
+    rc = L.pq_parse_mgf(raw, C.c_uint64(len(raw)), C.byref(ns), C.byref(npk), _p(sp["prec_mz"]), _p(sp["charge"]),
+                        _p(sp["peak_off"]), _p(sp["mz"]), _p(sp["inten"]))
+    if rc != 0:
+        raise PepQueryError(rc, "pq_parse_mgf")
+    return sp
