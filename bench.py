@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — peptide-spectrum pairs scored per second (incl. shuffles) on the C2-shaped workload.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--spectra S] [--peptides P]
+
+One "step" = one pass of the hot path (Step 2 target matching + Step 3 competitor search + Step 4 shuffles,
+SURVEY.md §3.2-3.4) over one resident batch of spectra.  N > 1: launched by torchrun, one rank per GPU, spectra sharded
+by precursor-mass range (weak scaling: each rank holds --spectra spectra of its own mass range; targets and the protein
+database are replicated); the per-rank PSM records are gathered to rank 0 over NCCL inside the timed region.
+
+Keys of the JSON line (rank 0): see the task contract.  `value` = pairs/s with inputs resident in HBM; `e2e` = the
+same metric through the C ABI from HOST (pinned) buffers, H2D/D2H and the host-side reference-table build inside the
+timed region; `roofline` = the Step-4 K1 launch against the measured HBM peak, algorithmic bytes (16*P_s+96 per pair,
+SURVEY.md §8d); `cpu_baseline` = the CPU oracle ("port") on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "peptide_spectrum_pairs_scored_per_sec"
+UNIT = "pairs/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spectra", type=int, default=1000000, help="spectra per GPU")
+    ap.add_argument("--peptides", type=int, default=10000)
+    ap.add_argument("--proteins", type=int, default=20000)
+    ap.add_argument("--shuffles", type=int, default=1000)
+    ap.add_argument("--method", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-sample", type=int, default=12000, help="spectra in the CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return ("C2: %d peptides x %d spectra/GPU x %d-protein DB, %s, %d shuffles, fixMod C+57 varMod M+16" %
+            (a.peptides, a.spectra, a.proteins, "hyperscore" if a.method == 1 else "MVH", a.shuffles))
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(a, rank, world, pinned):
+    from pepquery_b200 import synth
+    prot = synth.proteins(a.proteins)
+    tgt = synth.targets(a.peptides)
+    lo, hi = 0.0, 1e9
+    if world > 1:
+        b = synth.mass_bounds(world, tgt, prot)
+        lo, hi = float(b[rank]), float(b[rank + 1])
+    sp = synth.spectra(a.spectra, tgt, prot, first_index=rank * a.spectra, mass_lo=lo, mass_hi=hi, pinned=pinned)
+    return prot, tgt, sp
+
+
+def run_reference(a, rank, world):
+    """The reference arm: the CPU oracle ("port"; the Java reference cannot run here — no JVM, un-vendored jars),
+    all host threads, each step a bounded sample of the workload."""
+    if rank != 0:
+        return
+    from oracle import pq_oracle
+    from pepquery_b200 import _abi
+    threads = os.cpu_count() or 1
+    prot, tgt, sp = make_inputs(argparse.Namespace(**{**vars(a), "spectra": a.cpu_sample}), 0, 1, None)
+    p = _abi.default_params(n_random=a.shuffles, score_method=a.method)
+    times, pairs = [], 0
+    for it in range(a.warmup + a.steps):
+        o = pq_oracle.Oracle(p, threads=threads)
+        o.load_spectra(sp); o.set_targets(*tgt)
+        t0 = time.perf_counter()
+        o.step2()
+        t1 = time.perf_counter()
+        o.build_reference(*prot)          # not timed: fixed cost, independent of the sample size
+        t2 = time.perf_counter()
+        o.step3(); o.step4(); o.rank()
+        t3 = time.perf_counter()
+        if it >= a.warmup:
+            times.append((t1 - t0) + (t3 - t2))
+            pairs = int(o.pairs()[:3].sum())
+        o.close()
+        if it == 0 and (t1 - t0) + (t3 - t2) > 60 and a.warmup > 0:
+            a.warmup = 1
+    tot = sum(times)
+    val = pairs * len(times) / tot
+    sample = "%d spectra of the workload x all %d peptides x full DB, Steps 2-4, %d pairs per step" % (a.cpu_sample, a.peptides, pairs)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1000.0 * tot / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(a), "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    from pepquery_b200 import Search, _abi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    keep = []
+
+    def pinned(n):
+        t = torch.empty(int(n), dtype=torch.float64, pin_memory=True)
+        keep.append(t)
+        return t.numpy()
+
+    t_gen = time.time()
+    prot, tgt, sp = make_inputs(a, rank, world, pinned)
+    t_gen = time.time() - t_gen
+    p = _abi.default_params(n_random=a.shuffles, score_method=a.method, device=local)
+    g = Search(p)
+
+    def gather_psms(psms):
+        """NCCL gather of the fixed-size PSM records to rank 0 (the only collective of the path)."""
+        if world == 1:
+            return len(psms)
+        raw = torch.from_numpy(psms.view(np.uint8).reshape(-1).copy()).cuda()
+        n = torch.tensor([raw.numel()], device="cuda", dtype=torch.int64)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        mx = int(max(int(s.item()) for s in sizes))
+        buf = torch.zeros(mx, dtype=torch.uint8, device="cuda")
+        buf[:raw.numel()] = raw
+        out = [torch.zeros_like(buf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, out, dst=0)
+        if rank == 0:
+            return sum(int(s.item()) for s in sizes) // psms.dtype.itemsize
+        return 0
+
+    # ---- resident-input measurement ----------------------------------------------------------------------------
+    g.load_spectra(sp)
+    g.set_targets(*tgt)
+    g.step2()
+    g.build_reference(*prot)
+    c0 = g.counters()
+    ms_host_reference = c0.ms_host_reference
+
+    def step():
+        g.step2(); g.step3(); g.step4()
+        return gather_psms(g.rank_psms())
+
+    for _ in range(max(a.warmup, 3) if a.warmup >= 0 else 3):
+        step()
+    g.reset_counters()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    g.event_record(0)                      # CUDA events on the library's own stream
+    for _ in range(a.steps):
+        n_psm_total = step()
+    g.event_record(1)
+    dev_ms = g.event_elapsed_ms()
+    barrier()
+    wall = time.perf_counter() - t0
+    wall = max(wall, dev_ms / 1e3)         # device-event time; wall between syncs is the same interval seen from the host
+    clk = clocks.stop()
+    c = g.counters()
+    pairs_step = (c.pairs_step2 + c.pairs_step3 + c.pairs_step4) / a.steps
+    launches = (c.score_kernel_launches + c.other_kernel_launches)
+    # the library runs on its own stream: the elapsed time of the step loop is wall time between two device syncs
+    tmax = torch.tensor([wall], device="cuda", dtype=torch.float64)
+    tot_pairs = torch.tensor([pairs_step], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_pairs, op=dist.ReduceOp.SUM)
+    sec_per_step = float(tmax.item()) / a.steps
+    value = float(tot_pairs.item()) / sec_per_step
+
+    # roofline of the dominant kernel: the Step-4 K1 launch (CUDA events on the library's stream, around the launch)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+    k1_ms = c.ms_score_step[2] / a.steps
+    k1_bytes = c.bytes_score_step[2] / a.steps
+    achieved = (k1_bytes / 1e9) / (k1_ms / 1e3) if k1_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "k1_score_kernel<256,%d> (Step 4, one launch per step)" % a.method, "peak_source": peak_src,
+                "ms_per_launch": k1_ms, "pairs_per_launch": c.pairs_step4 / a.steps,
+                "note": "algorithmic bytes = sum over pairs of 16*P_s+96 (SURVEY.md 8d); each spectrum is staged once in shared memory and "
+                        "reused by ~1000 shuffles, so physical DRAM traffic is far lower and frac may exceed 1"}
+    kernel_ms = {"k1_step2": c.ms_score_step[0] / a.steps, "k1_step3": c.ms_score_step[1] / a.steps, "k1_step4": k1_ms,
+                 "k0_prepare+pack": c.ms_prepare / a.steps, "k3_window": c.ms_window / a.steps, "k2_shuffle": c.ms_shuffle / a.steps}
+
+    # ---- end-to-end from host buffers ---------------------------------------------------------------------------
+    e2e = None
+    if a.e2e_steps > 0:
+        g.reset_counters()
+        barrier()
+        t0 = time.perf_counter()
+        g.event_record(0)
+        for _ in range(a.e2e_steps):
+            g.load_spectra(sp)                     # H2D of the pinned CSR arrays + packing
+            g.set_targets(*tgt)
+            g.step2()
+            g.build_reference(*prot)               # host digest + form expansion + H2D of the table
+            g.step3(); g.step4()
+            gather_psms(g.rank_psms())             # D2H of the result records
+        g.event_record(1)
+        dms = g.event_elapsed_ms()
+        barrier()
+        w = max(time.perf_counter() - t0, dms / 1e3)
+        ce = g.counters()
+        pe = (ce.pairs_step2 + ce.pairs_step3 + ce.pairs_step4) / a.e2e_steps
+        tm = torch.tensor([w], device="cuda", dtype=torch.float64)
+        tp = torch.tensor([pe], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX); dist.all_reduce(tp, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(tp.item()) / (float(tm.item()) / a.e2e_steps), "unit": UNIT,
+               "h2d_bytes_per_step": int(ce.h2d_bytes / a.e2e_steps), "d2h_bytes_per_step": int(ce.d2h_bytes / a.e2e_steps),
+               "ms_per_step": 1000.0 * float(tm.item()) / a.e2e_steps, "steps": a.e2e_steps,
+               "ms_host_reference_build": ce.ms_host_reference / a.e2e_steps}
+    g.close()
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        from oracle import pq_oracle
+        threads = os.cpu_count() or 1
+        ns = min(a.cpu_sample, a.spectra)
+        sub = {"prec_mz": sp["prec_mz"][:ns].copy(), "charge": sp["charge"][:ns].copy(), "peak_off": sp["peak_off"][:ns + 1].copy(),
+               "mz": np.array(sp["mz"][:int(sp["peak_off"][ns])]), "inten": np.array(sp["inten"][:int(sp["peak_off"][ns])])}
+        o = pq_oracle.Oracle(p, threads=threads)
+        o.load_spectra(sub); o.set_targets(*tgt)
+        t0 = time.perf_counter(); o.step2(); t1 = time.perf_counter()
+        o.build_reference(*prot)
+        t2 = time.perf_counter(); o.step3(); o.step4(); t3 = time.perf_counter()
+        cp = int(o.pairs()[:3].sum())
+        o.close()
+        cpu = {"value": cp / ((t1 - t0) + (t3 - t2)), "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "first %d spectra of the workload x all %d peptides x full DB, Steps 2-4 (%d pairs, %.1f s; reference-table build "
+                         "not timed); as-written cost model: pre-processing redone per pair like scorePeptide2Spectrum" %
+                         (ns, a.peptides, cp, (t1 - t0) + (t3 - t2))}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": 1000.0 * sec_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(a), "sharding": "spectra by precursor-mass range, tables replicated" if world > 1 else "single GPU",
+                           "l2": "inputs larger than L2 (prepared spectra + shuffle rows >> 126 MB per step)",
+                           "pairs_per_step": float(tot_pairs.item()), "psms_per_step": int(n_psm_total),
+                           "timed_region": "Steps 2+3+4 + rank/accept + result gather, spectra/targets/reference table resident in HBM",
+                           "gen_seconds": round(t_gen, 1), "ms_host_reference_build_once": ms_host_reference},
+                "clocks": clk, "gpu_launches": int(launches), "kernel_ms_per_step": kernel_ms,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

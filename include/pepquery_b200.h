@@ -164,6 +164,9 @@ typedef struct pq_counters {
     uint64_t score_algorithmic_bytes;   /* sum over scored pairs of 16*P_s + 64 + 32   */
     double   ms_prepare, ms_window, ms_score, ms_shuffle, ms_total; /* CUDA-event time on the ctx stream */
     uint64_t h2d_bytes, d2h_bytes;
+    double   ms_score_step[4];          /* K1 launch time of Steps 2,3,4,5 (CUDA events around the launch)       */
+    uint64_t bytes_score_step[4];       /* algorithmic bytes of those launches                                   */
+    double   ms_host_reference;         /* wall time of the reference-table build (digest + forms + upload)      */
 } pq_counters;
 
 typedef struct pq_ctx pq_ctx;
@@ -225,6 +228,10 @@ int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_ind
 
 int32_t pq_get_counters(pq_ctx* ctx, pq_counters* out);
 int32_t pq_reset_counters(pq_ctx* ctx);
+/* Device-side stopwatch: CUDA events recorded on the context's own stream (torch.cuda.Event cannot see that stream).
+ * which = 0 records the start event, 1 the stop event; elapsed = stop - start after synchronising the stop event. */
+int32_t pq_event_record(pq_ctx* ctx, int32_t which);
+int32_t pq_event_elapsed_ms(pq_ctx* ctx, double* ms);
 
 /* Host-side text front end: single-pass MGF parser into CSR buffers.  Two-call pattern:
  * first call with NULL outputs returns the required sizes. */

@@ -83,7 +83,9 @@ class pq_counters(C.Structure):
                 ("score_algorithmic_bytes", C.c_uint64),
                 ("ms_prepare", C.c_double), ("ms_window", C.c_double), ("ms_score", C.c_double),
                 ("ms_shuffle", C.c_double), ("ms_total", C.c_double),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("ms_score_step", C.c_double * 4), ("bytes_score_step", C.c_uint64 * 4),
+                ("ms_host_reference", C.c_double)]
 
 
 # Modification constants pinned by the reference's resources/top_modifications.tsv (ids = -fixMod/-varMod numbers)

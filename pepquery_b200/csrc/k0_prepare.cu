@@ -196,19 +196,23 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             }
             if (threadIdx.x == 0) isotope_pass(r_mz, r_in, ord, keep, P, 1.5);                       // cleanIsotopes
             __syncthreads();
-            if (block_count(keep, P, s_u) > 50) keep_top(r_in, ord, keep, aux, P, 50);               // filterByPeakCount
+            const bool cut = block_count(keep, P, s_u) > 50;
+            if (cut) keep_top(r_in, ord, keep, aux, P, 50);                                          // filterByPeakCount
             double mx = block_max_kept(r_in, ord, keep, P, s_d);
-            // survivor ids by distinct m/z; normalised intensity of the last duplicate wins (HashMap.put, :71-78)
+            // survivor ids by distinct m/z.  Surviving duplicates of one m/z (possible below 200 Th) share a slot whose
+            // value is the LAST HashMap.put of calcHyperScore's final m/z-sorted walk (:71-78): that sort is stable, so
+            // equal m/z keep the order of the previous sort — by intensity when the top-50 cut ran, else file order.
             if (threadIdx.x == 0) {
-                uint32_t sid = 0; bool have = false; double last = 0.0;
+                uint32_t sid = 0; bool have = false; double last = 0.0, last_in = 0.0;
                 double* val = s_val;
                 for (uint32_t i = 0; i < P; ++i) {
                     aux[i] = kNoSurvivor;
                     if (!keep[i]) continue;
-                    double m = r_mz[ord[i]];
-                    if (have && m == last) { /* same slot */ } else { if (have) ++sid; have = true; last = m; }
+                    double m = r_mz[ord[i]], v = r_in[ord[i]];
+                    bool same = have && m == last;
+                    if (!same) { if (have) ++sid; have = true; last = m; }
                     aux[i] = sid;
-                    val[sid] = __ddiv_rn(__dmul_rn(__dmul_rn(1.0, 100.0), r_in[ord[i]]), mx);       // normalizePeaks(100)
+                    if (!same || !cut || v >= last_in) { val[sid] = __ddiv_rn(__dmul_rn(__dmul_rn(1.0, 100.0), v), mx); last_in = v; }   // normalizePeaks(100)
                 }
                 uint32_t ns = have ? sid + 1 : 0;
                 // a peak that was filtered out but shares its m/z with a survivor still hits the survivor map

@@ -178,7 +178,8 @@ __device__ __forceinline__ PairScore score_pair(const uint32_t* codes /* this th
         int matched = key0 + key1 + key2;
         r.a = matched; r.b = predicted;
         r.score = 0.0;
-        if (!(B.flags & 1u) || predicted <= 0) return r;
+        if (!(B.flags & 1u)) { r.a = 0; r.b = 0; return r; }     // fewer than 7 peaks survived: calcMVH returns before scoring
+        if (predicted <= 0) return r;
         int key[4] = {key0, key1, key2, predicted - matched};
         int N = (int)B.nsurv;
         double mvh = 0.0; bool died = false;

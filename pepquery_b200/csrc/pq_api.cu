@@ -22,6 +22,19 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// PQ_DEBUG=1: host wall-clock marks inside the step drivers (stderr)
+struct Marks {
+    const char* name; bool on; std::chrono::steady_clock::time_point t0, last;
+    explicit Marks(const char* n) : name(n), on(getenv("PQ_DEBUG") != nullptr) { t0 = last = std::chrono::steady_clock::now(); }
+    void mark(const char* what) {
+        if (!on) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pq] %s: %-28s %8.3f ms\n", name, what, std::chrono::duration<double, std::milli>(now - last).count());
+        last = now;
+    }
+    ~Marks() { if (on) fprintf(stderr, "[pq] %s: total %8.3f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
+};
+
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
     DevBuf() = default;
@@ -65,7 +78,7 @@ struct pq_ctx {
     Codes codes;
     std::string err;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, uev0 = nullptr, uev1 = nullptr;
     pq_counters cnt;
     // constant tables
     DevBuf d_mods, d_l10, d_lnf, d_shufmods;
@@ -90,7 +103,7 @@ struct pq_ctx {
     // work buffers
     DevBuf jobs, results, hits, hit_count, njobs;
     // shuffles
-    DevBuf sh_seqs, sh_forms, sh_raw, sh_kidx, sh_kcnt, sh_rows;
+    DevBuf sh_seqs, sh_forms, sh_raw, sh_kidx, sh_kcnt, sh_rows, sh_pred;
     std::vector<ShuffleSeq> h_sh_seqs; std::vector<uint32_t> h_kept; std::vector<int32_t> sh_slot_of_seq;
     // results
     std::vector<HostPsm> psms;
@@ -121,6 +134,10 @@ int32_t upload_table(pq_ctx* ctx, PeptideTable& T) {
     CU(T.mass.reserve(std::max<size_t>(n * 8, 64)));
     CU(cudaMemcpyAsync(T.rows.p, rows.data(), rows.size(), cudaMemcpyHostToDevice, ctx->st));
     CU(cudaMemcpyAsync(T.mass.p, T.h_mass.data(), n * 8, cudaMemcpyHostToDevice, ctx->st));
+    if (ctx->P.score_method == 2 && n > 0) {
+        CU(T.pred.reserve(n * 8));
+        ctx->cnt.other_kernel_launches += (uint64_t)launch_predict(T.rows.as<uint8_t>(), (uint32_t)n, ctx->d_mods.as<ModTable>(), ctx->P.itol, T.pred.as<int32_t>(), ctx->st);
+    }
     CU(cudaStreamSynchronize(ctx->st));
     ctx->cnt.h2d_bytes += rows.size() + n * 8;
     return PQ_OK;
@@ -135,7 +152,7 @@ ScoreConfig score_config(const pq_ctx* c, int check_window) {
 }
 
 // run K1 over a job list that already sits in ctx->jobs; fills results (+hits)
-int32_t run_score(pq_ctx* ctx, JobKind kind, uint32_t n_jobs, const PeptideTable* T, const uint8_t* rows, const double* row_mass,
+int32_t run_score(pq_ctx* ctx, JobKind kind, uint32_t n_jobs, const int32_t* row_pred, const uint8_t* rows, const double* row_mass,
                   uint32_t hit_capacity, int check_window) {
     CU(ctx->results.reserve(std::max<size_t>((size_t)n_jobs * sizeof(JobResult), 64)));
     CU(ctx->hits.reserve(std::max<size_t>((size_t)hit_capacity * sizeof(Hit), 64)));
@@ -146,13 +163,16 @@ int32_t run_score(pq_ctx* ctx, JobKind kind, uint32_t n_jobs, const PeptideTable
     L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>();
     L.rows = rows; L.row_mass = row_mass; L.mods = ctx->d_mods.as<ModTable>();
     L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>();
-    L.row_pred = T ? T->pred.as<int32_t>() : nullptr;
+    L.row_pred = row_pred;
     L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>();
     L.hit_capacity = hit_capacity; L.max_blob_bytes = ctx->max_blob;
     ScoreConfig cfg = score_config(ctx, check_window);
     {
-        Timer t(ctx, &ctx->cnt.ms_score);
-        ctx->cnt.score_kernel_launches += (uint64_t)launch_score(L, cfg, ctx->st);
+        double ms = 0.0;
+        { Timer t(ctx, &ms); ctx->cnt.score_kernel_launches += (uint64_t)launch_score(L, cfg, ctx->st); }
+        ctx->cnt.ms_score += ms;
+        int si = kind == kJobTargets ? 0 : kind == kJobCompetitors ? 1 : kind == kJobShuffles ? 2 : 3;
+        ctx->cnt.ms_score_step[si] += ms;
     }
     CU(cudaGetLastError());
     return PQ_OK;
@@ -206,7 +226,7 @@ int32_t pq_create(const pq_params* params, pq_ctx** out) {
     if (cudaSetDevice(params->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx; return fail(nullptr, PQ_ERR_CUDA, "cannot initialise device");
     }
-    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->uev0); cudaEventCreate(&ctx->uev1);
     int bins = (int)jround((double)(int)(2000.0 - 200.0) / (params->itol * 2.0));
     factorial_tables(ctx->log10_fact, ctx->ln_fact, std::max(bins + 512, 4096));
     bool ok = ctx->d_mods.reserve(sizeof(ModTable)) == cudaSuccess && ctx->d_l10.reserve(65 * 8) == cudaSuccess &&
@@ -234,6 +254,20 @@ int32_t pq_destroy(pq_ctx* ctx) {
     return PQ_OK;
 }
 
+int32_t pq_event_record(pq_ctx* ctx, int32_t which) {
+    if (!ctx) return PQ_ERR_BAD_ARG;
+    cudaSetDevice(ctx->P.device);
+    CU(cudaEventRecord(which ? ctx->uev1 : ctx->uev0, ctx->st));
+    return PQ_OK;
+}
+int32_t pq_event_elapsed_ms(pq_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return PQ_ERR_BAD_ARG;
+    cudaSetDevice(ctx->P.device);
+    CU(cudaEventSynchronize(ctx->uev1));
+    float f = 0; CU(cudaEventElapsedTime(&f, ctx->uev0, ctx->uev1));
+    *ms = f;
+    return PQ_OK;
+}
 int32_t pq_get_counters(pq_ctx* ctx, pq_counters* out) { if (!ctx || !out) return PQ_ERR_BAD_ARG; *out = ctx->cnt; return PQ_OK; }
 int32_t pq_reset_counters(pq_ctx* ctx) {
     if (!ctx) return PQ_ERR_BAD_ARG;
@@ -348,9 +382,9 @@ int32_t finalize_targets(pq_ctx* ctx) {
     PeptideTable S;     // temp sorted copy for upload
     S.seqs = T.seqs; S.forms.resize(n);
     for (size_t r = 0; r < n; ++r) S.forms[r] = T.forms[ord[r]];
-    std::swap(S.rows, T.rows); std::swap(S.mass, T.mass);
+    std::swap(S.rows, T.rows); std::swap(S.mass, T.mass); std::swap(S.pred, T.pred);
     int32_t rc = upload_table(ctx, S);
-    std::swap(S.rows, T.rows); std::swap(S.mass, T.mass);
+    std::swap(S.rows, T.rows); std::swap(S.mass, T.mass); std::swap(S.pred, T.pred);
     T.h_mass = S.h_mass;    // sorted masses (row order)
     return rc;
 }
@@ -373,6 +407,7 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     if (!ctx) return PQ_ERR_BAD_ARG;
     if (!ctx->have_targets) return fail(ctx, PQ_ERR_STATE, "pq_set_targets first");
     cudaSetDevice(ctx->P.device);
+    Marks mk("step2");
     int32_t rc = finalize_targets(ctx);
     if (rc) return rc;
     ctx->psms.clear(); ctx->step_done = 0; ctx->n_prepared = 0;
@@ -404,6 +439,7 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     CU(cudaMemcpyAsync(&h_nprep, ctx->prep_id.as<int32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->cnt.d2h_bytes += 8;
+    mk.mark("enumerate");
     if (h_njobs == 0) { ctx->step_done = 2; return PQ_OK; }
     // list of spectra to prepare (ascending sorted index) + blob offsets
     {
@@ -431,14 +467,16 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
         ctx->max_blob = blob_bytes((ctx->max_peaks + 3u) & ~3u);
     }
     CU(cudaGetLastError());
+    mk.mark("prepare launch");
     // hits capacity: every candidate could pass
     std::vector<Job> hj(h_njobs);
     CU(cudaMemcpyAsync(hj.data(), ctx->jobs.p, (size_t)h_njobs * sizeof(Job), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->cnt.d2h_bytes += (uint64_t)h_njobs * sizeof(Job);
     uint64_t cand = 0; for (auto& j : hj) cand += j.cand_count;
+    mk.mark("jobs d2h (waits for K0)");
     if (cand > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-2 candidates for one launch");
-    rc = run_score(ctx, kJobTargets, h_njobs, &T, T.rows.as<uint8_t>(), T.mass.as<double>(), (uint32_t)cand, 1);
+    rc = run_score(ctx, kJobTargets, h_njobs, T.pred.as<int32_t>(), T.rows.as<uint8_t>(), T.mass.as<double>(), (uint32_t)cand, 1);
     if (rc) return rc;
     std::vector<JobResult> hr(h_njobs);
     uint32_t nh = 0;
@@ -448,6 +486,7 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     std::vector<Hit> hh(nh);
     if (nh) { CU(cudaMemcpyAsync(hh.data(), ctx->hits.p, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
     ctx->cnt.d2h_bytes += (uint64_t)h_njobs * sizeof(JobResult) + (uint64_t)nh * sizeof(Hit) + 4;
+    mk.mark("score + results d2h");
     if (getenv("PQ_DEBUG")) {
         uint64_t nin = 0; for (auto& r : hr) nin += r.n_in_window;
         fprintf(stderr, "[pq] step2: jobs %u prepared %d candidates %llu in-window %llu hits %u max_blob %u\n", h_njobs, h_nprep,
@@ -458,7 +497,8 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     }
     for (size_t j = 0; j < hj.size(); ++j) {
         ctx->cnt.pairs_step2 += hr[j].n_in_window;
-        ctx->cnt.score_algorithmic_bytes += (uint64_t)hr[j].n_in_window * (16ull * ctx->h_npeaks[(size_t)hj[j].spectrum] + 96ull);
+        uint64_t ab = (uint64_t)hr[j].n_in_window * (16ull * ctx->h_npeaks[(size_t)hj[j].spectrum] + 96ull);
+        ctx->cnt.score_algorithmic_bytes += ab; ctx->cnt.bytes_score_step[0] += ab;
     }
     const TargetOrder& O = ctx->order;
     ctx->psms.reserve(nh);
@@ -471,6 +511,7 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     }
     std::sort(ctx->psms.begin(), ctx->psms.end(), [](const HostPsm& a, const HostPsm& b) { return a.spectrum != b.spectrum ? a.spectrum < b.spectrum : a.form < b.form; });
     ctx->cnt.psms = ctx->psms.size();
+    mk.mark("psm list + sort");
     ctx->step_done = 2;
     if (n_psms) *n_psms = (int64_t)ctx->psms.size();
     return PQ_OK;
@@ -483,8 +524,11 @@ int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off,
     cudaSetDevice(ctx->P.device);
     PeptideTable& R = ctx->reference;
     R.seqs.clear(); R.forms.clear();
+    auto t_begin = std::chrono::steady_clock::now();
+    Marks mk("build_reference");
     int threads = (int)std::thread::hardware_concurrency(); if (threads < 1) threads = 1; if (threads > 32) threads = 32;
     digest_proteins(ctx->P, ctx->codes.residue_mass, n_proteins, off, res, R.seqs, threads);
+    mk.mark("digest + unique + sort");
     {   // DatabaseInput.protein_digest(db, target_peptides) removes the target sequences (:480-488)
         std::vector<std::string> t(ctx->targets.seqs); std::sort(t.begin(), t.end());
         R.seqs.erase(std::remove_if(R.seqs.begin(), R.seqs.end(), [&](const std::string& s) { return std::binary_search(t.begin(), t.end(), s); }), R.seqs.end());
@@ -511,10 +555,14 @@ int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off,
         R.forms.reserve(tot);
         for (auto& p : part) R.forms.insert(R.forms.end(), p.begin(), p.end());
     }
+    mk.mark("expand forms");
     sort_table(R);
+    mk.mark("sort by mass");
     int32_t rc = upload_table(ctx, R);
+    mk.mark("encode + upload");
     if (rc) return rc;
     ctx->cnt.reference_sequences = R.seqs.size(); ctx->cnt.reference_forms = R.forms.size();
+    ctx->cnt.ms_host_reference += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     ctx->have_reference = true;
     return PQ_OK;
 }
@@ -535,6 +583,7 @@ int32_t pq_step3_competitors(pq_ctx* ctx) {
     if (ctx->step_done < 2 || !ctx->have_reference) return fail(ctx, PQ_ERR_STATE, "pq_step2_match_targets and pq_build_reference first");
     cudaSetDevice(ctx->P.device);
     ctx->comp3.clear();
+    Marks mk("step3");
     PeptideTable& R = ctx->reference;
     cudaStream_t st = ctx->st;
     // DatabaseInput.get_spectra2score(..., "max") (:637-669)
@@ -567,6 +616,7 @@ int32_t pq_step3_competitors(pq_ctx* ctx) {
             hj.push_back(J); cand += J.cand_count;
         }
     }
+    mk.mark("build jobs");
     std::vector<JobResult> hr(hj.size());
     std::vector<Hit> hh;
     if (!hj.empty()) {
@@ -574,7 +624,7 @@ int32_t pq_step3_competitors(pq_ctx* ctx) {
         CU(ctx->jobs.reserve(hj.size() * sizeof(Job)));
         CU(cudaMemcpyAsync(ctx->jobs.p, hj.data(), hj.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
         ctx->cnt.h2d_bytes += hj.size() * sizeof(Job);
-        int32_t rc = run_score(ctx, kJobCompetitors, (uint32_t)hj.size(), &R, R.rows.as<uint8_t>(), R.mass.as<double>(), (uint32_t)cand, 1);
+        int32_t rc = run_score(ctx, kJobCompetitors, (uint32_t)hj.size(), R.pred.as<int32_t>(), R.rows.as<uint8_t>(), R.mass.as<double>(), (uint32_t)cand, 1);
         if (rc) return rc;
         uint32_t nh = 0;
         CU(cudaMemcpyAsync(hr.data(), ctx->results.p, hj.size() * sizeof(JobResult), cudaMemcpyDeviceToHost, st));
@@ -584,6 +634,7 @@ int32_t pq_step3_competitors(pq_ctx* ctx) {
         if (nh) { CU(cudaMemcpyAsync(hh.data(), ctx->hits.p, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
         ctx->cnt.d2h_bytes += hj.size() * sizeof(JobResult) + (uint64_t)nh * sizeof(Hit) + 4;
     }
+    mk.mark("score + results d2h");
     struct Agg { int32_t matched = 0, better = 0; double best = -1.0; uint32_t best_row = 0xffffffffu; };
     std::vector<Agg> agg(specs.size());
     for (size_t j = 0; j < hj.size(); ++j) {
@@ -591,17 +642,22 @@ int32_t pq_step3_competitors(pq_ctx* ctx) {
         a.matched += (int32_t)hr[j].n_in_window; a.better += (int32_t)hr[j].n_better;
         if (hr[j].best_score > a.best) { a.best = hr[j].best_score; a.best_row = hr[j].best_cand; }     // isotope order, strict '<' (:63-65)
         ctx->cnt.pairs_step3 += hr[j].n_in_window;
-        ctx->cnt.score_algorithmic_bytes += (uint64_t)hr[j].n_in_window * (16ull * ctx->h_npeaks[(size_t)hj[j].spectrum] + 96ull);
+        uint64_t ab = (uint64_t)hr[j].n_in_window * (16ull * ctx->h_npeaks[(size_t)hj[j].spectrum] + 96ull);
+        ctx->cnt.score_algorithmic_bytes += ab; ctx->cnt.bytes_score_step[1] += ab;
     }
     // detail rows: better-or-equal competitors with score >= 20, plus the best competitor when its score > 0 (:71-76, :93-98)
     for (const Hit& h : hh) ctx->comp3.push_back({ctx->h_caller[(size_t)h.spectrum], (int32_t)h.cand, -1, -1, h.score, R.h_mass[h.cand]});
-    for (size_t si = 0; si < specs.size(); ++si) {
-        const Agg& a = agg[si];
-        if (a.best > 0 && a.best_row != 0xffffffffu) {
-            int32_t sp = ctx->h_caller[(size_t)specs[si].sorted];
-            bool dup = false;
-            for (const Hit& h : hh) if (h.spectrum == specs[si].sorted && h.cand == a.best_row) { dup = true; break; }
-            if (!dup) ctx->comp3.push_back({sp, (int32_t)a.best_row, -1, -1, a.best, R.h_mass[a.best_row]});
+    {
+        std::vector<uint64_t> seen(hh.size());
+        for (size_t i = 0; i < hh.size(); ++i) seen[i] = ((uint64_t)(uint32_t)hh[i].spectrum << 32) | hh[i].cand;
+        std::sort(seen.begin(), seen.end());
+        for (size_t si = 0; si < specs.size(); ++si) {
+            const Agg& a = agg[si];
+            if (a.best > 0 && a.best_row != 0xffffffffu) {
+                uint64_t key = ((uint64_t)(uint32_t)specs[si].sorted << 32) | a.best_row;
+                if (!std::binary_search(seen.begin(), seen.end(), key))
+                    ctx->comp3.push_back({ctx->h_caller[(size_t)specs[si].sorted], (int32_t)a.best_row, -1, -1, a.best, R.h_mass[a.best_row]});
+            }
         }
     }
     std::sort(ctx->comp3.begin(), ctx->comp3.end(), [](const pq_competitor& a, const pq_competitor& b) { return a.spectrum != b.spectrum ? a.spectrum < b.spectrum : a.ref_form < b.ref_form; });
@@ -612,6 +668,7 @@ int32_t pq_step3_competitors(pq_ctx* ctx) {
         p.total_db = a.matched; p.n_db = a.better;
         if (a.better >= 1) p.valid = 0;                                    // DatabaseInput.java:745-750
     }
+    mk.mark("aggregate");
     ctx->step_done = 3;
     return PQ_OK;
 }
@@ -622,6 +679,7 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
     if (ctx->step_done < 2) return fail(ctx, PQ_ERR_STATE, "pq_step2_match_targets first");
     cudaSetDevice(ctx->P.device);
     cudaStream_t st = ctx->st;
+    Marks mk("step4");
     PeptideTable& T = ctx->targets;
     // StatisticScoreCalc.run (:22-41): sequences with at least one still-valid PSM get shuffles
     std::vector<int32_t> slot_of_seq(T.seqs.size(), -1), slot_of_form(T.forms.size(), -1);
@@ -645,6 +703,7 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
     }
     ctx->h_sh_seqs = seqs; ctx->sh_slot_of_seq = slot_of_seq;
     ctx->h_kept.assign(seqs.size(), 0);
+    mk.mark("shuffle plans");
     if (seqs.empty()) { ctx->step_done = 4; return PQ_OK; }
     CU(ctx->sh_seqs.reserve(seqs.size() * sizeof(ShuffleSeq))); CU(ctx->sh_forms.reserve(forms.size() * sizeof(ShuffleForm)));
     CU(ctx->sh_raw.reserve((size_t)std::max(raw_rows, 1u) * kRowBytes)); CU(ctx->sh_kidx.reserve((size_t)std::max(raw_rows, 1u) * 4));
@@ -652,17 +711,20 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
     CU(cudaMemcpyAsync(ctx->sh_seqs.p, seqs.data(), seqs.size() * sizeof(ShuffleSeq), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->sh_forms.p, forms.data(), forms.size() * sizeof(ShuffleForm), cudaMemcpyHostToDevice, st));
     ctx->cnt.h2d_bytes += seqs.size() * sizeof(ShuffleSeq) + forms.size() * sizeof(ShuffleForm);
+    if (ctx->P.score_method == 2) { CU(ctx->sh_pred.reserve((size_t)std::max(out_rows, 1u) * 8)); CU(cudaMemsetAsync(ctx->sh_rows.p, 0, (size_t)out_rows * kRowBytes, st)); }
     {
         Timer t(ctx, &ctx->cnt.ms_shuffle);
         int k = launch_shuffles(ctx->sh_seqs.as<ShuffleSeq>(), (uint32_t)seqs.size(), ctx->sh_forms.as<ShuffleForm>(), (uint32_t)forms.size(),
                                 ctx->d_shufmods.as<ShuffleMods>(), ctx->sh_raw.as<uint8_t>(), ctx->sh_kidx.as<uint32_t>(), ctx->sh_kcnt.as<uint32_t>(),
                                 ctx->sh_rows.as<uint8_t>(), max_num, ctx->P.shuffle_seed, st);
+        if (ctx->P.score_method == 2) k += launch_predict(ctx->sh_rows.as<uint8_t>(), out_rows, ctx->d_mods.as<ModTable>(), ctx->P.itol, ctx->sh_pred.as<int32_t>(), st);
         ctx->cnt.other_kernel_launches += (uint64_t)k;
     }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(ctx->h_kept.data(), ctx->sh_kcnt.p, seqs.size() * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->cnt.d2h_bytes += seqs.size() * 4;
+    mk.mark("K2 shuffles");
     // one job per valid PSM (StatisticScoreWorker), ordered by form so consecutive CTAs share shuffle rows in L2
     std::vector<size_t> order;
     for (size_t i = 0; i < ctx->psms.size(); ++i) if (ctx->psms[i].valid) order.push_back(i);
@@ -675,17 +737,19 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
         J.mass = p.exp_mass; J.ref_score = p.score; J.charge = p.charge; J.iso = p.iso; J.spectrum = p.spectrum_sorted; J.aux = p.form;
         hj[k] = J;
     }
+    mk.mark("build jobs");
     std::vector<JobResult> hr(hj.size());
     if (!hj.empty()) {
         CU(ctx->jobs.reserve(hj.size() * sizeof(Job)));
         CU(cudaMemcpyAsync(ctx->jobs.p, hj.data(), hj.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
         ctx->cnt.h2d_bytes += hj.size() * sizeof(Job);
-        int32_t rc = run_score(ctx, kJobShuffles, (uint32_t)hj.size(), nullptr, ctx->sh_rows.as<uint8_t>(), nullptr, 1, 0);
+        int32_t rc = run_score(ctx, kJobShuffles, (uint32_t)hj.size(), ctx->sh_pred.as<int32_t>(), ctx->sh_rows.as<uint8_t>(), nullptr, 1, 0);
         if (rc) return rc;
         CU(cudaMemcpyAsync(hr.data(), ctx->results.p, hj.size() * sizeof(JobResult), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         ctx->cnt.d2h_bytes += hj.size() * sizeof(JobResult);
     }
+    mk.mark("score + results d2h");
     for (size_t k = 0; k < order.size(); ++k) {
         HostPsm& p = ctx->psms[order[k]];
         int32_t N = (int32_t)hj[k].cand_count;
@@ -693,7 +757,8 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
         p.n_random = (int32_t)hr[k].n_better; p.total_random = N;
         p.p_value = 1.0 * (p.n_random + 1) / (N + 1);
         ctx->cnt.pairs_step4 += hr[k].n_in_window;
-        ctx->cnt.score_algorithmic_bytes += (uint64_t)hr[k].n_in_window * (16ull * ctx->h_npeaks[(size_t)p.spectrum_sorted] + 96ull);
+        uint64_t ab = (uint64_t)hr[k].n_in_window * (16ull * ctx->h_npeaks[(size_t)p.spectrum_sorted] + 96ull);
+        ctx->cnt.score_algorithmic_bytes += ab; ctx->cnt.bytes_score_step[2] += ab;
     }
     ctx->step_done = 4;
     return PQ_OK;
@@ -737,6 +802,7 @@ static double tol_ppm_of(const HostPsm& p) { return (1.0e6) * (p.pep_mass - p.ex
 
 int32_t pq_rank_and_validate(pq_ctx* ctx) {
     if (!ctx) return PQ_ERR_BAD_ARG;
+    Marks mk("rank");
     PeptideTable& T = ctx->targets;
     // psms are sorted by (spectrum, form): rank inside each spectrum run (pg/RankPSM.java:107-149)
     size_t i = 0;
@@ -860,7 +926,11 @@ int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_ind
     L.mods = ctx->d_mods.as<ModTable>(); L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>(); L.row_pred = nullptr;
     L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>(); L.hit_capacity = 0;
     L.pair_score = d_score.as<double>(); L.pair_a = d_a.as<int32_t>(); L.pair_b = d_b.as<int32_t>(); L.max_blob_bytes = ctx->max_blob;
-    if (ctx->P.score_method == 2) return fail(ctx, PQ_ERR_UNSUPPORTED, "pq_score_pairs with MVH needs predicted-peak counts (not implemented yet)");
+    if (ctx->P.score_method == 2) {
+        CU(d_pred.reserve((size_t)n_pairs * 8));
+        ctx->cnt.other_kernel_launches += (uint64_t)launch_predict(d_rows.as<uint8_t>(), (uint32_t)n_pairs, ctx->d_mods.as<ModTable>(), ctx->P.itol, d_pred.as<int32_t>(), st);
+        L.row_pred = d_pred.as<int32_t>();
+    }
     ScoreConfig cfg = score_config(ctx, 0);
     {
         Timer t(ctx, &ctx->cnt.ms_score);

@@ -139,5 +139,7 @@ int launch_gather_peaks(int64_t n, const int32_t* order, const uint64_t* off_in,
                         const double* in_in, double* mz_out, double* in_out, cudaStream_t st);
 int launch_blob_sizes(const SpectraView& sp, const int32_t* list, int32_t n_list, uint64_t* sizes, cudaStream_t st);
 int launch_fix_job_blobs(Job* jobs, uint32_t n_jobs, const int32_t* prep_id, cudaStream_t st);
+// MVH predicted-peak counts per row (k4_predict.cu): out[2*row] for precursor charge 2, out[2*row+1] otherwise
+int launch_predict(const uint8_t* rows, uint32_t n_rows, const ModTable* mods, double itol, int32_t* out, cudaStream_t st);
 
 }  // namespace pq

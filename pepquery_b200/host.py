@@ -58,7 +58,7 @@ EXPORTS = ["pq_version", "pq_last_error", "pq_default_params", "pq_create", "pq_
            "pq_set_targets", "pq_get_target_forms", "pq_build_reference", "pq_get_reference_forms",
            "pq_step2_match_targets", "pq_step3_competitors", "pq_step4_shuffles", "pq_rank_and_validate",
            "pq_step5_ptm", "pq_get_psms", "pq_get_competitors", "pq_get_shuffles", "pq_score_pairs",
-           "pq_get_counters", "pq_reset_counters", "pq_parse_mgf"]
+           "pq_get_counters", "pq_reset_counters", "pq_event_record", "pq_event_elapsed_ms", "pq_parse_mgf"]
 
 
 def _p(a):
@@ -197,6 +197,14 @@ class Search:
 
     def reset_counters(self):
         self._ck(self.L.pq_reset_counters(self.h))
+
+    def event_record(self, which):
+        self._ck(self.L.pq_event_record(self.h, C.c_int32(which)))
+
+    def event_elapsed_ms(self):
+        ms = C.c_double()
+        self._ck(self.L.pq_event_elapsed_ms(self.h, C.byref(ms)))
+        return ms.value
 
     # -- the reference's names -------------------------------------------------------------------------------------
     def readMSMSfast(self, spectra, target_off, target_res):

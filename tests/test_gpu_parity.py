@@ -1,0 +1,389 @@
+"""GPU parity tests (run with -m gpu on the B200): the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs.  Bar: candidate sets, matched-ion counts, n_db/total_db, shuffle strings, shuffle win counts, ranks
+and accept/reject calls bit-exact; hyperscore / MVH within 1e-6 relative (tolerance of BASELINE.json north_star)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from pepquery_b200 import PepQueryError, Search, _abi, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REL = 1e-6      # north_star: "hyperscore/MVH within 1e-6 relative"
+INT_FIELDS = ("spectrum", "form", "count_b", "count_y", "isotope_error", "n_db", "total_db", "n_random", "total_random", "valid",
+              "rank", "confident")
+
+
+def run_gpu(params, sp, tgt, prot, steps=4):
+    g = Search(params)
+    g.load_spectra(sp); g.set_targets(*tgt)
+    g.step2()
+    if steps >= 3:
+        g.build_reference(*prot); g.step3()
+    if steps >= 4:
+        g.step4()
+    g.rank()
+    return g
+
+
+def run_oracle(params, sp, tgt, prot, steps=4, threads=8):
+    from oracle import pq_oracle
+    o = pq_oracle.Oracle(params, threads=threads)
+    o.load_spectra(sp); o.set_targets(*tgt)
+    o.step2()
+    if steps >= 3:
+        o.build_reference(*prot); o.step3()
+    if steps >= 4:
+        o.step4()
+    o.rank()
+    return o
+
+
+def assert_psms_equal(got, want):
+    assert len(got) == len(want), (len(got), len(want))
+    for f in INT_FIELDS:
+        assert np.array_equal(got[f], want[f]), (f, int(np.sum(got[f] != want[f])))
+    assert np.allclose(got["score"], want["score"], rtol=REL, atol=0)
+    for f in ("exp_mass", "pep_mass", "tol_ppm", "p_value"):
+        assert np.array_equal(got[f], want[f]), f
+
+
+def full_compare(params, sp, tgt, prot):
+    g = run_gpu(params, sp, tgt, prot)
+    o = run_oracle(params, sp, tgt, prot)
+    fo, nfo = o.target_forms(); fg, nfg = g.target_forms()
+    assert nfo == nfg and bytes(fo)[:nfo * C.sizeof(_abi.pq_form)] == bytes(fg)[:nfg * C.sizeof(_abi.pq_form)]
+    ro, nro = o.reference_forms(); rg, nrg = g.reference_forms()
+    assert nro == nrg and bytes(ro)[:nro * C.sizeof(_abi.pq_form)] == bytes(rg)[:nrg * C.sizeof(_abi.pq_form)]
+    got, want = g.psms(), o.psms()
+    assert_psms_equal(got, want)
+    co = np.sort(o.competitors(3), order=["spectrum", "ref_form"]); cg = np.sort(g.competitors(3), order=["spectrum", "ref_form"])
+    assert np.array_equal(co["spectrum"], cg["spectrum"]) and np.array_equal(co["ref_form"], cg["ref_form"])
+    assert np.allclose(co["score"], cg["score"], rtol=REL, atol=0)
+    c = g.counters()
+    assert [c.pairs_step2, c.pairs_step3, c.pairs_step4] == [int(x) for x in o.pairs()[:3]]      # same scorePeptide2Spectrum call counts
+    assert c.score_kernel_launches >= (3 if len(got) and got["valid"].sum() else 1)
+    return g, o, got
+
+
+@pytest.fixture(scope="module")
+def data():
+    prot = synth.proteins(600)
+    tgt = synth.targets(40)
+    sp = synth.spectra(1500, tgt, prot)
+    return prot, tgt, sp
+
+
+def test_default_search_hyperscore(data):
+    prot, tgt, sp = data
+    g, o, got = full_compare(_abi.default_params(n_random=200), sp, tgt, prot)
+    assert len(got) > 100 and got["confident"].sum() > 50 and (got["valid"] == 0).sum() >= 0
+    # the two arithmetic paths share the fdlibm log10 and the reference's summation order: expect identical bits
+    assert np.array_equal(got["score"], o.psms()["score"])
+
+
+def test_default_search_mvh(data):
+    prot, tgt, sp = data
+    g, o, got = full_compare(_abi.default_params(n_random=200, score_method=2), sp, tgt, prot)
+    assert len(got) > 50
+
+
+@pytest.mark.parametrize("over", [
+    dict(n_isotope=3, isotope=(0, 1, 2)),
+    dict(n_isotope=3, isotope=(-1, 0, 1)),
+    dict(tol=0.05, tol_ppm=0),
+    dict(tol=20.0),
+    dict(itol=0.05),
+    dict(itol=1.0),
+    dict(min_score=0.0),
+    dict(min_score=40.0),
+    dict(max_var_mods=1),
+    dict(max_missed=0, n_random=50),
+    dict(fast=0, hc=1),
+], ids=lambda d: ",".join("%s=%s" % kv for kv in d.items()))
+def test_parameter_variations(data, over):
+    prot, tgt, sp = data
+    over = dict(over)
+    iso = over.pop("isotope", None)
+    p = _abi.default_params(n_random=over.pop("n_random", 100), **over)
+    if iso:
+        for i, v in enumerate(iso):
+            p.isotope[i] = v
+    full_compare(p, sp, tgt, prot)
+
+
+@pytest.mark.parametrize("fixed,var", [
+    ((), ()),
+    ((_abi.CARBAMIDOMETHYL_C,), ()),
+    ((), (_abi.OXIDATION_M,)),
+    ((_abi.CARBAMIDOMETHYL_C,), (_abi.OXIDATION_M, dict(id=7, position=_abi.PQ_MOD_ANYWHERE, residues=b"STY", delta=79.96633052074999, neutral_loss=97.97689520445))),
+    ((_abi.CARBAMIDOMETHYL_C,), (_abi.ACETYL_NTERM, _abi.OXIDATION_M)),
+    ((_abi.CARBAMIDOMETHYL_C, dict(id=12, position=_abi.PQ_MOD_PEP_NTERM, residues=b"", delta=229.16293213472, neutral_loss=0.0)), (_abi.OXIDATION_M,)),
+    ((_abi.CARBAMIDOMETHYL_C,), (dict(id=28, position=_abi.PQ_MOD_PEP_NTERM_AA, residues=b"QE", delta=-17.02654910101, neutral_loss=0.0),)),
+], ids=["nomods", "fixC", "varM", "varM+phosphoSTY", "acetylNterm+oxM", "fixed-TMT-nterm", "pyro-QE-nterm-aa"])
+@pytest.mark.parametrize("method", [1, 2])
+def test_modification_sets(data, fixed, var, method):
+    prot, tgt, sp = data
+    p = _abi.default_params(fixed=fixed, var=var, n_random=60, score_method=method, max_var_mods=2)
+    full_compare(p, sp, tgt, prot)
+
+
+def test_golden_fixture_replay():
+    """Committed oracle outputs (tests/golden/oracle_vectors.json) — no oracle build needed on the box."""
+    gold = json.load(open(os.path.join(GOLD, "oracle_vectors.json")))
+    prot = synth.proteins(300); tgt = synth.targets(25); sp = synth.spectra(700, tgt, prot)
+    for method in (1, 2):
+        g = run_gpu(_abi.default_params(n_random=100, score_method=method), sp, tgt, prot)
+        ps = g.psms()
+        w = gold["method%d" % method]
+        for f in INT_FIELDS:
+            assert ps[f].tolist() == w[f], (method, f)
+        assert np.allclose(ps["score"], np.array(w["score"]), rtol=REL, atol=0)
+        assert ps["p_value"].tolist() == w["p_value"]
+        c = g.counters()
+        assert [c.pairs_step2, c.pairs_step3, c.pairs_step4] == w["pairs"][:3] and c.reference_forms == w["reference_forms"]
+
+
+def test_shuffle_streams_match_java_random(data):
+    """K2 replays java.util.Random(12457): identical shuffle strings in identical order (incl. dropped duplicates)."""
+    from oracle import pq_oracle
+    seqs = ["PEPTLDEK", "ELVLSQLGCK", "AAAAAAGK", "AAAAAGGK", "MCMKWYQR", "ACDEFGHLKLMNPQSTVWYR", "GGGGSSSSGGGGSSSSK",
+            "LLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLLMK", "ACDEFGHKLMNPQRSTVWYACDEFGHKLMNPQRSTVWYAAAAK"]
+    res = "".join(seqs).encode()
+    off = np.cumsum([0] + [len(s) for s in seqs]).astype(np.uint32)
+    # one spectrum per target built from its own fragments so that every target gets a valid PSM and therefore shuffles
+    tgt = (off, np.frombuffer(res, dtype=np.uint8).copy())
+    prot = synth.proteins(50)
+    sp = synth.spectra(len(seqs) * 60, tgt, prot, seed=5)
+    p = _abi.default_params(n_random=1000, min_score=5.0)
+    g = run_gpu(p, sp, tgt, prot)
+    o = run_oracle(p, sp, tgt, prot)
+    assert_psms_equal(g.psms(), o.psms())
+    fg, nfg = g.target_forms()
+    checked = 0
+    for ts, s in enumerate(seqs):
+        got = g.shuffles(ts, len(s))
+        if got:
+            assert got == pq_oracle.shuffles(s, 1000), s
+            checked += 1
+    assert checked >= 5
+
+
+def test_score_pairs_matches_oracle(data):
+    from oracle import pq_oracle
+    prot, tgt, sp = data
+    rng = np.random.default_rng(3)
+    for method in (1, 2):
+        p = _abi.default_params(score_method=method)
+        o = pq_oracle.Oracle(p, threads=8)
+        o.load_spectra(sp); o.set_targets(*tgt)
+        forms, nf = o.target_forms()
+        n = 3000
+        fi = rng.integers(0, nf, n); si = rng.integers(0, len(sp["prec_mz"]), n).astype(np.int32)
+        arr = (_abi.pq_form * n)()
+        for k in range(n):
+            f = forms[int(fi[k])]
+            if k % 3 == 0:      # a shuffled, re-modified version of the form (Step-4 style candidate)
+                s = list(f.seq.decode()); core = s[:-1]; rng.shuffle(core)
+                f = o.shuffle_form(int(fi[k]), "".join(core) + s[-1])
+            arr[k] = f
+        so, ao, bo = o.score_pairs(si, arr, n)
+        with Search(p) as g:
+            g.load_spectra(sp)
+            sg, ag, bg = g.score_pairs(si, arr, n)
+        assert np.array_equal(ao, ag) and np.array_equal(bo, bg)
+        assert np.allclose(so, sg, rtol=REL, atol=0)
+        assert (so > 0).sum() > n // 4
+
+
+def _csr(spectra):
+    """[(prec_mz, charge, [(mz, inten), ...]), ...] -> CSR dict"""
+    off = np.zeros(len(spectra) + 1, dtype=np.uint64)
+    mz, it = [], []
+    for i, (_, _, pk) in enumerate(spectra):
+        off[i + 1] = off[i] + len(pk)
+        mz += [p[0] for p in pk]; it += [p[1] for p in pk]
+    return dict(prec_mz=np.array([s[0] for s in spectra], dtype=np.float64), charge=np.array([s[1] for s in spectra], dtype=np.int32),
+                peak_off=off, mz=np.array(mz, dtype=np.float64), inten=np.array(it, dtype=np.float64))
+
+
+def test_edge_case_spectra(data):
+    """Ragged / degenerate spectra the reference's filters have special paths for."""
+    prot, tgt, base = data
+    rng = np.random.default_rng(11)
+    spectra = []
+    n0 = 300
+    for i in range(n0):          # real spectra, peaks in SHUFFLED file order, some with duplicated m/z and tied intensities
+        a, b = int(base["peak_off"][i]), int(base["peak_off"][i + 1])
+        pk = list(zip(base["mz"][a:b].tolist(), base["inten"][a:b].tolist()))
+        if i % 3 == 0:
+            pk += [(pk[j][0], pk[j][1] * (0.5 if j % 2 else 2.0)) for j in range(0, len(pk), 7)]     # duplicate m/z
+        if i % 4 == 0:
+            pk = [(m, float(int(v) // 50 * 50 + 50)) for m, v in pk]                                  # many equal intensities
+        if i % 5 == 0:
+            pk += [(round(pk[j][0] + 0.3, 4), pk[j][1]) for j in range(0, len(pk), 5)]                # equal-intensity neighbours inside one window
+        rng.shuffle(pk)
+        z = int(base["charge"][i])
+        if i % 11 == 0:
+            z = 1
+        if i % 13 == 0:
+            z = 5
+        mz0 = base["prec_mz"][i]
+        if z != int(base["charge"][i]):
+            m = base["prec_mz"][i] * base["charge"][i] - base["charge"][i] * 1.007276466812
+            mz0 = (m + z * 1.007276466812) / z
+        spectra.append((float(mz0), z, pk))
+    spectra.append((500.0, 2, []))                                                     # empty
+    spectra.append((500.0, 2, [(100.0 + k, 10.0) for k in range(10)]))                 # exactly min_peaks peaks: skipped
+    spectra.append((500.0, 2, [(100.0 + k, 10.0) for k in range(11)]))                 # just above, all < 150 except none: reload quirk path
+    spectra.append((800.0, 2, [(120.0 + 2 * k, 5.0 + k) for k in range(15)]))          # everything <= 150 -> reload
+    spectra.append((800.0, 2, [(800.0 + 0.01 * k, 5.0 + k) for k in range(15)]))       # everything inside the parent window
+    spectra.append((300.0, 2, [(2100.0 + 3 * k, 5.0 + k) for k in range(15)]))         # MVH: everything outside [200, 2000]
+    spectra.append((900.0, 2, [(250.0 + 30 * k, 1.0) for k in range(12)] + [(700.0, 1e6)]))   # one peak carries > 95 % of the TIC
+    sp = _csr(spectra)
+    # make sure a few of the degenerate precursors sit on a target mass so they are actually scored
+    toff, tres = tgt
+    for method in (1, 2):
+        p = _abi.default_params(n_random=80, score_method=method, min_score=0.0)
+        g = run_gpu(p, sp, tgt, prot)
+        o = run_oracle(p, sp, tgt, prot)
+        assert_psms_equal(g.psms(), o.psms())
+        assert g.counters().spectra_usable == sum(1 for s in spectra if len(s[2]) > 10)
+
+
+def test_degenerate_spectra_are_scored_like_the_reference():
+    """Degenerate peak lists placed exactly on a target's precursor mass, scored through pq_score_pairs."""
+    from oracle import pq_oracle
+    seq = "PEPTLDEKAGR"
+    tgt = (np.array([0, len(seq)], dtype=np.uint32), np.frombuffer(seq.encode(), dtype=np.uint8).copy())
+    p0 = _abi.default_params()
+    o = pq_oracle.Oracle(p0)
+    o.set_targets(*tgt)
+    forms, nf = o.target_forms()
+    mass = forms[0].mass
+    pmz = (mass + 2 * 1.007276466812) / 2
+    base = [(175.119, 50.0), (232.14, 20.0), (98.06, 30.0), (227.10, 40.0), (324.155, 35.0), (425.2, 10.0), (538.29, 60.0), (653.31, 15.0),
+            (782.36, 25.0), (910.45, 45.0), (981.49, 12.0), (1038.51, 33.0)]
+    cases = [
+        base,
+        [(m, 10.0) for m, _ in base],                                   # all intensities tied
+        [(100.0 + k, 10.0 + k) for k in range(14)],                     # all <= 150: low-mass filter empties the list -> reload
+        [(pmz + 0.01 * k, 5.0 + k) for k in range(14)],                 # all inside the parent-ion window -> reload
+        base + [(m, v) for m, v in base],                               # every peak duplicated
+        base + [(round(m + 0.5, 4), v) for m, v in base],               # equal-intensity pairs 0.5 apart (tie -> smaller error)
+        [(2100.0 + k, 5.0 + k) for k in range(14)],                     # outside the MVH range
+        [(250.0 + 30 * k, 1.0) for k in range(12)] + [(700.0, 1e6)],    # TIC filter drops everything
+    ]
+    sp = _csr([(pmz, 2, c) for c in cases] + [(pmz * 2 / 3 + 1.007276466812 / 3, 3, base), (mass + 1.007276466812, 1, base)])
+    n = len(sp["prec_mz"])
+    arr = (_abi.pq_form * n)(*[forms[0]] * n)
+    si = np.arange(n, dtype=np.int32)
+    for method in (1, 2):
+        p = _abi.default_params(score_method=method)
+        oo = pq_oracle.Oracle(p); oo.load_spectra(sp); oo.set_targets(*tgt)
+        so, ao, bo = oo.score_pairs(si, arr, n)
+        with Search(p) as g:
+            g.load_spectra(sp)
+            sg, ag, bg = g.score_pairs(si, arr, n)
+        assert np.array_equal(ao, ag) and np.array_equal(bo, bg), (method, ao, ag, bo, bg)
+        assert np.allclose(so, sg, rtol=REL, atol=0), (method, so, sg)
+
+
+def test_empty_inputs_and_call_order():
+    prot = synth.proteins(20); tgt = synth.targets(3)
+    empty = dict(prec_mz=np.zeros(0), charge=np.zeros(0, dtype=np.int32), peak_off=np.zeros(1, dtype=np.uint64), mz=np.zeros(0), inten=np.zeros(0))
+    with Search(_abi.default_params()) as g:
+        with pytest.raises(PepQueryError) as e:
+            g.step2()
+        assert e.value.code == _abi.PQ_ERR_STATE
+        g.load_spectra(empty); g.set_targets(*tgt)
+        assert g.step2() == 0
+        with pytest.raises(PepQueryError):
+            g.step3()                                   # no reference yet
+        g.build_reference(*prot); g.step3(); g.step4(); g.rank()
+        assert len(g.psms()) == 0
+    with Search(_abi.default_params()) as g:            # spectra but no targets
+        sp = synth.spectra(50, tgt, prot)
+        g.load_spectra(sp); g.set_targets(np.zeros(1, dtype=np.uint32), np.zeros(0, dtype=np.uint8))
+        assert g.step2() == 0
+    with pytest.raises(PepQueryError):                  # unsupported parameter is an error, not a silent fallback
+        Search(_abi.default_params(max_mods_per_aa=2))
+    big = dict(prec_mz=np.array([500.0]), charge=np.array([2], dtype=np.int32), peak_off=np.array([0, 5000], dtype=np.uint64),
+               mz=np.linspace(100, 2000, 5000), inten=np.ones(5000))
+    with Search(_abi.default_params()) as g:
+        with pytest.raises(PepQueryError) as e:
+            g.load_spectra(big)
+        assert e.value.code == _abi.PQ_ERR_UNSUPPORTED
+
+
+@pytest.fixture(scope="module")
+def large():
+    prot = synth.proteins(4000)
+    tgt = synth.targets(1500)
+    sp = synth.spectra(60000, tgt, prot)
+    return prot, tgt, sp
+
+
+def test_large_size_properties(large):
+    """Size-independent properties at a size the oracle would take minutes for."""
+    from pepquery_b200 import shard
+    prot, tgt, sp = large
+    p = _abi.default_params(n_random=1000)
+    g = run_gpu(p, sp, tgt, prot)
+    a = g.psms()
+    assert len(a) > 10000
+    # (1) idempotence: a second pass over the resident data gives identical records
+    g.step2(); g.step3(); g.step4(); g.rank()
+    b = g.psms()
+    assert a.tobytes() == b.tobytes()
+    # (2) internal consistency of the decisions (A.10)
+    ev = a["n_random"] >= 0
+    assert np.array_equal(a["valid"] == 1, a["n_db"] == 0)
+    assert np.array_equal(ev, a["valid"] == 1)
+    assert np.all(a["n_random"][ev] <= a["total_random"][ev]) and np.all(a["total_random"][ev] <= 1000)
+    assert np.array_equal(a["p_value"][ev], (a["n_random"][ev] + 1.0) / (a["total_random"][ev] + 1.0))
+    assert np.all(a["p_value"][~ev] == 100.0)
+    assert np.all(a["score"] > p.min_score) and np.all(a["n_db"] <= a["total_db"])
+    assert np.all(np.abs(a["tol_ppm"]) <= p.tol * (1 + 1e-12))
+    fg, nf = g.target_forms()
+    length = np.array([fg[int(f)].length for f in a["form"]])
+    thr = np.where(length <= 8, 0.05, 0.01)
+    assert np.array_equal(a["confident"] == 1, (a["rank"] == 1) & (a["n_db"] == 0) & (a["p_value"] <= thr))
+    # (3) permutation invariance: reorder the spectra, results follow the permutation
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(sp["prec_mz"]))
+    sub, gidx = shard.take_shard(sp, np.array([-np.inf, np.inf]), 0)
+    off = sp["peak_off"]
+    counts = (off[perm + 1] - off[perm]).astype(np.uint64)
+    noff = np.zeros(len(perm) + 1, dtype=np.uint64); np.cumsum(counts, out=noff[1:])
+    idx = np.concatenate([np.arange(int(off[s]), int(off[s + 1])) for s in perm])
+    sp2 = dict(prec_mz=sp["prec_mz"][perm].copy(), charge=sp["charge"][perm].copy(), peak_off=noff, mz=sp["mz"][idx].copy(), inten=sp["inten"][idx].copy())
+    g2 = run_gpu(p, sp2, tgt, prot)
+    c = g2.psms()
+    c["spectrum"] = perm[c["spectrum"]].astype(np.int32)
+    c = np.sort(c, order=["spectrum", "form"])
+    assert a.tobytes() == c.tobytes()
+    # (4) mass sharding: two shards searched separately give the union (what the N>1 bench does per rank)
+    mass = shard.precursor_mass(sp["prec_mz"], sp["charge"])
+    bounds = shard.shard_bounds(mass, 2)
+    parts = []
+    for r in range(2):
+        s_r, gi = shard.take_shard(sp, bounds, r)
+        gr = run_gpu(p, s_r, tgt, prot)
+        q = gr.psms()
+        q["spectrum"] = gi[q["spectrum"]].astype(np.int32)
+        parts.append(q)
+    u = np.sort(np.concatenate(parts), order=["spectrum", "form"])
+    assert a.tobytes() == u.tobytes()
+    # (5) a random sample of the PSMs against the oracle's scorePeptide2Spectrum
+    from oracle import pq_oracle
+    o = pq_oracle.Oracle(p, threads=8); o.load_spectra(sp); o.set_targets(*tgt)
+    fo, _ = o.target_forms()
+    pick = rng.choice(len(a), 400, replace=False)
+    arr = (_abi.pq_form * 400)(*[fo[int(a["form"][k])] for k in pick])
+    so, ao, bo = o.score_pairs(a["spectrum"][pick], arr, 400)
+    assert np.array_equal(ao, a["count_b"][pick]) and np.array_equal(bo, a["count_y"][pick])
+    assert np.allclose(so, a["score"][pick], rtol=REL, atol=0)
