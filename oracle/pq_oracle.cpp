@@ -1038,19 +1038,27 @@ static void step5(Ctx& C, const std::vector<pq_ptm>& ptms) {
         }
     });
     C.comp5.clear();
-    std::map<int, int> nptm;
+    std::map<int, int> t2i; for (size_t i = 0; i < titles.size(); ++i) t2i[titles[i]] = (int)i;
     for (size_t i = 0; i < titles.size(); ++i) {
         C.pairs[3] += res[i].pairs;
-        int n = 0;
-        for (auto& r : res[i].rows) { C.comp5.push_back(r); if (P.p.hc ? r.score >= spectra2score[titles[i]] : r.score > spectra2score[titles[i]]) n++; }
-        nptm[titles[i]] = n;
+        // ptm.txt rows: score >= spectra2score (ModificationDB.save :1660-1663; the extra "best row" is not a competitor)
+        for (auto& r : res[i].rows) if (r.score >= spectra2score[titles[i]]) C.comp5.push_back(r);
     }
-    for (auto& p : C.psms) { auto it = nptm.find(p.spectrum); p.n_ptm = it == nptm.end() ? -1 : it->second; }
-    // summariseResult compares against each PSM's own score (PSMT:920-943)
+    std::sort(C.comp5.begin(), C.comp5.end(), [](const pq_competitor& a, const pq_competitor& b) {
+        if (a.spectrum != b.spectrum) return a.spectrum < b.spectrum;
+        if (a.ref_form != b.ref_form) return a.ref_form < b.ref_form;
+        if (a.ptm != b.ptm) return a.ptm < b.ptm;
+        return a.ptm_site < b.ptm_site;
+    });
+    // PSMT.summariseResult (:920-1038): validated PSMs get n_ptm = #rows scoring > (>= with -hc) the PSM, others -1
     for (auto& p : C.psms) {
-        if (p.n_ptm < 0) continue;
+        p.n_ptm = -1;
+        int len = (int)C.target_forms[p.form].seq.size();
+        bool pv = (len <= 8 && p.p_value <= 0.05) || (len > 8 && p.p_value <= 0.01);
+        if (!(pv && p.n_db == 0 && p.rank == 1)) continue;
         int n = 0;
-        for (auto& r : C.comp5) if (r.spectrum == p.spectrum && (P.p.hc ? r.score >= p.sc.score : r.score > p.sc.score)) n++;
+        auto it = t2i.find(p.spectrum);
+        if (it != t2i.end()) for (auto& r : res[it->second].rows) if (P.p.hc ? r.score >= p.sc.score : r.score > p.sc.score) n++;
         p.n_ptm = n;
     }
     rank_and_validate(C);

@@ -1,0 +1,203 @@
+// k1_device.cuh — device-side pieces of the pair scorer shared by K1 (k1_score.cu) and the Step-5 kernel (k5_ptm.cu):
+// TMA/mbarrier helpers, the prepared-spectrum view, the annotator's peak pick, the fragment-ladder walk and the
+// precursor-window predicate.  See k1_score.cu for the reference citations.
+#pragma once
+#include "pq_internal.h"
+
+namespace pq {
+namespace dev {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct BlobView {
+    const double* pmz; const uint32_t* pinfo; const double* val; const uint16_t* cells;
+    uint32_t E; uint32_t nsurv; uint32_t flags; int32_t cls[4];
+};
+__device__ __forceinline__ BlobView view_blob(const uint8_t* b) {
+    const BlobHeader* h = reinterpret_cast<const BlobHeader*>(b);
+    BlobView v;
+    v.E = h->n_peaks; v.nsurv = h->n_survivors; v.flags = h->flags;
+    for (int c = 0; c < 4; ++c) v.cls[c] = h->cls_count[c];
+    uint32_t ep = h->n_pad;
+    v.pmz = reinterpret_cast<const double*>(b + sizeof(BlobHeader));
+    v.pinfo = reinterpret_cast<const uint32_t*>(b + sizeof(BlobHeader) + (size_t)ep * 8);
+    v.val = reinterpret_cast<const double*>(b + sizeof(BlobHeader) + (size_t)ep * 12);
+    v.cells = reinterpret_cast<const uint16_t*>(b + sizeof(BlobHeader) + (size_t)ep * 12 + kValSlots * 8);
+    return v;
+}
+
+// The annotator's peak pick for one theoretical m/z (A2-A4): most intense matchable peak with |mz - t| <= itol,
+// equal intensity -> smaller |error|.  Returns pinfo of the winner, 0 if none; *mz_out = its m/z.
+__device__ __forceinline__ uint32_t match_ion(const BlobView& B, double t, double itol, double itol_pad, double* mz_out) {
+    double lo = __dsub_rn(t, itol_pad);
+    uint32_t j = B.cells[cell_of(lo)];
+    uint32_t best = 0; double best_abs = 0.0;
+    for (; j < B.E; ++j) {
+        double m = B.pmz[j];
+        double err = __dsub_rn(m, t);
+        if (err > itol) break;
+        double ae = fabs(err);
+        if (ae <= itol) {
+            uint32_t info = B.pinfo[j];
+            uint32_t r = info >> 16, br = best >> 16;
+            if (r > br || (r == br && ae < best_abs)) { best = info; best_abs = ae; *mz_out = m; }
+        }
+    }
+    return best;
+}
+
+struct Extra { int32_t site; double delta; };   // Step 5: one extra modification (site -1 = none)
+
+struct PairScore { double score; int32_t a, b; };
+
+template <int BLOCK>
+__device__ __forceinline__ uint32_t row_byte(const uint32_t* codes, int idx) {
+    uint32_t w = codes[(idx >> 2) * BLOCK];
+    return (w >> ((idx & 3) * 8)) & 0xFFu;
+}
+
+// Walks the fragment ladder of one peptide row against the staged spectrum.
+// METHOD 1: hyperscore (count_b, count_y, sum of normalised intensities); METHOD 2: MVH class hits.
+template <int BLOCK, int METHOD>
+__device__ __forceinline__ PairScore score_pair(const uint32_t* codes /* this thread's column */, const BlobView& B,
+                                                const double* aa, const double* dl, const double* ntd, const double* ctd,
+                                                int z, double itol, double itol_pad, Extra ex,
+                                                const double* log10_fact, const double* ln_fact, int32_t predicted,
+                                                uint32_t* usedw /* MVH: this thread's column of the used bitmap */) {
+    const uint32_t head = codes[0];
+    const int L = (int)(head & 0xFF);
+    const int nch = z <= 1 ? 1 : z - 1;          // JMatch.java:398-407
+    uint64_t used = 0ull;
+    int ca = 0, cb = 0;
+    int key0 = 0, key1 = 0, key2 = 0;
+    double sum = 0.0;
+    if (METHOD == 2) for (int w = 0; w < 10; ++w) usedw[w * BLOCK] = 0u;
+
+    auto claim = [&](uint32_t info, double mz, bool is_b) {
+        uint32_t sid = info & 0xFFFu;
+        if (info == 0u || sid == kNoSurvivor) return;
+        if (METHOD == 1) {
+            uint64_t bit = 1ull << sid;
+            if (used & bit) return;
+            used |= bit;
+            if (is_b) ++ca; else ++cb;
+            sum = __dadd_rn(sum, B.val[sid]);
+        } else {
+            if (mz < 200.0 || mz > 2000.0) return;                    // MVHMatch.java:248-250
+            uint32_t w = usedw[(sid >> 5) * BLOCK], bit = 1u << (sid & 31);
+            if (w & bit) return;
+            usedw[(sid >> 5) * BLOCK] = w | bit;
+            uint32_t c = (info >> 12) & 3u;
+            key0 += c == 0; key1 += c == 1; key2 += c == 2;
+        }
+    };
+
+    // ---- b ions: forward sum, residue mass then its modification, N-term modification opens the sum ----
+    double acc = ntd[(head >> 8) & 0xFF];
+    if (ex.site == 0) acc = __dadd_rn(acc, ex.delta);
+    for (int k = 1; k <= L - 1; ++k) {
+        uint32_t code = row_byte<BLOCK>(codes, kRowHeader + k - 1);
+        acc = __dadd_rn(acc, aa[code]);
+        double d = dl[code];
+        if (d != 0.0) acc = __dadd_rn(acc, d);
+        if (k == ex.site) acc = __dadd_rn(acc, ex.delta);
+        for (int c = 1; c <= nch; ++c) {
+            if (c > 1 && c > k) break;                                 // A6 chargeValidated
+            double t = __ddiv_rn(__dadd_rn(acc, __dmul_rn((double)c, kProton)), (double)c);
+            double mz = 0.0;
+            uint32_t info = match_ion(B, t, itol, itol_pad, &mz);
+            claim(info, mz, true);
+        }
+    }
+    // ---- y ions: rewind sum from the C-terminus, + H2O ----
+    acc = ctd[(head >> 16) & 0xFF];
+    if (ex.site == L + 1) acc = __dadd_rn(acc, ex.delta);
+    for (int k = 1; k <= L - 1; ++k) {
+        int site = L - k + 1;
+        uint32_t code = row_byte<BLOCK>(codes, kRowHeader + site - 1);
+        acc = __dadd_rn(acc, aa[code]);
+        double d = dl[code];
+        if (d != 0.0) acc = __dadd_rn(acc, d);
+        if (site == ex.site) acc = __dadd_rn(acc, ex.delta);
+        double ym = __dadd_rn(acc, kWater);
+        for (int c = 1; c <= nch; ++c) {
+            if (c > 1 && c > k) break;
+            double t = __ddiv_rn(__dadd_rn(ym, __dmul_rn((double)c, kProton)), (double)c);
+            double mz = 0.0;
+            uint32_t info = match_ion(B, t, itol, itol_pad, &mz);
+            claim(info, mz, false);
+        }
+    }
+
+    PairScore r;
+    if (METHOD == 1) {
+        if (ca > 64) ca = 64;
+        if (cb > 64) cb = 64;
+        r.a = ca; r.b = cb;
+        if (ca == 0 && cb == 0) { r.score = 0.0; return r; }
+        double hs = jlog10(sum);
+        if (ca > 0 && cb > 0) hs = __dadd_rn(__dadd_rn(hs, log10_fact[ca]), log10_fact[cb]);
+        else if (cb > 0) hs = __dadd_rn(hs, log10_fact[cb]);
+        else hs = __dadd_rn(hs, log10_fact[ca]);
+        r.score = __dmul_rn(4.0, hs);
+    } else {
+        int matched = key0 + key1 + key2;
+        r.a = matched; r.b = predicted;
+        r.score = 0.0;
+        if (!(B.flags & 1u)) { r.a = 0; r.b = 0; return r; }     // fewer than 7 peaks survived: calcMVH returns before scoring
+        if (predicted <= 0) return r;
+        int key[4] = {key0, key1, key2, predicted - matched};
+        int N = (int)B.nsurv;
+        double mvh = 0.0; bool died = false;
+        for (int i = 0; i < 4; ++i) {
+            int n = B.cls[i], k = key[i];
+            if (n < 0 || k < 0) continue;
+            if (n < k) { died = true; continue; }
+            mvh = __dadd_rn(mvh, __dsub_rn(__dsub_rn(ln_fact[n], ln_fact[n - k]), ln_fact[k]));
+        }
+        int tb = B.cls[3] + N;
+        if (tb >= 0 && predicted >= 0) {
+            if (tb < predicted) died = true;
+            else mvh = __dsub_rn(mvh, __dsub_rn(__dsub_rn(ln_fact[tb], ln_fact[tb - predicted]), ln_fact[predicted]));
+        }
+        mvh = __dsub_rn(0.0, mvh);
+        r.score = died ? 0.0 : mvh;
+    }
+    return r;
+}
+
+// Precursor-window predicate exactly as DBSearchWorker.java:38-52 / FindCandidate...java:47-58:
+// bucket round(10*pepMass) within +-1 of round(10*mass) AND |pepMass - mass| (ppm of pepMass) <= tol.
+__device__ __forceinline__ bool in_window(double pm, double mass, long long va, const ScoreConfig& cfg) {
+    long long key = jround(__dmul_rn(pm, 10.0));
+    if (key < va - 1 || key > va + 1) return false;
+    double del = fabs(__dsub_rn(pm, mass));
+    if (cfg.tol_ppm) del = __ddiv_rn(__dmul_rn(__dmul_rn(1.0e6, 1.0), del), pm);
+    return del <= cfg.tol;
+}
+
+
+}  // namespace dev
+}  // namespace pq

@@ -1,0 +1,219 @@
+// k5_ptm.cu — K5: unrestricted-modification competitor search (Step 5).
+//
+// Replaces ModificationDB.getCandidateRefPeptidesFast (OpenModificationSearch/ModificationDB.java:993-1062) ->
+// ModPepQueryAndScoringWorker.do_score(Modification) (ModPepQueryAndScoringWorker.java:149-276) ->
+// ModificationDB.getCandidatePTMs(Peptide, Modification) (ModificationDB.java:263-326): for one validated spectrum, every
+// PTM specificity t (not protein-terminal, -250 <= delta <= 250), every reference form whose mass + delta_t sits in the
+// precursor window (bucket round(10*(precursor - delta_t)) +-1 and |ppm| <= tol), and every site of t on that form that
+// carries no modification yet, gives one candidate = the form plus t at that site; each is scored like any other pair.
+//
+// One CTA per validated spectrum (blob staged once by TMA).  Phase 1: one thread per PTM binary-searches the mass-sorted
+// reference table for its shifted window; a block scan turns the counts into a flat item list.  Phase 2: one thread per
+// (PTM, reference row) item checks the exact predicate and a residue-presence mask, then walks the free sites, scoring
+// each candidate with the shared pair scorer (k1_device.cuh, Extra{site, delta}).  Hyperscore only (MVH would need a
+// predicted-peak count per candidate).
+#include "k1_device.cuh"
+
+namespace pq {
+
+namespace {
+
+using namespace dev;
+
+constexpr int kPtmBlock = 256;
+constexpr int kMaxPtm = 2048;
+
+__device__ __forceinline__ uint32_t lower_bound_g(const double* a, uint32_t n, double v) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kPtmBlock)
+k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_scan[kPtmBlock / 32];
+    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_red_u[2][kPtmBlock / 32];
+    __shared__ int s_stop;
+    constexpr int BLOCK = kPtmBlock;
+
+    uint8_t* stage0 = smem;
+    uint32_t* codes_all = reinterpret_cast<uint32_t*>(smem + stage_bytes);            // [16][BLOCK]
+    double* s_aa = reinterpret_cast<double*>(codes_all + 16 * BLOCK);
+    double* s_dl = s_aa + kMaxCodes;
+    double* s_nt = s_dl + kMaxCodes;
+    double* s_ct = s_nt + kMaxTermCodes;
+    double* s_l10 = s_ct + kMaxTermCodes;                                               // [65]
+    uint32_t* s_lo = reinterpret_cast<uint32_t*>(s_l10 + 66);                           // [kMaxPtm]
+    uint32_t* s_off = s_lo + kMaxPtm;                                                   // [kMaxPtm + 1]
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kMaxCodes; i += BLOCK) { s_aa[i] = L.mods->aa[i]; s_dl[i] = L.mods->delta[i]; }
+    for (int i = tid; i < kMaxTermCodes; i += BLOCK) { s_nt[i] = L.mods->nterm[i]; s_ct[i] = L.mods->cterm[i]; }
+    for (int i = tid; i < 65; i += BLOCK) s_l10[i] = L.log10_fact[i];
+    if (tid == 0) { mbar_init(&s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    const double itol = cfg.itol, itol_pad = itol + 1e-6;
+    uint32_t* codes = codes_all + tid;
+    const bool plain_iso = L.n_isotope == 1 && L.isotope[0] == 0;
+
+    uint32_t it = 0;
+    for (uint32_t job = blockIdx.x; job < L.n_jobs; job += gridDim.x, ++it) {
+        const Job J = L.jobs[job];
+        if (tid == 0) {
+            uint32_t bytes = (uint32_t)(L.blob_off[J.blob + 1] - L.blob_off[J.blob]);
+            mbar_expect_tx(&s_bar, bytes);
+            tma_load_1d(stage0, L.blobs + L.blob_off[J.blob], bytes, &s_bar);
+            s_stop = 0;
+        }
+        mbar_wait(&s_bar, it & 1u);
+        __syncthreads();
+        const BlobView B = view_blob(stage0);
+        uint32_t n_pairs = 0, n_better = 0;
+
+        for (int ii = 0; ii < L.n_isotope; ++ii) {
+            double mono = J.mass;                                                       // CParameter.java:423-448
+            if (!plain_iso) mono = __dsub_rn(mono, __dmul_rn((double)L.isotope[ii], kIsotope));
+            // ---- phase 1: shifted window of every PTM ----
+            uint32_t local = 0;
+            for (uint32_t t = tid; t < (uint32_t)L.n_ptm; t += BLOCK) {
+                const pq_ptm P = L.ptms[t];
+                uint32_t lo = 0, cnt = 0;
+                if (P.position < PQ_MOD_PROT_NTERM && P.delta >= -250.0 && P.delta <= 250.0) {        // ModificationDB.java:1037-1042
+                    double c = __dsub_rn(mono, P.delta);
+                    double w = cfg.tol_ppm ? cfg.tol * 1e-6 * (fabs(mono) + 1.0) * 1.01 + 1e-6 : cfg.tol * 1.01 + 1e-6;
+                    if (w > 0.2) w = 0.2;
+                    lo = lower_bound_g(L.row_mass, L.n_rows, c - w);
+                    uint32_t hi = lower_bound_g(L.row_mass, L.n_rows, c + w);
+                    cnt = hi - lo;
+                }
+                s_lo[t] = lo; s_off[t] = cnt;
+            }
+            __syncthreads();
+            // ---- block exclusive scan over n_ptm counts (8 per thread) ----
+            {
+                const uint32_t per = (uint32_t)(L.n_ptm + BLOCK - 1) / BLOCK;
+                uint32_t b = tid * per, e = min(b + per, (uint32_t)L.n_ptm);
+                for (uint32_t t = b; t < e; ++t) local += s_off[t];
+                uint32_t incl = local;
+                for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += v; }
+                if ((tid & 31) == 31) s_scan[tid >> 5] = incl;
+                __syncthreads();
+                uint32_t base = 0;
+                for (int w = 0; w < (tid >> 5); ++w) base += s_scan[w];
+                uint32_t run = base + incl - local;
+                for (uint32_t t = b; t < e; ++t) { uint32_t c = s_off[t]; s_off[t] = run; run += c; }
+                if (tid == BLOCK - 1) { s_off[L.n_ptm] = run; s_total = run; }
+                __syncthreads();
+            }
+            const uint32_t total = s_total;
+            // ---- phase 2: one thread per (PTM, reference row) ----
+            for (uint32_t i0 = 0; i0 < total; i0 += BLOCK) {
+                if (cfg.fast && s_stop) break;
+                uint32_t i = i0 + tid;
+                if (i >= total) continue;
+                uint32_t lo = 0, hi = (uint32_t)L.n_ptm;                                 // last t with off[t] <= i
+                while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
+                const uint32_t t = lo;
+                const pq_ptm P = L.ptms[t];
+                const uint32_t row = s_lo[t] + (i - s_off[t]);
+                // exact window (ModPepQueryAndScoringWorker.java:165-203)
+                const double refm = __ldg(L.row_mass + row);
+                const long long ind = jround(__dmul_rn(10.0, __dsub_rn(mono, P.delta)));
+                const long long key = jround(__dmul_rn(refm, 10.0));
+                if (key < ind - 1 || key > ind + 1) continue;
+                const double pep_mass = __dadd_rn(refm, P.delta);
+                double del = cfg.tol_ppm ? __ddiv_rn(__dmul_rn(1.0e6, __dsub_rn(pep_mass, mono)), pep_mass) : __dsub_rn(pep_mass, mono);
+                if (!(fabs(del) <= cfg.tol)) continue;
+                const uint32_t rcode = P.residue ? (uint32_t)(P.residue - 'A') : 0xFFu;
+                if (P.residue && !((__ldg(L.row_mask + row) >> rcode) & 1u)) continue;   // :207-209 residue absent
+                const uint4* rp = reinterpret_cast<const uint4*>(L.rows + (size_t)row * kRowBytes);
+                uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+                codes[0 * BLOCK] = q0.x; codes[1 * BLOCK] = q0.y; codes[2 * BLOCK] = q0.z; codes[3 * BLOCK] = q0.w;
+                codes[4 * BLOCK] = q1.x; codes[5 * BLOCK] = q1.y; codes[6 * BLOCK] = q1.z; codes[7 * BLOCK] = q1.w;
+                codes[8 * BLOCK] = q2.x; codes[9 * BLOCK] = q2.y; codes[10 * BLOCK] = q2.z; codes[11 * BLOCK] = q2.w;
+                codes[12 * BLOCK] = q3.x; codes[13 * BLOCK] = q3.y; codes[14 * BLOCK] = q3.z; codes[15 * BLOCK] = q3.w;
+                const int Lp = (int)(q0.x & 0xFF);
+                const uint32_t ntc = (q0.x >> 8) & 0xFF, ctc = (q0.x >> 16) & 0xFF;
+                // sites of the PTM on this form that carry nothing yet (ModificationDB.java:268-292), ascending
+                int s_begin, s_end;
+                switch (P.position) {
+                    case PQ_MOD_ANYWHERE: s_begin = 1; s_end = Lp; break;
+                    case PQ_MOD_PEP_NTERM: s_begin = 0; s_end = 0; break;
+                    case PQ_MOD_PEP_CTERM: s_begin = Lp + 1; s_end = Lp + 1; break;
+                    case PQ_MOD_PEP_NTERM_AA: s_begin = 1; s_end = 1; break;
+                    default: s_begin = Lp; s_end = Lp; break;                            // PQ_MOD_PEP_CTERM_AA
+                }
+                for (int site = s_begin; site <= s_end; ++site) {
+                    bool ok;
+                    if (site == 0) ok = ntc == 0;
+                    else if (site == Lp + 1) ok = ctc == 0;
+                    else { uint32_t code = row_byte<BLOCK>(codes, kRowHeader + site - 1); ok = P.residue ? code == rcode : code < 26u; }
+                    if (!ok) continue;
+                    Extra ex; ex.site = site; ex.delta = P.delta;
+                    PairScore ps = score_pair<BLOCK, 1>(codes, B, s_aa, s_dl, s_nt, s_ct, J.charge, itol, itol_pad, ex, s_l10, nullptr, 0, nullptr);
+                    ++n_pairs;
+                    bool better = cfg.hc ? ps.score >= J.ref_score : ps.score > J.ref_score;      // :239-259, PSMT:920-943
+                    if (better) { ++n_better; if (cfg.fast) s_stop = 1; }
+                    if (ps.score >= cfg.min_score && ps.score >= J.ref_score) {                    // rows of ptm.txt (ModificationDB.java:1660-1663)
+                        uint32_t slot = atomicAdd(L.hit_count, 1u);
+                        if (slot < L.hit_capacity) {
+                            Hit h; h.spectrum = J.spectrum; h.cand = row; h.score = ps.score; h.mass = pep_mass;
+                            h.count_a = ps.a; h.count_b = ps.b; h.iso = plain_iso ? 0 : L.isotope[ii]; h.aux = (int32_t)((t << 8) | (uint32_t)site);
+                            h.blob = J.blob; h.pad = 0;
+                            L.hits[slot] = h;
+                        }
+                    }
+                    if (cfg.fast && better) break;
+                }
+            }
+            __syncthreads();
+        }
+        for (int o = 16; o > 0; o >>= 1) { n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, o); n_better += __shfl_xor_sync(0xffffffffu, n_better, o); }
+        if ((tid & 31) == 0) { s_red_u[0][tid >> 5] = n_pairs; s_red_u[1][tid >> 5] = n_better; }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t a = 0, b = 0;
+            for (int w = 0; w < BLOCK / 32; ++w) { a += s_red_u[0][w]; b += s_red_u[1][w]; }
+            JobResult R; R.n_in_window = a; R.n_better = b; R.best_score = -1.0; R.best_cand = 0xFFFFFFFFu; R.pad = 0;
+            L.results[job] = R;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_row_masks(const uint8_t* __restrict__ rows, uint32_t n_rows, uint32_t* __restrict__ mask) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const uint8_t* row = rows + (size_t)r * kRowBytes;
+    uint32_t m = 0; int L = row[0];
+    for (int k = 0; k < L; ++k) { uint32_t c = row[kRowHeader + k]; if (c < 26u) m |= 1u << c; }     // unmodified residues only
+    mask[r] = m;
+}
+
+}  // namespace
+
+int launch_row_masks(const uint8_t* rows, uint32_t n_rows, uint32_t* mask, cudaStream_t st) {
+    if (n_rows == 0) return 0;
+    k_row_masks<<<(n_rows + 255) / 256, 256, 0, st>>>(rows, n_rows, mask);
+    return 1;
+}
+
+int launch_ptm(const PtmLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
+    if (L.n_jobs == 0 || L.n_ptm == 0) return 0;
+    uint32_t stage = (L.max_blob_bytes + 127u) & ~127u;
+    size_t smem = (size_t)stage + (size_t)16 * kPtmBlock * 4 + (size_t)(2 * kMaxCodes + 2 * kMaxTermCodes + 66) * 8 + (size_t)(2 * kMaxPtm + 2) * 4;
+    cudaFuncSetAttribute(k5_ptm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k5_ptm_kernel, kPtmBlock, smem);
+    if (per_sm < 1) per_sm = 1;
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    uint32_t grid = (uint32_t)(sms * per_sm);
+    if (grid > L.n_jobs) grid = L.n_jobs;
+    k5_ptm_kernel<<<grid, kPtmBlock, smem, st>>>(L, cfg, stage);
+    return 1;
+}
+
+}  // namespace pq

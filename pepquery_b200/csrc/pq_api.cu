@@ -57,7 +57,8 @@ struct DevBuf {
 struct PeptideTable {               // a mass-sorted candidate table resident on the device
     std::vector<std::string> seqs;  // parent sequences
     std::vector<FormRec> forms;     // mass ascending
-    DevBuf rows, mass, pred;
+    DevBuf rows, mass, pred, mask;
+    bool have_mask = false;
     std::vector<double> h_mass;     // host copy for range searches
     size_t n() const { return forms.size(); }
 };
@@ -856,7 +857,107 @@ int32_t pq_get_competitors(pq_ctx* ctx, int32_t step, pq_competitor* out, int64_
     return PQ_OK;
 }
 
-int32_t pq_step5_ptm(pq_ctx* ctx, int32_t, const pq_ptm*) { return fail(ctx, PQ_ERR_UNSUPPORTED, "Step 5 (unrestricted modification search) is not implemented yet"); }
+int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms) {
+    if (!ctx || n_ptm < 0 || (n_ptm > 0 && !ptms)) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
+    if (ctx->step_done < 3 || !ctx->have_reference) return fail(ctx, PQ_ERR_STATE, "run Steps 2-4 and pq_build_reference first");
+    if (ctx->P.score_method != 1) return fail(ctx, PQ_ERR_UNSUPPORTED, "Step 5 is implemented for hyperscore only");
+    if (n_ptm > 2048) return fail(ctx, PQ_ERR_UNSUPPORTED, "more than 2048 PTM specificities");
+    cudaSetDevice(ctx->P.device);
+    cudaStream_t st = ctx->st;
+    Marks mk("step5");
+    int32_t rc = pq_rank_and_validate(ctx);       // doPTMValidation reads psm_rank.txt (ModificationDB.java:1340-1384)
+    if (rc) return rc;
+    ctx->comp5.clear();
+    PeptideTable& R = ctx->reference; PeptideTable& T = ctx->targets;
+    // spectra to validate: PSMs with passed_psm_validation(len, p, n_db, rank); target = MIN score per spectrum (:1369-1383)
+    std::vector<size_t> val;
+    for (size_t i = 0; i < ctx->psms.size(); ++i) {
+        HostPsm& p = ctx->psms[i];
+        p.n_ptm = -1;
+        int len = (int)T.seqs[(size_t)T.forms[(size_t)p.form].seq].size();
+        bool pv = (len <= 8 && p.p_value <= 0.05) || (len > 8 && p.p_value <= 0.01);
+        if (pv && p.n_db == 0 && p.rank == 1) val.push_back(i);
+    }
+    std::vector<Job> hj; std::vector<size_t> first_psm;
+    for (size_t k = 0; k < val.size(); ++k) {           // psms are sorted by spectrum
+        const HostPsm& p = ctx->psms[val[k]];
+        if (!hj.empty() && hj.back().spectrum == p.spectrum_sorted) { if (p.score < hj.back().ref_score) hj.back().ref_score = p.score; continue; }
+        Job J; J.blob = p.blob; J.cand_begin = 0; J.cand_count = 0; J.out = (uint32_t)hj.size(); J.mass = ctx->h_mass[(size_t)p.spectrum_sorted];
+        J.ref_score = p.score; J.charge = p.charge; J.iso = 0; J.spectrum = p.spectrum_sorted; J.aux = 0;
+        hj.push_back(J);
+    }
+    std::stable_sort(hj.begin(), hj.end(), [](const Job& a, const Job& b) { return a.spectrum < b.spectrum; });   // mass order: neighbouring CTAs share table rows in L2
+    for (size_t j = 0; j < hj.size(); ++j) hj[j].out = (uint32_t)j;
+    std::vector<JobResult> hr(hj.size());
+    std::vector<Hit> hh;
+    if (!hj.empty() && n_ptm > 0 && R.n() > 0) {
+        if (!R.have_mask) {
+            CU(R.mask.reserve(R.n() * 4));
+            ctx->cnt.other_kernel_launches += (uint64_t)launch_row_masks(R.rows.as<uint8_t>(), (uint32_t)R.n(), R.mask.as<uint32_t>(), st);
+            R.have_mask = true;
+        }
+        DevBuf d_ptm;
+        CU(d_ptm.reserve((size_t)n_ptm * sizeof(pq_ptm)));
+        CU(cudaMemcpyAsync(d_ptm.p, ptms, (size_t)n_ptm * sizeof(pq_ptm), cudaMemcpyHostToDevice, st));
+        CU(ctx->jobs.reserve(hj.size() * sizeof(Job)));
+        CU(cudaMemcpyAsync(ctx->jobs.p, hj.data(), hj.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
+        CU(ctx->results.reserve(hj.size() * sizeof(JobResult)));
+        CU(ctx->hit_count.reserve(64));
+        ctx->cnt.h2d_bytes += hj.size() * sizeof(Job) + (size_t)n_ptm * sizeof(pq_ptm);
+        uint32_t cap = (uint32_t)std::max<size_t>(1u << 20, hj.size() * 64);
+        for (int attempt = 0; attempt < 4; ++attempt) {
+            CU(ctx->hits.reserve((size_t)cap * sizeof(Hit)));
+            CU(cudaMemsetAsync(ctx->hit_count.p, 0, 4, st));
+            PtmLaunch L; memset(&L, 0, sizeof L);
+            L.jobs = ctx->jobs.as<Job>(); L.n_jobs = (uint32_t)hj.size(); L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>();
+            L.rows = R.rows.as<uint8_t>(); L.row_mass = R.mass.as<double>(); L.row_mask = R.mask.as<uint32_t>(); L.n_rows = (uint32_t)R.n();
+            L.ptms = d_ptm.as<pq_ptm>(); L.n_ptm = n_ptm; L.n_isotope = ctx->P.n_isotope;
+            for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) L.isotope[i] = ctx->P.isotope[i];
+            L.mods = ctx->d_mods.as<ModTable>(); L.log10_fact = ctx->d_l10.as<double>();
+            L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>(); L.hit_capacity = cap;
+            L.max_blob_bytes = ctx->max_blob;
+            ScoreConfig cfg = score_config(ctx, 1);
+            double ms = 0.0;
+            { Timer t(ctx, &ms); ctx->cnt.score_kernel_launches += (uint64_t)launch_ptm(L, cfg, st); }
+            ctx->cnt.ms_score += ms; ctx->cnt.ms_score_step[3] += ms;
+            CU(cudaGetLastError());
+            uint32_t nh = 0;
+            CU(cudaMemcpyAsync(&nh, ctx->hit_count.p, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(hr.data(), ctx->results.p, hj.size() * sizeof(JobResult), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (nh > cap) { cap = nh + 1024; continue; }       // rare: more rows than reserved, run again with room
+            hh.resize(nh);
+            if (nh) { CU(cudaMemcpyAsync(hh.data(), ctx->hits.p, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
+            ctx->cnt.d2h_bytes += hj.size() * sizeof(JobResult) + (uint64_t)nh * sizeof(Hit) + 4;
+            break;
+        }
+    }
+    mk.mark("score + results d2h");
+    std::unordered_map<int32_t, size_t> at;
+    for (size_t j = 0; j < hj.size(); ++j) {
+        at[hj[j].spectrum] = j;
+        ctx->cnt.pairs_step5 += hr[j].n_in_window;
+        uint64_t ab = (uint64_t)hr[j].n_in_window * (16ull * ctx->h_npeaks[(size_t)hj[j].spectrum] + 96ull);
+        ctx->cnt.score_algorithmic_bytes += ab; ctx->cnt.bytes_score_step[3] += ab;
+    }
+    for (const Hit& h : hh) ctx->comp5.push_back({ctx->h_caller[(size_t)h.spectrum], (int32_t)h.cand, (int32_t)((uint32_t)h.aux >> 8), (int32_t)(h.aux & 0xFF), h.score, h.mass});
+    std::sort(ctx->comp5.begin(), ctx->comp5.end(), [](const pq_competitor& a, const pq_competitor& b) {
+        if (a.spectrum != b.spectrum) return a.spectrum < b.spectrum;
+        if (a.ref_form != b.ref_form) return a.ref_form < b.ref_form;
+        if (a.ptm != b.ptm) return a.ptm < b.ptm;
+        return a.ptm_site < b.ptm_site;
+    });
+    // PSMT.summariseResult (:920-1038): a validated PSM gets n_ptm = #PTM rows scoring > (>= with -hc) its score, others -1
+    for (size_t i : val) {
+        HostPsm& p = ctx->psms[i];
+        auto it = at.find(p.spectrum_sorted);
+        if (it == at.end()) { p.n_ptm = 0; continue; }
+        if (p.score == hj[it->second].ref_score) p.n_ptm = (int32_t)hr[it->second].n_better;
+        else { int n = 0; for (const Hit& h : hh) if (h.spectrum == p.spectrum_sorted && (ctx->P.hc ? h.score >= p.score : h.score > p.score)) ++n; p.n_ptm = n; }
+    }
+    ctx->step_done = 5;
+    return pq_rank_and_validate(ctx);
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_index, const pq_form* forms, double* score,

@@ -139,6 +139,19 @@ int launch_gather_peaks(int64_t n, const int32_t* order, const uint64_t* off_in,
                         const double* in_in, double* mz_out, double* in_out, cudaStream_t st);
 int launch_blob_sizes(const SpectraView& sp, const int32_t* list, int32_t n_list, uint64_t* sizes, cudaStream_t st);
 int launch_fix_job_blobs(Job* jobs, uint32_t n_jobs, const int32_t* prep_id, cudaStream_t st);
+// Step 5 (k5_ptm.cu): one job per validated spectrum; candidates are enumerated inside the kernel
+struct PtmLaunch {
+    const Job* jobs; uint32_t n_jobs;                      // mass = precursor neutral mass, ref_score = target PSM score
+    const uint8_t* blobs; const uint64_t* blob_off;
+    const uint8_t* rows; const double* row_mass; const uint32_t* row_mask; uint32_t n_rows;   // reference table
+    const pq_ptm* ptms; int32_t n_ptm;
+    int32_t n_isotope; int32_t isotope[PQ_MAX_ISOTOPE];
+    const ModTable* mods; const double* log10_fact;
+    JobResult* results; Hit* hits; uint32_t* hit_count; uint32_t hit_capacity;
+    uint32_t max_blob_bytes;
+};
+int launch_ptm(const PtmLaunch& L, const ScoreConfig& cfg, cudaStream_t st);
+int launch_row_masks(const uint8_t* rows, uint32_t n_rows, uint32_t* mask, cudaStream_t st);
 // MVH predicted-peak counts per row (k4_predict.cu): out[2*row] for precursor charge 2, out[2*row+1] otherwise
 int launch_predict(const uint8_t* rows, uint32_t n_rows, const ModTable* mods, double itol, int32_t* out, cudaStream_t st);
 

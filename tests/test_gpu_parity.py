@@ -131,6 +131,106 @@ def test_modification_sets(data, fixed, var, method):
     full_compare(p, sp, tgt, prot)
 
 
+@pytest.mark.parametrize("over", [dict(), dict(hc=1), dict(n_isotope=2, isotope=(0, 1)), dict(fast=1)],
+                         ids=["default", "hc", "isotope01", "fast"])
+def test_step5_unrestricted_modification_search(data, over):
+    """Step 5 (config C4): every Unimod specificity x shifted precursor window x free site, n_ptm and accept/reject."""
+    from pepquery_b200 import unimod
+    prot, tgt, sp = data
+    over = dict(over)
+    iso = over.pop("isotope", None)
+    p = _abi.default_params(n_random=100, **over)
+    if iso:
+        for i, v in enumerate(iso):
+            p.isotope[i] = v
+    ptms = unimod.load_ptms()
+    assert 850 <= len(ptms) <= 1100          # SURVEY.md a12: 997 non-substitution specificities within +-250 Da
+    g = run_gpu(p, sp, tgt, prot); g.step5(ptms)
+    o = run_oracle(p, sp, tgt, prot); o.step5(ptms)
+    got, want = g.psms(), o.psms()
+    if p.fast:                                # only the accept/reject call is defined in fast mode (SURVEY.md H6)
+        assert np.array_equal(got["n_ptm"] > 0, want["n_ptm"] > 0) and np.array_equal(got["n_ptm"] < 0, want["n_ptm"] < 0)
+        assert np.array_equal(got["confident"], want["confident"])
+        return
+    assert np.array_equal(got["n_ptm"], want["n_ptm"])
+    assert_psms_equal(got, want)
+    co, cg = o.competitors(5), g.competitors(5)
+    assert len(co) == len(cg)
+    for f in ("spectrum", "ref_form", "ptm", "ptm_site"):
+        assert np.array_equal(co[f], cg[f]), f
+    assert np.allclose(co["score"], cg["score"], rtol=REL, atol=0) and np.array_equal(co["pep_mass"], cg["pep_mass"])
+    assert g.counters().pairs_step5 == int(o.pairs()[3]) > 100000
+    assert (got["n_ptm"] >= 0).sum() > 50
+
+
+RES_MASS = {"G": 57.02146372057, "A": 71.03711378471, "S": 87.03202840427, "P": 97.05276384885, "V": 99.06841391299, "T": 101.04767846841,
+            "C": 103.00918478471 + 57.02146372057, "L": 113.08406397713, "N": 114.04292744114, "D": 115.02694302383, "Q": 128.05857750528,
+            "K": 128.094963014, "E": 129.04259308797, "M": 131.04048491299, "H": 137.05891185845, "F": 147.06841391299, "R": 156.1011110236,
+            "Y": 163.06332853255, "W": 186.07931294986}
+
+
+def _spectrum_of(seq, rng, z=2):
+    """b/y (c=1) peaks of a plain sequence (C carbamidomethylated) + noise, like pepquery_b200.synth."""
+    m = [RES_MASS[c] for c in seq]
+    M = 18.0105646837 + sum(m)
+    pk = []
+    for k in range(1, len(seq)):
+        for mass in (sum(m[:k]), sum(m[len(seq) - k:]) + 18.0105646837):
+            pk.append((round(mass + 1.007276466812 + rng.normal(0, 0.05), 4), round(float(np.exp(8 + rng.normal())), 2)))
+    for _ in range(60):
+        pk.append((round(float(rng.uniform(100, min(M, 2000))), 4), round(float(np.exp(6 + rng.normal())), 2)))
+    pk = sorted(dict(pk).items())
+    return ((M + z * 1.007276466812) / z, z, pk)
+
+
+def test_step5_finds_a_better_modified_reference_peptide():
+    """A target that is a corrupted reading of a deamidated reference peptide: Steps 2-4 accept it, Step 5 must reject it
+    (n_ptm >= 1, confident = No) and list the PTM competitor — the purpose of PepQuery's unrestricted-modification filter."""
+    from oracle import pq_oracle
+    from pepquery_b200 import unimod
+    rng = np.random.default_rng(42)
+    prot = synth.proteins(400)
+    p = _abi.default_params(n_random=200)
+    # reference peptides with an internal N followed by a different residue
+    o0 = pq_oracle.Oracle(p)
+    dummy = _csr([(500.0, 2, [(100.0 + k, 1.0) for k in range(12)])])
+    o0.load_spectra(dummy); o0.set_targets(np.array([0, 8], dtype=np.uint32), np.frombuffer(b"PEPTLDEK", dtype=np.uint8).copy()); o0.step2()
+    o0.build_reference(*prot)
+    refs = [s for s in o0.reference_sequences() if 10 <= len(s) <= 16 and "M" not in s]
+    targets, spectra = [], []
+    for s in refs:
+        i = next((k for k in range(2, len(s) - 3) if s[k] == "N" and s[k + 1] not in "ND"), None)
+        if i is None:
+            continue
+        true_pep = s[:i] + "D" + s[i + 1:]                           # reference peptide, deamidated at N_i
+        tgt_pep = true_pep[:i] + true_pep[i + 1] + true_pep[i] + true_pep[i + 2:]   # the "novel" reading: two residues swapped
+        targets.append(tgt_pep); spectra.append(_spectrum_of(true_pep, rng))
+        if len(targets) == 25:
+            break
+    assert len(targets) >= 10
+    res = "".join(targets).encode()
+    tgt = (np.cumsum([0] + [len(t) for t in targets]).astype(np.uint32), np.frombuffer(res, dtype=np.uint8).copy())
+    sp = _csr(spectra)
+    ptms = unimod.load_ptms()
+    g = run_gpu(p, sp, tgt, prot); g.step5(ptms)
+    o = run_oracle(p, sp, tgt, prot); o.step5(ptms)
+    got, want = g.psms(), o.psms()
+    assert np.array_equal(got["n_ptm"], want["n_ptm"])
+    assert_psms_equal(got, want)
+    co, cg = o.competitors(5), g.competitors(5)
+    assert len(co) == len(cg) > 0
+    for f in ("spectrum", "ref_form", "ptm", "ptm_site"):
+        assert np.array_equal(co[f], cg[f]), f
+    assert np.allclose(co["score"], cg["score"], rtol=REL, atol=0)
+    validated = got["n_ptm"] >= 0
+    assert validated.sum() >= 5
+    assert (got["n_ptm"][validated] >= 1).sum() >= 5                 # the deamidated reference peptide beats the target
+    assert np.all(got["confident"][got["n_ptm"] != 0] == 0)
+    # the winning competitor is Deamidated (Unimod record 7, +0.984016) on the N of the reference peptide
+    deam = {k for k, t in enumerate(ptms) if t.id == 7 and t.residue == b"N"}
+    assert len(deam) == 1 and any(int(r["ptm"]) in deam for r in cg)
+
+
 def test_golden_fixture_replay():
     """Committed oracle outputs (tests/golden/oracle_vectors.json) — no oracle build needed on the box."""
     gold = json.load(open(os.path.join(GOLD, "oracle_vectors.json")))
