@@ -35,32 +35,16 @@ struct Marks {
     ~Marks() { if (on) fprintf(stderr, "[pq] %s: total %8.3f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
 };
 
-struct DevBuf {
-    void* p = nullptr; size_t cap = 0;
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { if (p) cudaFree(p); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; } return *this; }
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t reserve(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
 struct PeptideTable {               // a mass-sorted candidate table resident on the device
     std::vector<std::string> seqs;  // parent sequences
     std::vector<FormRec> forms;     // mass ascending
     DevBuf rows, mass, pred, mask;
     bool have_mask = false;
     std::vector<double> h_mass;     // host copy for range searches
-    size_t n() const { return forms.size(); }
+    RefDeviceTable dev;             // device-built table (reference only)
+    bool device_built = false, materialized = true;
+    size_t n_rows = 0;
+    size_t n() const { return device_built ? n_rows : forms.size(); }
 };
 
 struct TargetOrder { std::vector<uint32_t> row_of_form, form_of_row; };   // public (generation) order <-> device (mass) order
@@ -524,9 +508,39 @@ int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off,
     if (ctx->step_done < 2) return fail(ctx, PQ_ERR_STATE, "pq_step2_match_targets first (the reference mass window comes from the matched spectra)");
     cudaSetDevice(ctx->P.device);
     PeptideTable& R = ctx->reference;
-    R.seqs.clear(); R.forms.clear();
+    R.seqs.clear(); R.forms.clear(); R.have_mask = false; R.device_built = false; R.materialized = true;
     auto t_begin = std::chrono::steady_clock::now();
     Marks mk("build_reference");
+    if (ctx->P.max_len <= 48 && !getenv("PQ_HOST_REFERENCE")) {
+        // device path (K6): digest, unique, form expansion and the mass sort all run on the GPU
+        double mn = 1.7976931348623157e308, mx = 0.0;      // GeneratePeptideformWorker.set_mass_range (:40-52)
+        for (const HostPsm& p : ctx->psms) { double m = ctx->h_mass[(size_t)p.spectrum_sorted]; mn = std::min(mn, m); mx = std::max(mx, m); }
+        const double lo = mn - 250.0 - 5.0, hi = mx + 250.0 + 5.0;
+        R.dev.rows = &R.rows; R.dev.mass = &R.mass;
+        std::string err;
+        uint64_t launches = 0;
+        if (!build_reference_on_device(ctx->st, ctx->P, ctx->codes, n_proteins, off, res, ctx->targets.seqs, lo, hi, R.dev, &launches, err))
+            return fail(ctx, PQ_ERR_CUDA, "reference build: " + err);
+        ctx->cnt.other_kernel_launches += launches;
+        ctx->cnt.h2d_bytes += (n_proteins ? off[n_proteins] : 0) * 2;
+        R.device_built = true; R.materialized = false; R.n_rows = R.dev.n_forms;
+        mk.mark("device build");
+        R.h_mass.resize(R.n_rows);
+        if (R.n_rows) {
+            CU(cudaMemcpyAsync(R.h_mass.data(), R.mass.p, R.n_rows * 8, cudaMemcpyDeviceToHost, ctx->st));
+            if (ctx->P.score_method == 2) {
+                CU(R.pred.reserve(R.n_rows * 8));
+                ctx->cnt.other_kernel_launches += (uint64_t)launch_predict(R.rows.as<uint8_t>(), (uint32_t)R.n_rows, ctx->d_mods.as<ModTable>(), ctx->P.itol, R.pred.as<int32_t>(), ctx->st);
+            }
+            CU(cudaStreamSynchronize(ctx->st));
+            ctx->cnt.d2h_bytes += R.n_rows * 8;
+        }
+        mk.mark("mass d2h");
+        ctx->cnt.reference_sequences = R.dev.n_unique; ctx->cnt.reference_forms = R.n_rows;
+        ctx->cnt.ms_host_reference += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        ctx->have_reference = true;
+        return PQ_OK;
+    }
     int threads = (int)std::thread::hardware_concurrency(); if (threads < 1) threads = 1; if (threads > 32) threads = 32;
     digest_proteins(ctx->P, ctx->codes.residue_mass, n_proteins, off, res, R.seqs, threads);
     mk.mark("digest + unique + sort");
@@ -571,9 +585,27 @@ int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off,
 int32_t pq_get_reference_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int64_t* n_forms) {
     if (!ctx || !n_forms) return PQ_ERR_BAD_ARG;
     PeptideTable& T = ctx->reference;
-    *n_forms = (int64_t)T.forms.size();
+    *n_forms = (int64_t)T.n();
     if (!out) return PQ_OK;
     if (capacity < *n_forms) return fail(ctx, PQ_ERR_CAPACITY, "form buffer too small");
+    if (T.device_built) {
+        // the table lives on the device only; bring the rows back and decode them for the caller
+        cudaSetDevice(ctx->P.device);
+        const size_t n = T.n();
+        if (!n) return PQ_OK;
+        std::vector<uint8_t> rows(n * kRowBytes); std::vector<uint32_t> sid(n);
+        CU(cudaMemcpyAsync(rows.data(), T.rows.p, rows.size(), cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(sid.data(), T.dev.seq_id.p, n * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        ctx->cnt.d2h_bytes += rows.size() + n * 4;
+        std::string seq; FormRec fr;
+        for (size_t i = 0; i < n; ++i) {
+            ctx->codes.decode_row(rows.data() + i * kRowBytes, seq, fr);
+            fr.seq = (int32_t)sid[i]; fr.mass = T.h_mass[i];
+            ctx->codes.to_public(seq, fr, out + i);
+        }
+        return PQ_OK;
+    }
     for (size_t i = 0; i < T.forms.size(); ++i) ctx->codes.to_public(T.seqs[(size_t)T.forms[i].seq], T.forms[i], out + i);
     return PQ_OK;
 }

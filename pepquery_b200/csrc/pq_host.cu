@@ -174,6 +174,30 @@ bool Codes::from_public(const pq_form& p, std::string& seq, FormRec& out) const 
     return true;
 }
 
+void Codes::decode_row(const uint8_t* row, std::string& seq, FormRec& out) const {
+    const int L = row[0];
+    seq.resize((size_t)L);
+    memset(&out, 0, sizeof out);
+    int8_t mod_at[kMaxLen + 2];
+    for (int i = 0; i < kMaxLen + 2; ++i) mod_at[i] = -1;
+    const int nm = n_var + n_fixed;
+    for (int i = 0; i < L; ++i) {
+        uint8_t c = row[kRowHeader + i];
+        if (c < 26) { seq[(size_t)i] = (char)('A' + c); continue; }
+        for (int m = 0; m < nm && mod_at[i + 1] < 0; ++m)
+            for (int r = 0; r < 26; ++r) if (shuffle.code_of[m][r] == c) { seq[(size_t)i] = (char)('A' + r); mod_at[i + 1] = (int8_t)m; break; }
+    }
+    for (int m = 0; m < nm; ++m) {
+        if (!shuffle.term_code[m]) continue;
+        if (row[1] == shuffle.term_code[m] && (shuffle.position[m] == PQ_MOD_PEP_NTERM || shuffle.position[m] == PQ_MOD_PROT_NTERM)) mod_at[0] = (int8_t)m;
+        if (row[2] == shuffle.term_code[m] && (shuffle.position[m] == PQ_MOD_PEP_CTERM || shuffle.position[m] == PQ_MOD_PROT_CTERM)) mod_at[L + 1] = (int8_t)m;
+    }
+    for (int m = 0; m < nm; ++m)
+        for (int s = 0; s <= L + 1; ++s)
+            if (mod_at[s] == m && out.n < PQ_MAX_FORM_MODS) { out.site[out.n] = (uint8_t)s; out.mod[out.n] = (int8_t)m; ++out.n; }
+    out.mass = form_mass(seq, out);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 void digest_proteins(const pq_params& p, const double* residue_mass, int32_t n_proteins, const uint64_t* off, const char* res,
                      std::vector<std::string>& out, int threads) {

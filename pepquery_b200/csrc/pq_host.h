@@ -41,12 +41,23 @@ struct Codes {
     bool encode_row(const std::string& seq, const FormRec& f, uint8_t* row) const;   // 64-byte device row
     void to_public(const std::string& seq, const FormRec& f, pq_form* o) const;
     bool from_public(const pq_form& f, std::string& seq, FormRec& out) const;
+    // inverse of encode_row: the modification list comes back in reference list order (variable mods by (mod, site), then fixed)
+    void decode_row(const uint8_t* row, std::string& seq, FormRec& out) const;
 };
 
 // DigestProteinWorker.run (OpenModificationSearch/DigestProteinWorker.java:64-137) over all proteins; returns the unique
 // I->L sequences in lexicographic order.
 void digest_proteins(const pq_params& p, const double* residue_mass, int32_t n_proteins, const uint64_t* off, const char* res,
                      std::vector<std::string>& out, int threads);
+
+// The reference table as K6 builds it on the device (k6_reference.cu).  rows/mass point at the table's DevBufs.
+struct RefDeviceTable {
+    DevBuf residues, starts, cand_pos, cand_len, uniq, seq_id;   // normalised proteins, segment starts, candidate (pos,len), unique candidate ids (lexicographic), parent id per form
+    DevBuf* rows = nullptr; DevBuf* mass = nullptr;
+    uint32_t n_unique = 0, n_forms = 0;
+};
+bool build_reference_on_device(cudaStream_t st, const pq_params& P, const Codes& codes, int32_t n_proteins, const uint64_t* off, const char* res,
+                               const std::vector<std::string>& targets, double lo, double hi, RefDeviceTable& T, uint64_t* launches, std::string& err);
 
 // Group order + round count of PeptideInput.generateRandomPeptidesFast (pg/PeptideInput.java:387-422).
 void shuffle_plan(const std::string& seq, int n_random, ShuffleSeq& out);

@@ -7,6 +7,26 @@
 
 namespace pq {
 
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { if (p) cudaFree(p); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; } return *this; }
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 // Spectra as they sit in HBM: CSR peak arrays in precursor-mass order (SURVEY.md §8 a15 / north_star item 1).
 struct SpectraView {
     int64_t n;                    // spectra
