@@ -56,6 +56,7 @@ __device__ __forceinline__ uint32_t lower_bound_d(const double* a, uint32_t n, d
 
 __global__ void k_enumerate_targets(SpectraView sp, const double* __restrict__ table_mass, uint32_t n_rows, WindowConfig cfg,
                                     Job* __restrict__ jobs, uint32_t* __restrict__ n_jobs, int32_t* __restrict__ need) {
+    // n_jobs[0] = job count, n_jobs[2..3] = 64-bit total of candidate rows (sizes the Step-2 hit buffer)
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t s = t / cfg.n_isotope; int ii = (int)(t % cfg.n_isotope);
     if (s >= sp.n) return;
@@ -75,6 +76,7 @@ __global__ void k_enumerate_targets(SpectraView sp, const double* __restrict__ t
     J.charge = sp.charge[s]; J.iso = plain ? 0 : cfg.isotope[ii]; J.spectrum = (int32_t)s; J.aux = 0;
     jobs[slot] = J;
     need[s] = 1;
+    atomicAdd(reinterpret_cast<unsigned long long*>(n_jobs + 2), (unsigned long long)(hi - lo));
 }
 
 __global__ void k_blob_sizes(SpectraView sp, const int32_t* __restrict__ list, int32_t n_list, uint64_t* __restrict__ sizes) {

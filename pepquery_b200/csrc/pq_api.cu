@@ -49,11 +49,9 @@ struct PeptideTable {               // a mass-sorted candidate table resident on
 
 struct TargetOrder { std::vector<uint32_t> row_of_form, form_of_row; };   // public (generation) order <-> device (mass) order
 
-struct HostPsm {
+struct HostPsm {           // host mirror of a DevPsm (Step 5 only)
     int32_t spectrum_sorted, spectrum, form; uint32_t blob;
-    double score, exp_mass, pep_mass; int32_t iso, ca, cb, charge;
-    int32_t n_db = 0, total_db = 0, n_random = -1, total_random = -1, valid = 1;
-    double p_value = 100.0; int32_t rank = 0, n_ptm = -1, confident = 0;
+    double score; int32_t charge, n_db, rank, n_ptm; double p_value;
 };
 
 }  // namespace
@@ -65,6 +63,8 @@ struct pq_ctx {
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, uev0 = nullptr, uev1 = nullptr;
     pq_counters cnt;
+    struct PendingTimer { cudaEvent_t a, b; double* acc; double* acc2; };
+    std::vector<PendingTimer> timers; std::vector<cudaEvent_t> free_events;
     // constant tables
     DevBuf d_mods, d_l10, d_lnf, d_shufmods;
     std::vector<double> ln_fact; double log10_fact[65];
@@ -87,12 +87,26 @@ struct pq_ctx {
     int step_done = 0;
     // work buffers
     DevBuf jobs, results, hits, hit_count, njobs;
+    // device-resident PSM table (K7)
+    DevBuf d_psm, d_seg_start, d_out_perm, d_scalars, d_counters, d_agg, hits3, d_export;
+    DevBuf k_key_a, k_key_b, k_idx_a, k_idx_b, k_head;
+    uint32_t n_psm = 0, n_seg = 0, nh3 = 0;
+    double psm_mass_lo = 0.0, psm_mass_hi = 0.0;
+    // target-table side arrays on the device
+    DevBuf t_form_of_row, t_seq_of_form, t_strrank, t_form_mods, t_seq_off, t_seq_letters;
+    TargetAux aux() const {
+        TargetAux a; a.form_of_row = t_form_of_row.as<uint32_t>(); a.seq_of_form = t_seq_of_form.as<int32_t>(); a.strrank = t_strrank.as<uint32_t>();
+        a.form_mods = t_form_mods.as<FormMods>(); a.seq_off = t_seq_off.as<uint32_t>(); a.seq_letters = t_seq_letters.as<uint8_t>();
+        a.n_seq = (uint32_t)targets.seqs.size(); a.n_forms = (uint32_t)targets.forms.size();
+        return a;
+    }
     // shuffles
     DevBuf sh_seqs, sh_forms, sh_raw, sh_kidx, sh_kcnt, sh_rows, sh_pred;
-    std::vector<ShuffleSeq> h_sh_seqs; std::vector<uint32_t> h_kept; std::vector<int32_t> sh_slot_of_seq;
+    DevBuf sh_plans, sh_seq_flag, sh_form_flag, sh_valid_flag, sh_seq_slot, sh_form_slot, sh_row_base, sh_totals, sh_list, sh_order, sh_keys, sh_keys2;
+    bool have_shuffles = false;
     // results
-    std::vector<HostPsm> psms;
-    std::vector<pq_competitor> comp3, comp5;
+    std::vector<HostPsm> psms;          // Step 5 mirror
+    std::vector<pq_competitor> comp5;
 };
 
 namespace {
@@ -100,11 +114,34 @@ namespace {
 int32_t fail(pq_ctx* c, int32_t code, const std::string& msg) { if (c) c->err = msg; else g_create_error = msg; return code; }
 #define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, PQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
+// CUDA-event stopwatch around a group of launches.  Recording never blocks the host; the elapsed times are read when
+// the counters are asked for (flush_timers).
 struct Timer {
-    pq_ctx* c; double* acc;
-    Timer(pq_ctx* c_, double* a) : c(c_), acc(a) { cudaEventRecord(c->ev0, c->st); }
-    ~Timer() { cudaEventRecord(c->ev1, c->st); cudaEventSynchronize(c->ev1); float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); *acc += ms; c->cnt.ms_total += ms; }
+    pq_ctx* c; double* acc; double* acc2; cudaEvent_t a = nullptr, b = nullptr;
+    Timer(pq_ctx* c_, double* t, double* t2 = nullptr);
+    ~Timer();
 };
+void flush_timers(pq_ctx* c);
+
+Timer::Timer(pq_ctx* c_, double* t, double* t2) : c(c_), acc(t), acc2(t2) {
+    auto get = [&]() { cudaEvent_t e; if (!c->free_events.empty()) { e = c->free_events.back(); c->free_events.pop_back(); } else cudaEventCreate(&e); return e; };
+    a = get(); b = get();
+    cudaEventRecord(a, c->st);
+}
+Timer::~Timer() {
+    cudaEventRecord(b, c->st);
+    c->timers.push_back({a, b, acc, acc2});
+    if (c->timers.size() > 512) flush_timers(c);
+}
+void flush_timers(pq_ctx* c) {
+    for (auto& t : c->timers) {
+        cudaEventSynchronize(t.b);
+        float ms = 0; cudaEventElapsedTime(&ms, t.a, t.b);
+        *t.acc += ms; if (t.acc2) *t.acc2 += ms; c->cnt.ms_total += ms;
+        c->free_events.push_back(t.a); c->free_events.push_back(t.b);
+    }
+    c->timers.clear();
+}
 
 int32_t upload_table(pq_ctx* ctx, PeptideTable& T) {
     const size_t n = T.n();
@@ -153,11 +190,9 @@ int32_t run_score(pq_ctx* ctx, JobKind kind, uint32_t n_jobs, const int32_t* row
     L.hit_capacity = hit_capacity; L.max_blob_bytes = ctx->max_blob;
     ScoreConfig cfg = score_config(ctx, check_window);
     {
-        double ms = 0.0;
-        { Timer t(ctx, &ms); ctx->cnt.score_kernel_launches += (uint64_t)launch_score(L, cfg, ctx->st); }
-        ctx->cnt.ms_score += ms;
         int si = kind == kJobTargets ? 0 : kind == kJobCompetitors ? 1 : kind == kJobShuffles ? 2 : 3;
-        ctx->cnt.ms_score_step[si] += ms;
+        Timer t(ctx, &ctx->cnt.ms_score, &ctx->cnt.ms_score_step[si]);
+        ctx->cnt.score_kernel_launches += (uint64_t)launch_score(L, cfg, ctx->st);
     }
     CU(cudaGetLastError());
     return PQ_OK;
@@ -170,6 +205,37 @@ template <class T> int32_t scan_exclusive(pq_ctx* ctx, const T* in, T* out, int 
     CU(cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp, in, out, n, ctx->st));
     return PQ_OK;
 }
+
+// pair / algorithmic-byte counters are accumulated on the device (k7_job_counters); fold them into ctx->cnt and zero them
+int32_t pull_device_counters(pq_ctx* ctx) {
+    flush_timers(ctx);
+    if (!ctx->d_counters.p) return PQ_OK;
+    DevCounters h;
+    CU(cudaMemcpyAsync(&h, ctx->d_counters.p, sizeof h, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof h, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->cnt.pairs_step2 += h.pairs[0]; ctx->cnt.pairs_step3 += h.pairs[1]; ctx->cnt.pairs_step4 += h.pairs[2]; ctx->cnt.pairs_step5 += h.pairs[3];
+    for (int i = 0; i < 4; ++i) { ctx->cnt.bytes_score_step[i] += h.bytes[i]; ctx->cnt.score_algorithmic_bytes += h.bytes[i]; }
+    return PQ_OK;
+}
+
+int32_t ensure_counters(pq_ctx* ctx) {
+    if (ctx->d_counters.p) return PQ_OK;
+    CU(ctx->d_counters.reserve(sizeof(DevCounters)));
+    CU(cudaMemsetAsync(ctx->d_counters.p, 0, sizeof(DevCounters), ctx->st));
+    CU(ctx->d_scalars.reserve(256));
+    return PQ_OK;
+}
+
+template <class K, class V> int32_t sort_pairs(pq_ctx* ctx, const K* kin, K* kout, const V* vin, V* vout, int n, int end_bit) {
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, n, 0, end_bit, ctx->st);
+    CU(ctx->scan_tmp.reserve(tmp + 64));
+    CU(cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, tmp, kin, kout, vin, vout, n, 0, end_bit, ctx->st));
+    return PQ_OK;
+}
+
+void reset_psm_state(pq_ctx* ctx) { ctx->n_psm = 0; ctx->n_seg = 0; ctx->nh3 = 0; ctx->have_shuffles = false; ctx->psms.clear(); ctx->comp5.clear(); }
 
 }  // namespace
 
@@ -233,6 +299,10 @@ int32_t pq_destroy(pq_ctx* ctx) {
     cudaStreamSynchronize(ctx->st);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    flush_timers(ctx);
+    for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
+    if (ctx->uev0) cudaEventDestroy(ctx->uev0);
+    if (ctx->uev1) cudaEventDestroy(ctx->uev1);
     cudaStream_t st = ctx->st;
     delete ctx;
     if (st) cudaStreamDestroy(st);
@@ -253,9 +323,19 @@ int32_t pq_event_elapsed_ms(pq_ctx* ctx, double* ms) {
     *ms = f;
     return PQ_OK;
 }
-int32_t pq_get_counters(pq_ctx* ctx, pq_counters* out) { if (!ctx || !out) return PQ_ERR_BAD_ARG; *out = ctx->cnt; return PQ_OK; }
+int32_t pq_get_counters(pq_ctx* ctx, pq_counters* out) {
+    if (!ctx || !out) return PQ_ERR_BAD_ARG;
+    cudaSetDevice(ctx->P.device);
+    int32_t rc = pull_device_counters(ctx);
+    if (rc) return rc;
+    *out = ctx->cnt;
+    return PQ_OK;
+}
 int32_t pq_reset_counters(pq_ctx* ctx) {
     if (!ctx) return PQ_ERR_BAD_ARG;
+    cudaSetDevice(ctx->P.device);
+    int32_t rc = pull_device_counters(ctx);
+    if (rc) return rc;
     pq_counters k = ctx->cnt; memset(&ctx->cnt, 0, sizeof ctx->cnt);
     ctx->cnt.spectra_loaded = k.spectra_loaded; ctx->cnt.spectra_usable = k.spectra_usable; ctx->cnt.target_forms = k.target_forms;
     ctx->cnt.reference_sequences = k.reference_sequences; ctx->cnt.reference_forms = k.reference_forms;
@@ -278,7 +358,7 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
         if (c > maxp) maxp = (uint32_t)c;
         if ((int64_t)c > (int64_t)ctx->P.min_peaks) ++usable;
     }
-    ctx->nS = n; ctx->max_peaks = maxp; ctx->step_done = 0; ctx->psms.clear(); ctx->n_prepared = 0;
+    ctx->nS = n; ctx->max_peaks = maxp; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0;
     ctx->cnt.spectra_loaded = (uint64_t)n; ctx->cnt.spectra_usable = usable;
     if (n == 0) return PQ_OK;
     DevBuf in_prec, in_charge, in_off, in_mz, in_in, in_mass, key, key2, idx;
@@ -346,13 +426,23 @@ int32_t pq_set_targets(pq_ctx* ctx, int32_t n_seq, const uint32_t* off, const ch
     // the same forms sorted by mass; table_of_form / form_of_row translate.
     ctx->cnt.target_forms = T.forms.size();
     ctx->order.form_of_row.clear(); ctx->order.row_of_form.clear();
-    ctx->have_targets = true; ctx->step_done = 0; ctx->psms.clear();
+    ctx->have_targets = true; ctx->step_done = 0; reset_psm_state(ctx);
     return PQ_OK;
 }
 
 }  // extern "C"
 
 namespace {
+std::string mod_string(const pq_ctx* ctx, const FormRec& f) {
+    if (f.n == 0) return "-";
+    std::string s; char buf[96];
+    for (int i = 0; i < f.n; ++i) {
+        snprintf(buf, sizeof buf, "%d@%d[%.4f]", ctx->codes.mods[(size_t)f.mod[i]].id, (int)f.site[i], ctx->codes.mods[(size_t)f.mod[i]].delta);
+        if (i) s += ";";
+        s += buf;
+    }
+    return s;
+}
 // target forms keep two orders: public (generation) and device (mass-sorted)
 int32_t finalize_targets(pq_ctx* ctx) {
     PeptideTable& T = ctx->targets;
@@ -371,7 +461,39 @@ int32_t finalize_targets(pq_ctx* ctx) {
     int32_t rc = upload_table(ctx, S);
     std::swap(S.rows, T.rows); std::swap(S.mass, T.mass); std::swap(S.pred, T.pred);
     T.h_mass = S.h_mass;    // sorted masses (row order)
-    return rc;
+    if (rc) return rc;
+    // side arrays of the device pipeline (K7): row -> public form, form -> sequence, the form's modification list,
+    // rank of "sequence|modification" among the forms (RankPSMCompare's last tie-break), the target letters
+    const size_t nseq = T.seqs.size();
+    std::vector<int32_t> seq_of_form(n); std::vector<FormMods> fm(n); std::vector<uint32_t> strrank(n, 0);
+    for (size_t f = 0; f < n; ++f) {
+        seq_of_form[f] = T.forms[f].seq;
+        memset(&fm[f], 0, sizeof(FormMods)); fm[f].n_mods = T.forms[f].n;
+        for (int i = 0; i < T.forms[f].n; ++i) fm[f].mod[i] = T.forms[f].mod[i];
+    }
+    {
+        std::vector<std::string> key(n);
+        for (size_t f = 0; f < n; ++f) key[f] = T.seqs[(size_t)T.forms[f].seq] + "|" + mod_string(ctx, T.forms[f]);
+        std::vector<uint32_t> by(n); std::iota(by.begin(), by.end(), 0u);
+        std::sort(by.begin(), by.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+        uint32_t r = 0;
+        for (size_t k = 0; k < n; ++k) { if (k && key[by[k]] != key[by[k - 1]]) ++r; strrank[by[k]] = r; }
+    }
+    std::vector<uint32_t> soff(nseq + 1, 0); std::vector<uint8_t> letters;
+    for (size_t q = 0; q < nseq; ++q) { for (char c : T.seqs[q]) letters.push_back((uint8_t)(c - 'A')); soff[q + 1] = (uint32_t)letters.size(); }
+    CU(ctx->t_form_of_row.reserve(std::max<size_t>(n * 4, 64))); CU(ctx->t_seq_of_form.reserve(std::max<size_t>(n * 4, 64)));
+    CU(ctx->t_strrank.reserve(std::max<size_t>(n * 4, 64))); CU(ctx->t_form_mods.reserve(std::max<size_t>(n * sizeof(FormMods), 64)));
+    CU(ctx->t_seq_off.reserve((nseq + 1) * 4)); CU(ctx->t_seq_letters.reserve(std::max<size_t>(letters.size(), 64)));
+    cudaStream_t st = ctx->st;
+    CU(cudaMemcpyAsync(ctx->t_form_of_row.p, O.form_of_row.data(), n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->t_seq_of_form.p, seq_of_form.data(), n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->t_strrank.p, strrank.data(), n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->t_form_mods.p, fm.data(), n * sizeof(FormMods), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->t_seq_off.p, soff.data(), (nseq + 1) * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->t_seq_letters.p, letters.data(), letters.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->cnt.h2d_bytes += n * (12 + sizeof(FormMods)) + (nseq + 1) * 4 + letters.size();
+    return PQ_OK;
 }
 }  // namespace
 
@@ -395,7 +517,9 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     Marks mk("step2");
     int32_t rc = finalize_targets(ctx);
     if (rc) return rc;
-    ctx->psms.clear(); ctx->step_done = 0; ctx->n_prepared = 0;
+    rc = ensure_counters(ctx);
+    if (rc) return rc;
+    reset_psm_state(ctx); ctx->step_done = 0; ctx->n_prepared = 0;
     if (n_psms) *n_psms = 0;
     const int64_t n = ctx->nS;
     PeptideTable& T = ctx->targets;
@@ -407,12 +531,13 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     CU(ctx->need.reserve((size_t)(n + 1) * 4));
     CU(ctx->prep_id.reserve((size_t)(n + 1) * 4));
     CU(ctx->prep_list.reserve((size_t)(n + 1) * 4));
-    CU(cudaMemsetAsync(ctx->njobs.p, 0, 8, st));
+    CU(cudaMemsetAsync(ctx->njobs.p, 0, 16, st));
     CU(cudaMemsetAsync(ctx->need.p, 0, (size_t)(n + 1) * 4, st));
     WindowConfig W; W.tol = ctx->P.tol; W.tol_ppm = ctx->P.tol_ppm; W.n_isotope = ctx->P.n_isotope; W.min_peaks = ctx->P.min_peaks;
     for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) W.isotope[i] = ctx->P.isotope[i];
     SpectraView sp = ctx->view();
-    uint32_t h_njobs = 0; int32_t h_nprep = 0;
+    struct { uint32_t njobs, nprep; unsigned long long cand; } hn = {0, 0, 0};
+    int32_t h_nprep = 0;
     {
         Timer t(ctx, &ctx->cnt.ms_window);
         int k = launch_enumerate_targets(sp, T.mass.as<double>(), (uint32_t)T.n(), W, ctx->jobs.as<Job>(), ctx->njobs.as<uint32_t>(), ctx->need.as<int32_t>(), st);
@@ -420,12 +545,15 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
         if (rc) return rc;
         ctx->cnt.other_kernel_launches += (uint64_t)k + 1;
     }
-    CU(cudaMemcpyAsync(&h_njobs, ctx->njobs.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&hn, ctx->njobs.p, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&h_nprep, ctx->prep_id.as<int32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    ctx->cnt.d2h_bytes += 8;
+    ctx->cnt.d2h_bytes += 20;
+    const uint32_t h_njobs = hn.njobs;
+    const uint64_t cand = hn.cand;
     mk.mark("enumerate");
     if (h_njobs == 0) { ctx->step_done = 2; return PQ_OK; }
+    if (cand > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-2 candidates for one launch");
     // list of spectra to prepare (ascending sorted index) + blob offsets
     {
         Timer t(ctx, &ctx->cnt.ms_prepare);
@@ -453,52 +581,37 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     }
     CU(cudaGetLastError());
     mk.mark("prepare launch");
-    // hits capacity: every candidate could pass
-    std::vector<Job> hj(h_njobs);
-    CU(cudaMemcpyAsync(hj.data(), ctx->jobs.p, (size_t)h_njobs * sizeof(Job), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    ctx->cnt.d2h_bytes += (uint64_t)h_njobs * sizeof(Job);
-    uint64_t cand = 0; for (auto& j : hj) cand += j.cand_count;
-    mk.mark("jobs d2h (waits for K0)");
-    if (cand > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-2 candidates for one launch");
     rc = run_score(ctx, kJobTargets, h_njobs, T.pred.as<int32_t>(), T.rows.as<uint8_t>(), T.mass.as<double>(), (uint32_t)cand, 1);
     if (rc) return rc;
-    std::vector<JobResult> hr(h_njobs);
+    ctx->cnt.other_kernel_launches += (uint64_t)launch_job_counters(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), h_njobs, sp.off, 0, ctx->d_counters.as<DevCounters>(), st);
     uint32_t nh = 0;
-    CU(cudaMemcpyAsync(hr.data(), ctx->results.p, (size_t)h_njobs * sizeof(JobResult), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(&nh, ctx->hit_count.p, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    std::vector<Hit> hh(nh);
-    if (nh) { CU(cudaMemcpyAsync(hh.data(), ctx->hits.p, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
-    ctx->cnt.d2h_bytes += (uint64_t)h_njobs * sizeof(JobResult) + (uint64_t)nh * sizeof(Hit) + 4;
-    mk.mark("score + results d2h");
-    if (getenv("PQ_DEBUG")) {
-        uint64_t nin = 0; for (auto& r : hr) nin += r.n_in_window;
-        fprintf(stderr, "[pq] step2: jobs %u prepared %d candidates %llu in-window %llu hits %u max_blob %u\n", h_njobs, h_nprep,
-                (unsigned long long)cand, (unsigned long long)nin, nh, ctx->max_blob);
-        for (size_t j = 0; j < hj.size() && j < 4; ++j)
-            fprintf(stderr, "[pq]   job %zu: spec %d blob %u cand %u+%u mass %.6f -> in %u best %.4f\n", j, hj[j].spectrum, hj[j].blob, hj[j].cand_begin,
-                    hj[j].cand_count, hj[j].mass, hr[j].n_in_window, hr[j].best_score);
+    ctx->cnt.d2h_bytes += 4;
+    mk.mark("score (waits for K0 + K1)");
+    // hits -> PSM table in (mass-sorted spectrum, form) order, spectrum segments, caller-order permutation: all on the device
+    if (nh) {
+        CU(ctx->d_psm.reserve((size_t)nh * sizeof(DevPsm))); CU(ctx->d_seg_start.reserve(((size_t)nh + 2) * 4)); CU(ctx->d_out_perm.reserve((size_t)nh * 4));
+        std::string err; int launches = 0;
+        if (!psm_table_from_hits(ctx->hits.as<Hit>(), nh, sp, T.mass.as<double>(), T.rows.as<uint8_t>(), ctx->aux(), ctx->k_key_a, ctx->k_key_b, ctx->k_idx_a,
+                                 ctx->k_idx_b, ctx->k_head, ctx->scan_tmp, ctx->d_psm.as<DevPsm>(), ctx->d_seg_start.as<uint32_t>(),
+                                 ctx->d_scalars.as<uint32_t>(), ctx->d_out_perm.as<uint32_t>(), st, &launches, err))
+            return fail(ctx, PQ_ERR_CUDA, "psm table: " + err);
+        ctx->cnt.other_kernel_launches += (uint64_t)launches;
+        // segment count + the first / last matched spectrum (mass range of the reference table, GeneratePeptideformWorker.java:40-52)
+        uint32_t nseg = 0; int32_t s_first = 0, s_last = 0;
+        CU(cudaMemcpyAsync(&nseg, ctx->d_scalars.p, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&s_first, &ctx->d_psm.as<DevPsm>()[0].spectrum_sorted, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&s_last, &ctx->d_psm.as<DevPsm>()[nh - 1].spectrum_sorted, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        ctx->cnt.d2h_bytes += 12;
+        ctx->n_psm = nh; ctx->n_seg = nseg;
+        ctx->psm_mass_lo = ctx->h_mass[(size_t)s_first]; ctx->psm_mass_hi = ctx->h_mass[(size_t)s_last];
     }
-    for (size_t j = 0; j < hj.size(); ++j) {
-        ctx->cnt.pairs_step2 += hr[j].n_in_window;
-        uint64_t ab = (uint64_t)hr[j].n_in_window * (16ull * ctx->h_npeaks[(size_t)hj[j].spectrum] + 96ull);
-        ctx->cnt.score_algorithmic_bytes += ab; ctx->cnt.bytes_score_step[0] += ab;
-    }
-    const TargetOrder& O = ctx->order;
-    ctx->psms.reserve(nh);
-    for (const Hit& h : hh) {
-        HostPsm p;
-        p.spectrum_sorted = h.spectrum; p.spectrum = ctx->h_caller[(size_t)h.spectrum]; p.form = (int32_t)O.form_of_row[h.cand]; p.blob = h.blob;
-        p.score = h.score; p.exp_mass = h.mass; p.pep_mass = T.h_mass[h.cand]; p.iso = h.iso; p.ca = h.count_a; p.cb = h.count_b;
-        p.charge = ctx->h_charge[(size_t)h.spectrum];
-        ctx->psms.push_back(p);
-    }
-    std::sort(ctx->psms.begin(), ctx->psms.end(), [](const HostPsm& a, const HostPsm& b) { return a.spectrum != b.spectrum ? a.spectrum < b.spectrum : a.form < b.form; });
-    ctx->cnt.psms = ctx->psms.size();
-    mk.mark("psm list + sort");
+    ctx->cnt.psms = ctx->n_psm;
+    mk.mark("psm table");
     ctx->step_done = 2;
-    if (n_psms) *n_psms = (int64_t)ctx->psms.size();
+    if (n_psms) *n_psms = (int64_t)ctx->n_psm;
     return PQ_OK;
 }
 
@@ -514,7 +627,7 @@ int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off,
     if (ctx->P.max_len <= 48 && !getenv("PQ_HOST_REFERENCE")) {
         // device path (K6): digest, unique, form expansion and the mass sort all run on the GPU
         double mn = 1.7976931348623157e308, mx = 0.0;      // GeneratePeptideformWorker.set_mass_range (:40-52)
-        for (const HostPsm& p : ctx->psms) { double m = ctx->h_mass[(size_t)p.spectrum_sorted]; mn = std::min(mn, m); mx = std::max(mx, m); }
+        if (ctx->n_psm) { mn = ctx->psm_mass_lo; mx = ctx->psm_mass_hi; }
         const double lo = mn - 250.0 - 5.0, hi = mx + 250.0 + 5.0;
         R.dev.rows = &R.rows; R.dev.mass = &R.mass;
         std::string err;
@@ -550,7 +663,7 @@ int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off,
     }
     // GeneratePeptideformWorker.set_mass_range over the matched spectra (GeneratePeptideformWorker.java:40-52)
     double mn = 1.7976931348623157e308, mx = 0.0;
-    for (const HostPsm& p : ctx->psms) { double m = ctx->h_mass[(size_t)p.spectrum_sorted]; mn = std::min(mn, m); mx = std::max(mx, m); }
+    if (ctx->n_psm) { mn = ctx->psm_mass_lo; mx = ctx->psm_mass_hi; }
     const double lo = mn - 250.0 - 5.0, hi = mx + 250.0 + 5.0;
     {
         std::vector<std::vector<FormRec>> part((size_t)threads);
@@ -615,93 +728,47 @@ int32_t pq_step3_competitors(pq_ctx* ctx) {
     if (!ctx) return PQ_ERR_BAD_ARG;
     if (ctx->step_done < 2 || !ctx->have_reference) return fail(ctx, PQ_ERR_STATE, "pq_step2_match_targets and pq_build_reference first");
     cudaSetDevice(ctx->P.device);
-    ctx->comp3.clear();
     Marks mk("step3");
     PeptideTable& R = ctx->reference;
     cudaStream_t st = ctx->st;
-    // DatabaseInput.get_spectra2score(..., "max") (:637-669)
-    struct Spec { int32_t sorted; uint32_t blob; double best; int32_t charge; };
-    std::vector<Spec> specs;
-    {
-        std::unordered_map<int32_t, size_t> at;
-        for (const HostPsm& p : ctx->psms) {
-            auto it = at.find(p.spectrum_sorted);
-            if (it == at.end()) { at[p.spectrum_sorted] = specs.size(); specs.push_back({p.spectrum_sorted, p.blob, p.score, p.charge}); }
-            else if (specs[it->second].best < p.score) specs[it->second].best = p.score;
-        }
-        std::sort(specs.begin(), specs.end(), [](const Spec& a, const Spec& b) { return a.sorted < b.sorted; });
+    ctx->nh3 = 0;
+    const uint32_t n_seg = ctx->n_seg;
+    if (n_seg == 0 || R.n() == 0) {
+        // no matched spectrum, or an empty reference table: every PSM keeps n_db = total_db = 0
+        if (n_seg) { CU(ctx->d_agg.reserve((size_t)n_seg * sizeof(SegAgg))); CU(cudaMemsetAsync(ctx->d_agg.p, 0, (size_t)n_seg * sizeof(SegAgg), st)); }
+        ctx->step_done = 3;
+        return PQ_OK;
     }
-    std::vector<Job> hj;
-    const bool plain = ctx->P.n_isotope == 1 && ctx->P.isotope[0] == 0;
-    uint64_t cand = 0;
-    for (size_t si = 0; si < specs.size(); ++si) {
-        for (int ii = 0; ii < ctx->P.n_isotope; ++ii) {
-            double m = ctx->h_mass[(size_t)specs[si].sorted];
-            if (!plain) m = m - (double)ctx->P.isotope[ii] * kIsotope;
-            double w = ctx->P.tol_ppm ? ctx->P.tol * 1e-6 * (std::fabs(m) + 1.0) * 1.01 + 1e-6 : ctx->P.tol * 1.01 + 1e-6;
-            if (w > 0.2) w = 0.2;
-            size_t lo = std::lower_bound(R.h_mass.begin(), R.h_mass.end(), m - w) - R.h_mass.begin();
-            size_t hi = std::lower_bound(R.h_mass.begin(), R.h_mass.end(), m + w) - R.h_mass.begin();
-            if (hi <= lo) continue;
-            Job J; J.blob = specs[si].blob; J.cand_begin = (uint32_t)lo; J.cand_count = (uint32_t)(hi - lo); J.out = (uint32_t)si;
-            J.mass = m; J.ref_score = specs[si].best; J.charge = specs[si].charge; J.iso = plain ? 0 : ctx->P.isotope[ii];
-            J.spectrum = specs[si].sorted; J.aux = 0;
-            hj.push_back(J); cand += J.cand_count;
-        }
-    }
+    WindowConfig W; W.tol = ctx->P.tol; W.tol_ppm = ctx->P.tol_ppm; W.n_isotope = ctx->P.n_isotope; W.min_peaks = ctx->P.min_peaks;
+    for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) W.isotope[i] = ctx->P.isotope[i];
+    const uint32_t n_jobs = n_seg * (uint32_t)ctx->P.n_isotope;
+    CU(ctx->jobs.reserve((size_t)n_jobs * sizeof(Job)));
+    CU(ctx->d_agg.reserve((size_t)n_seg * sizeof(SegAgg)));
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(ctx->d_scalars.as<uint8_t>() + 64);
+    CU(cudaMemsetAsync(d_total, 0, 8, st));
+    // one job per (matched spectrum, isotope error); target best score per spectrum = DatabaseInput.get_spectra2score "max"
+    ctx->cnt.other_kernel_launches += (uint64_t)launch_step3_jobs(ctx->d_psm.as<DevPsm>(), ctx->d_seg_start.as<uint32_t>(), n_seg, R.mass.as<double>(), (uint32_t)R.n(),
+                                                                  W, ctx->s_mass.as<double>(), ctx->jobs.as<Job>(), ctx->d_agg.as<SegAgg>(), d_total, st);
+    unsigned long long cand = 0;
+    CU(cudaMemcpyAsync(&cand, d_total, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->cnt.d2h_bytes += 8;
     mk.mark("build jobs");
-    std::vector<JobResult> hr(hj.size());
-    std::vector<Hit> hh;
-    if (!hj.empty()) {
-        if (cand > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-3 candidates for one launch");
-        CU(ctx->jobs.reserve(hj.size() * sizeof(Job)));
-        CU(cudaMemcpyAsync(ctx->jobs.p, hj.data(), hj.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
-        ctx->cnt.h2d_bytes += hj.size() * sizeof(Job);
-        int32_t rc = run_score(ctx, kJobCompetitors, (uint32_t)hj.size(), R.pred.as<int32_t>(), R.rows.as<uint8_t>(), R.mass.as<double>(), (uint32_t)cand, 1);
-        if (rc) return rc;
-        uint32_t nh = 0;
-        CU(cudaMemcpyAsync(hr.data(), ctx->results.p, hj.size() * sizeof(JobResult), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(&nh, ctx->hit_count.p, 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        hh.resize(nh);
-        if (nh) { CU(cudaMemcpyAsync(hh.data(), ctx->hits.p, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
-        ctx->cnt.d2h_bytes += hj.size() * sizeof(JobResult) + (uint64_t)nh * sizeof(Hit) + 4;
-    }
-    mk.mark("score + results d2h");
-    struct Agg { int32_t matched = 0, better = 0; double best = -1.0; uint32_t best_row = 0xffffffffu; };
-    std::vector<Agg> agg(specs.size());
-    for (size_t j = 0; j < hj.size(); ++j) {
-        Agg& a = agg[hj[j].out];
-        a.matched += (int32_t)hr[j].n_in_window; a.better += (int32_t)hr[j].n_better;
-        if (hr[j].best_score > a.best) { a.best = hr[j].best_score; a.best_row = hr[j].best_cand; }     // isotope order, strict '<' (:63-65)
-        ctx->cnt.pairs_step3 += hr[j].n_in_window;
-        uint64_t ab = (uint64_t)hr[j].n_in_window * (16ull * ctx->h_npeaks[(size_t)hj[j].spectrum] + 96ull);
-        ctx->cnt.score_algorithmic_bytes += ab; ctx->cnt.bytes_score_step[1] += ab;
-    }
-    // detail rows: better-or-equal competitors with score >= 20, plus the best competitor when its score > 0 (:71-76, :93-98)
-    for (const Hit& h : hh) ctx->comp3.push_back({ctx->h_caller[(size_t)h.spectrum], (int32_t)h.cand, -1, -1, h.score, R.h_mass[h.cand]});
-    {
-        std::vector<uint64_t> seen(hh.size());
-        for (size_t i = 0; i < hh.size(); ++i) seen[i] = ((uint64_t)(uint32_t)hh[i].spectrum << 32) | hh[i].cand;
-        std::sort(seen.begin(), seen.end());
-        for (size_t si = 0; si < specs.size(); ++si) {
-            const Agg& a = agg[si];
-            if (a.best > 0 && a.best_row != 0xffffffffu) {
-                uint64_t key = ((uint64_t)(uint32_t)specs[si].sorted << 32) | a.best_row;
-                if (!std::binary_search(seen.begin(), seen.end(), key))
-                    ctx->comp3.push_back({ctx->h_caller[(size_t)specs[si].sorted], (int32_t)a.best_row, -1, -1, a.best, R.h_mass[a.best_row]});
-            }
-        }
-    }
-    std::sort(ctx->comp3.begin(), ctx->comp3.end(), [](const pq_competitor& a, const pq_competitor& b) { return a.spectrum != b.spectrum ? a.spectrum < b.spectrum : a.ref_form < b.ref_form; });
-    std::unordered_map<int32_t, size_t> at;
-    for (size_t si = 0; si < specs.size(); ++si) at[specs[si].sorted] = si;
-    for (HostPsm& p : ctx->psms) {
-        const Agg& a = agg[at[p.spectrum_sorted]];
-        p.total_db = a.matched; p.n_db = a.better;
-        if (a.better >= 1) p.valid = 0;                                    // DatabaseInput.java:745-750
-    }
-    mk.mark("aggregate");
+    if (cand > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-3 candidates for one launch");
+    int32_t rc = run_score(ctx, kJobCompetitors, n_jobs, R.pred.as<int32_t>(), R.rows.as<uint8_t>(), R.mass.as<double>(), (uint32_t)std::max<unsigned long long>(cand, 1), 1);
+    if (rc) return rc;
+    int k = launch_job_counters(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), n_jobs, ctx->s_off.as<uint64_t>(), 1, ctx->d_counters.as<DevCounters>(), st);
+    k += launch_step3_aggregate(ctx->results.as<JobResult>(), n_seg, ctx->P.n_isotope, ctx->d_seg_start.as<uint32_t>(), ctx->d_psm.as<DevPsm>(), ctx->d_agg.as<SegAgg>(), st);
+    ctx->cnt.other_kernel_launches += (uint64_t)k;
+    // detail rows stay on the device until pq_get_competitors(3) asks for them: keep this launch's hit rows
+    uint32_t nh = 0;
+    CU(cudaMemcpyAsync(&nh, ctx->hit_count.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->cnt.d2h_bytes += 4;
+    if (nh) { CU(ctx->hits3.reserve((size_t)nh * sizeof(Hit))); CU(cudaMemcpyAsync(ctx->hits3.p, ctx->hits.p, (size_t)nh * sizeof(Hit), cudaMemcpyDeviceToDevice, st)); }
+    ctx->nh3 = nh;
+    CU(cudaGetLastError());
+    mk.mark("score + aggregate");
     ctx->step_done = 3;
     return PQ_OK;
 }
@@ -714,85 +781,75 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
     cudaStream_t st = ctx->st;
     Marks mk("step4");
     PeptideTable& T = ctx->targets;
+    ctx->have_shuffles = false;
+    const uint32_t n_psm = ctx->n_psm;
+    if (n_psm == 0) { ctx->step_done = 4; return PQ_OK; }
+    if (ctx->P.n_random > 20000) return fail(ctx, PQ_ERR_UNSUPPORTED, "more than 20000 shuffles per peptide");
+    const TargetAux A = ctx->aux();
+    const size_t nseq = A.n_seq, nform = A.n_forms;
     // StatisticScoreCalc.run (:22-41): sequences with at least one still-valid PSM get shuffles
-    std::vector<int32_t> slot_of_seq(T.seqs.size(), -1), slot_of_form(T.forms.size(), -1);
-    std::vector<ShuffleSeq> seqs; std::vector<ShuffleForm> forms;
-    uint32_t raw_rows = 0, out_rows = 0, max_num = 1;
-    for (const HostPsm& p : ctx->psms) {
-        if (!p.valid) continue;
-        int32_t sq = T.forms[(size_t)p.form].seq;
-        if (slot_of_seq[(size_t)sq] < 0) {
-            ShuffleSeq S; shuffle_plan(T.seqs[(size_t)sq], ctx->P.n_random, S);
-            S.out_base = raw_rows; raw_rows += S.num; if (S.num > max_num) max_num = S.num;
-            slot_of_seq[(size_t)sq] = (int32_t)seqs.size(); seqs.push_back(S);
-        }
-        if (slot_of_form[(size_t)p.form] < 0) {
-            const FormRec& f = T.forms[(size_t)p.form];
-            ShuffleForm F; memset(&F, 0, sizeof F);
-            F.seq_slot = (uint32_t)slot_of_seq[(size_t)sq]; F.row_base = out_rows; out_rows += seqs[F.seq_slot].num;
-            F.n_mods = f.n; for (int i = 0; i < f.n; ++i) F.mod[i] = f.mod[i];
-            slot_of_form[(size_t)p.form] = (int32_t)forms.size(); forms.push_back(F);
-        }
+    CU(ctx->sh_seq_flag.reserve(nseq + 64)); CU(ctx->sh_form_flag.reserve(nform + 64)); CU(ctx->sh_valid_flag.reserve((size_t)n_psm + 64));
+    CU(ctx->sh_plans.reserve(nseq * sizeof(ShuffleSeq))); CU(ctx->sh_seqs.reserve(nseq * sizeof(ShuffleSeq))); CU(ctx->sh_forms.reserve(nform * sizeof(ShuffleForm)));
+    CU(ctx->sh_seq_slot.reserve(nseq * 4 + 64)); CU(ctx->sh_form_slot.reserve(nform * 4 + 64)); CU(ctx->sh_row_base.reserve(nform * 4 + 64));
+    CU(ctx->sh_totals.reserve(64)); CU(ctx->sh_kcnt.reserve(nseq * 4 + 64));
+    CU(cudaMemsetAsync(ctx->sh_seq_flag.p, 0, nseq, st)); CU(cudaMemsetAsync(ctx->sh_form_flag.p, 0, nform, st));
+    ShuffleTotals tot; memset(&tot, 0, sizeof tot);
+    {
+        Timer t(ctx, &ctx->cnt.ms_shuffle);
+        int k = launch_flag_valid(ctx->d_psm.as<DevPsm>(), n_psm, A.seq_of_form, ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint8_t>(), ctx->sh_valid_flag.as<uint8_t>(), st);
+        k += launch_shuffle_plans(ctx->sh_seq_flag.as<uint8_t>(), A, ctx->P.n_random, ctx->sh_plans.as<ShuffleSeq>(), st);
+        k += launch_shuffle_layout(ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint8_t>(), ctx->sh_valid_flag.as<uint8_t>(), n_psm, ctx->sh_plans.as<ShuffleSeq>(), A,
+                                   ctx->sh_seq_slot.as<uint32_t>(), ctx->sh_form_slot.as<uint32_t>(), ctx->sh_row_base.as<uint32_t>(), ctx->sh_seqs.as<ShuffleSeq>(),
+                                   ctx->sh_forms.as<ShuffleForm>(), ctx->sh_totals.as<ShuffleTotals>(), st);
+        ctx->cnt.other_kernel_launches += (uint64_t)k;
     }
-    ctx->h_sh_seqs = seqs; ctx->sh_slot_of_seq = slot_of_seq;
-    ctx->h_kept.assign(seqs.size(), 0);
-    mk.mark("shuffle plans");
-    if (seqs.empty()) { ctx->step_done = 4; return PQ_OK; }
-    CU(ctx->sh_seqs.reserve(seqs.size() * sizeof(ShuffleSeq))); CU(ctx->sh_forms.reserve(forms.size() * sizeof(ShuffleForm)));
+    CU(cudaMemcpyAsync(&tot, ctx->sh_totals.p, sizeof tot, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->cnt.d2h_bytes += sizeof tot;
+    mk.mark("shuffle plans + layout");
+    ctx->have_shuffles = true;
+    if (tot.n_seqs == 0 || tot.n_valid == 0) { ctx->step_done = 4; return PQ_OK; }
+    const uint32_t raw_rows = tot.raw_rows, out_rows = tot.out_rows, max_num = (uint32_t)std::max(ctx->P.n_random, 1);
     CU(ctx->sh_raw.reserve((size_t)std::max(raw_rows, 1u) * kRowBytes)); CU(ctx->sh_kidx.reserve((size_t)std::max(raw_rows, 1u) * 4));
-    CU(ctx->sh_kcnt.reserve(seqs.size() * 4)); CU(ctx->sh_rows.reserve((size_t)std::max(out_rows, 1u) * kRowBytes));
-    CU(cudaMemcpyAsync(ctx->sh_seqs.p, seqs.data(), seqs.size() * sizeof(ShuffleSeq), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->sh_forms.p, forms.data(), forms.size() * sizeof(ShuffleForm), cudaMemcpyHostToDevice, st));
-    ctx->cnt.h2d_bytes += seqs.size() * sizeof(ShuffleSeq) + forms.size() * sizeof(ShuffleForm);
+    CU(ctx->sh_rows.reserve((size_t)std::max(out_rows, 1u) * kRowBytes));
     if (ctx->P.score_method == 2) { CU(ctx->sh_pred.reserve((size_t)std::max(out_rows, 1u) * 8)); CU(cudaMemsetAsync(ctx->sh_rows.p, 0, (size_t)out_rows * kRowBytes, st)); }
     {
         Timer t(ctx, &ctx->cnt.ms_shuffle);
-        int k = launch_shuffles(ctx->sh_seqs.as<ShuffleSeq>(), (uint32_t)seqs.size(), ctx->sh_forms.as<ShuffleForm>(), (uint32_t)forms.size(),
+        int k = launch_shuffles(ctx->sh_seqs.as<ShuffleSeq>(), tot.n_seqs, ctx->sh_forms.as<ShuffleForm>(), tot.n_forms,
                                 ctx->d_shufmods.as<ShuffleMods>(), ctx->sh_raw.as<uint8_t>(), ctx->sh_kidx.as<uint32_t>(), ctx->sh_kcnt.as<uint32_t>(),
                                 ctx->sh_rows.as<uint8_t>(), max_num, ctx->P.shuffle_seed, st);
         if (ctx->P.score_method == 2) k += launch_predict(ctx->sh_rows.as<uint8_t>(), out_rows, ctx->d_mods.as<ModTable>(), ctx->P.itol, ctx->sh_pred.as<int32_t>(), st);
         ctx->cnt.other_kernel_launches += (uint64_t)k;
     }
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(ctx->h_kept.data(), ctx->sh_kcnt.p, seqs.size() * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    ctx->cnt.d2h_bytes += seqs.size() * 4;
-    mk.mark("K2 shuffles");
+    mk.mark("K2 shuffles (launch)");
     // one job per valid PSM (StatisticScoreWorker), ordered by form so consecutive CTAs share shuffle rows in L2
-    std::vector<size_t> order;
-    for (size_t i = 0; i < ctx->psms.size(); ++i) if (ctx->psms[i].valid) order.push_back(i);
-    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ctx->psms[a].form < ctx->psms[b].form; });
-    std::vector<Job> hj(order.size());
-    for (size_t k = 0; k < order.size(); ++k) {
-        const HostPsm& p = ctx->psms[order[k]];
-        const ShuffleForm& F = forms[(size_t)slot_of_form[(size_t)p.form]];
-        Job J; J.blob = p.blob; J.cand_begin = F.row_base; J.cand_count = ctx->h_kept[F.seq_slot]; J.out = (uint32_t)k;
-        J.mass = p.exp_mass; J.ref_score = p.score; J.charge = p.charge; J.iso = p.iso; J.spectrum = p.spectrum_sorted; J.aux = p.form;
-        hj[k] = J;
+    const uint32_t n_valid = tot.n_valid;
+    CU(ctx->sh_list.reserve((size_t)n_valid * 4 + 64)); CU(ctx->sh_order.reserve((size_t)n_valid * 4 + 64));
+    CU(ctx->sh_keys.reserve((size_t)n_valid * 4 + 64)); CU(ctx->sh_keys2.reserve((size_t)n_valid * 4 + 64));
+    {
+        size_t tmp = 0;
+        cub::CountingInputIterator<uint32_t> iota(0);
+        uint32_t* d_cnt = ctx->d_scalars.as<uint32_t>() + 4;
+        cub::DeviceSelect::Flagged(nullptr, tmp, iota, ctx->sh_valid_flag.as<uint8_t>(), ctx->sh_list.as<uint32_t>(), d_cnt, (int)n_psm, st);
+        CU(ctx->scan_tmp.reserve(tmp + 64));
+        CU(cub::DeviceSelect::Flagged(ctx->scan_tmp.p, tmp, iota, ctx->sh_valid_flag.as<uint8_t>(), ctx->sh_list.as<uint32_t>(), d_cnt, (int)n_psm, st));
     }
-    mk.mark("build jobs");
-    std::vector<JobResult> hr(hj.size());
-    if (!hj.empty()) {
-        CU(ctx->jobs.reserve(hj.size() * sizeof(Job)));
-        CU(cudaMemcpyAsync(ctx->jobs.p, hj.data(), hj.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
-        ctx->cnt.h2d_bytes += hj.size() * sizeof(Job);
-        int32_t rc = run_score(ctx, kJobShuffles, (uint32_t)hj.size(), ctx->sh_pred.as<int32_t>(), ctx->sh_rows.as<uint8_t>(), nullptr, 1, 0);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(hr.data(), ctx->results.p, hj.size() * sizeof(JobResult), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        ctx->cnt.d2h_bytes += hj.size() * sizeof(JobResult);
-    }
-    mk.mark("score + results d2h");
-    for (size_t k = 0; k < order.size(); ++k) {
-        HostPsm& p = ctx->psms[order[k]];
-        int32_t N = (int32_t)hj[k].cand_count;
-        if (N < 1) continue;        // the reference exits with "There is no random peptide!" (StatisticScoreWorker.java:59-62)
-        p.n_random = (int32_t)hr[k].n_better; p.total_random = N;
-        p.p_value = 1.0 * (p.n_random + 1) / (N + 1);
-        ctx->cnt.pairs_step4 += hr[k].n_in_window;
-        uint64_t ab = (uint64_t)hr[k].n_in_window * (16ull * ctx->h_npeaks[(size_t)p.spectrum_sorted] + 96ull);
-        ctx->cnt.score_algorithmic_bytes += ab; ctx->cnt.bytes_score_step[2] += ab;
-    }
+    int k = launch_psm_form_keys(ctx->d_psm.as<DevPsm>(), ctx->sh_list.as<uint32_t>(), n_valid, ctx->sh_keys.as<uint32_t>(), st);
+    int32_t rc = sort_pairs(ctx, ctx->sh_keys.as<uint32_t>(), ctx->sh_keys2.as<uint32_t>(), ctx->sh_list.as<uint32_t>(), ctx->sh_order.as<uint32_t>(), (int)n_valid, 32);
+    if (rc) return rc;
+    CU(ctx->jobs.reserve((size_t)n_valid * sizeof(Job)));
+    k += launch_step4_jobs(ctx->d_psm.as<DevPsm>(), ctx->sh_order.as<uint32_t>(), n_valid, ctx->sh_form_slot.as<uint32_t>(), ctx->sh_forms.as<ShuffleForm>(),
+                           ctx->sh_kcnt.as<uint32_t>(), ctx->jobs.as<Job>(), st);
+    ctx->cnt.other_kernel_launches += (uint64_t)k + 4;
+    rc = run_score(ctx, kJobShuffles, n_valid, ctx->sh_pred.as<int32_t>(), ctx->sh_rows.as<uint8_t>(), nullptr, 1, 0);
+    if (rc) return rc;
+    k = launch_job_counters(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), n_valid, ctx->s_off.as<uint64_t>(), 2, ctx->d_counters.as<DevCounters>(), st);
+    k += launch_step4_apply(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), ctx->sh_order.as<uint32_t>(), n_valid, ctx->d_psm.as<DevPsm>(), st);
+    ctx->cnt.other_kernel_launches += (uint64_t)k;
+    CU(cudaGetLastError());
+    mk.mark("jobs + score (launch)");
+    (void)T;
     ctx->step_done = 4;
     return PQ_OK;
 }
@@ -800,18 +857,24 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
 int32_t pq_get_shuffles(pq_ctx* ctx, int32_t target_seq, char* out, int64_t capacity, int32_t* n_shuffles) {
     if (!ctx || !n_shuffles) return PQ_ERR_BAD_ARG;
     *n_shuffles = 0;
-    if (target_seq < 0 || (size_t)target_seq >= ctx->sh_slot_of_seq.size() || ctx->sh_slot_of_seq[(size_t)target_seq] < 0) return PQ_OK;
+    if (!ctx->have_shuffles || target_seq < 0 || (size_t)target_seq >= ctx->targets.seqs.size()) return PQ_OK;
     cudaSetDevice(ctx->P.device);
-    size_t slot = (size_t)ctx->sh_slot_of_seq[(size_t)target_seq];
-    const ShuffleSeq& S = ctx->h_sh_seqs[slot];
-    uint32_t nk = ctx->h_kept[slot];
+    uint8_t flag = 0; uint32_t slot = 0;
+    CU(cudaMemcpy(&flag, ctx->sh_seq_flag.as<uint8_t>() + target_seq, 1, cudaMemcpyDeviceToHost));
+    if (!flag) return PQ_OK;
+    CU(cudaMemcpy(&slot, ctx->sh_seq_slot.as<uint32_t>() + target_seq, 4, cudaMemcpyDeviceToHost));
+    ShuffleSeq S; uint32_t nk = 0;
+    CU(cudaMemcpy(&S, ctx->sh_seqs.as<ShuffleSeq>() + slot, sizeof S, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&nk, ctx->sh_kcnt.as<uint32_t>() + slot, 4, cudaMemcpyDeviceToHost));
     *n_shuffles = (int32_t)nk;
     if (!out) return PQ_OK;
     int64_t L1 = (int64_t)S.len + 1;
     if (capacity < (int64_t)nk * L1) return fail(ctx, PQ_ERR_CAPACITY, "shuffle buffer too small");
     std::vector<uint8_t> raw((size_t)S.num * kRowBytes); std::vector<uint32_t> kidx(S.num);
-    CU(cudaMemcpy(raw.data(), ctx->sh_raw.as<uint8_t>() + (size_t)S.out_base * kRowBytes, raw.size(), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(kidx.data(), ctx->sh_kidx.as<uint32_t>() + S.out_base, (size_t)S.num * 4, cudaMemcpyDeviceToHost));
+    if (S.num) {
+        CU(cudaMemcpy(raw.data(), ctx->sh_raw.as<uint8_t>() + (size_t)S.out_base * kRowBytes, raw.size(), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(kidx.data(), ctx->sh_kidx.as<uint32_t>() + S.out_base, (size_t)S.num * 4, cudaMemcpyDeviceToHost));
+    }
     for (uint32_t k = 0; k < nk; ++k) {
         const uint8_t* r = raw.data() + (size_t)kidx[k] * kRowBytes;
         for (uint32_t i = 0; i < S.len; ++i) out[k * L1 + i] = (char)('A' + r[kRowHeader + i]);
@@ -821,71 +884,70 @@ int32_t pq_get_shuffles(pq_ctx* ctx, int32_t target_seq, char* out, int64_t capa
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-static std::string mod_string(const pq_ctx* ctx, const FormRec& f) {
-    if (f.n == 0) return "-";
-    std::string s; char buf[96];
-    for (int i = 0; i < f.n; ++i) {
-        snprintf(buf, sizeof buf, "%d@%d[%.4f]", ctx->codes.mods[(size_t)f.mod[i]].id, (int)f.site[i], ctx->codes.mods[(size_t)f.mod[i]].delta);
-        if (i) s += ";";
-        s += buf;
-    }
-    return s;
-}
-static double tol_ppm_of(const HostPsm& p) { return (1.0e6) * (p.pep_mass - p.exp_mass) / p.pep_mass; }
-
 int32_t pq_rank_and_validate(pq_ctx* ctx) {
     if (!ctx) return PQ_ERR_BAD_ARG;
-    Marks mk("rank");
-    PeptideTable& T = ctx->targets;
-    // psms are sorted by (spectrum, form): rank inside each spectrum run (pg/RankPSM.java:107-149)
-    size_t i = 0;
-    while (i < ctx->psms.size()) {
-        size_t j = i;
-        while (j < ctx->psms.size() && ctx->psms[j].spectrum == ctx->psms[i].spectrum) ++j;
-        std::vector<size_t> v(j - i); std::iota(v.begin(), v.end(), i);
-        std::stable_sort(v.begin(), v.end(), [&](size_t ia, size_t ib) {
-            const HostPsm& a = ctx->psms[ia]; const HostPsm& b = ctx->psms[ib];
-            if (a.score != b.score) return a.score > b.score;
-            if (a.p_value != b.p_value) return a.p_value < b.p_value;
-            double ta = std::fabs(tol_ppm_of(a)), tb = std::fabs(tol_ppm_of(b));
-            if (ta != tb) return ta < tb;
-            const FormRec& fa = T.forms[(size_t)a.form]; const FormRec& fb = T.forms[(size_t)b.form];
-            return T.seqs[(size_t)fa.seq] + "|" + mod_string(ctx, fa) < T.seqs[(size_t)fb.seq] + "|" + mod_string(ctx, fb);
-        });
-        for (size_t r = 0; r < v.size(); ++r) ctx->psms[v[r]].rank = (int32_t)r + 1;
-        i = j;
-    }
-    for (HostPsm& p : ctx->psms) {     // CParameter.passed_psm_validation (pg/CParameter.java:913-940)
-        int len = (int)T.seqs[(size_t)T.forms[(size_t)p.form].seq].size();
-        bool pv = (len <= 8 && p.p_value <= 0.05) || (len > 8 && p.p_value <= 0.01);
-        bool ok = pv && p.n_db == 0 && p.rank == 1;
-        if (p.n_ptm >= 0) ok = ok && p.n_ptm == 0;
-        p.confident = ok ? 1 : 0;
-    }
+    cudaSetDevice(ctx->P.device);
+    // rank inside each spectrum segment (pg/RankPSM.java:107-149) + CParameter.passed_psm_validation, on the device
+    ctx->cnt.other_kernel_launches += (uint64_t)launch_rank(ctx->d_psm.as<DevPsm>(), ctx->n_psm, ctx->d_seg_start.as<uint32_t>(), ctx->st);
+    CU(cudaGetLastError());
     return PQ_OK;
 }
 
 int32_t pq_get_psms(pq_ctx* ctx, pq_psm* out, int64_t capacity, int64_t* n_psms) {
     if (!ctx || !n_psms) return PQ_ERR_BAD_ARG;
-    *n_psms = (int64_t)ctx->psms.size();
+    *n_psms = (int64_t)ctx->n_psm;
     if (!out) return PQ_OK;
     if (capacity < *n_psms) return fail(ctx, PQ_ERR_CAPACITY, "psm buffer too small");
-    for (size_t i = 0; i < ctx->psms.size(); ++i) {
-        const HostPsm& p = ctx->psms[i]; pq_psm& q = out[i]; memset(&q, 0, sizeof q);
-        q.spectrum = p.spectrum; q.form = p.form; q.score = p.score; q.exp_mass = p.exp_mass; q.pep_mass = p.pep_mass; q.tol_ppm = tol_ppm_of(p);
-        q.isotope_error = p.iso; q.count_b = p.ca; q.count_y = p.cb; q.n_db = p.n_db; q.total_db = p.total_db; q.n_random = p.n_random;
-        q.total_random = p.total_random; q.valid = p.valid; q.p_value = p.p_value; q.rank = p.rank; q.n_ptm = p.n_ptm; q.confident = p.confident;
-    }
+    if (!ctx->n_psm) return PQ_OK;
+    cudaSetDevice(ctx->P.device);
+    const size_t bytes = (size_t)ctx->n_psm * sizeof(pq_psm);
+    CU(ctx->d_export.reserve(bytes));
+    ctx->cnt.other_kernel_launches += (uint64_t)launch_export_psms(ctx->d_psm.as<DevPsm>(), ctx->d_out_perm.as<uint32_t>(), ctx->n_psm, ctx->d_export.as<pq_psm>(), ctx->st);
+    CU(cudaMemcpyAsync(out, ctx->d_export.p, bytes, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->cnt.d2h_bytes += bytes;
     return PQ_OK;
 }
 
 int32_t pq_get_competitors(pq_ctx* ctx, int32_t step, pq_competitor* out, int64_t capacity, int64_t* n_rows) {
     if (!ctx || !n_rows) return PQ_ERR_BAD_ARG;
-    auto& v = step == 5 ? ctx->comp5 : ctx->comp3;
-    *n_rows = (int64_t)v.size();
+    if (step == 5) {
+        auto& v = ctx->comp5;
+        *n_rows = (int64_t)v.size();
+        if (!out) return PQ_OK;
+        if (capacity < *n_rows) return fail(ctx, PQ_ERR_CAPACITY, "competitor buffer too small");
+        if (!v.empty()) memcpy(out, v.data(), v.size() * sizeof(pq_competitor));
+        return PQ_OK;
+    }
+    // Step 3 detail rows: better-or-equal competitors with score >= 20 (the K1 hit rows) plus the best competitor of each
+    // spectrum when its score > 0 (pg/DBSearchWorker.java:71-76, 93-98), sorted by (spectrum, reference row) on the device
+    *n_rows = 0;
+    if (ctx->step_done < 3 || ctx->n_seg == 0 || !ctx->have_reference || ctx->reference.n() == 0) return PQ_OK;
+    cudaSetDevice(ctx->P.device);
+    cudaStream_t st = ctx->st;
+    const size_t cap = (size_t)ctx->nh3 + ctx->n_seg;
+    DevBuf rows, rows2, keys, keys2, idx, idx2;
+    CU(rows.reserve(cap * sizeof(pq_competitor))); CU(rows2.reserve(cap * sizeof(pq_competitor)));
+    CU(keys.reserve(cap * 8)); CU(keys2.reserve(cap * 8)); CU(idx.reserve(cap * 4)); CU(idx2.reserve(cap * 4));
+    uint32_t* d_cnt = ctx->d_scalars.as<uint32_t>() + 8;
+    CU(cudaMemsetAsync(d_cnt, 0, 4, st));
+    int k = launch_comp3_rows(ctx->hits3.as<Hit>(), ctx->nh3, ctx->d_agg.as<SegAgg>(), ctx->n_seg, ctx->d_seg_start.as<uint32_t>(), ctx->d_psm.as<DevPsm>(),
+                              ctx->s_caller.as<int32_t>(), ctx->reference.mass.as<double>(), rows.as<pq_competitor>(), keys.as<uint64_t>(), idx.as<uint32_t>(), d_cnt, st);
+    uint32_t extra = 0;
+    CU(cudaMemcpyAsync(&extra, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const uint32_t n = ctx->nh3 + extra;
+    *n_rows = (int64_t)n;
     if (!out) return PQ_OK;
     if (capacity < *n_rows) return fail(ctx, PQ_ERR_CAPACITY, "competitor buffer too small");
-    if (!v.empty()) memcpy(out, v.data(), v.size() * sizeof(pq_competitor));
+    if (!n) return PQ_OK;
+    int32_t rc = sort_pairs(ctx, keys.as<uint64_t>(), keys2.as<uint64_t>(), idx.as<uint32_t>(), idx2.as<uint32_t>(), (int)n, 64);
+    if (rc) return rc;
+    k += launch_gather_comp(rows.as<pq_competitor>(), idx2.as<uint32_t>(), n, rows2.as<pq_competitor>(), st);
+    ctx->cnt.other_kernel_launches += (uint64_t)k + 4;
+    CU(cudaMemcpyAsync(out, rows2.p, (size_t)n * sizeof(pq_competitor), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    ctx->cnt.d2h_bytes += (uint64_t)n * sizeof(pq_competitor) + 4;
     return PQ_OK;
 }
 
@@ -901,6 +963,18 @@ int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms) {
     if (rc) return rc;
     ctx->comp5.clear();
     PeptideTable& R = ctx->reference; PeptideTable& T = ctx->targets;
+    // Step 5 is driven from the host: mirror the device PSM table (table order: PSMs of one spectrum are contiguous)
+    {
+        std::vector<DevPsm> hp(ctx->n_psm);
+        if (ctx->n_psm) { CU(cudaMemcpyAsync(hp.data(), ctx->d_psm.p, (size_t)ctx->n_psm * sizeof(DevPsm), cudaMemcpyDeviceToHost, st)); CU(cudaStreamSynchronize(st)); }
+        ctx->cnt.d2h_bytes += (uint64_t)ctx->n_psm * sizeof(DevPsm);
+        ctx->psms.resize(ctx->n_psm);
+        for (size_t i = 0; i < hp.size(); ++i) {
+            const DevPsm& d = hp[i]; HostPsm& h = ctx->psms[i];
+            h.spectrum_sorted = d.spectrum_sorted; h.spectrum = d.spectrum; h.form = d.form; h.blob = d.blob; h.score = d.score; h.charge = d.charge;
+            h.n_db = d.n_db; h.rank = d.rank; h.n_ptm = d.n_ptm; h.p_value = d.p_value;
+        }
+    }
     // spectra to validate: PSMs with passed_psm_validation(len, p, n_db, rank); target = MIN score per spectrum (:1369-1383)
     std::vector<size_t> val;
     for (size_t i = 0; i < ctx->psms.size(); ++i) {
@@ -949,9 +1023,7 @@ int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms) {
             L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>(); L.hit_capacity = cap;
             L.max_blob_bytes = ctx->max_blob;
             ScoreConfig cfg = score_config(ctx, 1);
-            double ms = 0.0;
-            { Timer t(ctx, &ms); ctx->cnt.score_kernel_launches += (uint64_t)launch_ptm(L, cfg, st); }
-            ctx->cnt.ms_score += ms; ctx->cnt.ms_score_step[3] += ms;
+            { Timer t(ctx, &ctx->cnt.ms_score, &ctx->cnt.ms_score_step[3]); ctx->cnt.score_kernel_launches += (uint64_t)launch_ptm(L, cfg, st); }
             CU(cudaGetLastError());
             uint32_t nh = 0;
             CU(cudaMemcpyAsync(&nh, ctx->hit_count.p, 4, cudaMemcpyDeviceToHost, st));
@@ -986,6 +1058,15 @@ int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms) {
         if (it == at.end()) { p.n_ptm = 0; continue; }
         if (p.score == hj[it->second].ref_score) p.n_ptm = (int32_t)hr[it->second].n_better;
         else { int n = 0; for (const Hit& h : hh) if (h.spectrum == p.spectrum_sorted && (ctx->P.hc ? h.score >= p.score : h.score > p.score)) ++n; p.n_ptm = n; }
+    }
+    if (ctx->n_psm) {       // n_ptm back into the device table, then rank/accept again
+        std::vector<int32_t> np(ctx->n_psm);
+        for (size_t i = 0; i < np.size(); ++i) np[i] = ctx->psms[i].n_ptm;
+        CU(ctx->k_idx_a.reserve((size_t)ctx->n_psm * 4));
+        CU(cudaMemcpyAsync(ctx->k_idx_a.p, np.data(), np.size() * 4, cudaMemcpyHostToDevice, st));
+        ctx->cnt.other_kernel_launches += (uint64_t)launch_set_nptm(ctx->d_psm.as<DevPsm>(), ctx->n_psm, ctx->k_idx_a.as<int32_t>(), st);
+        CU(cudaStreamSynchronize(st));
+        ctx->cnt.h2d_bytes += np.size() * 4;
     }
     ctx->step_done = 5;
     return pq_rank_and_validate(ctx);

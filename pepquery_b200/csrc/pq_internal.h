@@ -172,6 +172,63 @@ struct PtmLaunch {
 };
 int launch_ptm(const PtmLaunch& L, const ScoreConfig& cfg, cudaStream_t st);
 int launch_row_masks(const uint8_t* rows, uint32_t n_rows, uint32_t* mask, cudaStream_t st);
+
+// ---- device-resident step pipeline (k7_steps.cu) --------------------------------------------------------------------
+// The PSM table lives on the device from Step 2 to the final export; the host only sees counts.
+struct DevPsm {
+    int32_t  spectrum_sorted;   // index into the mass-sorted spectra
+    int32_t  spectrum;          // caller's spectrum index
+    int32_t  form;              // public target form index
+    uint32_t row;               // target table row
+    uint32_t blob;              // prepared-spectrum id
+    int32_t  charge, iso, len;
+    double   score, exp_mass, pep_mass, p_value;
+    int32_t  ca, cb, n_db, total_db, n_random, total_random, valid, rank, n_ptm, confident;
+    uint32_t seg;               // spectrum segment (PSMs of one spectrum are contiguous)
+    uint32_t strrank;           // rank of "sequence|modification" among the target forms (RankPSM tie-break)
+};
+struct SegAgg {                 // Step-3 result per matched spectrum
+    int32_t matched, better;
+    double  best, ref_best;
+    uint32_t best_row, pad;
+};
+struct DevCounters { unsigned long long pairs[4]; unsigned long long bytes[4]; };
+struct FormMods { uint32_t n_mods; int8_t mod[PQ_MAX_FORM_MODS]; };     // a target form's modifications, list order
+struct ShuffleTotals { uint32_t n_seqs, raw_rows, n_forms, out_rows, n_valid; };
+
+struct TargetAux {              // per-target-table device arrays
+    const uint32_t* form_of_row;      // [rows]  mass-sorted row -> public form
+    const int32_t*  seq_of_form;      // [forms]
+    const uint32_t* strrank;          // [forms]
+    const FormMods* form_mods;        // [forms]
+    const uint32_t* seq_off;          // [seqs+1]
+    const uint8_t*  seq_letters;      // letter codes 0..25
+    uint32_t n_seq, n_forms;
+};
+
+// Step 2: hits -> sorted PSM table, segments, output permutation.  Returns false + err on CUDA failure.
+bool psm_table_from_hits(const Hit* hits, uint32_t nh, const SpectraView& sp, const double* t_mass, const uint8_t* t_rows, const TargetAux& A,
+                         DevBuf& key_a, DevBuf& key_b, DevBuf& idx_a, DevBuf& idx_b, DevBuf& head, DevBuf& tmp,
+                         DevPsm* psms, uint32_t* seg_start, uint32_t* d_nseg, uint32_t* out_perm, cudaStream_t st, int* launches, std::string& err);
+int launch_job_counters(const Job* jobs, const JobResult* res, uint32_t n_jobs, const uint64_t* sp_off, int which, DevCounters* c, cudaStream_t st);
+int launch_step3_jobs(const DevPsm* psms, const uint32_t* seg_start, uint32_t n_seg, const double* r_mass, uint32_t n_rows, const WindowConfig& W,
+                      const double* sp_mass, Job* jobs, SegAgg* agg, unsigned long long* total_cand, cudaStream_t st);
+int launch_step3_aggregate(const JobResult* res, uint32_t n_seg, int n_iso, const uint32_t* seg_start, DevPsm* psms, SegAgg* agg, cudaStream_t st);
+int launch_comp3_rows(const Hit* hits, uint32_t nh, const SegAgg* agg, uint32_t n_seg, const uint32_t* seg_start, const DevPsm* psms,
+                      const int32_t* caller_index, const double* r_mass, pq_competitor* rows, uint64_t* keys, uint32_t* idx, uint32_t* count, cudaStream_t st);
+int launch_gather_comp(const pq_competitor* in, const uint32_t* idx, uint32_t n, pq_competitor* out, cudaStream_t st);
+int launch_flag_valid(const DevPsm* psms, uint32_t n, const int32_t* seq_of_form, uint8_t* seq_flag, uint8_t* form_flag, uint8_t* valid_flag, cudaStream_t st);
+int launch_shuffle_plans(const uint8_t* seq_flag, const TargetAux& A, int32_t n_random, ShuffleSeq* plans, cudaStream_t st);
+int launch_shuffle_layout(const uint8_t* seq_flag, const uint8_t* form_flag, const uint8_t* valid_flag, uint32_t n_psm, const ShuffleSeq* plans, const TargetAux& A,
+                          uint32_t* seq_slot, uint32_t* form_slot, uint32_t* row_base, ShuffleSeq* seqs, ShuffleForm* forms, ShuffleTotals* totals, cudaStream_t st);
+int launch_step4_jobs(const DevPsm* psms, const uint32_t* order, uint32_t n_valid, const uint32_t* form_slot, const ShuffleForm* forms, const uint32_t* kept_count,
+                      Job* jobs, cudaStream_t st);
+int launch_step4_apply(const Job* jobs, const JobResult* res, const uint32_t* order, uint32_t n_valid, DevPsm* psms, cudaStream_t st);
+int launch_psm_form_keys(const DevPsm* psms, const uint32_t* list, uint32_t n, uint32_t* keys, cudaStream_t st);
+int launch_rank(DevPsm* psms, uint32_t n, const uint32_t* seg_start, cudaStream_t st);
+int launch_export_psms(const DevPsm* psms, const uint32_t* out_perm, uint32_t n, pq_psm* out, cudaStream_t st);
+int launch_set_nptm(DevPsm* psms, uint32_t n, const int32_t* n_ptm, cudaStream_t st);
+
 // MVH predicted-peak counts per row (k4_predict.cu): out[2*row] for precursor charge 2, out[2*row+1] otherwise
 int launch_predict(const uint8_t* rows, uint32_t n_rows, const ModTable* mods, double itol, int32_t* out, cudaStream_t st);
 
