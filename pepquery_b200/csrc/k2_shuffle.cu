@@ -42,28 +42,87 @@ __device__ __forceinline__ int select64(uint64_t x, int r) {
     return 32 + (int)__fns((uint32_t)(x >> 32), 0, r - c + 1);
 }
 
-__global__ void k2_generate(const ShuffleSeq* __restrict__ seqs, uint32_t n_seqs, int64_t seed, uint8_t* __restrict__ raw) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+// Affine map of n LCG steps: state -> A*state + C (mod 2^48).  The stream of one sequence is strictly serial, but the
+// number of draws per round is known (L-1, plus a retry of nextInt's rejection loop about once per 1e8 draws), so a lane
+// can jump straight to the start of its round.
+struct Affine { uint64_t a, c; };
+__device__ __forceinline__ Affine affine_pow(uint64_t n) {
+    const uint64_t M = (1ULL << 48) - 1;
+    Affine r{1ULL, 0ULL}, b{0x5DEECE66DULL, 0xBULL};
+    while (n) {
+        if (n & 1ULL) { r.a = (r.a * b.a) & M; r.c = (r.c * b.a + b.c) & M; }      // r = b o r
+        b.c = (b.c * b.a + b.c) & M; b.a = (b.a * b.a) & M;                          // b = b o b
+        n >>= 1;
+    }
+    return r;
+}
+
+constexpr int kGenWarps = 4;      // sequences per CTA (one warp each)
+
+// One warp per target sequence.  Lane l generates rounds base + l, base + l + 32, ...; every round starts from the LCG
+// state reached by skipping (round - base) * (L-1) draws from the state at `base`.  If some round had to redraw
+// (java.util.Random.nextInt's rejection loop), every later round starts one draw later: the warp restarts after the
+// first such round from its true end state.  Rounds before it are already exact.
+__global__ void __launch_bounds__(32 * kGenWarps)
+k2_generate(const ShuffleSeq* __restrict__ seqs, uint32_t n_seqs, int64_t seed, uint8_t* __restrict__ raw) {
+    __shared__ __align__(16) uint8_t s_rows[kGenWarps][32][kRowBytes + 16];        // +16: rows of neighbouring lanes start in different banks
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * kGenWarps + warp;
     if (t >= n_seqs) return;
     const ShuffleSeq& S = seqs[t];
     const int len = (int)S.len - 1;                     // C-terminal residue stays (fixCtermAA)
-    JRandom rnd(seed);
+    const uint32_t num = S.num;
+    const uint64_t M = (1ULL << 48) - 1;
     const uint64_t all = len >= 63 ? ~1ull : (((1ull << len) - 1ull) << 1);   // positions 1..len
-    for (uint32_t i = 0; i < S.num; ++i) {
-        uint8_t* row = raw + (size_t)(S.out_base + i) * kRowBytes;
-        uint64_t free_ = all;
-        for (uint32_t g = 0; g < S.n_groups; ++g) {
-            uint8_t code = S.group_code[g];
-            for (uint32_t r_ = 0; r_ < S.group_count[g]; ++r_) {
-                int r = rnd.nextInt(__popcll(free_));
-                int pp = select64(free_, r);
-                row[kRowHeader + pp - 1] = code;
-                free_ &= ~(1ull << pp);
+    uint8_t* row = s_rows[warp][lane];
+    const Affine per_round = affine_pow((uint64_t)len);
+    const Affine per_lane = affine_pow((uint64_t)len * lane);
+    const Affine per_sweep = affine_pow((uint64_t)len * 32u);
+    uint64_t base_state = ((uint64_t)seed ^ 0x5DEECE66DULL) & M;
+    uint32_t base_round = 0;
+    (void)per_round;
+    while (base_round < num) {
+        uint64_t st = (per_lane.a * base_state + per_lane.c) & M;              // state at the start of round base + lane
+        uint32_t first_retry = 0xFFFFFFFFu; uint64_t retry_state = 0;
+        for (uint32_t i = base_round + lane; i < num; i += 32) {
+            JRandom rnd(0); rnd.seed = st;
+            uint64_t free_ = all; int draws = 0;
+            for (int k = 0; k < kRowBytes / 4; ++k) reinterpret_cast<uint32_t*>(row)[k] = 0u;
+            for (uint32_t g = 0; g < S.n_groups; ++g) {
+                const uint8_t code = S.group_code[g];
+                for (uint32_t r_ = 0; r_ < S.group_count[g]; ++r_) {
+                    const int bound = __popcll(free_);
+                    // nextInt(bound) with the draw count exposed
+                    int32_t r = rnd.next31(); ++draws;
+                    const int32_t m = bound - 1;
+                    if ((bound & m) == 0) r = (int32_t)(((int64_t)bound * (int64_t)r) >> 31);
+                    else {
+                        for (int32_t u = r;; u = rnd.next31(), ++draws) {
+                            r = u % bound;
+                            if ((int64_t)u - (int64_t)r + (int64_t)m <= 0x7fffffffLL) break;
+                        }
+                    }
+                    const int pp = select64(free_, r);
+                    row[kRowHeader + pp - 1] = code;
+                    free_ &= ~(1ull << pp);
+                }
             }
+            row[kRowHeader + len] = S.seq[len];
+            row[0] = (uint8_t)S.len;
+            uint4* dst = reinterpret_cast<uint4*>(raw + (size_t)(S.out_base + i) * kRowBytes);
+            const uint4* srcv = reinterpret_cast<const uint4*>(row);
+            dst[0] = srcv[0]; dst[1] = srcv[1]; dst[2] = srcv[2]; dst[3] = srcv[3];
+            if (draws != len && first_retry == 0xFFFFFFFFu) { first_retry = i; retry_state = rnd.seed; }
+            if (first_retry != 0xFFFFFFFFu) break;                               // later rounds of this lane start from a wrong state anyway
+            st = (per_sweep.a * st + per_sweep.c) & M;
         }
-        row[kRowHeader + len] = S.seq[len];
-        row[0] = (uint8_t)S.len; row[1] = 0; row[2] = 0; row[3] = 0;
-        for (int k = (int)S.len; k < kMaxLen; ++k) row[kRowHeader + k] = 0;
+        // the earliest round that consumed extra draws decides where the stream really continues
+        uint32_t fr = first_retry;
+        for (int o = 16; o > 0; o >>= 1) fr = min(fr, __shfl_xor_sync(0xffffffffu, fr, o));
+        if (fr == 0xFFFFFFFFu) break;
+        const int owner = __ffs(__ballot_sync(0xffffffffu, first_retry == fr)) - 1;
+        base_state = __shfl_sync(0xffffffffu, retry_state, owner);
+        base_round = fr + 1;
     }
 }
 
@@ -189,7 +248,7 @@ int launch_shuffles(const ShuffleSeq* seqs, uint32_t n_seqs, const ShuffleForm* 
                     const ShuffleMods* mods, uint8_t* raw, uint32_t* kept_index, uint32_t* kept_count, uint8_t* rows,
                     uint32_t max_num, int64_t shuffle_seed, cudaStream_t st) {
     if (n_seqs == 0) return 0;
-    k2_generate<<<(n_seqs + 63) / 64, 64, 0, st>>>(seqs, n_seqs, shuffle_seed, raw);
+    k2_generate<<<(n_seqs + kGenWarps - 1) / kGenWarps, 32 * kGenWarps, 0, st>>>(seqs, n_seqs, shuffle_seed, raw);
     size_t smem = (size_t)max_num * 9 + 16;
     cudaFuncSetAttribute(k2_dedup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k2_dedup<<<n_seqs, 256, smem, st>>>(seqs, raw, kept_index, kept_count, max_num);

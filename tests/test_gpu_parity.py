@@ -272,6 +272,29 @@ def test_shuffle_streams_match_java_random(data):
     assert checked >= 5
 
 
+@pytest.mark.parametrize("seed,seq", [(374838, "ACDEFGHLMK"), (118583, "ACDEFGHLMNPQSTK"), (313646, "ACDEFGHLMNPQSTK"),
+                                      (118583, "ACDEFGHLMNPQSTVWYAGR")])
+def test_shuffle_stream_with_nextint_rejection(seed, seq):
+    """java.util.Random.nextInt(bound) redraws when its 31-bit sample falls in the biased tail (about once per 1e8 draws).
+    K2 lets every lane jump to the start of its round assuming L-1 draws per round, so a redraw shifts every later round:
+    these (seed, length) pairs hit a redraw inside the first 160 rounds (found by replaying the JDK LCG) and the shuffle
+    list must still equal the serial stream of the oracle, before and after the redraw."""
+    from oracle import pq_oracle
+    seqs = [seq, "PEPTLDEK"]
+    res = "".join(seqs).encode()
+    off = np.cumsum([0] + [len(s) for s in seqs]).astype(np.uint32)
+    tgt = (off, np.frombuffer(res, dtype=np.uint8).copy())
+    prot = synth.proteins(30)
+    sp = synth.spectra(200, tgt, prot, seed=11)
+    p = _abi.default_params(n_random=400, min_score=3.0, shuffle_seed=seed)
+    g = run_gpu(p, sp, tgt, prot)
+    o = run_oracle(p, sp, tgt, prot)
+    assert_psms_equal(g.psms(), o.psms())
+    got = g.shuffles(0, len(seq))
+    assert len(got) > 300
+    assert got == pq_oracle.shuffles(seq, 400, seed)
+
+
 def test_score_pairs_matches_oracle(data):
     from oracle import pq_oracle
     prot, tgt, sp = data
