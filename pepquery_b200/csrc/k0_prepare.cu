@@ -3,373 +3,520 @@
 // The reference redoes this for every (peptide, spectrum) pair inside scorePeptide2Spectrum
 // (pg/PeptideSearchMT.java:1144-1251): HyperscoreMatch.SpectrumPreProcessing (PSMMatch/HyperscoreMatch.java:47-59),
 // MVHMatch.SpectrumPreProcessing + classifyPeakIntensities (PSMMatch/MVHMatch.java:46-89) over the JMatch filters
-// (PSMMatch/JMatch.java:101-292,341-383), plus the annotator's intensity threshold (JMatch.java:427-430).
+// (PSMMatch/JMatch.java:101-292,341-383), plus the annotator's intensity threshold and peak pick (JMatch.java:411-451).
 // It depends only on the spectrum, so here it runs once per spectrum that has at least one candidate and writes one
 // "prepared spectrum" blob (pq_common.h) that K1 stages into shared memory.
 //
-// One CTA per spectrum.  Peaks live in shared memory; order-defining steps use a bitonic sort over index arrays
-// (stable through the file index), the two chain-dependent isotope passes and the TIC walk are sequential on one
-// thread because each decision depends on the previous one.
+// One WARP per spectrum, everything warp-synchronous in shared memory (no CTA barriers):
+//   * order-defining steps are bitonic sorts over index arrays (stable through the index); an m/z-ascending input
+//     (the normal MGF case) skips the m/z sort;
+//   * the isotope chains (removeIsotopes / cleanIsotopes) restart wherever two neighbouring kept peaks are >= gap apart or
+//     a peak lies below 200 Th, whatever happened before, so the chain segments between such hard boundaries run in
+//     parallel, one lane per segment; only the TIC walk of MVH stays a serial FP64 prefix on one lane;
+//   * the annotator's window predicate is inverted into exact break points in t (blob "ev"/"ans", pq_common.h).
 #include "pq_internal.h"
 
 namespace pq {
 
 namespace {
 
-constexpr int kPrepBlock = 128;
 
-struct PrepSmem {
-    double* r_mz; double* r_in; double* w_d;
-    uint32_t* ord; uint32_t* ordI; uint32_t* aux;
-    uint8_t* keep; uint16_t* cells;
+__device__ __forceinline__ double next_up(double x) { return __longlong_as_double(__double_as_longlong(x) + 1); }      // positive finite x
+__device__ __forceinline__ double next_down(double x) { return __longlong_as_double(__double_as_longlong(x) - 1); }
+
+struct WarpMem {
+    double* mz; double* in; double* da; double* db;            // raw m/z, raw intensity (file order), two work arrays
+    uint16_t* ord; uint16_t* ordI; uint16_t* aux; uint16_t* pr; uint16_t* eidx; uint16_t* cx;
+    uint8_t* keep; uint8_t* k2;
 };
-__host__ __device__ inline size_t prep_smem_bytes(uint32_t npad) {
-    return (size_t)npad * (8 * 3 + 4 * 3 + 1) + 16 + kCells * 2 + 64;
-}
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t cap) { return (size_t)cap * (8 * 4 + 2 * 6 + 2) + 64; }      // cap >= 256: the 30*cap bytes behind mz/db hold the cell histogram
 
-__device__ __forceinline__ bool key_less(const double* key, uint32_t a, uint32_t b) {
+__device__ __forceinline__ bool idx_less(const double* key, uint32_t a, uint32_t b) {
     double ka = key[a], kb = key[b];
     return ka < kb || (ka == kb && a < b);
 }
-
-__device__ void bitonic_sort_idx(uint32_t* idx, const double* key, uint32_t n) {
+// warp-synchronous bitonic sort of idx[0..n) by (key[idx], idx); n is a power of two >= 32
+__device__ void warp_sort_idx(uint16_t* idx, const double* key, uint32_t n, int lane) {
     for (uint32_t k = 2; k <= n; k <<= 1) {
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            for (uint32_t i = lane; i < n; i += 32) {
                 uint32_t ixj = i ^ j;
                 if (ixj > i) {
                     uint32_t a = idx[i], b = idx[ixj];
                     bool asc = (i & k) == 0;
-                    if (key_less(key, b, a) == asc) { idx[i] = b; idx[ixj] = a; }
+                    if (idx_less(key, b, a) == asc) { idx[i] = (uint16_t)b; idx[ixj] = (uint16_t)a; }
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
     }
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+__device__ __forceinline__ double warp_max(double m) { for (int o = 16; o > 0; o >>= 1) { double x = __shfl_xor_sync(0xffffffffu, m, o); if (m < x) m = x; } return m; }
+
+__device__ uint32_t count_kept(const uint8_t* keep, uint32_t P, int lane) {
+    uint32_t c = 0;
+    for (uint32_t i = lane; i < P; i += 32) c += keep[i];
+    return warp_sum(c);
+}
+__device__ void keep_all(uint8_t* keep, uint32_t P, int lane) { for (uint32_t i = lane; i < P; i += 32) keep[i] = 1; __syncwarp(); }
+__device__ double max_kept(const WarpMem& W, uint32_t P, int lane) {
+    double m = 0.0;                       // JSpectrum.getMaxIntensity starts at 0 (PSMMatch/JSpectrum.java:108-116)
+    for (uint32_t i = lane; i < P; i += 32) if (W.keep[i]) { double v = W.in[W.ord[i]]; if (m < v) m = v; }
+    return warp_max(m);
 }
 
 // JMatch.removeIsotopes / cleanIsotopes (PSMMatch/JMatch.java:223-280) over the kept entries, in m/z order.
-// Runs on one thread: each step depends on the current chain head.
-__device__ void isotope_pass(const double* r_mz, const double* r_in, const uint32_t* ord, uint8_t* keep, uint32_t P, double gap) {
-    uint32_t cnt = 0;
-    for (uint32_t i = 0; i < P; ++i) cnt += keep[i];
-    if (cnt <= 2) return;
-    int cur = -1; double ref = 0.0;
-    for (uint32_t i = 0; i < P; ++i) {
-        if (!keep[i]) continue;
-        keep[i] = 0;
-        double m = r_mz[ord[i]];
-        if (cur < 0) { cur = (int)i; ref = m; continue; }
-        if (__dsub_rn(m, ref) >= gap || m < 200.0) { keep[cur] = 1; cur = (int)i; ref = m; }
-        else if (r_in[ord[i]] > r_in[ord[cur]]) { cur = (int)i; ref = m; }
+// Reference chain: cur = first; for each next peak p: if p.mz - ref >= gap or p.mz < 200: emit cur, cur = p, ref = p.mz;
+// else if p.I > cur.I: cur = p, ref = p.mz.  `ref` is the m/z of a kept peak at or before the previous one, so a peak
+// that is >= gap above its kept predecessor (or below 200 Th) always restarts the chain: those are hard boundaries and
+// the segments between them are independent.
+__device__ void isotope_pass(const WarpMem& W, uint32_t P, double gap, int lane) {
+    if (count_kept(W.keep, P, lane) <= 2) return;
+    // hard-boundary flags in W.aux (1 = chain restarts here), result in W.k2
+    int carry = -1;                                                           // last kept position before this chunk
+    for (uint32_t c0 = 0; c0 < P; c0 += 32) {
+        uint32_t i = c0 + lane;
+        bool k = i < P && W.keep[i];
+        uint32_t bal = __ballot_sync(0xffffffffu, k);
+        if (i < P) {
+            W.k2[i] = 0;
+            uint32_t below = bal & ((1u << lane) - 1u);
+            int prev = below ? (int)(c0 + 31 - __clz(below)) : carry;
+            uint16_t hb = 0;
+            if (k) {
+                double m = W.mz[W.ord[i]];
+                hb = (prev < 0 || m < 200.0 || __dsub_rn(m, W.mz[W.ord[prev]]) >= gap) ? 1 : 0;
+            }
+            W.aux[i] = hb;
+        }
+        if (bal) carry = (int)(c0 + 31 - __clz(bal));
     }
-    if (cur >= 0) keep[cur] = 1;
+    __syncwarp();
+    for (uint32_t h = lane; h < P; h += 32) {
+        if (!W.keep[h] || !W.aux[h]) continue;
+        uint32_t cur = h; double ref = W.mz[W.ord[h]]; double cur_in = W.in[W.ord[h]];
+        for (uint32_t i = h + 1; i < P; ++i) {
+            if (!W.keep[i]) continue;
+            if (W.aux[i]) break;
+            double m = W.mz[W.ord[i]];
+            if (__dsub_rn(m, ref) >= gap) { W.k2[cur] = 1; cur = i; ref = m; cur_in = W.in[W.ord[i]]; }
+            else { double v = W.in[W.ord[i]]; if (v > cur_in) { cur = i; ref = m; cur_in = v; } }
+        }
+        W.k2[cur] = 1;
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < P; i += 32) W.keep[i] = W.k2[i];
+    __syncwarp();
 }
 
-__device__ uint32_t block_count(const uint8_t* keep, uint32_t P, uint32_t* s_tmp) {
-    uint32_t c = 0;
-    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) c += keep[i];
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = c;
-    __syncthreads();
-    uint32_t t = 0;
-    for (uint32_t w = 0; w < blockDim.x / 32; ++w) t += s_tmp[w];
-    __syncthreads();
-    return t;
-}
-__device__ double block_max_kept(const double* r_in, const uint32_t* ord, const uint8_t* keep, uint32_t P, double* s_tmp) {
-    double m = 0.0;                       // JSpectrum.getMaxIntensity starts at 0 (PSMMatch/JSpectrum.java:108-116)
-    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) if (keep[i]) { double v = r_in[ord[i]]; if (m < v) m = v; }
-    for (int o = 16; o > 0; o >>= 1) { double x = __shfl_xor_sync(0xffffffffu, m, o); if (m < x) m = x; }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_tmp[threadIdx.x >> 5] = m;
-    __syncthreads();
-    double t = 0.0;
-    for (uint32_t w = 0; w < blockDim.x / 32; ++w) if (t < s_tmp[w]) t = s_tmp[w];
-    __syncthreads();
-    return t;
-}
-// keep only the `top` largest kept entries by (intensity, m/z position): JMatch.filterByPeakCount (:148-174)
-__device__ void keep_top(const double* r_in, const uint32_t* ord, uint8_t* keep, uint32_t* aux, uint32_t P, uint32_t top) {
-    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+// rank from the top among the kept entries by (intensity, m/z position): g = #kept j with I_j > I_i or (I_j == I_i and j > i)
+__device__ void top_rank(const WarpMem& W, uint32_t P, uint16_t* out, int lane) {
+    for (uint32_t i = lane; i < P; i += 32) {
         uint32_t g = 0;
-        if (keep[i]) {
-            double vi = r_in[ord[i]];
+        if (W.keep[i]) {
+            double vi = W.in[W.ord[i]];
             for (uint32_t j = 0; j < P; ++j) {
-                if (!keep[j]) continue;
-                double vj = r_in[ord[j]];
+                if (!W.keep[j]) continue;
+                double vj = W.in[W.ord[j]];
                 g += (vj > vi || (vj == vi && j > i)) ? 1u : 0u;
             }
         }
-        aux[i] = g;
+        out[i] = (uint16_t)g;
     }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) if (keep[i] && aux[i] >= top) keep[i] = 0;
-    __syncthreads();
+    __syncwarp();
+}
+// keep only the `top` largest kept entries: JMatch.filterByPeakCount (:148-174)
+__device__ void keep_top(const WarpMem& W, uint32_t P, uint32_t top, int lane) {
+    top_rank(W, P, W.aux, lane);
+    for (uint32_t i = lane; i < P; i += 32) if (W.keep[i] && W.aux[i] >= top) W.keep[i] = 0;
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(kPrepBlock)
-k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_list, PrepConfig cfg,
-                  uint8_t* __restrict__ blobs, const uint64_t* __restrict__ blob_off, uint32_t npad_max) {
+__device__ __forceinline__ uint32_t count_le(const double* a, uint32_t n, double v) {      // #{a[i] <= v}, a ascending
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] <= v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ uint32_t count_lt(const double* a, uint32_t n, double v) {      // #{a[i] < v}
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+template <int kPrepWarps>
+__global__ void __launch_bounds__(32 * kPrepWarps)
+k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_list, PrepConfig cfg, uint8_t* __restrict__ blobs,
+                  const uint64_t* __restrict__ blob_off, uint32_t* __restrict__ blob_len, uint32_t cap, uint32_t p_lo, uint32_t p_hi) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ uint32_t s_u[8];
-    __shared__ double s_d[8];
-    __shared__ double s_limit, s_tic;
-    __shared__ uint32_t s_E, s_nsurv;
-    __shared__ int32_t s_cls[4];
-    __shared__ uint32_t s_flags;
-    __shared__ double s_val[kValSlots];
+    __shared__ double s_val[kPrepWarps][kValSlots];
+    __shared__ double s_d[kPrepWarps][4];
+    __shared__ uint32_t s_u[kPrepWarps][8];
+    __shared__ int32_t s_cls[kPrepWarps][4];
 
-    double* r_mz = reinterpret_cast<double*>(smem_raw);
-    double* r_in = r_mz + npad_max;
-    double* w_d = r_in + npad_max;
-    uint32_t* ord = reinterpret_cast<uint32_t*>(w_d + npad_max);
-    uint32_t* ordI = ord + npad_max;
-    uint32_t* aux = ordI + npad_max;
-    uint8_t* keep = reinterpret_cast<uint8_t*>(aux + npad_max);
-    uint16_t* cells = reinterpret_cast<uint16_t*>(smem_raw + (((size_t)npad_max * 37 + 15) & ~(size_t)15));
-
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* base_ptr = smem_raw + (size_t)warp * ((warp_smem_bytes(cap) + 15) & ~(size_t)15);
+    WarpMem W;
+    W.mz = reinterpret_cast<double*>(base_ptr); W.db = W.mz + cap; W.in = W.db + cap; W.da = W.in + cap;      // mz / db live to the end
+    W.ord = reinterpret_cast<uint16_t*>(W.da + cap); W.ordI = W.ord + cap; W.aux = W.ordI + cap; W.pr = W.aux + cap; W.eidx = W.pr + cap; W.cx = W.eidx + cap;
+    W.keep = reinterpret_cast<uint8_t*>(W.cx + cap); W.k2 = W.keep + cap;
+    double* val = s_val[warp];
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double itol = cfg.itol;
 
-    for (int32_t item = blockIdx.x; item < n_list; item += gridDim.x) {
+    const int32_t total_warps = (int32_t)gridDim.x * kPrepWarps;
+    for (int32_t item = (int32_t)blockIdx.x * kPrepWarps + warp; item < n_list; item += total_warps) {
         const int32_t s = list[item];
         const uint64_t base = sp.off[s];
         const uint32_t P = (uint32_t)(sp.off[s + 1] - base);
-        uint32_t n = 2; while (n < P) n <<= 1;
+        if (P < p_lo || P > p_hi) continue;                        // the other launch's size class
+        uint32_t n = 32; while (n < P) n <<= 1;
         const double prec_mz = sp.prec_mz[s];
         int z = sp.charge[s]; if (z == 0) z = 1;
 
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            r_mz[i] = i < P ? sp.mz[base + i] : inf;
-            r_in[i] = i < P ? sp.inten[base + i] : inf;
-            ord[i] = i; ordI[i] = i;
+        bool sorted = true;
+        for (uint32_t i = lane; i < n; i += 32) {
+            double m = i < P ? sp.mz[base + i] : inf;
+            W.mz[i] = m;
+            W.in[i] = i < P ? sp.inten[base + i] : inf;
+            W.ord[i] = (uint16_t)i; W.ordI[i] = (uint16_t)i;
+            if (i > 0 && i < P && !(sp.mz[base + i - 1] <= m)) sorted = false;
         }
-        __syncthreads();
-        bitonic_sort_idx(ord, r_mz, n);       // stable m/z order (JSpectrum.sortPeaksByMZ)
-        bitonic_sort_idx(ordI, r_in, n);      // stable intensity order (JSpectrum.sortPeaksByIntensity)
-        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) w_d[i] = r_in[ordI[i]];
-        __syncthreads();
+        sorted = __all_sync(0xffffffffu, sorted);
+        __syncwarp();
+        if (!sorted) warp_sort_idx(W.ord, W.mz, n, lane);          // stable m/z order (JSpectrum.sortPeaksByMZ)
+        warp_sort_idx(W.ordI, W.in, n, lane);                      // stable intensity order (JSpectrum.sortPeaksByIntensity)
+        for (uint32_t i = lane; i < P; i += 32) W.da[i] = W.in[W.ordI[i]];
+        __syncwarp();
 
         // annotator intensity limit: Spectrum.getIntensityLimit(percentile, 0.05) (JMatch.java:427-430; A2)
-        if (threadIdx.x == 0) {
-            double lim;
-            if (P == 1) lim = w_d[0];
-            else {
-                double indexDouble = __dmul_rn(0.05, (double)(P - 1));
-                int index = (int)indexDouble;
-                double valueAtIndex = w_d[index];
-                double rest = __dsub_rn(indexDouble, (double)index);
-                if (index == (int)P - 1 || rest == 0.0) lim = valueAtIndex;
-                else lim = __dadd_rn(valueAtIndex, __dmul_rn(rest, __dsub_rn(w_d[index + 1], valueAtIndex)));
-            }
-            s_limit = lim;
-            s_flags = 0;
+        double limit;
+        if (P == 1) limit = W.da[0];
+        else {
+            double indexDouble = __dmul_rn(0.05, (double)(P - 1));
+            int index = (int)indexDouble;
+            double valueAtIndex = W.da[index];
+            double rest = __dsub_rn(indexDouble, (double)index);
+            if (index == (int)P - 1 || rest == 0.0) limit = valueAtIndex;
+            else limit = __dadd_rn(valueAtIndex, __dmul_rn(rest, __dsub_rn(W.da[index + 1], valueAtIndex)));
         }
-        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) keep[i] = 1;
-        __syncthreads();
-        const double limit = s_limit;
+        // dense intensity rank (+1) of every raw peak, by file index; all peaks kept
+        bool has_dup = false;
+        for (uint32_t i = lane; i < P; i += 32) {
+            W.pr[i] = (uint16_t)(count_lt(W.da, P, W.in[i]) + 1u);
+            W.keep[i] = 1;
+            if (i > 0 && W.mz[W.ord[i]] == W.mz[W.ord[i - 1]]) has_dup = true;
+        }
+        has_dup = __any_sync(0xffffffffu, has_dup);
+        __syncwarp();
 
-        uint32_t nsurv = 0;
+        uint32_t nsurv = 0, flags = 0;
         if (cfg.method == 1) {
             // ---- HyperscoreMatch.SpectrumPreProcessing (HyperscoreMatch.java:47-59) ----
-            if (threadIdx.x == 0) isotope_pass(r_mz, r_in, ord, keep, P, 0.95);
-            __syncthreads();
-            const double tol_mz = __ddiv_rn(__dmul_rn(1.0, cfg.itol), (double)z);
-            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x)
-                if (keep[i] && fabs(__dsub_rn(r_mz[ord[i]], prec_mz)) <= tol_mz) keep[i] = 0;       // removeParentPeak
-            __syncthreads();
-            if (block_count(keep, P, s_u) == 0) { for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) keep[i] = 1; __syncthreads(); }
-            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x)
-                if (keep[i] && r_mz[ord[i]] <= 150.0) keep[i] = 0;                                   // removeLowMasses
-            __syncthreads();
-            if (block_count(keep, P, s_u) == 0) {
+            isotope_pass(W, P, 0.95, lane);
+            const double tol_mz = __ddiv_rn(__dmul_rn(1.0, itol), (double)z);
+            for (uint32_t i = lane; i < P; i += 32)
+                if (W.keep[i] && fabs(__dsub_rn(W.mz[W.ord[i]], prec_mz)) <= tol_mz) W.keep[i] = 0;          // removeParentPeak
+            __syncwarp();
+            if (count_kept(W.keep, P, lane) == 0) keep_all(W.keep, P, lane);
+            for (uint32_t i = lane; i < P; i += 32)
+                if (W.keep[i] && W.mz[W.ord[i]] <= 150.0) W.keep[i] = 0;                                      // removeLowMasses
+            __syncwarp();
+            if (count_kept(W.keep, P, lane) == 0) {
                 // getMaxIntensity() of an empty list is 0, then getPeaks() reloads the raw peaks (JSpectrum.java:71-76)
-                for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) keep[i] = 1;
-                __syncthreads();
+                keep_all(W.keep, P, lane);
             } else {
-                double mx = block_max_kept(r_in, ord, keep, P, s_d);
+                double mx = max_kept(W, P, lane);
                 double lim = __dmul_rn(__dmul_rn(1.0, 0.05), mx);
-                for (uint32_t i = threadIdx.x; i < P; i += blockDim.x)
-                    if (keep[i] && r_in[ord[i]] < lim) keep[i] = 0;                                  // removeLowIntensityPeak
-                __syncthreads();
+                for (uint32_t i = lane; i < P; i += 32)
+                    if (W.keep[i] && W.in[W.ord[i]] < lim) W.keep[i] = 0;                                     // removeLowIntensityPeak
+                __syncwarp();
             }
-            if (threadIdx.x == 0) isotope_pass(r_mz, r_in, ord, keep, P, 1.5);                       // cleanIsotopes
-            __syncthreads();
-            const bool cut = block_count(keep, P, s_u) > 50;
-            if (cut) keep_top(r_in, ord, keep, aux, P, 50);                                          // filterByPeakCount
-            double mx = block_max_kept(r_in, ord, keep, P, s_d);
-            // survivor ids by distinct m/z.  Surviving duplicates of one m/z (possible below 200 Th) share a slot whose
-            // value is the LAST HashMap.put of calcHyperScore's final m/z-sorted walk (:71-78): that sort is stable, so
-            // equal m/z keep the order of the previous sort — by intensity when the top-50 cut ran, else file order.
-            if (threadIdx.x == 0) {
-                uint32_t sid = 0; bool have = false; double last = 0.0, last_in = 0.0;
-                double* val = s_val;
-                for (uint32_t i = 0; i < P; ++i) {
-                    aux[i] = kNoSurvivor;
-                    if (!keep[i]) continue;
-                    double m = r_mz[ord[i]], v = r_in[ord[i]];
-                    bool same = have && m == last;
-                    if (!same) { if (have) ++sid; have = true; last = m; }
-                    aux[i] = sid;
-                    if (!same || !cut || v >= last_in) { val[sid] = __ddiv_rn(__dmul_rn(__dmul_rn(1.0, 100.0), v), mx); last_in = v; }   // normalizePeaks(100)
+            isotope_pass(W, P, 1.5, lane);                                                                    // cleanIsotopes
+            const bool cut = count_kept(W.keep, P, lane) > 50;
+            if (cut) keep_top(W, P, 50, lane);                                                                // filterByPeakCount
+            const double mx = max_kept(W, P, lane);
+            if (!has_dup) {
+                // survivor id = position among the kept peaks; normalizePeaks(100)
+                uint32_t run = 0;
+                for (uint32_t c0 = 0; c0 < P; c0 += 32) {
+                    uint32_t i = c0 + lane;
+                    bool k = i < P && W.keep[i];
+                    uint32_t bal = __ballot_sync(0xffffffffu, k);
+                    if (i < P) {
+                        uint32_t sid = run + __popc(bal & ((1u << lane) - 1u));
+                        W.aux[i] = k ? (uint16_t)sid : (uint16_t)kNoSurvivor;
+                        if (k && sid < (uint32_t)kValSlots) val[sid] = __ddiv_rn(__dmul_rn(__dmul_rn(1.0, 100.0), W.in[W.ord[i]]), mx);
+                    }
+                    run += __popc(bal);
                 }
-                uint32_t ns = have ? sid + 1 : 0;
-                // a peak that was filtered out but shares its m/z with a survivor still hits the survivor map
-                for (uint32_t i = 0; i < P; ++i) {
-                    if (aux[i] != kNoSurvivor) continue;
-                    double m = r_mz[ord[i]];
-                    uint32_t found = kNoSurvivor;
-                    for (uint32_t j = i; j-- > 0 && r_mz[ord[j]] == m;) if (aux[j] != kNoSurvivor) { found = aux[j]; break; }
-                    if (found == kNoSurvivor)
-                        for (uint32_t j = i + 1; j < P && r_mz[ord[j]] == m; ++j) if (aux[j] != kNoSurvivor) { found = aux[j]; break; }
-                    aux[i] = found;
+                nsurv = run;
+            } else {
+                // Surviving duplicates of one m/z (possible below 200 Th) share a slot whose value is the LAST HashMap.put of
+                // calcHyperScore's final m/z-sorted walk (:71-78): that sort is stable, so equal m/z keep the order of the
+                // previous sort — by intensity when the top-50 cut ran, else file order.
+                if (lane == 0) {
+                    uint32_t sid = 0; bool have = false; double last = 0.0, last_in = 0.0;
+                    for (uint32_t i = 0; i < P; ++i) {
+                        W.aux[i] = (uint16_t)kNoSurvivor;
+                        if (!W.keep[i]) continue;
+                        double m = W.mz[W.ord[i]], v = W.in[W.ord[i]];
+                        bool same = have && m == last;
+                        if (!same) { if (have) ++sid; have = true; last = m; }
+                        W.aux[i] = (uint16_t)sid;
+                        if (!same || !cut || v >= last_in) { if (sid < (uint32_t)kValSlots) val[sid] = __ddiv_rn(__dmul_rn(__dmul_rn(1.0, 100.0), v), mx); last_in = v; }
+                    }
+                    uint32_t ns = have ? sid + 1 : 0;
+                    // a peak that was filtered out but shares its m/z with a survivor still hits the survivor map
+                    for (uint32_t i = 0; i < P; ++i) {
+                        if (W.aux[i] != kNoSurvivor) continue;
+                        double m = W.mz[W.ord[i]];
+                        uint32_t found = kNoSurvivor;
+                        for (uint32_t j = i; j-- > 0 && W.mz[W.ord[j]] == m;) if (W.aux[j] != kNoSurvivor) { found = W.aux[j]; break; }
+                        if (found == kNoSurvivor)
+                            for (uint32_t j = i + 1; j < P && W.mz[W.ord[j]] == m; ++j) if (W.aux[j] != kNoSurvivor) { found = W.aux[j]; break; }
+                        W.aux[i] = (uint16_t)found;
+                    }
+                    s_u[warp][0] = ns;
                 }
-                s_nsurv = ns;
+                __syncwarp();
+                nsurv = s_u[warp][0];
             }
-            __syncthreads();
-            nsurv = s_nsurv;
+            __syncwarp();
         } else {
             // ---- MVHMatch.SpectrumPreProcessing + classifyPeakIntensities (MVHMatch.java:46-89) ----
-            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) { double m = r_mz[ord[i]]; if (m < 200.0 || m > 2000.0) keep[i] = 0; }
-            __syncthreads();
-            if (block_count(keep, P, s_u) == 0) { for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) keep[i] = 1; __syncthreads(); }
-            const double tol_mz = __ddiv_rn(__dmul_rn(1.0, cfg.itol), (double)z);
-            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x)
-                if (keep[i] && fabs(__dsub_rn(r_mz[ord[i]], prec_mz)) <= tol_mz) keep[i] = 0;
-            __syncthreads();
-            if (block_count(keep, P, s_u) == 0) { for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) keep[i] = 1; __syncthreads(); }
+            for (uint32_t i = lane; i < P; i += 32) { double m = W.mz[W.ord[i]]; if (m < 200.0 || m > 2000.0) W.keep[i] = 0; }
+            __syncwarp();
+            if (count_kept(W.keep, P, lane) == 0) keep_all(W.keep, P, lane);
+            const double tol_mz = __ddiv_rn(__dmul_rn(1.0, itol), (double)z);
+            for (uint32_t i = lane; i < P; i += 32)
+                if (W.keep[i] && fabs(__dsub_rn(W.mz[W.ord[i]], prec_mz)) <= tol_mz) W.keep[i] = 0;
+            __syncwarp();
+            if (count_kept(W.keep, P, lane) == 0) keep_all(W.keep, P, lane);
             // filterByTIC (JMatch.java:341-364): aux[] = sorted position of each file index
-            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) aux[ord[i]] = i;
-            __syncthreads();
-            if (block_count(keep, P, s_u) > 7) {
-                if (threadIdx.x == 0) {
+            for (uint32_t i = lane; i < P; i += 32) W.aux[W.ord[i]] = (uint16_t)i;
+            __syncwarp();
+            if (count_kept(W.keep, P, lane) > 7) {
+                if (lane == 0) {
                     double tic = 0.0;
-                    for (uint32_t f = 0; f < P; ++f) if (keep[aux[f]]) tic = __dadd_rn(tic, r_in[f]);   // list order = file order
+                    for (uint32_t f = 0; f < P; ++f) if (W.keep[W.aux[f]]) tic = __dadd_rn(tic, W.in[f]);   // list order = file order
                     double rel = 0.0;
                     for (uint32_t k = P; k-- > 0;) {
-                        uint32_t f = ordI[k]; uint32_t pos = aux[f];
-                        if (!keep[pos]) continue;
-                        rel = __dadd_rn(rel, __ddiv_rn(r_in[f], tic));
-                        if (!(rel <= 0.95)) keep[pos] = 0;
+                        uint32_t f = W.ordI[k]; uint32_t pos = W.aux[f];
+                        if (!W.keep[pos]) continue;
+                        rel = __dadd_rn(rel, __ddiv_rn(W.in[f], tic));
+                        if (!(rel <= 0.95)) W.keep[pos] = 0;
                     }
                 }
-                __syncthreads();
+                __syncwarp();
             }
-            if (block_count(keep, P, s_u) == 0) { for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) keep[i] = 1; __syncthreads(); }
-            if (threadIdx.x == 0) isotope_pass(r_mz, r_in, ord, keep, P, 0.95);
-            __syncthreads();
-            if (block_count(keep, P, s_u) > 300) keep_top(r_in, ord, keep, aux, P, 300);
-            uint32_t N = block_count(keep, P, s_u);
-            if (N == 0) { for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) keep[i] = 1; __syncthreads(); N = P; }
+            if (count_kept(W.keep, P, lane) == 0) keep_all(W.keep, P, lane);
+            isotope_pass(W, P, 0.95, lane);
+            if (count_kept(W.keep, P, lane) > 300) keep_top(W, P, 300, lane);
+            uint32_t N = count_kept(W.keep, P, lane);
+            if (N == 0) { keep_all(W.keep, P, lane); N = P; }
             // classes by descending (intensity, m/z position): top n -> 0, next 2n -> 1, rest -> 2
-            for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
-                uint32_t g = 0;
-                if (keep[i]) {
-                    double vi = r_in[ord[i]];
-                    for (uint32_t j = 0; j < P; ++j) { if (!keep[j]) continue; double vj = r_in[ord[j]]; g += (vj > vi || (vj == vi && j > i)) ? 1u : 0u; }
+            top_rank(W, P, W.eidx, lane);
+            const uint32_t npeak = N / 7;
+            if (!has_dup) {
+                uint32_t run = 0, c0n = 0, c1n = 0, c2n = 0;
+                for (uint32_t c0 = 0; c0 < P; c0 += 32) {
+                    uint32_t i = c0 + lane;
+                    bool k = i < P && W.keep[i];
+                    uint32_t bal = __ballot_sync(0xffffffffu, k);
+                    uint32_t c = 3;
+                    if (k) { uint32_t g = W.eidx[i]; c = g < npeak ? 0u : (g < 3 * npeak ? 1u : 2u); }
+                    if (i < P) {
+                        uint32_t sid = run + __popc(bal & ((1u << lane) - 1u));
+                        W.aux[i] = k ? (uint16_t)((c << 12) | sid) : (uint16_t)kNoSurvivor;
+                    }
+                    c0n += __popc(__ballot_sync(0xffffffffu, c == 0)); c1n += __popc(__ballot_sync(0xffffffffu, c == 1)); c2n += __popc(__ballot_sync(0xffffffffu, c == 2));
+                    run += __popc(bal);
                 }
-                ordI[i] = g;      // ordI is free from here on: rank from the top
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                uint32_t npeak = N / 7;
+                if (lane == 0) { s_cls[warp][0] = (int32_t)c0n; s_cls[warp][1] = (int32_t)c1n; s_cls[warp][2] = (int32_t)c2n; s_cls[warp][3] = cfg.mvh_bins - (int32_t)N; }
+            } else if (lane == 0) {
                 int32_t cc[4] = {0, 0, 0, 0};
                 uint32_t sid = 0; bool have = false; double last = 0.0;
                 for (uint32_t i = 0; i < P; ++i) {
-                    aux[i] = kNoSurvivor;
-                    if (!keep[i]) continue;
-                    uint32_t g = ordI[i];
+                    W.aux[i] = (uint16_t)kNoSurvivor;
+                    if (!W.keep[i]) continue;
+                    uint32_t g = W.eidx[i];
                     uint32_t c = g < npeak ? 0u : (g < 3 * npeak ? 1u : 2u);
                     cc[c]++;
-                    double m = r_mz[ord[i]];
+                    double m = W.mz[W.ord[i]];
                     if (have && m == last) { } else { if (have) ++sid; have = true; last = m; }
-                    aux[i] = (c << 12) | sid;
+                    W.aux[i] = (uint16_t)((c << 12) | sid);
                 }
                 for (uint32_t i = 0; i < P; ++i) {
-                    if (aux[i] != kNoSurvivor) continue;
-                    double m = r_mz[ord[i]];
+                    if (W.aux[i] != kNoSurvivor) continue;
+                    double m = W.mz[W.ord[i]];
                     uint32_t found = kNoSurvivor;
-                    for (uint32_t j = i; j-- > 0 && r_mz[ord[j]] == m;) if (aux[j] != kNoSurvivor) { found = aux[j]; break; }
+                    for (uint32_t j = i; j-- > 0 && W.mz[W.ord[j]] == m;) if (W.aux[j] != kNoSurvivor) { found = W.aux[j]; break; }
                     if (found == kNoSurvivor)
-                        for (uint32_t j = i + 1; j < P && r_mz[ord[j]] == m; ++j) if (aux[j] != kNoSurvivor) { found = aux[j]; break; }
-                    aux[i] = found;
+                        for (uint32_t j = i + 1; j < P && W.mz[W.ord[j]] == m; ++j) if (W.aux[j] != kNoSurvivor) { found = W.aux[j]; break; }
+                    W.aux[i] = (uint16_t)found;
                 }
                 cc[3] = cfg.mvh_bins - (int32_t)N;
-                for (int c = 0; c < 4; ++c) s_cls[c] = cc[c];
-                s_nsurv = N;
-                s_flags = N >= 7 ? 1u : 0u;
+                for (int c = 0; c < 4; ++c) s_cls[warp][c] = cc[c];
             }
-            __syncthreads();
-            nsurv = s_nsurv;
+            __syncwarp();
+            nsurv = N;
+            flags = N >= 7 ? 1u : 0u;
         }
 
-        // ---- blob: eligible peaks (intensity >= limit) in m/z order ----
+        // ---- matchable peaks (intensity >= limit) in m/z order: compact m/z -> da, rank -> ordI, claim code -> cx ----
+        uint32_t E = 0;
+        for (uint32_t c0 = 0; c0 < P; c0 += 32) {
+            uint32_t i = c0 + lane;
+            bool el = i < P && W.in[W.ord[i]] >= limit;
+            uint32_t bal = __ballot_sync(0xffffffffu, el);
+            if (i < P) W.eidx[i] = (uint16_t)(E + __popc(bal & ((1u << lane) - 1u)));
+            if (i < P && !el) W.eidx[i] = 0xFFFFu;
+            E += __popc(bal);
+        }
+        __syncwarp();
+        const BlobLayout BL = blob_layout(E);
         uint8_t* blob = blobs + blob_off[item];
-        // compaction index by a serial prefix over 128-wide chunks (P is small)
-        if (threadIdx.x == 0) {
-            uint32_t e = 0;
-            for (uint32_t i = 0; i < P; ++i) { bool el = r_in[ord[i]] >= limit; ord[i] |= el ? 0x80000000u : 0u; ordI[i] = e; e += el ? 1u : 0u; }
-            s_E = e;
+        double* g_ev = reinterpret_cast<double*>(blob + BL.ev);
+        uint16_t* g_ans = reinterpret_cast<uint16_t*>(blob + BL.ans);
+        double* g_pmz = reinterpret_cast<double*>(blob + BL.pmz);
+        uint32_t* g_pinfo = reinterpret_cast<uint32_t*>(blob + BL.pinfo);
+        double* g_val = reinterpret_cast<double*>(blob + BL.val);
+        uint16_t* g_cells = reinterpret_cast<uint16_t*>(blob + BL.cells);
+        // ordI is free from here on (the TIC walk was its last reader)
+        for (uint32_t i = lane; i < P; i += 32) {
+            uint32_t e = W.eidx[i];
+            if (e == 0xFFFFu) continue;
+            uint32_t f = W.ord[i];
+            double m = W.mz[f];
+            uint32_t code = W.aux[i];
+            W.da[e] = m; W.ordI[e] = W.pr[f]; W.cx[e] = (uint16_t)code;
+            g_pmz[e] = m;
+            g_pinfo[e] = ((uint32_t)W.pr[f] << 16) | code;
         }
-        __syncthreads();
-        const uint32_t E = s_E;
-        const uint32_t Epad = (E + 3u) & ~3u;
-        double* pmz = reinterpret_cast<double*>(blob + sizeof(BlobHeader));
-        uint32_t* pinfo = reinterpret_cast<uint32_t*>(blob + sizeof(BlobHeader) + (size_t)Epad * 8);
-        double* bval = reinterpret_cast<double*>(blob + sizeof(BlobHeader) + (size_t)Epad * 12);
-        uint16_t* bcells = reinterpret_cast<uint16_t*>(blob + sizeof(BlobHeader) + (size_t)Epad * 12 + kValSlots * 8);
-        for (uint32_t c = threadIdx.x; c < (uint32_t)kCells; c += blockDim.x) cells[c] = (uint16_t)E;
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
-            uint32_t o = ord[i];
-            if (!(o & 0x80000000u)) continue;
-            uint32_t f = o & 0x7fffffffu;
-            uint32_t e = ordI[i];
-            double m = r_mz[f];
-            // dense rank of the intensity among all raw peaks (+1): equal intensities share a rank
-            double v = r_in[f];
-            uint32_t lo = 0, hi = P;
-            while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (w_d[mid] < v) lo = mid + 1; else hi = mid; }
-            pmz[e] = m;
-            pinfo[e] = ((lo + 1u) << 16) | (aux[i] & 0xFFFFu);
-            // first-index table over the monotone cell map
-            int ce = cell_of(m);
-            int cp = -1;
-            // previous eligible peak
-            for (uint32_t j = i; j-- > 0;) if (ord[j] & 0x80000000u) { cp = cell_of(r_mz[ord[j] & 0x7fffffffu]); break; }
-            for (int c = cp + 1; c <= ce; ++c) cells[c] = (uint16_t)e;
+        if (lane == 0) { g_pmz[E] = inf; if (((E + 1u) & 1u) != 0u) g_pmz[E + 1] = inf; }
+        __syncwarp();
+        // ---- exact break points of the window predicate fabs(fl(mz - t)) <= itol: enter at lo, leave at rem = nextup(hi) ----
+        // (raw arrays are dead now: lo -> db, rem -> mz)
+        double* lo_a = W.db; double* rem_a = W.mz;
+        for (uint32_t e = lane; e < E; e += 32) {
+            const double m = W.da[e];
+            double g = __dsub_rn(m, itol);
+            double lo;
+            if (!(g > 0.0)) lo = 0.0;
+            else {
+                while (!(__dsub_rn(m, g) <= itol)) g = next_up(g);
+                for (;;) { double q = next_down(g); if (q > 0.0 && __dsub_rn(m, q) <= itol) g = q; else break; }
+                lo = g;
+            }
+            double h = __dadd_rn(m, itol);
+            while (!(__dsub_rn(h, m) <= itol)) h = next_down(h);
+            for (;;) { double q = next_up(h); if (__dsub_rn(q, m) <= itol) h = q; else break; }
+            lo_a[e] = lo; rem_a[e] = next_up(h);
         }
-        for (uint32_t e = E + threadIdx.x; e < Epad; e += blockDim.x) { pmz[e] = inf; pinfo[e] = kNoSurvivor; }
-        if (cfg.method == 1) for (uint32_t k = threadIdx.x; k < (uint32_t)kValSlots; k += blockDim.x) bval[k] = k < nsurv ? s_val[k] : 0.0;
-        else for (uint32_t k = threadIdx.x; k < (uint32_t)kValSlots; k += blockDim.x) bval[k] = 0.0;
-        __syncthreads();
-        for (uint32_t c = threadIdx.x; c < (uint32_t)kCells / 2; c += blockDim.x)
-            reinterpret_cast<uint32_t*>(bcells)[c] = reinterpret_cast<const uint32_t*>(cells)[c];
-        if (threadIdx.x == 0) {
+        __syncwarp();
+        // merged, sorted event list (a leave event goes before an enter event of the same value) and its answers
+        const uint32_t NE = 2u * E + 2u;
+        for (uint32_t q = lane; q < 2u * E; q += 32) {
+            const bool is_add = q < E;
+            const uint32_t e = is_add ? q : q - E;
+            const double v = is_add ? lo_a[e] : rem_a[e];
+            const uint32_t pos = is_add ? 1u + e + count_le(rem_a, E, v) : 1u + e + count_lt(lo_a, E, v);
+            // peaks in the window for ev[pos] <= t < ev[pos+1]: entered (lo <= v) and not yet left (rem > v)
+            const uint32_t a = count_le(rem_a, E, v);
+            const uint32_t bend = count_le(lo_a, E, v);
+            uint32_t code = kAnsNone;
+            if (a < bend) {
+                uint32_t best = a, best_r = W.ordI[a]; bool tie = false;
+                for (uint32_t j = a + 1; j < bend; ++j) {
+                    uint32_t r = W.ordI[j];
+                    if (r > best_r) { best = j; best_r = r; tie = false; }
+                    else if (r == best_r) tie = true;
+                }
+                if (tie) code = kAnsTie | a;
+                else {
+                    uint32_t cc = W.cx[best];
+                    if ((cc & 0xFFFu) == kNoSurvivor) code = kAnsNone;
+                    else if (cfg.method == 2 && (W.da[best] < 200.0 || W.da[best] > 2000.0)) code = kAnsNone;     // MVHMatch.java:248-250
+                    else code = cc;
+                }
+            }
+            g_ev[pos] = v; g_ans[pos] = (uint16_t)code;
+        }
+        if (lane == 0) { g_ev[0] = -inf; g_ans[0] = (uint16_t)kAnsNone; g_ev[NE - 1] = inf; g_ans[NE - 1] = (uint16_t)kAnsNone; }
+        for (uint32_t k = NE + lane; k < ((NE + 7u) & ~7u); k += 32) g_ans[k] = (uint16_t)kAnsNone;
+        // ---- cell table: cells[c] = number of real events below the lower edge of cell c (= index of the last of them) ----
+        // An event lies below the lower edge of exactly the cells above its own, so cells[] is the exclusive prefix sum of
+        // the per-cell event histogram (built in the shared memory the dead work arrays leave behind).
+        __syncwarp();
+        {
+            uint32_t* hist = reinterpret_cast<uint32_t*>(W.in);                      // kCells u16 counters, two per word
+            for (uint32_t k = lane; k < (uint32_t)kCells / 2; k += 32) hist[k] = 0u;
+            __syncwarp();
+            for (uint32_t e = lane; e < E; e += 32) {
+                int c1 = cell_of(lo_a[e]), c2 = cell_of(rem_a[e]);
+                atomicAdd(&hist[c1 >> 1], 1u << (16 * (c1 & 1)));
+                atomicAdd(&hist[c2 >> 1], 1u << (16 * (c2 & 1)));
+            }
+            __syncwarp();
+            constexpr uint32_t kPerLane = (uint32_t)kCells / 32;                       // 80 consecutive cells per lane
+            static_assert(kCells % (32 * 8) == 0, "cell table must split into uint4 chunks per lane");
+            const uint16_t* h16 = reinterpret_cast<const uint16_t*>(hist);
+            uint32_t mine = 0;
+            for (uint32_t k = 0; k < kPerLane; ++k) mine += h16[lane * kPerLane + k];
+            uint32_t incl = mine;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            uint32_t run = incl - mine;
+            for (uint32_t k8 = 0; k8 < kPerLane; k8 += 8) {
+                uint32_t w[4];
+                for (int h2 = 0; h2 < 4; ++h2) {
+                    uint32_t c = lane * kPerLane + k8 + (uint32_t)h2 * 2u;
+                    uint32_t v0 = run; run += h16[c];
+                    uint32_t v1 = run; run += h16[c + 1];
+                    w[h2] = (v0 & 0xFFFFu) | (v1 << 16);
+                }
+                *reinterpret_cast<uint4*>(g_cells + lane * kPerLane + k8) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        if (cfg.method == 1) for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = k < nsurv ? val[k] : 0.0;
+        else for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = 0.0;
+        if (lane == 0) {
             BlobHeader h;
-            h.n_peaks = E; h.n_pad = Epad; h.n_survivors = nsurv; h.flags = s_flags;
-            for (int c = 0; c < 4; ++c) h.cls_count[c] = cfg.method == 2 ? s_cls[c] : 0;
-            h.total_bytes = blob_bytes(Epad); h.raw_peaks = P; h.pad[0] = h.pad[1] = 0;
+            h.n_peaks = E; h.n_events = NE; h.n_survivors = nsurv; h.flags = flags;
+            for (int c = 0; c < 4; ++c) h.cls_count[c] = cfg.method == 2 ? s_cls[warp][c] : 0;
+            h.total_bytes = BL.total; h.raw_peaks = P; h.pad[0] = h.pad[1] = 0;
             *reinterpret_cast<BlobHeader*>(blob) = h;
+            blob_len[item] = BL.total;
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
 }  // namespace
 
 int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, const PrepConfig& cfg, uint8_t* blobs,
-                   const uint64_t* blob_off, uint32_t max_peaks, cudaStream_t st) {
+                   const uint64_t* blob_off, uint32_t* blob_len, uint32_t max_peaks, cudaStream_t st) {
     if (n_list <= 0) return 0;
-    uint32_t npad = 32; while (npad < max_peaks) npad <<= 1;
-    size_t smem = prep_smem_bytes(npad);
-    cudaFuncSetAttribute(k0_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    int per_sm = (int)(200 * 1024 / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 12) per_sm = 12;
-    int grid = sms * per_sm; if (grid > n_list) grid = n_list;
-    k0_prepare_kernel<<<grid, kPrepBlock, smem, st>>>(sp, list, n_list, cfg, blobs, blob_off, npad);
-    return 1;
+    int launched = 0;
+    auto run = [&](auto kernel, int warps, uint32_t cap, uint32_t p_lo, uint32_t p_hi) {
+        size_t per_warp = (warp_smem_bytes(cap) + 15) & ~(size_t)15;
+        size_t smem = per_warp * (size_t)warps;
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int per_sm = (int)(220 * 1024 / (smem + 2048)); if (per_sm < 1) per_sm = 1; if (per_sm > 16) per_sm = 16;
+        int grid = sms * per_sm; int need = (n_list + warps - 1) / warps; if (grid > need) grid = need;
+        kernel<<<grid, 32 * warps, smem, st>>>(sp, list, n_list, cfg, blobs, blob_off, blob_len, cap, p_lo, p_hi);
+        ++launched;
+    };
+    // size class 1: up to 256 peaks (the common case), four spectra per CTA; size class 2: the rest, capacity = next power of two
+    run(k0_prepare_kernel<4>, 4, 256, 0, 256);
+    if (max_peaks > 256) {
+        uint32_t cap = 512; while (cap < max_peaks) cap <<= 1;
+        if (cap <= 1024) run(k0_prepare_kernel<4>, 4, cap, 257, 0xFFFFFFFFu);
+        else run(k0_prepare_kernel<1>, 1, cap, 257, 0xFFFFFFFFu);
+    }
+    return launched;
 }
 
 }  // namespace pq

@@ -32,7 +32,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 struct BlobView {
-    const double* pmz; const uint32_t* pinfo; const double* val; const uint16_t* cells;
+    const double* ev; const uint16_t* ans; const double* pmz; const uint32_t* pinfo; const double* val; const uint16_t* cells;
     uint32_t E; uint32_t nsurv; uint32_t flags; int32_t cls[4];
 };
 __device__ __forceinline__ BlobView view_blob(const uint8_t* b) {
@@ -40,32 +40,43 @@ __device__ __forceinline__ BlobView view_blob(const uint8_t* b) {
     BlobView v;
     v.E = h->n_peaks; v.nsurv = h->n_survivors; v.flags = h->flags;
     for (int c = 0; c < 4; ++c) v.cls[c] = h->cls_count[c];
-    uint32_t ep = h->n_pad;
-    v.pmz = reinterpret_cast<const double*>(b + sizeof(BlobHeader));
-    v.pinfo = reinterpret_cast<const uint32_t*>(b + sizeof(BlobHeader) + (size_t)ep * 8);
-    v.val = reinterpret_cast<const double*>(b + sizeof(BlobHeader) + (size_t)ep * 12);
-    v.cells = reinterpret_cast<const uint16_t*>(b + sizeof(BlobHeader) + (size_t)ep * 12 + kValSlots * 8);
+    const BlobLayout L = blob_layout(v.E);
+    v.ev = reinterpret_cast<const double*>(b + L.ev);
+    v.ans = reinterpret_cast<const uint16_t*>(b + L.ans);
+    v.pmz = reinterpret_cast<const double*>(b + L.pmz);
+    v.pinfo = reinterpret_cast<const uint32_t*>(b + L.pinfo);
+    v.val = reinterpret_cast<const double*>(b + L.val);
+    v.cells = reinterpret_cast<const uint16_t*>(b + L.cells);
     return v;
 }
 
-// The annotator's peak pick for one theoretical m/z (A2-A4): most intense matchable peak with |mz - t| <= itol,
-// equal intensity -> smaller |error|.  Returns pinfo of the winner, 0 if none; *mz_out = its m/z.
-__device__ __forceinline__ uint32_t match_ion(const BlobView& B, double t, double itol, double itol_pad, double* mz_out) {
-    double lo = __dsub_rn(t, itol_pad);
-    uint32_t j = B.cells[cell_of(lo)];
-    uint32_t best = 0; double best_abs = 0.0;
-    for (; j < B.E; ++j) {
-        double m = B.pmz[j];
+// The annotator's peak pick for one theoretical m/z (A2-A4): most intense matchable peak with |mz - t| <= itol, equal
+// intensity -> smaller |error|.  K0 has inverted the predicate into exact break points (pq_common.h): find the interval
+// of t in the event list and read its answer.  Returns the claim code (kAnsNone = nothing to claim).
+// METHOD 1: code = survivor id; METHOD 2: code = (class << 12) | survivor id, m/z range already applied.
+template <int METHOD>
+__device__ __forceinline__ uint32_t match_ion(const BlobView& B, double t, double itol) {
+    uint32_t k = B.cells[cell_of(t)];
+    while (B.ev[k + 1] <= t) ++k;
+    uint32_t a = B.ans[k];
+    if (a < kAnsTie || a == kAnsNone) return a;
+    // two in-window peaks tie on intensity: the reference's scan decides (first peak wins unless a later one is strictly closer)
+    uint32_t best = 0; double best_abs = 0.0, best_mz = 0.0;
+    for (uint32_t j = a & 0xFFFu;; ++j) {
+        double m = B.pmz[j];                               // +inf after the last peak ends the scan
         double err = __dsub_rn(m, t);
         if (err > itol) break;
         double ae = fabs(err);
         if (ae <= itol) {
             uint32_t info = B.pinfo[j];
             uint32_t r = info >> 16, br = best >> 16;
-            if (r > br || (r == br && ae < best_abs)) { best = info; best_abs = ae; *mz_out = m; }
+            if (r > br || (r == br && ae < best_abs)) { best = info; best_abs = ae; best_mz = m; }
         }
     }
-    return best;
+    uint32_t code = best & 0xFFFFu;
+    if ((code & 0xFFFu) == kNoSurvivor) return kAnsNone;
+    if (METHOD == 2 && (best_mz < 200.0 || best_mz > 2000.0)) return kAnsNone;      // MVHMatch.java:248-250
+    return code;
 }
 
 struct Extra { int32_t site; double delta; };   // Step 5: one extra modification (site -1 = none)
@@ -83,7 +94,7 @@ __device__ __forceinline__ uint32_t row_byte(const uint32_t* codes, int idx) {
 template <int BLOCK, int METHOD>
 __device__ __forceinline__ PairScore score_pair(const uint32_t* codes /* this thread's column */, const BlobView& B,
                                                 const double* aa, const double* dl, const double* ntd, const double* ctd,
-                                                int z, double itol, double itol_pad, Extra ex,
+                                                int z, double itol, Extra ex,
                                                 const double* log10_fact, const double* ln_fact, int32_t predicted,
                                                 uint32_t* usedw /* MVH: this thread's column of the used bitmap */) {
     const uint32_t head = codes[0];
@@ -95,41 +106,43 @@ __device__ __forceinline__ PairScore score_pair(const uint32_t* codes /* this th
     double sum = 0.0;
     if (METHOD == 2) for (int w = 0; w < 10; ++w) usedw[w * BLOCK] = 0u;
 
-    auto claim = [&](uint32_t info, double mz, bool is_b) {
-        uint32_t sid = info & 0xFFFu;
-        if (info == 0u || sid == kNoSurvivor) return;
+    auto claim = [&](uint32_t code, bool is_b) {
+        if (code == kAnsNone) return;
         if (METHOD == 1) {
-            uint64_t bit = 1ull << sid;
+            uint64_t bit = 1ull << code;
             if (used & bit) return;
             used |= bit;
             if (is_b) ++ca; else ++cb;
-            sum = __dadd_rn(sum, B.val[sid]);
+            sum = __dadd_rn(sum, B.val[code]);
         } else {
-            if (mz < 200.0 || mz > 2000.0) return;                    // MVHMatch.java:248-250
+            uint32_t sid = code & 0xFFFu;
             uint32_t w = usedw[(sid >> 5) * BLOCK], bit = 1u << (sid & 31);
             if (w & bit) return;
             usedw[(sid >> 5) * BLOCK] = w | bit;
-            uint32_t c = (info >> 12) & 3u;
+            uint32_t c = (code >> 12) & 3u;
             key0 += c == 0; key1 += c == 1; key2 += c == 2;
         }
     };
+    // m/z of an ion of neutral mass m at charge c: (m + c*proton) / c.  c*proton is exact for c = 1, 2, 4 and so is the
+    // division by a power of two, so only c = 3 (and >= 5) needs a real FP64 divide.
+    auto ion_mz = [&](double m, int c) -> double {
+        if (c == 1) return __dadd_rn(m, kProton);
+        if (c == 2) return __dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5);
+        if (c == 4) return __dmul_rn(__dadd_rn(m, 4.0 * kProton), 0.25);
+        return __ddiv_rn(__dadd_rn(m, __dmul_rn((double)c, kProton)), (double)c);
+    };
 
     // ---- b ions: forward sum, residue mass then its modification, N-term modification opens the sum ----
+    // (a plain residue has modification mass +0.0: adding it leaves the positive running sum unchanged, so no branch)
     double acc = ntd[(head >> 8) & 0xFF];
     if (ex.site == 0) acc = __dadd_rn(acc, ex.delta);
     for (int k = 1; k <= L - 1; ++k) {
         uint32_t code = row_byte<BLOCK>(codes, kRowHeader + k - 1);
-        acc = __dadd_rn(acc, aa[code]);
-        double d = dl[code];
-        if (d != 0.0) acc = __dadd_rn(acc, d);
+        acc = __dadd_rn(__dadd_rn(acc, aa[code]), dl[code]);
         if (k == ex.site) acc = __dadd_rn(acc, ex.delta);
-        for (int c = 1; c <= nch; ++c) {
-            if (c > 1 && c > k) break;                                 // A6 chargeValidated
-            double t = __ddiv_rn(__dadd_rn(acc, __dmul_rn((double)c, kProton)), (double)c);
-            double mz = 0.0;
-            uint32_t info = match_ion(B, t, itol, itol_pad, &mz);
-            claim(info, mz, true);
-        }
+        claim(match_ion<METHOD>(B, ion_mz(acc, 1), itol), true);
+        for (int c = 2; c <= nch && c <= k; ++c)                        // A6 chargeValidated: c > 1 needs c <= ion number
+            claim(match_ion<METHOD>(B, ion_mz(acc, c), itol), true);
     }
     // ---- y ions: rewind sum from the C-terminus, + H2O ----
     acc = ctd[(head >> 16) & 0xFF];
@@ -137,18 +150,12 @@ __device__ __forceinline__ PairScore score_pair(const uint32_t* codes /* this th
     for (int k = 1; k <= L - 1; ++k) {
         int site = L - k + 1;
         uint32_t code = row_byte<BLOCK>(codes, kRowHeader + site - 1);
-        acc = __dadd_rn(acc, aa[code]);
-        double d = dl[code];
-        if (d != 0.0) acc = __dadd_rn(acc, d);
+        acc = __dadd_rn(__dadd_rn(acc, aa[code]), dl[code]);
         if (site == ex.site) acc = __dadd_rn(acc, ex.delta);
         double ym = __dadd_rn(acc, kWater);
-        for (int c = 1; c <= nch; ++c) {
-            if (c > 1 && c > k) break;
-            double t = __ddiv_rn(__dadd_rn(ym, __dmul_rn((double)c, kProton)), (double)c);
-            double mz = 0.0;
-            uint32_t info = match_ion(B, t, itol, itol_pad, &mz);
-            claim(info, mz, false);
-        }
+        claim(match_ion<METHOD>(B, ion_mz(ym, 1), itol), false);
+        for (int c = 2; c <= nch && c <= k; ++c)
+            claim(match_ion<METHOD>(B, ion_mz(ym, c), itol), false);
     }
 
     PairScore r;

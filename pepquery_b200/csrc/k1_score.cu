@@ -46,7 +46,6 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     __syncthreads();
 
     const double itol = cfg.itol;
-    const double itol_pad = itol + 1e-6;
     uint32_t* codes = codes_all + tid;
     uint32_t* usedw = usedw_all + tid;
 
@@ -55,7 +54,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     // prologue: stage the first job's blob
     if (job < L.n_jobs && tid == 0) {
         const Job& J = L.jobs[job];
-        uint32_t bytes = (uint32_t)(L.blob_off[J.blob + 1] - L.blob_off[J.blob]);
+        uint32_t bytes = L.blob_len[J.blob];
         mbar_expect_tx(&s_bar[0], bytes);
         tma_load_1d(stage0, L.blobs + L.blob_off[J.blob], bytes, &s_bar[0]);
     }
@@ -67,7 +66,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
             uint32_t nj = job + gridDim.x;
             if (nj < L.n_jobs && tid == 0) {
                 const Job& Jn = L.jobs[nj];
-                uint32_t bytes = (uint32_t)(L.blob_off[Jn.blob + 1] - L.blob_off[Jn.blob]);
+                uint32_t bytes = L.blob_len[Jn.blob];
                 mbar_expect_tx(&s_bar[cur ^ 1u], bytes);
                 tma_load_1d(stage0 + (size_t)stage_bytes * (cur ^ 1u), L.blobs + L.blob_off[Jn.blob], bytes, &s_bar[cur ^ 1u]);
             }
@@ -96,7 +95,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
             if (active) {
                 int32_t pred = 0;
                 if (METHOD == 2) pred = L.row_pred[2 * (size_t)row + (J.charge == 2 ? 0 : 1)];
-                PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_aa, s_dl, s_nt, s_ct, J.charge, itol, itol_pad, ex,
+                PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_aa, s_dl, s_nt, s_ct, J.charge, itol, ex,
                                                          s_l10, L.ln_fact, pred, usedw);
                 ++n_in;
                 if (ps.score > best) { best = ps.score; best_cand = row; }
@@ -144,7 +143,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
                 uint32_t nj = job + gridDim.x;
                 if (nj < L.n_jobs) {
                     const Job& Jn = L.jobs[nj];
-                    uint32_t bytes = (uint32_t)(L.blob_off[Jn.blob + 1] - L.blob_off[Jn.blob]);
+                    uint32_t bytes = L.blob_len[Jn.blob];
                     mbar_expect_tx(&s_bar[0], bytes);
                     tma_load_1d(stage0, L.blobs + L.blob_off[Jn.blob], bytes, &s_bar[0]);
                 }

@@ -85,7 +85,7 @@ __global__ void k_blob_sizes(SpectraView sp, const int32_t* __restrict__ list, i
     if (i == n_list) { sizes[i] = 0; return; }
     int32_t s = list[i];
     uint32_t P = (uint32_t)(sp.off[s + 1] - sp.off[s]);
-    sizes[i] = blob_bytes((P + 3u) & ~3u);
+    sizes[i] = blob_bytes(P);
 }
 
 __global__ void k_fix_job_blobs(Job* __restrict__ jobs, uint32_t n_jobs, const int32_t* __restrict__ prep_id) {

@@ -55,7 +55,7 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
     for (int i = tid; i < 65; i += BLOCK) s_l10[i] = L.log10_fact[i];
     if (tid == 0) { mbar_init(&s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
-    const double itol = cfg.itol, itol_pad = itol + 1e-6;
+    const double itol = cfg.itol;
     uint32_t* codes = codes_all + tid;
     const bool plain_iso = L.n_isotope == 1 && L.isotope[0] == 0;
 
@@ -63,7 +63,7 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
     for (uint32_t job = blockIdx.x; job < L.n_jobs; job += gridDim.x, ++it) {
         const Job J = L.jobs[job];
         if (tid == 0) {
-            uint32_t bytes = (uint32_t)(L.blob_off[J.blob + 1] - L.blob_off[J.blob]);
+            uint32_t bytes = L.blob_len[J.blob];
             mbar_expect_tx(&s_bar, bytes);
             tma_load_1d(stage0, L.blobs + L.blob_off[J.blob], bytes, &s_bar);
             s_stop = 0;
@@ -153,7 +153,7 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
                     else { uint32_t code = row_byte<BLOCK>(codes, kRowHeader + site - 1); ok = P.residue ? code == rcode : code < 26u; }
                     if (!ok) continue;
                     Extra ex; ex.site = site; ex.delta = P.delta;
-                    PairScore ps = score_pair<BLOCK, 1>(codes, B, s_aa, s_dl, s_nt, s_ct, J.charge, itol, itol_pad, ex, s_l10, nullptr, 0, nullptr);
+                    PairScore ps = score_pair<BLOCK, 1>(codes, B, s_aa, s_dl, s_nt, s_ct, J.charge, itol, ex, s_l10, nullptr, 0, nullptr);
                     ++n_pairs;
                     bool better = cfg.hc ? ps.score >= J.ref_score : ps.score > J.ref_score;      // :239-259, PSMT:920-943
                     if (better) { ++n_better; if (cfg.fast) s_stop = 1; }

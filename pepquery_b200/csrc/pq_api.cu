@@ -78,7 +78,7 @@ struct pq_ctx {
         return v;
     }
     // prepared spectra
-    DevBuf blobs, blob_off, prep_id, prep_list, need, scratch, scan_tmp;
+    DevBuf blobs, blob_off, blob_len, prep_id, prep_list, need, scratch, scan_tmp;
     uint32_t n_prepared = 0; uint32_t max_blob = 0;
     // tables
     PeptideTable targets, reference;
@@ -182,7 +182,7 @@ int32_t run_score(pq_ctx* ctx, JobKind kind, uint32_t n_jobs, const int32_t* row
     CU(cudaMemsetAsync(ctx->hit_count.p, 0, 4, ctx->st));
     ScoreLaunch L; memset(&L, 0, sizeof L);
     L.kind = kind; L.jobs = ctx->jobs.as<Job>(); L.n_jobs = n_jobs;
-    L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>();
+    L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>(); L.blob_len = ctx->blob_len.as<uint32_t>();
     L.rows = rows; L.row_mass = row_mass; L.mods = ctx->d_mods.as<ModTable>();
     L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>();
     L.row_pred = row_pred;
@@ -563,7 +563,7 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
         CU(ctx->scan_tmp.reserve(tmp + 64));
         CU(cub::DeviceSelect::Flagged(ctx->scan_tmp.p, tmp, iota, ctx->need.as<int32_t>(), ctx->prep_list.as<int32_t>(), ctx->njobs.as<uint32_t>() + 1, (int)n, st));
         CU(ctx->scratch.reserve((size_t)(h_nprep + 2) * 8));
-        CU(ctx->blob_off.reserve((size_t)(h_nprep + 2) * 8));
+        CU(ctx->blob_off.reserve((size_t)(h_nprep + 2) * 8)); CU(ctx->blob_len.reserve((size_t)(h_nprep + 2) * 4));
         launch_blob_sizes(sp, ctx->prep_list.as<int32_t>(), h_nprep, ctx->scratch.as<uint64_t>(), st);
         rc = scan_exclusive(ctx, ctx->scratch.as<uint64_t>(), ctx->blob_off.as<uint64_t>(), h_nprep + 1);
         if (rc) return rc;
@@ -573,11 +573,11 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
         CU(ctx->blobs.reserve(total_blob + 256));
         PrepConfig pc; pc.itol = ctx->P.itol; pc.method = ctx->P.score_method;
         pc.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (ctx->P.itol * 2.0));
-        int k = launch_prepare(sp, ctx->prep_list.as<int32_t>(), h_nprep, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(), ctx->max_peaks, st);
+        int k = launch_prepare(sp, ctx->prep_list.as<int32_t>(), h_nprep, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(), ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st);
         k += launch_fix_job_blobs(ctx->jobs.as<Job>(), h_njobs, ctx->prep_id.as<int32_t>(), st);
         ctx->cnt.other_kernel_launches += (uint64_t)k + 3;
         ctx->n_prepared = (uint32_t)h_nprep; ctx->cnt.spectra_prepared = (uint64_t)h_nprep;
-        ctx->max_blob = blob_bytes((ctx->max_peaks + 3u) & ~3u);
+        ctx->max_blob = blob_bytes(ctx->max_peaks);
     }
     CU(cudaGetLastError());
     mk.mark("prepare launch");
@@ -1015,7 +1015,7 @@ int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms) {
             CU(ctx->hits.reserve((size_t)cap * sizeof(Hit)));
             CU(cudaMemsetAsync(ctx->hit_count.p, 0, 4, st));
             PtmLaunch L; memset(&L, 0, sizeof L);
-            L.jobs = ctx->jobs.as<Job>(); L.n_jobs = (uint32_t)hj.size(); L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>();
+            L.jobs = ctx->jobs.as<Job>(); L.n_jobs = (uint32_t)hj.size(); L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>(); L.blob_len = ctx->blob_len.as<uint32_t>();
             L.rows = R.rows.as<uint8_t>(); L.row_mass = R.mass.as<double>(); L.row_mask = R.mask.as<uint32_t>(); L.n_rows = (uint32_t)R.n();
             L.ptms = d_ptm.as<pq_ptm>(); L.n_ptm = n_ptm; L.n_isotope = ctx->P.n_isotope;
             for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) L.isotope[i] = ctx->P.isotope[i];
@@ -1115,7 +1115,7 @@ int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_ind
     SpectraView sp = ctx->view();
     // this call owns the prepared-spectrum pool: invalidate the step pipeline's blobs
     ctx->step_done = std::min(ctx->step_done, 1); ctx->n_prepared = 0;
-    CU(ctx->scratch.reserve((list.size() + 2) * 8)); CU(ctx->blob_off.reserve((list.size() + 2) * 8));
+    CU(ctx->scratch.reserve((list.size() + 2) * 8)); CU(ctx->blob_off.reserve((list.size() + 2) * 8)); CU(ctx->blob_len.reserve((list.size() + 2) * 4));
     launch_blob_sizes(sp, d_list.as<int32_t>(), (int32_t)list.size(), ctx->scratch.as<uint64_t>(), st);
     int32_t rc = scan_exclusive(ctx, ctx->scratch.as<uint64_t>(), ctx->blob_off.as<uint64_t>(), (int)list.size() + 1);
     if (rc) return rc;
@@ -1127,16 +1127,16 @@ int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_ind
     pc.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (ctx->P.itol * 2.0));
     {
         Timer t(ctx, &ctx->cnt.ms_prepare);
-        ctx->cnt.other_kernel_launches += (uint64_t)launch_prepare(sp, d_list.as<int32_t>(), (int32_t)list.size(), pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(), ctx->max_peaks, st) + 2;
+        ctx->cnt.other_kernel_launches += (uint64_t)launch_prepare(sp, d_list.as<int32_t>(), (int32_t)list.size(), pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(), ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st) + 2;
     }
-    ctx->max_blob = blob_bytes((ctx->max_peaks + 3u) & ~3u);
+    ctx->max_blob = blob_bytes(ctx->max_peaks);
     CU(ctx->jobs.reserve(hj.size() * sizeof(Job)));
     CU(cudaMemcpyAsync(ctx->jobs.p, hj.data(), hj.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
     CU(ctx->results.reserve(hj.size() * sizeof(JobResult))); CU(ctx->hits.reserve(64)); CU(ctx->hit_count.reserve(64));
     CU(cudaMemsetAsync(ctx->hit_count.p, 0, 4, st));
     ScoreLaunch L; memset(&L, 0, sizeof L);
     L.kind = kJobPairs; L.jobs = ctx->jobs.as<Job>(); L.n_jobs = (uint32_t)hj.size();
-    L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>(); L.rows = d_rows.as<uint8_t>(); L.row_mass = nullptr;
+    L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>(); L.blob_len = ctx->blob_len.as<uint32_t>(); L.rows = d_rows.as<uint8_t>(); L.row_mass = nullptr;
     L.mods = ctx->d_mods.as<ModTable>(); L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>(); L.row_pred = nullptr;
     L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>(); L.hit_capacity = 0;
     L.pair_score = d_score.as<double>(); L.pair_a = d_a.as<int32_t>(); L.pair_b = d_b.as<int32_t>(); L.max_blob_bytes = ctx->max_blob;

@@ -38,20 +38,32 @@ struct ModTable {
 
 // ---- prepared spectrum blob (output of K0, input of K1) -----------------------------------------------------------
 // Everything K1 needs about one spectrum, contiguous and 16-byte aligned so one cp.async.bulk stages it:
-//   BlobHeader | pmz f64[Epad] | pinfo u32[Epad] | val f64[kValSlots] | cells u16[kCells]
-// pmz   : m/z of the peaks the annotator may match (intensity >= 5th-percentile limit), ascending
-// pinfo : (intensity rank << 16) | (class << 12) | survivor id (0xFFF = the peak did not survive pre-processing)
-// val   : hyperscore: normalised intensity of survivor id; MVH: unused
-// cells : first index i with cell(pmz[i]) >= c, for the monotone cell map below
-constexpr int kCells = 2304;         // 9 binades [32, 16384) x 256 cells
-constexpr int kCellShift = 12;       // keep 8 mantissa bits of the high word
-constexpr uint32_t kCellBase = 0x40400000u >> kCellShift;   // high word of 32.0
+//   BlobHeader | ev f64[NE] | ans u16[NE pad 8] | pmz f64[E+1 pad 2] | pinfo u32[E pad 4] | val f64[kValSlots] | cells u16[kCells]
+//
+// The annotator's question "which matchable peak is the most intense one with |mz - t| <= itol" (JMatch.java:411-451,
+// A2-A4) has a piecewise-constant answer in t.  K0 inverts the predicate once per spectrum: for every matchable peak j
+// the set {t : fabs(fl(mz_j - t)) <= itol} is an interval of doubles [lo_j, hi_j] whose end points are found by testing
+// the predicate itself on neighbouring doubles, so membership is bit-exact.  The sorted end points are the events:
+//   ev    : ev[0] = -inf, then every lo_j (peak j enters at t >= lo_j) and nextup(hi_j) (leaves), ascending, then +inf
+//   ans   : answer for ev[k] <= t < ev[k+1]: 0xFFFF = nothing to claim; 0x8000|a = two in-window peaks tie on intensity,
+//           take the exact scan from peak a (pmz/pinfo); else the claim code of the winner: hyperscore = survivor id,
+//           MVH = (class << 12) | survivor id (a winner that did not survive pre-processing, or an MVH winner outside
+//           200..2000 Th, is already folded into 0xFFFF)
+//   pmz   : m/z of the matchable peaks (intensity >= 5th-percentile limit), ascending, +inf after the last
+//   pinfo : (intensity rank << 16) | (class << 12) | survivor id (0xFFF = the peak did not survive pre-processing)
+//   val   : hyperscore: normalised intensity of survivor id; MVH: unused
+//   cells : cells[c] = index of the last event below the lower edge of cell c of the monotone m/z -> cell map
+constexpr int kCellShift = 11;                              // 512 cells per binade
+constexpr uint32_t kCellBase = 0x40600000u >> kCellShift;   // high word of 128.0
+constexpr int kCells = 5 * 512;                             // [128, 4096) Th; below / above clamp to the first / last cell
 constexpr int kValSlots = 64;
 constexpr uint32_t kNoSurvivor = 0xFFFu;
+constexpr uint32_t kAnsNone = 0xFFFFu;
+constexpr uint32_t kAnsTie = 0x8000u;
 
 struct BlobHeader {
     uint32_t n_peaks;        // E
-    uint32_t n_pad;          // E rounded up to a multiple of 4 (keeps the sections 16-byte aligned)
+    uint32_t n_events;       // NE = 2E + 2
     uint32_t n_survivors;    // hyperscore: distinct surviving m/z (<= 50); MVH: surviving peaks N (<= 300)
     uint32_t flags;          // bit0: MVH pre-processing succeeded (N >= 7)
     int32_t  cls_count[4];   // MVH intenClassCounts[0..2], [3] = bins - N
@@ -61,9 +73,20 @@ struct BlobHeader {
 };
 static_assert(sizeof(BlobHeader) == 48, "BlobHeader must stay 16-byte aligned");
 
-PQ_HD uint32_t blob_bytes(uint32_t e_pad) {
-    return (uint32_t)sizeof(BlobHeader) + e_pad * 8u + e_pad * 4u + kValSlots * 8u + kCells * 2u;
+struct BlobLayout { uint32_t ev, ans, pmz, pinfo, val, cells, total; };
+PQ_HD BlobLayout blob_layout(uint32_t E) {
+    BlobLayout L;
+    const uint32_t ne = 2u * E + 2u;
+    L.ev = (uint32_t)sizeof(BlobHeader);
+    L.ans = L.ev + ne * 8u;
+    L.pmz = L.ans + ((ne * 2u + 15u) & ~15u);
+    L.pinfo = L.pmz + (((E + 1u) * 8u + 15u) & ~15u);
+    L.val = L.pinfo + ((E * 4u + 15u) & ~15u);
+    L.cells = L.val + kValSlots * 8u;
+    L.total = L.cells + kCells * 2u;
+    return L;
 }
+PQ_HD uint32_t blob_bytes(uint32_t n_peaks) { return blob_layout(n_peaks).total; }
 
 PQ_HD uint32_t hi32(double x) {
 #ifdef __CUDA_ARCH__
@@ -75,7 +98,6 @@ PQ_HD uint32_t hi32(double x) {
 // Monotone map m/z -> cell: the high word of a positive double orders like the double itself.
 PQ_HD int cell_of(double mz) {
     int c = (int)(hi32(mz) >> kCellShift) - (int)kCellBase;
-    if (mz < 32.0) c = 0;
     return c < 0 ? 0 : (c >= kCells ? kCells - 1 : c);
 }
 

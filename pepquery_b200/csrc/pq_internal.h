@@ -96,7 +96,7 @@ struct ScoreConfig {
 struct ScoreLaunch {
     JobKind kind;
     const Job* jobs; uint32_t n_jobs;
-    const uint8_t* blobs; const uint64_t* blob_off;       // prepared spectra
+    const uint8_t* blobs; const uint64_t* blob_off; const uint32_t* blob_len;   // prepared spectra (slot offsets, used bytes)
     const uint8_t* rows; const double* row_mass;           // candidate table (64-byte rows) + masses (may be null)
     const ModTable* mods;
     const double* log10_fact;                              // [65]  log10(n!)
@@ -112,7 +112,7 @@ struct ScoreLaunch {
 
 // kernel launchers (each returns the number of kernels it launched; errors via cudaGetLastError by the caller)
 int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, const PrepConfig& cfg, uint8_t* blobs,
-                   const uint64_t* blob_off, uint32_t max_peaks, cudaStream_t st);
+                   const uint64_t* blob_off, uint32_t* blob_len, uint32_t max_peaks, cudaStream_t st);
 int launch_score(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st);
 
 // Step-2 window enumeration on device: for every usable spectrum x isotope error, the run of target rows whose mass
@@ -162,7 +162,7 @@ int launch_fix_job_blobs(Job* jobs, uint32_t n_jobs, const int32_t* prep_id, cud
 // Step 5 (k5_ptm.cu): one job per validated spectrum; candidates are enumerated inside the kernel
 struct PtmLaunch {
     const Job* jobs; uint32_t n_jobs;                      // mass = precursor neutral mass, ref_score = target PSM score
-    const uint8_t* blobs; const uint64_t* blob_off;
+    const uint8_t* blobs; const uint64_t* blob_off; const uint32_t* blob_len;
     const uint8_t* rows; const double* row_mass; const uint32_t* row_mask; uint32_t n_rows;   // reference table
     const pq_ptm* ptms; int32_t n_ptm;
     int32_t n_isotope; int32_t isotope[PQ_MAX_ISOTOPE];
