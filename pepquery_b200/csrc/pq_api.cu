@@ -62,6 +62,7 @@ struct pq_ctx {
     std::string err;
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, uev0 = nullptr, uev1 = nullptr;
+    void* stage_host = nullptr; cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     pq_counters cnt;
     struct PendingTimer { cudaEvent_t a, b; double* acc; double* acc2; };
     std::vector<PendingTimer> timers; std::vector<cudaEvent_t> free_events;
@@ -235,6 +236,36 @@ template <class K, class V> int32_t sort_pairs(pq_ctx* ctx, const K* kin, K* kou
     return PQ_OK;
 }
 
+// Device -> caller buffer.  A pinned (page-locked) caller buffer takes the DMA directly; pageable memory goes through the
+// context's pinned staging buffer in two alternating halves so the DMA of one chunk overlaps the memcpy of the previous one.
+int32_t copy_to_caller(pq_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!bytes) return PQ_OK;
+    cudaPointerAttributes at; memset(&at, 0, sizeof at);
+    bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        return PQ_OK;
+    }
+    const size_t kChunk = 4u << 20;
+    if (!ctx->stage_host) { CU(cudaHostAlloc(&ctx->stage_host, 2 * kChunk, cudaHostAllocDefault)); CU(cudaEventCreateWithFlags(&ctx->stage_ev[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&ctx->stage_ev[1], cudaEventDisableTiming)); }
+    size_t n_chunks = (bytes + kChunk - 1) / kChunk;
+    for (size_t c = 0; c <= n_chunks; ++c) {
+        if (c < n_chunks) {
+            size_t off = c * kChunk, len = std::min(kChunk, bytes - off);
+            CU(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->stage_host) + (c & 1) * kChunk, static_cast<const uint8_t*>(src) + off, len, cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaEventRecord(ctx->stage_ev[c & 1], ctx->st));
+        }
+        if (c > 0) {
+            size_t off = (c - 1) * kChunk, len = std::min(kChunk, bytes - off);
+            CU(cudaEventSynchronize(ctx->stage_ev[(c - 1) & 1]));
+            memcpy(static_cast<uint8_t*>(dst) + off, static_cast<uint8_t*>(ctx->stage_host) + ((c - 1) & 1) * kChunk, len);
+        }
+    }
+    return PQ_OK;
+}
+
 void reset_psm_state(pq_ctx* ctx) { ctx->n_psm = 0; ctx->n_seg = 0; ctx->nh3 = 0; ctx->have_shuffles = false; ctx->psms.clear(); ctx->comp5.clear(); }
 
 }  // namespace
@@ -300,6 +331,7 @@ int32_t pq_destroy(pq_ctx* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     flush_timers(ctx);
+    if (ctx->stage_host) { cudaFreeHost(ctx->stage_host); cudaEventDestroy(ctx->stage_ev[0]); cudaEventDestroy(ctx->stage_ev[1]); }
     for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
     if (ctx->uev0) cudaEventDestroy(ctx->uev0);
     if (ctx->uev1) cudaEventDestroy(ctx->uev1);
@@ -903,8 +935,8 @@ int32_t pq_get_psms(pq_ctx* ctx, pq_psm* out, int64_t capacity, int64_t* n_psms)
     const size_t bytes = (size_t)ctx->n_psm * sizeof(pq_psm);
     CU(ctx->d_export.reserve(bytes));
     ctx->cnt.other_kernel_launches += (uint64_t)launch_export_psms(ctx->d_psm.as<DevPsm>(), ctx->d_out_perm.as<uint32_t>(), ctx->n_psm, ctx->d_export.as<pq_psm>(), ctx->st);
-    CU(cudaMemcpyAsync(out, ctx->d_export.p, bytes, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
+    int32_t rc = copy_to_caller(ctx, out, ctx->d_export.p, bytes);
+    if (rc) return rc;
     ctx->cnt.d2h_bytes += bytes;
     return PQ_OK;
 }
@@ -945,8 +977,8 @@ int32_t pq_get_competitors(pq_ctx* ctx, int32_t step, pq_competitor* out, int64_
     if (rc) return rc;
     k += launch_gather_comp(rows.as<pq_competitor>(), idx2.as<uint32_t>(), n, rows2.as<pq_competitor>(), st);
     ctx->cnt.other_kernel_launches += (uint64_t)k + 4;
-    CU(cudaMemcpyAsync(out, rows2.p, (size_t)n * sizeof(pq_competitor), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    rc = copy_to_caller(ctx, out, rows2.p, (size_t)n * sizeof(pq_competitor));
+    if (rc) return rc;
     ctx->cnt.d2h_bytes += (uint64_t)n * sizeof(pq_competitor) + 4;
     return PQ_OK;
 }

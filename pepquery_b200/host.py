@@ -158,19 +158,29 @@ class Search:
         arr = (_abi.pq_ptm * max(1, len(ptms)))(*ptms)
         self._ck(self.L.pq_step5_ptm(self.h, C.c_int32(len(ptms)), arr))
 
-    def psms(self):
+    def psms(self, out=None):
+        """PSM records in the caller's spectrum order.  `out`: optional uint8 buffer (e.g. pinned memory) to fill."""
         n = C.c_int64()
         self._ck(self.L.pq_get_psms(self.h, None, C.c_int64(0), C.byref(n)))
-        arr = (_abi.pq_psm * max(1, n.value))()
-        self._ck(self.L.pq_get_psms(self.h, arr, C.c_int64(n.value), C.byref(n)))
-        return np.frombuffer(arr, dtype=psm_dtype(), count=n.value).copy()
+        dt = psm_dtype()
+        if out is None:
+            arr = np.empty(max(1, n.value), dtype=dt)
+        else:
+            arr = np.frombuffer(out, dtype=dt, count=max(1, n.value))
+        self._ck(self.L.pq_get_psms(self.h, _p(arr), C.c_int64(n.value), C.byref(n)))
+        return arr[:n.value]
+
+    def psm_count(self):
+        n = C.c_int64()
+        self._ck(self.L.pq_get_psms(self.h, None, C.c_int64(0), C.byref(n)))
+        return n.value
 
     def competitors(self, step=3):
         n = C.c_int64()
         self._ck(self.L.pq_get_competitors(self.h, C.c_int32(step), None, C.c_int64(0), C.byref(n)))
-        arr = (_abi.pq_competitor * max(1, n.value))()
-        self._ck(self.L.pq_get_competitors(self.h, C.c_int32(step), arr, C.c_int64(n.value), C.byref(n)))
-        return np.frombuffer(arr, dtype=competitor_dtype(), count=n.value).copy()
+        arr = np.empty(max(1, n.value), dtype=competitor_dtype())
+        self._ck(self.L.pq_get_competitors(self.h, C.c_int32(step), _p(arr), C.c_int64(n.value), C.byref(n)))
+        return arr[:n.value]
 
     def shuffles(self, target_seq, length):
         n = C.c_int32()
@@ -222,10 +232,10 @@ class Search:
         """StatisticScoreCalc.run (pg/StatisticScoreCalc.java:19-63)."""
         self.step4()
 
-    def rank_psms(self):
+    def rank_psms(self, out=None):
         """RankPSM.rankPSMs (pg/RankPSM.java:36) + CParameter.passed_psm_validation (pg/CParameter.java:913)."""
         self.rank()
-        return self.psms()
+        return self.psms(out)
 
     def do_ptm_validation(self, ptms):
         """ModificationDB.doPTMValidation (OpenModificationSearch/ModificationDB.java:1320-1466)."""
