@@ -106,6 +106,8 @@ __device__ __forceinline__ PairScore score_pair(const uint32_t* codes /* this th
     double sum = 0.0;
     if (METHOD == 2) for (int w = 0; w < 10; ++w) usedw[w * BLOCK] = 0u;
 
+    // Claim in annotator order (A5): a surviving peak counts once, for the first ion that reaches it.
+    // (A branch-free variant — a miss adding +0.0 — was measured slower on the Step-4 launch: most lanes miss.)
     auto claim = [&](uint32_t code, bool is_b) {
         if (code == kAnsNone) return;
         if (METHOD == 1) {

@@ -13,7 +13,13 @@
 // window) have the same or similar lengths, so 32 pairs walk their fragment ladders in lock-step with no divergence,
 // the b-before-y claim order and the sequential FP64 intensity sum of the reference fall out of program order, and no
 // shuffle/ballot traffic is spent on 1-2 ions per lane.  See DESIGN.md §K1.
+#include <cstdlib>
+
 #include "k1_device.cuh"
+
+#ifndef K1_MIN_BLOCKS
+#define K1_MIN_BLOCKS 4
+#endif
 
 namespace pq {
 
@@ -22,7 +28,7 @@ namespace {
 using namespace dev;
 
 template <int BLOCK, int METHOD>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? K1_MIN_BLOCKS : 1)
 k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -36,7 +42,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     double* s_nt = s_dl + kMaxCodes;
     double* s_ct = s_nt + kMaxTermCodes;
     double* s_l10 = s_ct + kMaxTermCodes;                                                              // [65]
-    uint32_t* usedw_all = reinterpret_cast<uint32_t*>(s_l10 + 66);                                     // MVH [10][BLOCK]
+    uint32_t* usedw_all = reinterpret_cast<uint32_t*>(s_l10 + 66);                                     // MVH only: [10][BLOCK]
 
     const int tid = threadIdx.x;
     for (int i = tid; i < kMaxCodes; i += BLOCK) { s_aa[i] = L.mods->aa[i]; s_dl[i] = L.mods->delta[i]; }
@@ -49,28 +55,26 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     uint32_t* codes = codes_all + tid;
     uint32_t* usedw = usedw_all + tid;
 
-    uint32_t job = blockIdx.x;
-    uint32_t it = 0;
-    // prologue: stage the first job's blob
-    if (job < L.n_jobs && tid == 0) {
-        const Job& J = L.jobs[job];
-        uint32_t bytes = L.blob_len[J.blob];
-        mbar_expect_tx(&s_bar[0], bytes);
-        tma_load_1d(stage0, L.blobs + L.blob_off[J.blob], bytes, &s_bar[0]);
-    }
-    for (; job < L.n_jobs; job += gridDim.x, ++it) {
+    // Jobs are handed out by an atomic counter (in list order, so neighbouring CTAs share table rows in L2); the next
+    // job's blob is already in flight (second stage) while the current one is scored.
+    __shared__ uint32_t s_job[2];
+    auto fetch = [&](uint32_t slot) {           // thread 0: take the next job and start its TMA into `slot`
+        uint32_t nj = atomicAdd(L.job_counter, 1u);
+        s_job[slot] = nj;
+        if (nj < L.n_jobs) {
+            const Job& Jn = L.jobs[nj];
+            uint32_t bytes = L.blob_len[Jn.blob];
+            mbar_expect_tx(&s_bar[slot], bytes);
+            tma_load_1d(stage0 + (size_t)stage_bytes * slot, L.blobs + L.blob_off[Jn.blob], bytes, &s_bar[slot]);
+        }
+    };
+    if (tid == 0) fetch(0);
+    __syncthreads();
+    uint32_t job = s_job[0];
+    for (uint32_t it = 0; job < L.n_jobs; ++it) {
         const uint32_t cur = nstage == 2 ? (it & 1u) : 0u;
         const uint32_t parity = nstage == 2 ? ((it >> 1) & 1u) : (it & 1u);
-        // prefetch the next job's blob into the other stage
-        if (nstage == 2) {
-            uint32_t nj = job + gridDim.x;
-            if (nj < L.n_jobs && tid == 0) {
-                const Job& Jn = L.jobs[nj];
-                uint32_t bytes = L.blob_len[Jn.blob];
-                mbar_expect_tx(&s_bar[cur ^ 1u], bytes);
-                tma_load_1d(stage0 + (size_t)stage_bytes * (cur ^ 1u), L.blobs + L.blob_off[Jn.blob], bytes, &s_bar[cur ^ 1u]);
-            }
-        }
+        if (nstage == 2 && tid == 0) fetch(cur ^ 1u);
         const Job J = L.jobs[job];
         mbar_wait(&s_bar[cur], parity);
         const BlobView B = view_blob(stage0 + (size_t)stage_bytes * cur);
@@ -139,42 +143,39 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
             }
             JobResult R; R.n_in_window = a; R.n_better = b; R.best_score = bs; R.best_cand = bc; R.pad = 0;
             L.results[job] = R;
-            if (nstage == 1) {
-                uint32_t nj = job + gridDim.x;
-                if (nj < L.n_jobs) {
-                    const Job& Jn = L.jobs[nj];
-                    uint32_t bytes = L.blob_len[Jn.blob];
-                    mbar_expect_tx(&s_bar[0], bytes);
-                    tma_load_1d(stage0, L.blobs + L.blob_off[Jn.blob], bytes, &s_bar[0]);
-                }
-            }
+            if (nstage == 1) fetch(0);
         }
         __syncthreads();
+        job = s_job[nstage == 2 ? (cur ^ 1u) : 0u];
     }
 }
 
-template <int BLOCK>
-int launch_block(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
-    uint32_t stage = (L.max_blob_bytes + 127u) & ~127u;
-    size_t tail = (size_t)16 * BLOCK * 4 + (size_t)(2 * kMaxCodes + 2 * kMaxTermCodes + 66) * 8 + (size_t)10 * BLOCK * 4;
-    int nstage = 2;
+template <int BLOCK, int METHOD>
+int launch_kernel(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
+    const uint32_t stage = (L.max_blob_bytes + 127u) & ~127u;
+    const size_t tail = (size_t)16 * BLOCK * 4 + (size_t)(2 * kMaxCodes + 2 * kMaxTermCodes + 66) * 8 + (METHOD == 2 ? (size_t)10 * BLOCK * 4 : 0);
+    // Shuffle jobs (~1000 pairs each) hide the blob load behind a second stage; target / competitor jobs are short, there
+    // one stage and more resident CTAs win (measured: Step 2 9.1 -> 5.4 ms, Step 3 18.7 -> 13.4 ms).
+    int nstage = BLOCK == 256 ? 2 : 1;
     if ((size_t)stage * 2 + tail > 100 * 1024) nstage = 1;
-    size_t smem = (size_t)stage * nstage + tail;
-    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    int per_sm = (int)((220 * 1024) / (smem + 2048));
-    int by_threads = 2048 / BLOCK;
-    if (per_sm > by_threads) per_sm = by_threads;
+    if (const char* e = getenv("PQ_K1_STAGES")) nstage = atoi(e) == 1 ? 1 : (atoi(e) == 2 ? 2 : nstage);
+    const size_t smem = (size_t)stage * nstage + tail;
+    auto kernel = k1_score_kernel<BLOCK, METHOD>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0; cudaGetDevice(&dev);
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, smem);      // resident CTAs: registers, shared memory, warps
     if (per_sm < 1) per_sm = 1;
     uint32_t grid = (uint32_t)(sms * per_sm);
     if (grid > L.n_jobs) grid = L.n_jobs;
-    if (cfg.method == 2) {
-        cudaFuncSetAttribute(k1_score_kernel<BLOCK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k1_score_kernel<BLOCK, 2><<<grid, BLOCK, smem, st>>>(L, cfg, stage, nstage);
-    } else {
-        cudaFuncSetAttribute(k1_score_kernel<BLOCK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k1_score_kernel<BLOCK, 1><<<grid, BLOCK, smem, st>>>(L, cfg, stage, nstage);
-    }
+    cudaMemsetAsync(L.job_counter, 0, 4, st);
+    kernel<<<grid, BLOCK, smem, st>>>(L, cfg, stage, nstage);
     return 1;
+}
+template <int BLOCK>
+int launch_block(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
+    return cfg.method == 2 ? launch_kernel<BLOCK, 2>(L, cfg, st) : launch_kernel<BLOCK, 1>(L, cfg, st);
 }
 
 }  // namespace

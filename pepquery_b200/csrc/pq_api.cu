@@ -91,7 +91,8 @@ struct pq_ctx {
     // device-resident PSM table (K7)
     DevBuf d_psm, d_seg_start, d_out_perm, d_scalars, d_counters, d_agg, hits3, d_export;
     DevBuf k_key_a, k_key_b, k_idx_a, k_idx_b, k_head;
-    uint32_t n_psm = 0, n_seg = 0, nh3 = 0;
+    uint32_t n_psm = 0, n_seg = 0, nh3 = 0, comp3_n = 0; bool comp3_ready = false;
+    DevBuf c_rows, c_rows2, c_keys, c_keys2, c_idx, c_idx2;
     double psm_mass_lo = 0.0, psm_mass_hi = 0.0;
     // target-table side arrays on the device
     DevBuf t_form_of_row, t_seq_of_form, t_strrank, t_form_mods, t_seq_off, t_seq_letters;
@@ -188,7 +189,7 @@ int32_t run_score(pq_ctx* ctx, JobKind kind, uint32_t n_jobs, const int32_t* row
     L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>();
     L.row_pred = row_pred;
     L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>();
-    L.hit_capacity = hit_capacity; L.max_blob_bytes = ctx->max_blob;
+    L.hit_capacity = hit_capacity; L.max_blob_bytes = ctx->max_blob; L.job_counter = ctx->d_scalars.as<uint32_t>() + 12;
     ScoreConfig cfg = score_config(ctx, check_window);
     {
         int si = kind == kJobTargets ? 0 : kind == kJobCompetitors ? 1 : kind == kJobShuffles ? 2 : 3;
@@ -266,7 +267,7 @@ int32_t copy_to_caller(pq_ctx* ctx, void* dst, const void* src, size_t bytes) {
     return PQ_OK;
 }
 
-void reset_psm_state(pq_ctx* ctx) { ctx->n_psm = 0; ctx->n_seg = 0; ctx->nh3 = 0; ctx->have_shuffles = false; ctx->psms.clear(); ctx->comp5.clear(); }
+void reset_psm_state(pq_ctx* ctx) { ctx->n_psm = 0; ctx->n_seg = 0; ctx->nh3 = 0; ctx->comp3_ready = false; ctx->comp3_n = 0; ctx->have_shuffles = false; ctx->psms.clear(); ctx->comp5.clear(); }
 
 }  // namespace
 
@@ -763,7 +764,7 @@ int32_t pq_step3_competitors(pq_ctx* ctx) {
     Marks mk("step3");
     PeptideTable& R = ctx->reference;
     cudaStream_t st = ctx->st;
-    ctx->nh3 = 0;
+    ctx->nh3 = 0; ctx->comp3_ready = false; ctx->comp3_n = 0;
     const uint32_t n_seg = ctx->n_seg;
     if (n_seg == 0 || R.n() == 0) {
         // no matched spectrum, or an empty reference table: every PSM keeps n_db = total_db = 0
@@ -952,34 +953,41 @@ int32_t pq_get_competitors(pq_ctx* ctx, int32_t step, pq_competitor* out, int64_
         return PQ_OK;
     }
     // Step 3 detail rows: better-or-equal competitors with score >= 20 (the K1 hit rows) plus the best competitor of each
-    // spectrum when its score > 0 (pg/DBSearchWorker.java:71-76, 93-98), sorted by (spectrum, reference row) on the device
+    // spectrum when its score > 0 (pg/DBSearchWorker.java:71-76, 93-98), sorted by (spectrum, reference row) on the device.
+    // Built once per Step 3 (first call), the size query and the fill share it.
     *n_rows = 0;
     if (ctx->step_done < 3 || ctx->n_seg == 0 || !ctx->have_reference || ctx->reference.n() == 0) return PQ_OK;
     cudaSetDevice(ctx->P.device);
     cudaStream_t st = ctx->st;
-    const size_t cap = (size_t)ctx->nh3 + ctx->n_seg;
-    DevBuf rows, rows2, keys, keys2, idx, idx2;
-    CU(rows.reserve(cap * sizeof(pq_competitor))); CU(rows2.reserve(cap * sizeof(pq_competitor)));
-    CU(keys.reserve(cap * 8)); CU(keys2.reserve(cap * 8)); CU(idx.reserve(cap * 4)); CU(idx2.reserve(cap * 4));
-    uint32_t* d_cnt = ctx->d_scalars.as<uint32_t>() + 8;
-    CU(cudaMemsetAsync(d_cnt, 0, 4, st));
-    int k = launch_comp3_rows(ctx->hits3.as<Hit>(), ctx->nh3, ctx->d_agg.as<SegAgg>(), ctx->n_seg, ctx->d_seg_start.as<uint32_t>(), ctx->d_psm.as<DevPsm>(),
-                              ctx->s_caller.as<int32_t>(), ctx->reference.mass.as<double>(), rows.as<pq_competitor>(), keys.as<uint64_t>(), idx.as<uint32_t>(), d_cnt, st);
-    uint32_t extra = 0;
-    CU(cudaMemcpyAsync(&extra, d_cnt, 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    const uint32_t n = ctx->nh3 + extra;
-    *n_rows = (int64_t)n;
+    if (!ctx->comp3_ready) {
+        const size_t cap = (size_t)ctx->nh3 + ctx->n_seg;
+        CU(ctx->c_rows.reserve(cap * sizeof(pq_competitor))); CU(ctx->c_rows2.reserve(cap * sizeof(pq_competitor)));
+        CU(ctx->c_keys.reserve(cap * 8)); CU(ctx->c_keys2.reserve(cap * 8)); CU(ctx->c_idx.reserve(cap * 4)); CU(ctx->c_idx2.reserve(cap * 4));
+        uint32_t* d_cnt = ctx->d_scalars.as<uint32_t>() + 8;
+        CU(cudaMemsetAsync(d_cnt, 0, 4, st));
+        int k = launch_comp3_rows(ctx->hits3.as<Hit>(), ctx->nh3, ctx->d_agg.as<SegAgg>(), ctx->n_seg, ctx->d_seg_start.as<uint32_t>(), ctx->d_psm.as<DevPsm>(),
+                                  ctx->s_caller.as<int32_t>(), ctx->reference.mass.as<double>(), ctx->c_rows.as<pq_competitor>(), ctx->c_keys.as<uint64_t>(),
+                                  ctx->c_idx.as<uint32_t>(), d_cnt, st);
+        uint32_t extra = 0;
+        CU(cudaMemcpyAsync(&extra, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const uint32_t n = ctx->nh3 + extra;
+        if (n) {
+            int32_t rc = sort_pairs(ctx, ctx->c_keys.as<uint64_t>(), ctx->c_keys2.as<uint64_t>(), ctx->c_idx.as<uint32_t>(), ctx->c_idx2.as<uint32_t>(), (int)n, 64);
+            if (rc) return rc;
+            k += launch_gather_comp(ctx->c_rows.as<pq_competitor>(), ctx->c_idx2.as<uint32_t>(), n, ctx->c_rows2.as<pq_competitor>(), st);
+        }
+        ctx->cnt.other_kernel_launches += (uint64_t)k + (n ? 4 : 0);
+        ctx->cnt.d2h_bytes += 4;
+        ctx->comp3_n = n; ctx->comp3_ready = true;
+    }
+    *n_rows = (int64_t)ctx->comp3_n;
     if (!out) return PQ_OK;
     if (capacity < *n_rows) return fail(ctx, PQ_ERR_CAPACITY, "competitor buffer too small");
-    if (!n) return PQ_OK;
-    int32_t rc = sort_pairs(ctx, keys.as<uint64_t>(), keys2.as<uint64_t>(), idx.as<uint32_t>(), idx2.as<uint32_t>(), (int)n, 64);
+    if (!ctx->comp3_n) return PQ_OK;
+    int32_t rc = copy_to_caller(ctx, out, ctx->c_rows2.p, (size_t)ctx->comp3_n * sizeof(pq_competitor));
     if (rc) return rc;
-    k += launch_gather_comp(rows.as<pq_competitor>(), idx2.as<uint32_t>(), n, rows2.as<pq_competitor>(), st);
-    ctx->cnt.other_kernel_launches += (uint64_t)k + 4;
-    rc = copy_to_caller(ctx, out, rows2.p, (size_t)n * sizeof(pq_competitor));
-    if (rc) return rc;
-    ctx->cnt.d2h_bytes += (uint64_t)n * sizeof(pq_competitor) + 4;
+    ctx->cnt.d2h_bytes += (uint64_t)ctx->comp3_n * sizeof(pq_competitor);
     return PQ_OK;
 }
 
@@ -1111,6 +1119,7 @@ int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_ind
     if (n_pairs == 0) return PQ_OK;
     if (n_pairs > 0x7ffffff0LL) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many pairs for one call");
     cudaSetDevice(ctx->P.device);
+    { int32_t rc0 = ensure_counters(ctx); if (rc0) return rc0; }
     cudaStream_t st = ctx->st;
     const int64_t n = ctx->nS;
     // caller index -> sorted index
@@ -1171,7 +1180,7 @@ int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_ind
     L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>(); L.blob_len = ctx->blob_len.as<uint32_t>(); L.rows = d_rows.as<uint8_t>(); L.row_mass = nullptr;
     L.mods = ctx->d_mods.as<ModTable>(); L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>(); L.row_pred = nullptr;
     L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>(); L.hit_capacity = 0;
-    L.pair_score = d_score.as<double>(); L.pair_a = d_a.as<int32_t>(); L.pair_b = d_b.as<int32_t>(); L.max_blob_bytes = ctx->max_blob;
+    L.pair_score = d_score.as<double>(); L.pair_a = d_a.as<int32_t>(); L.pair_b = d_b.as<int32_t>(); L.max_blob_bytes = ctx->max_blob; L.job_counter = ctx->d_scalars.as<uint32_t>() + 12;
     if (ctx->P.score_method == 2) {
         CU(d_pred.reserve((size_t)n_pairs * 8));
         ctx->cnt.other_kernel_launches += (uint64_t)launch_predict(d_rows.as<uint8_t>(), (uint32_t)n_pairs, ctx->d_mods.as<ModTable>(), ctx->P.itol, d_pred.as<int32_t>(), st);

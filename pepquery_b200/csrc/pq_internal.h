@@ -106,6 +106,7 @@ struct ScoreLaunch {
     Hit* hits; uint32_t* hit_count; uint32_t hit_capacity; // appended rows
     double* pair_score; int32_t* pair_a; int32_t* pair_b;  // kJobPairs: per-candidate outputs
     uint32_t max_blob_bytes;
+    uint32_t* job_counter;                                 // device word, zeroed by the launcher: next job to hand out
     // Step 5
     double ptm_delta; int32_t ptm_position; int32_t ptm_residue_code;
 };
