@@ -29,7 +29,7 @@ struct WarpMem {
     uint16_t* ord; uint16_t* ordI; uint16_t* aux; uint16_t* pr; uint16_t* eidx; uint16_t* cx;
     uint8_t* keep; uint8_t* k2;
 };
-__host__ __device__ inline size_t warp_smem_bytes(uint32_t cap) { return (size_t)cap * (8 * 4 + 2 * 6 + 2) + 64; }      // cap >= 256: the 30*cap bytes behind mz/db hold the cell histogram
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t cap) { return (size_t)cap * (8 * 4 + 2 * 6 + 2) + 64; }      // cap >= 256: the 30*cap bytes behind mz/in hold the cell histogram
 
 __device__ __forceinline__ bool idx_less(const double* key, uint32_t a, uint32_t b) {
     double ka = key[a], kb = key[b];
@@ -158,8 +158,8 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t* base_ptr = smem_raw + (size_t)warp * ((warp_smem_bytes(cap) + 15) & ~(size_t)15);
     WarpMem W;
-    W.mz = reinterpret_cast<double*>(base_ptr); W.db = W.mz + cap; W.in = W.db + cap; W.da = W.in + cap;      // mz / db live to the end
-    W.ord = reinterpret_cast<uint16_t*>(W.da + cap); W.ordI = W.ord + cap; W.aux = W.ordI + cap; W.pr = W.aux + cap; W.eidx = W.pr + cap; W.cx = W.eidx + cap;
+    W.mz = reinterpret_cast<double*>(base_ptr); W.in = W.mz + cap; W.da = W.in + cap; W.db = W.da + cap;      // mz / in live to the end (lo / rem)
+    W.ord = reinterpret_cast<uint16_t*>(W.db + cap); W.ordI = W.ord + cap; W.aux = W.ordI + cap; W.pr = W.aux + cap; W.eidx = W.pr + cap; W.cx = W.eidx + cap;
     W.keep = reinterpret_cast<uint8_t*>(W.cx + cap); W.k2 = W.keep + cap;
     double* val = s_val[warp];
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
@@ -186,25 +186,49 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         sorted = __all_sync(0xffffffffu, sorted);
         __syncwarp();
         if (!sorted) warp_sort_idx(W.ord, W.mz, n, lane);          // stable m/z order (JSpectrum.sortPeaksByMZ)
-        warp_sort_idx(W.ordI, W.in, n, lane);                      // stable intensity order (JSpectrum.sortPeaksByIntensity)
-        for (uint32_t i = lane; i < P; i += 32) W.da[i] = W.in[W.ordI[i]];
-        __syncwarp();
 
-        // annotator intensity limit: Spectrum.getIntensityLimit(percentile, 0.05) (JMatch.java:427-430; A2)
+        // annotator intensity limit: Spectrum.getIntensityLimit(percentile, 0.05) (JMatch.java:427-430; A2) needs the two
+        // order statistics index, index+1 of the raw intensities.  MVH sorts by intensity anyway (the TIC walk needs the
+        // order); hyperscore extracts the index+2 smallest values with warp minima instead of sorting.
         double limit;
-        if (P == 1) limit = W.da[0];
-        else {
-            double indexDouble = __dmul_rn(0.05, (double)(P - 1));
-            int index = (int)indexDouble;
-            double valueAtIndex = W.da[index];
-            double rest = __dsub_rn(indexDouble, (double)index);
-            if (index == (int)P - 1 || rest == 0.0) limit = valueAtIndex;
-            else limit = __dadd_rn(valueAtIndex, __dmul_rn(rest, __dsub_rn(W.da[index + 1], valueAtIndex)));
+        {
+            const double indexDouble = P > 1 ? __dmul_rn(0.05, (double)(P - 1)) : 0.0;
+            const int index = (int)indexDouble;
+            double valueAtIndex, valueNext = 0.0;
+            const bool extract = cfg.method == 1 && P <= 256 && index + 2 <= 24;
+            if (!extract) {
+                warp_sort_idx(W.ordI, W.in, n, lane);              // stable intensity order (JSpectrum.sortPeaksByIntensity)
+                for (uint32_t i = lane; i < P; i += 32) W.da[i] = W.in[W.ordI[i]];
+                __syncwarp();
+                valueAtIndex = W.da[index];
+                if (index + 1 < (int)P) valueNext = W.da[index + 1];
+            } else {
+                uint32_t taken = 0;                                 // bit q: this lane's element lane + 32 q is already extracted
+                valueAtIndex = 0.0;
+                for (int r = 0; r <= index + 1 && r < (int)P; ++r) {
+                    double best = inf; int bq = -1;
+                    for (uint32_t q = 0, i = lane; i < P; ++q, i += 32)
+                        if (!((taken >> q) & 1u)) { double v = W.in[i]; if (bq < 0 || v < best) { best = v; bq = (int)q; } }
+                    // warp minimum by (value, lane): ties may be taken in any order, only the values matter
+                    double mv = best; int ml = bq >= 0 ? lane : 64;
+                    for (int o = 16; o > 0; o >>= 1) {
+                        double ov = __shfl_xor_sync(0xffffffffu, mv, o); int ol = __shfl_xor_sync(0xffffffffu, ml, o);
+                        if (ol < 64 && (ml >= 64 || ov < mv || (ov == mv && ol < ml))) { mv = ov; ml = ol; }
+                    }
+                    if (ml == lane) taken |= 1u << bq;
+                    if (r == index) valueAtIndex = mv;
+                    if (r == index + 1) valueNext = mv;
+                }
+            }
+            if (P == 1) limit = valueAtIndex;
+            else {
+                double rest = __dsub_rn(indexDouble, (double)index);
+                if (index == (int)P - 1 || rest == 0.0) limit = valueAtIndex;
+                else limit = __dadd_rn(valueAtIndex, __dmul_rn(rest, __dsub_rn(valueNext, valueAtIndex)));
+            }
         }
-        // dense intensity rank (+1) of every raw peak, by file index; all peaks kept
         bool has_dup = false;
         for (uint32_t i = lane; i < P; i += 32) {
-            W.pr[i] = (uint16_t)(count_lt(W.da, P, W.in[i]) + 1u);
             W.keep[i] = 1;
             if (i > 0 && W.mz[W.ord[i]] == W.mz[W.ord[i - 1]]) has_dup = true;
         }
@@ -365,14 +389,13 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             flags = N >= 7 ? 1u : 0u;
         }
 
-        // ---- matchable peaks (intensity >= limit) in m/z order: compact m/z -> da, rank -> ordI, claim code -> cx ----
+        // ---- matchable peaks (intensity >= limit) in m/z order: compact m/z -> da, intensity -> db, claim code -> cx ----
         uint32_t E = 0;
         for (uint32_t c0 = 0; c0 < P; c0 += 32) {
             uint32_t i = c0 + lane;
             bool el = i < P && W.in[W.ord[i]] >= limit;
             uint32_t bal = __ballot_sync(0xffffffffu, el);
-            if (i < P) W.eidx[i] = (uint16_t)(E + __popc(bal & ((1u << lane) - 1u)));
-            if (i < P && !el) W.eidx[i] = 0xFFFFu;
+            if (i < P) W.eidx[i] = el ? (uint16_t)(E + __popc(bal & ((1u << lane) - 1u))) : (uint16_t)0xFFFFu;
             E += __popc(bal);
         }
         __syncwarp();
@@ -381,25 +404,24 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         double* g_ev = reinterpret_cast<double*>(blob + BL.ev);
         uint16_t* g_ans = reinterpret_cast<uint16_t*>(blob + BL.ans);
         double* g_pmz = reinterpret_cast<double*>(blob + BL.pmz);
-        uint32_t* g_pinfo = reinterpret_cast<uint32_t*>(blob + BL.pinfo);
+        double* g_pin = reinterpret_cast<double*>(blob + BL.pin);
+        uint16_t* g_pcode = reinterpret_cast<uint16_t*>(blob + BL.pcode);
         double* g_val = reinterpret_cast<double*>(blob + BL.val);
         uint16_t* g_cells = reinterpret_cast<uint16_t*>(blob + BL.cells);
-        // ordI is free from here on (the TIC walk was its last reader)
         for (uint32_t i = lane; i < P; i += 32) {
             uint32_t e = W.eidx[i];
             if (e == 0xFFFFu) continue;
             uint32_t f = W.ord[i];
-            double m = W.mz[f];
+            double m = W.mz[f], v = W.in[f];
             uint32_t code = W.aux[i];
-            W.da[e] = m; W.ordI[e] = W.pr[f]; W.cx[e] = (uint16_t)code;
-            g_pmz[e] = m;
-            g_pinfo[e] = ((uint32_t)W.pr[f] << 16) | code;
+            W.da[e] = m; W.db[e] = v; W.cx[e] = (uint16_t)code;
+            g_pmz[e] = m; g_pin[e] = v; g_pcode[e] = (uint16_t)code;
         }
         if (lane == 0) { g_pmz[E] = inf; if (((E + 1u) & 1u) != 0u) g_pmz[E + 1] = inf; }
         __syncwarp();
         // ---- exact break points of the window predicate fabs(fl(mz - t)) <= itol: enter at lo, leave at rem = nextup(hi) ----
-        // (raw arrays are dead now: lo -> db, rem -> mz)
-        double* lo_a = W.db; double* rem_a = W.mz;
+        // (the raw arrays are dead now: lo -> mz, rem -> in)
+        double* lo_a = W.mz; double* rem_a = W.in;
         for (uint32_t e = lane; e < E; e += 32) {
             const double m = W.da[e];
             double g = __dsub_rn(m, itol);
@@ -416,23 +438,33 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             lo_a[e] = lo; rem_a[e] = next_up(h);
         }
         __syncwarp();
-        // merged, sorted event list (a leave event goes before an enter event of the same value) and its answers
+        // merged, sorted event list (a leave event goes before an enter event of the same value) and its answers.
+        // lo[] and rem[] are the m/z list shifted by -+itol, so the counts below are a short walk from the peak itself.
         const uint32_t NE = 2u * E + 2u;
         for (uint32_t q = lane; q < 2u * E; q += 32) {
             const bool is_add = q < E;
             const uint32_t e = is_add ? q : q - E;
             const double v = is_add ? lo_a[e] : rem_a[e];
-            const uint32_t pos = is_add ? 1u + e + count_le(rem_a, E, v) : 1u + e + count_lt(lo_a, E, v);
-            // peaks in the window for ev[pos] <= t < ev[pos+1]: entered (lo <= v) and not yet left (rem > v)
-            const uint32_t a = count_le(rem_a, E, v);
-            const uint32_t bend = count_le(lo_a, E, v);
+            // a = #{rem <= v}: peaks that have left; bend = #{lo <= v}: peaks that have entered
+            uint32_t a, bend, pos;
+            if (is_add) {
+                a = e; while (a > 0 && rem_a[a - 1] > v) --a;                 // rem[e] > lo[e]: walk down from e
+                bend = e + 1; while (bend < E && lo_a[bend] <= v) ++bend;     // equal lo above e
+                pos = 1u + e + a;
+            } else {
+                a = e + 1; while (a < E && rem_a[a] <= v) ++a;               // equal rem above e
+                bend = e + 1; while (bend < E && lo_a[bend] <= v) ++bend;     // lo[e] < rem[e]: walk up from e
+                uint32_t lt = bend; while (lt > 0 && !(lo_a[lt - 1] < v)) --lt;   // #{lo < v}
+                pos = 1u + e + lt;
+            }
+            // window for ev[pos] <= t < ev[pos+1] = peaks [a, bend): the most intense wins, equal intensities tie
             uint32_t code = kAnsNone;
             if (a < bend) {
-                uint32_t best = a, best_r = W.ordI[a]; bool tie = false;
+                uint32_t best = a; double best_v = W.db[a]; bool tie = false;
                 for (uint32_t j = a + 1; j < bend; ++j) {
-                    uint32_t r = W.ordI[j];
-                    if (r > best_r) { best = j; best_r = r; tie = false; }
-                    else if (r == best_r) tie = true;
+                    double r = W.db[j];
+                    if (r > best_v) { best = j; best_v = r; tie = false; }
+                    else if (r == best_v) tie = true;
                 }
                 if (tie) code = kAnsTie | a;
                 else {
@@ -451,7 +483,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         // the per-cell event histogram (built in the shared memory the dead work arrays leave behind).
         __syncwarp();
         {
-            uint32_t* hist = reinterpret_cast<uint32_t*>(W.in);                      // kCells u16 counters, two per word
+            uint32_t* hist = reinterpret_cast<uint32_t*>(W.da);                      // kCells u16 counters, two per word
             for (uint32_t k = lane; k < (uint32_t)kCells / 2; k += 32) hist[k] = 0u;
             __syncwarp();
             for (uint32_t e = lane; e < E; e += 32) {

@@ -32,7 +32,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 struct BlobView {
-    const double* ev; const uint16_t* ans; const double* pmz; const uint32_t* pinfo; const double* val; const uint16_t* cells;
+    const double* ev; const uint16_t* ans; const double* pmz; const double* pin; const uint16_t* pcode; const double* val; const uint16_t* cells;
     uint32_t E; uint32_t nsurv; uint32_t flags; int32_t cls[4];
 };
 __device__ __forceinline__ BlobView view_blob(const uint8_t* b) {
@@ -44,7 +44,8 @@ __device__ __forceinline__ BlobView view_blob(const uint8_t* b) {
     v.ev = reinterpret_cast<const double*>(b + L.ev);
     v.ans = reinterpret_cast<const uint16_t*>(b + L.ans);
     v.pmz = reinterpret_cast<const double*>(b + L.pmz);
-    v.pinfo = reinterpret_cast<const uint32_t*>(b + L.pinfo);
+    v.pin = reinterpret_cast<const double*>(b + L.pin);
+    v.pcode = reinterpret_cast<const uint16_t*>(b + L.pcode);
     v.val = reinterpret_cast<const double*>(b + L.val);
     v.cells = reinterpret_cast<const uint16_t*>(b + L.cells);
     return v;
@@ -61,19 +62,17 @@ __device__ __forceinline__ uint32_t match_ion(const BlobView& B, double t, doubl
     uint32_t a = B.ans[k];
     if (a < kAnsTie || a == kAnsNone) return a;
     // two in-window peaks tie on intensity: the reference's scan decides (first peak wins unless a later one is strictly closer)
-    uint32_t best = 0; double best_abs = 0.0, best_mz = 0.0;
+    uint32_t code = kNoSurvivor; double best_in = __longlong_as_double(0xfff0000000000000LL), best_abs = 0.0, best_mz = 0.0;   // -inf
     for (uint32_t j = a & 0xFFFu;; ++j) {
         double m = B.pmz[j];                               // +inf after the last peak ends the scan
         double err = __dsub_rn(m, t);
         if (err > itol) break;
         double ae = fabs(err);
         if (ae <= itol) {
-            uint32_t info = B.pinfo[j];
-            uint32_t r = info >> 16, br = best >> 16;
-            if (r > br || (r == br && ae < best_abs)) { best = info; best_abs = ae; best_mz = m; }
+            double v = B.pin[j];
+            if (v > best_in || (v == best_in && ae < best_abs)) { best_in = v; best_abs = ae; best_mz = m; code = B.pcode[j]; }
         }
     }
-    uint32_t code = best & 0xFFFFu;
     if ((code & 0xFFFu) == kNoSurvivor) return kAnsNone;
     if (METHOD == 2 && (best_mz < 200.0 || best_mz > 2000.0)) return kAnsNone;      // MVHMatch.java:248-250
     return code;

@@ -38,7 +38,7 @@ struct ModTable {
 
 // ---- prepared spectrum blob (output of K0, input of K1) -----------------------------------------------------------
 // Everything K1 needs about one spectrum, contiguous and 16-byte aligned so one cp.async.bulk stages it:
-//   BlobHeader | ev f64[NE] | ans u16[NE pad 8] | pmz f64[E+1 pad 2] | pinfo u32[E pad 4] | val f64[kValSlots] | cells u16[kCells]
+//   BlobHeader | ev f64[NE] | ans u16[NE pad 8] | pmz f64[E+1 pad 2] | pin f64[E pad 2] | pcode u16[E pad 8] | val f64[kValSlots] | cells u16[kCells]
 //
 // The annotator's question "which matchable peak is the most intense one with |mz - t| <= itol" (JMatch.java:411-451,
 // A2-A4) has a piecewise-constant answer in t.  K0 inverts the predicate once per spectrum: for every matchable peak j
@@ -50,7 +50,8 @@ struct ModTable {
 //           MVH = (class << 12) | survivor id (a winner that did not survive pre-processing, or an MVH winner outside
 //           200..2000 Th, is already folded into 0xFFFF)
 //   pmz   : m/z of the matchable peaks (intensity >= 5th-percentile limit), ascending, +inf after the last
-//   pinfo : (intensity rank << 16) | (class << 12) | survivor id (0xFFF = the peak did not survive pre-processing)
+//   pin   : raw intensity of the matchable peaks (only the tie scan reads it)
+//   pcode : claim code of each matchable peak: (class << 12) | survivor id (0xFFF = the peak did not survive pre-processing)
 //   val   : hyperscore: normalised intensity of survivor id; MVH: unused
 //   cells : cells[c] = index of the last event below the lower edge of cell c of the monotone m/z -> cell map
 constexpr int kCellShift = 11;                              // 512 cells per binade
@@ -73,15 +74,16 @@ struct BlobHeader {
 };
 static_assert(sizeof(BlobHeader) == 48, "BlobHeader must stay 16-byte aligned");
 
-struct BlobLayout { uint32_t ev, ans, pmz, pinfo, val, cells, total; };
+struct BlobLayout { uint32_t ev, ans, pmz, pin, pcode, val, cells, total; };
 PQ_HD BlobLayout blob_layout(uint32_t E) {
     BlobLayout L;
     const uint32_t ne = 2u * E + 2u;
     L.ev = (uint32_t)sizeof(BlobHeader);
     L.ans = L.ev + ne * 8u;
     L.pmz = L.ans + ((ne * 2u + 15u) & ~15u);
-    L.pinfo = L.pmz + (((E + 1u) * 8u + 15u) & ~15u);
-    L.val = L.pinfo + ((E * 4u + 15u) & ~15u);
+    L.pin = L.pmz + (((E + 1u) * 8u + 15u) & ~15u);
+    L.pcode = L.pin + ((E * 8u + 15u) & ~15u);
+    L.val = L.pcode + ((E * 2u + 15u) & ~15u);
     L.cells = L.val + kValSlots * 8u;
     L.total = L.cells + kCells * 2u;
     return L;
