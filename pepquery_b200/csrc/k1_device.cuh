@@ -55,27 +55,33 @@ __device__ __forceinline__ BlobView view_blob(const uint8_t* b) {
 // intensity -> smaller |error|.  K0 has inverted the predicate into exact break points (pq_common.h): find the interval
 // of t in the event list and read its answer.  Returns the claim code (kAnsNone = nothing to claim).
 // METHOD 1: code = survivor id; METHOD 2: code = (class << 12) | survivor id, m/z range already applied.
+// Tie scan: two in-window peaks have equal intensity, the reference's scan decides (the first peak wins unless a later
+// one is strictly closer to t).  Rare, so it stays out of line: the hot loop keeps a small instruction footprint.
+template <int METHOD>
+__device__ __noinline__ uint32_t match_ion_tie(const double* pmz, const double* pin, const uint16_t* pcode, uint32_t first, double t, double itol) {
+    uint32_t code = kNoSurvivor; double best_in = __longlong_as_double(0xfff0000000000000LL), best_abs = 0.0, best_mz = 0.0;   // -inf
+    for (uint32_t j = first;; ++j) {
+        double m = pmz[j];                                 // +inf after the last peak ends the scan
+        double err = __dsub_rn(m, t);
+        if (err > itol) break;
+        double ae = fabs(err);
+        if (ae <= itol) {
+            double v = pin[j];
+            if (v > best_in || (v == best_in && ae < best_abs)) { best_in = v; best_abs = ae; best_mz = m; code = pcode[j]; }
+        }
+    }
+    if ((code & 0xFFFu) == kNoSurvivor) return kAnsNone;
+    if (METHOD == 2 && (best_mz < 200.0 || best_mz > 2000.0)) return kAnsNone;      // MVHMatch.java:248-250
+    return code;
+}
+
 template <int METHOD>
 __device__ __forceinline__ uint32_t match_ion(const BlobView& B, double t, double itol) {
     uint32_t k = B.cells[cell_of(t)];
     while (B.ev[k + 1] <= t) ++k;
     uint32_t a = B.ans[k];
     if (a < kAnsTie || a == kAnsNone) return a;
-    // two in-window peaks tie on intensity: the reference's scan decides (first peak wins unless a later one is strictly closer)
-    uint32_t code = kNoSurvivor; double best_in = __longlong_as_double(0xfff0000000000000LL), best_abs = 0.0, best_mz = 0.0;   // -inf
-    for (uint32_t j = a & 0xFFFu;; ++j) {
-        double m = B.pmz[j];                               // +inf after the last peak ends the scan
-        double err = __dsub_rn(m, t);
-        if (err > itol) break;
-        double ae = fabs(err);
-        if (ae <= itol) {
-            double v = B.pin[j];
-            if (v > best_in || (v == best_in && ae < best_abs)) { best_in = v; best_abs = ae; best_mz = m; code = B.pcode[j]; }
-        }
-    }
-    if ((code & 0xFFFu) == kNoSurvivor) return kAnsNone;
-    if (METHOD == 2 && (best_mz < 200.0 || best_mz > 2000.0)) return kAnsNone;      // MVHMatch.java:248-250
-    return code;
+    return match_ion_tie<METHOD>(B.pmz, B.pin, B.pcode, a & 0xFFFu, t, itol);
 }
 
 struct Extra { int32_t site; double delta; };   // Step 5: one extra modification (site -1 = none)
@@ -90,15 +96,18 @@ __device__ __forceinline__ uint32_t row_byte(const uint32_t* codes, int idx) {
 
 // Walks the fragment ladder of one peptide row against the staged spectrum.
 // METHOD 1: hyperscore (count_b, count_y, sum of normalised intensities); METHOD 2: MVH class hits.
-template <int BLOCK, int METHOD>
-__device__ __forceinline__ PairScore score_pair(const uint32_t* codes /* this thread's column */, const BlobView& B,
-                                                const double* aa, const double* dl, const double* ntd, const double* ctd,
-                                                int z, double itol, Extra ex,
-                                                const double* log10_fact, const double* ln_fact, int32_t predicted,
-                                                uint32_t* usedw /* MVH: this thread's column of the used bitmap */) {
+// NCH = number of fragment charges (precursor charge - 1, JMatch.java:398-407) when it is 1, 2 or 3: the charge loop
+// unrolls and charges 1 and 2 need no divide; NCH = 0 takes the charge count at run time.
+// tab[code] = {residue mass, modification mass} (one 16-byte shared-memory load per residue).
+template <int BLOCK, int METHOD, int NCH>
+__device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this thread's column */, const BlobView& B,
+                                                  const double2* tab, const double* ntd, const double* ctd,
+                                                  int z, double itol, Extra ex,
+                                                  const double* log10_fact, const double* ln_fact, int32_t predicted,
+                                                  uint32_t* usedw /* MVH: this thread's column of the used bitmap */) {
     const uint32_t head = codes[0];
     const int L = (int)(head & 0xFF);
-    const int nch = z <= 1 ? 1 : z - 1;          // JMatch.java:398-407
+    const int nch = NCH > 0 ? NCH : (z <= 1 ? 1 : z - 1);
     uint64_t used = 0ull;
     int ca = 0, cb = 0;
     int key0 = 0, key1 = 0, key2 = 0;
@@ -124,39 +133,53 @@ __device__ __forceinline__ PairScore score_pair(const uint32_t* codes /* this th
             key0 += c == 0; key1 += c == 1; key2 += c == 2;
         }
     };
-    // m/z of an ion of neutral mass m at charge c: (m + c*proton) / c.  c*proton is exact for c = 1, 2, 4 and so is the
-    // division by a power of two, so only c = 3 (and >= 5) needs a real FP64 divide.
-    auto ion_mz = [&](double m, int c) -> double {
-        if (c == 1) return __dadd_rn(m, kProton);
-        if (c == 2) return __dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5);
-        if (c == 4) return __dmul_rn(__dadd_rn(m, 4.0 * kProton), 0.25);
-        return __ddiv_rn(__dadd_rn(m, __dmul_rn((double)c, kProton)), (double)c);
+    // All charge states of one ion, charge ascending (A5).  m/z at charge c = (m + c*proton) / c: c*proton is exact for
+    // c = 1, 2, 4 and so is the division by a power of two, so only c = 3 (and >= 5) needs a real FP64 divide.
+    // A6 chargeValidated: c > 1 needs c <= ion number k.
+    auto ion = [&](double m, int k, bool is_b) {
+        claim(match_ion<METHOD>(B, __dadd_rn(m, kProton), itol), is_b);
+        if (nch >= 2 && k >= 2) claim(match_ion<METHOD>(B, __dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5), itol), is_b);
+        if (nch >= 3 && k >= 3) claim(match_ion<METHOD>(B, __ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0), itol), is_b);
+        if (NCH == 0) {
+            if (nch >= 4 && k >= 4) claim(match_ion<METHOD>(B, __dmul_rn(__dadd_rn(m, 4.0 * kProton), 0.25), itol), is_b);
+            for (int c = 5; c <= nch && c <= k; ++c)
+                claim(match_ion<METHOD>(B, __ddiv_rn(__dadd_rn(m, __dmul_rn((double)c, kProton)), (double)c), itol), is_b);
+        }
     };
 
     // ---- b ions: forward sum, residue mass then its modification, N-term modification opens the sum ----
     // (a plain residue has modification mass +0.0: adding it leaves the positive running sum unchanged, so no branch)
+    // Residue i (0-based) is byte i & 3 of row word 1 + i / 4: one shared-memory word feeds four ladder steps.
+    // The inner loops stay rolled and the tie scan out of line: a small instruction footprint measured faster than
+    // unrolled ladders, and separate b / y loops faster than one shared body.
     double acc = ntd[(head >> 8) & 0xFF];
     if (ex.site == 0) acc = __dadd_rn(acc, ex.delta);
-    for (int k = 1; k <= L - 1; ++k) {
-        uint32_t code = row_byte<BLOCK>(codes, kRowHeader + k - 1);
-        acc = __dadd_rn(__dadd_rn(acc, aa[code]), dl[code]);
-        if (k == ex.site) acc = __dadd_rn(acc, ex.delta);
-        claim(match_ion<METHOD>(B, ion_mz(acc, 1), itol), true);
-        for (int c = 2; c <= nch && c <= k; ++c)                        // A6 chargeValidated: c > 1 needs c <= ion number
-            claim(match_ion<METHOD>(B, ion_mz(acc, c), itol), true);
+    for (int i0 = 0; i0 < L - 1; i0 += 4) {
+        uint32_t word = codes[(1 + (i0 >> 2)) * BLOCK];
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            const int k = i0 + j + 1;
+            if (k > L - 1) break;
+            const double2 t = tab[word & 0xFFu];
+            word >>= 8;
+            acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+            if (k == ex.site) acc = __dadd_rn(acc, ex.delta);
+            ion(acc, k, true);
+        }
     }
     // ---- y ions: rewind sum from the C-terminus, + H2O ----
     acc = ctd[(head >> 16) & 0xFF];
     if (ex.site == L + 1) acc = __dadd_rn(acc, ex.delta);
-    for (int k = 1; k <= L - 1; ++k) {
-        int site = L - k + 1;
-        uint32_t code = row_byte<BLOCK>(codes, kRowHeader + site - 1);
-        acc = __dadd_rn(__dadd_rn(acc, aa[code]), dl[code]);
-        if (site == ex.site) acc = __dadd_rn(acc, ex.delta);
-        double ym = __dadd_rn(acc, kWater);
-        claim(match_ion<METHOD>(B, ion_mz(ym, 1), itol), false);
-        for (int c = 2; c <= nch && c <= k; ++c)
-            claim(match_ion<METHOD>(B, ion_mz(ym, c), itol), false);
+    for (int i = L - 1; i >= 1;) {
+        uint32_t word = codes[(1 + (i >> 2)) * BLOCK] << (8 * (3 - (i & 3)));        // residue i in the top byte
+#pragma unroll 1
+        for (int j = i & 3; j >= 0 && i >= 1; --j, --i) {
+            const double2 t = tab[word >> 24];
+            word <<= 8;
+            acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+            if (i + 1 == ex.site) acc = __dadd_rn(acc, ex.delta);
+            ion(__dadd_rn(acc, kWater), L - i, false);
+        }
     }
 
     PairScore r;
@@ -194,6 +217,18 @@ __device__ __forceinline__ PairScore score_pair(const uint32_t* codes /* this th
         r.score = died ? 0.0 : mvh;
     }
     return r;
+}
+
+template <int BLOCK, int METHOD>
+__device__ __forceinline__ PairScore score_pair(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd, const double* ctd,
+                                                int z, double itol, Extra ex, const double* log10_fact, const double* ln_fact, int32_t predicted,
+                                                uint32_t* usedw) {
+    switch (z) {                                  // fragment charges = precursor charge - 1, at least 1 (JMatch.java:398-407)
+        case 0: case 1: case 2: return score_pair_n<BLOCK, METHOD, 1>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw);
+        case 3: return score_pair_n<BLOCK, METHOD, 2>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw);
+        case 4: return score_pair_n<BLOCK, METHOD, 3>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw);
+        default: return score_pair_n<BLOCK, METHOD, 0>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw);
+    }
 }
 
 // Precursor-window predicate exactly as DBSearchWorker.java:38-52 / FindCandidate...java:47-58:

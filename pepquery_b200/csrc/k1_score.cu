@@ -37,15 +37,14 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
 
     uint8_t* stage0 = smem;
     uint32_t* codes_all = reinterpret_cast<uint32_t*>(smem + (size_t)stage_bytes * nstage);           // [16][BLOCK]
-    double* s_aa = reinterpret_cast<double*>(codes_all + 16 * BLOCK);
-    double* s_dl = s_aa + kMaxCodes;
-    double* s_nt = s_dl + kMaxCodes;
+    double2* s_tab = reinterpret_cast<double2*>(codes_all + 16 * BLOCK);                               // {residue mass, modification mass} per code
+    double* s_nt = reinterpret_cast<double*>(s_tab + kMaxCodes);
     double* s_ct = s_nt + kMaxTermCodes;
     double* s_l10 = s_ct + kMaxTermCodes;                                                              // [65]
     uint32_t* usedw_all = reinterpret_cast<uint32_t*>(s_l10 + 66);                                     // MVH only: [10][BLOCK]
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < kMaxCodes; i += BLOCK) { s_aa[i] = L.mods->aa[i]; s_dl[i] = L.mods->delta[i]; }
+    for (int i = tid; i < kMaxCodes; i += BLOCK) s_tab[i] = make_double2(L.mods->aa[i], L.mods->delta[i]);
     for (int i = tid; i < kMaxTermCodes; i += BLOCK) { s_nt[i] = L.mods->nterm[i]; s_ct[i] = L.mods->cterm[i]; }
     for (int i = tid; i < 65; i += BLOCK) s_l10[i] = L.log10_fact[i];
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -99,7 +98,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
             if (active) {
                 int32_t pred = 0;
                 if (METHOD == 2) pred = L.row_pred[2 * (size_t)row + (J.charge == 2 ? 0 : 1)];
-                PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_aa, s_dl, s_nt, s_ct, J.charge, itol, ex,
+                PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex,
                                                          s_l10, L.ln_fact, pred, usedw);
                 ++n_in;
                 if (ps.score > best) { best = ps.score; best_cand = row; }

@@ -41,16 +41,15 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
 
     uint8_t* stage0 = smem;
     uint32_t* codes_all = reinterpret_cast<uint32_t*>(smem + stage_bytes);            // [16][BLOCK]
-    double* s_aa = reinterpret_cast<double*>(codes_all + 16 * BLOCK);
-    double* s_dl = s_aa + kMaxCodes;
-    double* s_nt = s_dl + kMaxCodes;
+    double2* s_tab = reinterpret_cast<double2*>(codes_all + 16 * BLOCK);                               // {residue mass, modification mass} per code
+    double* s_nt = reinterpret_cast<double*>(s_tab + kMaxCodes);
     double* s_ct = s_nt + kMaxTermCodes;
     double* s_l10 = s_ct + kMaxTermCodes;                                               // [65]
     uint32_t* s_lo = reinterpret_cast<uint32_t*>(s_l10 + 66);                           // [kMaxPtm]
     uint32_t* s_off = s_lo + kMaxPtm;                                                   // [kMaxPtm + 1]
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < kMaxCodes; i += BLOCK) { s_aa[i] = L.mods->aa[i]; s_dl[i] = L.mods->delta[i]; }
+    for (int i = tid; i < kMaxCodes; i += BLOCK) s_tab[i] = make_double2(L.mods->aa[i], L.mods->delta[i]);
     for (int i = tid; i < kMaxTermCodes; i += BLOCK) { s_nt[i] = L.mods->nterm[i]; s_ct[i] = L.mods->cterm[i]; }
     for (int i = tid; i < 65; i += BLOCK) s_l10[i] = L.log10_fact[i];
     if (tid == 0) { mbar_init(&s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -153,7 +152,7 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
                     else { uint32_t code = row_byte<BLOCK>(codes, kRowHeader + site - 1); ok = P.residue ? code == rcode : code < 26u; }
                     if (!ok) continue;
                     Extra ex; ex.site = site; ex.delta = P.delta;
-                    PairScore ps = score_pair<BLOCK, 1>(codes, B, s_aa, s_dl, s_nt, s_ct, J.charge, itol, ex, s_l10, nullptr, 0, nullptr);
+                    PairScore ps = score_pair<BLOCK, 1>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, nullptr, 0, nullptr);
                     ++n_pairs;
                     bool better = cfg.hc ? ps.score >= J.ref_score : ps.score > J.ref_score;      // :239-259, PSMT:920-943
                     if (better) { ++n_better; if (cfg.fast) s_stop = 1; }
