@@ -377,6 +377,46 @@ def test_edge_case_spectra(data):
         assert g.counters().spectra_usable == sum(1 for s in spectra if len(s[2]) > 10)
 
 
+def test_large_spectra_take_the_wide_prepare_path(data):
+    """Spectra with more than 256 peaks use K0's second size class (capacity = next power of two, one warp per CTA above
+    1024 peaks) and bigger K1 stages; up to the 4096-peak limit.  Dense peak lists also put many peaks into one fragment
+    window (multi-peak windows, ties).  Full pipeline, both scoring methods."""
+    prot, tgt, base = data
+    rng = np.random.default_rng(23)
+    spectra = []
+    sizes = [257, 300, 511, 512, 513, 900, 1024, 1025, 2000, 3000, 4096]
+    for n_extra, i in zip(sizes, range(0, 10 * len(sizes), 10)):
+        a, b = int(base["peak_off"][i]), int(base["peak_off"][i + 1])
+        pk = {round(float(m), 4): float(v) for m, v in zip(base["mz"][a:b], base["inten"][a:b])}
+        while len(pk) < n_extra:                            # dense noise, two-decimal intensities with many repeats
+            pk[round(float(rng.uniform(100.0, 1900.0)), 4)] = float(rng.integers(1, 40) * 25)
+        items = sorted(pk.items())[:n_extra]
+        if n_extra % 2:
+            rng.shuffle(items)                              # unsorted file order on the odd sizes
+        spectra.append((float(base["prec_mz"][i]), int(base["charge"][i]), items))
+    for i in range(200, 260):                                # ordinary spectra around them
+        a, b = int(base["peak_off"][i]), int(base["peak_off"][i + 1])
+        spectra.append((float(base["prec_mz"][i]), int(base["charge"][i]), list(zip(base["mz"][a:b].tolist(), base["inten"][a:b].tolist()))))
+    sp = _csr(spectra)
+    assert int(np.diff(sp["peak_off"]).max()) == 4096
+    for method in (1, 2):
+        p = _abi.default_params(n_random=60, score_method=method, min_score=0.0)
+        g = run_gpu(p, sp, tgt, prot)
+        o = run_oracle(p, sp, tgt, prot)
+        got = g.psms()
+        assert_psms_equal(got, o.psms())
+        assert len(got) > 0
+
+
+def test_more_than_4096_peaks_is_refused(data):
+    prot, tgt, base = data
+    sp = _csr([(600.0, 2, [(100.0 + 0.25 * k, 10.0 + (k % 7)) for k in range(4097)])])
+    with Search(_abi.default_params()) as g:
+        with pytest.raises(PepQueryError) as e:
+            g.load_spectra(sp)
+        assert e.value.code == _abi.PQ_ERR_UNSUPPORTED
+
+
 def test_degenerate_spectra_are_scored_like_the_reference():
     """Degenerate peak lists placed exactly on a target's precursor mass, scored through pq_score_pairs."""
     from oracle import pq_oracle
