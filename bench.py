@@ -26,6 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+STRIPS_PER_GPU = 16
 METRIC = "peptide_spectrum_pairs_scored_per_sec"
 UNIT = "pairs/s"
 
@@ -105,11 +106,14 @@ def make_inputs(a, rank, world, pinned):
     from pepquery_b200 import synth
     prot = synth.proteins(a.proteins)
     tgt = synth.targets(a.peptides)
-    lo, hi = 0.0, 1e9
     if world > 1:
-        b = synth.mass_bounds(world, tgt, prot)
-        lo, hi = float(b[rank]), float(b[rank + 1])
-    sp = synth.spectra(a.spectra, tgt, prot, first_index=rank * a.spectra, mass_lo=lo, mass_hi=hi, pinned=pinned)
+        # mass-range sharding with equal expected work: the precursor-mass axis is cut into STRIPS_PER_GPU * world quantile
+        # strips and rank r owns strips r, r + world, ... (contiguous mass ranges, interleaved so that every rank sees the
+        # same mix of peptide lengths); each rank holds --spectra spectra of its own strips (weak scaling)
+        b = synth.mass_bounds(STRIPS_PER_GPU * world, tgt, prot)
+        synth.set_strips(b[:-1], world, rank)
+    sp = synth.spectra(a.spectra, tgt, prot, first_index=rank * a.spectra, pinned=pinned)
+    synth.set_strips(None, 1, 0)
     return prot, tgt, sp
 
 
@@ -187,21 +191,42 @@ def main():
     p = _abi.default_params(n_random=a.shuffles, score_method=a.method, device=local)
     g = Search(p)
 
-    def gather_psms(psms):
-        """NCCL gather of the fixed-size PSM records to rank 0 (the only collective of the path)."""
+    class _DevView:
+        """CUDA array interface over a device address (the context's export buffer)."""
+        def __init__(self, addr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (addr, False), "version": 2}
+
+    gbuf = {}
+
+    def gather_psms():
+        """Results to the host.  One GPU: device -> pinned host.  N GPUs: NCCL gather of the fixed-size PSM records from
+        every rank's device buffer to rank 0 (the only collective of the path), then device -> pinned host on rank 0."""
+        g.rank()
         if world == 1:
-            return len(psms)
-        raw = torch.from_numpy(psms.view(np.uint8).reshape(-1).copy()).cuda()
-        n = torch.tensor([raw.numel()], device="cuda", dtype=torch.int64)
-        sizes = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(sizes, n)
-        mx = int(max(int(s.item()) for s in sizes))
-        buf = torch.zeros(mx, dtype=torch.uint8, device="cuda")
-        buf[:raw.numel()] = raw
-        out = [torch.zeros_like(buf) for _ in range(world)] if rank == 0 else None
-        dist.gather(buf, out, dst=0)
+            ps = results_host()
+            return len(ps)
+        addr, n = g.psms_device()
+        nbytes = n * 96
+        cnt = torch.tensor([nbytes], device="cuda", dtype=torch.int64)
+        sizes = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(sizes, cnt)
+        sizes = [int(x.item()) for x in sizes]
+        mx = max(max(sizes), 96)
+        if gbuf.get("mx", 0) < mx:
+            gbuf["mx"] = mx + mx // 8
+            gbuf["send"] = torch.zeros(gbuf["mx"], dtype=torch.uint8, device="cuda")
+            gbuf["recv"] = [torch.zeros(gbuf["mx"], dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+            gbuf["host"] = torch.empty(gbuf["mx"] * world, dtype=torch.uint8, pin_memory=True) if rank == 0 else None
+        if nbytes:
+            gbuf["send"][:nbytes].copy_(torch.as_tensor(_DevView(addr, nbytes), device="cuda"))
+        dist.gather(gbuf["send"], gbuf["recv"], dst=0)
+        g.competitors(3)                    # detail rows stay with the rank that owns the spectra
         if rank == 0:
-            return sum(int(s.item()) for s in sizes) // psms.dtype.itemsize
+            o = 0
+            for r in range(world):
+                gbuf["host"][o:o + sizes[r]].copy_(gbuf["recv"][r][:sizes[r]], non_blocking=True); o += sizes[r]
+            torch.cuda.synchronize()
+            return o // 96
         return 0
 
     # ---- resident-input measurement ----------------------------------------------------------------------------
@@ -214,18 +239,18 @@ def main():
 
     pin = {"buf": None}
 
-    def results():
-        """rank/accept, then the two result tables the Java host writes: PSM rows and Step-3 detail rows (device -> pinned host)."""
+    def results_host():
+        """The two result tables the Java host writes: PSM rows and Step-3 detail rows (device -> pinned host)."""
         if pin["buf"] is None:
-            n0 = len(g.rank_psms())
+            n0 = g.psm_count()
             pin["buf"] = torch.empty(max(1, 2 * n0) * 96 + 4096, dtype=torch.uint8, pin_memory=True).numpy()
-        ps = g.rank_psms(pin["buf"]) if g.psm_count() * 96 <= pin["buf"].nbytes else g.rank_psms()
+        ps = g.psms(pin["buf"]) if g.psm_count() * 96 <= pin["buf"].nbytes else g.psms()
         g.competitors(3)
         return ps
 
     def step():
         g.step2(); g.step3(); g.step4()
-        return gather_psms(results())
+        return gather_psms()
 
     for _ in range(max(a.warmup, 3) if a.warmup >= 0 else 3):
         step()
@@ -286,7 +311,7 @@ def main():
             g.step2()
             g.build_reference(*prot)               # H2D of the proteins; digest + form expansion + mass sort on the device (K6)
             g.step3(); g.step4()
-            gather_psms(results())                 # D2H of the result records
+            gather_psms()                          # rank/accept + D2H of the result records
         g.event_record(1)
         dms = g.event_elapsed_ms()
         barrier()
@@ -327,7 +352,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                 "ms_per_step": 1000.0 * sec_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(a), "sharding": "spectra by precursor-mass range, tables replicated" if world > 1 else "single GPU",
+                "config": {"workload": workload_name(a), "sharding": ("spectra by precursor-mass strips (%d per GPU, interleaved), tables replicated" % STRIPS_PER_GPU) if world > 1 else "single GPU",
                            "l2": "inputs larger than L2 (prepared spectra + shuffle rows >> 126 MB per step)",
                            "pairs_per_step": float(tot_pairs.item()), "psms_per_step": int(n_psm_total),
                            "timed_region": "Steps 2+3+4 + rank/accept + PSM and detail rows to the host, spectra/targets/reference table resident in HBM",

@@ -215,6 +215,10 @@ int32_t pq_rank_and_validate(pq_ctx* ctx);
 int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms);
 
 int32_t pq_get_psms(pq_ctx* ctx, pq_psm* out, int64_t capacity, int64_t* n_psms);
+/* Multi-GPU gather: exports the PSM records (same layout and order as pq_get_psms) into a device buffer
+ * owned by the context and returns its device address, so that the one collective of the path (NCCL gather of per-shard
+ * PSM records) reads them without a host round trip.  The address stays valid until the next call on this context. */
+int32_t pq_export_psms_device(pq_ctx* ctx, uint64_t* device_address, int64_t* n_psms);
 int32_t pq_get_competitors(pq_ctx* ctx, int32_t step /* 3 or 5 */, pq_competitor* out, int64_t capacity, int64_t* n_rows);
 /* Shuffled sequences of one target sequence, in generation order (for parity checks of the RNG stream). */
 int32_t pq_get_shuffles(pq_ctx* ctx, int32_t target_seq, char* out /* n * (L+1) bytes, NUL separated */,

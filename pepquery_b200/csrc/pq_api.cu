@@ -942,6 +942,18 @@ int32_t pq_get_psms(pq_ctx* ctx, pq_psm* out, int64_t capacity, int64_t* n_psms)
     return PQ_OK;
 }
 
+int32_t pq_export_psms_device(pq_ctx* ctx, uint64_t* device_address, int64_t* n_psms) {
+    if (!ctx || !device_address || !n_psms) return PQ_ERR_BAD_ARG;
+    *n_psms = (int64_t)ctx->n_psm; *device_address = 0;
+    if (!ctx->n_psm) return PQ_OK;
+    cudaSetDevice(ctx->P.device);
+    CU(ctx->d_export.reserve((size_t)ctx->n_psm * sizeof(pq_psm)));
+    ctx->cnt.other_kernel_launches += (uint64_t)launch_export_psms(ctx->d_psm.as<DevPsm>(), ctx->d_out_perm.as<uint32_t>(), ctx->n_psm, ctx->d_export.as<pq_psm>(), ctx->st);
+    CU(cudaStreamSynchronize(ctx->st));       // the caller's collective runs on another stream
+    *device_address = (uint64_t)(uintptr_t)ctx->d_export.p;
+    return PQ_OK;
+}
+
 int32_t pq_get_competitors(pq_ctx* ctx, int32_t step, pq_competitor* out, int64_t capacity, int64_t* n_rows) {
     if (!ctx || !n_rows) return PQ_ERR_BAD_ARG;
     if (step == 5) {

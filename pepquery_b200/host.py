@@ -57,7 +57,7 @@ def load_library():
 EXPORTS = ["pq_version", "pq_last_error", "pq_default_params", "pq_create", "pq_destroy", "pq_load_spectra",
            "pq_set_targets", "pq_get_target_forms", "pq_build_reference", "pq_get_reference_forms",
            "pq_step2_match_targets", "pq_step3_competitors", "pq_step4_shuffles", "pq_rank_and_validate",
-           "pq_step5_ptm", "pq_get_psms", "pq_get_competitors", "pq_get_shuffles", "pq_score_pairs",
+           "pq_step5_ptm", "pq_get_psms", "pq_export_psms_device", "pq_get_competitors", "pq_get_shuffles", "pq_score_pairs",
            "pq_get_counters", "pq_reset_counters", "pq_event_record", "pq_event_elapsed_ms", "pq_parse_mgf"]
 
 
@@ -169,6 +169,12 @@ class Search:
             arr = np.frombuffer(out, dtype=dt, count=max(1, n.value))
         self._ck(self.L.pq_get_psms(self.h, _p(arr), C.c_int64(n.value), C.byref(n)))
         return arr[:n.value]
+
+    def psms_device(self):
+        """(device address, count) of the exported PSM records, for a device-side gather (NCCL)."""
+        addr = C.c_uint64(); n = C.c_int64()
+        self._ck(self.L.pq_export_psms_device(self.h, C.byref(addr), C.byref(n)))
+        return addr.value, n.value
 
     def psm_count(self):
         n = C.c_int64()

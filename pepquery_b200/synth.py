@@ -75,6 +75,18 @@ def mass_bounds(shards, tgt, prot, seed=99):
     return b
 
 
+def set_strips(bounds, world, rank):
+    """Shard rule for the next spectra() calls: shard `rank` owns every world-th strip of the given mass boundaries
+    (None switches back to the plain [mass_lo, mass_hi) rule)."""
+    L = _lib()
+    L.syn_set_strips.restype = None
+    if bounds is None:
+        L.syn_set_strips(C.c_int32(0), None, C.c_int32(1), C.c_int32(0))
+    else:
+        b = np.ascontiguousarray(bounds, dtype=np.float64)
+        L.syn_set_strips(C.c_int32(len(b)), _p(b), C.c_int32(world), C.c_int32(rank))
+
+
 def spectra(n, tgt, prot, seed=99, itol=0.6, first_index=0, mass_lo=0.0, mass_hi=1e9, threads=0, pinned=None):
     """-> dict(prec_mz f64[n], charge i32[n], peak_off u64[n+1], mz f64[P], inten f64[P]).
 

@@ -110,6 +110,16 @@ bool make_source(Rng& r, int n_targets, const uint32_t* toff, const char* tres, 
     return true;
 }
 
+// Optional shard rule for the multi-GPU bench: the precursor-mass axis is cut into strips (quantile bounds) and shard
+// `g_rank` of `g_world` owns every g_world-th strip (interleaved contiguous mass ranges of equal expected work).
+std::vector<double> g_strips; int g_world = 1, g_rank = 0;
+bool in_shard(double M, double mlo, double mhi) {
+    if (g_strips.empty() || g_world <= 1) return M >= mlo && M < mhi;
+    int strip = (int)(std::upper_bound(g_strips.begin(), g_strips.end(), M) - g_strips.begin()) - 1;
+    if (strip < 0) strip = 0;
+    return strip % g_world == g_rank;
+}
+
 void make_spectrum(uint64_t seed, int64_t index, int n_targets, const uint32_t* toff, const char* tres, int n_prot,
                    const uint64_t* poff, const char* pres, double itol, double mlo, double mhi, SpecOut& o) {
     Rng r(seed, (uint64_t)index);
@@ -118,7 +128,7 @@ void make_spectrum(uint64_t seed, int64_t index, int n_targets, const uint32_t* 
     for (int attempt = 0;; ++attempt) {
         if (!make_source(r, n_targets, toff, tres, n_prot, poff, pres, src)) { src.seq = "PEPTLDEK"; apply_mods(r, src); }
         M = neutral_mass(src);
-        if ((M >= mlo && M < mhi) || attempt > 4000) break;
+        if (in_shard(M, mlo, mhi) || attempt > 4000) break;
     }
     double uz = r.uni();
     int z = uz < 0.6 ? 2 : (uz < 0.95 ? 3 : 4);
@@ -188,6 +198,12 @@ int64_t syn_targets(int32_t n, uint64_t seed, uint32_t* off, char* res, int64_t 
     }
     if (off) off[n] = (uint32_t)total;
     return total;
+}
+
+// Shard rule of the following syn_spectra calls: n_bounds strip boundaries (ascending), this process owns strips
+// rank, rank + world, ...  n_bounds == 0 switches back to the plain [mass_lo, mass_hi) rule.
+void syn_set_strips(int32_t n_bounds, const double* bounds, int32_t world, int32_t rank) {
+    g_strips.assign(bounds, bounds + (n_bounds > 0 ? n_bounds : 0)); g_world = world; g_rank = rank;
 }
 
 // Mass quantile boundaries for S shards (S+1 doubles), estimated from a fixed sample of sources.
