@@ -30,6 +30,33 @@ namespace {
 constexpr int kKeyWords = 4;            // 48 residues x 5 bits
 constexpr int kMaxSlots = 64;
 
+struct ByteToU32 { __host__ __device__ uint32_t operator()(uint8_t b) const { return b; } };
+
+// DigestProteinWorker.java:66-70 on the device: upper-case, I -> L, '*' dropped (keep flag for the compaction)
+__global__ void k6_normalise(const uint8_t* __restrict__ raw, uint32_t n, uint8_t* __restrict__ norm, uint8_t* __restrict__ keep) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t c = raw[i];
+    if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
+    if (c == 'I') c = 'L';
+    norm[i] = c; keep[i] = c != '*';
+}
+__global__ void k6_compact(const uint8_t* __restrict__ norm, const uint8_t* __restrict__ keep, const uint32_t* __restrict__ pos, uint32_t n,
+                           uint8_t* __restrict__ out, uint8_t* __restrict__ first) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (keep[i]) { out[pos[i]] = norm[i]; first[pos[i]] = 0; }
+}
+// a protein starts at the first kept residue at or after its raw offset
+__global__ void k6_protein_starts(const uint64_t* __restrict__ off, int32_t n_prot, const uint32_t* __restrict__ pos, uint32_t n_raw, uint32_t n_kept,
+                                  uint8_t* __restrict__ first) {
+    int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_prot) return;
+    uint64_t a = off[p], b = off[p + 1];
+    uint32_t pa = a < n_raw ? pos[a] : n_kept, pb = b < n_raw ? pos[b] : n_kept;
+    if (pa < pb) first[pa] = 1;
+}
+
 __global__ void k6_cut_flags(const uint8_t* __restrict__ res, const uint8_t* __restrict__ first, uint32_t n, uint8_t* __restrict__ is_start) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -245,28 +272,38 @@ template <class F> bool select_flagged(const uint8_t* flags, uint32_t n, uint32_
 
 bool build_reference_on_device(cudaStream_t st, const pq_params& P, const Codes& codes, int32_t n_proteins, const uint64_t* off, const char* res,
                                const std::vector<std::string>& targets, double lo, double hi, RefDeviceTable& T, uint64_t* launches, std::string& err) {
-    // ---- host: normalise residues (DigestProteinWorker.java:66-70) ----
+    // ---- residues: H2D as they are, normalised and compacted on the device (DigestProteinWorker.java:66-70) ----
     uint64_t total = n_proteins ? off[n_proteins] : 0;
     if (total >= 0x7fffff00ull) { err = "protein database too large for one table"; return false; }
-    std::vector<uint8_t> h_res; h_res.reserve((size_t)total + 1);
-    std::vector<uint8_t> h_first; h_first.reserve((size_t)total + 1);
-    for (int32_t p = 0; p < n_proteins; ++p) {
-        bool first = true;
-        for (uint64_t k = off[p]; k < off[p + 1]; ++k) {
-            char c = res[k];
-            if (c >= 'a' && c <= 'z') c = (char)(c - 32);
-            if (c == '*') continue;
-            if (c == 'I') c = 'L';
-            h_res.push_back((uint8_t)c); h_first.push_back(first ? 1 : 0); first = false;
-        }
-    }
-    const uint32_t n = (uint32_t)h_res.size();
     T.n_forms = 0; T.n_unique = 0;
+    if (total == 0) return true;
+    const uint32_t n_raw = (uint32_t)total;
+    DevBuf& d_first = T.w[0]; DevBuf& d_start = T.w[1]; DevBuf& d_flags = T.w[2]; DevBuf& d_cnt = T.w[3]; DevBuf& d_cand = T.w[4]; DevBuf& d_keys = T.w[5];
+    DevBuf& d_tmpkey = T.w[6]; DevBuf& d_tmpkey2 = T.w[7]; DevBuf& d_perm = T.w[8]; DevBuf& d_perm2 = T.w[9]; DevBuf& d_tk = T.w[10]; DevBuf& d_count = T.w[11];
+    DevBuf& d_foff = T.w[12]; DevBuf& d_rows = T.w[13]; DevBuf& d_mass = T.w[14]; DevBuf& d_seq = T.w[15]; DevBuf& d_mkey = T.w[16]; DevBuf& d_mkey2 = T.w[17];
+    DevBuf& d_idx = T.w[18]; DevBuf& d_idx2 = T.w[19]; DevBuf& tmp = T.w[20]; DevBuf& d_raw = T.w[21]; DevBuf& d_norm = T.w[22]; DevBuf& d_keep = T.w[23];
+    DevBuf& d_pos = T.w[24]; DevBuf& d_off = T.w[25];
+    RB(d_raw.reserve(n_raw)); RB(d_norm.reserve(n_raw)); RB(d_keep.reserve(n_raw)); RB(d_pos.reserve(((size_t)n_raw + 1) * 4)); RB(d_off.reserve(((size_t)n_proteins + 1) * 8));
+    RB(T.residues.reserve(n_raw)); RB(d_first.reserve(n_raw)); RB(d_start.reserve(n_raw)); RB(d_cnt.reserve(64));
+    RB(cudaMemcpyAsync(d_raw.p, res, n_raw, cudaMemcpyHostToDevice, st));
+    RB(cudaMemcpyAsync(d_off.p, off, ((size_t)n_proteins + 1) * 8, cudaMemcpyHostToDevice, st));
+    k6_normalise<<<(n_raw + 255) / 256, 256, 0, st>>>(d_raw.as<uint8_t>(), n_raw, d_norm.as<uint8_t>(), d_keep.as<uint8_t>());
+    {
+        size_t bytes = 0;
+        cub::TransformInputIterator<uint32_t, ByteToU32, const uint8_t*> keep32(d_keep.as<uint8_t>(), ByteToU32());      // accumulate in 32 bits
+        cub::DeviceScan::ExclusiveSum(nullptr, bytes, keep32, d_pos.as<uint32_t>(), (int)n_raw, st);
+        RB(tmp.reserve(bytes + 64));
+        RB(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, keep32, d_pos.as<uint32_t>(), (int)n_raw, st));
+    }
+    uint32_t last_pos = 0; uint8_t last_keep = 0;
+    RB(cudaMemcpyAsync(&last_pos, d_pos.as<uint32_t>() + (n_raw - 1), 4, cudaMemcpyDeviceToHost, st));
+    RB(cudaMemcpyAsync(&last_keep, d_keep.as<uint8_t>() + (n_raw - 1), 1, cudaMemcpyDeviceToHost, st));
+    RB(cudaStreamSynchronize(st));
+    const uint32_t n = last_pos + (last_keep ? 1u : 0u);
     if (n == 0) return true;
-    DevBuf d_first, d_start, d_flags, d_cnt, d_cand, d_keys, d_tmpkey, d_tmpkey2, d_perm, d_perm2, d_tk, d_count, d_foff, d_rows, d_mass, d_seq, d_mkey, d_mkey2, d_idx, d_idx2, tmp;
-    RB(T.residues.reserve(n)); RB(d_first.reserve(n)); RB(d_start.reserve(n)); RB(d_cnt.reserve(64));
-    RB(cudaMemcpyAsync(T.residues.p, h_res.data(), n, cudaMemcpyHostToDevice, st));
-    RB(cudaMemcpyAsync(d_first.p, h_first.data(), n, cudaMemcpyHostToDevice, st));
+    k6_compact<<<(n_raw + 255) / 256, 256, 0, st>>>(d_norm.as<uint8_t>(), d_keep.as<uint8_t>(), d_pos.as<uint32_t>(), n_raw, T.residues.as<uint8_t>(), d_first.as<uint8_t>());
+    k6_protein_starts<<<((uint32_t)n_proteins + 255) / 256, 256, 0, st>>>(d_off.as<uint64_t>(), n_proteins, d_pos.as<uint32_t>(), n_raw, n, d_first.as<uint8_t>());
+    *launches += 5;
     const uint8_t* d_res = T.residues.as<uint8_t>();
     k6_cut_flags<<<(n + 255) / 256, 256, 0, st>>>(d_res, d_first.as<uint8_t>(), n, d_start.as<uint8_t>());
     // segment starts (+ sentinel)

@@ -71,7 +71,7 @@ struct pq_ctx {
     std::vector<double> ln_fact; double log10_fact[65];
     // spectra
     int64_t nS = 0; uint32_t max_peaks = 0;
-    DevBuf s_prec, s_charge, s_mass, s_off, s_mz, s_in, s_caller;
+    DevBuf s_prec, s_charge, s_mass, s_off, s_mz, s_in, s_caller, ld[9];
     std::vector<int32_t> h_caller; std::vector<double> h_mass; std::vector<int32_t> h_charge; std::vector<uint32_t> h_npeaks;
     SpectraView view() const {
         SpectraView v; v.n = nS; v.prec_mz = s_prec.as<double>(); v.charge = s_charge.as<int32_t>(); v.mass = s_mass.as<double>();
@@ -394,7 +394,9 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
     ctx->nS = n; ctx->max_peaks = maxp; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0;
     ctx->cnt.spectra_loaded = (uint64_t)n; ctx->cnt.spectra_usable = usable;
     if (n == 0) return PQ_OK;
-    DevBuf in_prec, in_charge, in_off, in_mz, in_in, in_mass, key, key2, idx;
+    // staging buffers live in the context: a reload of the same size allocates nothing
+    DevBuf& in_prec = ctx->ld[0]; DevBuf& in_charge = ctx->ld[1]; DevBuf& in_off = ctx->ld[2]; DevBuf& in_mz = ctx->ld[3]; DevBuf& in_in = ctx->ld[4];
+    DevBuf& in_mass = ctx->ld[5]; DevBuf& key = ctx->ld[6]; DevBuf& key2 = ctx->ld[7]; DevBuf& idx = ctx->ld[8];
     CU(in_prec.reserve(n * 8)); CU(in_charge.reserve(n * 4)); CU(in_off.reserve((n + 1) * 8));
     CU(in_mz.reserve(std::max<uint64_t>(total, 1) * 8)); CU(in_in.reserve(std::max<uint64_t>(total, 1) * 8));
     CU(in_mass.reserve(n * 8)); CU(key.reserve(n * 8)); CU(key2.reserve(n * 8)); CU(idx.reserve(n * 4));

@@ -54,6 +54,7 @@ void digest_proteins(const pq_params& p, const double* residue_mass, int32_t n_p
 struct RefDeviceTable {
     DevBuf residues, starts, cand_pos, cand_len, uniq, seq_id;   // normalised proteins, segment starts, candidate (pos,len), unique candidate ids (lexicographic), parent id per form
     DevBuf* rows = nullptr; DevBuf* mass = nullptr;
+    DevBuf w[26];                       // work buffers of the build, kept so that a rebuild allocates nothing
     uint32_t n_unique = 0, n_forms = 0;
 };
 bool build_reference_on_device(cudaStream_t st, const pq_params& P, const Codes& codes, int32_t n_proteins, const uint64_t* off, const char* res,
