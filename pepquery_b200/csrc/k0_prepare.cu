@@ -36,7 +36,7 @@ __device__ __forceinline__ bool idx_less(const double* key, uint32_t a, uint32_t
     return ka < kb || (ka == kb && a < b);
 }
 // warp-synchronous bitonic sort of idx[0..n) by (key[idx], idx); n is a power of two >= 32
-__device__ void warp_sort_idx(uint16_t* idx, const double* key, uint32_t n, int lane) {
+__device__ __noinline__ void warp_sort_idx(uint16_t* idx, const double* key, uint32_t n, int lane) {
     for (uint32_t k = 2; k <= n; k <<= 1) {
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
             for (uint32_t i = lane; i < n; i += 32) {
@@ -55,71 +55,74 @@ __device__ void warp_sort_idx(uint16_t* idx, const double* key, uint32_t n, int 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
 __device__ __forceinline__ double warp_max(double m) { for (int o = 16; o > 0; o >>= 1) { double x = __shfl_xor_sync(0xffffffffu, m, o); if (m < x) m = x; } return m; }
 
-__device__ uint32_t count_kept(const uint8_t* keep, uint32_t P, int lane) {
+__device__ __noinline__ uint32_t count_kept(const uint8_t* keep, uint32_t P, int lane) {
     uint32_t c = 0;
     for (uint32_t i = lane; i < P; i += 32) c += keep[i];
     return warp_sum(c);
 }
 __device__ void keep_all(uint8_t* keep, uint32_t P, int lane) { for (uint32_t i = lane; i < P; i += 32) keep[i] = 1; __syncwarp(); }
-__device__ double max_kept(const WarpMem& W, uint32_t P, int lane) {
+__device__ __noinline__ double max_kept_p(const uint8_t* keep, const double* in, const uint16_t* ord, uint32_t P, int lane) {
     double m = 0.0;                       // JSpectrum.getMaxIntensity starts at 0 (PSMMatch/JSpectrum.java:108-116)
-    for (uint32_t i = lane; i < P; i += 32) if (W.keep[i]) { double v = W.in[W.ord[i]]; if (m < v) m = v; }
+    for (uint32_t i = lane; i < P; i += 32) if (keep[i]) { double v = in[ord[i]]; if (m < v) m = v; }
     return warp_max(m);
 }
+__device__ __forceinline__ double max_kept(const WarpMem& W, uint32_t P, int lane) { return max_kept_p(W.keep, W.in, W.ord, P, lane); }
 
 // JMatch.removeIsotopes / cleanIsotopes (PSMMatch/JMatch.java:223-280) over the kept entries, in m/z order.
 // Reference chain: cur = first; for each next peak p: if p.mz - ref >= gap or p.mz < 200: emit cur, cur = p, ref = p.mz;
 // else if p.I > cur.I: cur = p, ref = p.mz.  `ref` is the m/z of a kept peak at or before the previous one, so a peak
 // that is >= gap above its kept predecessor (or below 200 Th) always restarts the chain: those are hard boundaries and
 // the segments between them are independent.
-__device__ void isotope_pass(const WarpMem& W, uint32_t P, double gap, int lane) {
-    if (count_kept(W.keep, P, lane) <= 2) return;
-    // hard-boundary flags in W.aux (1 = chain restarts here), result in W.k2
+__device__ __noinline__ void isotope_pass_p(const double* mz, const double* in, const uint16_t* ord, uint8_t* keep, uint8_t* k2, uint16_t* aux, uint32_t P, double gap, int lane) {
+    if (count_kept(keep, P, lane) <= 2) return;
+    // hard-boundary flags in aux (1 = chain restarts here), result in k2
     int carry = -1;                                                           // last kept position before this chunk
     for (uint32_t c0 = 0; c0 < P; c0 += 32) {
         uint32_t i = c0 + lane;
-        bool k = i < P && W.keep[i];
+        bool k = i < P && keep[i];
         uint32_t bal = __ballot_sync(0xffffffffu, k);
         if (i < P) {
-            W.k2[i] = 0;
+            k2[i] = 0;
             uint32_t below = bal & ((1u << lane) - 1u);
             int prev = below ? (int)(c0 + 31 - __clz(below)) : carry;
             uint16_t hb = 0;
             if (k) {
-                double m = W.mz[W.ord[i]];
-                hb = (prev < 0 || m < 200.0 || __dsub_rn(m, W.mz[W.ord[prev]]) >= gap) ? 1 : 0;
+                double m = mz[ord[i]];
+                hb = (prev < 0 || m < 200.0 || __dsub_rn(m, mz[ord[prev]]) >= gap) ? 1 : 0;
             }
-            W.aux[i] = hb;
+            aux[i] = hb;
         }
         if (bal) carry = (int)(c0 + 31 - __clz(bal));
     }
     __syncwarp();
     for (uint32_t h = lane; h < P; h += 32) {
-        if (!W.keep[h] || !W.aux[h]) continue;
-        uint32_t cur = h; double ref = W.mz[W.ord[h]]; double cur_in = W.in[W.ord[h]];
+        if (!keep[h] || !aux[h]) continue;
+        uint32_t cur = h; double ref = mz[ord[h]]; double cur_in = in[ord[h]];
         for (uint32_t i = h + 1; i < P; ++i) {
-            if (!W.keep[i]) continue;
-            if (W.aux[i]) break;
-            double m = W.mz[W.ord[i]];
-            if (__dsub_rn(m, ref) >= gap) { W.k2[cur] = 1; cur = i; ref = m; cur_in = W.in[W.ord[i]]; }
-            else { double v = W.in[W.ord[i]]; if (v > cur_in) { cur = i; ref = m; cur_in = v; } }
+            if (!keep[i]) continue;
+            if (aux[i]) break;
+            double m = mz[ord[i]];
+            if (__dsub_rn(m, ref) >= gap) { k2[cur] = 1; cur = i; ref = m; cur_in = in[ord[i]]; }
+            else { double v = in[ord[i]]; if (v > cur_in) { cur = i; ref = m; cur_in = v; } }
         }
-        W.k2[cur] = 1;
+        k2[cur] = 1;
     }
     __syncwarp();
-    for (uint32_t i = lane; i < P; i += 32) W.keep[i] = W.k2[i];
+    for (uint32_t i = lane; i < P; i += 32) keep[i] = k2[i];
     __syncwarp();
 }
 
+__device__ __forceinline__ void isotope_pass(const WarpMem& W, uint32_t P, double gap, int lane) { isotope_pass_p(W.mz, W.in, W.ord, W.keep, W.k2, W.aux, P, gap, lane); }
+
 // rank from the top among the kept entries by (intensity, m/z position): g = #kept j with I_j > I_i or (I_j == I_i and j > i)
-__device__ void top_rank(const WarpMem& W, uint32_t P, uint16_t* out, int lane) {
+__device__ __noinline__ void top_rank_p(const uint8_t* keep, const double* in, const uint16_t* ord, uint32_t P, uint16_t* out, int lane) {
     for (uint32_t i = lane; i < P; i += 32) {
         uint32_t g = 0;
-        if (W.keep[i]) {
-            double vi = W.in[W.ord[i]];
+        if (keep[i]) {
+            double vi = in[ord[i]];
             for (uint32_t j = 0; j < P; ++j) {
-                if (!W.keep[j]) continue;
-                double vj = W.in[W.ord[j]];
+                if (!keep[j]) continue;
+                double vj = in[ord[j]];
                 g += (vj > vi || (vj == vi && j > i)) ? 1u : 0u;
             }
         }
@@ -127,6 +130,7 @@ __device__ void top_rank(const WarpMem& W, uint32_t P, uint16_t* out, int lane) 
     }
     __syncwarp();
 }
+__device__ __forceinline__ void top_rank(const WarpMem& W, uint32_t P, uint16_t* out, int lane) { top_rank_p(W.keep, W.in, W.ord, P, out, lane); }
 // keep only the `top` largest kept entries: JMatch.filterByPeakCount (:148-174)
 __device__ void keep_top(const WarpMem& W, uint32_t P, uint32_t top, int lane) {
     top_rank(W, P, W.aux, lane);
@@ -145,7 +149,7 @@ __device__ __forceinline__ uint32_t count_lt(const double* a, uint32_t n, double
     return lo;
 }
 
-template <int kPrepWarps>
+template <int kPrepWarps, int METHOD>
 __global__ void __launch_bounds__(32 * kPrepWarps)
 k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_list, PrepConfig cfg, uint8_t* __restrict__ blobs,
                   const uint64_t* __restrict__ blob_off, uint32_t* __restrict__ blob_len, uint32_t cap, uint32_t p_lo, uint32_t p_hi) {
@@ -195,7 +199,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             const double indexDouble = P > 1 ? __dmul_rn(0.05, (double)(P - 1)) : 0.0;
             const int index = (int)indexDouble;
             double valueAtIndex, valueNext = 0.0;
-            const bool extract = cfg.method == 1 && P <= 256 && index + 2 <= 24;
+            const bool extract = METHOD == 1 && P <= 256 && index + 2 <= 24;
             if (!extract) {
                 warp_sort_idx(W.ordI, W.in, n, lane);              // stable intensity order (JSpectrum.sortPeaksByIntensity)
                 for (uint32_t i = lane; i < P; i += 32) W.da[i] = W.in[W.ordI[i]];
@@ -236,7 +240,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         __syncwarp();
 
         uint32_t nsurv = 0, flags = 0;
-        if (cfg.method == 1) {
+        if (METHOD == 1) {
             // ---- HyperscoreMatch.SpectrumPreProcessing (HyperscoreMatch.java:47-59) ----
             isotope_pass(W, P, 0.95, lane);
             const double tol_mz = __ddiv_rn(__dmul_rn(1.0, itol), (double)z);
@@ -470,7 +474,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
                 else {
                     uint32_t cc = W.cx[best];
                     if ((cc & 0xFFFu) == kNoSurvivor) code = kAnsNone;
-                    else if (cfg.method == 2 && (W.da[best] < 200.0 || W.da[best] > 2000.0)) code = kAnsNone;     // MVHMatch.java:248-250
+                    else if (METHOD == 2 && (W.da[best] < 200.0 || W.da[best] > 2000.0)) code = kAnsNone;     // MVHMatch.java:248-250
                     else code = cc;
                 }
             }
@@ -511,12 +515,12 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
                 *reinterpret_cast<uint4*>(g_cells + lane * kPerLane + k8) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
-        if (cfg.method == 1) for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = k < nsurv ? val[k] : 0.0;
+        if (METHOD == 1) for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = k < nsurv ? val[k] : 0.0;
         else for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = 0.0;
         if (lane == 0) {
             BlobHeader h;
             h.n_peaks = E; h.n_events = NE; h.n_survivors = nsurv; h.flags = flags;
-            for (int c = 0; c < 4; ++c) h.cls_count[c] = cfg.method == 2 ? s_cls[warp][c] : 0;
+            for (int c = 0; c < 4; ++c) h.cls_count[c] = METHOD == 2 ? s_cls[warp][c] : 0;
             h.total_bytes = BL.total; h.raw_peaks = P; h.pad[0] = h.pad[1] = 0;
             *reinterpret_cast<BlobHeader*>(blob) = h;
             blob_len[item] = BL.total;
@@ -542,11 +546,12 @@ int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, c
         ++launched;
     };
     // size class 1: up to 256 peaks (the common case), four spectra per CTA; size class 2: the rest, capacity = next power of two
-    run(k0_prepare_kernel<4>, 4, 256, 0, 256);
+    const bool mvh = cfg.method == 2;
+    if (mvh) run(k0_prepare_kernel<4, 2>, 4, 256, 0, 256); else run(k0_prepare_kernel<4, 1>, 4, 256, 0, 256);
     if (max_peaks > 256) {
         uint32_t cap = 512; while (cap < max_peaks) cap <<= 1;
-        if (cap <= 1024) run(k0_prepare_kernel<4>, 4, cap, 257, 0xFFFFFFFFu);
-        else run(k0_prepare_kernel<1>, 1, cap, 257, 0xFFFFFFFFu);
+        if (cap <= 1024) { if (mvh) run(k0_prepare_kernel<4, 2>, 4, cap, 257, 0xFFFFFFFFu); else run(k0_prepare_kernel<4, 1>, 4, cap, 257, 0xFFFFFFFFu); }
+        else { if (mvh) run(k0_prepare_kernel<1, 2>, 1, cap, 257, 0xFFFFFFFFu); else run(k0_prepare_kernel<1, 1>, 1, cap, 257, 0xFFFFFFFFu); }
     }
     return launched;
 }
