@@ -73,6 +73,7 @@ struct pq_ctx {
     int64_t nS = 0; uint32_t max_peaks = 0;
     DevBuf s_prec, s_charge, s_mass, s_off, s_mz, s_in, s_caller, ld[9];
     std::vector<int32_t> h_caller; std::vector<double> h_mass; std::vector<int32_t> h_charge; std::vector<uint32_t> h_npeaks;
+    bool host_spectra_valid = false;
     SpectraView view() const {
         SpectraView v; v.n = nS; v.prec_mz = s_prec.as<double>(); v.charge = s_charge.as<int32_t>(); v.mass = s_mass.as<double>();
         v.off = s_off.as<uint64_t>(); v.mz = s_mz.as<double>(); v.inten = s_in.as<double>(); v.caller_index = s_caller.as<int32_t>();
@@ -267,6 +268,25 @@ int32_t copy_to_caller(pq_ctx* ctx, void* dst, const void* src, size_t bytes) {
     return PQ_OK;
 }
 
+// Host mirrors of the sorted spectrum metadata, only needed by the host-driven entry points (Step 5, pq_score_pairs)
+int32_t ensure_host_spectra(pq_ctx* ctx) {
+    if (ctx->host_spectra_valid) return PQ_OK;
+    const int64_t n = ctx->nS;
+    ctx->h_caller.resize(n); ctx->h_mass.resize(n); ctx->h_charge.resize(n); ctx->h_npeaks.resize(n);
+    if (n) {
+        std::vector<uint64_t> off((size_t)n + 1);
+        CU(cudaMemcpyAsync(ctx->h_caller.data(), ctx->s_caller.p, n * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(ctx->h_mass.data(), ctx->s_mass.p, n * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(ctx->h_charge.data(), ctx->s_charge.p, n * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(off.data(), ctx->s_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        ctx->cnt.d2h_bytes += (uint64_t)n * 24 + 8;
+        for (int64_t i = 0; i < n; ++i) ctx->h_npeaks[i] = (uint32_t)(off[i + 1] - off[i]);
+    }
+    ctx->host_spectra_valid = true;
+    return PQ_OK;
+}
+
 void reset_psm_state(pq_ctx* ctx) { ctx->n_psm = 0; ctx->n_seg = 0; ctx->nh3 = 0; ctx->comp3_ready = false; ctx->comp3_n = 0; ctx->have_shuffles = false; ctx->psms.clear(); ctx->comp5.clear(); }
 
 }  // namespace
@@ -429,13 +449,8 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
         ctx->cnt.other_kernel_launches += (uint64_t)k + 4;
     }
     CU(cudaGetLastError());
-    ctx->h_caller.resize(n); ctx->h_mass.resize(n); ctx->h_charge.resize(n); ctx->h_npeaks.resize(n);
-    CU(cudaMemcpyAsync(ctx->h_caller.data(), ctx->s_caller.p, n * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(ctx->h_mass.data(), ctx->s_mass.p, n * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(ctx->h_charge.data(), ctx->s_charge.p, n * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    ctx->cnt.d2h_bytes += (uint64_t)n * 16;
-    for (int64_t i = 0; i < n; ++i) { int32_t c = ctx->h_caller[i]; ctx->h_npeaks[i] = (uint32_t)(off[c + 1] - off[c]); }
+    ctx->host_spectra_valid = false;          // host mirrors (Step 5, pq_score_pairs) are pulled on first use
     return PQ_OK;
 }
 
@@ -639,9 +654,11 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
         CU(cudaMemcpyAsync(&s_first, &ctx->d_psm.as<DevPsm>()[0].spectrum_sorted, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaMemcpyAsync(&s_last, &ctx->d_psm.as<DevPsm>()[nh - 1].spectrum_sorted, 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        ctx->cnt.d2h_bytes += 12;
+        CU(cudaMemcpyAsync(&ctx->psm_mass_lo, ctx->s_mass.as<double>() + s_first, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&ctx->psm_mass_hi, ctx->s_mass.as<double>() + s_last, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        ctx->cnt.d2h_bytes += 28;
         ctx->n_psm = nh; ctx->n_seg = nseg;
-        ctx->psm_mass_lo = ctx->h_mass[(size_t)s_first]; ctx->psm_mass_hi = ctx->h_mass[(size_t)s_last];
     }
     ctx->cnt.psms = ctx->n_psm;
     mk.mark("psm table");
@@ -1015,6 +1032,8 @@ int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms) {
     Marks mk("step5");
     int32_t rc = pq_rank_and_validate(ctx);       // doPTMValidation reads psm_rank.txt (ModificationDB.java:1340-1384)
     if (rc) return rc;
+    rc = ensure_host_spectra(ctx);
+    if (rc) return rc;
     ctx->comp5.clear();
     PeptideTable& R = ctx->reference; PeptideTable& T = ctx->targets;
     // Step 5 is driven from the host: mirror the device PSM table (table order: PSMs of one spectrum are contiguous)
@@ -1133,7 +1152,7 @@ int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_ind
     if (n_pairs == 0) return PQ_OK;
     if (n_pairs > 0x7ffffff0LL) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many pairs for one call");
     cudaSetDevice(ctx->P.device);
-    { int32_t rc0 = ensure_counters(ctx); if (rc0) return rc0; }
+    { int32_t rc0 = ensure_counters(ctx); if (rc0) return rc0; rc0 = ensure_host_spectra(ctx); if (rc0) return rc0; }
     cudaStream_t st = ctx->st;
     const int64_t n = ctx->nS;
     // caller index -> sorted index
