@@ -37,6 +37,8 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_red_u[2][kPtmBlock / 32];
     __shared__ int s_stop;
+    __shared__ uint32_t s_fill;
+    __shared__ uint64_t s_cand[2 * kPtmBlock];          // compacted (row, PTM, site) candidates waiting to be scored
     constexpr int BLOCK = kPtmBlock;
 
     uint8_t* stage0 = smem;
@@ -65,15 +67,44 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
             uint32_t bytes = L.blob_len[J.blob];
             mbar_expect_tx(&s_bar, bytes);
             tma_load_1d(stage0, L.blobs + L.blob_off[J.blob], bytes, &s_bar);
-            s_stop = 0;
+            s_stop = 0; s_fill = 0;
         }
         mbar_wait(&s_bar, it & 1u);
         __syncthreads();
         const BlobView B = view_blob(stage0);
         uint32_t n_pairs = 0, n_better = 0;
 
+        double mono = J.mass; int cur_iso = 0;
+        // one thread per candidate: the reference form plus one PTM at one site, scored like any other pair
+        auto score_batch = [&](uint32_t base, uint32_t count) {
+            if (tid < (int)count) {
+                const uint64_t cand = s_cand[base + tid];
+                const uint32_t row = (uint32_t)cand, t = (uint32_t)(cand >> 32) & 0xFFFFu; const int site = (int)(cand >> 48);
+                const pq_ptm P = L.ptms[t];
+                const uint4* rp = reinterpret_cast<const uint4*>(L.rows + (size_t)row * kRowBytes);
+                uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+                codes[0 * BLOCK] = q0.x; codes[1 * BLOCK] = q0.y; codes[2 * BLOCK] = q0.z; codes[3 * BLOCK] = q0.w;
+                codes[4 * BLOCK] = q1.x; codes[5 * BLOCK] = q1.y; codes[6 * BLOCK] = q1.z; codes[7 * BLOCK] = q1.w;
+                codes[8 * BLOCK] = q2.x; codes[9 * BLOCK] = q2.y; codes[10 * BLOCK] = q2.z; codes[11 * BLOCK] = q2.w;
+                codes[12 * BLOCK] = q3.x; codes[13 * BLOCK] = q3.y; codes[14 * BLOCK] = q3.z; codes[15 * BLOCK] = q3.w;
+                Extra ex; ex.site = site; ex.delta = P.delta;
+                PairScore ps = score_pair<BLOCK, 1>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, nullptr, 0, nullptr);
+                ++n_pairs;
+                bool better = cfg.hc ? ps.score >= J.ref_score : ps.score > J.ref_score;      // :239-259, PSMT:920-943
+                if (better) { ++n_better; if (cfg.fast) s_stop = 1; }
+                if (ps.score >= cfg.min_score && ps.score >= J.ref_score) {                    // rows of ptm.txt (ModificationDB.java:1660-1663)
+                    uint32_t slot = atomicAdd(L.hit_count, 1u);
+                    if (slot < L.hit_capacity) {
+                        Hit h; h.spectrum = J.spectrum; h.cand = row; h.score = ps.score; h.mass = __dadd_rn(__ldg(L.row_mass + row), P.delta);
+                        h.count_a = ps.a; h.count_b = ps.b; h.iso = cur_iso; h.aux = (int32_t)((t << 8) | (uint32_t)site);
+                        h.blob = J.blob; h.pad = 0;
+                        L.hits[slot] = h;
+                    }
+                }
+            }
+        };
         for (int ii = 0; ii < L.n_isotope; ++ii) {
-            double mono = J.mass;                                                       // CParameter.java:423-448
+            mono = J.mass; cur_iso = plain_iso ? 0 : L.isotope[ii];                                                       // CParameter.java:423-448
             if (!plain_iso) mono = __dsub_rn(mono, __dmul_rn((double)L.isotope[ii], kIsotope));
             // ---- phase 1: shifted window of every PTM ----
             uint32_t local = 0;
@@ -108,66 +139,83 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
                 __syncthreads();
             }
             const uint32_t total = s_total;
-            // ---- phase 2: one thread per (PTM, reference row) ----
+            // ---- phase 2: enumerate the candidates (PTM, reference row, free site) of one chunk of items, compact them
+            // into a shared-memory list, and score the list densely, one thread per candidate, BLOCK at a time ----
             for (uint32_t i0 = 0; i0 < total; i0 += BLOCK) {
                 if (cfg.fast && s_stop) break;
-                uint32_t i = i0 + tid;
-                if (i >= total) continue;
-                uint32_t lo = 0, hi = (uint32_t)L.n_ptm;                                 // last t with off[t] <= i
-                while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
-                const uint32_t t = lo;
-                const pq_ptm P = L.ptms[t];
-                const uint32_t row = s_lo[t] + (i - s_off[t]);
-                // exact window (ModPepQueryAndScoringWorker.java:165-203)
-                const double refm = __ldg(L.row_mass + row);
-                const long long ind = jround(__dmul_rn(10.0, __dsub_rn(mono, P.delta)));
-                const long long key = jround(__dmul_rn(refm, 10.0));
-                if (key < ind - 1 || key > ind + 1) continue;
-                const double pep_mass = __dadd_rn(refm, P.delta);
-                double del = cfg.tol_ppm ? __ddiv_rn(__dmul_rn(1.0e6, __dsub_rn(pep_mass, mono)), pep_mass) : __dsub_rn(pep_mass, mono);
-                if (!(fabs(del) <= cfg.tol)) continue;
-                const uint32_t rcode = P.residue ? (uint32_t)(P.residue - 'A') : 0xFFu;
-                if (P.residue && !((__ldg(L.row_mask + row) >> rcode) & 1u)) continue;   // :207-209 residue absent
-                const uint4* rp = reinterpret_cast<const uint4*>(L.rows + (size_t)row * kRowBytes);
-                uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
-                codes[0 * BLOCK] = q0.x; codes[1 * BLOCK] = q0.y; codes[2 * BLOCK] = q0.z; codes[3 * BLOCK] = q0.w;
-                codes[4 * BLOCK] = q1.x; codes[5 * BLOCK] = q1.y; codes[6 * BLOCK] = q1.z; codes[7 * BLOCK] = q1.w;
-                codes[8 * BLOCK] = q2.x; codes[9 * BLOCK] = q2.y; codes[10 * BLOCK] = q2.z; codes[11 * BLOCK] = q2.w;
-                codes[12 * BLOCK] = q3.x; codes[13 * BLOCK] = q3.y; codes[14 * BLOCK] = q3.z; codes[15 * BLOCK] = q3.w;
-                const int Lp = (int)(q0.x & 0xFF);
-                const uint32_t ntc = (q0.x >> 8) & 0xFF, ctc = (q0.x >> 16) & 0xFF;
-                // sites of the PTM on this form that carry nothing yet (ModificationDB.java:268-292), ascending
-                int s_begin, s_end;
-                switch (P.position) {
-                    case PQ_MOD_ANYWHERE: s_begin = 1; s_end = Lp; break;
-                    case PQ_MOD_PEP_NTERM: s_begin = 0; s_end = 0; break;
-                    case PQ_MOD_PEP_CTERM: s_begin = Lp + 1; s_end = Lp + 1; break;
-                    case PQ_MOD_PEP_NTERM_AA: s_begin = 1; s_end = 1; break;
-                    default: s_begin = Lp; s_end = Lp; break;                            // PQ_MOD_PEP_CTERM_AA
-                }
-                for (int site = s_begin; site <= s_end; ++site) {
-                    bool ok;
-                    if (site == 0) ok = ntc == 0;
-                    else if (site == Lp + 1) ok = ctc == 0;
-                    else { uint32_t code = row_byte<BLOCK>(codes, kRowHeader + site - 1); ok = P.residue ? code == rcode : code < 26u; }
-                    if (!ok) continue;
-                    Extra ex; ex.site = site; ex.delta = P.delta;
-                    PairScore ps = score_pair<BLOCK, 1>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, nullptr, 0, nullptr);
-                    ++n_pairs;
-                    bool better = cfg.hc ? ps.score >= J.ref_score : ps.score > J.ref_score;      // :239-259, PSMT:920-943
-                    if (better) { ++n_better; if (cfg.fast) s_stop = 1; }
-                    if (ps.score >= cfg.min_score && ps.score >= J.ref_score) {                    // rows of ptm.txt (ModificationDB.java:1660-1663)
-                        uint32_t slot = atomicAdd(L.hit_count, 1u);
-                        if (slot < L.hit_capacity) {
-                            Hit h; h.spectrum = J.spectrum; h.cand = row; h.score = ps.score; h.mass = pep_mass;
-                            h.count_a = ps.a; h.count_b = ps.b; h.iso = plain_iso ? 0 : L.isotope[ii]; h.aux = (int32_t)((t << 8) | (uint32_t)site);
-                            h.blob = J.blob; h.pad = 0;
-                            L.hits[slot] = h;
+                const uint32_t i = i0 + tid;
+                uint64_t sites = 0ull;                 // bit s: site s of this item takes the PTM
+                uint32_t row = 0, t = 0;
+                if (i < total) {
+                    uint32_t lo = 0, hi = (uint32_t)L.n_ptm;                                 // last t with off[t] <= i
+                    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
+                    t = lo;
+                    const pq_ptm P = L.ptms[t];
+                    row = s_lo[t] + (i - s_off[t]);
+                    // exact window (ModPepQueryAndScoringWorker.java:165-203)
+                    const double refm = __ldg(L.row_mass + row);
+                    const long long ind = jround(__dmul_rn(10.0, __dsub_rn(mono, P.delta)));
+                    const long long key = jround(__dmul_rn(refm, 10.0));
+                    bool ok = key >= ind - 1 && key <= ind + 1;
+                    if (ok) {
+                        const double pep_mass = __dadd_rn(refm, P.delta);
+                        double del = cfg.tol_ppm ? __ddiv_rn(__dmul_rn(1.0e6, __dsub_rn(pep_mass, mono)), pep_mass) : __dsub_rn(pep_mass, mono);
+                        ok = fabs(del) <= cfg.tol;
+                    }
+                    const uint32_t rcode = P.residue ? (uint32_t)(P.residue - 'A') : 0xFFu;
+                    if (ok && P.residue && !((__ldg(L.row_mask + row) >> rcode) & 1u)) ok = false;   // :207-209 residue absent
+                    if (ok) {
+                        // sites of the PTM on this form that carry nothing yet (ModificationDB.java:268-292)
+                        const uint32_t* rw = reinterpret_cast<const uint32_t*>(L.rows + (size_t)row * kRowBytes);
+                        const uint32_t head = __ldg(rw);
+                        const int Lp = (int)(head & 0xFF);
+                        const uint32_t ntc = (head >> 8) & 0xFF, ctc = (head >> 16) & 0xFF;
+                        auto residue_ok = [&](int site) {
+                            uint32_t w = __ldg(rw + ((kRowHeader + site - 1) >> 2));
+                            uint32_t code = (w >> (((kRowHeader + site - 1) & 3) * 8)) & 0xFFu;
+                            return P.residue ? code == rcode : code < 26u;
+                        };
+                        switch (P.position) {
+                            case PQ_MOD_ANYWHERE: for (int site = 1; site <= Lp; ++site) if (residue_ok(site)) sites |= 1ull << site; break;
+                            case PQ_MOD_PEP_NTERM: if (ntc == 0) sites = 1ull; break;
+                            case PQ_MOD_PEP_CTERM: if (ctc == 0) sites = 1ull << (Lp + 1); break;
+                            case PQ_MOD_PEP_NTERM_AA: if (residue_ok(1)) sites = 1ull << 1; break;
+                            default: if (residue_ok(Lp)) sites = 1ull << Lp; break;                 // PQ_MOD_PEP_CTERM_AA
                         }
                     }
-                    if (cfg.fast && better) break;
+                }
+                // append the chunk's candidates round by round (round r = every item's r-th site): at most BLOCK per round
+                for (;;) {
+                    const bool have = sites != 0ull;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, have);
+                    if ((tid & 31) == 0) s_scan[tid >> 5] = __popc(bal);
+                    __syncthreads();
+                    uint32_t before = 0, all = 0;
+                    for (int w = 0; w < BLOCK / 32; ++w) { uint32_t c = s_scan[w]; if (w < (tid >> 5)) before += c; all += c; }
+                    if (all == 0) { __syncthreads(); break; }
+                    if (have) {
+                        const int site = __ffsll((long long)sites) - 1;
+                        sites &= sites - 1;
+                        s_cand[s_fill + before + __popc(bal & ((1u << (tid & 31)) - 1u))] = (uint64_t)row | ((uint64_t)t << 32) | ((uint64_t)site << 48);
+                    }
+                    __syncthreads();
+                    if (tid == 0) s_fill += all;
+                    __syncthreads();
+                    // score full batches (always leaves room for the next round)
+                    while (s_fill >= (uint32_t)BLOCK) {
+                        const uint32_t base = s_fill - BLOCK;
+                        score_batch(base, BLOCK);
+                        __syncthreads();
+                        if (tid == 0) s_fill = base;
+                        __syncthreads();
+                        if (cfg.fast && s_stop) break;
+                    }
+                    if (cfg.fast && s_stop) break;
                 }
             }
+            if (!(cfg.fast && s_stop) && s_fill > 0) score_batch(0, s_fill);
+            __syncthreads();
+            if (tid == 0) s_fill = 0;
             __syncthreads();
         }
         for (int o = 16; o > 0; o >>= 1) { n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, o); n_better += __shfl_xor_sync(0xffffffffu, n_better, o); }
