@@ -319,11 +319,19 @@ def main():
     k1_ms = c.ms_score_step[2] / a.steps
     k1_bytes = c.bytes_score_step[2] / a.steps
     achieved = (k1_bytes / 1e9) / (k1_ms / 1e3) if k1_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_step4_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)); w = tj.get("workload", {})
+        if (w.get("spectra"), w.get("peptides"), w.get("proteins"), w.get("shuffles"), w.get("method")) == (a.spectra, a.peptides, a.proteins, a.shuffles, a.method):
+            traffic = tj["bytes_per_launch"]          # measured DRAM bytes of this launch (ncu), same per-GPU workload
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "k1_score_kernel<256,%d> (Step 4, one launch per step)" % a.method, "peak_source": peak_src,
                 "ms_per_launch": k1_ms, "pairs_per_launch": c.pairs_step4 / a.steps,
+                "algorithmic_bytes_per_launch": k1_bytes,
                 "note": "algorithmic bytes = sum over pairs of 16*P_s+96 (SURVEY.md 8d); each spectrum is staged once in shared memory and "
-                        "reused by ~1000 shuffles, so physical DRAM traffic is far lower and frac may exceed 1"}
+                        "reused by ~1000 shuffles, so physical DRAM traffic (traffic, bytes per launch from ncu, profiles/) is ~140x lower and "
+                        "frac exceeds 1: the kernel is bound by warp-issue slots (ncu: 75 % issue-active), not by HBM"}
     kernel_ms = {"k1_step2": c.ms_score_step[0] / a.steps, "k1_step3": c.ms_score_step[1] / a.steps, "k1_step4": k1_ms,
                  "k0_prepare+pack": c.ms_prepare / a.steps, "k3_window": c.ms_window / a.steps, "k2_shuffle": c.ms_shuffle / a.steps}
 
