@@ -136,7 +136,7 @@ __device__ __forceinline__ bool row_equal(const uint8_t* a, const uint8_t* b, in
     return true;
 }
 
-__global__ void k2_dedup(const ShuffleSeq* __restrict__ seqs, const uint8_t* __restrict__ raw, uint32_t* __restrict__ kept_index,
+__global__ void k2_dedup_quadratic(const ShuffleSeq* __restrict__ seqs, const uint8_t* __restrict__ raw, uint32_t* __restrict__ kept_index,
                          uint32_t* __restrict__ kept_count, uint32_t max_num) {
     extern __shared__ __align__(16) uint8_t sm[];
     uint64_t* hs = reinterpret_cast<uint64_t*>(sm);                  // [max_num]
@@ -156,6 +156,75 @@ __global__ void k2_dedup(const ShuffleSeq* __restrict__ seqs, const uint8_t* __r
         if (h == ht) { bool eq = true; for (int k = 0; k < L; ++k) if (ri[kRowHeader + k] != S.seq[k]) { eq = false; break; } if (eq) keep = false; }
         for (uint32_t j = 0; keep && j < i; ++j)
             if (hs[j] == h && row_equal(ri, rows + (size_t)j * kRowBytes, L)) keep = false;
+        flag[i] = keep ? 1 : 0;
+    }
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    // order-preserving compaction, one block-wide chunk at a time
+    for (uint32_t c0 = 0; c0 < S.num; c0 += blockDim.x) {
+        uint32_t i = c0 + threadIdx.x;
+        uint32_t f = (i < S.num) ? flag[i] : 0u;
+        uint32_t bal = __ballot_sync(0xffffffffu, f);
+        __shared__ uint32_t s_w[32];
+        uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) s_w[wid] = __popc(bal);
+        __syncthreads();
+        uint32_t before = 0;
+        for (uint32_t w = 0; w < wid; ++w) before += s_w[w];
+        uint32_t pos = s_base + before + __popc(bal & ((1u << lane) - 1u));
+        if (f) kept_index[S.out_base + pos] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) { uint32_t tot = 0; for (uint32_t w = 0; w < blockDim.x / 32; ++w) tot += s_w[w]; s_base += tot; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) kept_count[blockIdx.x] = s_base;
+}
+
+// Same filter with a shared-memory hash table (open addressing on the 64-bit row hash, smallest row index per hash): O(n)
+// instead of O(n^2) hash compares.  A row is a duplicate iff an earlier row is byte-equal; the table gives the first row
+// with the same hash, an exact compare confirms; if two different rows ever share a 64-bit hash the row falls back to the
+// exact scan over all earlier rows, so the result is identical to the quadratic kernel.
+__global__ void k2_dedup_hashed(const ShuffleSeq* __restrict__ seqs, const uint8_t* __restrict__ raw, uint32_t* __restrict__ kept_index,
+                                uint32_t* __restrict__ kept_count, uint32_t max_num, uint32_t table) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    unsigned long long* hk = reinterpret_cast<unsigned long long*>(sm);             // [table] hash keys, 0 = empty
+    unsigned long long* hs = hk + table;                                            // [max_num] row hashes
+    uint32_t* first = reinterpret_cast<uint32_t*>(hs + max_num);                    // [table] smallest row index of the key
+    uint8_t* flag = reinterpret_cast<uint8_t*>(first + table);                      // [max_num]
+    __shared__ uint32_t s_base;
+    const ShuffleSeq& S = seqs[blockIdx.x];
+    const int L = (int)S.len;
+    const uint8_t* rows = raw + (size_t)S.out_base * kRowBytes;
+    unsigned long long ht = 1469598103934665603ull;
+    for (int k = 0; k < L; ++k) { ht ^= S.seq[k]; ht *= 1099511628211ull; }
+    if (ht == 0ull) ht = 1ull;
+    for (uint32_t i = threadIdx.x; i < table; i += blockDim.x) { hk[i] = 0ull; first[i] = 0xFFFFFFFFu; }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < S.num; i += blockDim.x) {
+        unsigned long long h = row_hash(rows + (size_t)i * kRowBytes, L);
+        if (h == 0ull) h = 1ull;
+        hs[i] = h;
+        for (uint32_t slot = (uint32_t)h & (table - 1);; slot = (slot + 1) & (table - 1)) {
+            unsigned long long old = atomicCAS(&hk[slot], 0ull, h);
+            if (old == 0ull || old == h) { atomicMin(&first[slot], i); break; }
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < S.num; i += blockDim.x) {
+        const uint8_t* ri = rows + (size_t)i * kRowBytes;
+        const unsigned long long h = hs[i];
+        bool keep = true;
+        if (h == ht) { bool eq = true; for (int k = 0; k < L; ++k) if (ri[kRowHeader + k] != S.seq[k]) { eq = false; break; } if (eq) keep = false; }
+        if (keep) {
+            uint32_t slot = (uint32_t)h & (table - 1);
+            while (hk[slot] != h) slot = (slot + 1) & (table - 1);
+            const uint32_t f = first[slot];
+            if (f != i) {
+                if (row_equal(ri, rows + (size_t)f * kRowBytes, L)) keep = false;
+                else for (uint32_t j = 0; keep && j < i; ++j)                       // two rows share a 64-bit hash: exact scan
+                    if (hs[j] == h && row_equal(ri, rows + (size_t)j * kRowBytes, L)) keep = false;
+            }
+        }
         flag[i] = keep ? 1 : 0;
     }
     if (threadIdx.x == 0) s_base = 0;
@@ -249,9 +318,16 @@ int launch_shuffles(const ShuffleSeq* seqs, uint32_t n_seqs, const ShuffleForm* 
                     uint32_t max_num, int64_t shuffle_seed, cudaStream_t st) {
     if (n_seqs == 0) return 0;
     k2_generate<<<(n_seqs + kGenWarps - 1) / kGenWarps, 32 * kGenWarps, 0, st>>>(seqs, n_seqs, shuffle_seed, raw);
-    size_t smem = (size_t)max_num * 9 + 16;
-    cudaFuncSetAttribute(k2_dedup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k2_dedup<<<n_seqs, 256, smem, st>>>(seqs, raw, kept_index, kept_count, max_num);
+    uint32_t table = 64; while (table < 2 * max_num) table <<= 1;
+    const size_t smem_hashed = (size_t)table * 12 + (size_t)max_num * 9 + 16;
+    if (smem_hashed <= 160 * 1024) {
+        cudaFuncSetAttribute(k2_dedup_hashed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hashed);
+        k2_dedup_hashed<<<n_seqs, 256, smem_hashed, st>>>(seqs, raw, kept_index, kept_count, max_num, table);
+    } else {
+        size_t smem = (size_t)max_num * 9 + 16;
+        cudaFuncSetAttribute(k2_dedup_quadratic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k2_dedup_quadratic<<<n_seqs, 256, smem, st>>>(seqs, raw, kept_index, kept_count, max_num);
+    }
     if (n_forms > 0) {
         dim3 grid(n_forms, (max_num + 127) / 128);
         k2_place_mods<<<grid, 128, 0, st>>>(seqs, forms, n_forms, mods, raw, kept_index, kept_count, rows);
