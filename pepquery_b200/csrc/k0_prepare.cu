@@ -29,7 +29,7 @@ struct WarpMem {
     uint16_t* ord; uint16_t* ordI; uint16_t* aux; uint16_t* pr; uint16_t* eidx; uint16_t* cx;
     uint8_t* keep; uint8_t* k2;
 };
-__host__ __device__ inline size_t warp_smem_bytes(uint32_t cap) { return (size_t)cap * (8 * 4 + 2 * 6 + 2) + 64; }      // cap >= 256: the 30*cap bytes behind mz/in hold the cell histogram
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t cap) { return (size_t)cap * (8 * 4 + 2 * 6 + 2) + 64; }      // cap >= 256: the 30*cap bytes behind mz/in hold the cell histogram (2*kCells bytes) + one bit per event
 
 __device__ __forceinline__ bool idx_less(const double* key, uint32_t a, uint32_t b) {
     double ka = key[a], kb = key[b];
@@ -489,8 +489,10 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         // avoids this read-back but measured slower: 17.2 vs 14.5 ms for K0.)
         __syncwarp();
         uint32_t* hist = reinterpret_cast<uint32_t*>(W.da);                          // kCells u16 counters, two per word
-        for (uint32_t k = lane; k < (uint32_t)kCells / 2; k += 32) hist[k] = 0u;
+        uint32_t* none_bits = hist + kCells / 2;                                     // bit k: kept event k answers "nothing" (2E+2 bits)
+        for (uint32_t k = lane; k < (uint32_t)kCells / 2 + (NE + 31u) / 32u; k += 32) hist[k] = 0u;
         __syncwarp();
+        if (lane == 0) none_bits[0] = 1u;                                            // the -inf sentinel
         uint32_t kept = 1;                                                           // slot 0 = the -inf sentinel
         {
             uint32_t prev_code = kAnsNone;
@@ -511,6 +513,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
                     g_ev[idx] = v; g_ans[idx] = (uint16_t)code;
                     const int c = cell_of(v);
                     atomicAdd(&hist[c >> 1], 1u << (16 * (c & 1)));
+                    if (code == kAnsNone) atomicOr(&none_bits[idx >> 5], 1u << (idx & 31));
                 }
                 kept += __popc(bal);
                 __syncwarp();
@@ -532,12 +535,21 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             uint32_t incl = mine;
             for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             uint32_t run = incl - mine;
+            // kCellClean: no event inside the cell and nothing to claim at its lower edge, i.e. every t of the cell answers
+            // "nothing": K1 skips the event scan for such cells (most of the m/z axis)
+            auto cell_word = [&](uint32_t c) -> uint32_t {
+                const uint32_t here = h16[c];
+                const uint32_t none = (none_bits[run >> 5] >> (run & 31)) & 1u;
+                const uint32_t w = run | ((here == 0u && none) ? kCellClean : 0u);
+                run += here;
+                return w;
+            };
             for (uint32_t k8 = 0; k8 < kPerLane; k8 += 8) {
                 uint32_t w[4];
                 for (int h2 = 0; h2 < 4; ++h2) {
                     uint32_t c = lane * kPerLane + k8 + (uint32_t)h2 * 2u;
-                    uint32_t v0 = run; run += h16[c];
-                    uint32_t v1 = run; run += h16[c + 1];
+                    uint32_t v0 = cell_word(c);
+                    uint32_t v1 = cell_word(c + 1);
                     w[h2] = (v0 & 0xFFFFu) | (v1 << 16);
                 }
                 *reinterpret_cast<uint4*>(g_cells + lane * kPerLane + k8) = make_uint4(w[0], w[1], w[2], w[3]);

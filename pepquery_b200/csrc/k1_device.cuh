@@ -77,12 +77,14 @@ __device__ __noinline__ uint32_t match_ion_tie(const double* pmz, const double* 
 
 template <int METHOD>
 __device__ __forceinline__ uint32_t match_ion(const BlobView& B, double t, double itol) {
-    uint32_t k = B.cells[cell_of(t)];
+    uint32_t k = B.cells[cell_of(t)] & 0x7FFFu;
     while (B.ev[k + 1] <= t) ++k;
     uint32_t a = B.ans[k];
     if (a < kAnsTie || a == kAnsNone) return a;
     return match_ion_tie<METHOD>(B.pmz, B.pin, B.pcode, a & 0xFFFu, t, itol);
 }
+// Most theoretical m/z fall into cells where nothing can be claimed (kCellClean): one table load answers them.
+__device__ __forceinline__ bool ion_may_match(const BlobView& B, double t) { return !(B.cells[cell_of(t)] & kCellClean); }
 
 struct Extra { int32_t site; double delta; };   // Step 5: one extra modification (site -1 = none)
 
@@ -136,14 +138,27 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
     // All charge states of one ion, charge ascending (A5).  m/z at charge c = (m + c*proton) / c: c*proton is exact for
     // c = 1, 2, 4 and so is the division by a power of two, so only c = 3 (and >= 5) needs a real FP64 divide.
     // A6 chargeValidated: c > 1 needs c <= ion number k.
+    // Only ~1 theoretical m/z in 10 lands in a cell where something can be claimed.  Those are queued (per thread, in ion
+    // order) and resolved after the ladder walk: the warp runs the long look-up as often as its busiest lane needs it,
+    // not once per ion.  Claims happen in queue order = annotator order, and a miss claims nothing, so nothing changes.
+    constexpr int kQueue = 16;
+    double q[kQueue]; int qn = 0;
+    auto drain = [&](bool is_b) {
+        for (int i = 0; i < qn; ++i) claim(match_ion<METHOD>(B, q[i], itol), is_b);
+        qn = 0;
+    };
+    auto push = [&](double t) { if (ion_may_match(B, t)) q[qn++] = t; };
     auto ion = [&](double m, int k, bool is_b) {
-        claim(match_ion<METHOD>(B, __dadd_rn(m, kProton), itol), is_b);
-        if (nch >= 2 && k >= 2) claim(match_ion<METHOD>(B, __dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5), itol), is_b);
-        if (nch >= 3 && k >= 3) claim(match_ion<METHOD>(B, __ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0), itol), is_b);
+        if (qn > kQueue - 4) drain(is_b);
+        push(__dadd_rn(m, kProton));
+        if (nch >= 2 && k >= 2) push(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5));
+        if (nch >= 3 && k >= 3) push(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0));
         if (NCH == 0) {
-            if (nch >= 4 && k >= 4) claim(match_ion<METHOD>(B, __dmul_rn(__dadd_rn(m, 4.0 * kProton), 0.25), itol), is_b);
-            for (int c = 5; c <= nch && c <= k; ++c)
-                claim(match_ion<METHOD>(B, __ddiv_rn(__dadd_rn(m, __dmul_rn((double)c, kProton)), (double)c), itol), is_b);
+            if (nch >= 4 && k >= 4) push(__dmul_rn(__dadd_rn(m, 4.0 * kProton), 0.25));
+            for (int c = 5; c <= nch && c <= k; ++c) {
+                if (qn >= kQueue) drain(is_b);
+                push(__ddiv_rn(__dadd_rn(m, __dmul_rn((double)c, kProton)), (double)c));
+            }
         }
     };
 
@@ -167,6 +182,7 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
             ion(acc, k, true);
         }
     }
+    drain(true);
     // ---- y ions: rewind sum from the C-terminus, + H2O ----
     acc = ctd[(head >> 16) & 0xFF];
     if (ex.site == L + 1) acc = __dadd_rn(acc, ex.delta);
@@ -181,6 +197,7 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
             ion(__dadd_rn(acc, kWater), L - i, false);
         }
     }
+    drain(false);
 
     PairScore r;
     if (METHOD == 1) {

@@ -53,7 +53,8 @@ struct ModTable {
 //   pin   : raw intensity of the matchable peaks (only the tie scan reads it)
 //   pcode : claim code of each matchable peak: (class << 12) | survivor id (0xFFF = the peak did not survive pre-processing)
 //   val   : hyperscore: normalised intensity of survivor id; MVH: unused
-//   cells : cells[c] = index of the last event below the lower edge of cell c of the monotone m/z -> cell map
+//   cells : cells[c] = index of the last event below the lower edge of cell c of the monotone m/z -> cell map,
+//           | kCellClean when the whole cell answers 0xFFFF (K1 then skips the event scan)
 constexpr int kCellShift = 11;                              // 512 cells per binade
 constexpr uint32_t kCellBase = 0x40600000u >> kCellShift;   // high word of 128.0
 constexpr int kCells = 5 * 512;                             // [128, 4096) Th; below / above clamp to the first / last cell
@@ -61,6 +62,7 @@ constexpr int kValSlots = 64;
 constexpr uint32_t kNoSurvivor = 0xFFFu;
 constexpr uint32_t kAnsNone = 0xFFFFu;
 constexpr uint32_t kAnsTie = 0x8000u;
+constexpr uint32_t kCellClean = 0x8000u;     // cells[] flag: every t of the cell answers kAnsNone (no event inside, nothing to claim at its lower edge)
 
 struct BlobHeader {
     uint32_t n_peaks;        // E
