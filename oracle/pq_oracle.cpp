@@ -719,9 +719,34 @@ static void digest_protein(const Params& P, std::string prot, std::set<std::stri
     prot.erase(std::remove(prot.begin(), prot.end(), '*'), prot.end());
     for (auto& c : prot) if (c == 'I') c = 'L';
     int n = (int)prot.size();
-    std::vector<int> starts; starts.push_back(0);                       // A10: cleave after K/R unless next is P
+    // Enzyme table of DatabaseInput.getEnzymeByIndex (pg/DatabaseInput.java:145-267): residues cleaved after ("before" the
+    // cut), residues cleaved before ("after" the cut), and the residue that blocks a cut when it follows (restrictionAfter).
+    // compomics Enzyme.isCleavageSite(x, y): (x in before and y not in restrictionAfter) or (y in after) (A10).
+    static const struct { const char* before; const char* after; const char* restrict_after; } kEnzymes[18] = {
+        {"", "", ""},              // 0 NoEnzyme: unspecific, not supported
+        {"RK", "", "P"},           // 1 Trypsin
+        {"RK", "", ""},            // 2 Trypsin (no P rule)
+        {"R", "", "P"},            // 3 Arg-C
+        {"R", "", ""},             // 4 Arg-C (no P rule)
+        {"", "R", ""},             // 5 Arg-N
+        {"E", "", ""},             // 6 Glu-C
+        {"K", "", "P"},            // 7 Lys-C
+        {"K", "", ""},             // 8 Lys-C (no P rule)
+        {"", "K", ""},             // 9 Lys-N
+        {"", "D", ""},             // 10 Asp-N
+        {"", "DE", ""},            // 11 Asp-N (ambic)
+        {"FYWL", "", "P"},         // 12 Chymotrypsin
+        {"FYWL", "", ""},          // 13 Chymotrypsin (no P rule)
+        {"FL", "", ""},            // 14 Pepsin A
+        {"M", "", ""},             // 15 CNBr
+        {"", "AFILMV", ""},        // 16 Thermolysin
+        {"", "RK", ""},            // 17 LysargiNase
+    };
+    const auto& E = kEnzymes[(P.p.enzyme >= 1 && P.p.enzyme <= 17) ? P.p.enzyme : 1];
+    auto in = [](const char* set, char c) { return strchr(set, c) != nullptr && c != 0; };
+    std::vector<int> starts; starts.push_back(0);
     for (int i = 0; i < n - 1; ++i)
-        if ((prot[i] == 'K' || prot[i] == 'R') && prot[i + 1] != 'P') starts.push_back(i + 1);
+        if ((in(E.before, prot[i]) && !in(E.restrict_after, prot[i + 1])) || in(E.after, prot[i + 1])) starts.push_back(i + 1);
     starts.push_back(n);
     int ns = (int)starts.size() - 1;
     for (int i = 0; i < ns; ++i) {

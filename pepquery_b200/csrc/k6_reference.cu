@@ -57,11 +57,15 @@ __global__ void k6_protein_starts(const uint64_t* __restrict__ off, int32_t n_pr
     if (pa < pb) first[pa] = 1;
 }
 
-__global__ void k6_cut_flags(const uint8_t* __restrict__ res, const uint8_t* __restrict__ first, uint32_t n, uint8_t* __restrict__ is_start) {
+__global__ void k6_cut_flags(const uint8_t* __restrict__ res, const uint8_t* __restrict__ first, uint32_t n, EnzymeRule rule, uint8_t* __restrict__ is_start) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t f = first[i];
-    if (!f && i > 0) { uint8_t p = res[i - 1]; f = ((p == 'K' || p == 'R') && res[i] != 'P') ? 1 : 0; }
+    if (!f && i > 0) {                                      // compomics Enzyme.isCleavageSite(x, y) (A10)
+        const uint8_t x = res[i - 1], y = res[i];
+        if (x >= 'A' && x <= 'Z' && y >= 'A' && y <= 'Z')
+            f = ((((rule.cut_after >> (x - 'A')) & 1u) && !((rule.block_next >> (y - 'A')) & 1u)) || ((rule.cut_before >> (y - 'A')) & 1u)) ? 1 : 0;
+    }
     is_start[i] = f;
 }
 
@@ -305,7 +309,8 @@ bool build_reference_on_device(cudaStream_t st, const pq_params& P, const Codes&
     k6_protein_starts<<<((uint32_t)n_proteins + 255) / 256, 256, 0, st>>>(d_off.as<uint64_t>(), n_proteins, d_pos.as<uint32_t>(), n_raw, n, d_first.as<uint8_t>());
     *launches += 5;
     const uint8_t* d_res = T.residues.as<uint8_t>();
-    k6_cut_flags<<<(n + 255) / 256, 256, 0, st>>>(d_res, d_first.as<uint8_t>(), n, d_start.as<uint8_t>());
+    EnzymeRule rule; if (!enzyme_rule(P.enzyme, rule)) { err = "unsupported enzyme index"; return false; }
+    k6_cut_flags<<<(n + 255) / 256, 256, 0, st>>>(d_res, d_first.as<uint8_t>(), n, rule, d_start.as<uint8_t>());
     // segment starts (+ sentinel)
     RB(T.starts.reserve(((size_t)n + 2) * 4));
     if (!select_flagged(d_start.as<uint8_t>(), n, T.starts.as<uint32_t>(), d_cnt.as<uint32_t>(), tmp, st, err, 0)) return false;

@@ -198,10 +198,24 @@ void Codes::decode_row(const uint8_t* row, std::string& seq, FormRec& out) const
     out.mass = form_mass(seq, out);
 }
 
+bool enzyme_rule(int32_t index, EnzymeRule& out) {
+    struct Def { const char* after; const char* before; const char* block; };
+    static const Def defs[18] = {
+        {"", "", ""},            // 0 NoEnzyme
+        {"RK", "", "P"}, {"RK", "", ""}, {"R", "", "P"}, {"R", "", ""}, {"", "R", ""}, {"E", "", ""}, {"K", "", "P"}, {"K", "", ""},
+        {"", "K", ""}, {"", "D", ""}, {"", "DE", ""}, {"FYWL", "", "P"}, {"FYWL", "", ""}, {"FL", "", ""}, {"M", "", ""},
+        {"", "AFILMV", ""}, {"", "RK", ""}};
+    if (index < 1 || index > 17) return false;
+    auto mask = [](const char* s) { uint32_t m = 0; for (; *s; ++s) m |= 1u << (*s - 'A'); return m; };
+    out.cut_after = mask(defs[index].after); out.cut_before = mask(defs[index].before); out.block_next = mask(defs[index].block);
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 void digest_proteins(const pq_params& p, const double* residue_mass, int32_t n_proteins, const uint64_t* off, const char* res,
                      std::vector<std::string>& out, int threads) {
     if (threads < 1) threads = 1;
+    EnzymeRule rule; if (!enzyme_rule(p.enzyme, rule)) enzyme_rule(1, rule);
     std::vector<std::unordered_set<std::string>> part((size_t)threads);
     auto work = [&](int t) {
         std::string prot; std::vector<int> cut;
@@ -217,8 +231,11 @@ void digest_proteins(const pq_params& p, const double* residue_mass, int32_t n_p
             }
             const int n = (int)prot.size();
             cut.clear(); cut.push_back(0);
-            for (int i = 0; i + 1 < n; ++i)                        // trypsin: after K/R unless P follows (A10)
-                if ((prot[i] == 'K' || prot[i] == 'R') && prot[i + 1] != 'P') cut.push_back(i + 1);
+            for (int i = 0; i + 1 < n; ++i) {                      // compomics Enzyme.isCleavageSite (A10)
+                const char x = prot[i], y = prot[i + 1];
+                if (x < 'A' || x > 'Z' || y < 'A' || y > 'Z') continue;
+                if ((((rule.cut_after >> (x - 'A')) & 1u) && !((rule.block_next >> (y - 'A')) & 1u)) || ((rule.cut_before >> (y - 'A')) & 1u)) cut.push_back(i + 1);
+            }
             cut.push_back(n);
             const int nseg = (int)cut.size() - 1;
             for (int a = 0; a < nseg; ++a) {

@@ -45,6 +45,12 @@ struct Codes {
     void decode_row(const uint8_t* row, std::string& seq, FormRec& out) const;
 };
 
+// Cleavage rule of one enzyme as residue bit masks (bit = letter - 'A'): a cut between residues x | y happens when
+// (x in cut_after and y not in block_next) or (y in cut_before).  pg/DatabaseInput.java:145-267 lists 17 enzymes
+// (index = the -e option); compomics Enzyme.isCleavageSite applies the rule (A10).
+struct EnzymeRule { uint32_t cut_after, cut_before, block_next; };
+bool enzyme_rule(int32_t index, EnzymeRule& out);          // false: unknown index or 0 (NoEnzyme, unspecific: not supported)
+
 // DigestProteinWorker.run (OpenModificationSearch/DigestProteinWorker.java:64-137) over all proteins; returns the unique
 // I->L sequences in lexicographic order.
 void digest_proteins(const pq_params& p, const double* residue_mass, int32_t n_proteins, const uint64_t* off, const char* res,

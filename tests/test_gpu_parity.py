@@ -163,6 +163,22 @@ def test_step5_unrestricted_modification_search(data, over):
     assert (got["n_ptm"] >= 0).sum() > 50
 
 
+@pytest.mark.parametrize("enzyme", [2, 5, 6, 9, 11, 12, 16, 17])
+def test_enzymes(data, enzyme):
+    """K6's digest with other cleavage rules of the reference's -e table (cut after / cut before / blocked by the next
+    residue): the device-built reference table and Step 3 must equal the oracle's."""
+    prot, tgt, sp = data
+    p = _abi.default_params(n_random=40, enzyme=enzyme, max_missed=1 if enzyme in (12, 16) else 2)
+    g, o, got = full_compare(p, sp, tgt, prot)
+    assert g.counters().reference_forms > 1000
+
+
+def test_enzyme_zero_is_refused():
+    with pytest.raises(PepQueryError) as e:
+        Search(_abi.default_params(enzyme=0))
+    assert e.value.code == _abi.PQ_ERR_UNSUPPORTED
+
+
 RES_MASS = {"G": 57.02146372057, "A": 71.03711378471, "S": 87.03202840427, "P": 97.05276384885, "V": 99.06841391299, "T": 101.04767846841,
             "C": 103.00918478471 + 57.02146372057, "L": 113.08406397713, "N": 114.04292744114, "D": 115.02694302383, "Q": 128.05857750528,
             "K": 128.094963014, "E": 129.04259308797, "M": 131.04048491299, "H": 137.05891185845, "F": 147.06841391299, "R": 156.1011110236,

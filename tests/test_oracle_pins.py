@@ -183,6 +183,45 @@ def test_digest_rules():
     assert all(7 <= len(s) <= 45 and "I" not in s and "*" not in s for s in seqs)
 
 
+# the -e table of pg/DatabaseInput.java:145-267 restated independently of the oracle: (cleave after, cleave before, blocked by next)
+ENZYMES = {1: ("RK", "", "P"), 2: ("RK", "", ""), 3: ("R", "", "P"), 4: ("R", "", ""), 5: ("", "R", ""), 6: ("E", "", ""), 7: ("K", "", "P"),
+           8: ("K", "", ""), 9: ("", "K", ""), 10: ("", "D", ""), 11: ("", "DE", ""), 12: ("FYWL", "", "P"), 13: ("FYWL", "", ""),
+           14: ("FL", "", ""), 15: ("M", "", ""), 16: ("", "AFILMV", ""), 17: ("", "RK", "")}
+
+
+def python_digest(prot, enzyme, missed=2, min_len=7, max_len=45):
+    after, before, block = ENZYMES[enzyme]
+    prot = prot.upper().replace("*", "").replace("I", "L")
+    cuts = [0] + [i + 1 for i in range(len(prot) - 1)
+                  if (prot[i] in after and prot[i + 1] not in block) or prot[i + 1] in before] + [len(prot)]
+    out = set()
+    for a in range(len(cuts) - 1):
+        for mc in range(missed + 1):
+            if a + mc + 1 < len(cuts):
+                pep = prot[cuts[a]:cuts[a + mc + 1]]
+                if min_len <= len(pep) <= max_len:
+                    out.add(pep)
+    return out
+
+
+@pytest.mark.parametrize("enzyme", sorted(ENZYMES))
+def test_enzyme_table(enzyme):
+    """Every enzyme of the reference's -e list (compomics Enzyme.isCleavageSite semantics, A10)."""
+    from pepquery_b200 import synth
+    poff, pres = synth.proteins(12)
+    prots = [bytes(pres[poff[i]:poff[i + 1]]).decode() for i in range(len(poff) - 1)]
+    o = pq_oracle.Oracle(_abi.default_params(enzyme=enzyme, min_mass=0.0, max_mass=1e9))
+    o.load_spectra(dict(prec_mz=np.array([500.0]), charge=np.array([2], dtype=np.int32), peak_off=np.array([0, 0], dtype=np.uint64),
+                        mz=np.zeros(0), inten=np.zeros(0)))
+    o.set_targets(np.array([0, 8], dtype=np.uint32), np.frombuffer(b"AAAAAAAK", dtype=np.uint8).copy())
+    o.build_reference(poff, pres)
+    want = set()
+    for pr in prots:
+        want |= python_digest(pr, enzyme)
+    want.discard("AAAAAAAK")
+    assert set(o.reference_sequences()) == want and len(want) > 50
+
+
 def test_oracle_regression_fixture():
     """The oracle must keep reproducing its committed outputs (tests/golden/oracle_vectors.json, tools/make_golden.py)."""
     from pepquery_b200 import synth
