@@ -14,6 +14,8 @@
 //     a peak lies below 200 Th, whatever happened before, so the chain segments between such hard boundaries run in
 //     parallel, one lane per segment; only the TIC walk of MVH stays a serial FP64 prefix on one lane;
 //   * the annotator's window predicate is inverted into exact break points in t (blob "ev"/"ans", pq_common.h).
+#include <cstdlib>
+
 #include "pq_internal.h"
 
 namespace pq {
@@ -587,7 +589,10 @@ int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, c
     };
     // size class 1: up to 256 peaks (the common case), four spectra per CTA; size class 2: the rest, capacity = next power of two
     const bool mvh = cfg.method == 2;
-    if (mvh) run(k0_prepare_kernel<4, 2>, 4, 256, 0, 256); else run(k0_prepare_kernel<4, 1>, 4, 256, 0, 256);
+    const char* ew = getenv("PQ_K0_WARPS");
+    if (ew && atoi(ew) == 2) { if (mvh) run(k0_prepare_kernel<2, 2>, 2, 256, 0, 256); else run(k0_prepare_kernel<2, 1>, 2, 256, 0, 256); }
+    else if (ew && atoi(ew) == 8) { if (mvh) run(k0_prepare_kernel<8, 2>, 8, 256, 0, 256); else run(k0_prepare_kernel<8, 1>, 8, 256, 0, 256); }
+    else if (mvh) run(k0_prepare_kernel<4, 2>, 4, 256, 0, 256); else run(k0_prepare_kernel<4, 1>, 4, 256, 0, 256);
     if (max_peaks > 256) {
         uint32_t cap = 512; while (cap < max_peaks) cap <<= 1;
         if (cap <= 1024) { if (mvh) run(k0_prepare_kernel<4, 2>, 4, cap, 257, 0xFFFFFFFFu); else run(k0_prepare_kernel<4, 1>, 4, cap, 257, 0xFFFFFFFFu); }
