@@ -8,80 +8,20 @@
 //
 // Each (ion type, loss, charge) series is ascending in the ion number, so the sorted unique stream is an S-way merge of
 // at most 2*3*2 series; one thread per row, two results per row: [2*row] for precursor charge 2, [2*row+1] otherwise.
-#include "pq_internal.h"
+#include "k4_device.cuh"
 
 namespace pq {
 
 namespace {
-
-constexpr int kMaxLoss = 3;
 
 __global__ void k4_predict_kernel(const uint8_t* __restrict__ rows, uint32_t n_rows, const ModTable* __restrict__ M, double itol,
                                   int32_t* __restrict__ out) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     const uint8_t* row = rows + (size_t)r * kRowBytes;
-    const int L = row[0];
-    double b[kMaxLen], y[kMaxLen];
-    double loss[kMaxLoss]; int nloss = 0;
-    auto add_loss = [&](double l) {
-        if (l == 0.0) return;
-        for (int i = 0; i < nloss; ++i) if (loss[i] == l) return;
-        if (nloss < kMaxLoss) loss[nloss++] = l;
-    };
-    add_loss(M->nterm_loss[row[1]]); add_loss(M->cterm_loss[row[2]]);
-    double acc = M->nterm[row[1]];
-    for (int k = 1; k <= L - 1; ++k) {
-        uint32_t code = row[kRowHeader + k - 1];
-        acc = __dadd_rn(acc, M->aa[code]);
-        double d = M->delta[code];
-        if (d != 0.0) acc = __dadd_rn(acc, d);
-        b[k] = acc;
-    }
-    acc = M->cterm[row[2]];
-    for (int k = 1; k <= L - 1; ++k) {
-        uint32_t code = row[kRowHeader + L - k];
-        acc = __dadd_rn(acc, M->aa[code]);
-        double d = M->delta[code];
-        if (d != 0.0) acc = __dadd_rn(acc, d);
-        y[k] = __dadd_rn(acc, kWater);
-    }
-    for (int k = 0; k < L; ++k) add_loss(M->loss[row[kRowHeader + k]]);
-
-    for (int maxc = 1; maxc <= 2; ++maxc) {
-        // series s = ((type * (nloss+1)) + l) * maxc + (c-1)
-        const int S = 2 * (nloss + 1) * maxc;
-        int idx[2 * (kMaxLoss + 1) * 2];
-        double head[2 * (kMaxLoss + 1) * 2];
-        auto value = [&](int s, int k) -> double {
-            int c = s % maxc + 1; int q = s / maxc; int l = q % (nloss + 1); int t = q / (nloss + 1);
-            double m = t ? y[k] : b[k];
-            if (l > 0) m = __dsub_rn(m, loss[l - 1]);
-            return __ddiv_rn(__dadd_rn(m, __dmul_rn((double)c, kProton)), (double)c);
-        };
-        const double inf = __longlong_as_double(0x7ff0000000000000LL);
-        auto advance = [&](int s) {          // next in-range value of series s, or +inf
-            for (;;) {
-                int k = ++idx[s];
-                if (k > L - 1) { head[s] = inf; return; }
-                double v = value(s, k);
-                if (v > 2000.0) { head[s] = inf; idx[s] = L; return; }
-                if (v >= 200.0) { head[s] = v; return; }
-            }
-        };
-        for (int s = 0; s < S; ++s) { idx[s] = 0; advance(s); }
-        int count = 0; bool have = false; double last = 0.0;
-        for (;;) {
-            int best = -1; double bv = inf;
-            for (int s = 0; s < S; ++s) if (head[s] < bv) { bv = head[s]; best = s; }
-            if (best < 0) break;
-            if (!have) { have = true; last = bv; }
-            else if (bv != last) { if (__dsub_rn(bv, last) >= itol) ++count; last = bv; }
-            advance(best);
-        }
-        if (have) ++count;
-        out[2 * (size_t)r + (maxc - 1)] = count;
-    }
+    dev::Extra ex; ex.site = -1; ex.delta = 0.0;
+    out[2 * (size_t)r] = dev::predict_peaks(row, M, itol, 1, ex);          // precursor charge 2: fragment charge 1 only
+    out[2 * (size_t)r + 1] = dev::predict_peaks(row, M, itol, 2, ex);
 }
 
 }  // namespace

@@ -12,7 +12,7 @@
 // (PTM, reference row) item checks the exact predicate and a residue-presence mask, then walks the free sites, scoring
 // each candidate with the shared pair scorer (k1_device.cuh, Extra{site, delta}).  Hyperscore only (MVH would need a
 // predicted-peak count per candidate).
-#include "k1_device.cuh"
+#include "k4_device.cuh"
 
 namespace pq {
 
@@ -29,6 +29,7 @@ __device__ __forceinline__ uint32_t lower_bound_g(const double* a, uint32_t n, d
     return lo;
 }
 
+template <int METHOD>
 __global__ void __launch_bounds__(kPtmBlock)
 k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -49,6 +50,7 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
     double* s_l10 = s_ct + kMaxTermCodes;                                               // [65]
     uint32_t* s_lo = reinterpret_cast<uint32_t*>(s_l10 + 66);                           // [kMaxPtm]
     uint32_t* s_off = s_lo + kMaxPtm;                                                   // [kMaxPtm + 1]
+    uint32_t* usedw_all = s_off + kMaxPtm + 2;                                          // MVH only: [10][BLOCK]
 
     const int tid = threadIdx.x;
     for (int i = tid; i < kMaxCodes; i += BLOCK) s_tab[i] = make_double2(L.mods->aa[i], L.mods->delta[i]);
@@ -58,6 +60,7 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
     __syncthreads();
     const double itol = cfg.itol;
     uint32_t* codes = codes_all + tid;
+    uint32_t* usedw = usedw_all + tid;
     const bool plain_iso = L.n_isotope == 1 && L.isotope[0] == 0;
 
     uint32_t it = 0;
@@ -88,7 +91,9 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
                 codes[8 * BLOCK] = q2.x; codes[9 * BLOCK] = q2.y; codes[10 * BLOCK] = q2.z; codes[11 * BLOCK] = q2.w;
                 codes[12 * BLOCK] = q3.x; codes[13 * BLOCK] = q3.y; codes[14 * BLOCK] = q3.z; codes[15 * BLOCK] = q3.w;
                 Extra ex; ex.site = site; ex.delta = P.delta;
-                PairScore ps = score_pair<BLOCK, 1>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, nullptr, 0, nullptr);
+                int32_t predicted = 0;
+                if (METHOD == 2) predicted = predict_peaks(L.rows + (size_t)row * kRowBytes, L.mods, itol, J.charge == 2 ? 1 : 2, ex);   // MVHMatch.java:165-172
+                PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, predicted, usedw);
                 ++n_pairs;
                 bool better = cfg.hc ? ps.score >= J.ref_score : ps.score > J.ref_score;      // :239-259, PSMT:920-943
                 if (better) { ++n_better; if (cfg.fast) s_stop = 1; }
@@ -248,19 +253,27 @@ int launch_row_masks(const uint8_t* rows, uint32_t n_rows, uint32_t* mask, cudaS
     return 1;
 }
 
-int launch_ptm(const PtmLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
-    if (L.n_jobs == 0 || L.n_ptm == 0) return 0;
+template <int METHOD>
+static int launch_ptm_m(const PtmLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
     uint32_t stage = (L.max_blob_bytes + 127u) & ~127u;
-    size_t smem = (size_t)stage + (size_t)16 * kPtmBlock * 4 + (size_t)(2 * kMaxCodes + 2 * kMaxTermCodes + 66) * 8 + (size_t)(2 * kMaxPtm + 2) * 4;
-    cudaFuncSetAttribute(k5_ptm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    size_t smem = (size_t)stage + (size_t)16 * kPtmBlock * 4 + (size_t)(2 * kMaxCodes + 2 * kMaxTermCodes + 66) * 8 + (size_t)(2 * kMaxPtm + 4) * 4 +
+                  (METHOD == 2 ? (size_t)10 * kPtmBlock * 4 : 0);
+    auto kernel = k5_ptm_kernel<METHOD>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k5_ptm_kernel, kPtmBlock, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPtmBlock, smem);
     if (per_sm < 1) per_sm = 1;
-    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int dev = 0; cudaGetDevice(&dev);
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     uint32_t grid = (uint32_t)(sms * per_sm);
     if (grid > L.n_jobs) grid = L.n_jobs;
-    k5_ptm_kernel<<<grid, kPtmBlock, smem, st>>>(L, cfg, stage);
+    kernel<<<grid, kPtmBlock, smem, st>>>(L, cfg, stage);
     return 1;
+}
+
+int launch_ptm(const PtmLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
+    if (L.n_jobs == 0 || L.n_ptm == 0) return 0;
+    return cfg.method == 2 ? launch_ptm_m<2>(L, cfg, st) : launch_ptm_m<1>(L, cfg, st);
 }
 
 }  // namespace pq

@@ -1025,7 +1025,6 @@ int32_t pq_get_competitors(pq_ctx* ctx, int32_t step, pq_competitor* out, int64_
 int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms) {
     if (!ctx || n_ptm < 0 || (n_ptm > 0 && !ptms)) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
     if (ctx->step_done < 3 || !ctx->have_reference) return fail(ctx, PQ_ERR_STATE, "run Steps 2-4 and pq_build_reference first");
-    if (ctx->P.score_method != 1) return fail(ctx, PQ_ERR_UNSUPPORTED, "Step 5 is implemented for hyperscore only");
     if (n_ptm > 2048) return fail(ctx, PQ_ERR_UNSUPPORTED, "more than 2048 PTM specificities");
     cudaSetDevice(ctx->P.device);
     cudaStream_t st = ctx->st;
@@ -1092,7 +1091,7 @@ int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms) {
             L.rows = R.rows.as<uint8_t>(); L.row_mass = R.mass.as<double>(); L.row_mask = R.mask.as<uint32_t>(); L.n_rows = (uint32_t)R.n();
             L.ptms = d_ptm.as<pq_ptm>(); L.n_ptm = n_ptm; L.n_isotope = ctx->P.n_isotope;
             for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) L.isotope[i] = ctx->P.isotope[i];
-            L.mods = ctx->d_mods.as<ModTable>(); L.log10_fact = ctx->d_l10.as<double>();
+            L.mods = ctx->d_mods.as<ModTable>(); L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>();
             L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>(); L.hit_capacity = cap;
             L.max_blob_bytes = ctx->max_blob;
             ScoreConfig cfg = score_config(ctx, 1);

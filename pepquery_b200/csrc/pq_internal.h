@@ -167,7 +167,7 @@ struct PtmLaunch {
     const uint8_t* rows; const double* row_mass; const uint32_t* row_mask; uint32_t n_rows;   // reference table
     const pq_ptm* ptms; int32_t n_ptm;
     int32_t n_isotope; int32_t isotope[PQ_MAX_ISOTOPE];
-    const ModTable* mods; const double* log10_fact;
+    const ModTable* mods; const double* log10_fact; const double* ln_fact;
     JobResult* results; Hit* hits; uint32_t* hit_count; uint32_t hit_capacity;
     uint32_t max_blob_bytes;
 };

@@ -163,6 +163,27 @@ def test_step5_unrestricted_modification_search(data, over):
     assert (got["n_ptm"] >= 0).sum() > 50
 
 
+def test_step5_with_mvh_scoring(data):
+    """Step 5 under -m 2: every candidate (reference form + one PTM at one site) needs its own predicted-peak count
+    (MVHMatch.java:150-227), computed per candidate inside K5."""
+    from pepquery_b200 import unimod
+    prot, tgt, sp = data
+    p = _abi.default_params(n_random=100, score_method=2)
+    ptms = unimod.load_ptms()
+    g = run_gpu(p, sp, tgt, prot); g.step5(ptms)
+    o = run_oracle(p, sp, tgt, prot); o.step5(ptms)
+    got, want = g.psms(), o.psms()
+    assert np.array_equal(got["n_ptm"], want["n_ptm"])
+    assert_psms_equal(got, want)
+    co, cg = o.competitors(5), g.competitors(5)
+    assert len(co) == len(cg)
+    for f in ("spectrum", "ref_form", "ptm", "ptm_site"):
+        assert np.array_equal(co[f], cg[f]), f
+    assert np.allclose(co["score"], cg["score"], rtol=REL, atol=0)
+    assert g.counters().pairs_step5 == int(o.pairs()[3]) > 10000
+    assert (got["n_ptm"] >= 0).sum() > 20
+
+
 @pytest.mark.parametrize("enzyme", [2, 5, 6, 9, 11, 12, 16, 17])
 def test_enzymes(data, enzyme):
     """K6's digest with other cleavage rules of the reference's -e table (cut after / cut before / blocked by the next
