@@ -84,7 +84,7 @@ __device__ __forceinline__ uint32_t match_ion(const BlobView& B, double t, doubl
     return match_ion_tie<METHOD>(B.pmz, B.pin, B.pcode, a & 0xFFFu, t, itol);
 }
 // Most theoretical m/z fall into cells where nothing can be claimed (kCellClean): one table load answers them.
-__device__ __forceinline__ bool ion_may_match(const BlobView& B, double t) { return !(B.cells[cell_of(t)] & kCellClean); }
+__device__ __forceinline__ bool ion_may_match(const BlobView& B, double t) { return reinterpret_cast<const int16_t*>(B.cells)[cell_of(t)] >= 0; }   // kCellClean = sign bit
 
 struct Extra { int32_t site; double delta; };   // Step 5: one extra modification (site -1 = none)
 

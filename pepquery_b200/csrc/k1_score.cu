@@ -18,7 +18,7 @@
 #include "k1_device.cuh"
 
 #ifndef K1_MIN_BLOCKS
-#define K1_MIN_BLOCKS 4
+#define K1_MIN_BLOCKS 3
 #endif
 
 namespace pq {

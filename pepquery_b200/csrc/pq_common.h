@@ -101,8 +101,12 @@ PQ_HD uint32_t hi32(double x) {
 }
 // Monotone map m/z -> cell: the high word of a positive double orders like the double itself.
 PQ_HD int cell_of(double mz) {
-    int c = (int)(hi32(mz) >> kCellShift) - (int)kCellBase;
+    int c = ((int)hi32(mz) >> kCellShift) - (int)kCellBase;       // arithmetic shift: below 128 Th and for a negative mz (sign bit) c < 0 -> cell 0
+#ifdef __CUDA_ARCH__
+    return min(max(c, 0), kCells - 1);
+#else
     return c < 0 ? 0 : (c >= kCells ? kCells - 1 : c);
+#endif
 }
 
 // ---- exact arithmetic ------------------------------------------------------------------------------------------------
