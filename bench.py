@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=12000, help="spectra in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--score-all-shuffles", action="store_true", help="compute every shuffle score in full (no upper-bound decision in Step 4)")
     ap.add_argument("--step5", action="store_true", help="config C4: time the unrestricted-modification search (Step 5) after Steps 2-4; prints its own JSON line")
     return ap.parse_args()
 
@@ -213,7 +214,7 @@ def main():
     t_gen = time.time()
     prot, tgt, sp = make_inputs(a, rank, world, pinned)
     t_gen = time.time() - t_gen
-    p = _abi.default_params(n_random=a.shuffles, score_method=a.method, device=local)
+    p = _abi.default_params(n_random=a.shuffles, score_method=a.method, device=local, score_all_shuffles=1 if a.score_all_shuffles else 0)
     g = Search(p)
 
     class _DevView:
@@ -392,6 +393,11 @@ def main():
                 "config": {"workload": workload_name(a), "sharding": ("spectra by precursor-mass strips (%d per GPU, interleaved), tables replicated" % STRIPS_PER_GPU) if world > 1 else "single GPU",
                            "l2": "inputs larger than L2 (prepared spectra + shuffle rows >> 126 MB per step)",
                            "pairs_per_step": float(tot_pairs.item()), "psms_per_step": int(n_psm_total),
+                           "step4_pairs_decided_by_score_bound": float(c.pairs_step4_bounded) / a.steps,
+                           "step4_rule": ("every shuffle scored in full" if a.score_all_shuffles else
+                                          "Step 4 needs only shuffleScore >= targetScore (StatisticScoreWorker.java:51): a shuffle whose hyperscore "
+                                          "upper bound (from its count of possible matches) is below the target score is decided without resolving "
+                                          "its matches; counts and p-values identical (tests); --score-all-shuffles disables it"),
                            "timed_region": "Steps 2+3+4 + rank/accept + PSM and detail rows to the host, spectra/targets/reference table resident in HBM",
                            "gen_seconds": round(t_gen, 1), "ms_host_reference_build_once": ms_host_reference},
                 "clocks": clk, "gpu_launches": int(launches), "kernel_ms_per_step": kernel_ms,

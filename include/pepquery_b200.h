@@ -98,7 +98,10 @@ typedef struct pq_params {
     pq_mod  fixed[PQ_MAX_MODS];
     pq_mod  var[PQ_MAX_MODS];
     int32_t device;             /* CUDA device ordinal                                                 */
-    int32_t reserved;
+    int32_t score_all_shuffles; /* 1 = compute every shuffle's hyperscore in full.  0 (default): Step 4 only needs
+                                   "shuffleScore >= targetScore" (pg/StatisticScoreWorker.java:51), so a shuffle whose
+                                   score upper bound (from its count of possible matches) stays below the target's
+                                   score is decided without resolving its matches; counts and p-values are identical */
 } pq_params;
 
 /* One peptide form (sequence + placed modifications) as the caller sees it. */
@@ -168,6 +171,7 @@ typedef struct pq_counters {
     double   ms_score_step[4];          /* K1 launch time of Steps 2,3,4,5 (CUDA events around the launch)       */
     uint64_t bytes_score_step[4];       /* algorithmic bytes of those launches                                   */
     double   ms_host_reference;         /* wall time of the reference-table build (digest + forms + upload)      */
+    uint64_t pairs_step4_bounded;       /* Step-4 pairs decided by the score upper bound (subset of pairs_step4)   */
 } pq_counters;
 
 typedef struct pq_ctx pq_ctx;

@@ -106,7 +106,8 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
                                                   const double2* tab, const double* ntd, const double* ctd,
                                                   int z, double itol, Extra ex,
                                                   const double* log10_fact, const double* ln_fact, int32_t predicted,
-                                                  uint32_t* usedw /* MVH: this thread's column of the used bitmap */) {
+                                                  uint32_t* usedw /* MVH: this thread's column of the used bitmap */,
+                                                  double cutoff /* > 0: only "score >= cutoff" matters (Step 4) */) {
     const uint32_t head = codes[0];
     const int L = (int)(head & 0xFF);
     const int nch = NCH > 0 ? NCH : (z <= 1 ? 1 : z - 1);
@@ -141,22 +142,30 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
     // Only ~1 theoretical m/z in 10 lands in a cell where something can be claimed.  Those are queued (per thread, in ion
     // order) and resolved after the ladder walk: the warp runs the long look-up as often as its busiest lane needs it,
     // not once per ion.  Claims happen in queue order = annotator order, and a miss claims nothing, so nothing changes.
-    constexpr int kQueue = 16;
+    // When only "score >= cutoff" matters (Step 4 counts shuffles that reach the target's score), both series are held in
+    // the queue: hyperscore is monotone in the two counts and the intensity sum, the counts cannot exceed the queued
+    // possible matches (nor the survivor count together) and a normalised intensity cannot exceed 100, so
+    // 4 (log10(100 n) + log10 nb! + log10 ny!) bounds the score from above.  A pair whose bound stays below the cutoff is
+    // reported as 0 without resolving a single match (it could never count).
+    constexpr int kQueue = 24;
     double q[kQueue]; int qn = 0;
-    auto drain = [&](bool is_b) {
-        for (int i = 0; i < qn; ++i) claim(match_ion<METHOD>(B, q[i], itol), is_b);
-        qn = 0;
+    bool in_b = true; int nb_q = 0;
+    bool holding = METHOD == 1 && cutoff > 0.0;
+    auto flush = [&]() {                                       // resolve everything queued, in ion order
+        const int split = in_b ? qn : nb_q;
+        for (int i = 0; i < qn; ++i) claim(match_ion<METHOD>(B, q[i], itol), i < split);
+        qn = 0; nb_q = 0;
     };
     auto push = [&](double t) { if (ion_may_match(B, t)) q[qn++] = t; };
-    auto ion = [&](double m, int k, bool is_b) {
-        if (qn > kQueue - 4) drain(is_b);
+    auto ion = [&](double m, int k) {
+        if (qn > kQueue - 4) { flush(); holding = false; }
         push(__dadd_rn(m, kProton));
         if (nch >= 2 && k >= 2) push(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5));
         if (nch >= 3 && k >= 3) push(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0));
         if (NCH == 0) {
             if (nch >= 4 && k >= 4) push(__dmul_rn(__dadd_rn(m, 4.0 * kProton), 0.25));
             for (int c = 5; c <= nch && c <= k; ++c) {
-                if (qn >= kQueue) drain(is_b);
+                if (qn >= kQueue) { flush(); holding = false; }
                 push(__ddiv_rn(__dadd_rn(m, __dmul_rn((double)c, kProton)), (double)c));
             }
         }
@@ -179,10 +188,11 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
             word >>= 8;
             acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
             if (k == ex.site) acc = __dadd_rn(acc, ex.delta);
-            ion(acc, k, true);
+            ion(acc, k);
         }
     }
-    drain(true);
+    if (holding) nb_q = qn; else flush();
+    in_b = false;
     // ---- y ions: rewind sum from the C-terminus, + H2O ----
     acc = ctd[(head >> 16) & 0xFF];
     if (ex.site == L + 1) acc = __dadd_rn(acc, ex.delta);
@@ -194,10 +204,16 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
             word <<= 8;
             acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
             if (i + 1 == ex.site) acc = __dadd_rn(acc, ex.delta);
-            ion(__dadd_rn(acc, kWater), L - i, false);
+            ion(__dadd_rn(acc, kWater), L - i);
         }
     }
-    drain(false);
+    if (holding) {
+        const int nb = min(nb_q, 64), ny = min(qn - nb_q, 64), n = min(min(nb_q + (qn - nb_q), (int)B.nsurv), 64);
+        double ub = 0.0;
+        if (n > 0) ub = 4.0 * (log10_fact[65 + n] + log10_fact[nb] + log10_fact[ny]);        // log10_fact[65 + n] = log10(100 n)
+        if (ub * (1.0 + 1e-12) + 1e-9 < cutoff) { PairScore r0; r0.score = 0.0; r0.a = -1; r0.b = 0; return r0; }      // a = -1: decided by the bound
+    }
+    flush();
 
     PairScore r;
     if (METHOD == 1) {
@@ -239,12 +255,12 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
 template <int BLOCK, int METHOD>
 __device__ __forceinline__ PairScore score_pair(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd, const double* ctd,
                                                 int z, double itol, Extra ex, const double* log10_fact, const double* ln_fact, int32_t predicted,
-                                                uint32_t* usedw) {
+                                                uint32_t* usedw, double cutoff = 0.0) {
     switch (z) {                                  // fragment charges = precursor charge - 1, at least 1 (JMatch.java:398-407)
-        case 0: case 1: case 2: return score_pair_n<BLOCK, METHOD, 1>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw);
-        case 3: return score_pair_n<BLOCK, METHOD, 2>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw);
-        case 4: return score_pair_n<BLOCK, METHOD, 3>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw);
-        default: return score_pair_n<BLOCK, METHOD, 0>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw);
+        case 0: case 1: case 2: return score_pair_n<BLOCK, METHOD, 1>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
+        case 3: return score_pair_n<BLOCK, METHOD, 2>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
+        case 4: return score_pair_n<BLOCK, METHOD, 3>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
+        default: return score_pair_n<BLOCK, METHOD, 0>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
     }
 }
 

@@ -33,7 +33,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ double s_red_d[BLOCK / 32];
-    __shared__ uint32_t s_red_u[3][BLOCK / 32];
+    __shared__ uint32_t s_red_u[4][BLOCK / 32];
 
     uint8_t* stage0 = smem;
     uint32_t* codes_all = reinterpret_cast<uint32_t*>(smem + (size_t)stage_bytes * nstage);           // [16][BLOCK]
@@ -41,12 +41,12 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     double* s_nt = reinterpret_cast<double*>(s_tab + kMaxCodes);
     double* s_ct = s_nt + kMaxTermCodes;
     double* s_l10 = s_ct + kMaxTermCodes;                                                              // [65]
-    uint32_t* usedw_all = reinterpret_cast<uint32_t*>(s_l10 + 66);                                     // MVH only: [10][BLOCK]
+    uint32_t* usedw_all = reinterpret_cast<uint32_t*>(s_l10 + 130);                                     // MVH only: [10][BLOCK]
 
     const int tid = threadIdx.x;
     for (int i = tid; i < kMaxCodes; i += BLOCK) s_tab[i] = make_double2(L.mods->aa[i], L.mods->delta[i]);
     for (int i = tid; i < kMaxTermCodes; i += BLOCK) { s_nt[i] = L.mods->nterm[i]; s_ct[i] = L.mods->cterm[i]; }
-    for (int i = tid; i < 65; i += BLOCK) s_l10[i] = L.log10_fact[i];
+    for (int i = tid; i < 130; i += BLOCK) s_l10[i] = L.log10_fact[i];     // [0..64] log10(n!), [65..129] log10(100 n)
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
 
@@ -79,7 +79,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
         const BlobView B = view_blob(stage0 + (size_t)stage_bytes * cur);
         const long long va = jround(__dmul_rn(J.mass, 10.0));
 
-        uint32_t n_in = 0, n_better = 0;
+        uint32_t n_in = 0, n_better = 0, n_bound = 0;
         double best = -1.0; uint32_t best_cand = 0xFFFFFFFFu;
         for (uint32_t c0 = 0; c0 < J.cand_count; c0 += BLOCK) {
             uint32_t c = c0 + tid;
@@ -99,8 +99,9 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
                 int32_t pred = 0;
                 if (METHOD == 2) pred = L.row_pred[2 * (size_t)row + (J.charge == 2 ? 0 : 1)];
                 PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex,
-                                                         s_l10, L.ln_fact, pred, usedw);
+                                                         s_l10, L.ln_fact, pred, usedw, (L.kind == kJobShuffles && !cfg.score_all) ? J.ref_score : 0.0);
                 ++n_in;
+                if (ps.a < 0) ++n_bound;
                 if (ps.score > best) { best = ps.score; best_cand = row; }
                 bool emit = false;
                 switch (L.kind) {
@@ -128,19 +129,20 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
         for (int o = 16; o > 0; o >>= 1) {
             n_in += __shfl_xor_sync(0xffffffffu, n_in, o);
             n_better += __shfl_xor_sync(0xffffffffu, n_better, o);
+            n_bound += __shfl_xor_sync(0xffffffffu, n_bound, o);
             double ob = __shfl_xor_sync(0xffffffffu, best, o);
             uint32_t oc = __shfl_xor_sync(0xffffffffu, best_cand, o);
             if (ob > best || (ob == best && oc < best_cand)) { best = ob; best_cand = oc; }
         }
-        if ((tid & 31) == 0) { s_red_u[0][tid >> 5] = n_in; s_red_u[1][tid >> 5] = n_better; s_red_u[2][tid >> 5] = best_cand; s_red_d[tid >> 5] = best; }
+        if ((tid & 31) == 0) { s_red_u[0][tid >> 5] = n_in; s_red_u[1][tid >> 5] = n_better; s_red_u[2][tid >> 5] = best_cand; s_red_u[3][tid >> 5] = n_bound; s_red_d[tid >> 5] = best; }
         __syncthreads();     // also: every thread is done with this stage's blob
         if (tid == 0) {
-            uint32_t a = 0, b = 0; double bs = -1.0; uint32_t bc = 0xFFFFFFFFu;
+            uint32_t a = 0, b = 0, nb = 0; double bs = -1.0; uint32_t bc = 0xFFFFFFFFu;
             for (int w = 0; w < BLOCK / 32; ++w) {
-                a += s_red_u[0][w]; b += s_red_u[1][w];
+                a += s_red_u[0][w]; b += s_red_u[1][w]; nb += s_red_u[3][w];
                 if (s_red_d[w] > bs || (s_red_d[w] == bs && s_red_u[2][w] < bc)) { bs = s_red_d[w]; bc = s_red_u[2][w]; }
             }
-            JobResult R; R.n_in_window = a; R.n_better = b; R.best_score = bs; R.best_cand = bc; R.pad = 0;
+            JobResult R; R.n_in_window = a; R.n_better = b; R.best_score = bs; R.best_cand = bc; R.pad = nb;
             L.results[job] = R;
             if (nstage == 1) fetch(0);
         }
@@ -152,7 +154,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
 template <int BLOCK, int METHOD>
 int launch_kernel(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
     const uint32_t stage = (L.max_blob_bytes + 127u) & ~127u;
-    const size_t tail = (size_t)16 * BLOCK * 4 + (size_t)(2 * kMaxCodes + 2 * kMaxTermCodes + 66) * 8 + (METHOD == 2 ? (size_t)10 * BLOCK * 4 : 0);
+    const size_t tail = (size_t)16 * BLOCK * 4 + (size_t)(2 * kMaxCodes + 2 * kMaxTermCodes + 130) * 8 + (METHOD == 2 ? (size_t)10 * BLOCK * 4 : 0);
     // Shuffle jobs (~1000 pairs each) hide the blob load behind a second stage; target / competitor jobs are short, there
     // one stage and more resident CTAs win (measured: Step 2 9.1 -> 5.4 ms, Step 3 18.7 -> 13.4 ms).
     int nstage = BLOCK == 256 ? 2 : 1;

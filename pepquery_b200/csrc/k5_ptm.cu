@@ -48,14 +48,14 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
     double* s_nt = reinterpret_cast<double*>(s_tab + kMaxCodes);
     double* s_ct = s_nt + kMaxTermCodes;
     double* s_l10 = s_ct + kMaxTermCodes;                                               // [65]
-    uint32_t* s_lo = reinterpret_cast<uint32_t*>(s_l10 + 66);                           // [kMaxPtm]
+    uint32_t* s_lo = reinterpret_cast<uint32_t*>(s_l10 + 130);                           // [kMaxPtm]
     uint32_t* s_off = s_lo + kMaxPtm;                                                   // [kMaxPtm + 1]
     uint32_t* usedw_all = s_off + kMaxPtm + 2;                                          // MVH only: [10][BLOCK]
 
     const int tid = threadIdx.x;
     for (int i = tid; i < kMaxCodes; i += BLOCK) s_tab[i] = make_double2(L.mods->aa[i], L.mods->delta[i]);
     for (int i = tid; i < kMaxTermCodes; i += BLOCK) { s_nt[i] = L.mods->nterm[i]; s_ct[i] = L.mods->cterm[i]; }
-    for (int i = tid; i < 65; i += BLOCK) s_l10[i] = L.log10_fact[i];
+    for (int i = tid; i < 130; i += BLOCK) s_l10[i] = L.log10_fact[i];
     if (tid == 0) { mbar_init(&s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
     const double itol = cfg.itol;
@@ -256,7 +256,7 @@ int launch_row_masks(const uint8_t* rows, uint32_t n_rows, uint32_t* mask, cudaS
 template <int METHOD>
 static int launch_ptm_m(const PtmLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
     uint32_t stage = (L.max_blob_bytes + 127u) & ~127u;
-    size_t smem = (size_t)stage + (size_t)16 * kPtmBlock * 4 + (size_t)(2 * kMaxCodes + 2 * kMaxTermCodes + 66) * 8 + (size_t)(2 * kMaxPtm + 4) * 4 +
+    size_t smem = (size_t)stage + (size_t)16 * kPtmBlock * 4 + (size_t)(2 * kMaxCodes + 2 * kMaxTermCodes + 130) * 8 + (size_t)(2 * kMaxPtm + 4) * 4 +
                   (METHOD == 2 ? (size_t)10 * kPtmBlock * 4 : 0);
     auto kernel = k5_ptm_kernel<METHOD>;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

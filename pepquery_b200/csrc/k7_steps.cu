@@ -68,15 +68,15 @@ __global__ void k7_out_keys(const DevPsm* __restrict__ psms, uint32_t n, uint64_
 __global__ void k7_job_counters(const Job* __restrict__ jobs, const JobResult* __restrict__ res, uint32_t n, const uint64_t* __restrict__ sp_off, int which,
                                 DevCounters* __restrict__ c) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long pairs = 0, bytes = 0;
+    unsigned long long pairs = 0, bytes = 0, bounded = 0;
     if (i < n) {
         int32_t s = jobs[i].spectrum;
         unsigned long long P = sp_off[s + 1] - sp_off[s];
-        pairs = res[i].n_in_window;
+        pairs = res[i].n_in_window; bounded = res[i].pad;
         bytes = pairs * (16ull * P + 96ull);
     }
-    for (int o = 16; o > 0; o >>= 1) { pairs += __shfl_xor_sync(0xffffffffu, pairs, o); bytes += __shfl_xor_sync(0xffffffffu, bytes, o); }
-    if ((threadIdx.x & 31) == 0 && pairs) { atomicAdd(&c->pairs[which], pairs); atomicAdd(&c->bytes[which], bytes); }
+    for (int o = 16; o > 0; o >>= 1) { pairs += __shfl_xor_sync(0xffffffffu, pairs, o); bytes += __shfl_xor_sync(0xffffffffu, bytes, o); bounded += __shfl_xor_sync(0xffffffffu, bounded, o); }
+    if ((threadIdx.x & 31) == 0 && pairs) { atomicAdd(&c->pairs[which], pairs); atomicAdd(&c->bytes[which], bytes); if (bounded) atomicAdd(&c->bounded, bounded); }
 }
 
 __device__ __forceinline__ uint32_t lower_bound_d(const double* a, uint32_t n, double v) {

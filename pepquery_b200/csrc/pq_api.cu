@@ -68,7 +68,7 @@ struct pq_ctx {
     std::vector<PendingTimer> timers; std::vector<cudaEvent_t> free_events;
     // constant tables
     DevBuf d_mods, d_l10, d_lnf, d_shufmods;
-    std::vector<double> ln_fact; double log10_fact[65];
+    std::vector<double> ln_fact; double log10_fact[130];    // [0..64] log10(n!), [65..129] log10(100 n) (upper-bound table of K1)
     // spectra
     int64_t nS = 0; uint32_t max_peaks = 0;
     DevBuf s_prec, s_charge, s_mass, s_off, s_mz, s_in, s_caller, ld[9];
@@ -173,6 +173,7 @@ ScoreConfig score_config(const pq_ctx* c, int check_window) {
     s.min_score = c->P.min_score; s.fast = c->P.fast; s.hc = c->P.hc;
     s.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (c->P.itol * 2.0));
     s.check_window = check_window;
+    s.score_all = c->P.score_all_shuffles || getenv("PQ_SCORE_ALL_SHUFFLES") != nullptr;
     return s;
 }
 
@@ -219,6 +220,7 @@ int32_t pull_device_counters(pq_ctx* ctx) {
     CU(cudaStreamSynchronize(ctx->st));
     ctx->cnt.pairs_step2 += h.pairs[0]; ctx->cnt.pairs_step3 += h.pairs[1]; ctx->cnt.pairs_step4 += h.pairs[2]; ctx->cnt.pairs_step5 += h.pairs[3];
     for (int i = 0; i < 4; ++i) { ctx->cnt.bytes_score_step[i] += h.bytes[i]; ctx->cnt.score_algorithmic_bytes += h.bytes[i]; }
+    ctx->cnt.pairs_step4_bounded += h.bounded;
     return PQ_OK;
 }
 
@@ -332,11 +334,13 @@ int32_t pq_create(const pq_params* params, pq_ctx** out) {
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->uev0); cudaEventCreate(&ctx->uev1);
     int bins = (int)jround((double)(int)(2000.0 - 200.0) / (params->itol * 2.0));
     factorial_tables(ctx->log10_fact, ctx->ln_fact, std::max(bins + 512, 4096));
-    bool ok = ctx->d_mods.reserve(sizeof(ModTable)) == cudaSuccess && ctx->d_l10.reserve(65 * 8) == cudaSuccess &&
+    ctx->log10_fact[65] = 0.0;
+    for (int i = 1; i <= 64; ++i) ctx->log10_fact[65 + i] = std::log10(100.0 * i);
+    bool ok = ctx->d_mods.reserve(sizeof(ModTable)) == cudaSuccess && ctx->d_l10.reserve(130 * 8) == cudaSuccess &&
               ctx->d_lnf.reserve(ctx->ln_fact.size() * 8) == cudaSuccess && ctx->d_shufmods.reserve(sizeof(ShuffleMods)) == cudaSuccess;
     if (ok) {
         cudaMemcpy(ctx->d_mods.p, &ctx->codes.table, sizeof(ModTable), cudaMemcpyHostToDevice);
-        cudaMemcpy(ctx->d_l10.p, ctx->log10_fact, 65 * 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(ctx->d_l10.p, ctx->log10_fact, 130 * 8, cudaMemcpyHostToDevice);
         cudaMemcpy(ctx->d_lnf.p, ctx->ln_fact.data(), ctx->ln_fact.size() * 8, cudaMemcpyHostToDevice);
         ok = cudaMemcpy(ctx->d_shufmods.p, &ctx->codes.shuffle, sizeof(ShuffleMods), cudaMemcpyHostToDevice) == cudaSuccess;
     }

@@ -67,7 +67,7 @@ struct JobResult {            // per job, reduced in the CTA
     uint32_t n_better;        // Step 3: score >= ref_score; Step 4: score >= ref_score; Step 5: better per -hc rule
     double   best_score;      // max score over the job (-1 if none)
     uint32_t best_cand;       // lowest candidate row attaining it
-    uint32_t pad;
+    uint32_t pad;             // Step 4: pairs whose comparison with ref_score was decided by the score upper bound
 };
 
 struct Hit {                  // appended rows (Step 2 PSMs, Step 3 detail rows, Step 5 ptm rows)
@@ -91,6 +91,7 @@ struct ScoreConfig {
     int32_t fast, hc;
     int32_t mvh_bins;
     int32_t check_window;     // candidates must pass the bucket + tolerance predicate (Steps 2, 3, 5)
+    int32_t score_all;        // Step 4: compute every shuffle's score in full (no upper-bound decision)
 };
 
 struct ScoreLaunch {
@@ -193,7 +194,7 @@ struct SegAgg {                 // Step-3 result per matched spectrum
     double  best, ref_best;
     uint32_t best_row, pad;
 };
-struct DevCounters { unsigned long long pairs[4]; unsigned long long bytes[4]; };
+struct DevCounters { unsigned long long pairs[4]; unsigned long long bytes[4]; unsigned long long bounded; };
 struct FormMods { uint32_t n_mods; int8_t mod[PQ_MAX_FORM_MODS]; };     // a target form's modifications, list order
 struct ShuffleTotals { uint32_t n_seqs, raw_rows, n_forms, out_rows, n_valid; };
 
