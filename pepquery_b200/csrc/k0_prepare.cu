@@ -39,7 +39,9 @@ __device__ __forceinline__ bool idx_less(const double* key, uint32_t a, uint32_t
 }
 // warp-synchronous bitonic sort of idx[0..n) by (key[idx], idx); n is a power of two >= 32
 __device__ __noinline__ void warp_sort_idx(uint16_t* idx, const double* key, uint32_t n, int lane) {
+    #pragma unroll 1
     for (uint32_t k = 2; k <= n; k <<= 1) {
+        #pragma unroll 1
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
             for (uint32_t i = lane; i < n; i += 32) {
                 uint32_t ixj = i ^ j;
@@ -59,12 +61,14 @@ __device__ __forceinline__ double warp_max(double m) { for (int o = 16; o > 0; o
 
 __device__ __noinline__ uint32_t count_kept(const uint8_t* keep, uint32_t P, int lane) {
     uint32_t c = 0;
+    #pragma unroll 1
     for (uint32_t i = lane; i < P; i += 32) c += keep[i];
     return warp_sum(c);
 }
 __device__ void keep_all(uint8_t* keep, uint32_t P, int lane) { for (uint32_t i = lane; i < P; i += 32) keep[i] = 1; __syncwarp(); }
 __device__ __noinline__ double max_kept_p(const uint8_t* keep, const double* in, const uint16_t* ord, uint32_t P, int lane) {
     double m = 0.0;                       // JSpectrum.getMaxIntensity starts at 0 (PSMMatch/JSpectrum.java:108-116)
+    #pragma unroll 1
     for (uint32_t i = lane; i < P; i += 32) if (keep[i]) { double v = in[ord[i]]; if (m < v) m = v; }
     return warp_max(m);
 }
@@ -79,6 +83,7 @@ __device__ __noinline__ void isotope_pass_p(const double* mz, const double* in, 
     if (count_kept(keep, P, lane) <= 2) return;
     // hard-boundary flags in aux (1 = chain restarts here), result in k2
     int carry = -1;                                                           // last kept position before this chunk
+    #pragma unroll 1
     for (uint32_t c0 = 0; c0 < P; c0 += 32) {
         uint32_t i = c0 + lane;
         bool k = i < P && keep[i];
@@ -97,9 +102,11 @@ __device__ __noinline__ void isotope_pass_p(const double* mz, const double* in, 
         if (bal) carry = (int)(c0 + 31 - __clz(bal));
     }
     __syncwarp();
+    #pragma unroll 1
     for (uint32_t h = lane; h < P; h += 32) {
         if (!keep[h] || !aux[h]) continue;
         uint32_t cur = h; double ref = mz[ord[h]]; double cur_in = in[ord[h]];
+        #pragma unroll 1
         for (uint32_t i = h + 1; i < P; ++i) {
             if (!keep[i]) continue;
             if (aux[i]) break;
@@ -110,6 +117,7 @@ __device__ __noinline__ void isotope_pass_p(const double* mz, const double* in, 
         k2[cur] = 1;
     }
     __syncwarp();
+    #pragma unroll 1
     for (uint32_t i = lane; i < P; i += 32) keep[i] = k2[i];
     __syncwarp();
 }
@@ -118,6 +126,7 @@ __device__ __forceinline__ void isotope_pass(const WarpMem& W, uint32_t P, doubl
 
 // rank from the top among the kept entries by (intensity, m/z position): g = #kept j with I_j > I_i or (I_j == I_i and j > i)
 __device__ __noinline__ void top_rank_p(const uint8_t* keep, const double* in, const uint16_t* ord, uint32_t P, uint16_t* out, int lane) {
+    #pragma unroll 1
     for (uint32_t i = lane; i < P; i += 32) {
         uint32_t g = 0;
         if (keep[i]) {
@@ -136,17 +145,20 @@ __device__ __forceinline__ void top_rank(const WarpMem& W, uint32_t P, uint16_t*
 // keep only the `top` largest kept entries: JMatch.filterByPeakCount (:148-174)
 __device__ void keep_top(const WarpMem& W, uint32_t P, uint32_t top, int lane) {
     top_rank(W, P, W.aux, lane);
+    #pragma unroll 1
     for (uint32_t i = lane; i < P; i += 32) if (W.keep[i] && W.aux[i] >= top) W.keep[i] = 0;
     __syncwarp();
 }
 
 __device__ __forceinline__ uint32_t count_le(const double* a, uint32_t n, double v) {      // #{a[i] <= v}, a ascending
     uint32_t lo = 0, hi = n;
+    #pragma unroll 1
     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] <= v) lo = mid + 1; else hi = mid; }
     return lo;
 }
 __device__ __forceinline__ uint32_t count_lt(const double* a, uint32_t n, double v) {      // #{a[i] < v}
     uint32_t lo = 0, hi = n;
+    #pragma unroll 1
     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
     return lo;
 }
@@ -172,6 +184,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
     const double itol = cfg.itol;
 
     const int32_t total_warps = (int32_t)gridDim.x * kPrepWarps;
+    #pragma unroll 1
     for (int32_t item = (int32_t)blockIdx.x * kPrepWarps + warp; item < n_list; item += total_warps) {
         const int32_t s = list[item];
         const uint64_t base = sp.off[s];
@@ -182,6 +195,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         int z = sp.charge[s]; if (z == 0) z = 1;
 
         bool sorted = true;
+        #pragma unroll 1
         for (uint32_t i = lane; i < n; i += 32) {
             double m = i < P ? sp.mz[base + i] : inf;
             W.mz[i] = m;
@@ -204,6 +218,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             const bool extract = METHOD == 1 && P <= 256 && index + 2 <= 24;
             if (!extract) {
                 warp_sort_idx(W.ordI, W.in, n, lane);              // stable intensity order (JSpectrum.sortPeaksByIntensity)
+                #pragma unroll 1
                 for (uint32_t i = lane; i < P; i += 32) W.da[i] = W.in[W.ordI[i]];
                 __syncwarp();
                 valueAtIndex = W.da[index];
@@ -211,12 +226,14 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             } else {
                 uint32_t taken = 0;                                 // bit q: this lane's element lane + 32 q is already extracted
                 valueAtIndex = 0.0;
+                #pragma unroll 1
                 for (int r = 0; r <= index + 1 && r < (int)P; ++r) {
                     double best = inf; int bq = -1;
                     for (uint32_t q = 0, i = lane; i < P; ++q, i += 32)
                         if (!((taken >> q) & 1u)) { double v = W.in[i]; if (bq < 0 || v < best) { best = v; bq = (int)q; } }
                     // warp minimum by (value, lane): ties may be taken in any order, only the values matter
                     double mv = best; int ml = bq >= 0 ? lane : 64;
+                    #pragma unroll 1
                     for (int o = 16; o > 0; o >>= 1) {
                         double ov = __shfl_xor_sync(0xffffffffu, mv, o); int ol = __shfl_xor_sync(0xffffffffu, ml, o);
                         if (ol < 64 && (ml >= 64 || ov < mv || (ov == mv && ol < ml))) { mv = ov; ml = ol; }
@@ -234,6 +251,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             }
         }
         bool has_dup = false;
+        #pragma unroll 1
         for (uint32_t i = lane; i < P; i += 32) {
             W.keep[i] = 1;
             if (i > 0 && W.mz[W.ord[i]] == W.mz[W.ord[i - 1]]) has_dup = true;
@@ -246,10 +264,12 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             // ---- HyperscoreMatch.SpectrumPreProcessing (HyperscoreMatch.java:47-59) ----
             isotope_pass(W, P, 0.95, lane);
             const double tol_mz = __ddiv_rn(__dmul_rn(1.0, itol), (double)z);
+            #pragma unroll 1
             for (uint32_t i = lane; i < P; i += 32)
                 if (W.keep[i] && fabs(__dsub_rn(W.mz[W.ord[i]], prec_mz)) <= tol_mz) W.keep[i] = 0;          // removeParentPeak
             __syncwarp();
             if (count_kept(W.keep, P, lane) == 0) keep_all(W.keep, P, lane);
+            #pragma unroll 1
             for (uint32_t i = lane; i < P; i += 32)
                 if (W.keep[i] && W.mz[W.ord[i]] <= 150.0) W.keep[i] = 0;                                      // removeLowMasses
             __syncwarp();
@@ -259,6 +279,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             } else {
                 double mx = max_kept(W, P, lane);
                 double lim = __dmul_rn(__dmul_rn(1.0, 0.05), mx);
+                #pragma unroll 1
                 for (uint32_t i = lane; i < P; i += 32)
                     if (W.keep[i] && W.in[W.ord[i]] < lim) W.keep[i] = 0;                                     // removeLowIntensityPeak
                 __syncwarp();
@@ -270,6 +291,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             if (!has_dup) {
                 // survivor id = position among the kept peaks; normalizePeaks(100)
                 uint32_t run = 0;
+                #pragma unroll 1
                 for (uint32_t c0 = 0; c0 < P; c0 += 32) {
                     uint32_t i = c0 + lane;
                     bool k = i < P && W.keep[i];
@@ -288,6 +310,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
                 // previous sort — by intensity when the top-50 cut ran, else file order.
                 if (lane == 0) {
                     uint32_t sid = 0; bool have = false; double last = 0.0, last_in = 0.0;
+                    #pragma unroll 1
                     for (uint32_t i = 0; i < P; ++i) {
                         W.aux[i] = (uint16_t)kNoSurvivor;
                         if (!W.keep[i]) continue;
@@ -299,12 +322,15 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
                     }
                     uint32_t ns = have ? sid + 1 : 0;
                     // a peak that was filtered out but shares its m/z with a survivor still hits the survivor map
+                    #pragma unroll 1
                     for (uint32_t i = 0; i < P; ++i) {
                         if (W.aux[i] != kNoSurvivor) continue;
                         double m = W.mz[W.ord[i]];
                         uint32_t found = kNoSurvivor;
+                        #pragma unroll 1
                         for (uint32_t j = i; j-- > 0 && W.mz[W.ord[j]] == m;) if (W.aux[j] != kNoSurvivor) { found = W.aux[j]; break; }
                         if (found == kNoSurvivor)
+                            #pragma unroll 1
                             for (uint32_t j = i + 1; j < P && W.mz[W.ord[j]] == m; ++j) if (W.aux[j] != kNoSurvivor) { found = W.aux[j]; break; }
                         W.aux[i] = (uint16_t)found;
                     }
@@ -316,15 +342,18 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             __syncwarp();
         } else {
             // ---- MVHMatch.SpectrumPreProcessing + classifyPeakIntensities (MVHMatch.java:46-89) ----
+            #pragma unroll 1
             for (uint32_t i = lane; i < P; i += 32) { double m = W.mz[W.ord[i]]; if (m < 200.0 || m > 2000.0) W.keep[i] = 0; }
             __syncwarp();
             if (count_kept(W.keep, P, lane) == 0) keep_all(W.keep, P, lane);
             const double tol_mz = __ddiv_rn(__dmul_rn(1.0, itol), (double)z);
+            #pragma unroll 1
             for (uint32_t i = lane; i < P; i += 32)
                 if (W.keep[i] && fabs(__dsub_rn(W.mz[W.ord[i]], prec_mz)) <= tol_mz) W.keep[i] = 0;
             __syncwarp();
             if (count_kept(W.keep, P, lane) == 0) keep_all(W.keep, P, lane);
             // filterByTIC (JMatch.java:341-364): aux[] = sorted position of each file index
+            #pragma unroll 1
             for (uint32_t i = lane; i < P; i += 32) W.aux[W.ord[i]] = (uint16_t)i;
             __syncwarp();
             if (count_kept(W.keep, P, lane) > 7) {
@@ -351,6 +380,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             const uint32_t npeak = N / 7;
             if (!has_dup) {
                 uint32_t run = 0, c0n = 0, c1n = 0, c2n = 0;
+                #pragma unroll 1
                 for (uint32_t c0 = 0; c0 < P; c0 += 32) {
                     uint32_t i = c0 + lane;
                     bool k = i < P && W.keep[i];
@@ -368,6 +398,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             } else if (lane == 0) {
                 int32_t cc[4] = {0, 0, 0, 0};
                 uint32_t sid = 0; bool have = false; double last = 0.0;
+                #pragma unroll 1
                 for (uint32_t i = 0; i < P; ++i) {
                     W.aux[i] = (uint16_t)kNoSurvivor;
                     if (!W.keep[i]) continue;
@@ -378,16 +409,20 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
                     if (have && m == last) { } else { if (have) ++sid; have = true; last = m; }
                     W.aux[i] = (uint16_t)((c << 12) | sid);
                 }
+                #pragma unroll 1
                 for (uint32_t i = 0; i < P; ++i) {
                     if (W.aux[i] != kNoSurvivor) continue;
                     double m = W.mz[W.ord[i]];
                     uint32_t found = kNoSurvivor;
+                    #pragma unroll 1
                     for (uint32_t j = i; j-- > 0 && W.mz[W.ord[j]] == m;) if (W.aux[j] != kNoSurvivor) { found = W.aux[j]; break; }
                     if (found == kNoSurvivor)
+                        #pragma unroll 1
                         for (uint32_t j = i + 1; j < P && W.mz[W.ord[j]] == m; ++j) if (W.aux[j] != kNoSurvivor) { found = W.aux[j]; break; }
                     W.aux[i] = (uint16_t)found;
                 }
                 cc[3] = cfg.mvh_bins - (int32_t)N;
+                #pragma unroll 1
                 for (int c = 0; c < 4; ++c) s_cls[warp][c] = cc[c];
             }
             __syncwarp();
@@ -397,6 +432,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
 
         // ---- matchable peaks (intensity >= limit) in m/z order: compact m/z -> da, intensity -> db, claim code -> cx ----
         uint32_t E = 0;
+        #pragma unroll 1
         for (uint32_t c0 = 0; c0 < P; c0 += 32) {
             uint32_t i = c0 + lane;
             bool el = i < P && W.in[W.ord[i]] >= limit;
@@ -414,6 +450,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         uint16_t* g_pcode = reinterpret_cast<uint16_t*>(blob + BL.pcode);
         double* g_val = reinterpret_cast<double*>(blob + BL.val);
         uint16_t* g_cells = reinterpret_cast<uint16_t*>(blob + BL.cells);
+        #pragma unroll 1
         for (uint32_t i = lane; i < P; i += 32) {
             uint32_t e = W.eidx[i];
             if (e == 0xFFFFu) continue;
@@ -428,18 +465,23 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         // ---- exact break points of the window predicate fabs(fl(mz - t)) <= itol: enter at lo, leave at rem = nextup(hi) ----
         // (the raw arrays are dead now: lo -> mz, rem -> in)
         double* lo_a = W.mz; double* rem_a = W.in;
+        #pragma unroll 1
         for (uint32_t e = lane; e < E; e += 32) {
             const double m = W.da[e];
             double g = __dsub_rn(m, itol);
             double lo;
             if (!(g > 0.0)) lo = 0.0;
             else {
+                #pragma unroll 1
                 while (!(__dsub_rn(m, g) <= itol)) g = next_up(g);
+                #pragma unroll 1
                 for (;;) { double q = next_down(g); if (q > 0.0 && __dsub_rn(m, q) <= itol) g = q; else break; }
                 lo = g;
             }
             double h = __dadd_rn(m, itol);
+            #pragma unroll 1
             while (!(__dsub_rn(h, m) <= itol)) h = next_down(h);
+            #pragma unroll 1
             for (;;) { double q = next_up(h); if (__dsub_rn(q, m) <= itol) h = q; else break; }
             lo_a[e] = lo; rem_a[e] = next_up(h);
         }
@@ -447,6 +489,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         // merged, sorted event list (a leave event goes before an enter event of the same value) and its answers.
         // lo[] and rem[] are the m/z list shifted by -+itol, so the counts below are a short walk from the peak itself.
         const uint32_t NE = 2u * E + 2u;
+        #pragma unroll 1
         for (uint32_t q = lane; q < 2u * E; q += 32) {
             const bool is_add = q < E;
             const uint32_t e = is_add ? q : q - E;
@@ -467,6 +510,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             uint32_t code = kAnsNone;
             if (a < bend) {
                 uint32_t best = a; double best_v = W.db[a]; bool tie = false;
+                #pragma unroll 1
                 for (uint32_t j = a + 1; j < bend; ++j) {
                     double r = W.db[j];
                     if (r > best_v) { best = j; best_v = r; tie = false; }
@@ -492,12 +536,14 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         __syncwarp();
         uint32_t* hist = reinterpret_cast<uint32_t*>(W.da);                          // kCells u16 counters, two per word
         uint32_t* none_bits = hist + kCells / 2;                                     // bit k: kept event k answers "nothing" (2E+2 bits)
+        #pragma unroll 1
         for (uint32_t k = lane; k < (uint32_t)kCells / 2 + (NE + 31u) / 32u; k += 32) hist[k] = 0u;
         __syncwarp();
         if (lane == 0) none_bits[0] = 1u;                                            // the -inf sentinel
         uint32_t kept = 1;                                                           // slot 0 = the -inf sentinel
         {
             uint32_t prev_code = kAnsNone;
+            #pragma unroll 1
             for (uint32_t c0 = 1; c0 < NE - 1; c0 += 32) {
                 const uint32_t p = c0 + lane;
                 const bool in = p < NE - 1;
@@ -523,6 +569,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         }
         const uint32_t NE2 = kept + 1;                                               // + the +inf sentinel
         if (lane == 0) { g_ev[kept] = inf; g_ans[kept] = (uint16_t)kAnsNone; }
+        #pragma unroll 1
         for (uint32_t k = NE2 + lane; k < ((NE2 + 7u) & ~7u); k += 32) g_ans[k] = (uint16_t)kAnsNone;
         // ---- cell table: cells[c] = number of real events below the lower edge of cell c (= index of the last of them).
         // An event lies below the lower edge of exactly the cells above its own, so cells[] is the exclusive prefix sum of
@@ -533,8 +580,10 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             static_assert(kCells % (32 * 8) == 0, "cell table must split into uint4 chunks per lane");
             const uint16_t* h16 = reinterpret_cast<const uint16_t*>(hist);
             uint32_t mine = 0;
+            #pragma unroll 1
             for (uint32_t k = 0; k < kPerLane; ++k) mine += h16[lane * kPerLane + k];
             uint32_t incl = mine;
+            #pragma unroll 1
             for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             uint32_t run = incl - mine;
             // kCellClean: no event inside the cell and nothing to claim at its lower edge, i.e. every t of the cell answers
@@ -546,8 +595,10 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
                 run += here;
                 return w;
             };
+            #pragma unroll 1
             for (uint32_t k8 = 0; k8 < kPerLane; k8 += 8) {
                 uint32_t w[4];
+                #pragma unroll 1
                 for (int h2 = 0; h2 < 4; ++h2) {
                     uint32_t c = lane * kPerLane + k8 + (uint32_t)h2 * 2u;
                     uint32_t v0 = cell_word(c);
@@ -562,6 +613,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         if (lane == 0) {
             BlobHeader h;
             h.n_peaks = E; h.n_events = NE2; h.n_survivors = nsurv; h.flags = flags;
+            #pragma unroll 1
             for (int c = 0; c < 4; ++c) h.cls_count[c] = METHOD == 2 ? s_cls[warp][c] : 0;
             h.total_bytes = BL.total; h.raw_peaks = P; h.pad[0] = h.pad[1] = 0;
             *reinterpret_cast<BlobHeader*>(blob) = h;
