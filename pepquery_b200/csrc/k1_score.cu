@@ -151,6 +151,92 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     }
 }
 
+// Short jobs (Step 2: one or two target forms per spectrum) leave a CTA-per-job kernel with one busy lane per warp.
+// Here every THREAD takes its own job and reads that spectrum's blob straight from global memory (L2): no staging, all
+// lanes busy, latency hidden by occupancy.  Same pair scorer, same results.
+template <int BLOCK, int METHOD>
+__global__ void __launch_bounds__(BLOCK)
+k1_scatter_kernel(ScoreLaunch L, ScoreConfig cfg) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t* codes_all = reinterpret_cast<uint32_t*>(smem);                                            // [16][BLOCK]
+    double2* s_tab = reinterpret_cast<double2*>(codes_all + 16 * BLOCK);
+    double* s_nt = reinterpret_cast<double*>(s_tab + kMaxCodes);
+    double* s_ct = s_nt + kMaxTermCodes;
+    double* s_l10 = s_ct + kMaxTermCodes;                                                              // [130]
+    uint32_t* usedw_all = reinterpret_cast<uint32_t*>(s_l10 + 130);                                     // MVH only: [10][BLOCK]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kMaxCodes; i += BLOCK) s_tab[i] = make_double2(L.mods->aa[i], L.mods->delta[i]);
+    for (int i = tid; i < kMaxTermCodes; i += BLOCK) { s_nt[i] = L.mods->nterm[i]; s_ct[i] = L.mods->cterm[i]; }
+    for (int i = tid; i < 130; i += BLOCK) s_l10[i] = L.log10_fact[i];
+    __syncthreads();
+    const double itol = cfg.itol;
+    uint32_t* codes = codes_all + tid;
+    uint32_t* usedw = usedw_all + tid;
+    for (uint32_t job = blockIdx.x * BLOCK + tid; job < L.n_jobs; job += gridDim.x * BLOCK) {
+        const Job J = L.jobs[job];
+        const BlobView B = view_blob(L.blobs + L.blob_off[J.blob]);
+        const long long va = jround(__dmul_rn(J.mass, 10.0));
+        uint32_t n_in = 0, n_better = 0;
+        double best = -1.0; uint32_t best_cand = 0xFFFFFFFFu;
+        for (uint32_t c = 0; c < J.cand_count; ++c) {
+            const uint32_t row = J.cand_begin + c;
+            if (cfg.check_window && !in_window(L.row_mass[row], J.mass, va, cfg)) continue;
+            const uint4* rp = reinterpret_cast<const uint4*>(L.rows + (size_t)row * kRowBytes);
+            uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+            codes[0 * BLOCK] = q0.x; codes[1 * BLOCK] = q0.y; codes[2 * BLOCK] = q0.z; codes[3 * BLOCK] = q0.w;
+            codes[4 * BLOCK] = q1.x; codes[5 * BLOCK] = q1.y; codes[6 * BLOCK] = q1.z; codes[7 * BLOCK] = q1.w;
+            codes[8 * BLOCK] = q2.x; codes[9 * BLOCK] = q2.y; codes[10 * BLOCK] = q2.z; codes[11 * BLOCK] = q2.w;
+            codes[12 * BLOCK] = q3.x; codes[13 * BLOCK] = q3.y; codes[14 * BLOCK] = q3.z; codes[15 * BLOCK] = q3.w;
+            Extra ex; ex.site = -1; ex.delta = 0.0;
+            int32_t pred = 0;
+            if (METHOD == 2) pred = L.row_pred[2 * (size_t)row + (J.charge == 2 ? 0 : 1)];
+            PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, pred, usedw, 0.0);
+            ++n_in;
+            if (ps.score > best) { best = ps.score; best_cand = row; }
+            bool emit = false;
+            switch (L.kind) {
+                case kJobTargets: emit = ps.score > cfg.min_score; break;                      // FindCandidate...java:78
+                case kJobCompetitors:
+                    if (J.ref_score <= ps.score) { ++n_better; emit = ps.score >= 20.0; }      // DBSearchWorker.java:68-76
+                    break;
+                case kJobShuffles: if (ps.score >= J.ref_score) ++n_better; break;             // StatisticScoreWorker.java:51
+                case kJobPairs:
+                    L.pair_score[J.out + c] = ps.score; L.pair_a[J.out + c] = ps.a; L.pair_b[J.out + c] = ps.b;
+                    break;
+                default: break;
+            }
+            if (emit) {
+                uint32_t slot = atomicAdd(L.hit_count, 1u);
+                if (slot < L.hit_capacity) {
+                    Hit h; h.spectrum = J.spectrum; h.cand = row; h.score = ps.score; h.mass = J.mass;
+                    h.count_a = ps.a; h.count_b = ps.b; h.iso = J.iso; h.aux = J.aux; h.blob = J.blob; h.pad = 0;
+                    L.hits[slot] = h;
+                }
+            }
+        }
+        JobResult R; R.n_in_window = n_in; R.n_better = n_better; R.best_score = best; R.best_cand = best_cand; R.pad = 0;
+        L.results[job] = R;
+    }
+}
+
+template <int METHOD>
+int launch_scatter(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
+    constexpr int BLOCK = 128;
+    const size_t smem = (size_t)16 * BLOCK * 4 + (size_t)(2 * kMaxCodes + 2 * kMaxTermCodes + 130) * 8 + (METHOD == 2 ? (size_t)10 * BLOCK * 4 : 0);
+    auto kernel = k1_scatter_kernel<BLOCK, METHOD>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0; cudaGetDevice(&dev);
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BLOCK, smem);
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = (uint32_t)(sms * per_sm);
+    uint32_t need = (L.n_jobs + BLOCK - 1) / BLOCK;
+    if (grid > need) grid = need;
+    kernel<<<grid, BLOCK, smem, st>>>(L, cfg);
+    return 1;
+}
+
 template <int BLOCK, int METHOD>
 int launch_kernel(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
     const uint32_t stage = (L.max_blob_bytes + 127u) & ~127u;
@@ -186,6 +272,9 @@ int launch_score(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) 
     switch (L.kind) {
         case kJobShuffles: return launch_block<256>(L, cfg, st);
         case kJobCompetitors: return launch_block<64>(L, cfg, st);
+        case kJobTargets:
+            if (!getenv("PQ_STEP2_STAGED")) return cfg.method == 2 ? launch_scatter<2>(L, cfg, st) : launch_scatter<1>(L, cfg, st);
+            return launch_block<32>(L, cfg, st);
         default: return launch_block<32>(L, cfg, st);
     }
 }
