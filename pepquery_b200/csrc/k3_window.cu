@@ -94,7 +94,34 @@ __global__ void k_fix_job_blobs(Job* __restrict__ jobs, uint32_t n_jobs, const i
     jobs[i].blob = (uint32_t)prep_id[jobs[i].spectrum];
 }
 
+// Step-2 jobs leave k_enumerate_targets in atomic-slot order.  The scatter scorer gives every lane its own job, so a warp
+// runs as long as its slowest lane and serialises lanes that differ in fragment-charge count: order the jobs by
+// (precursor charge, first target row, row count) -> neighbouring lanes score peptides of the same length and charge.
+__global__ void k_job_keys(const Job* __restrict__ jobs, uint32_t n, uint64_t* __restrict__ key, uint32_t* __restrict__ idx) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Job& J = jobs[i];
+    uint64_t z = (uint64_t)min(max(J.charge, 0), 15);
+    key[i] = (z << 40) | ((uint64_t)J.cand_begin << 8) | (uint64_t)min(J.cand_count, 255u);
+    idx[i] = i;
+}
+__global__ void k_gather_jobs(const Job* __restrict__ in, const uint32_t* __restrict__ idx, uint32_t n, Job* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[idx[i]];
+}
+
 }  // namespace
+
+int launch_job_keys(const Job* jobs, uint32_t n, uint64_t* key, uint32_t* idx, cudaStream_t st) {
+    if (!n) return 0;
+    k_job_keys<<<(n + 255) / 256, 256, 0, st>>>(jobs, n, key, idx);
+    return 1;
+}
+int launch_gather_jobs(const Job* in, const uint32_t* idx, uint32_t n, Job* out, cudaStream_t st) {
+    if (!n) return 0;
+    k_gather_jobs<<<(n + 255) / 256, 256, 0, st>>>(in, idx, n, out);
+    return 1;
+}
 
 int launch_precursor_mass(int64_t n, const double* prec_mz, const int32_t* charge, double* mass, uint64_t* key, int32_t* idx, cudaStream_t st) {
     if (n <= 0) return 0;

@@ -88,7 +88,7 @@ struct pq_ctx {
     bool have_targets = false, have_reference = false;
     int step_done = 0;
     // work buffers
-    DevBuf jobs, results, hits, hit_count, njobs;
+    DevBuf jobs, jobs2, results, hits, hit_count, njobs;
     // device-resident PSM table (K7)
     DevBuf d_psm, d_seg_start, d_out_perm, d_scalars, d_counters, d_agg, hits3, d_export;
     DevBuf k_key_a, k_key_b, k_idx_a, k_idx_b, k_head;
@@ -629,6 +629,15 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
         pc.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (ctx->P.itol * 2.0));
         int k = launch_prepare(sp, ctx->prep_list.as<int32_t>(), h_nprep, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(), ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st);
         k += launch_fix_job_blobs(ctx->jobs.as<Job>(), h_njobs, ctx->prep_id.as<int32_t>(), st);
+        // order the jobs by (charge, first target row): lanes of a warp then score peptides of equal length and charge
+        CU(ctx->k_key_a.reserve((size_t)h_njobs * 8)); CU(ctx->k_key_b.reserve((size_t)h_njobs * 8));
+        CU(ctx->k_idx_a.reserve((size_t)h_njobs * 4)); CU(ctx->k_idx_b.reserve((size_t)h_njobs * 4));
+        CU(ctx->jobs2.reserve((size_t)h_njobs * sizeof(Job)));
+        k += launch_job_keys(ctx->jobs.as<Job>(), h_njobs, ctx->k_key_a.as<uint64_t>(), ctx->k_idx_a.as<uint32_t>(), st);
+        rc = sort_pairs(ctx, ctx->k_key_a.as<uint64_t>(), ctx->k_key_b.as<uint64_t>(), ctx->k_idx_a.as<uint32_t>(), ctx->k_idx_b.as<uint32_t>(), (int)h_njobs, 44);
+        if (rc) return rc;
+        k += launch_gather_jobs(ctx->jobs.as<Job>(), ctx->k_idx_b.as<uint32_t>(), h_njobs, ctx->jobs2.as<Job>(), st);
+        std::swap(ctx->jobs, ctx->jobs2);
         ctx->cnt.other_kernel_launches += (uint64_t)k + 3;
         ctx->n_prepared = (uint32_t)h_nprep; ctx->cnt.spectra_prepared = (uint64_t)h_nprep;
         ctx->max_blob = blob_bytes(ctx->max_peaks);

@@ -161,6 +161,8 @@ int launch_gather_peaks(int64_t n, const int32_t* order, const uint64_t* off_in,
                         const double* in_in, double* mz_out, double* in_out, cudaStream_t st);
 int launch_blob_sizes(const SpectraView& sp, const int32_t* list, int32_t n_list, uint64_t* sizes, cudaStream_t st);
 int launch_fix_job_blobs(Job* jobs, uint32_t n_jobs, const int32_t* prep_id, cudaStream_t st);
+int launch_job_keys(const Job* jobs, uint32_t n, uint64_t* key, uint32_t* idx, cudaStream_t st);
+int launch_gather_jobs(const Job* in, const uint32_t* idx, uint32_t n, Job* out, cudaStream_t st);
 // Step 5 (k5_ptm.cu): one job per validated spectrum; candidates are enumerated inside the kernel
 struct PtmLaunch {
     const Job* jobs; uint32_t n_jobs;                      // mass = precursor neutral mass, ref_score = target PSM score
