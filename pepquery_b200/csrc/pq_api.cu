@@ -503,9 +503,11 @@ int32_t finalize_targets(pq_ctx* ctx) {
     TargetOrder& O = ctx->order;
     if (!O.form_of_row.empty() && O.form_of_row.size() == T.forms.size() && T.rows.p) return PQ_OK;
     const size_t n = T.forms.size();
+    Marks mk("finalize_targets");
     std::vector<uint32_t> ord(n);
     std::iota(ord.begin(), ord.end(), 0u);
     std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return T.forms[a].mass < T.forms[b].mass; });
+    mk.mark("sort by mass");
     O.form_of_row = ord; O.row_of_form.assign(n, 0);
     for (size_t r = 0; r < n; ++r) O.row_of_form[ord[r]] = (uint32_t)r;
     PeptideTable S;     // temp sorted copy for upload
@@ -516,6 +518,7 @@ int32_t finalize_targets(pq_ctx* ctx) {
     std::swap(S.rows, T.rows); std::swap(S.mass, T.mass); std::swap(S.pred, T.pred);
     T.h_mass = S.h_mass;    // sorted masses (row order)
     if (rc) return rc;
+    mk.mark("encode + upload");
     // side arrays of the device pipeline (K7): row -> public form, form -> sequence, the form's modification list,
     // rank of "sequence|modification" among the forms (RankPSMCompare's last tie-break), the target letters
     const size_t nseq = T.seqs.size();
@@ -533,6 +536,7 @@ int32_t finalize_targets(pq_ctx* ctx) {
         uint32_t r = 0;
         for (size_t k = 0; k < n; ++k) { if (k && key[by[k]] != key[by[k - 1]]) ++r; strrank[by[k]] = r; }
     }
+    mk.mark("form aux + string ranks");
     std::vector<uint32_t> soff(nseq + 1, 0); std::vector<uint8_t> letters;
     for (size_t q = 0; q < nseq; ++q) { for (char c : T.seqs[q]) letters.push_back((uint8_t)(c - 'A')); soff[q + 1] = (uint32_t)letters.size(); }
     CU(ctx->t_form_of_row.reserve(std::max<size_t>(n * 4, 64))); CU(ctx->t_seq_of_form.reserve(std::max<size_t>(n * 4, 64)));
