@@ -529,12 +529,48 @@ int32_t finalize_targets(pq_ctx* ctx) {
         for (int i = 0; i < T.forms[f].n; ++i) fm[f].mod[i] = T.forms[f].mod[i];
     }
     {
-        std::vector<std::string> key(n);
-        for (size_t f = 0; f < n; ++f) key[f] = T.seqs[(size_t)T.forms[f].seq] + "|" + mod_string(ctx, T.forms[f]);
-        std::vector<uint32_t> by(n); std::iota(by.begin(), by.end(), 0u);
-        std::sort(by.begin(), by.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
-        uint32_t r = 0;
-        for (size_t k = 0; k < n; ++k) { if (k && key[by[k]] != key[by[k - 1]]) ++r; strrank[by[k]] = r; }
+        // rank of "sequence|modification string" (RankPSMCompare's last tie-break).  The forms of one sequence are contiguous
+        // (generation order), '|' sorts above every letter, and the "%d@%d[%.4f]" pieces repeat: sort the distinct
+        // sequences once under the "a proper prefix sorts after its extensions" rule, then each sequence's forms by their
+        // modification strings built from cached pieces.
+        std::vector<std::string> piece((size_t)(ctx->codes.n_var + ctx->codes.n_fixed) * 64);
+        auto piece_of = [&](int m, int site) -> const std::string& {
+            std::string& p = piece[(size_t)m * 64 + (size_t)site];
+            if (p.empty()) { char buf[96]; snprintf(buf, sizeof buf, "%d@%d[%.4f]", ctx->codes.mods[(size_t)m].id, site, ctx->codes.mods[(size_t)m].delta); p = buf; }
+            return p;
+        };
+        std::vector<std::string> mods(n);
+        for (size_t f = 0; f < n; ++f) {
+            const FormRec& fr = T.forms[f];
+            if (fr.n == 0) { mods[f] = "-"; continue; }
+            std::string& ms = mods[f];
+            for (int i = 0; i < fr.n; ++i) { if (i) ms += ';'; ms += piece_of(fr.mod[i], fr.site[i]); }
+        }
+        auto seq_less = [&](uint32_t a, uint32_t b) {        // "A|" vs "B|": the first difference decides; a proper prefix meets '|' > letter
+            const std::string& x = T.seqs[a]; const std::string& y = T.seqs[b];
+            const size_t m = std::min(x.size(), y.size());
+            int c = memcmp(x.data(), y.data(), m);
+            if (c) return c < 0;
+            return x.size() > y.size();
+        };
+        std::vector<uint32_t> sq(nseq); std::iota(sq.begin(), sq.end(), 0u);
+        std::sort(sq.begin(), sq.end(), seq_less);
+        // forms of each sequence (contiguous runs of T.forms)
+        std::vector<uint32_t> first(nseq + 1, 0);
+        for (size_t f = 0; f < n; ++f) first[(size_t)T.forms[f].seq + 1]++;
+        for (size_t q = 0; q < nseq; ++q) first[q + 1] += first[q];
+        uint32_t r = 0; bool any = false;
+        const std::string* prev_seq = nullptr; const std::string* prev_mod = nullptr;
+        std::vector<uint32_t> fo;
+        for (size_t k = 0; k < nseq; ++k) {
+            const uint32_t q = sq[k];
+            fo.assign(first[q + 1] - first[q], 0u); std::iota(fo.begin(), fo.end(), first[q]);
+            std::sort(fo.begin(), fo.end(), [&](uint32_t a, uint32_t b) { return mods[a] < mods[b]; });
+            for (uint32_t f : fo) {
+                if (any && !(*prev_seq == T.seqs[q] && *prev_mod == mods[f])) ++r;      // equal keys (a sequence given twice) share a rank
+                strrank[f] = r; any = true; prev_seq = &T.seqs[q]; prev_mod = &mods[f];
+            }
+        }
     }
     mk.mark("form aux + string ranks");
     std::vector<uint32_t> soff(nseq + 1, 0); std::vector<uint8_t> letters;

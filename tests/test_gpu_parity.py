@@ -184,6 +184,35 @@ def test_step5_with_mvh_scoring(data):
     assert (got["n_ptm"] >= 0).sum() > 20
 
 
+def test_rank_ties_fall_back_to_the_peptide_string():
+    """RankPSMCompare (pg/RankPSM.java:107-149): score, p-value and |tol| all equal -> "sequence|modification" string order.
+    Isobaric targets (permuted residues; the same sequence oxidised at different M) against spectra whose peaks match none
+    of their fragments score 0 with p = 1, so only the string tie-break orders them."""
+    seqs = ["ACDEFGHMK", "ACDEGFHMK", "CADEFGHMK", "AMDEFGHMK", "MADEFGHMK"]
+    res = "".join(seqs).encode()
+    off = np.cumsum([0] + [len(s) for s in seqs]).astype(np.uint32)
+    tgt = (off, np.frombuffer(res, dtype=np.uint8).copy())
+    prot = synth.proteins(20)
+    p = _abi.default_params(n_random=30, min_score=-1.0)
+    from oracle import pq_oracle
+    o0 = pq_oracle.Oracle(p); o0.set_targets(*tgt)
+    forms, nf = o0.target_forms()
+    masses = sorted({round(forms[i].mass, 6) for i in range(nf)})
+    spectra = []
+    for m in masses:                                         # peaks only above 1900 Th: no b/y ion of a 9-mer gets there
+        spectra.append(((m + 2 * 1.007276466812) / 2, 2, [(1900.0 + 3.1 * k, 50.0 + k) for k in range(14)]))
+    sp = _csr(spectra)
+    g = run_gpu(p, sp, tgt, prot)
+    o = run_oracle(p, sp, tgt, prot)
+    got, want = g.psms(), o.psms()
+    assert_psms_equal(got, want)
+    by_spec = {}
+    for r in got:
+        by_spec.setdefault(int(r["spectrum"]), []).append(r)
+    assert any(len(v) >= 3 and len({float(x["score"]) for x in v}) == 1 for v in by_spec.values())     # real ties were ranked
+    assert all(sorted(int(x["rank"]) for x in v) == list(range(1, len(v) + 1)) for v in by_spec.values())
+
+
 @pytest.mark.parametrize("enzyme", [2, 5, 6, 9, 11, 12, 16, 17])
 def test_enzymes(data, enzyme):
     """K6's digest with other cleavage rules of the reference's -e table (cut after / cut before / blocked by the next
