@@ -28,7 +28,7 @@ namespace {
 using namespace dev;
 
 template <int BLOCK, int METHOD>
-__global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? K1_MIN_BLOCKS : 1)
+__global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? K1_MIN_BLOCKS : (BLOCK == 64 ? 11 : 1))
 k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar[2];
