@@ -31,7 +31,7 @@ struct WarpMem {
     uint16_t* ord; uint16_t* ordI; uint16_t* aux; uint16_t* pr; uint16_t* eidx; uint16_t* cx;
     uint8_t* keep; uint8_t* k2;
 };
-__host__ __device__ inline size_t warp_smem_bytes(uint32_t cap) { return (size_t)cap * (8 * 4 + 2 * 6 + 2) + 64; }      // cap >= 256: the 30*cap bytes behind mz/in hold the cell histogram (2*kCells bytes) + one bit per event
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t cap) { return (size_t)cap * (8 * 4 + 2 * 6 + 2) + 64; }      // cap >= 128: the region is reused for the cell histogram (2*kCells bytes) + one bit per event once the events are written
 
 __device__ __forceinline__ bool idx_less(const double* key, uint32_t a, uint32_t b) {
     double ka = key[a], kb = key[b];
@@ -534,7 +534,8 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         // (Deciding "kept" while the events are created — comparing the window just below each event with the window at it —
         // avoids this read-back but measured slower: 17.2 vs 14.5 ms for K0.)
         __syncwarp();
-        uint32_t* hist = reinterpret_cast<uint32_t*>(W.da);                          // kCells u16 counters, two per word
+        // (every work array is dead once the events are in global memory: the histogram takes the warp's region from its start)
+        uint32_t* hist = reinterpret_cast<uint32_t*>(W.mz);                          // kCells u16 counters, two per word
         uint32_t* none_bits = hist + kCells / 2;                                     // bit k: kept event k answers "nothing" (2E+2 bits)
         #pragma unroll 1
         for (uint32_t k = lane; k < (uint32_t)kCells / 2 + (NE + 31u) / 32u; k += 32) hist[k] = 0u;
@@ -634,17 +635,24 @@ int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, c
         size_t per_warp = (warp_smem_bytes(cap) + 15) & ~(size_t)15;
         size_t smem = per_warp * (size_t)warps;
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int per_sm = (int)(220 * 1024 / (smem + 2048)); if (per_sm < 1) per_sm = 1; if (per_sm > 16) per_sm = 16;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * warps, smem);
+        if (per_sm < 1) per_sm = 1;
         int grid = sms * per_sm; int need = (n_list + warps - 1) / warps; if (grid > need) grid = need;
         kernel<<<grid, 32 * warps, smem, st>>>(sp, list, n_list, cfg, blobs, blob_off, blob_len, cap, p_lo, p_hi);
         ++launched;
     };
     // size class 1: up to 256 peaks (the common case), four spectra per CTA; size class 2: the rest, capacity = next power of two
+    // size classes by peak count: K0 is bound by shared-memory capacity (46 bytes per peak slot and warp), so spectra of up
+    // to 128 peaks run with half the footprint and twice the resident warps
     const bool mvh = cfg.method == 2;
-    const char* ew = getenv("PQ_K0_WARPS");
-    if (ew && atoi(ew) == 2) { if (mvh) run(k0_prepare_kernel<2, 2>, 2, 256, 0, 256); else run(k0_prepare_kernel<2, 1>, 2, 256, 0, 256); }
-    else if (ew && atoi(ew) == 8) { if (mvh) run(k0_prepare_kernel<8, 2>, 8, 256, 0, 256); else run(k0_prepare_kernel<8, 1>, 8, 256, 0, 256); }
-    else if (mvh) run(k0_prepare_kernel<4, 2>, 4, 256, 0, 256); else run(k0_prepare_kernel<4, 1>, 4, 256, 0, 256);
+    const bool split = getenv("PQ_K0_ONE_CLASS") == nullptr;
+    if (split) {
+        if (mvh) run(k0_prepare_kernel<4, 2>, 4, 128, 0, 128); else run(k0_prepare_kernel<4, 1>, 4, 128, 0, 128);
+        if (max_peaks > 128) { if (mvh) run(k0_prepare_kernel<4, 2>, 4, 256, 129, 256); else run(k0_prepare_kernel<4, 1>, 4, 256, 129, 256); }
+    } else {
+        if (mvh) run(k0_prepare_kernel<4, 2>, 4, 256, 0, 256); else run(k0_prepare_kernel<4, 1>, 4, 256, 0, 256);
+    }
     if (max_peaks > 256) {
         uint32_t cap = 512; while (cap < max_peaks) cap <<= 1;
         if (cap <= 1024) { if (mvh) run(k0_prepare_kernel<4, 2>, 4, cap, 257, 0xFFFFFFFFu); else run(k0_prepare_kernel<4, 1>, 4, cap, 257, 0xFFFFFFFFu); }
