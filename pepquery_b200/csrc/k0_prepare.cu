@@ -28,10 +28,10 @@ __device__ __forceinline__ double next_down(double x) { return __longlong_as_dou
 
 struct WarpMem {
     double* mz; double* in; double* da; double* db;            // raw m/z, raw intensity (file order), two work arrays
-    uint16_t* ord; uint16_t* ordI; uint16_t* aux; uint16_t* pr; uint16_t* eidx; uint16_t* cx;
+    uint16_t* ord; uint16_t* ordI; uint16_t* aux; uint16_t* eidx; uint16_t* cx;
     uint8_t* keep; uint8_t* k2;
 };
-__host__ __device__ inline size_t warp_smem_bytes(uint32_t cap) { return (size_t)cap * (8 * 4 + 2 * 6 + 2) + 64; }      // cap >= 128: the region is reused for the cell histogram (2*kCells bytes) + one bit per event once the events are written
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t cap) { return (size_t)cap * (8 * 4 + 2 * 5 + 2) + 64; }      // cap >= 128: the region is reused for the cell histogram (2*kCells bytes) + one bit per event once the events are written
 
 __device__ __forceinline__ bool idx_less(const double* key, uint32_t a, uint32_t b) {
     double ka = key[a], kb = key[b];
@@ -177,7 +177,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
     uint8_t* base_ptr = smem_raw + (size_t)warp * ((warp_smem_bytes(cap) + 15) & ~(size_t)15);
     WarpMem W;
     W.mz = reinterpret_cast<double*>(base_ptr); W.in = W.mz + cap; W.da = W.in + cap; W.db = W.da + cap;      // mz / in live to the end (lo / rem)
-    W.ord = reinterpret_cast<uint16_t*>(W.db + cap); W.ordI = W.ord + cap; W.aux = W.ordI + cap; W.pr = W.aux + cap; W.eidx = W.pr + cap; W.cx = W.eidx + cap;
+    W.ord = reinterpret_cast<uint16_t*>(W.db + cap); W.ordI = W.ord + cap; W.aux = W.ordI + cap; W.eidx = W.aux + cap; W.cx = W.eidx + cap;
     W.keep = reinterpret_cast<uint8_t*>(W.cx + cap); W.k2 = W.keep + cap;
     double* val = s_val[warp];
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
