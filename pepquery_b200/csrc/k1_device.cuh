@@ -147,7 +147,7 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
     // possible matches (nor the survivor count together) and a normalised intensity cannot exceed 100, so
     // 4 (log10(100 n) + log10 nb! + log10 ny!) bounds the score from above.  A pair whose bound stays below the cutoff is
     // reported as 0 without resolving a single match (it could never count).
-    constexpr int kQueue = 24;
+    constexpr int kQueue = 32;
     double q[kQueue]; int qn = 0;
     bool in_b = true; int nb_q = 0;
     bool holding = METHOD == 1 && cutoff > 0.0;
@@ -158,7 +158,6 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
     };
     auto push = [&](double t) { if (ion_may_match(B, t)) q[qn++] = t; };
     auto ion = [&](double m, int k) {
-        if (qn > kQueue - 4) { flush(); holding = false; }
         push(__dadd_rn(m, kProton));
         if (nch >= 2 && k >= 2) push(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5));
         if (nch >= 3 && k >= 3) push(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0));
@@ -179,6 +178,7 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
     double acc = ntd[(head >> 8) & 0xFF];
     if (ex.site == 0) acc = __dadd_rn(acc, ex.delta);
     for (int i0 = 0; i0 < L - 1; i0 += 4) {
+        if (qn > kQueue - 16) { flush(); holding = false; }        // room for the next four ions (up to four charges each)
         uint32_t word = codes[(1 + (i0 >> 2)) * BLOCK];
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
@@ -197,6 +197,7 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
     acc = ctd[(head >> 16) & 0xFF];
     if (ex.site == L + 1) acc = __dadd_rn(acc, ex.delta);
     for (int i = L - 1; i >= 1;) {
+        if (qn > kQueue - 16) { flush(); holding = false; }
         uint32_t word = codes[(1 + (i >> 2)) * BLOCK] << (8 * (3 - (i & 3)));        // residue i in the top byte
 #pragma unroll 1
         for (int j = i & 3; j >= 0 && i >= 1; --j, --i) {
