@@ -1,51 +1,174 @@
-// pq_mgf.cu — single-pass MGF text parser into CSR buffers.  Replaces compomics MgfFileIterator as
-// used by SpectraInput.readMSMSfast (pg/SpectraInput.java:150-195); the writer-side format is index/IndexWorker.java:431-457
+// pq_mgf.cu — MGF text parser into CSR buffers.  Replaces compomics MgfFileIterator as used by
+// SpectraInput.readMSMSfast (pg/SpectraInput.java:150-195); the writer-side format is index/IndexWorker.java:431-457
 // (BEGIN IONS / TITLE / PEPMASS / CHARGE / "mz intensity" lines / END IONS).  Host code, no device work.
+//
+// Once scoring runs on the GPU the text parse is the upstream bottleneck (1 M spectra ~ 3 GB of text), so the parser is
+// parallel: the text is cut at "BEGIN IONS" lines into one chunk per host thread, every chunk is parsed independently
+// (count pass when the caller asks for sizes, fill pass into the caller's arrays at prefix-summed offsets), and decimal
+// numbers take Clinger's exact fast path — up to 19 digits collected in an integer, one correctly rounded multiply or
+// divide by an exactly representable power of ten when the integer is below 2^53 and |exponent| <= 22 — which returns the
+// same double as strtod / Java's Double.parseDouble; anything else falls back to strtod.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #include "pq_common.h"
+
+namespace {
+
+const double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                           1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+
+// Parses one decimal number at p (p < end).  *next = first character after it; *next == p when nothing was parsed.
+inline double parse_double(const char* p, const char* end, const char** next) {
+    const char* s = p;
+    while (s < end && (*s == ' ' || *s == '\t')) ++s;              // strtod skips leading blanks
+    bool neg = false;
+    if (s < end && (*s == '+' || *s == '-')) { neg = *s == '-'; ++s; }
+    if (s < end && ((*s | 0x20) == 'i' || (*s | 0x20) == 'n')) {   // "inf" / "nan": strtod's business
+        char buf[64]; size_t k = 0; while (k < 63 && p + k < end && p[k] != '\n' && p[k] != '\r') { buf[k] = p[k]; ++k; }
+        buf[k] = 0;
+        char* e = nullptr; double v = strtod(buf, &e);
+        *next = p + (e - buf);
+        return v;
+    }
+    uint64_t m = 0; int digits = 0, dropped = 0, frac = 0; bool any = false;
+    while (s < end && *s >= '0' && *s <= '9') { any = true; if (digits < 19) { m = m * 10 + (uint64_t)(*s - '0'); if (m) ++digits; } else ++dropped; ++s; }
+    if (s < end && *s == '.') {
+        ++s;
+        while (s < end && *s >= '0' && *s <= '9') { any = true; if (digits < 19) { m = m * 10 + (uint64_t)(*s - '0'); if (m) ++digits; ++frac; } ++s; }
+    }
+    if (!any) { *next = p; return 0.0; }
+    int e10 = dropped - frac;
+    bool simple = true;
+    if (s < end && (*s == 'e' || *s == 'E')) {
+        const char* t = s + 1; bool eneg = false;
+        if (t < end && (*t == '+' || *t == '-')) { eneg = *t == '-'; ++t; }
+        if (t < end && *t >= '0' && *t <= '9') {
+            int ev = 0;
+            while (t < end && *t >= '0' && *t <= '9') { if (ev < 100000) ev = ev * 10 + (*t - '0'); ++t; }
+            e10 += eneg ? -ev : ev; s = t;
+        }
+    }
+    // hex floats ("0x..."), "inf"/"nan", more than 19 significant digits, big exponents: let strtod decide
+    if (s < end && (*s == 'x' || *s == 'X' || *s == 'p' || *s == 'P')) simple = false;
+    if (dropped || m >= (1ull << 53) || e10 < -22 || e10 > 22) simple = false;
+    if (!simple) {
+        char buf[400]; size_t n = (size_t)std::min<ptrdiff_t>(end - p, 399);
+        size_t k = 0; while (k < n && p[k] != '\n' && p[k] != '\r') ++k;          // never read past the line
+        memcpy(buf, p, k); buf[k] = 0;
+        char* e = nullptr; double v = strtod(buf, &e);
+        *next = p + (e - buf);
+        return v;
+    }
+    double v = (double)m;
+    v = e10 < 0 ? v / kPow10[-e10] : v * kPow10[e10];
+    *next = s;
+    return neg ? -v : v;
+}
+
+struct Out { double* prec; int32_t* charge; uint64_t* off; double* mz; double* inten; };
+
+// The sequential state machine over [p, end): a chunk always starts at a BEGIN IONS line (or at the start of the text).
+// fill == nullptr: count only.  s0 / p0: index of the chunk's first spectrum / peak in the caller's arrays.
+void parse_chunk(const char* p, const char* end, const Out* fill, int64_t s0, uint64_t p0, int64_t* n_spec, uint64_t* n_peak) {
+    int64_t ns = 0; uint64_t np = 0;
+    bool in_ions = false; double pmz = 0.0; int32_t z = 0;
+    while (p < end) {
+        const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+        if (!eol) eol = end;
+        const char* q = p;
+        while (q < eol && (*q == ' ' || *q == '\t' || *q == '\r')) ++q;
+        const size_t len = (size_t)(eol - q);
+        if (len > 0) {
+            const char c = *q;
+            if (in_ions && ((c >= '0' && c <= '9') || c == '.')) {
+                if (!fill) { if (c != '.' || (len > 1 && q[1] >= '0' && q[1] <= '9')) ++np; }      // what the fill pass will accept
+                else {
+                    const char* e1; const double a = parse_double(q, eol, &e1);
+                    if (e1 != q) {
+                        const char* t = e1; while (t < eol && (*t == ' ' || *t == '\t')) ++t;
+                        const char* e2 = t; double b = 0.0;
+                        if (t < eol) b = parse_double(t, eol, &e2);
+                        fill->mz[p0 + np] = a; fill->inten[p0 + np] = (e2 != t) ? b : 0.0;
+                        ++np;
+                    }
+                }
+            } else if (c == 'B' && len >= 10 && !memcmp(q, "BEGIN IONS", 10)) {
+                in_ions = true; pmz = 0.0; z = 0;
+                if (fill) fill->off[s0 + ns] = p0 + np;
+            } else if (c == 'E' && len >= 8 && !memcmp(q, "END IONS", 8)) {
+                if (in_ions) {
+                    if (fill) { fill->prec[s0 + ns] = pmz; fill->charge[s0 + ns] = z; }
+                    ++ns; in_ions = false;
+                }
+            } else if (in_ions && c == 'P' && len >= 8 && !memcmp(q, "PEPMASS=", 8)) {
+                const char* e; pmz = parse_double(q + 8, eol, &e);                                   // first token = m/z (A11)
+            } else if (in_ions && c == 'C' && len >= 7 && !memcmp(q, "CHARGE=", 7)) {
+                z = (int32_t)strtol(q + 7, nullptr, 10);                                            // "2+" -> 2
+                if (z < 0) z = -z;
+            }
+        }
+        p = eol + 1;
+    }
+    *n_spec = ns; *n_peak = np;
+}
+
+// first line at or after `from` whose first non-blank text is BEGIN IONS; `end` if none
+const char* next_begin(const char* text, const char* from, const char* end) {
+    const char* p = from;
+    if (p > text) { const char* nl = (const char*)memchr(p - 1, '\n', (size_t)(end - (p - 1))); if (!nl) return end; p = nl + 1; }
+    while (p < end) {
+        const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+        if (!eol) eol = end;
+        const char* q = p;
+        while (q < eol && (*q == ' ' || *q == '\t' || *q == '\r')) ++q;
+        if ((size_t)(eol - q) >= 10 && !memcmp(q, "BEGIN IONS", 10)) return p;
+        p = eol + 1;
+    }
+    return end;
+}
+
+}  // namespace
 
 extern "C" int32_t pq_parse_mgf(const char* text, uint64_t n_bytes, int64_t* n_spectra, uint64_t* n_peaks, double* precursor_mz,
                                 int32_t* charge, uint64_t* peak_offset, double* mz, double* intensity) {
     if (!text || !n_spectra || !n_peaks) return PQ_ERR_BAD_ARG;
     const bool fill = precursor_mz && charge && peak_offset && mz && intensity;
     const int64_t cap_s = *n_spectra; const uint64_t cap_p = *n_peaks;
-    int64_t ns = 0; uint64_t np = 0;
-    bool in_ions = false; double pmz = 0.0; int32_t z = 0;
-    const char* p = text; const char* end = text + n_bytes;
-    while (p < end) {
-        const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
-        if (!eol) eol = end;
-        const char* q = p;
-        while (q < eol && (*q == ' ' || *q == '\t' || *q == '\r')) ++q;
-        size_t len = (size_t)(eol - q);
-        if (len >= 10 && !memcmp(q, "BEGIN IONS", 10)) {
-            in_ions = true; pmz = 0.0; z = 0;
-            if (fill) { if (ns >= cap_s) return PQ_ERR_CAPACITY; peak_offset[ns] = np; }
-        } else if (len >= 8 && !memcmp(q, "END IONS", 8)) {
-            if (in_ions) {
-                if (fill) { precursor_mz[ns] = pmz; charge[ns] = z; }
-                ++ns; in_ions = false;
-            }
-        } else if (in_ions && len > 0) {
-            if ((*q >= '0' && *q <= '9') || *q == '.') {
-                char* e1 = nullptr; double a = strtod(q, &e1);
-                char* e2 = nullptr; double b = (e1 && e1 < eol) ? strtod(e1, &e2) : 0.0;
-                if (e1 != q) {
-                    if (fill) { if (np >= cap_p) return PQ_ERR_CAPACITY; mz[np] = a; intensity[np] = (e2 && e2 != e1) ? b : 0.0; }
-                    ++np;
-                }
-            } else if (len >= 8 && !memcmp(q, "PEPMASS=", 8)) {
-                pmz = strtod(q + 8, nullptr);                       // first token = m/z (A11)
-            } else if (len >= 7 && !memcmp(q, "CHARGE=", 7)) {
-                z = (int32_t)strtol(q + 7, nullptr, 10);            // "2+" -> 2
-                if (z < 0) z = -z;
-            }
-        }
-        p = eol + 1;
+    const char* end = text + n_bytes;
+    int threads = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("PQ_MGF_THREADS")) threads = atoi(e);
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    if (n_bytes < (1u << 20)) threads = 1;
+    // chunk boundaries at BEGIN IONS lines
+    std::vector<const char*> cut; cut.push_back(text);
+    for (int t = 1; t < threads; ++t) {
+        const char* b = next_begin(text, text + n_bytes * (uint64_t)t / (uint64_t)threads, end);
+        if (b > cut.back() && b < end) cut.push_back(b);
     }
-    if (fill) peak_offset[ns] = np;
+    cut.push_back(end);
+    const int nc = (int)cut.size() - 1;
+    std::vector<int64_t> cs((size_t)nc, 0); std::vector<uint64_t> cp((size_t)nc, 0);
+    auto run = [&](const Out* out, const std::vector<int64_t>& s0, const std::vector<uint64_t>& p0) {
+        std::vector<std::thread> th;
+        for (int c = 1; c < nc; ++c) th.emplace_back([&, c]() { parse_chunk(cut[(size_t)c], cut[(size_t)c + 1], out, s0[(size_t)c], p0[(size_t)c], &cs[(size_t)c], &cp[(size_t)c]); });
+        parse_chunk(cut[0], cut[1], out, s0[0], p0[0], &cs[0], &cp[0]);
+        for (auto& t : th) t.join();
+    };
+    std::vector<int64_t> s0((size_t)nc + 1, 0); std::vector<uint64_t> p0((size_t)nc + 1, 0);
+    run(nullptr, s0, p0);                                  // count pass (cheap: no number parsing)
+    for (int c = 0; c < nc; ++c) { s0[(size_t)c + 1] = s0[(size_t)c] + cs[(size_t)c]; p0[(size_t)c + 1] = p0[(size_t)c] + cp[(size_t)c]; }
+    const int64_t ns = s0[(size_t)nc]; const uint64_t np = p0[(size_t)nc];
+    if (fill) {
+        if (ns > cap_s || np > cap_p) return PQ_ERR_CAPACITY;
+        Out out{precursor_mz, charge, peak_offset, mz, intensity};
+        run(&out, s0, p0);
+        peak_offset[ns] = np;
+    }
     *n_spectra = ns; *n_peaks = np;
     return PQ_OK;
 }

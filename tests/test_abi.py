@@ -133,3 +133,55 @@ def test_parse_mgf(lib):
     rc = lib.pq_parse_mgf(raw, C.c_uint64(len(raw)), C.byref(ns), C.byref(npk), z.ctypes.data_as(C.c_void_p), zi.ctypes.data_as(C.c_void_p),
                           zo.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p))
     assert rc == _abi.PQ_ERR_CAPACITY
+
+
+def test_parse_mgf_numbers_equal_python_float(lib):
+    """Every accepted number text must become the correctly rounded double (strtod / Double.parseDouble): the fast path
+    (integer mantissa times an exact power of ten) and the strtod fallback, against Python's float()."""
+    import random
+    from pepquery_b200 import parse_mgf
+    rng = random.Random(5)
+    toks = ["0", "0.0", "5.", ".5", "123.4567", "1234567.89", "0.000001", "1e5", "1E-5", "2.5e+3", "9007199254740993", "9007199254740992",
+            "123456789012345678901234567890", "0.1234567890123456789012345", "1e22", "1e23", "1e-22", "1e-23", "4.35", "1.7976931348623157e308",
+            "4.9e-324", "100.", "00012.5000", "1234.5678e-2", "3.14159265358979323846"]
+    for _ in range(400):
+        k = rng.randint(1, 17)
+        digits = "".join(rng.choice("0123456789") for _ in range(k))
+        cut = rng.randint(0, k)
+        t = (digits[:cut] or "0") + "." + digits[cut:]
+        if rng.random() < 0.3:
+            t += "e%+d" % rng.randint(-30, 30)
+        toks.append(t)
+    text = "BEGIN IONS\nPEPMASS=%s\nCHARGE=2+\n" % toks[4] + "".join("%s %s\n" % (a, b) for a, b in zip(toks, reversed(toks))) + "END IONS\n"
+    sp = parse_mgf(text)
+    assert len(sp["mz"]) == len(toks)
+    want_a = np.array([float(t) for t in toks]); want_b = want_a[::-1]
+    assert np.array_equal(sp["mz"], want_a) and np.array_equal(sp["inten"], want_b)
+    assert sp["prec_mz"][0] == float(toks[4])
+
+
+def test_parse_mgf_threads_agree(lib, monkeypatch):
+    """The parallel parse (chunks cut at BEGIN IONS lines) must equal the one-thread parse, also with blank-prefixed and
+    CRLF lines, comment / header lines between spectra, a spectrum without peaks and intensity-less peak lines."""
+    import random
+    from pepquery_b200 import parse_mgf
+    rng = random.Random(9)
+    parts = ["# produced by a test\nCOM=x\n"]
+    for i in range(30000):
+        eol = "\r\n" if i % 7 == 0 else "\n"
+        ind = "  " if i % 5 == 0 else ""
+        n = 0 if i % 97 == 0 else rng.randint(1, 40)
+        parts.append("%sBEGIN IONS%sTITLE=s%d%sPEPMASS=%.5f 1234.5%sCHARGE=%d+%s" % (ind, eol, i, eol, 300 + rng.random() * 900, eol, rng.randint(1, 4), eol))
+        for k in range(n):
+            parts.append("%s%.4f%s%s" % (ind, 100 + rng.random() * 1800, "" if k % 11 == 0 else " %.2f" % (rng.random() * 1e5), eol))
+        parts.append("END IONS%s%s" % (eol, "\n" if i % 3 == 0 else ""))
+    text = "".join(parts)
+    assert len(text) > (1 << 20)
+    monkeypatch.setenv("PQ_MGF_THREADS", "1")
+    one = parse_mgf(text)
+    for th in ("2", "7", "16"):
+        monkeypatch.setenv("PQ_MGF_THREADS", th)
+        many = parse_mgf(text)
+        for k in one:
+            assert np.array_equal(one[k], many[k]), (th, k)
+    assert len(one["prec_mz"]) == 30000 and int(one["peak_off"][-1]) == len(one["mz"])
