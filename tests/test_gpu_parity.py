@@ -184,6 +184,32 @@ def test_step5_with_mvh_scoring(data):
     assert (got["n_ptm"] >= 0).sum() > 20
 
 
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_random_configurations(seed):
+    """Seeded random mixes of the search parameters (fragment / precursor tolerances, scoring method, isotope errors, charges of
+    the synthetic spectra, shuffle count, score floor, missed cleavages, enzyme) on their own synthetic data: full parity."""
+    rng = np.random.default_rng(1000 + seed)
+    prot = synth.proteins(int(rng.integers(150, 400)), seed=int(rng.integers(1, 1 << 30)))
+    tgt = synth.targets(int(rng.integers(15, 40)), seed=int(rng.integers(1, 1 << 30)))
+    itol = float(rng.choice([0.01, 0.02, 0.05, 0.3, 0.6, 1.3]))
+    sp = synth.spectra(int(rng.integers(500, 1200)), tgt, prot, seed=int(rng.integers(1, 1 << 30)), itol=itol)
+    over = dict(itol=itol, score_method=int(rng.choice([1, 1, 2])), n_random=int(rng.choice([17, 64, 150])),
+                min_score=float(rng.choice([0.0, 5.0, 12.0])), max_missed=int(rng.choice([0, 1, 2])), enzyme=int(rng.choice([1, 1, 2, 7, 12])),
+                max_var_mods=int(rng.choice([1, 2, 3])), hc=int(rng.choice([0, 1])))
+    if rng.random() < 0.4:
+        over.update(tol=float(rng.choice([0.02, 0.1])), tol_ppm=0)
+    else:
+        over.update(tol=float(rng.choice([5.0, 10.0, 25.0])))
+    p = _abi.default_params(**over)
+    if rng.random() < 0.4:
+        iso = [(0, 1), (-1, 0, 1), (0, 1, 2)][int(rng.integers(0, 3))]
+        p.n_isotope = len(iso)
+        for i, v in enumerate(iso):
+            p.isotope[i] = v
+    g, o, got = full_compare(p, sp, tgt, prot)
+    assert len(got) > 0
+
+
 def test_rank_ties_fall_back_to_the_peptide_string():
     """RankPSMCompare (pg/RankPSM.java:107-149): score, p-value and |tol| all equal -> "sequence|modification" string order.
     Isobaric targets (permuted residues; the same sequence oxidised at different M) against spectra whose peaks match none
