@@ -172,6 +172,7 @@ typedef struct pq_counters {
     uint64_t bytes_score_step[4];       /* algorithmic bytes of those launches                                   */
     double   ms_host_reference;         /* wall time of the reference-table build (digest + forms + upload)      */
     uint64_t pairs_step4_bounded;       /* Step-4 pairs decided by the score upper bound (subset of pairs_step4)   */
+    uint64_t pairs_step5_bounded;       /* Step-5 pairs decided by the score upper bound (subset of pairs_step5)   */
 } pq_counters;
 
 typedef struct pq_ctx pq_ctx;

@@ -36,7 +36,7 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_scan[kPtmBlock / 32];
     __shared__ uint32_t s_total;
-    __shared__ uint32_t s_red_u[2][kPtmBlock / 32];
+    __shared__ uint32_t s_red_u[3][kPtmBlock / 32];
     __shared__ int s_stop;
     __shared__ uint32_t s_fill;
     __shared__ uint64_t s_cand[2 * kPtmBlock];          // compacted (row, PTM, site) candidates waiting to be scored
@@ -75,7 +75,7 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
         mbar_wait(&s_bar, it & 1u);
         __syncthreads();
         const BlobView B = view_blob(stage0);
-        uint32_t n_pairs = 0, n_better = 0;
+        uint32_t n_pairs = 0, n_better = 0, n_bound = 0;
 
         double mono = J.mass; int cur_iso = 0;
         // one thread per candidate: the reference form plus one PTM at one site, scored like any other pair
@@ -93,8 +93,11 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
                 Extra ex; ex.site = site; ex.delta = P.delta;
                 int32_t predicted = 0;
                 if (METHOD == 2) predicted = predict_peaks(L.rows + (size_t)row * kRowBytes, L.mods, itol, J.charge == 2 ? 1 : 2, ex);   // MVHMatch.java:165-172
-                PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, predicted, usedw);
+                // only candidates that reach the target's score matter (rows of ptm.txt, n_ptm): the score bound decides most others
+                PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, predicted, usedw,
+                                                         cfg.score_all ? 0.0 : J.ref_score);
                 ++n_pairs;
+                if (ps.a < 0) { ++n_bound; return; }                                           // decided by the bound: below the target
                 bool better = cfg.hc ? ps.score >= J.ref_score : ps.score > J.ref_score;      // :239-259, PSMT:920-943
                 if (better) { ++n_better; if (cfg.fast) s_stop = 1; }
                 if (ps.score >= cfg.min_score && ps.score >= J.ref_score) {                    // rows of ptm.txt (ModificationDB.java:1660-1663)
@@ -223,13 +226,13 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
             if (tid == 0) s_fill = 0;
             __syncthreads();
         }
-        for (int o = 16; o > 0; o >>= 1) { n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, o); n_better += __shfl_xor_sync(0xffffffffu, n_better, o); }
-        if ((tid & 31) == 0) { s_red_u[0][tid >> 5] = n_pairs; s_red_u[1][tid >> 5] = n_better; }
+        for (int o = 16; o > 0; o >>= 1) { n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, o); n_better += __shfl_xor_sync(0xffffffffu, n_better, o); n_bound += __shfl_xor_sync(0xffffffffu, n_bound, o); }
+        if ((tid & 31) == 0) { s_red_u[0][tid >> 5] = n_pairs; s_red_u[1][tid >> 5] = n_better; s_red_u[2][tid >> 5] = n_bound; }
         __syncthreads();
         if (tid == 0) {
-            uint32_t a = 0, b = 0;
-            for (int w = 0; w < BLOCK / 32; ++w) { a += s_red_u[0][w]; b += s_red_u[1][w]; }
-            JobResult R; R.n_in_window = a; R.n_better = b; R.best_score = -1.0; R.best_cand = 0xFFFFFFFFu; R.pad = 0;
+            uint32_t a = 0, b = 0, nb = 0;
+            for (int w = 0; w < BLOCK / 32; ++w) { a += s_red_u[0][w]; b += s_red_u[1][w]; nb += s_red_u[2][w]; }
+            JobResult R; R.n_in_window = a; R.n_better = b; R.best_score = -1.0; R.best_cand = 0xFFFFFFFFu; R.pad = nb;
             L.results[job] = R;
         }
         __syncthreads();

@@ -1165,7 +1165,7 @@ int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms) {
     std::unordered_map<int32_t, size_t> at;
     for (size_t j = 0; j < hj.size(); ++j) {
         at[hj[j].spectrum] = j;
-        ctx->cnt.pairs_step5 += hr[j].n_in_window;
+        ctx->cnt.pairs_step5 += hr[j].n_in_window; ctx->cnt.pairs_step5_bounded += hr[j].pad;
         uint64_t ab = (uint64_t)hr[j].n_in_window * (16ull * ctx->h_npeaks[(size_t)hj[j].spectrum] + 96ull);
         ctx->cnt.score_algorithmic_bytes += ab; ctx->cnt.bytes_score_step[3] += ab;
     }
