@@ -580,33 +580,39 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             constexpr uint32_t kPerLane = (uint32_t)kCells / 32;                       // 80 consecutive cells per lane
             static_assert(kCells % (32 * 8) == 0, "cell table must split into uint4 chunks per lane");
             const uint16_t* h16 = reinterpret_cast<const uint16_t*>(hist);
+            const uint4* h128 = reinterpret_cast<const uint4*>(h16 + lane * kPerLane);      // this lane's 80 counters = 10 x 16 bytes
             uint32_t mine = 0;
-            #pragma unroll 1
-            for (uint32_t k = 0; k < kPerLane; ++k) mine += h16[lane * kPerLane + k];
+#pragma unroll
+            for (uint32_t k = 0; k < kPerLane / 8; ++k) {
+                const uint4 v = h128[k];
+                mine += (v.x & 0xFFFFu) + (v.x >> 16) + (v.y & 0xFFFFu) + (v.y >> 16) + (v.z & 0xFFFFu) + (v.z >> 16) + (v.w & 0xFFFFu) + (v.w >> 16);
+            }
             uint32_t incl = mine;
-            #pragma unroll 1
+#pragma unroll
             for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             uint32_t run = incl - mine;
             // kCellClean: no event inside the cell and nothing to claim at its lower edge, i.e. every t of the cell answers
-            // "nothing": K1 skips the event scan for such cells (most of the m/z axis)
-            auto cell_word = [&](uint32_t c) -> uint32_t {
-                const uint32_t here = h16[c];
+            // "nothing": K1 skips the event scan for such cells (most of the m/z axis).  Eight cells per 16-byte store; a group
+            // without events (the usual case) is one value repeated.
+            auto word_of = [&](uint32_t here) -> uint32_t {
                 const uint32_t none = (none_bits[run >> 5] >> (run & 31)) & 1u;
                 const uint32_t w = run | ((here == 0u && none) ? kCellClean : 0u);
                 run += here;
                 return w;
             };
-            #pragma unroll 1
-            for (uint32_t k8 = 0; k8 < kPerLane; k8 += 8) {
-                uint32_t w[4];
-                #pragma unroll 1
-                for (int h2 = 0; h2 < 4; ++h2) {
-                    uint32_t c = lane * kPerLane + k8 + (uint32_t)h2 * 2u;
-                    uint32_t v0 = cell_word(c);
-                    uint32_t v1 = cell_word(c + 1);
-                    w[h2] = (v0 & 0xFFFFu) | (v1 << 16);
+#pragma unroll 1
+            for (uint32_t k = 0; k < kPerLane / 8; ++k) {
+                const uint4 v = h128[k];
+                uint4 o;
+                if ((v.x | v.y | v.z | v.w) == 0u) {
+                    const uint32_t w = word_of(0u); const uint32_t ww = w | (w << 16);
+                    o = make_uint4(ww, ww, ww, ww);
+                } else {
+                    uint32_t a0 = word_of(v.x & 0xFFFFu), a1 = word_of(v.x >> 16), a2 = word_of(v.y & 0xFFFFu), a3 = word_of(v.y >> 16);
+                    uint32_t a4 = word_of(v.z & 0xFFFFu), a5 = word_of(v.z >> 16), a6 = word_of(v.w & 0xFFFFu), a7 = word_of(v.w >> 16);
+                    o = make_uint4(a0 | (a1 << 16), a2 | (a3 << 16), a4 | (a5 << 16), a6 | (a7 << 16));
                 }
-                *reinterpret_cast<uint4*>(g_cells + lane * kPerLane + k8) = make_uint4(w[0], w[1], w[2], w[3]);
+                reinterpret_cast<uint4*>(g_cells + lane * kPerLane)[k] = o;
             }
         }
         if (METHOD == 1) for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = k < nsurv ? val[k] : 0.0;
