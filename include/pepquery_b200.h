@@ -102,6 +102,12 @@ typedef struct pq_params {
                                    "shuffleScore >= targetScore" (pg/StatisticScoreWorker.java:51), so a shuffle whose
                                    score upper bound (from its count of possible matches) stays below the target's
                                    score is decided without resolving its matches; counts and p-values are identical */
+    int32_t prepare_at_load;    /* 1 (default): pq_load_spectra also runs the peptide-independent spectrum preparation
+                                   (HyperscoreMatch/MVHMatch.SpectrumPreProcessing + the annotator's window tables) for
+                                   every usable spectrum, chunk by chunk while the next chunk of peaks is still crossing
+                                   PCIe, so the upload hides it.  0: pq_step2_match_targets prepares only the spectra that
+                                   have a target in their precursor window (less HBM, nothing overlapped).  Same results */
+    int32_t reserved0;
 } pq_params;
 
 /* One peptide form (sequence + placed modifications) as the caller sees it. */

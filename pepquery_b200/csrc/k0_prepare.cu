@@ -633,7 +633,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
 }  // namespace
 
 int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, const PrepConfig& cfg, uint8_t* blobs,
-                   const uint64_t* blob_off, uint32_t* blob_len, uint32_t max_peaks, cudaStream_t st) {
+                   const uint64_t* blob_off, uint32_t* blob_len, uint32_t max_peaks, cudaStream_t st, uint32_t min_peaks) {
     if (n_list <= 0) return 0;
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int launched = 0;
@@ -654,10 +654,10 @@ int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, c
     const bool mvh = cfg.method == 2;
     const bool split = getenv("PQ_K0_ONE_CLASS") == nullptr;
     if (split) {
-        if (mvh) run(k0_prepare_kernel<4, 2>, 4, 128, 0, 128); else run(k0_prepare_kernel<4, 1>, 4, 128, 0, 128);
+        if (mvh) run(k0_prepare_kernel<4, 2>, 4, 128, min_peaks, 128); else run(k0_prepare_kernel<4, 1>, 4, 128, min_peaks, 128);
         if (max_peaks > 128) { if (mvh) run(k0_prepare_kernel<4, 2>, 4, 256, 129, 256); else run(k0_prepare_kernel<4, 1>, 4, 256, 129, 256); }
     } else {
-        if (mvh) run(k0_prepare_kernel<4, 2>, 4, 256, 0, 256); else run(k0_prepare_kernel<4, 1>, 4, 256, 0, 256);
+        if (mvh) run(k0_prepare_kernel<4, 2>, 4, 256, min_peaks, 256); else run(k0_prepare_kernel<4, 1>, 4, 256, min_peaks, 256);
     }
     if (max_peaks > 256) {
         uint32_t cap = 512; while (cap < max_peaks) cap <<= 1;

@@ -48,6 +48,23 @@ __global__ void k_gather_peaks(int64_t n, const int32_t* __restrict__ order, con
     for (uint64_t k = lane; k < cnt; k += 32) { mz_out[b + k] = mz_in[a + k]; in_out[b + k] = in_in[a + k]; }
 }
 
+// prepare-at-load path: peaks arrive in caller order chunk by chunk, so the copy is driven by the caller index
+// (inv[i] = mass-sorted position of caller spectrum i)
+__global__ void k_invert_order(int64_t n, const int32_t* __restrict__ order, int32_t* __restrict__ inv) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[order[i]] = (int32_t)i;
+}
+__global__ void k_gather_peaks_by_caller(int64_t first, int64_t count, const int32_t* __restrict__ inv, const uint64_t* __restrict__ off_in,
+                                         const uint64_t* __restrict__ off_out, const double* __restrict__ mz_in,
+                                         const double* __restrict__ in_in, double* __restrict__ mz_out, double* __restrict__ in_out) {
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (w >= count) return;
+    int64_t s = first + w;
+    uint64_t a = off_in[s], cnt = off_in[s + 1] - a, b = off_out[inv[s]];
+    for (uint64_t k = lane; k < cnt; k += 32) { mz_out[b + k] = mz_in[a + k]; in_out[b + k] = in_in[a + k]; }
+}
+
 __device__ __forceinline__ uint32_t lower_bound_d(const double* a, uint32_t n, double v) {
     uint32_t lo = 0, hi = n;
     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
@@ -139,6 +156,18 @@ int launch_gather_peaks(int64_t n, const int32_t* order, const uint64_t* off_in,
     if (n <= 0) return 0;
     int64_t threads = n * 32;
     k_gather_peaks<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n, order, off_in, off_out, mz_in, in_in, mz_out, in_out);
+    return 1;
+}
+int launch_invert_order(int64_t n, const int32_t* order, int32_t* inv, cudaStream_t st) {
+    if (n <= 0) return 0;
+    k_invert_order<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, order, inv);
+    return 1;
+}
+int launch_gather_peaks_by_caller(int64_t first, int64_t count, const int32_t* inv, const uint64_t* off_in, const uint64_t* off_out,
+                                  const double* mz_in, const double* in_in, double* mz_out, double* in_out, cudaStream_t st) {
+    if (count <= 0) return 0;
+    int64_t threads = count * 32;
+    k_gather_peaks_by_caller<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(first, count, inv, off_in, off_out, mz_in, in_in, mz_out, in_out);
     return 1;
 }
 int launch_enumerate_targets(const SpectraView& sp, const double* table_mass, uint32_t n_rows, const WindowConfig& cfg,

@@ -1,7 +1,6 @@
 // pq_api.cu — the C ABI of libpepquery_b200.so (include/pepquery_b200.h): context, device residency, step drivers.
 // No CPU fallback: every scoring entry point launches CUDA kernels or fails.
 #include <algorithm>
-#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -60,7 +59,8 @@ struct pq_ctx {
     pq_params P;
     Codes codes;
     std::string err;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;       // one per upload chunk of pq_load_spectra
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, uev0 = nullptr, uev1 = nullptr;
     void* stage_host = nullptr; cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     pq_counters cnt;
@@ -82,6 +82,8 @@ struct pq_ctx {
     // prepared spectra
     DevBuf blobs, blob_off, blob_len, prep_id, prep_list, need, scratch, scan_tmp;
     uint32_t n_prepared = 0; uint32_t max_blob = 0;
+    bool prepared_at_load = false;           // blobs hold every usable spectrum, blob id = caller index (prepare_at_load)
+    DevBuf s_inv;                            // caller index -> mass-sorted position
     // tables
     PeptideTable targets, reference;
     TargetOrder order;
@@ -303,7 +305,7 @@ void pq_default_params(pq_params* p) {
     p->tol = 10.0; p->tol_ppm = 1; p->score_method = 1; p->itol = 0.6; p->min_score = 12.0; p->min_peaks = 10;
     p->n_isotope = 1; p->isotope[0] = 0; p->max_var_mods = 3; p->max_mods_per_aa = 1; p->n_random = 1000;
     p->enzyme = 1; p->max_missed = 2; p->min_len = 7; p->max_len = 45; p->min_mass = 500.0; p->max_mass = 10000.0;
-    p->shuffle_seed = 12457; p->mod_seed = 2022;
+    p->shuffle_seed = 12457; p->mod_seed = 2022; p->prepare_at_load = 1;
     p->n_fixed = 1; p->fixed[0].id = 1; p->fixed[0].position = PQ_MOD_ANYWHERE; strcpy(p->fixed[0].residues, "C"); p->fixed[0].delta = 57.02146372057;
     p->n_var = 1; p->var[0].id = 2; p->var[0].position = PQ_MOD_ANYWHERE; strcpy(p->var[0].residues, "M"); p->var[0].delta = 15.99491461956;
     p->var[0].neutral_loss = 63.99828574784;
@@ -328,7 +330,8 @@ int32_t pq_create(const pq_params* params, pq_ctx** out) {
     memset(&ctx->cnt, 0, sizeof ctx->cnt);
     std::string err;
     if (!ctx->codes.init(*params, err)) { delete ctx; return fail(nullptr, PQ_ERR_UNSUPPORTED, err); }
-    if (cudaSetDevice(params->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaSetDevice(params->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx; return fail(nullptr, PQ_ERR_CUDA, "cannot initialise device");
     }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->uev0); cudaEventCreate(&ctx->uev1);
@@ -360,9 +363,11 @@ int32_t pq_destroy(pq_ctx* ctx) {
     for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
     if (ctx->uev0) cudaEventDestroy(ctx->uev0);
     if (ctx->uev1) cudaEventDestroy(ctx->uev1);
-    cudaStream_t st = ctx->st;
+    for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
+    cudaStream_t st = ctx->st, st_copy = ctx->st_copy;
     delete ctx;
     if (st) cudaStreamDestroy(st);
+    if (st_copy) cudaStreamDestroy(st_copy);
     return PQ_OK;
 }
 
@@ -427,13 +432,36 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
     CU(ctx->s_prec.reserve(n * 8)); CU(ctx->s_charge.reserve(n * 4)); CU(ctx->s_mass.reserve(n * 8)); CU(ctx->s_off.reserve((n + 1) * 8));
     CU(ctx->s_mz.reserve(std::max<uint64_t>(total, 1) * 8)); CU(ctx->s_in.reserve(std::max<uint64_t>(total, 1) * 8)); CU(ctx->s_caller.reserve(n * 4));
     CU(ctx->scratch.reserve((n + 1) * 8));
-    cudaStream_t st = ctx->st;
+    cudaStream_t st = ctx->st, sc = ctx->st_copy;
     CU(cudaMemcpyAsync(in_prec.p, prec_mz, n * 8, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(in_charge.p, charge, n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(in_off.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(in_mz.p, mz, total * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(in_in.p, inten, total * 8, cudaMemcpyHostToDevice, st));
+    // The peaks cross PCIe in chunks of whole spectra (caller order) on a second stream; the compute stream follows chunk by
+    // chunk: copy into the mass-sorted CSR and, with prepare_at_load, K0 for the chunk, while the next chunk is in flight.
+    std::vector<int64_t> cut; cut.push_back(0);
+    {
+        uint64_t chunk_peaks = 4u << 20;                             // 64 MB of m/z + intensity per chunk
+        if (const char* e = getenv("PQ_LOAD_CHUNK_PEAKS")) { long long v = atoll(e); if (v > 0) chunk_peaks = (uint64_t)v; }   // tests: many small chunks
+        uint64_t next = chunk_peaks;
+        for (int64_t i = 1; i < n; ++i) if (off[i] - off[0] >= next) { cut.push_back(i); next = off[i] - off[0] + chunk_peaks; }
+        cut.push_back(n);
+    }
+    const size_t n_chunks = cut.size() - 1;
+    while (ctx->chunk_ev.size() < n_chunks) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+    auto enqueue_copies = [&]() -> int32_t {
+        for (size_t c = 0; c < n_chunks; ++c) {
+            const uint64_t a = off[cut[c]], b = off[cut[c + 1]];
+            if (b > a) {
+                CU(cudaMemcpyAsync(in_mz.as<double>() + a, mz + a, (b - a) * 8, cudaMemcpyHostToDevice, sc));
+                CU(cudaMemcpyAsync(in_in.as<double>() + a, inten + a, (b - a) * 8, cudaMemcpyHostToDevice, sc));
+            }
+            CU(cudaEventRecord(ctx->chunk_ev[c], sc));
+        }
+        return PQ_OK;
+    };
     ctx->cnt.h2d_bytes += (uint64_t)n * 28 + 8 + total * 16;
+    ctx->prepared_at_load = false;
+
     {
         Timer t(ctx, &ctx->cnt.ms_prepare);
         int k = 0;
@@ -448,8 +476,46 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
         CU(cudaMemsetAsync(counts + n, 0, 8, st));
         int32_t rc = scan_exclusive(ctx, counts, ctx->s_off.as<uint64_t>(), (int)n + 1);
         if (rc) return rc;
-        k += launch_gather_peaks(n, ctx->s_caller.as<int32_t>(), in_off.as<uint64_t>(), ctx->s_off.as<uint64_t>(), in_mz.as<double>(), in_in.as<double>(),
-                                 ctx->s_mz.as<double>(), ctx->s_in.as<double>(), st);
+        // The peak copies are queued only now: queued ahead of the kernels above they held those kernels back until the last
+        // chunk had landed (measured: 60 ms per load instead of 36 ms), so the small precursor work goes first.
+        rc = enqueue_copies();
+        if (rc) return rc;
+        CU(ctx->s_inv.reserve(n * 4));
+        k += launch_invert_order(n, ctx->s_caller.as<int32_t>(), ctx->s_inv.as<int32_t>(), st);
+        SpectraView sp = ctx->view();
+        // prepare_at_load: blob i belongs to caller spectrum i (the list K0 walks is the inverse order), sizes from the peak counts
+        bool eager = ctx->P.prepare_at_load != 0 && getenv("PQ_PREPARE_AT_STEP2") == nullptr;
+        PrepConfig pc; pc.itol = ctx->P.itol; pc.method = ctx->P.score_method;
+        pc.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (ctx->P.itol * 2.0));
+        if (eager) {
+            CU(ctx->blob_off.reserve((size_t)(n + 2) * 8)); CU(ctx->blob_len.reserve((size_t)(n + 2) * 4));
+            CU(ctx->prep_list.reserve((size_t)(n + 2) * 8));
+            uint64_t* sizes = ctx->prep_list.as<uint64_t>();
+            k += launch_blob_sizes(sp, ctx->s_inv.as<int32_t>(), (int32_t)n, sizes, st);
+            rc = scan_exclusive(ctx, sizes, ctx->blob_off.as<uint64_t>(), (int)n + 1);
+            if (rc) return rc;
+            uint64_t total_blob = 0;
+            CU(cudaMemcpyAsync(&total_blob, ctx->blob_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (ctx->blobs.cap < total_blob + 256) {                // growing: only if it fits beside what is still to come
+                size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+                if ((double)(total_blob + 256 - ctx->blobs.cap) > 0.6 * (double)free_b) eager = false;
+            }
+            if (eager && ctx->blobs.reserve(total_blob + 256) != cudaSuccess) { cudaGetLastError(); eager = false; }
+        }
+        for (size_t c = 0; c < n_chunks; ++c) {
+            CU(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
+            const int64_t a = cut[c], cnt = cut[c + 1] - cut[c];
+            k += launch_gather_peaks_by_caller(a, cnt, ctx->s_inv.as<int32_t>(), in_off.as<uint64_t>(), ctx->s_off.as<uint64_t>(), in_mz.as<double>(),
+                                               in_in.as<double>(), ctx->s_mz.as<double>(), ctx->s_in.as<double>(), st);
+            if (eager)
+                k += launch_prepare(sp, ctx->s_inv.as<int32_t>() + a, (int32_t)cnt, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>() + a,
+                                    ctx->blob_len.as<uint32_t>() + a, ctx->max_peaks, st, (uint32_t)std::max(ctx->P.min_peaks + 1, 0));
+        }
+        if (eager) {
+            ctx->prepared_at_load = true; ctx->n_prepared = (uint32_t)n; ctx->cnt.spectra_prepared = usable;
+            ctx->max_blob = blob_bytes(ctx->max_peaks);
+        }
         ctx->cnt.other_kernel_launches += (uint64_t)k + 4;
     }
     CU(cudaGetLastError());
@@ -613,7 +679,8 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     if (rc) return rc;
     rc = ensure_counters(ctx);
     if (rc) return rc;
-    reset_psm_state(ctx); ctx->step_done = 0; ctx->n_prepared = 0;
+    reset_psm_state(ctx); ctx->step_done = 0;
+    if (!ctx->prepared_at_load) ctx->n_prepared = 0;
     if (n_psms) *n_psms = 0;
     const int64_t n = ctx->nS;
     PeptideTable& T = ctx->targets;
@@ -651,6 +718,11 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     // list of spectra to prepare (ascending sorted index) + blob offsets
     {
         Timer t(ctx, &ctx->cnt.ms_prepare);
+        int k = 0;
+        if (ctx->prepared_at_load) {
+            // every usable spectrum was prepared during the upload; blob id = caller index
+            k += launch_fix_job_blobs(ctx->jobs.as<Job>(), h_njobs, ctx->s_caller.as<int32_t>(), st);
+        } else {
         size_t tmp = 0;
         cub::CountingInputIterator<int32_t> iota(0);
         cub::DeviceSelect::Flagged(nullptr, tmp, iota, ctx->need.as<int32_t>(), ctx->prep_list.as<int32_t>(), ctx->njobs.as<uint32_t>() + 1, (int)n, st);
@@ -667,8 +739,11 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
         CU(ctx->blobs.reserve(total_blob + 256));
         PrepConfig pc; pc.itol = ctx->P.itol; pc.method = ctx->P.score_method;
         pc.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (ctx->P.itol * 2.0));
-        int k = launch_prepare(sp, ctx->prep_list.as<int32_t>(), h_nprep, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(), ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st);
+        k += launch_prepare(sp, ctx->prep_list.as<int32_t>(), h_nprep, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(), ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st);
         k += launch_fix_job_blobs(ctx->jobs.as<Job>(), h_njobs, ctx->prep_id.as<int32_t>(), st);
+        ctx->n_prepared = (uint32_t)h_nprep; ctx->cnt.spectra_prepared = (uint64_t)h_nprep;
+        ctx->max_blob = blob_bytes(ctx->max_peaks);
+        }
         // order the jobs by (charge, first target row): lanes of a warp then score peptides of equal length and charge
         CU(ctx->k_key_a.reserve((size_t)h_njobs * 8)); CU(ctx->k_key_b.reserve((size_t)h_njobs * 8));
         CU(ctx->k_idx_a.reserve((size_t)h_njobs * 4)); CU(ctx->k_idx_b.reserve((size_t)h_njobs * 4));
@@ -679,8 +754,6 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
         k += launch_gather_jobs(ctx->jobs.as<Job>(), ctx->k_idx_b.as<uint32_t>(), h_njobs, ctx->jobs2.as<Job>(), st);
         std::swap(ctx->jobs, ctx->jobs2);
         ctx->cnt.other_kernel_launches += (uint64_t)k + 3;
-        ctx->n_prepared = (uint32_t)h_nprep; ctx->cnt.spectra_prepared = (uint64_t)h_nprep;
-        ctx->max_blob = blob_bytes(ctx->max_peaks);
     }
     CU(cudaGetLastError());
     mk.mark("prepare launch");
@@ -1240,7 +1313,7 @@ int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_ind
     CU(cudaMemcpyAsync(d_list.p, list.data(), list.size() * 4, cudaMemcpyHostToDevice, st));
     SpectraView sp = ctx->view();
     // this call owns the prepared-spectrum pool: invalidate the step pipeline's blobs
-    ctx->step_done = std::min(ctx->step_done, 1); ctx->n_prepared = 0;
+    ctx->step_done = std::min(ctx->step_done, 1); ctx->n_prepared = 0; ctx->prepared_at_load = false;   // the blobs are re-used below
     CU(ctx->scratch.reserve((list.size() + 2) * 8)); CU(ctx->blob_off.reserve((list.size() + 2) * 8)); CU(ctx->blob_len.reserve((list.size() + 2) * 4));
     launch_blob_sizes(sp, d_list.as<int32_t>(), (int32_t)list.size(), ctx->scratch.as<uint64_t>(), st);
     int32_t rc = scan_exclusive(ctx, ctx->scratch.as<uint64_t>(), ctx->blob_off.as<uint64_t>(), (int)list.size() + 1);

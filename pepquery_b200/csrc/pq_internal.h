@@ -114,7 +114,7 @@ struct ScoreLaunch {
 
 // kernel launchers (each returns the number of kernels it launched; errors via cudaGetLastError by the caller)
 int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, const PrepConfig& cfg, uint8_t* blobs,
-                   const uint64_t* blob_off, uint32_t* blob_len, uint32_t max_peaks, cudaStream_t st);
+                   const uint64_t* blob_off, uint32_t* blob_len, uint32_t max_peaks, cudaStream_t st, uint32_t min_peaks = 0);
 int launch_score(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st);
 
 // Step-2 window enumeration on device: for every usable spectrum x isotope error, the run of target rows whose mass
@@ -159,6 +159,9 @@ int launch_gather_meta(int64_t n, const int32_t* order, const double* prec_mz_in
                        const uint64_t* off_in, double* prec_mz, int32_t* charge, double* mass, uint64_t* count, cudaStream_t st);
 int launch_gather_peaks(int64_t n, const int32_t* order, const uint64_t* off_in, const uint64_t* off_out, const double* mz_in,
                         const double* in_in, double* mz_out, double* in_out, cudaStream_t st);
+int launch_invert_order(int64_t n, const int32_t* order, int32_t* inv, cudaStream_t st);
+int launch_gather_peaks_by_caller(int64_t first, int64_t count, const int32_t* inv, const uint64_t* off_in, const uint64_t* off_out,
+                                  const double* mz_in, const double* in_in, double* mz_out, double* in_out, cudaStream_t st);
 int launch_blob_sizes(const SpectraView& sp, const int32_t* list, int32_t n_list, uint64_t* sizes, cudaStream_t st);
 int launch_fix_job_blobs(Job* jobs, uint32_t n_jobs, const int32_t* prep_id, cudaStream_t st);
 int launch_job_keys(const Job* jobs, uint32_t n, uint64_t* key, uint32_t* idx, cudaStream_t st);

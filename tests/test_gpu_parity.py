@@ -85,6 +85,21 @@ def test_default_search_hyperscore(data):
     assert np.array_equal(got["score"], o.psms()["score"])
 
 
+@pytest.mark.parametrize("method", [1, 2])
+def test_prepare_at_step2_and_chunked_upload(data, method, monkeypatch):
+    """prepare_at_load = 0 (K0 inside Step 2, only for matched spectra) and prepare_at_load = 1 with the upload cut into many
+    small chunks (K0 per chunk while the next one is copied) give the oracle's rows, bit for bit the same as each other."""
+    prot, tgt, sp = data
+    g0, o, got0 = full_compare(_abi.default_params(n_random=100, score_method=method, prepare_at_load=0), sp, tgt, prot)
+    monkeypatch.setenv("PQ_LOAD_CHUNK_PEAKS", "7000")
+    g1, _, got1 = full_compare(_abi.default_params(n_random=100, score_method=method, prepare_at_load=1), sp, tgt, prot)
+    assert got0.tobytes() == got1.tobytes()
+    assert g0.counters().spectra_prepared < g1.counters().spectra_prepared          # matched spectra only vs every usable spectrum
+    # a reload into the same context (second search) re-prepares
+    g1.load_spectra(sp); g1.set_targets(*tgt); g1.step2(); g1.build_reference(*prot); g1.step3(); g1.step4(); g1.rank()
+    assert g1.psms().tobytes() == got1.tobytes()
+
+
 def test_default_search_mvh(data):
     prot, tgt, sp = data
     g, o, got = full_compare(_abi.default_params(n_random=200, score_method=2), sp, tgt, prot)
