@@ -615,6 +615,13 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
                 reinterpret_cast<uint4*>(g_cells + lane * kPerLane)[k] = o;
             }
         }
+        // cell_filter() sends every m/z outside the table to the last cell: it may only stay clean if cell 0 (all events below
+        // 128 Th) is clean too
+        __syncwarp();
+        if (lane == 0) {
+            const uint16_t first = __ldcg(g_cells), last = __ldcg(g_cells + kCells - 1);
+            if (!(first & kCellClean) && (last & kCellClean)) g_cells[kCells - 1] = (uint16_t)(last & ~kCellClean);
+        }
         if (METHOD == 1) for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = k < nsurv ? val[k] : 0.0;
         else for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = 0.0;
         if (lane == 0) {

@@ -84,7 +84,7 @@ __device__ __forceinline__ uint32_t match_ion(const BlobView& B, double t, doubl
     return match_ion_tie<METHOD>(B.pmz, B.pin, B.pcode, a & 0xFFFu, t, itol);
 }
 // Most theoretical m/z fall into cells where nothing can be claimed (kCellClean): one table load answers them.
-__device__ __forceinline__ bool ion_may_match(const BlobView& B, double t) { return reinterpret_cast<const int16_t*>(B.cells)[cell_of(t)] >= 0; }   // kCellClean = sign bit
+__device__ __forceinline__ bool ion_may_match(const BlobView& B, double t) { return reinterpret_cast<const int16_t*>(B.cells)[cell_filter(t)] >= 0; }   // kCellClean = sign bit
 
 struct Extra { int32_t site; double delta; };   // Step 5: one extra modification (site -1 = none)
 
@@ -263,6 +263,85 @@ __device__ __forceinline__ PairScore score_pair(const uint32_t* codes, const Blo
         case 4: return score_pair_n<BLOCK, METHOD, 3>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
         default: return score_pair_n<BLOCK, METHOD, 0>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
     }
+}
+
+// Count pass of the score bound (Step 4, no extra modification): walks the same fragment ladder as score_pair_n — the same sums
+// in the same order, so the same theoretical m/z — but only counts the ions that land in a cell where something can be
+// claimed.  Returns possible b matches | possible y matches << 16.  No queue, no claims: this is all a shuffle costs when
+// its bound 4 (log10(100 n) + log10 nb! + log10 ny!) stays below the target's score.  Four residues per row word, unrolled
+// (every shuffle of a job has the same length, so the guards are uniform); clean cells are counted through the sign bit
+// and subtracted from the number of ion / charge combinations.
+template <int BLOCK, int NCH>
+__device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd,
+                                                     const double* ctd, int z) {
+    const uint32_t head = codes[0];
+    const int L = (int)(head & 0xFF);
+    const int nch = NCH > 0 ? NCH : (z <= 1 ? 1 : z - 1);
+    const int16_t* cells = reinterpret_cast<const int16_t*>(B.cells);
+    auto clean = [&](double t) -> int { return (int)cells[cell_filter(t)] >> 15; };           // -1: nothing can be claimed at t
+    auto ion = [&](double m, int k) -> int {
+        int c = clean(__dadd_rn(m, kProton));
+        if (nch >= 2 && k >= 2) c += clean(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5));
+        if (nch >= 3 && k >= 3) c += clean(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0));
+        if (NCH == 0) {
+            if (nch >= 4 && k >= 4) c += clean(__dmul_rn(__dadd_rn(m, 4.0 * kProton), 0.25));
+            for (int f = 5; f <= nch && f <= k; ++f) c += clean(__ddiv_rn(__dadd_rn(m, __dmul_rn((double)f, kProton)), (double)f));
+        }
+        return c;
+    };
+    // ion / charge combinations of one series: sum over k = 1..L-1 of min(nch, k)
+    const int full = max(L - 1 - nch, 0), ramp = min(nch, L - 1);
+    const int per_side = full * nch + ramp * (ramp + 1) / 2;
+    int cb = 0, cy = 0;                                     // minus the clean ones
+    const int Lm1 = L - 1;
+    double acc = ntd[(head >> 8) & 0xFF];
+#pragma unroll 1
+    for (int w = 0; 4 * w < Lm1; ++w) {
+        const uint32_t word = codes[(1 + w) * BLOCK];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = 4 * w + j + 1;
+            if (k <= Lm1) {
+                const double2 t = tab[(word >> (8 * j)) & 0xFFu];
+                acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+                cb += ion(acc, k);
+            }
+        }
+    }
+    acc = ctd[(head >> 16) & 0xFF];
+#pragma unroll 1
+    for (int w = Lm1 >> 2; w >= 0; --w) {
+        const uint32_t word = codes[(1 + w) * BLOCK];
+#pragma unroll
+        for (int j = 3; j >= 0; --j) {
+            const int i = 4 * w + j;
+            if (i <= Lm1 && i >= 1) {
+                const double2 t = tab[(word >> (8 * j)) & 0xFFu];
+                acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+                cy += ion(__dadd_rn(acc, kWater), L - i);
+            }
+        }
+    }
+    const uint32_t nb = (uint32_t)(per_side + cb), ny = (uint32_t)(per_side + cy);
+    return min(nb, 0xFFFFu) | (min(ny, 0xFFFFu) << 16);
+}
+
+// true: the hyperscore of this row cannot reach `cutoff` (see count_possible_n); false: score it
+template <int BLOCK>
+__device__ __forceinline__ bool below_score_bound(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd,
+                                                  const double* ctd, int z, const double* log10_fact, double cutoff) {
+    uint32_t c;
+    switch (z) {
+        case 0: case 1: case 2: c = count_possible_n<BLOCK, 1>(codes, B, tab, ntd, ctd, z); break;
+        case 3: c = count_possible_n<BLOCK, 2>(codes, B, tab, ntd, ctd, z); break;
+        case 4: c = count_possible_n<BLOCK, 3>(codes, B, tab, ntd, ctd, z); break;
+        default: c = count_possible_n<BLOCK, 0>(codes, B, tab, ntd, ctd, z); break;
+    }
+    const int nbq = (int)(c & 0xFFFFu), nyq = (int)(c >> 16);
+    const int nb = min(nbq, 64), ny = min(nyq, 64), n = min(min(nbq + nyq, (int)B.nsurv), 64);
+    double ub = 0.0;
+    if (n > 0) ub = 4.0 * (log10_fact[65 + n] + log10_fact[nb] + log10_fact[ny]);        // log10_fact[65 + n] = log10(100 n)
+    return ub * (1.0 + 1e-12) + 1e-9 < cutoff;
 }
 
 // Precursor-window predicate exactly as DBSearchWorker.java:38-52 / FindCandidate...java:47-58:

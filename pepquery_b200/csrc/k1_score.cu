@@ -18,7 +18,7 @@
 #include "k1_device.cuh"
 
 #ifndef K1_MIN_BLOCKS
-#define K1_MIN_BLOCKS 3
+#define K1_MIN_BLOCKS 4
 #endif
 
 namespace pq {
@@ -57,6 +57,9 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     // Jobs are handed out by an atomic counter (in list order, so neighbouring CTAs share table rows in L2); the next
     // job's blob is already in flight (second stage) while the current one is scored.
     __shared__ uint32_t s_job[2];
+    __shared__ uint32_t s_surv[2 * BLOCK];        // bounded Step 4: candidates the score bound could not decide
+    __shared__ uint32_t s_nsurv;
+    const bool bounded = METHOD == 1 && L.kind == kJobShuffles && !cfg.score_all && !cfg.check_window;
     auto fetch = [&](uint32_t slot) {           // thread 0: take the next job and start its TMA into `slot`
         uint32_t nj = atomicAdd(L.job_counter, 1u);
         s_job[slot] = nj;
@@ -81,27 +84,63 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
 
         uint32_t n_in = 0, n_better = 0, n_bound = 0;
         double best = -1.0; uint32_t best_cand = 0xFFFFFFFFu;
+        auto load_row = [&](uint32_t row) {
+            const uint4* rp = reinterpret_cast<const uint4*>(L.rows + (size_t)row * kRowBytes);
+            uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+            codes[0 * BLOCK] = q0.x; codes[1 * BLOCK] = q0.y; codes[2 * BLOCK] = q0.z; codes[3 * BLOCK] = q0.w;
+            codes[4 * BLOCK] = q1.x; codes[5 * BLOCK] = q1.y; codes[6 * BLOCK] = q1.z; codes[7 * BLOCK] = q1.w;
+            codes[8 * BLOCK] = q2.x; codes[9 * BLOCK] = q2.y; codes[10 * BLOCK] = q2.z; codes[11 * BLOCK] = q2.w;
+            codes[12 * BLOCK] = q3.x; codes[13 * BLOCK] = q3.y; codes[14 * BLOCK] = q3.z; codes[15 * BLOCK] = q3.w;
+        };
+        if (bounded) {
+            // Step 4 only counts shuffles that reach the target's score (StatisticScoreWorker.java:51).  Count pass: every
+            // shuffle's possible matches and the score bound they allow; the few shuffles the bound cannot decide (a few per
+            // cent) are collected per CTA and scored in full, densely — the full scorer never runs on a warp with one live lane.
+            Extra ex; ex.site = -1; ex.delta = 0.0;
+            auto score_survivors = [&](uint32_t first, uint32_t count) {
+                if ((uint32_t)tid < count) {
+                    const uint32_t row = J.cand_begin + s_surv[first + tid];
+                    load_row(row);
+                    PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, 0, usedw, 0.0);
+                    if (ps.score >= J.ref_score) ++n_better;
+                }
+            };
+            if (tid == 0) s_nsurv = 0;
+            __syncthreads();
+            for (uint32_t c0 = 0; c0 < J.cand_count; c0 += BLOCK) {
+                const uint32_t c = c0 + tid;
+                if (c < J.cand_count) {
+                    load_row(J.cand_begin + c);
+                    ++n_in;
+                    if (below_score_bound<BLOCK>(codes, B, s_tab, s_nt, s_ct, J.charge, s_l10, J.ref_score)) ++n_bound;
+                    else s_surv[atomicAdd(&s_nsurv, 1u)] = c;
+                }
+                __syncthreads();
+                const uint32_t ns = s_nsurv;
+                if (ns >= (uint32_t)BLOCK) {
+                    score_survivors(ns - BLOCK, BLOCK);
+                    __syncthreads();
+                    if (tid == 0) s_nsurv = ns - BLOCK;
+                    __syncthreads();
+                }
+            }
+            score_survivors(0, s_nsurv);
+        } else
         for (uint32_t c0 = 0; c0 < J.cand_count; c0 += BLOCK) {
             uint32_t c = c0 + tid;
             bool active = c < J.cand_count;
             uint32_t row = J.cand_begin + (active ? c : 0u);
             Extra ex; ex.site = -1; ex.delta = 0.0;
             if (active) {
-                const uint4* rp = reinterpret_cast<const uint4*>(L.rows + (size_t)row * kRowBytes);
-                uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
-                codes[0 * BLOCK] = q0.x; codes[1 * BLOCK] = q0.y; codes[2 * BLOCK] = q0.z; codes[3 * BLOCK] = q0.w;
-                codes[4 * BLOCK] = q1.x; codes[5 * BLOCK] = q1.y; codes[6 * BLOCK] = q1.z; codes[7 * BLOCK] = q1.w;
-                codes[8 * BLOCK] = q2.x; codes[9 * BLOCK] = q2.y; codes[10 * BLOCK] = q2.z; codes[11 * BLOCK] = q2.w;
-                codes[12 * BLOCK] = q3.x; codes[13 * BLOCK] = q3.y; codes[14 * BLOCK] = q3.z; codes[15 * BLOCK] = q3.w;
+                load_row(row);
                 if (cfg.check_window) active = in_window(L.row_mass[row], J.mass, va, cfg);
             }
             if (active) {
                 int32_t pred = 0;
                 if (METHOD == 2) pred = L.row_pred[2 * (size_t)row + (J.charge == 2 ? 0 : 1)];
                 PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex,
-                                                         s_l10, L.ln_fact, pred, usedw, (L.kind == kJobShuffles && !cfg.score_all) ? J.ref_score : 0.0);
+                                                         s_l10, L.ln_fact, pred, usedw, 0.0);
                 ++n_in;
-                if (ps.a < 0) ++n_bound;
                 if (ps.score > best) { best = ps.score; best_cand = row; }
                 bool emit = false;
                 switch (L.kind) {

@@ -109,6 +109,18 @@ PQ_HD int cell_of(double mz) {
 #endif
 }
 
+// Cell for the "can anything be claimed here?" filter only: one unsigned minimum.  Everything outside [128, 4096) Th — below
+// the table, negative, NaN — wraps or clamps to the LAST cell, whose clean flag K0 therefore clears unless cell 0 (which
+// holds the events below 128 Th) is clean as well.
+PQ_HD uint32_t cell_filter(double mz) {
+    uint32_t c = (hi32(mz) >> kCellShift) - kCellBase;
+#ifdef __CUDA_ARCH__
+    return min(c, (uint32_t)(kCells - 1));
+#else
+    return c < (uint32_t)(kCells - 1) ? c : (uint32_t)(kCells - 1);
+#endif
+}
+
 // ---- exact arithmetic ------------------------------------------------------------------------------------------------
 // On the device every step is an explicit round-to-nearest intrinsic so that no FMA contraction can change a bit.
 PQ_HD double dadd(double a, double b) {
