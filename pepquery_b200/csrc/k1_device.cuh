@@ -265,22 +265,31 @@ __device__ __forceinline__ PairScore score_pair(const uint32_t* codes, const Blo
     }
 }
 
+// Shared-memory loads by 32-bit shared address.  The count pass below is a few instructions per ion, and converting a generic
+// pointer to its shared address inside the unrolled steps (the compiler re-derives it each time rather than hold a register)
+// showed up as 10 % of K1's instructions; one conversion per row and explicit ld.shared avoids that.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ double2 lds_f64x2(uint32_t a) { double2 v; asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
+
 // Count pass of the score bound (Step 4, no extra modification): walks the same fragment ladder as score_pair_n — the same sums
 // in the same order, so the same theoretical m/z — but only counts the ions that land in a cell where something can be
 // claimed.  Returns possible b matches | possible y matches << 16.  No queue, no claims: this is all a shuffle costs when
-// its bound 4 (log10(100 n) + log10 nb! + log10 ny!) stays below the target's score.  Four residues per row word, unrolled
-// (every shuffle of a job has the same length, so the guards are uniform); clean cells are counted through the sign bit
-// and subtracted from the number of ion / charge combinations.
+// its bound 4 (log10(100 n) + log10 nb! + log10 ny!) stays below the target's score.
+// Four residues per row word.  Words whose four ions all carry every fragment charge (ion number >= NCH) and all exist run
+// as straight-line code; the first ions of each series and the ragged ends take the guarded step.  Clean cells are counted
+// through the flag bit and subtracted from the number of ion / charge combinations.
 template <int BLOCK, int NCH>
 __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd,
                                                      const double* ctd, int z) {
     const uint32_t head = codes[0];
-    const int L = (int)(head & 0xFF);
+    const int L = (int)(head & 0xFF), Lm1 = L - 1;
     const int nch = NCH > 0 ? NCH : (z <= 1 ? 1 : z - 1);
-    const int16_t* cells = reinterpret_cast<const int16_t*>(B.cells);
-    auto clean = [&](double t) -> int { return (int)cells[cell_filter(t)] >> 15; };           // -1: nothing can be claimed at t
-    auto ion = [&](double m, int k) -> int {
-        int c = clean(__dadd_rn(m, kProton));
+    const uint32_t cells_s = smem_addr(B.cells), tab_s = smem_addr(tab);
+    auto clean = [&](double t) -> uint32_t { return lds_u16(cells_s + 2u * cell_filter(t)) >> 15; };   // 1: nothing can be claimed at t
+    auto residue = [&](uint32_t word, int j) -> double2 { return lds_f64x2(tab_s + ((word >> (8 * j)) & 0xFFu) * 16u); };
+    auto ion = [&](double m, int k) -> uint32_t {                        // any ion number (A6: charge c needs c <= k)
+        uint32_t c = clean(__dadd_rn(m, kProton));
         if (nch >= 2 && k >= 2) c += clean(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5));
         if (nch >= 3 && k >= 3) c += clean(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0));
         if (NCH == 0) {
@@ -289,40 +298,82 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
         }
         return c;
     };
+    auto ion_full = [&](double m, int k) -> uint32_t {                   // ion number >= NCH: every charge exists
+        if (NCH == 0) return ion(m, k);
+        uint32_t c = clean(__dadd_rn(m, kProton));
+        if (NCH >= 2) c += clean(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5));
+        if (NCH >= 3) c += clean(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0));
+        return c;
+    };
     // ion / charge combinations of one series: sum over k = 1..L-1 of min(nch, k)
-    const int full = max(L - 1 - nch, 0), ramp = min(nch, L - 1);
+    const int full = max(Lm1 - nch, 0), ramp = min(nch, Lm1);
     const int per_side = full * nch + ramp * (ramp + 1) / 2;
-    int cb = 0, cy = 0;                                     // minus the clean ones
-    const int Lm1 = L - 1;
+    uint32_t cb = 0, cy = 0;                                // minus the clean ones
+
+    // ---- b ions: residue k - 1 closes ion k; word g holds ions 4g+1 .. 4g+4 ----
     double acc = ntd[(head >> 8) & 0xFF];
-#pragma unroll 1
-    for (int w = 0; 4 * w < Lm1; ++w) {
-        const uint32_t word = codes[(1 + w) * BLOCK];
+    {
+        const uint32_t word = codes[1 * BLOCK];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int k = 4 * w + j + 1;
-            if (k <= Lm1) {
-                const double2 t = tab[(word >> (8 * j)) & 0xFFu];
+            if (j + 1 <= Lm1) {
+                const double2 t = residue(word, j);
                 acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
-                cb += ion(acc, k);
+                cb += ion(acc, j + 1);
             }
         }
     }
-    acc = ctd[(head >> 16) & 0xFF];
+    const int G = Lm1 >> 2;                                 // words 0 .. G-1 are full
 #pragma unroll 1
-    for (int w = Lm1 >> 2; w >= 0; --w) {
-        const uint32_t word = codes[(1 + w) * BLOCK];
+    for (int g = 1; g < G; ++g) {
+        const uint32_t word = codes[(1 + g) * BLOCK];
 #pragma unroll
-        for (int j = 3; j >= 0; --j) {
-            const int i = 4 * w + j;
-            if (i <= Lm1 && i >= 1) {
-                const double2 t = tab[(word >> (8 * j)) & 0xFFu];
+        for (int j = 0; j < 4; ++j) {
+            const double2 t = residue(word, j);
+            acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+            cb += ion_full(acc, 4 * g + j + 1);
+        }
+    }
+    if (G >= 1 && (Lm1 & 3)) {
+        const uint32_t word = codes[(1 + G) * BLOCK];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (4 * G + j + 1 <= Lm1) {
+                const double2 t = residue(word, j);
                 acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
-                cy += ion(__dadd_rn(acc, kWater), L - i);
+                cb += ion_full(acc, 4 * G + j + 1);
             }
         }
     }
-    const uint32_t nb = (uint32_t)(per_side + cb), ny = (uint32_t)(per_side + cy);
+    // ---- y ions: residue i (from L-1 down to 1) closes ion L - i ----
+    acc = ctd[(head >> 16) & 0xFF];
+    int i = Lm1;
+#pragma unroll 1
+    for (; i >= 1 && ((L - i) < nch || (i & 3) != 3); --i) {           // first ions and the ragged top word
+        const double2 t = residue(codes[(1 + (i >> 2)) * BLOCK], i & 3);
+        acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+        cy += ion(__dadd_rn(acc, kWater), L - i);
+    }
+    if (i >= 3) {                                                       // here i & 3 == 3
+#pragma unroll 1
+        for (int w = i >> 2; w >= 1; --w) {
+            const uint32_t word = codes[(1 + w) * BLOCK];
+#pragma unroll
+            for (int j = 3; j >= 0; --j) {
+                const double2 t = residue(word, j);
+                acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+                cy += ion_full(__dadd_rn(acc, kWater), L - (4 * w + j));
+            }
+        }
+        const uint32_t word = codes[1 * BLOCK];
+#pragma unroll
+        for (int j = 3; j >= 1; --j) {
+            const double2 t = residue(word, j);
+            acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+            cy += ion_full(__dadd_rn(acc, kWater), L - j);
+        }
+    }
+    const uint32_t nb = (uint32_t)per_side - cb, ny = (uint32_t)per_side - cy;
     return min(nb, 0xFFFFu) | (min(ny, 0xFFFFu) << 16);
 }
 

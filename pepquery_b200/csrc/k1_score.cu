@@ -27,6 +27,12 @@ namespace {
 
 using namespace dev;
 
+// bytes of the fixed part of K1's dynamic shared memory (row columns + tables [+ MVH used-bitmap columns]), 128-byte aligned
+template <int BLOCK, int METHOD>
+__host__ __device__ constexpr size_t kFixedSmem() {
+    return ((size_t)16 * BLOCK * 4 + (size_t)(2 * kMaxCodes + 2 * kMaxTermCodes + 130) * 8 + (METHOD == 2 ? (size_t)10 * BLOCK * 4 : 0) + 127) & ~(size_t)127;
+}
+
 template <int BLOCK, int METHOD>
 __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? K1_MIN_BLOCKS : (BLOCK == 64 ? 11 : 1))
 k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage) {
@@ -35,13 +41,15 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     __shared__ double s_red_d[BLOCK / 32];
     __shared__ uint32_t s_red_u[4][BLOCK / 32];
 
-    uint8_t* stage0 = smem;
-    uint32_t* codes_all = reinterpret_cast<uint32_t*>(smem + (size_t)stage_bytes * nstage);           // [16][BLOCK]
+    // The per-thread row columns and the small tables sit at compile-time offsets from the start of dynamic shared memory (so
+    // their addresses fold into the load instructions); the blob stages, whose size is a launch parameter, come after them.
+    uint32_t* codes_all = reinterpret_cast<uint32_t*>(smem);                                            // [16][BLOCK]
     double2* s_tab = reinterpret_cast<double2*>(codes_all + 16 * BLOCK);                               // {residue mass, modification mass} per code
     double* s_nt = reinterpret_cast<double*>(s_tab + kMaxCodes);
     double* s_ct = s_nt + kMaxTermCodes;
-    double* s_l10 = s_ct + kMaxTermCodes;                                                              // [65]
+    double* s_l10 = s_ct + kMaxTermCodes;                                                              // [130]
     uint32_t* usedw_all = reinterpret_cast<uint32_t*>(s_l10 + 130);                                     // MVH only: [10][BLOCK]
+    uint8_t* stage0 = smem + kFixedSmem<BLOCK, METHOD>();
 
     const int tid = threadIdx.x;
     for (int i = tid; i < kMaxCodes; i += BLOCK) s_tab[i] = make_double2(L.mods->aa[i], L.mods->delta[i]);
@@ -279,7 +287,7 @@ int launch_scatter(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st
 template <int BLOCK, int METHOD>
 int launch_kernel(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
     const uint32_t stage = (L.max_blob_bytes + 127u) & ~127u;
-    const size_t tail = (size_t)16 * BLOCK * 4 + (size_t)(2 * kMaxCodes + 2 * kMaxTermCodes + 130) * 8 + (METHOD == 2 ? (size_t)10 * BLOCK * 4 : 0);
+    const size_t tail = kFixedSmem<BLOCK, METHOD>();
     // Shuffle jobs (~1000 pairs each) hide the blob load behind a second stage; target / competitor jobs are short, there
     // one stage and more resident CTAs win (measured: Step 2 9.1 -> 5.4 ms, Step 3 18.7 -> 13.4 ms).
     int nstage = BLOCK == 256 ? 2 : 1;
