@@ -269,7 +269,7 @@ __device__ __forceinline__ PairScore score_pair(const uint32_t* codes, const Blo
 // pointer to its shared address inside the unrolled steps (the compiler re-derives it each time rather than hold a register)
 // showed up as 10 % of K1's instructions; one conversion per row and explicit ld.shared avoids that.
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }   // zero-extended
 __device__ __forceinline__ double2 lds_f64x2(uint32_t a) { double2 v; asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
 
 // Count pass of the score bound (Step 4, no extra modification): walks the same fragment ladder as score_pair_n — the same sums
