@@ -65,7 +65,8 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     // Jobs are handed out by an atomic counter (in list order, so neighbouring CTAs share table rows in L2); the next
     // job's blob is already in flight (second stage) while the current one is scored.
     __shared__ uint32_t s_job[2];
-    __shared__ uint32_t s_surv[2 * BLOCK];        // bounded Step 4: candidates the score bound could not decide
+    constexpr uint32_t kSurvCap = BLOCK == 256 ? 2048 : 2 * BLOCK;      // only the Step-4 configuration (BLOCK 256) pays for a long list
+    __shared__ uint16_t s_surv[kSurvCap];         // bounded Step 4: candidates the score bound could not decide (index within the job)
     __shared__ uint32_t s_nsurv;
     const bool bounded = METHOD == 1 && L.kind == kJobShuffles && !cfg.score_all && !cfg.check_window;
     auto fetch = [&](uint32_t slot) {           // thread 0: take the next job and start its TMA into `slot`
@@ -105,9 +106,9 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
             // shuffle's possible matches and the score bound they allow; the few shuffles the bound cannot decide (a few per
             // cent) are collected per CTA and scored in full, densely — the full scorer never runs on a warp with one live lane.
             Extra ex; ex.site = -1; ex.delta = 0.0;
-            auto score_survivors = [&](uint32_t first, uint32_t count) {
+            auto score_survivors = [&](uint32_t base, uint32_t first, uint32_t count) {
                 if ((uint32_t)tid < count) {
-                    const uint32_t row = J.cand_begin + s_surv[first + tid];
+                    const uint32_t row = J.cand_begin + base + s_surv[first + tid];
                     load_row(row);
                     PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, 0, usedw, 0.0);
                     if (ps.score >= J.ref_score) ++n_better;
@@ -115,24 +116,22 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
             };
             if (tid == 0) s_nsurv = 0;
             __syncthreads();
-            for (uint32_t c0 = 0; c0 < J.cand_count; c0 += BLOCK) {
-                const uint32_t c = c0 + tid;
-                if (c < J.cand_count) {
+            // jobs whose whole candidate list fits the survivor list (the usual case: -n 1000) run the count pass without a
+            // barrier; longer jobs drain the list in rounds of BLOCK, 2048 candidates at a time
+            for (uint32_t s0 = 0; s0 < J.cand_count; s0 += kSurvCap) {
+                const uint32_t s1 = min(s0 + kSurvCap, J.cand_count);
+                for (uint32_t c = s0 + tid; c < s1; c += BLOCK) {
                     load_row(J.cand_begin + c);
                     ++n_in;
                     if (below_score_bound<BLOCK>(codes, B, s_tab, s_nt, s_ct, J.charge, s_l10, J.ref_score)) ++n_bound;
-                    else s_surv[atomicAdd(&s_nsurv, 1u)] = c;
+                    else s_surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)(c - s0);
                 }
                 __syncthreads();
                 const uint32_t ns = s_nsurv;
-                if (ns >= (uint32_t)BLOCK) {
-                    score_survivors(ns - BLOCK, BLOCK);
-                    __syncthreads();
-                    if (tid == 0) s_nsurv = ns - BLOCK;
-                    __syncthreads();
-                }
+                for (uint32_t f = 0; f < ns; f += BLOCK) score_survivors(s0, f, min((uint32_t)BLOCK, ns - f));
+                __syncthreads();
+                if (tid == 0) s_nsurv = 0;
             }
-            score_survivors(0, s_nsurv);
         } else
         for (uint32_t c0 = 0; c0 < J.cand_count; c0 += BLOCK) {
             uint32_t c = c0 + tid;
