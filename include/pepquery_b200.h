@@ -230,6 +230,10 @@ int32_t pq_get_psms(pq_ctx* ctx, pq_psm* out, int64_t capacity, int64_t* n_psms)
 /* Multi-GPU gather: exports the PSM records (same layout and order as pq_get_psms) into a device buffer
  * owned by the context and returns its device address, so that the one collective of the path (NCCL gather of per-shard
  * PSM records) reads them without a host round trip.  The address stays valid until the next call on this context. */
+/* ref_delta_score / mod_delta_score of psm_rank.txt (PeptideSearchMT.add_delta_score, pg/PeptideSearchMT.java:1365-1475), one
+ * pair per PSM in pq_get_psms order: score minus the best detail.txt (Step 3) / ptm.txt (Step 5) row of the same spectrum;
+ * the plain score where the spectrum has no such row or the step has not run.  NULL outputs: only n_psms is written. */
+int32_t pq_get_delta_scores(pq_ctx* ctx, double* ref_delta_score, double* mod_delta_score, int64_t capacity, int64_t* n_psms);
 int32_t pq_export_psms_device(pq_ctx* ctx, uint64_t* device_address, int64_t* n_psms);
 int32_t pq_get_competitors(pq_ctx* ctx, int32_t step /* 3 or 5 */, pq_competitor* out, int64_t capacity, int64_t* n_rows);
 /* Shuffled sequences of one target sequence, in generation order (for parity checks of the RNG stream). */

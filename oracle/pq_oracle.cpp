@@ -1234,6 +1234,30 @@ int32_t orc_get_competitors(orc_ctx* o, int32_t step, pq_competitor* out, int64_
     memcpy(out, v.data(), v.size() * sizeof(pq_competitor));
     return 0;
 }
+// PeptideSearchMT.add_delta_score (pg/PeptideSearchMT.java:1365-1475): per row of psm_rank.txt, the target's score minus the
+// best score among that spectrum's rows of detail.txt (ref_delta_score) / ptm.txt (mod_delta_score); the plain score when
+// the spectrum has no row there.
+int32_t orc_get_delta_scores(orc_ctx* o, double* ref_delta, double* mod_delta, int64_t cap, int64_t* n) {
+    Ctx& C = o->c; *n = (int64_t)C.psms.size();
+    if (!ref_delta || !mod_delta) return 0;
+    if (cap < *n) return PQ_ERR_CAPACITY;
+    std::map<int32_t, double> ref_best, mod_best;
+    auto fill = [](const std::vector<pq_competitor>& rows, std::map<int32_t, double>& best) {
+        for (const pq_competitor& r : rows) {
+            auto it = best.find(r.spectrum);
+            if (it == best.end()) best[r.spectrum] = r.score;
+            else if (it->second < r.score) it->second = r.score;             // :1389-1392
+        }
+    };
+    fill(C.comp3, ref_best); fill(C.comp5, mod_best);
+    for (size_t i = 0; i < C.psms.size(); ++i) {
+        const Psm& p = C.psms[i];
+        auto a = ref_best.find(p.spectrum); auto b = mod_best.find(p.spectrum);
+        ref_delta[i] = a != ref_best.end() ? p.sc.score - a->second : p.sc.score;   // :1456-1463
+        mod_delta[i] = b != mod_best.end() ? p.sc.score - b->second : p.sc.score;
+    }
+    return 0;
+}
 int32_t orc_get_pairs(orc_ctx* o, uint64_t* out4) { for (int i = 0; i < 4; ++i) out4[i] = o->c.pairs[i]; return 0; }
 
 // scorePeptide2Spectrum on an explicit pair list (multi-threaded; the CPU-baseline timing leg uses this too)

@@ -141,6 +141,14 @@ class Oracle:
         self.L.orc_get_competitors(self.h, C.c_int32(step), arr, C.c_int64(n.value), C.byref(n))
         return np.frombuffer(arr, dtype=competitor_dtype(), count=n.value).copy()
 
+    def delta_scores(self):
+        """(ref_delta_score, mod_delta_score) per PSM, psms() order."""
+        n = C.c_int64()
+        self.L.orc_get_delta_scores(self.h, None, None, C.c_int64(0), C.byref(n))
+        a = np.zeros(max(1, n.value)); b = np.zeros(max(1, n.value))
+        self.L.orc_get_delta_scores(self.h, _p(a), _p(b), C.c_int64(n.value), C.byref(n))
+        return a[:n.value], b[:n.value]
+
     def pairs(self):
         out = np.zeros(4, dtype=np.uint64)
         self.L.orc_get_pairs(self.h, _p(out))

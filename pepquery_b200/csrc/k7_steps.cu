@@ -335,6 +335,23 @@ __global__ void k7_export(const DevPsm* __restrict__ psms, const uint32_t* __res
     out[j] = q;
 }
 
+// PeptideSearchMT.add_delta_score (pg/PeptideSearchMT.java:1365-1475) in export order: score minus the best detail.txt row
+// of the spectrum (= the best reference competitor when its score > 0, DBSearchWorker.java:93-98), score minus the best
+// ptm.txt row of the spectrum (sorted caller-spectrum keys, binary search); the plain score where there is no row.
+__global__ void k7_delta_scores(const DevPsm* __restrict__ psms, const uint32_t* __restrict__ out_perm, uint32_t n, const SegAgg* __restrict__ agg,
+                                const int32_t* __restrict__ mod_key, const double* __restrict__ mod_best, uint32_t n_mod,
+                                double* __restrict__ ref_delta, double* __restrict__ mod_delta) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const DevPsm& p = psms[out_perm[j]];
+    double r = p.score, m = p.score;
+    if (agg) { const double b = agg[p.seg].best; if (b > 0.0) r = __dsub_rn(p.score, b); }
+    uint32_t lo = 0, hi = n_mod;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (mod_key[mid] < p.spectrum) lo = mid + 1; else hi = mid; }
+    if (lo < n_mod && mod_key[lo] == p.spectrum) m = __dsub_rn(p.score, mod_best[lo]);
+    ref_delta[j] = r; mod_delta[j] = m;
+}
+
 __global__ void k7_set_nptm(DevPsm* __restrict__ psms, uint32_t n, const int32_t* __restrict__ n_ptm) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) psms[i].n_ptm = n_ptm[i];
@@ -433,6 +450,12 @@ int launch_rank(DevPsm* psms, uint32_t n, const uint32_t* seg_start, cudaStream_
 int launch_export_psms(const DevPsm* psms, const uint32_t* out_perm, uint32_t n, pq_psm* out, cudaStream_t st) {
     if (!n) return 0;
     k7_export<<<blocks(n), 256, 0, st>>>(psms, out_perm, n, out);
+    return 1;
+}
+int launch_delta_scores(const DevPsm* psms, const uint32_t* out_perm, uint32_t n, const SegAgg* agg, const int32_t* mod_key, const double* mod_best,
+                        uint32_t n_mod, double* ref_delta, double* mod_delta, cudaStream_t st) {
+    if (!n) return 0;
+    k7_delta_scores<<<blocks(n), 256, 0, st>>>(psms, out_perm, n, agg, mod_key, mod_best, n_mod, ref_delta, mod_delta);
     return 1;
 }
 int launch_set_nptm(DevPsm* psms, uint32_t n, const int32_t* n_ptm, cudaStream_t st) {

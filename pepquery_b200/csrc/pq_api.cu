@@ -92,7 +92,7 @@ struct pq_ctx {
     // work buffers
     DevBuf jobs, jobs2, results, hits, hit_count, njobs;
     // device-resident PSM table (K7)
-    DevBuf d_psm, d_seg_start, d_out_perm, d_scalars, d_counters, d_agg, hits3, d_export;
+    DevBuf d_psm, d_seg_start, d_out_perm, d_scalars, d_counters, d_agg, hits3, d_export, d_delta, d_modkey, d_modbest;
     DevBuf k_key_a, k_key_b, k_idx_a, k_idx_b, k_head;
     uint32_t n_psm = 0, n_seg = 0, nh3 = 0, comp3_n = 0; bool comp3_ready = false;
     DevBuf c_rows, c_rows2, c_keys, c_keys2, c_idx, c_idx2;
@@ -1084,6 +1084,41 @@ int32_t pq_get_psms(pq_ctx* ctx, pq_psm* out, int64_t capacity, int64_t* n_psms)
     int32_t rc = copy_to_caller(ctx, out, ctx->d_export.p, bytes);
     if (rc) return rc;
     ctx->cnt.d2h_bytes += bytes;
+    return PQ_OK;
+}
+
+int32_t pq_get_delta_scores(pq_ctx* ctx, double* ref_delta, double* mod_delta, int64_t capacity, int64_t* n_psms) {
+    if (!ctx || !n_psms) return PQ_ERR_BAD_ARG;
+    *n_psms = (int64_t)ctx->n_psm;
+    if (!ref_delta || !mod_delta) return PQ_OK;
+    if (capacity < *n_psms) return fail(ctx, PQ_ERR_CAPACITY, "delta score buffers too small");
+    if (!ctx->n_psm) return PQ_OK;
+    cudaSetDevice(ctx->P.device);
+    cudaStream_t st = ctx->st;
+    const size_t n = ctx->n_psm;
+    // best ptm.txt row per spectrum (rows of Step 5 live on the host, sorted by spectrum): a short sorted key list for the kernel
+    std::vector<int32_t> mk; std::vector<double> mb;
+    if (ctx->step_done >= 5)
+        for (const pq_competitor& r : ctx->comp5) {
+            if (mk.empty() || mk.back() != r.spectrum) { mk.push_back(r.spectrum); mb.push_back(r.score); }
+            else if (mb.back() < r.score) mb.back() = r.score;
+        }
+    for (size_t i = 1; i < mk.size(); ++i) if (mk[i - 1] >= mk[i]) return fail(ctx, PQ_ERR_STATE, "ptm rows are not ordered by spectrum");
+    CU(ctx->d_delta.reserve(2 * n * 8)); CU(ctx->d_modkey.reserve(mk.size() * 4 + 4)); CU(ctx->d_modbest.reserve(mb.size() * 8 + 8));
+    if (!mk.empty()) {
+        CU(cudaMemcpyAsync(ctx->d_modkey.p, mk.data(), mk.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_modbest.p, mb.data(), mb.size() * 8, cudaMemcpyHostToDevice, st));
+        ctx->cnt.h2d_bytes += mk.size() * 12;
+    }
+    const SegAgg* agg = (ctx->step_done >= 3 && ctx->n_seg) ? ctx->d_agg.as<SegAgg>() : nullptr;
+    ctx->cnt.other_kernel_launches += (uint64_t)launch_delta_scores(ctx->d_psm.as<DevPsm>(), ctx->d_out_perm.as<uint32_t>(), ctx->n_psm, agg, ctx->d_modkey.as<int32_t>(),
+                                                                    ctx->d_modbest.as<double>(), (uint32_t)mk.size(), ctx->d_delta.as<double>(), ctx->d_delta.as<double>() + n, st);
+    CU(cudaStreamSynchronize(st));                      // mk / mb leave scope
+    int32_t rc = copy_to_caller(ctx, ref_delta, ctx->d_delta.p, n * 8);
+    if (rc) return rc;
+    rc = copy_to_caller(ctx, mod_delta, ctx->d_delta.as<double>() + n, n * 8);
+    if (rc) return rc;
+    ctx->cnt.d2h_bytes += 2 * n * 8;
     return PQ_OK;
 }
 

@@ -234,6 +234,8 @@ int launch_step4_apply(const Job* jobs, const JobResult* res, const uint32_t* or
 int launch_psm_form_keys(const DevPsm* psms, const uint32_t* list, uint32_t n, uint32_t* keys, cudaStream_t st);
 int launch_rank(DevPsm* psms, uint32_t n, const uint32_t* seg_start, cudaStream_t st);
 int launch_export_psms(const DevPsm* psms, const uint32_t* out_perm, uint32_t n, pq_psm* out, cudaStream_t st);
+int launch_delta_scores(const DevPsm* psms, const uint32_t* out_perm, uint32_t n, const SegAgg* agg, const int32_t* mod_key, const double* mod_best,
+                        uint32_t n_mod, double* ref_delta, double* mod_delta, cudaStream_t st);
 int launch_set_nptm(DevPsm* psms, uint32_t n, const int32_t* n_ptm, cudaStream_t st);
 
 // MVH predicted-peak counts per row (k4_predict.cu): out[2*row] for precursor charge 2, out[2*row+1] otherwise

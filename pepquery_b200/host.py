@@ -57,7 +57,7 @@ def load_library():
 EXPORTS = ["pq_version", "pq_last_error", "pq_default_params", "pq_create", "pq_destroy", "pq_load_spectra",
            "pq_set_targets", "pq_get_target_forms", "pq_build_reference", "pq_get_reference_forms",
            "pq_step2_match_targets", "pq_step3_competitors", "pq_step4_shuffles", "pq_rank_and_validate",
-           "pq_step5_ptm", "pq_get_psms", "pq_export_psms_device", "pq_get_competitors", "pq_get_shuffles", "pq_score_pairs",
+           "pq_step5_ptm", "pq_get_psms", "pq_get_delta_scores", "pq_export_psms_device", "pq_get_competitors", "pq_get_shuffles", "pq_score_pairs",
            "pq_get_counters", "pq_reset_counters", "pq_event_record", "pq_event_elapsed_ms", "pq_parse_mgf"]
 
 
@@ -180,6 +180,14 @@ class Search:
         n = C.c_int64()
         self._ck(self.L.pq_get_psms(self.h, None, C.c_int64(0), C.byref(n)))
         return n.value
+
+    def delta_scores(self):
+        """(ref_delta_score, mod_delta_score) per PSM in psms() order (PeptideSearchMT.add_delta_score)."""
+        n = C.c_int64()
+        self._ck(self.L.pq_get_delta_scores(self.h, None, None, C.c_int64(0), C.byref(n)))
+        a = np.zeros(max(1, n.value)); b = np.zeros(max(1, n.value))
+        self._ck(self.L.pq_get_delta_scores(self.h, _p(a), _p(b), C.c_int64(n.value), C.byref(n)))
+        return a[:n.value], b[:n.value]
 
     def competitors(self, step=3):
         n = C.c_int64()

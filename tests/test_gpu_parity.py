@@ -63,6 +63,8 @@ def full_compare(params, sp, tgt, prot):
     co = np.sort(o.competitors(3), order=["spectrum", "ref_form"]); cg = np.sort(g.competitors(3), order=["spectrum", "ref_form"])
     assert np.array_equal(co["spectrum"], cg["spectrum"]) and np.array_equal(co["ref_form"], cg["ref_form"])
     assert np.allclose(co["score"], cg["score"], rtol=REL, atol=0)
+    (gr, gm), (wr, wm) = g.delta_scores(), o.delta_scores()                                      # ref_delta_score / mod_delta_score columns
+    assert np.allclose(gr, wr, rtol=REL, atol=1e-9) and np.allclose(gm, wm, rtol=REL, atol=1e-9) and np.array_equal(gm, got["score"])
     c = g.counters()
     assert [c.pairs_step2, c.pairs_step3, c.pairs_step4] == [int(x) for x in o.pairs()[:3]]      # same scorePeptide2Spectrum call counts
     assert c.score_kernel_launches >= (3 if len(got) and got["valid"].sum() else 1)
@@ -176,6 +178,9 @@ def test_step5_unrestricted_modification_search(data, over):
     assert np.allclose(co["score"], cg["score"], rtol=REL, atol=0) and np.array_equal(co["pep_mass"], cg["pep_mass"])
     assert g.counters().pairs_step5 == int(o.pairs()[3]) > 100000
     assert (got["n_ptm"] >= 0).sum() > 50
+    (gr, gm), (wr, wm) = g.delta_scores(), o.delta_scores()
+    assert np.allclose(gr, wr, rtol=REL, atol=1e-9) and np.allclose(gm, wm, rtol=REL, atol=1e-9)
+    assert (gm < got["score"]).sum() == (wm < want["score"]).sum() and ((gm != got["score"]).sum() > 0 or len(cg) == 0)
 
 
 def test_step5_with_mvh_scoring(data):
@@ -657,3 +662,15 @@ def test_large_size_properties(large):
     so, ao, bo = o.score_pairs(a["spectrum"][pick], arr, 400)
     assert np.array_equal(ao, a["count_b"][pick]) and np.array_equal(bo, a["count_y"][pick])
     assert np.allclose(so, a["score"][pick], rtol=REL, atol=0)
+
+
+def test_delta_scores_before_step3(data):
+    """add_delta_score with no detail.txt / ptm.txt: both columns equal the score (PeptideSearchMT.java:1456-1463)."""
+    prot, tgt, sp = data
+    g = run_gpu(_abi.default_params(n_random=50), sp, tgt, prot, steps=2)
+    o = run_oracle(_abi.default_params(n_random=50), sp, tgt, prot, steps=2)
+    got = g.psms()
+    r, m = g.delta_scores()
+    assert np.array_equal(r, got["score"]) and np.array_equal(m, got["score"])
+    wr, wm = o.delta_scores()
+    assert np.array_equal(wr, r) and np.array_equal(wm, m)

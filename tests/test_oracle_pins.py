@@ -263,3 +263,22 @@ def test_oracle_thread_count_does_not_change_results(small_inputs, threads):
     ps = o.psms()
     gold = json.load(open(os.path.join(GOLD, "oracle_vectors.json")))["method1"]
     assert ps["spectrum"].tolist() == gold["spectrum"] and ps["score"].tolist() == gold["score"] and ps["n_db"].tolist() == gold["n_db"]
+
+
+def test_delta_scores_follow_the_detail_rows(small_inputs):
+    """ref_delta_score / mod_delta_score (PeptideSearchMT.add_delta_score, pg/PeptideSearchMT.java:1365-1475) restated in
+    Python from the rows the oracle reports for detail.txt: score minus the spectrum's best row, the plain score without one."""
+    prot, tgt, sp = small_inputs
+    o = pq_oracle.Oracle(_abi.default_params(n_random=20), threads=4)
+    o.load_spectra(sp); o.set_targets(*tgt); o.step2(); o.build_reference(*prot); o.step3(); o.step4(); o.rank()
+    ps, rows = o.psms(), o.competitors(3)
+    best = {}
+    for r in rows:
+        s = int(r["spectrum"])
+        if s not in best or best[s] < r["score"]:
+            best[s] = float(r["score"])
+    want = np.array([p["score"] - best[int(p["spectrum"])] if int(p["spectrum"]) in best else p["score"] for p in ps])
+    ref, mod = o.delta_scores()
+    assert np.array_equal(ref, want) and np.array_equal(mod, ps["score"]) and len(best) > 10
+    assert (ref < 0).sum() == (ps["n_db"] > 0).sum() + ((ref < 0) & (ps["n_db"] == 0)).sum()   # a better reference match => negative delta
+    assert np.all(ref[ps["n_db"] > 0] <= 0)
