@@ -230,6 +230,13 @@ int32_t pq_get_psms(pq_ctx* ctx, pq_psm* out, int64_t capacity, int64_t* n_psms)
 /* Multi-GPU gather: exports the PSM records (same layout and order as pq_get_psms) into a device buffer
  * owned by the context and returns its device address, so that the one collective of the path (NCCL gather of per-shard
  * PSM records) reads them without a host round trip.  The address stays valid until the next call on this context. */
+/* Step-1 novelty filter (pg/InputProcessor.java:379-448 with the default FM-index mapping, pg/PepMapping.java:60-107):
+ * nhit[i] = 1 when target sequence i occurs as a substring of some protein of the reference database, I and L
+ * indistinguishable, case ignored; 0 otherwise.  Exact substring semantics (not digest membership).  Independent of the
+ * search state of ctx (only its device and stream are used). */
+int32_t pq_find_in_proteome(pq_ctx* ctx, int32_t n_seq, const uint32_t* seq_offset /* n+1 */, const char* residues,
+                            int32_t n_proteins, const uint64_t* protein_offset /* n+1 */, const char* protein_residues, int32_t* nhit);
+
 /* ref_delta_score / mod_delta_score of psm_rank.txt (PeptideSearchMT.add_delta_score, pg/PeptideSearchMT.java:1365-1475), one
  * pair per PSM in pq_get_psms order: score minus the best detail.txt (Step 3) / ptm.txt (Step 5) row of the same spectrum;
  * the plain score where the spectrum has no such row or the step has not run.  NULL outputs: only n_psms is written. */

@@ -1258,6 +1258,21 @@ int32_t orc_get_delta_scores(orc_ctx* o, double* ref_delta, double* mod_delta, i
     }
     return 0;
 }
+// Step-1 novelty filter with the default FM-index mapping (pg/InputProcessor.java:416-427, pg/PepMapping.java:60-107):
+// hasProtein(seq) = seq occurs in some protein with I and L indistinguishable (A13: compomics FMIndex,
+// MatchingType.indistiguishableAminoAcids, treated as exact substring search after I -> L; case folded).
+int32_t orc_find_in_proteome(int32_t n_seq, const uint32_t* seq_off, const char* res, int32_t n_prot, const uint64_t* prot_off, const char* prot_res,
+                             int32_t* nhit) {
+    auto fold = [](char c) { char u = (char)toupper((unsigned char)c); return u == 'I' ? 'L' : u; };
+    std::vector<std::string> prots((size_t)n_prot);
+    for (int32_t i = 0; i < n_prot; ++i) { std::string& p = prots[(size_t)i]; for (uint64_t k = prot_off[i]; k < prot_off[i + 1]; ++k) p.push_back(fold(prot_res[k])); }
+    for (int32_t t = 0; t < n_seq; ++t) {
+        std::string q; for (uint32_t k = seq_off[t]; k < seq_off[t + 1]; ++k) q.push_back(fold(res[k]));
+        nhit[t] = 0;
+        for (const std::string& p : prots) if (p.find(q) != std::string::npos) { nhit[t] = 1; break; }
+    }
+    return 0;
+}
 int32_t orc_get_pairs(orc_ctx* o, uint64_t* out4) { for (int i = 0; i < 4; ++i) out4[i] = o->c.pairs[i]; return 0; }
 
 // scorePeptide2Spectrum on an explicit pair list (multi-threaded; the CPU-baseline timing leg uses this too)

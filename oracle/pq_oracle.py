@@ -43,6 +43,15 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+def find_in_proteome(toff, tres, poff, pres):
+    """Step-1 novelty filter (FM-index semantics): target offsets u32[n+1] + residues, protein offsets u64[n+1] + residues."""
+    toff = np.ascontiguousarray(toff, dtype=np.uint32); poff = np.ascontiguousarray(poff, dtype=np.uint64)
+    tres = np.ascontiguousarray(tres, dtype=np.uint8); pres = np.ascontiguousarray(pres, dtype=np.uint8)
+    out = np.zeros(max(1, len(toff) - 1), dtype=np.int32)
+    lib().orc_find_in_proteome(C.c_int32(len(toff) - 1), _p(toff), _p(tres), C.c_int32(len(poff) - 1), _p(poff), _p(pres), _p(out))
+    return out[:len(toff) - 1]
+
+
 def java_random(seed, bound, n):
     out = np.zeros(n, dtype=np.int32)
     lib().orc_java_random_ints(C.c_int64(seed), C.c_int32(bound), C.c_int32(n), _p(out))

@@ -1122,6 +1122,18 @@ int32_t pq_get_delta_scores(pq_ctx* ctx, double* ref_delta, double* mod_delta, i
     return PQ_OK;
 }
 
+int32_t pq_find_in_proteome(pq_ctx* ctx, int32_t n_seq, const uint32_t* seq_off, const char* res, int32_t n_prot, const uint64_t* prot_off,
+                            const char* prot_res, int32_t* nhit) {
+    if (!ctx || n_seq < 0 || n_prot < 0 || (n_seq > 0 && (!seq_off || !res || !nhit)) || (n_prot > 0 && (!prot_off || !prot_res)))
+        return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
+    cudaSetDevice(ctx->P.device);
+    std::string err; int launches = 0;
+    if (!find_in_proteome(n_seq, seq_off, res, n_prot, prot_off, prot_res, nhit, ctx->st, &ctx->cnt.h2d_bytes, &ctx->cnt.d2h_bytes, &launches, err))
+        return fail(ctx, err.find("target") != std::string::npos ? PQ_ERR_BAD_ARG : PQ_ERR_CUDA, "novelty filter: " + err);
+    ctx->cnt.other_kernel_launches += (uint64_t)launches;
+    return PQ_OK;
+}
+
 int32_t pq_export_psms_device(pq_ctx* ctx, uint64_t* device_address, int64_t* n_psms) {
     if (!ctx || !device_address || !n_psms) return PQ_ERR_BAD_ARG;
     *n_psms = (int64_t)ctx->n_psm; *device_address = 0;

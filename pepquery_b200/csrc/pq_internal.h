@@ -234,6 +234,9 @@ int launch_step4_apply(const Job* jobs, const JobResult* res, const uint32_t* or
 int launch_psm_form_keys(const DevPsm* psms, const uint32_t* list, uint32_t n, uint32_t* keys, cudaStream_t st);
 int launch_rank(DevPsm* psms, uint32_t n, const uint32_t* seg_start, cudaStream_t st);
 int launch_export_psms(const DevPsm* psms, const uint32_t* out_perm, uint32_t n, pq_psm* out, cudaStream_t st);
+// Step-1 novelty filter (k8_novelty.cu): nhit[i] = 1 when target i occurs in a protein (I = L); false + err on refusal / CUDA error
+bool find_in_proteome(int32_t n_seq, const uint32_t* seq_off, const char* res, int32_t n_prot, const uint64_t* prot_off, const char* prot_res,
+                      int32_t* nhit, cudaStream_t st, uint64_t* h2d, uint64_t* d2h, int* launches, std::string& err);
 int launch_delta_scores(const DevPsm* psms, const uint32_t* out_perm, uint32_t n, const SegAgg* agg, const int32_t* mod_key, const double* mod_best,
                         uint32_t n_mod, double* ref_delta, double* mod_delta, cudaStream_t st);
 int launch_set_nptm(DevPsm* psms, uint32_t n, const int32_t* n_ptm, cudaStream_t st);

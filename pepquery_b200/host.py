@@ -58,7 +58,7 @@ EXPORTS = ["pq_version", "pq_last_error", "pq_default_params", "pq_create", "pq_
            "pq_set_targets", "pq_get_target_forms", "pq_build_reference", "pq_get_reference_forms",
            "pq_step2_match_targets", "pq_step3_competitors", "pq_step4_shuffles", "pq_rank_and_validate",
            "pq_step5_ptm", "pq_get_psms", "pq_get_delta_scores", "pq_export_psms_device", "pq_get_competitors", "pq_get_shuffles", "pq_score_pairs",
-           "pq_get_counters", "pq_reset_counters", "pq_event_record", "pq_event_elapsed_ms", "pq_parse_mgf"]
+           "pq_find_in_proteome", "pq_get_counters", "pq_reset_counters", "pq_event_record", "pq_event_elapsed_ms", "pq_parse_mgf"]
 
 
 def _p(a):
@@ -180,6 +180,14 @@ class Search:
         n = C.c_int64()
         self._ck(self.L.pq_get_psms(self.h, None, C.c_int64(0), C.byref(n)))
         return n.value
+
+    def find_in_proteome(self, toff, tres, poff, pres):
+        """Step-1 novelty filter: 1 per target sequence that occurs in a protein (I = L), else 0."""
+        toff = np.ascontiguousarray(toff, dtype=np.uint32); poff = np.ascontiguousarray(poff, dtype=np.uint64)
+        tres = np.ascontiguousarray(tres, dtype=np.uint8); pres = np.ascontiguousarray(pres, dtype=np.uint8)
+        out = np.zeros(max(1, len(toff) - 1), dtype=np.int32)
+        self._ck(self.L.pq_find_in_proteome(self.h, C.c_int32(len(toff) - 1), _p(toff), _p(tres), C.c_int32(len(poff) - 1), _p(poff), _p(pres), _p(out)))
+        return out[:len(toff) - 1]
 
     def delta_scores(self):
         """(ref_delta_score, mod_delta_score) per PSM in psms() order (PeptideSearchMT.add_delta_score)."""

@@ -107,3 +107,34 @@ def spectra(n, tgt, prot, seed=99, itol=0.6, first_index=0, mass_lo=0.0, mass_hi
         inten = np.zeros(total, dtype=np.float64)
     L.syn_spectra(*args, _p(prec), _p(chg), _p(off), _p(mz), _p(inten), threads)
     return dict(prec_mz=prec, charge=chg, peak_off=off, mz=mz, inten=inten)
+
+
+def planted_targets(prot, rng):
+    """Substrings of the proteome (some with I/L swapped, lower case, at protein ends), a sequence that only exists across a
+    protein boundary, and random sequences; -> offsets, residues, expected nhit (Python `in` on I->L folded strings)."""
+    poff, pres = prot
+    prots = [bytes(pres[int(poff[i]):int(poff[i + 1])]).decode() for i in range(len(poff) - 1)]
+    fold = lambda s: s.upper().replace("I", "L")
+    seqs = []
+    for k in range(60):
+        p = prots[int(rng.integers(len(prots)))]
+        L = int(rng.integers(1 if k < 5 else 6, 30))
+        a = int(rng.integers(0, max(1, len(p) - L)))
+        if k % 7 == 0: a = 0
+        if k % 7 == 1: a = max(0, len(p) - L)
+        s = p[a:a + L]
+        if k % 3 == 0: s = s.replace("L", "I")
+        if k % 3 == 1: s = "".join("L" if (c == "I" and i % 2) else c for i, c in enumerate(s))
+        if k % 5 == 0: s = s.lower()
+        seqs.append(s)
+    seqs.append(prots[0][-5:] + prots[1][:5])                       # crosses a protein boundary
+    letters = "ACDEFGHKLMNPQRSTVWY"
+    for k in range(40):
+        seqs.append("".join(letters[int(x)] for x in rng.integers(0, len(letters), int(rng.integers(7, 26)))))
+    seqs.append(prots[3][:-1] + "W" if not prots[3].endswith("W") else prots[3][:-1] + "A")     # a whole protein with its last residue changed
+    seqs.append(prots[4])                                            # a whole protein
+    folded = [fold(p) for p in prots]
+    want = np.array([1 if any(fold(s) in p for p in folded) else 0 for s in seqs], dtype=np.int32)
+    off = np.zeros(len(seqs) + 1, dtype=np.uint32); off[1:] = np.cumsum([len(s) for s in seqs])
+    res = np.frombuffer("".join(seqs).encode(), dtype=np.uint8).copy()
+    return off, res, want

@@ -674,3 +674,50 @@ def test_delta_scores_before_step3(data):
     assert np.array_equal(r, got["score"]) and np.array_equal(m, got["score"])
     wr, wm = o.delta_scores()
     assert np.array_equal(wr, r) and np.array_equal(wm, m)
+
+
+def test_novelty_filter(data):
+    """Step 1: target present in the reference proteome?  Device K-mer scan against the oracle's substring search
+    and Python's `in`: planted substrings (I/L swapped, lower case, protein ends, whole proteins), a sequence that only exists
+    across a protein boundary, random sequences, targets shorter than the K-mer."""
+    from oracle import pq_oracle
+    prot, tgt, sp = data
+    prot = (prot[0], prot[1].copy())
+    prot[1][::41] |= 0x20
+    off, res, want = synth.planted_targets(prot, np.random.default_rng(11))
+    g = Search(_abi.default_params())
+    got = g.find_in_proteome(off, res, prot[0], prot[1])
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, pq_oracle.find_in_proteome(off, res, prot[0], prot[1]))
+    # the synthetic targets are novel by construction (rejected if present in the digest): none is found
+    nov = g.find_in_proteome(tgt[0], tgt[1], prot[0], prot[1])
+    assert np.array_equal(nov, pq_oracle.find_in_proteome(tgt[0], tgt[1], prot[0], prot[1])) and nov.sum() == 0
+    # long targets only (K = 6) and an empty target list
+    keep = [i for i in range(len(off) - 1) if off[i + 1] - off[i] >= 6]
+    off2 = np.zeros(len(keep) + 1, dtype=np.uint32); off2[1:] = np.cumsum([off[i + 1] - off[i] for i in keep])
+    res2 = np.concatenate([res[off[i]:off[i + 1]] for i in keep])
+    assert np.array_equal(g.find_in_proteome(off2, res2, prot[0], prot[1]), want[keep])
+    assert len(g.find_in_proteome(np.zeros(1, dtype=np.uint32), np.zeros(0, dtype=np.uint8), prot[0], prot[1])) == 0
+    with pytest.raises(PepQueryError):
+        g.find_in_proteome(np.array([0, 3], dtype=np.uint32), np.frombuffer(b"A*C", dtype=np.uint8), prot[0], prot[1])
+
+
+def test_novelty_filter_full_size_properties():
+    """20 k-protein database (9 M residues), 10 k targets: every planted substring is found, a changed copy is not."""
+    rng = np.random.default_rng(3)
+    prot = synth.proteins(20000)
+    poff, pres = prot
+    seqs, want = [], []
+    for k in range(5000):
+        i = int(rng.integers(0, len(poff) - 1)); a, b = int(poff[i]), int(poff[i + 1])
+        L = int(rng.integers(7, 26)); s0 = int(rng.integers(a, max(a + 1, b - L)))
+        s = bytes(pres[s0:s0 + L]); seqs.append(s); want.append(1)
+        t = bytearray(s) * 2; t[L // 2] = ord("W") if t[L // 2] != ord("W") else ord("A")      # doubled + changed: 14-50 residues, absent
+        seqs.append(bytes(t)); want.append(0)
+    off = np.zeros(len(seqs) + 1, dtype=np.uint32); off[1:] = np.cumsum([len(s) for s in seqs])
+    res = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy()
+    g = Search(_abi.default_params())
+    got = g.find_in_proteome(off, res, poff, pres)
+    want = np.array(want, dtype=np.int32)
+    assert np.array_equal(got[want == 1], want[want == 1])
+    assert got[want == 0].sum() <= 2                                   # a doubled, mutated sequence occurring by chance is (nearly) impossible

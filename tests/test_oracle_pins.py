@@ -282,3 +282,14 @@ def test_delta_scores_follow_the_detail_rows(small_inputs):
     assert np.array_equal(ref, want) and np.array_equal(mod, ps["score"]) and len(best) > 10
     assert (ref < 0).sum() == (ps["n_db"] > 0).sum() + ((ref < 0) & (ps["n_db"] == 0)).sum()   # a better reference match => negative delta
     assert np.all(ref[ps["n_db"] > 0] <= 0)
+
+
+def test_novelty_filter_against_python_substring_search():
+    """Step-1 novelty filter (pg/InputProcessor.java:416-427, pg/PepMapping.java:60-107): the oracle against Python's `in`."""
+    from pepquery_b200 import synth
+    prot = synth.proteins(120)
+    prot = (prot[0], prot[1].copy())
+    prot[1][::53] |= 0x20                                            # some lower-case residues in the database
+    off, res, want = synth.planted_targets(prot, np.random.default_rng(5))
+    got = pq_oracle.find_in_proteome(off, res, prot[0], prot[1])
+    assert np.array_equal(got, want) and 40 < want.sum() < len(want)
