@@ -366,8 +366,8 @@ def main():
         g = Search(mk_params(1))                   # a fresh context with the library defaults
 
         def e2e_step():
-            g.load_spectra(sp)                     # H2D of the pinned CSR arrays + packing (+ K0 under the upload)
-            g.set_targets(*tgt)
+            g.set_targets(*tgt)                    # the reference's order: targets (Step 1) before the spectra are read
+            g.load_spectra(sp)                     # H2D of the pinned CSR arrays + packing; K0 and the target table under the upload
             g.step2()
             g.build_reference(*prot)               # H2D of the proteins; digest + form expansion + mass sort on the device (K6)
             g.step3(); g.step4()

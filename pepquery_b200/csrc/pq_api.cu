@@ -87,7 +87,7 @@ struct pq_ctx {
     // tables
     PeptideTable targets, reference;
     TargetOrder order;
-    bool have_targets = false, have_reference = false;
+    bool have_targets = false, have_reference = false, forms_expanded = false;
     int step_done = 0;
     // work buffers
     DevBuf jobs, jobs2, results, hits, hit_count, njobs;
@@ -127,6 +127,8 @@ struct Timer {
     ~Timer();
 };
 void flush_timers(pq_ctx* c);
+int32_t finalize_targets(pq_ctx* ctx);
+void ensure_forms(pq_ctx* ctx);
 
 Timer::Timer(pq_ctx* c_, double* t, double* t2) : c(c_), acc(t), acc2(t2) {
     auto get = [&]() { cudaEvent_t e; if (!c->free_events.empty()) { e = c->free_events.back(); c->free_events.pop_back(); } else cudaEventCreate(&e); return e; };
@@ -390,6 +392,7 @@ int32_t pq_get_counters(pq_ctx* ctx, pq_counters* out) {
     cudaSetDevice(ctx->P.device);
     int32_t rc = pull_device_counters(ctx);
     if (rc) return rc;
+    ensure_forms(ctx);                       // cnt.target_forms
     *out = ctx->cnt;
     return PQ_OK;
 }
@@ -519,6 +522,8 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
         ctx->cnt.other_kernel_launches += (uint64_t)k + 4;
     }
     CU(cudaGetLastError());
+    // targets given before the spectra: their expansion, sort and encoding (host work) overlap the upload
+    if (ctx->have_targets) { int32_t rc = finalize_targets(ctx); if (rc) return rc; }
     CU(cudaStreamSynchronize(st));
     ctx->host_spectra_valid = false;          // host mirrors (Step 5, pq_score_pairs) are pulled on first use
     return PQ_OK;
@@ -540,11 +545,10 @@ int32_t pq_set_targets(pq_ctx* ctx, int32_t n_seq, const uint32_t* off, const ch
         if (s.size() < 2 || s.size() > (size_t)kMaxLen) return fail(ctx, PQ_ERR_UNSUPPORTED, "target length must be 2..60: " + s);
         for (char c : s) if (c < 'A' || c > 'Z' || ctx->codes.residue_mass[c - 'A'] == 0.0) return fail(ctx, PQ_ERR_BAD_ARG, "target has a non-standard residue: " + s);
         T.seqs.push_back(s);
-        ctx->codes.expand_forms(s, i, T.forms);
     }
-    // caller-visible form order = generation order (sequence order, then calcPeptideIsoforms order); the device table is
-    // the same forms sorted by mass; table_of_form / form_of_row translate.
-    ctx->cnt.target_forms = T.forms.size();
+    // The isoform expansion, the mass-sorted device table and its side arrays are host work that the next pq_load_spectra
+    // (while the peaks cross PCIe) or, failing that, pq_step2_match_targets does: finalize_targets().
+    ctx->forms_expanded = false; ctx->cnt.target_forms = 0;
     ctx->order.form_of_row.clear(); ctx->order.row_of_form.clear();
     ctx->have_targets = true; ctx->step_done = 0; reset_psm_state(ctx);
     return PQ_OK;
@@ -564,9 +568,21 @@ std::string mod_string(const pq_ctx* ctx, const FormRec& f) {
     return s;
 }
 // target forms keep two orders: public (generation) and device (mass-sorted)
+// caller-visible form order = generation order (sequence order, then calcPeptideIsoforms order); the device table is the
+// same forms sorted by mass; row_of_form / form_of_row translate.
+void ensure_forms(pq_ctx* ctx) {
+    if (ctx->forms_expanded || !ctx->have_targets) return;
+    PeptideTable& T = ctx->targets;
+    T.forms.clear();
+    for (size_t i = 0; i < T.seqs.size(); ++i) ctx->codes.expand_forms(T.seqs[i], (int32_t)i, T.forms);
+    ctx->cnt.target_forms = T.forms.size();
+    ctx->forms_expanded = true;
+}
+
 int32_t finalize_targets(pq_ctx* ctx) {
     PeptideTable& T = ctx->targets;
     TargetOrder& O = ctx->order;
+    ensure_forms(ctx);
     if (!O.form_of_row.empty() && O.form_of_row.size() == T.forms.size() && T.rows.p) return PQ_OK;
     const size_t n = T.forms.size();
     Marks mk("finalize_targets");
@@ -576,15 +592,19 @@ int32_t finalize_targets(pq_ctx* ctx) {
     mk.mark("sort by mass");
     O.form_of_row = ord; O.row_of_form.assign(n, 0);
     for (size_t r = 0; r < n; ++r) O.row_of_form[ord[r]] = (uint32_t)r;
-    PeptideTable S;     // temp sorted copy for upload
-    S.seqs = T.seqs; S.forms.resize(n);
-    for (size_t r = 0; r < n; ++r) S.forms[r] = T.forms[ord[r]];
-    std::swap(S.rows, T.rows); std::swap(S.mass, T.mass); std::swap(S.pred, T.pred);
-    int32_t rc = upload_table(ctx, S);
-    std::swap(S.rows, T.rows); std::swap(S.mass, T.mass); std::swap(S.pred, T.pred);
-    T.h_mass = S.h_mass;    // sorted masses (row order)
-    if (rc) return rc;
-    mk.mark("encode + upload");
+    // all host work first, one batch of uploads and one synchronisation at the end: called from pq_load_spectra this runs
+    // while the peaks are still crossing PCIe
+    std::vector<uint8_t> rows(n * kRowBytes);
+    T.h_mass.resize(n);     // sorted masses (row order)
+    for (size_t r = 0; r < n; ++r) {
+        const FormRec& f = T.forms[ord[r]];
+        if (!ctx->codes.encode_row(T.seqs[(size_t)f.seq], f, rows.data() + r * kRowBytes)) {
+            O.form_of_row.clear(); O.row_of_form.clear();
+            return fail(ctx, PQ_ERR_UNSUPPORTED, "peptide form cannot be encoded (length > 60 or two modifications on one site): " + T.seqs[(size_t)f.seq]);
+        }
+        T.h_mass[r] = f.mass;
+    }
+    mk.mark("encode");
     // side arrays of the device pipeline (K7): row -> public form, form -> sequence, the form's modification list,
     // rank of "sequence|modification" among the forms (RankPSMCompare's last tie-break), the target letters
     const size_t nseq = T.seqs.size();
@@ -645,6 +665,15 @@ int32_t finalize_targets(pq_ctx* ctx) {
     CU(ctx->t_strrank.reserve(std::max<size_t>(n * 4, 64))); CU(ctx->t_form_mods.reserve(std::max<size_t>(n * sizeof(FormMods), 64)));
     CU(ctx->t_seq_off.reserve((nseq + 1) * 4)); CU(ctx->t_seq_letters.reserve(std::max<size_t>(letters.size(), 64)));
     cudaStream_t st = ctx->st;
+    CU(T.rows.reserve(std::max<size_t>(rows.size(), 64)));
+    CU(T.mass.reserve(std::max<size_t>(n * 8, 64)));
+    CU(cudaMemcpyAsync(T.rows.p, rows.data(), rows.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(T.mass.p, T.h_mass.data(), n * 8, cudaMemcpyHostToDevice, st));
+    if (ctx->P.score_method == 2 && n > 0) {
+        CU(T.pred.reserve(n * 8));
+        ctx->cnt.other_kernel_launches += (uint64_t)launch_predict(T.rows.as<uint8_t>(), (uint32_t)n, ctx->d_mods.as<ModTable>(), ctx->P.itol, T.pred.as<int32_t>(), st);
+    }
+    ctx->cnt.h2d_bytes += rows.size() + n * 8;
     CU(cudaMemcpyAsync(ctx->t_form_of_row.p, O.form_of_row.data(), n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->t_seq_of_form.p, seq_of_form.data(), n * 4, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->t_strrank.p, strrank.data(), n * 4, cudaMemcpyHostToDevice, st));
@@ -662,6 +691,7 @@ extern "C" {
 int32_t pq_get_target_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int64_t* n_forms) {
     if (!ctx || !n_forms) return PQ_ERR_BAD_ARG;
     PeptideTable& T = ctx->targets;
+    ensure_forms(ctx);
     *n_forms = (int64_t)T.forms.size();
     if (!out) return PQ_OK;
     if (capacity < *n_forms) return fail(ctx, PQ_ERR_CAPACITY, "form buffer too small");
