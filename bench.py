@@ -367,9 +367,10 @@ def main():
 
         def e2e_step():
             g.set_targets(*tgt)                    # the reference's order: targets (Step 1) before the spectra are read
-            g.load_spectra(sp)                     # H2D of the pinned CSR arrays + packing; K0 and the target table under the upload
+            g.stage_reference(*prot)               # H2D of the proteins (the database is known from the command line)
+            g.load_spectra(sp)                     # H2D of the pinned CSR arrays + packing; K0, the target table and the digest under the upload
             g.step2()
-            g.build_reference(*prot)               # H2D of the proteins; digest + form expansion + mass sort on the device (K6)
+            g.build_reference()                    # isoform expansion inside the matched-spectra mass window + mass sort (K6)
             g.step3(); g.step4()
             gather_psms()                          # rank/accept + D2H of the result records
 

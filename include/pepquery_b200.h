@@ -208,6 +208,11 @@ int32_t pq_get_target_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int64_t
  * mass-sorted device table with 0.1-Da buckets.  Call after pq_step2 (the mass window is taken from the
  * matched spectra, GeneratePeptideformWorker.set_mass_range). */
 int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* seq_offset /* n+1 */, const char* residues);
+/* Optional: hand the protein database over early (any time before pq_build_reference).  The bytes go to the device at once; the
+ * part of the index build that does not depend on the spectra — digestion, unique sequences, minus the targets
+ * (DatabaseInput.protein_digest :402-478) — then runs inside the next pq_load_spectra, beside the upload of the peaks, and
+ * pq_build_reference(ctx, 0, NULL, NULL) only expands the isoforms inside the matched-spectra mass window.  Same table. */
+int32_t pq_stage_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* seq_offset /* n+1 */, const char* residues);
 int32_t pq_get_reference_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int64_t* n_forms);
 
 /* Step 2.  Replaces FindCandidateSpectraAndScoreWorker.run (pg/FindCandidateSpectraAndScoreWorker.java:33-100):

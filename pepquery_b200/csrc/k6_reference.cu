@@ -171,6 +171,8 @@ __device__ __forceinline__ uint64_t sites_of(const ExpandCfg& C, int m, const ui
 }
 
 // FILL = false: count the forms of each unique sequence inside the mass window; FILL = true: write them.
+__global__ void k6_set_u32(uint32_t* p, uint32_t v) { *p = v; }
+
 template <bool FILL>
 __global__ void k6_expand(const uint32_t* __restrict__ uniq, uint32_t n_uniq, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ len,
                           const uint8_t* __restrict__ res, ExpandCfg C, uint32_t* __restrict__ count, const uint32_t* __restrict__ form_off,
@@ -274,23 +276,62 @@ template <class F> bool select_flagged(const uint8_t* flags, uint32_t n, uint32_
 
 }  // namespace
 
-bool build_reference_on_device(cudaStream_t st, const pq_params& P, const Codes& codes, int32_t n_proteins, const uint64_t* off, const char* res,
-                               const std::vector<std::string>& targets, double lo, double hi, RefDeviceTable& T, uint64_t* launches, std::string& err) {
-    // ---- residues: H2D as they are, normalised and compacted on the device (DigestProteinWorker.java:66-70) ----
+// Work buffers of the build (RefDeviceTable::w), by role
+#define K6_BUFFERS(T) \
+    DevBuf& d_first = T.w[0]; DevBuf& d_start = T.w[1]; DevBuf& d_flags = T.w[2]; DevBuf& d_cnt = T.w[3]; DevBuf& d_cand = T.w[4]; DevBuf& d_keys = T.w[5]; \
+    DevBuf& d_tmpkey = T.w[6]; DevBuf& d_tmpkey2 = T.w[7]; DevBuf& d_perm = T.w[8]; DevBuf& d_perm2 = T.w[9]; DevBuf& d_tk = T.w[10]; DevBuf& d_count = T.w[11]; \
+    DevBuf& d_foff = T.w[12]; DevBuf& d_rows = T.w[13]; DevBuf& d_mass = T.w[14]; DevBuf& d_seq = T.w[15]; DevBuf& d_mkey = T.w[16]; DevBuf& d_mkey2 = T.w[17]; \
+    DevBuf& d_idx = T.w[18]; DevBuf& d_idx2 = T.w[19]; DevBuf& tmp = T.w[20]; DevBuf& d_raw = T.w[21]; DevBuf& d_norm = T.w[22]; DevBuf& d_keep = T.w[23]; \
+    DevBuf& d_pos = T.w[24]; DevBuf& d_off = T.w[25]; \
+    (void)d_first; (void)d_start; (void)d_flags; (void)d_cnt; (void)d_cand; (void)d_keys; (void)d_tmpkey; (void)d_tmpkey2; (void)d_perm; (void)d_perm2; (void)d_tk; \
+    (void)d_count; (void)d_foff; (void)d_rows; (void)d_mass; (void)d_seq; (void)d_mkey; (void)d_mkey2; (void)d_idx; (void)d_idx2; (void)tmp; (void)d_raw; (void)d_norm; \
+    (void)d_keep; (void)d_pos; (void)d_off;
+
+// Part 0: the raw protein bytes and offsets to the device (they are normalised there, DigestProteinWorker.java:66-70).
+// Sorted, unique 240-bit keys of the target sequences (the digest removes them, DatabaseInput.java:480-488).  A host-to-device
+// copy, so it is issued before the spectrum upload is queued, not from inside the digest.
+bool upload_target_keys_for_reference(cudaStream_t st, const std::vector<std::string>& targets, RefDeviceTable& T, std::string& err) {
+    std::vector<uint64_t> tk;
+    std::vector<std::string> ts(targets);
+    std::sort(ts.begin(), ts.end());
+    ts.erase(std::unique(ts.begin(), ts.end()), ts.end());
+    for (const std::string& s : ts) {
+        uint64_t k[kKeyWords] = {0, 0, 0, 0};
+        if (s.size() > 48) continue;
+        for (size_t r = 0; r < s.size(); ++r) k[r / 12] |= (uint64_t)(s[r] - 'A' + 1) << (59 - 5 * (r % 12));
+        for (int w = 0; w < kKeyWords; ++w) tk.push_back(k[w]);
+    }
+    T.n_tkeys = (uint32_t)(tk.size() / kKeyWords);
+    DevBuf& d_tk = T.w[10];
+    RB(d_tk.reserve(tk.size() * 8 + 64));
+    if (T.n_tkeys) RB(cudaMemcpyAsync(d_tk.p, tk.data(), tk.size() * 8, cudaMemcpyHostToDevice, st));
+    RB(cudaStreamSynchronize(st));
+    return true;
+}
+
+bool upload_proteins_for_reference(cudaStream_t st, int32_t n_proteins, const uint64_t* off, const char* res, RefDeviceTable& T, std::string& err) {
     uint64_t total = n_proteins ? off[n_proteins] : 0;
     if (total >= 0x7fffff00ull) { err = "protein database too large for one table"; return false; }
-    T.n_forms = 0; T.n_unique = 0;
+    T.n_forms = 0; T.n_unique = 0; T.n_raw = (uint32_t)total; T.n_proteins = n_proteins;
     if (total == 0) return true;
-    const uint32_t n_raw = (uint32_t)total;
-    DevBuf& d_first = T.w[0]; DevBuf& d_start = T.w[1]; DevBuf& d_flags = T.w[2]; DevBuf& d_cnt = T.w[3]; DevBuf& d_cand = T.w[4]; DevBuf& d_keys = T.w[5];
-    DevBuf& d_tmpkey = T.w[6]; DevBuf& d_tmpkey2 = T.w[7]; DevBuf& d_perm = T.w[8]; DevBuf& d_perm2 = T.w[9]; DevBuf& d_tk = T.w[10]; DevBuf& d_count = T.w[11];
-    DevBuf& d_foff = T.w[12]; DevBuf& d_rows = T.w[13]; DevBuf& d_mass = T.w[14]; DevBuf& d_seq = T.w[15]; DevBuf& d_mkey = T.w[16]; DevBuf& d_mkey2 = T.w[17];
-    DevBuf& d_idx = T.w[18]; DevBuf& d_idx2 = T.w[19]; DevBuf& tmp = T.w[20]; DevBuf& d_raw = T.w[21]; DevBuf& d_norm = T.w[22]; DevBuf& d_keep = T.w[23];
-    DevBuf& d_pos = T.w[24]; DevBuf& d_off = T.w[25];
-    RB(d_raw.reserve(n_raw)); RB(d_norm.reserve(n_raw)); RB(d_keep.reserve(n_raw)); RB(d_pos.reserve(((size_t)n_raw + 1) * 4)); RB(d_off.reserve(((size_t)n_proteins + 1) * 8));
-    RB(T.residues.reserve(n_raw)); RB(d_first.reserve(n_raw)); RB(d_start.reserve(n_raw)); RB(d_cnt.reserve(64));
-    RB(cudaMemcpyAsync(d_raw.p, res, n_raw, cudaMemcpyHostToDevice, st));
+    K6_BUFFERS(T)
+    RB(d_raw.reserve(T.n_raw)); RB(d_off.reserve(((size_t)n_proteins + 1) * 8));
+    RB(cudaMemcpyAsync(d_raw.p, res, T.n_raw, cudaMemcpyHostToDevice, st));
     RB(cudaMemcpyAsync(d_off.p, off, ((size_t)n_proteins + 1) * 8, cudaMemcpyHostToDevice, st));
+    RB(cudaStreamSynchronize(st));            // the caller's buffers are free again
+    return true;
+}
+
+// Part 1: digest, unique sequences, minus the targets -> T.uniq / T.n_unique.  Independent of the spectra, so it can run while
+// they are still being uploaded (any stream; synchronised at return).
+bool digest_reference_on_device(cudaStream_t st, const pq_params& P, const Codes& codes, const std::vector<std::string>& targets, RefDeviceTable& T,
+                                uint64_t* launches, std::string& err) {
+    T.n_forms = 0; T.n_unique = 0;
+    if (T.n_raw == 0) return true;
+    const uint32_t n_raw = T.n_raw; const int32_t n_proteins = T.n_proteins;
+    K6_BUFFERS(T)
+    RB(d_norm.reserve(n_raw)); RB(d_keep.reserve(n_raw)); RB(d_pos.reserve(((size_t)n_raw + 1) * 4));
+    RB(T.residues.reserve(n_raw)); RB(d_first.reserve(n_raw)); RB(d_start.reserve(n_raw)); RB(d_cnt.reserve(64));
     k6_normalise<<<(n_raw + 255) / 256, 256, 0, st>>>(d_raw.as<uint8_t>(), n_raw, d_norm.as<uint8_t>(), d_keep.as<uint8_t>());
     {
         size_t bytes = 0;
@@ -317,7 +358,7 @@ bool build_reference_on_device(cudaStream_t st, const pq_params& P, const Codes&
     uint32_t n_seg = 0;
     RB(cudaMemcpyAsync(&n_seg, d_cnt.p, 4, cudaMemcpyDeviceToHost, st));
     RB(cudaStreamSynchronize(st));
-    RB(cudaMemcpyAsync(T.starts.as<uint32_t>() + n_seg, &n, 4, cudaMemcpyHostToDevice, st));
+    k6_set_u32<<<1, 1, 0, st>>>(T.starts.as<uint32_t>() + n_seg, n);          // (no host-to-device copy here: the copy engine may be busy with the spectra)
     // candidate peptides
     const uint32_t per = (uint32_t)P.max_missed + 1;
     const uint64_t n_slots64 = (uint64_t)n_seg * per;
@@ -352,22 +393,8 @@ bool build_reference_on_device(cudaStream_t st, const pq_params& P, const Codes&
         }
         if (pa != d_perm.as<uint32_t>()) RB(cudaMemcpyAsync(d_perm.p, pa, (size_t)n_cand * 4, cudaMemcpyDeviceToDevice, st));
     }
-    // target keys (sorted) for the set difference
-    std::vector<uint64_t> tk;
-    {
-        std::vector<std::string> ts(targets);
-        std::sort(ts.begin(), ts.end());
-        ts.erase(std::unique(ts.begin(), ts.end()), ts.end());
-        for (const std::string& s : ts) {
-            uint64_t k[kKeyWords] = {0, 0, 0, 0};
-            if (s.size() > 48) continue;
-            for (size_t r = 0; r < s.size(); ++r) k[r / 12] |= (uint64_t)(s[r] - 'A' + 1) << (59 - 5 * (r % 12));
-            for (int w = 0; w < kKeyWords; ++w) tk.push_back(k[w]);
-        }
-    }
-    const uint32_t n_t = (uint32_t)(tk.size() / kKeyWords);
-    RB(d_tk.reserve(tk.size() * 8 + 64));
-    if (n_t) RB(cudaMemcpyAsync(d_tk.p, tk.data(), tk.size() * 8, cudaMemcpyHostToDevice, st));
+    const uint32_t n_t = T.n_tkeys;          // uploaded by upload_target_keys_for_reference
+    (void)targets;
     RB(d_flags.reserve((size_t)n_cand + 64)); RB(T.uniq.reserve(((size_t)n_cand + 2) * 4));
     k6_unique_flags<<<(n_cand + 255) / 256, 256, 0, st>>>(d_perm.as<uint32_t>(), d_keys.as<uint64_t>(), n_cand, d_tk.as<uint64_t>(), n_t, d_flags.as<uint8_t>());
     // uniq[] must hold candidate ids (perm values), not positions: select over the perm array
@@ -382,7 +409,18 @@ bool build_reference_on_device(cudaStream_t st, const pq_params& P, const Codes&
     RB(cudaStreamSynchronize(st));
     *launches += 4;
     T.n_unique = n_uniq;
+    return true;
+}
+
+// Part 2: isoforms of the unique sequences inside the mass window of the matched spectra, mass-sorted rows.
+bool expand_reference_on_device(cudaStream_t st, const pq_params& P, const Codes& codes, double lo, double hi, RefDeviceTable& T, uint64_t* launches,
+                                std::string& err) {
+    (void)P;
+    T.n_forms = 0;
+    const uint32_t n_uniq = T.n_unique;
     if (n_uniq == 0) return true;
+    K6_BUFFERS(T)
+    const uint8_t* d_res = T.residues.as<uint8_t>();
     // forms
     ExpandCfg ec; memset(&ec, 0, sizeof ec);
     ec.n_var = codes.n_var; ec.n_fixed = codes.n_fixed; ec.max_var = codes.max_var; ec.lo = lo; ec.hi = hi;
@@ -426,6 +464,13 @@ bool build_reference_on_device(cudaStream_t st, const pq_params& P, const Codes&
     RB(cudaGetLastError());
     *launches += 8;
     return true;
+}
+
+bool build_reference_on_device(cudaStream_t st, const pq_params& P, const Codes& codes, int32_t n_proteins, const uint64_t* off, const char* res,
+                               const std::vector<std::string>& targets, double lo, double hi, RefDeviceTable& T, uint64_t* launches, std::string& err) {
+    return upload_proteins_for_reference(st, n_proteins, off, res, T, err) && upload_target_keys_for_reference(st, targets, T, err) &&
+           digest_reference_on_device(st, P, codes, targets, T, launches, err) &&
+           expand_reference_on_device(st, P, codes, lo, hi, T, launches, err);
 }
 
 }  // namespace pq

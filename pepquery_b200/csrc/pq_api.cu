@@ -59,7 +59,7 @@ struct pq_ctx {
     pq_params P;
     Codes codes;
     std::string err;
-    cudaStream_t st = nullptr, st_copy = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr, st_aux = nullptr;
     std::vector<cudaEvent_t> chunk_ev;       // one per upload chunk of pq_load_spectra
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, uev0 = nullptr, uev1 = nullptr;
     void* stage_host = nullptr; cudaEvent_t stage_ev[2] = {nullptr, nullptr};
@@ -88,6 +88,7 @@ struct pq_ctx {
     PeptideTable targets, reference;
     TargetOrder order;
     bool have_targets = false, have_reference = false, forms_expanded = false;
+    bool ref_staged = false, ref_digested = false;      // pq_stage_reference: proteins on the device / digest done (valid for the current targets)
     int step_done = 0;
     // work buffers
     DevBuf jobs, jobs2, results, hits, hit_count, njobs;
@@ -129,6 +130,7 @@ struct Timer {
 void flush_timers(pq_ctx* c);
 int32_t finalize_targets(pq_ctx* ctx);
 void ensure_forms(pq_ctx* ctx);
+int32_t digest_staged_reference(pq_ctx* ctx, cudaStream_t st, bool count_time = true);
 
 Timer::Timer(pq_ctx* c_, double* t, double* t2) : c(c_), acc(t), acc2(t2) {
     auto get = [&]() { cudaEvent_t e; if (!c->free_events.empty()) { e = c->free_events.back(); c->free_events.pop_back(); } else cudaEventCreate(&e); return e; };
@@ -333,7 +335,8 @@ int32_t pq_create(const pq_params* params, pq_ctx** out) {
     std::string err;
     if (!ctx->codes.init(*params, err)) { delete ctx; return fail(nullptr, PQ_ERR_UNSUPPORTED, err); }
     if (cudaSetDevice(params->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->st_aux, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx; return fail(nullptr, PQ_ERR_CUDA, "cannot initialise device");
     }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->uev0); cudaEventCreate(&ctx->uev1);
@@ -366,10 +369,11 @@ int32_t pq_destroy(pq_ctx* ctx) {
     if (ctx->uev0) cudaEventDestroy(ctx->uev0);
     if (ctx->uev1) cudaEventDestroy(ctx->uev1);
     for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
-    cudaStream_t st = ctx->st, st_copy = ctx->st_copy;
+    cudaStream_t st = ctx->st, st_copy = ctx->st_copy, st_aux = ctx->st_aux;
     delete ctx;
     if (st) cudaStreamDestroy(st);
     if (st_copy) cudaStreamDestroy(st_copy);
+    if (st_aux) cudaStreamDestroy(st_aux);
     return PQ_OK;
 }
 
@@ -479,6 +483,12 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
         CU(cudaMemsetAsync(counts + n, 0, 8, st));
         int32_t rc = scan_exclusive(ctx, counts, ctx->s_off.as<uint64_t>(), (int)n + 1);
         if (rc) return rc;
+        // the target keys of a staged reference digest go up before the copy engine fills with spectra
+        const bool digest_here = ctx->ref_staged && !ctx->ref_digested && ctx->have_targets;
+        if (digest_here) {
+            std::string err;
+            if (!upload_target_keys_for_reference(st, ctx->targets.seqs, ctx->reference.dev, err)) return fail(ctx, PQ_ERR_CUDA, "reference digest: " + err);
+        }
         // The peak copies are queued only now: queued ahead of the kernels above they held those kernels back until the last
         // chunk had landed (measured: 60 ms per load instead of 36 ms), so the small precursor work goes first.
         rc = enqueue_copies();
@@ -522,6 +532,9 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
         ctx->cnt.other_kernel_launches += (uint64_t)k + 4;
     }
     CU(cudaGetLastError());
+    // a protein database staged before the spectra (pq_stage_reference): its digest does not depend on them and runs now, on a
+    // third stream, beside the chunk work above
+    if (ctx->ref_staged && !ctx->ref_digested && ctx->have_targets) { int32_t rc = digest_staged_reference(ctx, ctx->st_aux); if (rc) return rc; }
     // targets given before the spectra: their expansion, sort and encoding (host work) overlap the upload
     if (ctx->have_targets) { int32_t rc = finalize_targets(ctx); if (rc) return rc; }
     CU(cudaStreamSynchronize(st));
@@ -548,7 +561,7 @@ int32_t pq_set_targets(pq_ctx* ctx, int32_t n_seq, const uint32_t* off, const ch
     }
     // The isoform expansion, the mass-sorted device table and its side arrays are host work that the next pq_load_spectra
     // (while the peaks cross PCIe) or, failing that, pq_step2_match_targets does: finalize_targets().
-    ctx->forms_expanded = false; ctx->cnt.target_forms = 0;
+    ctx->forms_expanded = false; ctx->cnt.target_forms = 0; ctx->ref_digested = false;     // the digest is 'minus the targets'
     ctx->order.form_of_row.clear(); ctx->order.row_of_form.clear();
     ctx->have_targets = true; ctx->step_done = 0; reset_psm_state(ctx);
     return PQ_OK;
@@ -824,15 +837,51 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+bool device_reference_path(const pq_ctx* ctx) { return ctx->P.max_len <= 48 && !getenv("PQ_HOST_REFERENCE"); }
+
+// digest of the staged proteins (K6 part 1) on stream st; synchronised at return
+int32_t digest_staged_reference(pq_ctx* ctx, cudaStream_t st, bool count_time) {
+    auto t_begin = std::chrono::steady_clock::now();
+    PeptideTable& R = ctx->reference;
+    std::string err; uint64_t launches = 0;
+    if (!digest_reference_on_device(st, ctx->P, ctx->codes, ctx->targets.seqs, R.dev, &launches, err)) return fail(ctx, PQ_ERR_CUDA, "reference digest: " + err);   // (target keys already uploaded)
+    ctx->cnt.other_kernel_launches += launches;
+    ctx->ref_digested = true;
+    if (count_time) ctx->cnt.ms_host_reference += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return PQ_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int32_t pq_stage_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off, const char* res) {
+    if (!ctx || n_proteins < 0 || (n_proteins > 0 && (!off || !res))) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
+    if (!device_reference_path(ctx)) return fail(ctx, PQ_ERR_UNSUPPORTED, "pq_stage_reference needs the device-built reference table (max_len <= 48)");
+    cudaSetDevice(ctx->P.device);
+    auto t_begin = std::chrono::steady_clock::now();
+    ctx->ref_staged = false; ctx->ref_digested = false; ctx->have_reference = false;
+    std::string err;
+    if (!upload_proteins_for_reference(ctx->st, n_proteins, off, res, ctx->reference.dev, err)) return fail(ctx, PQ_ERR_CUDA, "reference upload: " + err);
+    ctx->cnt.h2d_bytes += (n_proteins ? off[n_proteins] : 0) + ((uint64_t)n_proteins + 1) * 8;
+    ctx->ref_staged = true;
+    ctx->cnt.ms_host_reference += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return PQ_OK;
+}
+
 int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off, const char* res) {
     if (!ctx || n_proteins < 0 || (n_proteins > 0 && (!off || !res))) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
     if (ctx->step_done < 2) return fail(ctx, PQ_ERR_STATE, "pq_step2_match_targets first (the reference mass window comes from the matched spectra)");
+    const bool use_staged = n_proteins == 0 && !off && !res && ctx->ref_staged;      // the database handed over by pq_stage_reference
     cudaSetDevice(ctx->P.device);
     PeptideTable& R = ctx->reference;
     R.seqs.clear(); R.forms.clear(); R.have_mask = false; R.device_built = false; R.materialized = true;
     auto t_begin = std::chrono::steady_clock::now();
     Marks mk("build_reference");
-    if (ctx->P.max_len <= 48 && !getenv("PQ_HOST_REFERENCE")) {
+    if (!use_staged) { ctx->ref_staged = false; ctx->ref_digested = false; }
+    if (device_reference_path(ctx)) {
         // device path (K6): digest, unique, form expansion and the mass sort all run on the GPU
         double mn = 1.7976931348623157e308, mx = 0.0;      // GeneratePeptideformWorker.set_mass_range (:40-52)
         if (ctx->n_psm) { mn = ctx->psm_mass_lo; mx = ctx->psm_mass_hi; }
@@ -840,23 +889,29 @@ int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off,
         R.dev.rows = &R.rows; R.dev.mass = &R.mass;
         std::string err;
         uint64_t launches = 0;
-        if (!build_reference_on_device(ctx->st, ctx->P, ctx->codes, n_proteins, off, res, ctx->targets.seqs, lo, hi, R.dev, &launches, err))
-            return fail(ctx, PQ_ERR_CUDA, "reference build: " + err);
+        if (use_staged) {
+            if (!ctx->ref_digested) {
+                if (!upload_target_keys_for_reference(ctx->st, ctx->targets.seqs, R.dev, err)) return fail(ctx, PQ_ERR_CUDA, "reference digest: " + err);
+                int32_t rc = digest_staged_reference(ctx, ctx->st, false); if (rc) return rc;
+            }
+            if (!expand_reference_on_device(ctx->st, ctx->P, ctx->codes, lo, hi, R.dev, &launches, err)) return fail(ctx, PQ_ERR_CUDA, "reference build: " + err);
+        } else {
+            if (!build_reference_on_device(ctx->st, ctx->P, ctx->codes, n_proteins, off, res, ctx->targets.seqs, lo, hi, R.dev, &launches, err))
+                return fail(ctx, PQ_ERR_CUDA, "reference build: " + err);
+            ctx->cnt.h2d_bytes += (n_proteins ? off[n_proteins] : 0) + ((uint64_t)n_proteins + 1) * 8;
+        }
         ctx->cnt.other_kernel_launches += launches;
-        ctx->cnt.h2d_bytes += (n_proteins ? off[n_proteins] : 0) * 2;
         R.device_built = true; R.materialized = false; R.n_rows = R.dev.n_forms;
         mk.mark("device build");
-        R.h_mass.resize(R.n_rows);
+        R.h_mass.clear();                 // the host copy of the masses is pulled by pq_get_reference_forms when it is asked for
         if (R.n_rows) {
-            CU(cudaMemcpyAsync(R.h_mass.data(), R.mass.p, R.n_rows * 8, cudaMemcpyDeviceToHost, ctx->st));
             if (ctx->P.score_method == 2) {
                 CU(R.pred.reserve(R.n_rows * 8));
                 ctx->cnt.other_kernel_launches += (uint64_t)launch_predict(R.rows.as<uint8_t>(), (uint32_t)R.n_rows, ctx->d_mods.as<ModTable>(), ctx->P.itol, R.pred.as<int32_t>(), ctx->st);
             }
             CU(cudaStreamSynchronize(ctx->st));
-            ctx->cnt.d2h_bytes += R.n_rows * 8;
         }
-        mk.mark("mass d2h");
+        mk.mark("predicted peaks");
         ctx->cnt.reference_sequences = R.dev.n_unique; ctx->cnt.reference_forms = R.n_rows;
         ctx->cnt.ms_host_reference += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         ctx->have_reference = true;
@@ -915,6 +970,11 @@ int32_t pq_get_reference_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int6
         const size_t n = T.n();
         if (!n) return PQ_OK;
         std::vector<uint8_t> rows(n * kRowBytes); std::vector<uint32_t> sid(n);
+        if (T.h_mass.size() != n) {
+            T.h_mass.resize(n);
+            CU(cudaMemcpyAsync(T.h_mass.data(), T.mass.p, n * 8, cudaMemcpyDeviceToHost, ctx->st));
+            ctx->cnt.d2h_bytes += n * 8;
+        }
         CU(cudaMemcpyAsync(rows.data(), T.rows.p, rows.size(), cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaMemcpyAsync(sid.data(), T.dev.seq_id.p, n * 4, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));

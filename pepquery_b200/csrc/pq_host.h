@@ -61,8 +61,15 @@ struct RefDeviceTable {
     DevBuf residues, starts, cand_pos, cand_len, uniq, seq_id;   // normalised proteins, segment starts, candidate (pos,len), unique candidate ids (lexicographic), parent id per form
     DevBuf* rows = nullptr; DevBuf* mass = nullptr;
     DevBuf w[26];                       // work buffers of the build, kept so that a rebuild allocates nothing
-    uint32_t n_unique = 0, n_forms = 0;
+    uint32_t n_unique = 0, n_forms = 0, n_raw = 0, n_tkeys = 0; int32_t n_proteins = 0;
 };
+// the three parts of build_reference_on_device (k6_reference.cu): upload, digest (independent of the spectra), expansion
+bool upload_target_keys_for_reference(cudaStream_t st, const std::vector<std::string>& targets, RefDeviceTable& T, std::string& err);
+bool upload_proteins_for_reference(cudaStream_t st, int32_t n_proteins, const uint64_t* off, const char* res, RefDeviceTable& T, std::string& err);
+bool digest_reference_on_device(cudaStream_t st, const pq_params& P, const Codes& codes, const std::vector<std::string>& targets, RefDeviceTable& T,
+                                uint64_t* launches, std::string& err);
+bool expand_reference_on_device(cudaStream_t st, const pq_params& P, const Codes& codes, double lo, double hi, RefDeviceTable& T, uint64_t* launches,
+                                std::string& err);
 bool build_reference_on_device(cudaStream_t st, const pq_params& P, const Codes& codes, int32_t n_proteins, const uint64_t* off, const char* res,
                                const std::vector<std::string>& targets, double lo, double hi, RefDeviceTable& T, uint64_t* launches, std::string& err);
 

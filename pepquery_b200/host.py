@@ -55,7 +55,7 @@ def load_library():
 
 # every symbol include/pepquery_b200.h declares
 EXPORTS = ["pq_version", "pq_last_error", "pq_default_params", "pq_create", "pq_destroy", "pq_load_spectra",
-           "pq_set_targets", "pq_get_target_forms", "pq_build_reference", "pq_get_reference_forms",
+           "pq_set_targets", "pq_get_target_forms", "pq_build_reference", "pq_stage_reference", "pq_get_reference_forms",
            "pq_step2_match_targets", "pq_step3_competitors", "pq_step4_shuffles", "pq_rank_and_validate",
            "pq_step5_ptm", "pq_get_psms", "pq_get_delta_scores", "pq_export_psms_device", "pq_get_competitors", "pq_get_shuffles", "pq_score_pairs",
            "pq_find_in_proteome", "pq_get_counters", "pq_reset_counters", "pq_event_record", "pq_event_elapsed_ms", "pq_parse_mgf"]
@@ -137,8 +137,15 @@ class Search:
     def reference_forms(self):
         return self._forms(self.L.pq_get_reference_forms)
 
-    def build_reference(self, off, res):
-        self._ck(self.L.pq_build_reference(self.h, C.c_int32(len(off) - 1), _p(off), _p(res)))
+    def build_reference(self, off=None, res=None):
+        """off/res = None: the database handed over earlier by stage_reference()."""
+        if off is None:
+            self._ck(self.L.pq_build_reference(self.h, C.c_int32(0), None, None))
+        else:
+            self._ck(self.L.pq_build_reference(self.h, C.c_int32(len(off) - 1), _p(off), _p(res)))
+
+    def stage_reference(self, off, res):
+        self._ck(self.L.pq_stage_reference(self.h, C.c_int32(len(off) - 1), _p(off), _p(res)))
 
     def step2(self):
         n = C.c_int64()

@@ -721,3 +721,27 @@ def test_novelty_filter_full_size_properties():
     want = np.array(want, dtype=np.int32)
     assert np.array_equal(got[want == 1], want[want == 1])
     assert got[want == 0].sum() <= 2                                   # a doubled, mutated sequence occurring by chance is (nearly) impossible
+
+
+@pytest.mark.parametrize("order", ["stage,targets,load", "targets,stage,load", "targets,load,stage"])
+def test_staged_reference_gives_the_same_table(data, order):
+    """pq_stage_reference: the digest runs inside pq_load_spectra (beside the upload) when the targets are known by then,
+    otherwise inside pq_build_reference(NULL); the table, the detail rows and the PSMs equal the one-call build."""
+    prot, tgt, sp = data
+    p = _abi.default_params(n_random=50)
+    ref = run_gpu(p, sp, tgt, prot)
+    g = Search(p)
+    for what in order.split(","):
+        {"stage": lambda: g.stage_reference(*prot), "targets": lambda: g.set_targets(*tgt), "load": lambda: g.load_spectra(sp)}[what]()
+    g.step2(); g.build_reference(); g.step3(); g.step4(); g.rank()
+    assert g.psms().tobytes() == ref.psms().tobytes()
+    ra, na = ref.reference_forms(); rb, nb = g.reference_forms()
+    assert na == nb and bytes(ra)[:na * C.sizeof(_abi.pq_form)] == bytes(rb)[:nb * C.sizeof(_abi.pq_form)]
+    assert np.sort(ref.competitors(3), order=["spectrum", "ref_form"]).tobytes() == np.sort(g.competitors(3), order=["spectrum", "ref_form"]).tobytes()
+    # new targets invalidate the digest (it is "minus the targets"); a second search on the same context still matches
+    tgt2 = synth.targets(30, seed=12345)
+    g.set_targets(*tgt2); g.load_spectra(sp); g.step2(); g.build_reference(); g.step3(); g.rank()
+    ref2 = run_gpu(p, sp, tgt2, prot, steps=3)
+    assert g.psms().tobytes() == ref2.psms().tobytes()
+    c = g.counters(); c2 = ref2.counters()
+    assert c.reference_forms == c2.reference_forms and c.reference_sequences == c2.reference_sequences
