@@ -160,12 +160,15 @@ __global__ void k7_gather_comp(const pq_competitor* __restrict__ in, const uint3
 }
 
 __global__ void k7_flag_valid(const DevPsm* __restrict__ psms, uint32_t n, const int32_t* __restrict__ seq_of_form, uint8_t* __restrict__ seq_flag,
-                              uint8_t* __restrict__ form_flag, uint8_t* __restrict__ valid_flag) {
+                              uint8_t* __restrict__ form_flag, uint8_t* __restrict__ valid_flag, uint32_t* __restrict__ n_valid) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int v = psms[i].valid;
-    valid_flag[i] = v ? 1 : 0;
-    if (v) { int32_t f = psms[i].form; form_flag[f] = 1; seq_flag[seq_of_form[f]] = 1; }
+    const int v = i < n ? psms[i].valid : 0;
+    if (i < n) {
+        valid_flag[i] = v ? 1 : 0;
+        if (v) { int32_t f = psms[i].form; form_flag[f] = 1; seq_flag[seq_of_form[f]] = 1; }
+    }
+    const uint32_t b = __ballot_sync(0xffffffffu, v != 0);             // still-valid PSMs, one atomic per warp
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_valid, (uint32_t)__popc(b));
 }
 
 __device__ unsigned long long choose_u64(int n, int k) {
@@ -256,13 +259,8 @@ k7_shuffle_layout(const uint8_t* __restrict__ seq_flag, const uint8_t* __restric
         if (threadIdx.x == 0) carry = make_uint2(c.x + tot.x, c.y + tot.y);
         __syncthreads();
     }
-    if (threadIdx.x == 0) { totals->n_forms = carry.x; totals->out_rows = carry.y; }
-    uint32_t nv = 0;
-    for (uint32_t i = threadIdx.x; i < n_psm; i += kLayoutThreads) nv += valid_flag[i];
-    typedef cub::BlockReduce<uint32_t, kLayoutThreads> Red;
-    __shared__ typename Red::TempStorage rtmp;
-    uint32_t all = Red(rtmp).Sum(nv);
-    if (threadIdx.x == 0) totals->n_valid = all;
+    if (threadIdx.x == 0) { totals->n_forms = carry.x; totals->out_rows = carry.y; }       // totals->n_valid: counted by k7_flag_valid
+    (void)valid_flag; (void)n_psm;
 }
 
 __global__ void k7_psm_form_keys(const DevPsm* __restrict__ psms, const uint32_t* __restrict__ list, uint32_t n, uint32_t* __restrict__ keys) {
@@ -411,9 +409,10 @@ int launch_gather_comp(const pq_competitor* in, const uint32_t* idx, uint32_t n,
     k7_gather_comp<<<blocks(n), 256, 0, st>>>(in, idx, n, out);
     return 1;
 }
-int launch_flag_valid(const DevPsm* psms, uint32_t n, const int32_t* seq_of_form, uint8_t* seq_flag, uint8_t* form_flag, uint8_t* valid_flag, cudaStream_t st) {
+int launch_flag_valid(const DevPsm* psms, uint32_t n, const int32_t* seq_of_form, uint8_t* seq_flag, uint8_t* form_flag, uint8_t* valid_flag,
+                      ShuffleTotals* totals /* zeroed by the caller */, cudaStream_t st) {
     if (!n) return 0;
-    k7_flag_valid<<<blocks(n), 256, 0, st>>>(psms, n, seq_of_form, seq_flag, form_flag, valid_flag);
+    k7_flag_valid<<<blocks(n), 256, 0, st>>>(psms, n, seq_of_form, seq_flag, form_flag, valid_flag, &totals->n_valid);
     return 1;
 }
 int launch_shuffle_plans(const uint8_t* seq_flag, const TargetAux& A, int32_t n_random, ShuffleSeq* plans, cudaStream_t st) {

@@ -1064,7 +1064,9 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
     ShuffleTotals tot; memset(&tot, 0, sizeof tot);
     {
         Timer t(ctx, &ctx->cnt.ms_shuffle);
-        int k = launch_flag_valid(ctx->d_psm.as<DevPsm>(), n_psm, A.seq_of_form, ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint8_t>(), ctx->sh_valid_flag.as<uint8_t>(), st);
+        CU(cudaMemsetAsync(ctx->sh_totals.p, 0, sizeof(ShuffleTotals), st));
+        int k = launch_flag_valid(ctx->d_psm.as<DevPsm>(), n_psm, A.seq_of_form, ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint8_t>(), ctx->sh_valid_flag.as<uint8_t>(),
+                                  ctx->sh_totals.as<ShuffleTotals>(), st);
         k += launch_shuffle_plans(ctx->sh_seq_flag.as<uint8_t>(), A, ctx->P.n_random, ctx->sh_plans.as<ShuffleSeq>(), st);
         k += launch_shuffle_layout(ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint8_t>(), ctx->sh_valid_flag.as<uint8_t>(), n_psm, ctx->sh_plans.as<ShuffleSeq>(), A,
                                    ctx->sh_seq_slot.as<uint32_t>(), ctx->sh_form_slot.as<uint32_t>(), ctx->sh_row_base.as<uint32_t>(), ctx->sh_seqs.as<ShuffleSeq>(),

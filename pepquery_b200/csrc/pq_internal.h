@@ -224,7 +224,8 @@ int launch_step3_aggregate(const JobResult* res, uint32_t n_seg, int n_iso, cons
 int launch_comp3_rows(const Hit* hits, uint32_t nh, const SegAgg* agg, uint32_t n_seg, const uint32_t* seg_start, const DevPsm* psms,
                       const int32_t* caller_index, const double* r_mass, pq_competitor* rows, uint64_t* keys, uint32_t* idx, uint32_t* count, cudaStream_t st);
 int launch_gather_comp(const pq_competitor* in, const uint32_t* idx, uint32_t n, pq_competitor* out, cudaStream_t st);
-int launch_flag_valid(const DevPsm* psms, uint32_t n, const int32_t* seq_of_form, uint8_t* seq_flag, uint8_t* form_flag, uint8_t* valid_flag, cudaStream_t st);
+int launch_flag_valid(const DevPsm* psms, uint32_t n, const int32_t* seq_of_form, uint8_t* seq_flag, uint8_t* form_flag, uint8_t* valid_flag,
+                      ShuffleTotals* totals /* zeroed by the caller */, cudaStream_t st);
 int launch_shuffle_plans(const uint8_t* seq_flag, const TargetAux& A, int32_t n_random, ShuffleSeq* plans, cudaStream_t st);
 int launch_shuffle_layout(const uint8_t* seq_flag, const uint8_t* form_flag, const uint8_t* valid_flag, uint32_t n_psm, const ShuffleSeq* plans, const TargetAux& A,
                           uint32_t* seq_slot, uint32_t* form_slot, uint32_t* row_base, ShuffleSeq* seqs, ShuffleForm* forms, ShuffleTotals* totals, cudaStream_t st);
