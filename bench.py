@@ -117,6 +117,17 @@ def make_inputs(a, rank, world, pinned):
         synth.set_strips(b[:-1], world, rank)
     sp = synth.spectra(a.spectra, tgt, prot, first_index=rank * a.spectra, pinned=pinned)
     synth.set_strips(None, 1, 0)
+    if pinned is not None:
+        # every host buffer the library reads is pinned (the end-to-end arm copies "from pinned host memory"): with all five
+        # spectrum arrays pinned pq_load_spectra starts the upload at once instead of after the precursor kernels
+        def pin(arr):
+            buf = pinned((arr.nbytes + 7) // 8)                     # float64 words
+            out = buf.view(np.uint8)[:arr.nbytes].view(arr.dtype)
+            out[:] = arr
+            return out
+        for k in ("prec_mz", "charge", "peak_off"):
+            sp[k] = pin(sp[k])
+        prot = (pin(prot[0]), pin(prot[1]))
     return prot, tgt, sp
 
 

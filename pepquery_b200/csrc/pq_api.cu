@@ -61,6 +61,7 @@ struct pq_ctx {
     std::string err;
     cudaStream_t st = nullptr, st_copy = nullptr, st_aux = nullptr;
     std::vector<cudaEvent_t> chunk_ev;       // one per upload chunk of pq_load_spectra
+    cudaEvent_t meta_ev = nullptr;           // precursor arrays of pq_load_spectra on the device
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, uev0 = nullptr, uev1 = nullptr;
     void* stage_host = nullptr; cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     pq_counters cnt;
@@ -369,6 +370,7 @@ int32_t pq_destroy(pq_ctx* ctx) {
     if (ctx->uev0) cudaEventDestroy(ctx->uev0);
     if (ctx->uev1) cudaEventDestroy(ctx->uev1);
     for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
+    if (ctx->meta_ev) cudaEventDestroy(ctx->meta_ev);
     cudaStream_t st = ctx->st, st_copy = ctx->st_copy, st_aux = ctx->st_aux;
     delete ctx;
     if (st) cudaStreamDestroy(st);
@@ -417,53 +419,106 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
     if (!ctx || n < 0 || (n > 0 && (!prec_mz || !charge || !off || !mz || !inten))) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
     if (n > 0x7fffffffLL / PQ_MAX_ISOTOPE) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many spectra for one context");
     cudaSetDevice(ctx->P.device);
-    uint64_t total = n ? off[n] : 0;
-    uint32_t maxp = 0; uint64_t usable = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        if (off[i + 1] < off[i]) return fail(ctx, PQ_ERR_BAD_ARG, "peak offsets must be non-decreasing");
-        uint64_t c = off[i + 1] - off[i];
-        if (c > 4096) return fail(ctx, PQ_ERR_UNSUPPORTED, "more than 4096 peaks in one spectrum");
-        if (charge[i] < 1) return fail(ctx, PQ_ERR_BAD_ARG, "charge must be >= 1");
-        if (c > maxp) maxp = (uint32_t)c;
-        if ((int64_t)c > (int64_t)ctx->P.min_peaks) ++usable;
-    }
-    ctx->nS = n; ctx->max_peaks = maxp; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0;
-    ctx->cnt.spectra_loaded = (uint64_t)n; ctx->cnt.spectra_usable = usable;
-    if (n == 0) return PQ_OK;
+    Marks mk("load_spectra");
+    const uint64_t total = n ? off[n] : 0;
+    cudaStream_t st = ctx->st, sc = ctx->st_copy;
     // staging buffers live in the context: a reload of the same size allocates nothing
     DevBuf& in_prec = ctx->ld[0]; DevBuf& in_charge = ctx->ld[1]; DevBuf& in_off = ctx->ld[2]; DevBuf& in_mz = ctx->ld[3]; DevBuf& in_in = ctx->ld[4];
     DevBuf& in_mass = ctx->ld[5]; DevBuf& key = ctx->ld[6]; DevBuf& key2 = ctx->ld[7]; DevBuf& idx = ctx->ld[8];
-    CU(in_prec.reserve(n * 8)); CU(in_charge.reserve(n * 4)); CU(in_off.reserve((n + 1) * 8));
-    CU(in_mz.reserve(std::max<uint64_t>(total, 1) * 8)); CU(in_in.reserve(std::max<uint64_t>(total, 1) * 8));
-    CU(in_mass.reserve(n * 8)); CU(key.reserve(n * 8)); CU(key2.reserve(n * 8)); CU(idx.reserve(n * 4));
-    CU(ctx->s_prec.reserve(n * 8)); CU(ctx->s_charge.reserve(n * 4)); CU(ctx->s_mass.reserve(n * 8)); CU(ctx->s_off.reserve((n + 1) * 8));
-    CU(ctx->s_mz.reserve(std::max<uint64_t>(total, 1) * 8)); CU(ctx->s_in.reserve(std::max<uint64_t>(total, 1) * 8)); CU(ctx->s_caller.reserve(n * 4));
-    CU(ctx->scratch.reserve((n + 1) * 8));
-    cudaStream_t st = ctx->st, sc = ctx->st_copy;
-    CU(cudaMemcpyAsync(in_prec.p, prec_mz, n * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(in_charge.p, charge, n * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(in_off.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n > 0) {
+        CU(in_prec.reserve(n * 8)); CU(in_charge.reserve(n * 4)); CU(in_off.reserve((n + 1) * 8));
+        CU(in_mz.reserve(std::max<uint64_t>(total, 1) * 8)); CU(in_in.reserve(std::max<uint64_t>(total, 1) * 8));
+        CU(in_mass.reserve(n * 8)); CU(key.reserve(n * 8)); CU(key2.reserve(n * 8)); CU(idx.reserve(n * 4));
+        CU(ctx->s_prec.reserve(n * 8)); CU(ctx->s_charge.reserve(n * 4)); CU(ctx->s_mass.reserve(n * 8)); CU(ctx->s_off.reserve((n + 1) * 8));
+        CU(ctx->s_mz.reserve(std::max<uint64_t>(total, 1) * 8)); CU(ctx->s_in.reserve(std::max<uint64_t>(total, 1) * 8)); CU(ctx->s_caller.reserve(n * 4));
+        CU(ctx->scratch.reserve((n + 1) * 8));
+    }
     // The peaks cross PCIe in chunks of whole spectra (caller order) on a second stream; the compute stream follows chunk by
     // chunk: copy into the mass-sorted CSR and, with prepare_at_load, K0 for the chunk, while the next chunk is in flight.
-    std::vector<int64_t> cut; cut.push_back(0);
+    uint64_t chunk_peaks = 4u << 20;                                 // 64 MB of m/z + intensity per chunk
+    if (const char* e = getenv("PQ_LOAD_CHUNK_PEAKS")) { long long v = atoll(e); if (v > 0) chunk_peaks = (uint64_t)v; }   // tests: many small chunks
     {
-        uint64_t chunk_peaks = 4u << 20;                             // 64 MB of m/z + intensity per chunk
-        if (const char* e = getenv("PQ_LOAD_CHUNK_PEAKS")) { long long v = atoll(e); if (v > 0) chunk_peaks = (uint64_t)v; }   // tests: many small chunks
-        uint64_t next = chunk_peaks;
-        for (int64_t i = 1; i < n; ++i) if (off[i] - off[0] >= next) { cut.push_back(i); next = off[i] - off[0] + chunk_peaks; }
-        cut.push_back(n);
+        const size_t max_chunks = (size_t)(total / chunk_peaks) + 2;
+        while (ctx->chunk_ev.size() < max_chunks) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+    }
+    // Pinned caller buffers: every copy below is asynchronous, so the upload starts at once — the precursor arrays first, then
+    // each chunk of peaks as soon as the walk over the offsets (validation + chunk boundaries) has passed it.  Pageable
+    // precursor arrays are staged by the driver; kernels queued behind such a copy were seen to wait for every chunk queued
+    // in between (60 ms per load instead of 36 ms), so in that case the chunks are queued after the precursor kernels.
+    auto is_pinned = [](const void* p) { cudaPointerAttributes a; if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; } return a.type == cudaMemoryTypeHost; };
+    const bool early_copies = n > 0 && is_pinned(prec_mz) && is_pinned(charge) && is_pinned(off) && is_pinned(mz) && is_pinned(inten) && !getenv("PQ_LOAD_LATE_COPIES");
+    // the target keys of a staged reference digest go up before the copy engine fills with spectra
+    const bool digest_here = n > 0 && ctx->ref_staged && !ctx->ref_digested && ctx->have_targets;
+    if (digest_here) {
+        std::string err;
+        if (!upload_target_keys_for_reference(st, ctx->targets.seqs, ctx->reference.dev, err)) return fail(ctx, PQ_ERR_CUDA, "reference digest: " + err);
+    }
+    int meta_launches = 0;
+    auto precursor_kernels = [&]() -> int32_t {      // neutral masses, the mass order, the sorted precursor arrays and peak offsets
+        Timer t(ctx, &ctx->cnt.ms_prepare);
+        meta_launches += launch_precursor_mass(n, in_prec.as<double>(), in_charge.as<int32_t>(), in_mass.as<double>(), key.as<uint64_t>(), idx.as<int32_t>(), st);
+        size_t tmp = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, key.as<uint64_t>(), key2.as<uint64_t>(), idx.as<int32_t>(), ctx->s_caller.as<int32_t>(), (int)n, 0, 64, st);
+        CU(ctx->scan_tmp.reserve(tmp + 64));
+        CU(cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, tmp, key.as<uint64_t>(), key2.as<uint64_t>(), idx.as<int32_t>(), ctx->s_caller.as<int32_t>(), (int)n, 0, 64, st));
+        uint64_t* counts = ctx->scratch.as<uint64_t>();
+        meta_launches += launch_gather_meta(n, ctx->s_caller.as<int32_t>(), in_prec.as<double>(), in_charge.as<int32_t>(), in_mass.as<double>(), in_off.as<uint64_t>(),
+                                            ctx->s_prec.as<double>(), ctx->s_charge.as<int32_t>(), ctx->s_mass.as<double>(), counts, st);
+        CU(cudaMemsetAsync(counts + n, 0, 8, st));
+        return scan_exclusive(ctx, counts, ctx->s_off.as<uint64_t>(), (int)n + 1);
+    };
+    if (early_copies) {
+        // the precursor arrays and the kernels that consume them are queued BEFORE the first chunk (kernels first queued behind
+        // the chunk copies were held back until the last chunk had landed: 60 ms per load); the walk over the offsets below
+        // validates while they run
+        CU(cudaMemcpyAsync(in_prec.p, prec_mz, n * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(in_charge.p, charge, n * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(in_off.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        int32_t rc = precursor_kernels();
+        if (rc) return rc;
+    }
+    std::vector<int64_t> cut; cut.push_back(0);
+    auto copy_chunk = [&](size_t c) -> int32_t {
+        const uint64_t a = off[cut[c]], b = off[cut[c + 1]];
+        if (b > a) {
+            CU(cudaMemcpyAsync(in_mz.as<double>() + a, mz + a, (b - a) * 8, cudaMemcpyHostToDevice, sc));
+            CU(cudaMemcpyAsync(in_in.as<double>() + a, inten + a, (b - a) * 8, cudaMemcpyHostToDevice, sc));
+        }
+        CU(cudaEventRecord(ctx->chunk_ev[c], sc));
+        return PQ_OK;
+    };
+    uint32_t maxp = 0; uint64_t usable = 0;
+    {
+        const char* bad = nullptr; int32_t bad_rc = PQ_OK;
+        uint64_t next = (n ? off[0] : 0) + chunk_peaks;
+        for (int64_t i = 0; i < n; ++i) {
+            if (off[i + 1] < off[i]) { bad = "peak offsets must be non-decreasing"; bad_rc = PQ_ERR_BAD_ARG; break; }
+            const uint64_t c = off[i + 1] - off[i];
+            if (c > 4096) { bad = "more than 4096 peaks in one spectrum"; bad_rc = PQ_ERR_UNSUPPORTED; break; }
+            if (charge[i] < 1) { bad = "charge must be >= 1"; bad_rc = PQ_ERR_BAD_ARG; break; }
+            if (c > maxp) maxp = (uint32_t)c;
+            if ((int64_t)c > (int64_t)ctx->P.min_peaks) ++usable;
+            if (i + 1 < n && off[i + 1] >= next) {                   // spectra cut.back() .. i form a chunk
+                cut.push_back(i + 1); next = off[i + 1] + chunk_peaks;
+                if (early_copies) { int32_t rc = copy_chunk(cut.size() - 2); if (rc) return rc; }
+            }
+        }
+        if (bad) { if (early_copies) { cudaStreamSynchronize(sc); cudaStreamSynchronize(st); } return fail(ctx, bad_rc, bad); }
+        if (n > 0) { cut.push_back(n); if (early_copies) { int32_t rc = copy_chunk(cut.size() - 2); if (rc) return rc; } }
     }
     const size_t n_chunks = cut.size() - 1;
-    while (ctx->chunk_ev.size() < n_chunks) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+    ctx->nS = n; ctx->max_peaks = maxp; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0;
+    ctx->cnt.spectra_loaded = (uint64_t)n; ctx->cnt.spectra_usable = usable;
+    if (n == 0) return PQ_OK;
+    mk.mark("validate + reserve (+ early copies)");
+    if (!early_copies) {
+        CU(cudaMemcpyAsync(in_prec.p, prec_mz, n * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(in_charge.p, charge, n * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(in_off.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    }
     auto enqueue_copies = [&]() -> int32_t {
-        for (size_t c = 0; c < n_chunks; ++c) {
-            const uint64_t a = off[cut[c]], b = off[cut[c + 1]];
-            if (b > a) {
-                CU(cudaMemcpyAsync(in_mz.as<double>() + a, mz + a, (b - a) * 8, cudaMemcpyHostToDevice, sc));
-                CU(cudaMemcpyAsync(in_in.as<double>() + a, inten + a, (b - a) * 8, cudaMemcpyHostToDevice, sc));
-            }
-            CU(cudaEventRecord(ctx->chunk_ev[c], sc));
-        }
+        if (early_copies) return PQ_OK;                              // already on their way
+        for (size_t c = 0; c < n_chunks; ++c) { int32_t rc = copy_chunk(c); if (rc) return rc; }
         return PQ_OK;
     };
     ctx->cnt.h2d_bytes += (uint64_t)n * 28 + 8 + total * 16;
@@ -472,27 +527,15 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
     {
         Timer t(ctx, &ctx->cnt.ms_prepare);
         int k = 0;
-        k += launch_precursor_mass(n, in_prec.as<double>(), in_charge.as<int32_t>(), in_mass.as<double>(), key.as<uint64_t>(), idx.as<int32_t>(), st);
-        size_t tmp = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp, key.as<uint64_t>(), key2.as<uint64_t>(), idx.as<int32_t>(), ctx->s_caller.as<int32_t>(), (int)n, 0, 64, st);
-        CU(ctx->scan_tmp.reserve(tmp + 64));
-        CU(cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, tmp, key.as<uint64_t>(), key2.as<uint64_t>(), idx.as<int32_t>(), ctx->s_caller.as<int32_t>(), (int)n, 0, 64, st));
-        uint64_t* counts = ctx->scratch.as<uint64_t>();
-        k += launch_gather_meta(n, ctx->s_caller.as<int32_t>(), in_prec.as<double>(), in_charge.as<int32_t>(), in_mass.as<double>(), in_off.as<uint64_t>(),
-                                ctx->s_prec.as<double>(), ctx->s_charge.as<int32_t>(), ctx->s_mass.as<double>(), counts, st);
-        CU(cudaMemsetAsync(counts + n, 0, 8, st));
-        int32_t rc = scan_exclusive(ctx, counts, ctx->s_off.as<uint64_t>(), (int)n + 1);
-        if (rc) return rc;
-        // the target keys of a staged reference digest go up before the copy engine fills with spectra
-        const bool digest_here = ctx->ref_staged && !ctx->ref_digested && ctx->have_targets;
-        if (digest_here) {
-            std::string err;
-            if (!upload_target_keys_for_reference(st, ctx->targets.seqs, ctx->reference.dev, err)) return fail(ctx, PQ_ERR_CUDA, "reference digest: " + err);
-        }
-        // The peak copies are queued only now: queued ahead of the kernels above they held those kernels back until the last
+        int32_t rc = PQ_OK;
+        if (!early_copies) { rc = precursor_kernels(); if (rc) return rc; }
+        k += meta_launches;
+        // The peak copies are queued only now (pageable precursor arrays, see above): queued ahead of the kernels above they held those kernels back until the last
         // chunk had landed (measured: 60 ms per load instead of 36 ms), so the small precursor work goes first.
+        mk.mark("precursor arrays + sort queued");
         rc = enqueue_copies();
         if (rc) return rc;
+        mk.mark("chunk copies queued");
         CU(ctx->s_inv.reserve(n * 4));
         k += launch_invert_order(n, ctx->s_caller.as<int32_t>(), ctx->s_inv.as<int32_t>(), st);
         SpectraView sp = ctx->view();
@@ -532,12 +575,16 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
         ctx->cnt.other_kernel_launches += (uint64_t)k + 4;
     }
     CU(cudaGetLastError());
+    mk.mark("chunk work queued");
     // a protein database staged before the spectra (pq_stage_reference): its digest does not depend on them and runs now, on a
     // third stream, beside the chunk work above
     if (ctx->ref_staged && !ctx->ref_digested && ctx->have_targets) { int32_t rc = digest_staged_reference(ctx, ctx->st_aux); if (rc) return rc; }
     // targets given before the spectra: their expansion, sort and encoding (host work) overlap the upload
+    mk.mark("digest (staged reference)");
     if (ctx->have_targets) { int32_t rc = finalize_targets(ctx); if (rc) return rc; }
+    mk.mark("target table");
     CU(cudaStreamSynchronize(st));
+    mk.mark("wait for the upload");
     ctx->host_spectra_valid = false;          // host mirrors (Step 5, pq_score_pairs) are pulled on first use
     return PQ_OK;
 }

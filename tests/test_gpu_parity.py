@@ -745,3 +745,32 @@ def test_staged_reference_gives_the_same_table(data, order):
     assert g.psms().tobytes() == ref2.psms().tobytes()
     c = g.counters(); c2 = ref2.counters()
     assert c.reference_forms == c2.reference_forms and c.reference_sequences == c2.reference_sequences
+
+
+@pytest.mark.parametrize("chunk", [None, "5000"])
+def test_pinned_caller_buffers(data, chunk, monkeypatch):
+    """All five spectrum arrays in pinned host memory: pq_load_spectra queues the precursor kernels, then each chunk of peaks as
+    soon as its walk over the offsets has passed it (the other tests hand over pageable numpy arrays).  Same rows; a bad offset
+    found after copies were queued is still reported and leaves the context usable."""
+    import torch
+    prot, tgt, sp = data
+    keep = []
+
+    def pin(arr):
+        t = torch.empty(max(1, (arr.nbytes + 7) // 8), dtype=torch.float64, pin_memory=True); keep.append(t)
+        out = t.numpy().view(np.uint8)[:arr.nbytes].view(arr.dtype)
+        out[:] = arr
+        return out
+    spp = {k: pin(v) for k, v in sp.items()}
+    if chunk:
+        monkeypatch.setenv("PQ_LOAD_CHUNK_PEAKS", chunk)
+    p = _abi.default_params(n_random=50)
+    ref = run_gpu(p, sp, tgt, prot)
+    g = Search(p)
+    g.set_targets(*tgt); g.stage_reference(*prot); g.load_spectra(spp); g.step2(); g.build_reference(); g.step3(); g.step4(); g.rank()
+    assert g.psms().tobytes() == ref.psms().tobytes()
+    bad = dict(spp); bad["peak_off"] = pin(sp["peak_off"].copy()); bad["peak_off"][len(bad["peak_off"]) // 2] += 10 ** 6
+    with pytest.raises(PepQueryError):
+        g.load_spectra(bad)
+    g.load_spectra(spp); g.step2(); g.build_reference(); g.step3(); g.step4(); g.rank()
+    assert g.psms().tobytes() == ref.psms().tobytes()
