@@ -42,8 +42,8 @@ def parse_args():
     ap.add_argument("--proteins", type=int, default=20000)
     ap.add_argument("--shuffles", type=int, default=1000)
     ap.add_argument("--method", type=int, default=1)
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-warmup", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-warmup", type=int, default=2)
     ap.add_argument("--cpu-sample", type=int, default=12000, help="spectra in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--score-all-shuffles", action="store_true", help="compute every shuffle score in full (no upper-bound decision in Step 4)")
