@@ -100,8 +100,10 @@ __device__ __forceinline__ uint32_t row_byte(const uint32_t* codes, int idx) {
 // METHOD 1: hyperscore (count_b, count_y, sum of normalised intensities); METHOD 2: MVH class hits.
 // NCH = number of fragment charges (precursor charge - 1, JMatch.java:398-407) when it is 1, 2 or 3: the charge loop
 // unrolls and charges 1 and 2 need no divide; NCH = 0 takes the charge count at run time.
-// tab[code] = {residue mass, modification mass} (one 16-byte shared-memory load per residue).
-template <int BLOCK, int METHOD, int NCH>
+// tab[code * TS] = {residue mass, modification mass} (one 16-byte shared-memory load per residue).  TS = 8: the table holds 8
+// copies of every entry, copy (lane & 7) at tab[code * 8 + (lane & 7)], and `tab` arrives offset by (lane & 7): the eight lanes
+// of a quarter-warp then hit eight different 16-byte bank groups whatever their residues are (no bank conflicts).
+template <int BLOCK, int METHOD, int NCH, int TS = 1>
 __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this thread's column */, const BlobView& B,
                                                   const double2* tab, const double* ntd, const double* ctd,
                                                   int z, double itol, Extra ex,
@@ -184,7 +186,7 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
         for (int j = 0; j < 4; ++j) {
             const int k = i0 + j + 1;
             if (k > L - 1) break;
-            const double2 t = tab[word & 0xFFu];
+            const double2 t = tab[(word & 0xFFu) * TS];
             word >>= 8;
             acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
             if (k == ex.site) acc = __dadd_rn(acc, ex.delta);
@@ -201,7 +203,7 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
         uint32_t word = codes[(1 + (i >> 2)) * BLOCK] << (8 * (3 - (i & 3)));        // residue i in the top byte
 #pragma unroll 1
         for (int j = i & 3; j >= 0 && i >= 1; --j, --i) {
-            const double2 t = tab[word >> 24];
+            const double2 t = tab[(word >> 24) * TS];
             word <<= 8;
             acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
             if (i + 1 == ex.site) acc = __dadd_rn(acc, ex.delta);
@@ -253,15 +255,15 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
     return r;
 }
 
-template <int BLOCK, int METHOD>
+template <int BLOCK, int METHOD, int TS = 1>
 __device__ __forceinline__ PairScore score_pair(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd, const double* ctd,
                                                 int z, double itol, Extra ex, const double* log10_fact, const double* ln_fact, int32_t predicted,
                                                 uint32_t* usedw, double cutoff = 0.0) {
     switch (z) {                                  // fragment charges = precursor charge - 1, at least 1 (JMatch.java:398-407)
-        case 0: case 1: case 2: return score_pair_n<BLOCK, METHOD, 1>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
-        case 3: return score_pair_n<BLOCK, METHOD, 2>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
-        case 4: return score_pair_n<BLOCK, METHOD, 3>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
-        default: return score_pair_n<BLOCK, METHOD, 0>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
+        case 0: case 1: case 2: return score_pair_n<BLOCK, METHOD, 1, TS>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
+        case 3: return score_pair_n<BLOCK, METHOD, 2, TS>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
+        case 4: return score_pair_n<BLOCK, METHOD, 3, TS>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
+        default: return score_pair_n<BLOCK, METHOD, 0, TS>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
     }
 }
 
@@ -279,7 +281,7 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t a) { double2 v; asm("ld.sh
 // Four residues per row word.  Words whose four ions all carry every fragment charge (ion number >= NCH) and all exist run
 // as straight-line code; the first ions of each series and the ragged ends take the guarded step.  Clean cells are counted
 // through the flag bit and subtracted from the number of ion / charge combinations.
-template <int BLOCK, int NCH>
+template <int BLOCK, int NCH, int TS = 1>
 __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd,
                                                      const double* ctd, int z) {
     const uint32_t head = codes[0];
@@ -287,7 +289,7 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
     const int nch = NCH > 0 ? NCH : (z <= 1 ? 1 : z - 1);
     const uint32_t cells_s = smem_addr(B.cells), tab_s = smem_addr(tab);
     auto clean = [&](double t) -> uint32_t { return lds_u16(cells_s + 2u * cell_filter(t)) >> 15; };   // 1: nothing can be claimed at t
-    auto residue = [&](uint32_t word, int j) -> double2 { return lds_f64x2(tab_s + ((word >> (8 * j)) & 0xFFu) * 16u); };
+    auto residue = [&](uint32_t word, int j) -> double2 { return lds_f64x2(tab_s + ((word >> (8 * j)) & 0xFFu) * (16u * TS)); };
     auto ion = [&](double m, int k) -> uint32_t {                        // any ion number (A6: charge c needs c <= k)
         uint32_t c = clean(__dadd_rn(m, kProton));
         if (nch >= 2 && k >= 2) c += clean(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5));
@@ -378,15 +380,15 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
 }
 
 // true: the hyperscore of this row cannot reach `cutoff` (see count_possible_n); false: score it
-template <int BLOCK>
+template <int BLOCK, int TS = 1>
 __device__ __forceinline__ bool below_score_bound(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd,
                                                   const double* ctd, int z, const double* log10_fact, double cutoff) {
     uint32_t c;
     switch (z) {
-        case 0: case 1: case 2: c = count_possible_n<BLOCK, 1>(codes, B, tab, ntd, ctd, z); break;
-        case 3: c = count_possible_n<BLOCK, 2>(codes, B, tab, ntd, ctd, z); break;
-        case 4: c = count_possible_n<BLOCK, 3>(codes, B, tab, ntd, ctd, z); break;
-        default: c = count_possible_n<BLOCK, 0>(codes, B, tab, ntd, ctd, z); break;
+        case 0: case 1: case 2: c = count_possible_n<BLOCK, 1, TS>(codes, B, tab, ntd, ctd, z); break;
+        case 3: c = count_possible_n<BLOCK, 2, TS>(codes, B, tab, ntd, ctd, z); break;
+        case 4: c = count_possible_n<BLOCK, 3, TS>(codes, B, tab, ntd, ctd, z); break;
+        default: c = count_possible_n<BLOCK, 0, TS>(codes, B, tab, ntd, ctd, z); break;
     }
     const int nbq = (int)(c & 0xFFFFu), nyq = (int)(c >> 16);
     const int nb = min(nbq, 64), ny = min(nyq, 64), n = min(min(nbq + nyq, (int)B.nsurv), 64);

@@ -29,13 +29,17 @@ using namespace dev;
 
 // bytes of the fixed part of K1's dynamic shared memory (row columns + tables [+ MVH used-bitmap columns]), 128-byte aligned
 template <int BLOCK, int METHOD>
-__host__ __device__ constexpr size_t kFixedSmem() {
-    return ((size_t)16 * BLOCK * 4 + (size_t)(2 * kMaxCodes + 2 * kMaxTermCodes + 130) * 8 + (METHOD == 2 ? (size_t)10 * BLOCK * 4 : 0) + 127) & ~(size_t)127;
+__host__ __device__ constexpr size_t kFixedSmem() {      // without the residue table, which follows it (its size is a launch parameter)
+    return ((size_t)16 * BLOCK * 4 + (size_t)(2 * kMaxTermCodes + 130) * 8 + (METHOD == 2 ? (size_t)10 * BLOCK * 4 : 0) + 127) & ~(size_t)127;
 }
+// Copies of every residue-table entry: the Step-4 configuration (BLOCK 256) is bound by shared-memory bandwidth (ncu: 0.77
+// wavefronts per cycle and SM, 41 % of them bank conflicts of the random 16-byte table look-ups); with 8 copies, copy
+// lane & 7, a quarter-warp's look-ups are conflict-free.
+template <int BLOCK> __host__ __device__ constexpr int kTabCopies() { return BLOCK == 256 ? 8 : 1; }
 
 template <int BLOCK, int METHOD>
 __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? K1_MIN_BLOCKS : (BLOCK == 64 ? 11 : 1))
-k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage) {
+k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage, uint32_t tab_bytes, uint32_t n_codes) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ double s_red_d[BLOCK / 32];
@@ -43,16 +47,18 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
 
     // The per-thread row columns and the small tables sit at compile-time offsets from the start of dynamic shared memory (so
     // their addresses fold into the load instructions); the blob stages, whose size is a launch parameter, come after them.
+    constexpr int TS = kTabCopies<BLOCK>();
     uint32_t* codes_all = reinterpret_cast<uint32_t*>(smem);                                            // [16][BLOCK]
-    double2* s_tab = reinterpret_cast<double2*>(codes_all + 16 * BLOCK);                               // {residue mass, modification mass} per code
-    double* s_nt = reinterpret_cast<double*>(s_tab + kMaxCodes);
+    double* s_nt = reinterpret_cast<double*>(codes_all + 16 * BLOCK);
     double* s_ct = s_nt + kMaxTermCodes;
     double* s_l10 = s_ct + kMaxTermCodes;                                                              // [130]
     uint32_t* usedw_all = reinterpret_cast<uint32_t*>(s_l10 + 130);                                     // MVH only: [10][BLOCK]
-    uint8_t* stage0 = smem + kFixedSmem<BLOCK, METHOD>();
+    double2* s_tab_all = reinterpret_cast<double2*>(smem + kFixedSmem<BLOCK, METHOD>());               // {residue mass, modification mass} per code, TS copies each
+    uint8_t* stage0 = smem + kFixedSmem<BLOCK, METHOD>() + tab_bytes;
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < kMaxCodes; i += BLOCK) s_tab[i] = make_double2(L.mods->aa[i], L.mods->delta[i]);
+    for (int i = tid; i < (int)n_codes * TS; i += BLOCK) s_tab_all[i] = make_double2(L.mods->aa[i / TS], L.mods->delta[i / TS]);
+    const double2* s_tab = s_tab_all + (TS > 1 ? (tid & (TS - 1)) : 0);                                // this lane's copy
     for (int i = tid; i < kMaxTermCodes; i += BLOCK) { s_nt[i] = L.mods->nterm[i]; s_ct[i] = L.mods->cterm[i]; }
     for (int i = tid; i < 130; i += BLOCK) s_l10[i] = L.log10_fact[i];     // [0..64] log10(n!), [65..129] log10(100 n)
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -65,7 +71,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     // Jobs are handed out by an atomic counter (in list order, so neighbouring CTAs share table rows in L2); the next
     // job's blob is already in flight (second stage) while the current one is scored.
     __shared__ uint32_t s_job[2];
-    constexpr uint32_t kSurvCap = BLOCK == 256 ? 2048 : 2 * BLOCK;      // only the Step-4 configuration (BLOCK 256) pays for a long list
+    constexpr uint32_t kSurvCap = BLOCK == 256 ? 1024 : 2 * BLOCK;      // only the Step-4 configuration (BLOCK 256) pays for a long list
     __shared__ uint16_t s_surv[kSurvCap];         // bounded Step 4: candidates the score bound could not decide (index within the job)
     __shared__ uint32_t s_nsurv;
     const bool bounded = METHOD == 1 && L.kind == kJobShuffles && !cfg.score_all && !cfg.check_window;
@@ -110,7 +116,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
                 if ((uint32_t)tid < count) {
                     const uint32_t row = J.cand_begin + base + s_surv[first + tid];
                     load_row(row);
-                    PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, 0, usedw, 0.0);
+                    PairScore ps = score_pair<BLOCK, METHOD, TS>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, 0, usedw, 0.0);
                     if (ps.score >= J.ref_score) ++n_better;
                 }
             };
@@ -123,7 +129,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
                 for (uint32_t c = s0 + tid; c < s1; c += BLOCK) {
                     load_row(J.cand_begin + c);
                     ++n_in;
-                    if (below_score_bound<BLOCK>(codes, B, s_tab, s_nt, s_ct, J.charge, s_l10, J.ref_score)) ++n_bound;
+                    if (below_score_bound<BLOCK, TS>(codes, B, s_tab, s_nt, s_ct, J.charge, s_l10, J.ref_score)) ++n_bound;
                     else s_surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)(c - s0);
                 }
                 __syncthreads();
@@ -145,7 +151,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
             if (active) {
                 int32_t pred = 0;
                 if (METHOD == 2) pred = L.row_pred[2 * (size_t)row + (J.charge == 2 ? 0 : 1)];
-                PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex,
+                PairScore ps = score_pair<BLOCK, METHOD, TS>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex,
                                                          s_l10, L.ln_fact, pred, usedw, 0.0);
                 ++n_in;
                 if (ps.score > best) { best = ps.score; best_cand = row; }
@@ -286,7 +292,9 @@ int launch_scatter(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st
 template <int BLOCK, int METHOD>
 int launch_kernel(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
     const uint32_t stage = (L.max_blob_bytes + 127u) & ~127u;
-    const size_t tail = kFixedSmem<BLOCK, METHOD>();
+    const uint32_t n_codes = kTabCopies<BLOCK>() > 1 ? std::min<uint32_t>(std::max<uint32_t>(L.n_codes, 26u), (uint32_t)kMaxCodes) : (uint32_t)kMaxCodes;
+    const uint32_t tab_bytes = (n_codes * (uint32_t)kTabCopies<BLOCK>() * 16u + 127u) & ~127u;
+    const size_t tail = kFixedSmem<BLOCK, METHOD>() + tab_bytes;
     // Shuffle jobs (~1000 pairs each) hide the blob load behind a second stage; target / competitor jobs are short, there
     // one stage and more resident CTAs win (measured: Step 2 9.1 -> 5.4 ms, Step 3 18.7 -> 13.4 ms).
     int nstage = BLOCK == 256 ? 2 : 1;
@@ -303,7 +311,7 @@ int launch_kernel(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st)
     uint32_t grid = (uint32_t)(sms * per_sm);
     if (grid > L.n_jobs) grid = L.n_jobs;
     cudaMemsetAsync(L.job_counter, 0, 4, st);
-    kernel<<<grid, BLOCK, smem, st>>>(L, cfg, stage, nstage);
+    kernel<<<grid, BLOCK, smem, st>>>(L, cfg, stage, nstage, tab_bytes, n_codes);
     return 1;
 }
 template <int BLOCK>

@@ -194,7 +194,7 @@ int32_t run_score(pq_ctx* ctx, JobKind kind, uint32_t n_jobs, const int32_t* row
     ScoreLaunch L; memset(&L, 0, sizeof L);
     L.kind = kind; L.jobs = ctx->jobs.as<Job>(); L.n_jobs = n_jobs;
     L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>(); L.blob_len = ctx->blob_len.as<uint32_t>();
-    L.rows = rows; L.row_mass = row_mass; L.mods = ctx->d_mods.as<ModTable>();
+    L.rows = rows; L.row_mass = row_mass; L.mods = ctx->d_mods.as<ModTable>(); L.n_codes = (uint32_t)ctx->codes.n_codes;
     L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>();
     L.row_pred = row_pred;
     L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>();
@@ -1522,7 +1522,7 @@ int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_ind
     ScoreLaunch L; memset(&L, 0, sizeof L);
     L.kind = kJobPairs; L.jobs = ctx->jobs.as<Job>(); L.n_jobs = (uint32_t)hj.size();
     L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>(); L.blob_len = ctx->blob_len.as<uint32_t>(); L.rows = d_rows.as<uint8_t>(); L.row_mass = nullptr;
-    L.mods = ctx->d_mods.as<ModTable>(); L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>(); L.row_pred = nullptr;
+    L.mods = ctx->d_mods.as<ModTable>(); L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>(); L.row_pred = nullptr; L.n_codes = (uint32_t)ctx->codes.n_codes;
     L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>(); L.hit_capacity = 0;
     L.pair_score = d_score.as<double>(); L.pair_a = d_a.as<int32_t>(); L.pair_b = d_b.as<int32_t>(); L.max_blob_bytes = ctx->max_blob; L.job_counter = ctx->d_scalars.as<uint32_t>() + 12;
     if (ctx->P.score_method == 2) {

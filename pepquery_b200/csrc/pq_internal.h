@@ -95,6 +95,7 @@ struct ScoreConfig {
 };
 
 struct ScoreLaunch {
+    uint32_t n_codes = kMaxCodes;   // residue codes in use (26 letters + the (residue, modification) pairs of this search)
     JobKind kind;
     const Job* jobs; uint32_t n_jobs;
     const uint8_t* blobs; const uint64_t* blob_off; const uint32_t* blob_len;   // prepared spectra (slot offsets, used bytes)
