@@ -366,7 +366,7 @@ def main():
                 "algorithmic_bytes_per_launch": k1_bytes,
                 "note": "algorithmic bytes = sum over pairs of 16*P_s+96 (SURVEY.md 8d); each spectrum is staged once in shared memory and "
                         "reused by ~1000 shuffles, so physical DRAM traffic (traffic, bytes per launch from ncu, profiles/) is ~140x lower and "
-                        "frac exceeds 1: the kernel is bound by warp-issue slots and shared-memory latency (ncu: 51 % issue-active after the count pass halved the instruction count), not by HBM"}
+                        "frac exceeds 1: the kernel is bound by warp-issue slots and the shared-memory pipe (ncu: 63 % issue-active, 0.69 shared-memory wavefronts per cycle and SM), not by HBM"}
     kernel_ms = {"k1_step2": c.ms_score_step[0] / a.steps, "k1_step3": c.ms_score_step[1] / a.steps, "k1_step4": k1_ms,
                  "k0_prepare+pack": c.ms_prepare / a.steps, "k3_window": c.ms_window / a.steps, "k2_shuffle": c.ms_shuffle / a.steps}
 
