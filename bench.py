@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--method", type=int, default=1)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-warmup", type=int, default=2)
+    ap.add_argument("--e2e-two-in-flight", type=int, default=1, help="also time the end-to-end step with two searches in flight (informational)")
     ap.add_argument("--cpu-sample", type=int, default=12000, help="spectra in the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--score-all-shuffles", action="store_true", help="compute every shuffle score in full (no upper-bound decision in Step 4)")
@@ -407,6 +408,47 @@ def main():
                "h2d_bytes_per_step": int(ce.h2d_bytes / a.e2e_steps), "d2h_bytes_per_step": int(ce.d2h_bytes / a.e2e_steps),
                "ms_per_step": 1000.0 * float(tm.item()) / a.e2e_steps, "steps": a.e2e_steps,
                "ms_host_reference_build": ce.ms_host_reference / a.e2e_steps}
+        # Informational (not `value`): the same end-to-end step with TWO searches in flight, each in its own context driven by its
+        # own host thread — what a sweep over many spectrum files does: one search uploads while the other computes, so PCIe
+        # and the SMs are both kept busy.  Every step still uploads its inputs and reads its results back.
+        if world == 1 and a.e2e_two_in_flight:
+            try:
+                import threading
+                ctxs = [g, Search(mk_params(1))]
+                bufs = [None, None]
+
+                upload, compute = threading.Lock(), threading.Lock()   # one search uploads while the other computes
+
+                def full_step(i):
+                    c = ctxs[i]
+                    with upload:
+                        c.set_targets(*tgt); c.stage_reference(*prot); c.load_spectra(sp)
+                    with compute:
+                        c.step2(); c.build_reference(); c.step3(); c.step4(); c.rank()
+                        if bufs[i] is None:
+                            bufs[i] = torch.empty(max(1, 2 * c.psm_count()) * 96 + 4096, dtype=torch.uint8, pin_memory=True).numpy()
+                        n = len(c.psms(bufs[i]) if c.psm_count() * 96 <= bufs[i].nbytes else c.psms())
+                        c.competitors(3)
+                    return n
+
+                for _ in range(2):
+                    full_step(1)                                   # warm the second context up
+                per = max(2, a.e2e_steps)
+                ctxs[0].reset_counters(); ctxs[1].reset_counters()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                th = [threading.Thread(target=lambda i=i: [full_step(i) for _ in range(per)]) for i in range(2)]
+                for t in th: t.start()
+                for t in th: t.join()
+                torch.cuda.synchronize()
+                w2 = time.perf_counter() - t0
+                c0, c1 = ctxs[0].counters(), ctxs[1].counters()
+                p2 = (c0.pairs_step2 + c0.pairs_step3 + c0.pairs_step4 + c1.pairs_step2 + c1.pairs_step3 + c1.pairs_step4)
+                e2e["two_in_flight"] = {"value": p2 / w2, "unit": UNIT, "ms_per_step": 1000.0 * w2 / (2 * per), "steps": 2 * per,
+                                        "note": "two contexts, two host threads; informational, e2e.value is one search at a time"}
+                ctxs[1].close()
+            except Exception as e:                 # informational only: never lose the bench line over it
+                e2e["two_in_flight"] = {"error": repr(e)[:200]}
     g.close()
 
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------------------------
