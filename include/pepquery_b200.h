@@ -193,12 +193,16 @@ int32_t pq_destroy(pq_ctx* ctx);
 /* Spectrum loader.  Replaces the MGF->task loop of pg/SpectraInput.java:142-198 (readMSMSfast):
  * packs peak lists into precursor-mass-sorted CSR device arrays with a 0.1-Da bucket index.
  * Peaks may be in any order; spectra with n_peaks <= min_peaks are kept but never scored
- * (SpectraInput.java:183).  charge[i] must be >= 1. */
+ * (SpectraInput.java:183).  charge[i] must be >= 1.  The upload runs in chunks and hides work that does not depend on the
+ * matched spectra (spectrum preparation with prepare_at_load; the target table when pq_set_targets came first; the digest of
+ * a database handed over by pq_stage_reference); with all five arrays in pinned host memory it starts before the offsets
+ * have been validated.  A load that fails leaves the context without spectra. */
 int32_t pq_load_spectra(pq_ctx* ctx, int64_t n_spectra, const double* precursor_mz, const int32_t* charge,
                         const uint64_t* peak_offset /* n+1 */, const double* mz, const double* intensity);
 
 /* Target peptides.  Replaces CreatePeptideInputWorker -> PeptideInput.calcPeptideIsoforms
- * (pg/PeptideInput.java:114-237): expands each sequence into its modification forms. */
+ * (pg/PeptideInput.java:114-237): expands each sequence into its modification forms (lazily: under the next
+ * pq_load_spectra, else in pq_step2_match_targets / pq_get_target_forms). */
 int32_t pq_set_targets(pq_ctx* ctx, int32_t n_seq, const uint32_t* seq_offset /* n+1 */, const char* residues);
 int32_t pq_get_target_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int64_t* n_forms);
 

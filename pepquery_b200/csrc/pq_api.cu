@@ -503,7 +503,13 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
                 if (early_copies) { int32_t rc = copy_chunk(cut.size() - 2); if (rc) return rc; }
             }
         }
-        if (bad) { if (early_copies) { cudaStreamSynchronize(sc); cudaStreamSynchronize(st); } return fail(ctx, bad_rc, bad); }
+        if (bad) {
+            // the early path has already overwritten staging and sorted precursor arrays: the context is left without spectra
+            if (early_copies) { cudaStreamSynchronize(sc); cudaStreamSynchronize(st); }
+            ctx->nS = 0; ctx->max_peaks = 0; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0; ctx->prepared_at_load = false;
+            ctx->cnt.spectra_loaded = 0; ctx->cnt.spectra_usable = 0;
+            return fail(ctx, bad_rc, bad);
+        }
         if (n > 0) { cut.push_back(n); if (early_copies) { int32_t rc = copy_chunk(cut.size() - 2); if (rc) return rc; } }
     }
     const size_t n_chunks = cut.size() - 1;
