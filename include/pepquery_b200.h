@@ -98,7 +98,7 @@ typedef struct pq_params {
     pq_mod  fixed[PQ_MAX_MODS];
     pq_mod  var[PQ_MAX_MODS];
     int32_t device;             /* CUDA device ordinal                                                 */
-    int32_t score_all_shuffles; /* 1 = compute every shuffle's hyperscore in full.  0 (default): Step 4 only needs
+    int32_t score_all_shuffles; /* 1 = compute every shuffle's score (hyperscore or MVH) in full.  0 (default): Step 4 only needs
                                    "shuffleScore >= targetScore" (pg/StatisticScoreWorker.java:51), so a shuffle whose
                                    score upper bound (from its count of possible matches) stays below the target's
                                    score is decided without resolving its matches; counts and p-values are identical */

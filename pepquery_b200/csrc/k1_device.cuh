@@ -379,10 +379,22 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
     return min(nb, 0xFFFFu) | (min(ny, 0xFFFFu) << 16);
 }
 
-// true: the hyperscore of this row cannot reach `cutoff` (see count_possible_n); false: score it
-template <int BLOCK, int TS = 1>
+// true: the score of this row cannot reach `cutoff` (see count_possible_n); false: score it.
+// Hyperscore: 4 (log10(100 n) + log10 nb! + log10 ny!).  MVH (MVHMatch.java:281-299): score = lnC(bins, predicted) - sum over the
+// three intensity classes of lnC(classCount, hits) - lnC(emptyBins, predicted - matched); every lnC is >= 0 and, for
+// predicted <= emptyBins / 2, lnC(emptyBins, j) grows with j, so with matched <= m = min(possible, survivors, predicted)
+// the score is at most lnC(bins, predicted) - lnC(emptyBins, predicted - m).
+template <int BLOCK, int TS = 1, int METHOD = 1>
 __device__ __forceinline__ bool below_score_bound(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd,
-                                                  const double* ctd, int z, const double* log10_fact, double cutoff) {
+                                                  const double* ctd, int z, const double* log10_fact, double cutoff,
+                                                  const double* ln_fact = nullptr, int32_t predicted = 0) {
+    if (!(cutoff > 0.0)) return false;
+    if (METHOD == 2) {
+        if (!(B.flags & 1u) || predicted <= 0) return true;             // the scorer returns 0 for these
+        const int N = (int)B.nsurv, empty = B.cls[3], bins = empty + N;
+        if (empty < 0 || 2 * predicted > empty) return false;            // no bound: score it
+        if (bins < predicted) return true;                               // "died": the scorer returns 0
+    }
     uint32_t c;
     switch (z) {
         case 0: case 1: case 2: c = count_possible_n<BLOCK, 1, TS>(codes, B, tab, ntd, ctd, z); break;
@@ -391,6 +403,13 @@ __device__ __forceinline__ bool below_score_bound(const uint32_t* codes, const B
         default: c = count_possible_n<BLOCK, 0, TS>(codes, B, tab, ntd, ctd, z); break;
     }
     const int nbq = (int)(c & 0xFFFFu), nyq = (int)(c >> 16);
+    if (METHOD == 2) {
+        const int N = (int)B.nsurv, empty = B.cls[3], bins = empty + N;
+        const int m = min(min(nbq + nyq, N), predicted), j = predicted - m;
+        auto lnC = [&](int n, int k) { return __dsub_rn(__dsub_rn(ln_fact[n], ln_fact[n - k]), ln_fact[k]); };
+        const double ub = __dsub_rn(lnC(bins, predicted), lnC(empty, j));
+        return ub * (1.0 + 1e-12) + 1e-6 < cutoff;
+    }
     const int nb = min(nbq, 64), ny = min(nyq, 64), n = min(min(nbq + nyq, (int)B.nsurv), 64);
     double ub = 0.0;
     if (n > 0) ub = 4.0 * (log10_fact[65 + n] + log10_fact[nb] + log10_fact[ny]);        // log10_fact[65 + n] = log10(100 n)

@@ -74,7 +74,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     constexpr uint32_t kSurvCap = BLOCK == 256 ? 1024 : 2 * BLOCK;      // only the Step-4 configuration (BLOCK 256) pays for a long list
     __shared__ uint16_t s_surv[kSurvCap];         // bounded Step 4: candidates the score bound could not decide (index within the job)
     __shared__ uint32_t s_nsurv;
-    const bool bounded = METHOD == 1 && L.kind == kJobShuffles && !cfg.score_all && !cfg.check_window;
+    const bool bounded = L.kind == kJobShuffles && !cfg.score_all && !cfg.check_window;
     auto fetch = [&](uint32_t slot) {           // thread 0: take the next job and start its TMA into `slot`
         uint32_t nj = atomicAdd(L.job_counter, 1u);
         s_job[slot] = nj;
@@ -116,7 +116,9 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
                 if ((uint32_t)tid < count) {
                     const uint32_t row = J.cand_begin + base + s_surv[first + tid];
                     load_row(row);
-                    PairScore ps = score_pair<BLOCK, METHOD, TS>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, 0, usedw, 0.0);
+                    int32_t pred = 0;
+                    if (METHOD == 2) pred = L.row_pred[2 * (size_t)row + (J.charge == 2 ? 0 : 1)];
+                    PairScore ps = score_pair<BLOCK, METHOD, TS>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, pred, usedw, 0.0);
                     if (ps.score >= J.ref_score) ++n_better;
                 }
             };
@@ -129,7 +131,9 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
                 for (uint32_t c = s0 + tid; c < s1; c += BLOCK) {
                     load_row(J.cand_begin + c);
                     ++n_in;
-                    if (below_score_bound<BLOCK, TS>(codes, B, s_tab, s_nt, s_ct, J.charge, s_l10, J.ref_score)) ++n_bound;
+                    int32_t pred = 0;
+                    if (METHOD == 2) pred = L.row_pred[2 * ((size_t)J.cand_begin + c) + (J.charge == 2 ? 0 : 1)];
+                    if (below_score_bound<BLOCK, TS, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, s_l10, J.ref_score, L.ln_fact, pred)) ++n_bound;
                     else s_surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)(c - s0);
                 }
                 __syncthreads();
