@@ -481,7 +481,7 @@ def main():
                            "pairs_per_step": float(tot_pairs.item()), "psms_per_step": int(n_psm_total),
                            "step4_pairs_decided_by_score_bound": float(c.pairs_step4_bounded) / a.steps,
                            "step4_rule": ("every shuffle scored in full" if a.score_all_shuffles else
-                                          "Step 4 needs only shuffleScore >= targetScore (StatisticScoreWorker.java:51): a shuffle whose hyperscore "
+                                          "Step 4 needs only shuffleScore >= targetScore (StatisticScoreWorker.java:51): a shuffle whose score "
                                           "upper bound (from its count of possible matches) is below the target score is decided without resolving "
                                           "its matches; counts and p-values identical (tests); --score-all-shuffles disables it"),
                            "timed_region": "Steps 2 (incl. spectrum preparation K0)+3+4 + rank/accept + PSM and detail rows to the host, spectra/targets/reference table resident in HBM; e2e: load (K0 under the upload) + targets + Steps 2-4 + reference build + results to the host",
