@@ -281,9 +281,9 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t a) { double2 v; asm("ld.sh
 // Four residues per row word.  Words whose four ions all carry every fragment charge (ion number >= NCH) and all exist run
 // as straight-line code; the first ions of each series and the ragged ends take the guarded step.  Clean cells are counted
 // through the flag bit and subtracted from the number of ion / charge combinations.
-template <int BLOCK, int NCH, int TS = 1>
+template <int BLOCK, int NCH, int TS = 1, bool HAS_EX = false>
 __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd,
-                                                     const double* ctd, int z) {
+                                                     const double* ctd, int z, Extra ex = Extra{-1, 0.0}) {
     const uint32_t head = codes[0];
     const int L = (int)(head & 0xFF), Lm1 = L - 1;
     const int nch = NCH > 0 ? NCH : (z <= 1 ? 1 : z - 1);
@@ -314,6 +314,7 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
 
     // ---- b ions: residue k - 1 closes ion k; word g holds ions 4g+1 .. 4g+4 ----
     double acc = ntd[(head >> 8) & 0xFF];
+    if (HAS_EX && ex.site == 0) acc = __dadd_rn(acc, ex.delta);
     {
         const uint32_t word = codes[1 * BLOCK];
 #pragma unroll
@@ -321,6 +322,7 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
             if (j + 1 <= Lm1) {
                 const double2 t = residue(word, j);
                 acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+                if (HAS_EX && j + 1 == ex.site) acc = __dadd_rn(acc, ex.delta);
                 cb += ion(acc, j + 1);
             }
         }
@@ -333,6 +335,7 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
         for (int j = 0; j < 4; ++j) {
             const double2 t = residue(word, j);
             acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+            if (HAS_EX && 4 * g + j + 1 == ex.site) acc = __dadd_rn(acc, ex.delta);
             cb += ion_full(acc, 4 * g + j + 1);
         }
     }
@@ -343,17 +346,20 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
             if (4 * G + j + 1 <= Lm1) {
                 const double2 t = residue(word, j);
                 acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+                if (HAS_EX && 4 * G + j + 1 == ex.site) acc = __dadd_rn(acc, ex.delta);
                 cb += ion_full(acc, 4 * G + j + 1);
             }
         }
     }
     // ---- y ions: residue i (from L-1 down to 1) closes ion L - i ----
     acc = ctd[(head >> 16) & 0xFF];
+    if (HAS_EX && ex.site == L + 1) acc = __dadd_rn(acc, ex.delta);
     int i = Lm1;
 #pragma unroll 1
     for (; i >= 1 && ((L - i) < nch || (i & 3) != 3); --i) {           // first ions and the ragged top word
         const double2 t = residue(codes[(1 + (i >> 2)) * BLOCK], i & 3);
         acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+        if (HAS_EX && i + 1 == ex.site) acc = __dadd_rn(acc, ex.delta);
         cy += ion(__dadd_rn(acc, kWater), L - i);
     }
     if (i >= 3) {                                                       // here i & 3 == 3
@@ -364,6 +370,7 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
             for (int j = 3; j >= 0; --j) {
                 const double2 t = residue(word, j);
                 acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+                if (HAS_EX && 4 * w + j + 1 == ex.site) acc = __dadd_rn(acc, ex.delta);
                 cy += ion_full(__dadd_rn(acc, kWater), L - (4 * w + j));
             }
         }
@@ -372,6 +379,7 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
         for (int j = 3; j >= 1; --j) {
             const double2 t = residue(word, j);
             acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+            if (HAS_EX && j + 1 == ex.site) acc = __dadd_rn(acc, ex.delta);
             cy += ion_full(__dadd_rn(acc, kWater), L - j);
         }
     }
@@ -384,10 +392,10 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
 // three intensity classes of lnC(classCount, hits) - lnC(emptyBins, predicted - matched); every lnC is >= 0 and, for
 // predicted <= emptyBins / 2, lnC(emptyBins, j) grows with j, so with matched <= m = min(possible, survivors, predicted)
 // the score is at most lnC(bins, predicted) - lnC(emptyBins, predicted - m).
-template <int BLOCK, int TS = 1, int METHOD = 1>
+template <int BLOCK, int TS = 1, int METHOD = 1, bool HAS_EX = false>
 __device__ __forceinline__ bool below_score_bound(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd,
                                                   const double* ctd, int z, const double* log10_fact, double cutoff,
-                                                  const double* ln_fact = nullptr, int32_t predicted = 0) {
+                                                  const double* ln_fact = nullptr, int32_t predicted = 0, Extra ex = Extra{-1, 0.0}) {
     if (!(cutoff > 0.0)) return false;
     if (METHOD == 2) {
         if (!(B.flags & 1u) || predicted <= 0) return true;             // the scorer returns 0 for these
@@ -397,10 +405,10 @@ __device__ __forceinline__ bool below_score_bound(const uint32_t* codes, const B
     }
     uint32_t c;
     switch (z) {
-        case 0: case 1: case 2: c = count_possible_n<BLOCK, 1, TS>(codes, B, tab, ntd, ctd, z); break;
-        case 3: c = count_possible_n<BLOCK, 2, TS>(codes, B, tab, ntd, ctd, z); break;
-        case 4: c = count_possible_n<BLOCK, 3, TS>(codes, B, tab, ntd, ctd, z); break;
-        default: c = count_possible_n<BLOCK, 0, TS>(codes, B, tab, ntd, ctd, z); break;
+        case 0: case 1: case 2: c = count_possible_n<BLOCK, 1, TS, HAS_EX>(codes, B, tab, ntd, ctd, z, ex); break;
+        case 3: c = count_possible_n<BLOCK, 2, TS, HAS_EX>(codes, B, tab, ntd, ctd, z, ex); break;
+        case 4: c = count_possible_n<BLOCK, 3, TS, HAS_EX>(codes, B, tab, ntd, ctd, z, ex); break;
+        default: c = count_possible_n<BLOCK, 0, TS, HAS_EX>(codes, B, tab, ntd, ctd, z, ex); break;
     }
     const int nbq = (int)(c & 0xFFFFu), nyq = (int)(c >> 16);
     if (METHOD == 2) {

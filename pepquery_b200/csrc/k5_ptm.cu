@@ -94,9 +94,12 @@ k5_ptm_kernel(PtmLaunch L, ScoreConfig cfg, uint32_t stage_bytes) {
                 int32_t predicted = 0;
                 if (METHOD == 2) predicted = predict_peaks(L.rows + (size_t)row * kRowBytes, L.mods, itol, J.charge == 2 ? 1 : 2, ex);   // MVHMatch.java:165-172
                 // only candidates that reach the target's score matter (rows of ptm.txt, n_ptm): the score bound decides most others
-                PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, predicted, usedw,
-                                                         cfg.score_all ? 0.0 : J.ref_score);
                 ++n_pairs;
+                // (hyperscore: the count pass of Step 4 with the extra modification; survivors are ~0.1 %, so no compaction here)
+                if (METHOD == 1 && !cfg.score_all &&
+                    below_score_bound<BLOCK, 1, 1, true>(codes, B, s_tab, s_nt, s_ct, J.charge, s_l10, J.ref_score, nullptr, 0, ex)) { ++n_bound; return; }
+                PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, predicted, usedw,
+                                                         (cfg.score_all || METHOD == 1) ? 0.0 : J.ref_score);
                 if (ps.a < 0) { ++n_bound; return; }                                           // decided by the bound: below the target
                 bool better = cfg.hc ? ps.score >= J.ref_score : ps.score > J.ref_score;      // :239-259, PSMT:920-943
                 if (better) { ++n_better; if (cfg.fast) s_stop = 1; }
