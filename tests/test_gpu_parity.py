@@ -357,6 +357,9 @@ def test_golden_fixture_replay():
         assert ps["p_value"].tolist() == w["p_value"]
         c = g.counters()
         assert [c.pairs_step2, c.pairs_step3, c.pairs_step4] == w["pairs"][:3] and c.reference_forms == w["reference_forms"]
+        assert np.allclose(g.delta_scores()[0], np.array(w["ref_delta_score"]), rtol=REL, atol=1e-9)
+    toff, tres, want = synth.planted_targets(prot, np.random.default_rng(7))
+    assert g.find_in_proteome(toff, tres, prot[0], prot[1]).tolist() == gold["novelty_seed7"]
 
 
 def test_shuffle_streams_match_java_random(data):

@@ -237,6 +237,9 @@ def test_oracle_regression_fixture():
             assert ps[f].tolist() == g[f], (method, f)
         assert ps["score"].tolist() == g["score"] and ps["p_value"].tolist() == g["p_value"]
         assert [int(x) for x in o.pairs()] == g["pairs"]
+        assert o.delta_scores()[0].tolist() == g["ref_delta_score"]
+    toff, tres, want = synth.planted_targets(prot, np.random.default_rng(7))
+    assert pq_oracle.find_in_proteome(toff, tres, prot[0], prot[1]).tolist() == gold["novelty_seed7"] == want.tolist()
 
 
 def test_preprocessing_invariants(small_inputs):

@@ -70,12 +70,16 @@ def oracle_vectors():
         out["method%d" % method]["pairs"] = [int(x) for x in o.pairs()]
         _, nref = o.reference_forms()
         out["method%d" % method]["reference_forms"] = nref
+        out["method%d" % method]["ref_delta_score"] = o.delta_scores()[0].tolist()
         o.close()
     out["java_random_12457_next31"] = pq_oracle.java_random(12457, 0, 3).tolist()
     out["java_random_12457_nextInt10"] = pq_oracle.java_random(12457, 10, 8).tolist()
     out["java_random_2022_nextInt3"] = pq_oracle.java_random(2022, 3, 8).tolist()
     out["shuffles_PEPTLDEK"] = pq_oracle.shuffles("PEPTLDEK", 5)
     out["shuffles_ELVLSQLGCK"] = pq_oracle.shuffles("ELVLSQLGCK", 5)
+    toff, tres, want = synth.planted_targets(prot, np.random.default_rng(7))
+    out["novelty_seed7"] = pq_oracle.find_in_proteome(toff, tres, prot[0], prot[1]).tolist()
+    assert out["novelty_seed7"] == want.tolist()
     json.dump(out, open(os.path.join(OUT, "oracle_vectors.json"), "w"))
     return out
 
