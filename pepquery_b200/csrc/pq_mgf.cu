@@ -69,6 +69,26 @@ inline double parse_double(const char* p, const char* end, const char** next) {
     return neg ? -v : v;
 }
 
+// The common peak-line number: digits [. digits], at most 18 digits in all, no sign / exponent.  Same value as parse_double
+// (the integer below 2^53 divided by an exact power of ten: one correctly rounded IEEE division); false = not that shape,
+// the caller takes the general path from the same position.
+inline bool fast_number(const char*& s, const char* end, double& v) {
+    const char* p = s;
+    uint64_t m = 0; int nd = 0, frac = 0;
+    while (p < end && (unsigned)(*p - '0') <= 9u) { m = m * 10 + (uint64_t)(*p - '0'); ++nd; ++p; }
+    if (p < end && *p == '.') {
+        ++p;
+        const char* f0 = p;
+        while (p < end && (unsigned)(*p - '0') <= 9u) { m = m * 10 + (uint64_t)(*p - '0'); ++p; }
+        frac = (int)(p - f0); nd += frac;
+    }
+    if (nd == 0 || nd > 18 || m >= (1ull << 53)) return false;
+    if (p < end) { const char c = *p; if (c != ' ' && c != '\t' && c != '\r' && c != '\n') return false; }     // 'e', 'x', letters ...: general path
+    v = frac ? (double)m / kPow10[frac] : (double)m;
+    s = p;
+    return true;
+}
+
 struct Out { double* prec; int32_t* charge; uint64_t* off; double* mz; double* inten; };
 
 // The sequential state machine over [p, end): a chunk always starts at a BEGIN IONS line (or at the start of the text).
@@ -87,11 +107,12 @@ void parse_chunk(const char* p, const char* end, const Out* fill, int64_t s0, ui
             if (in_ions && ((c >= '0' && c <= '9') || c == '.')) {
                 if (!fill) { if (c != '.' || (len > 1 && q[1] >= '0' && q[1] <= '9')) ++np; }      // what the fill pass will accept
                 else {
-                    const char* e1; const double a = parse_double(q, eol, &e1);
+                    const char* e1 = q; double a;
+                    if (!fast_number(e1, eol, a)) a = parse_double(q, eol, &e1);
                     if (e1 != q) {
                         const char* t = e1; while (t < eol && (*t == ' ' || *t == '\t')) ++t;
                         const char* e2 = t; double b = 0.0;
-                        if (t < eol) b = parse_double(t, eol, &e2);
+                        if (t < eol && !fast_number(e2, eol, b)) b = parse_double(t, eol, &e2);
                         fill->mz[p0 + np] = a; fill->inten[p0 + np] = (e2 != t) ? b : 0.0;
                         ++np;
                     }
