@@ -852,7 +852,11 @@ static void build_reference(Ctx& C, const std::vector<std::string>& proteins) {
     const Params& P = C.P;
     std::set<std::string> seqs;
     for (auto& pr : proteins) digest_protein(P, pr, seqs);
-    for (auto& t : C.target_seqs) seqs.erase(t);                        // DatabaseInput.java:480-488
+    for (auto& t : C.target_seqs) {                                     // DatabaseInput.java:480-488; the targets were I -> L folded
+        std::string f(t);                                               // when they were registered (add_target_peptides :47-51)
+        for (auto& c : f) if (c == 'I') c = 'L';
+        seqs.erase(f);
+    }
     // GeneratePeptideformWorker.set_mass_range over SpectraInput.spectraMap (= spectra that produced a PSM)
     double mn = 1.7976931348623157e308, mx = 0;
     std::set<int> matched;
@@ -1223,6 +1227,7 @@ int32_t orc_get_psms(orc_ctx* o, pq_psm* out, int64_t cap, int64_t* n) {
         q.spectrum = p.spectrum; q.form = p.form; q.score = p.sc.score; q.exp_mass = p.exp_mass; q.pep_mass = p.pep_mass;
         q.tol_ppm = tol_ppm_of(p); q.isotope_error = p.iso; q.count_b = p.sc.a; q.count_y = p.sc.b;
         q.n_db = p.n_db; q.total_db = p.total_db; q.n_random = p.n_random; q.total_random = p.total_random;
+        if (p.rank >= 2) { q.n_db = -1; q.total_db = -1; }                  // psm_rank.txt: RankPSM.rankPSMs (pg/RankPSM.java:89-92)
         q.valid = p.valid ? 1 : 0; q.p_value = p.p_value; q.rank = p.rank; q.n_ptm = p.n_ptm; q.confident = p.confident;
     }
     return 0;

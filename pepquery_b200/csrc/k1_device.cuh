@@ -3,6 +3,7 @@
 // precursor-window predicate.  See k1_score.cu for the reference citations.
 #pragma once
 #include "pq_internal.h"
+#include "k_cells.cuh"
 
 namespace pq {
 namespace dev {
@@ -387,30 +388,14 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
     return min(nb, 0xFFFFu) | (min(ny, 0xFFFFu) << 16);
 }
 
-// true: the score of this row cannot reach `cutoff` (see count_possible_n); false: score it.
+// The decision itself, from the numbers of possible b / y matches.
 // Hyperscore: 4 (log10(100 n) + log10 nb! + log10 ny!).  MVH (MVHMatch.java:281-299): score = lnC(bins, predicted) - sum over the
 // three intensity classes of lnC(classCount, hits) - lnC(emptyBins, predicted - matched); every lnC is >= 0 and, for
 // predicted <= emptyBins / 2, lnC(emptyBins, j) grows with j, so with matched <= m = min(possible, survivors, predicted)
 // the score is at most lnC(bins, predicted) - lnC(emptyBins, predicted - m).
-template <int BLOCK, int TS = 1, int METHOD = 1, bool HAS_EX = false>
-__device__ __forceinline__ bool below_score_bound(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd,
-                                                  const double* ctd, int z, const double* log10_fact, double cutoff,
-                                                  const double* ln_fact = nullptr, int32_t predicted = 0, Extra ex = Extra{-1, 0.0}) {
-    if (!(cutoff > 0.0)) return false;
-    if (METHOD == 2) {
-        if (!(B.flags & 1u) || predicted <= 0) return true;             // the scorer returns 0 for these
-        const int N = (int)B.nsurv, empty = B.cls[3], bins = empty + N;
-        if (empty < 0 || 2 * predicted > empty) return false;            // no bound: score it
-        if (bins < predicted) return true;                               // "died": the scorer returns 0
-    }
-    uint32_t c;
-    switch (z) {
-        case 0: case 1: case 2: c = count_possible_n<BLOCK, 1, TS, HAS_EX>(codes, B, tab, ntd, ctd, z, ex); break;
-        case 3: c = count_possible_n<BLOCK, 2, TS, HAS_EX>(codes, B, tab, ntd, ctd, z, ex); break;
-        case 4: c = count_possible_n<BLOCK, 3, TS, HAS_EX>(codes, B, tab, ntd, ctd, z, ex); break;
-        default: c = count_possible_n<BLOCK, 0, TS, HAS_EX>(codes, B, tab, ntd, ctd, z, ex); break;
-    }
-    const int nbq = (int)(c & 0xFFFFu), nyq = (int)(c >> 16);
+template <int METHOD>
+__device__ __forceinline__ bool bound_below_cutoff(const BlobView& B, int nbq, int nyq, const double* log10_fact, double cutoff,
+                                                   const double* ln_fact, int32_t predicted) {
     if (METHOD == 2) {
         const int N = (int)B.nsurv, empty = B.cls[3], bins = empty + N;
         const int m = min(min(nbq + nyq, N), predicted), j = predicted - m;
@@ -422,6 +407,65 @@ __device__ __forceinline__ bool below_score_bound(const uint32_t* codes, const B
     double ub = 0.0;
     if (n > 0) ub = 4.0 * (log10_fact[65 + n] + log10_fact[nb] + log10_fact[ny]);        // log10_fact[65 + n] = log10(100 n)
     return ub * (1.0 + 1e-12) + 1e-9 < cutoff;
+}
+// MVH rows the bound cannot judge, or that the scorer answers with 0 anyway: 1 = below (decided), 0 = score it, -1 = go on and count
+template <int METHOD>
+__device__ __forceinline__ int bound_precheck(const BlobView& B, int32_t predicted) {
+    if (METHOD == 2) {
+        if (!(B.flags & 1u) || predicted <= 0) return 1;                // the scorer returns 0 for these
+        const int N = (int)B.nsurv, empty = B.cls[3], bins = empty + N;
+        if (empty < 0 || 2 * predicted > empty) return 0;               // no bound: score it
+        if (bins < predicted) return 1;                                  // "died": the scorer returns 0
+    }
+    return -1;
+}
+
+// true: the score of this row cannot reach `cutoff` (see count_possible_n); false: score it.
+template <int BLOCK, int TS = 1, int METHOD = 1, bool HAS_EX = false>
+__device__ __forceinline__ bool below_score_bound(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd,
+                                                  const double* ctd, int z, const double* log10_fact, double cutoff,
+                                                  const double* ln_fact = nullptr, int32_t predicted = 0, Extra ex = Extra{-1, 0.0}) {
+    if (!(cutoff > 0.0)) return false;
+    const int pre = bound_precheck<METHOD>(B, predicted);
+    if (pre >= 0) return pre != 0;
+    uint32_t c;
+    switch (z) {
+        case 0: case 1: case 2: c = count_possible_n<BLOCK, 1, TS, HAS_EX>(codes, B, tab, ntd, ctd, z, ex); break;
+        case 3: c = count_possible_n<BLOCK, 2, TS, HAS_EX>(codes, B, tab, ntd, ctd, z, ex); break;
+        case 4: c = count_possible_n<BLOCK, 3, TS, HAS_EX>(codes, B, tab, ntd, ctd, z, ex); break;
+        default: c = count_possible_n<BLOCK, 0, TS, HAS_EX>(codes, B, tab, ntd, ctd, z, ex); break;
+    }
+    return bound_below_cutoff<METHOD>(B, (int)(c & 0xFFFFu), (int)(c >> 16), log10_fact, cutoff, ln_fact, predicted);
+}
+
+// The same decision from the row's cell lists (k_cells.cuh): K2 walked the ladder once when it wrote the row; here every
+// (ion, fragment charge) is one 2-byte entry — the byte offset of its cell in the staged spectrum's table, whose top bit says
+// "nothing can be claimed in this cell".  n entries per side, eight per 16-byte unit.
+__device__ __forceinline__ uint32_t count_clean_list(const uint4* __restrict__ p, uint32_t n, uint32_t cells_s) {
+    uint32_t clean = 0;
+    auto word = [&](uint32_t w) { clean += (lds_u16(cells_s + (w & 0xFFFFu)) >> 15) + (lds_u16(cells_s + (w >> 16)) >> 15); };
+    const uint32_t full = n >> 3, rem = n & 7u;
+#pragma unroll 2
+    for (uint32_t i = 0; i < full; ++i) { const uint4 q = __ldg(p + i); word(q.x); word(q.y); word(q.z); word(q.w); }
+    if (rem) {
+        const uint4 q = __ldg(p + full);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (uint32_t j = 0; j < 7; ++j)
+            if (j < rem) clean += lds_u16(cells_s + ((w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu)) >> 15;
+    }
+    return clean;
+}
+template <int METHOD>
+__device__ __forceinline__ bool below_score_bound_lists(const uint4* __restrict__ row_lists, uint32_t chunks_side, uint32_t n_side, const BlobView& B,
+                                                        const double* log10_fact, double cutoff, const double* ln_fact, int32_t predicted) {
+    if (!(cutoff > 0.0)) return false;
+    const int pre = bound_precheck<METHOD>(B, predicted);
+    if (pre >= 0) return pre != 0;
+    const uint32_t cells_s = smem_addr(B.cells);
+    const uint32_t nb = n_side - count_clean_list(row_lists, n_side, cells_s);
+    const uint32_t ny = n_side - count_clean_list(row_lists + chunks_side, n_side, cells_s);
+    return bound_below_cutoff<METHOD>(B, (int)min(nb, 0xFFFFu), (int)min(ny, 0xFFFFu), log10_fact, cutoff, ln_fact, predicted);
 }
 
 // Precursor-window predicate exactly as DBSearchWorker.java:38-52 / FindCandidate...java:47-58:

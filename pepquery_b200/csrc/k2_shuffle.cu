@@ -10,6 +10,7 @@
 //   k2_place_mods PeptideInput.getModificationPeptide (:485-557): a fresh Random(2022) per (target form, shuffle)
 //                 re-places the form's modifications; then addFixedModification (:213-237).  One thread per row.
 #include "pq_internal.h"
+#include "k_cells.cuh"
 
 namespace pq {
 
@@ -252,7 +253,7 @@ __global__ void k2_dedup_hashed(const ShuffleSeq* __restrict__ seqs, const uint8
 __global__ void k2_place_mods(const ShuffleSeq* __restrict__ seqs, const ShuffleForm* __restrict__ forms, uint32_t n_forms,
                               const ShuffleMods* __restrict__ M, const uint8_t* __restrict__ raw,
                               const uint32_t* __restrict__ kept_index, const uint32_t* __restrict__ kept_count,
-                              uint8_t* __restrict__ rows) {
+                              uint8_t* __restrict__ rows, const ModTable* __restrict__ table, uint4* __restrict__ lists) {
     const uint32_t f = blockIdx.x;
     if (f >= n_forms) return;
     const ShuffleForm& F = forms[f];
@@ -308,6 +309,8 @@ __global__ void k2_place_mods(const ShuffleSeq* __restrict__ seqs, const Shuffle
         uint4* dst = reinterpret_cast<uint4*>(rows + (size_t)(F.row_base + k) * kRowBytes);
         dst[0] = make_uint4(w[0], w[1], w[2], w[3]); dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
         dst[2] = make_uint4(w[8], w[9], w[10], w[11]); dst[3] = make_uint4(w[12], w[13], w[14], w[15]);
+        // the spectrum-independent half of K1's Step-4 count pass: the cell of every (ion, fragment charge) of this row (k_cells.cuh)
+        if (lists) write_cell_lists(b, table, (int)F.list_nch, lists + F.list_base + (size_t)k * (2u * F.list_chunks), F.list_chunks);
     }
 }
 
@@ -315,7 +318,7 @@ __global__ void k2_place_mods(const ShuffleSeq* __restrict__ seqs, const Shuffle
 
 int launch_shuffles(const ShuffleSeq* seqs, uint32_t n_seqs, const ShuffleForm* forms, uint32_t n_forms,
                     const ShuffleMods* mods, uint8_t* raw, uint32_t* kept_index, uint32_t* kept_count, uint8_t* rows,
-                    uint32_t max_num, int64_t shuffle_seed, cudaStream_t st) {
+                    uint32_t max_num, int64_t shuffle_seed, const ModTable* mod_table, uint4* lists, cudaStream_t st) {
     if (n_seqs == 0) return 0;
     k2_generate<<<(n_seqs + kGenWarps - 1) / kGenWarps, 32 * kGenWarps, 0, st>>>(seqs, n_seqs, shuffle_seed, raw);
     uint32_t table = 64; while (table < 2 * max_num) table <<= 1;
@@ -330,7 +333,7 @@ int launch_shuffles(const ShuffleSeq* seqs, uint32_t n_seqs, const ShuffleForm* 
     }
     if (n_forms > 0) {
         dim3 grid(n_forms, (max_num + 127) / 128);
-        k2_place_mods<<<grid, 128, 0, st>>>(seqs, forms, n_forms, mods, raw, kept_index, kept_count, rows);
+        k2_place_mods<<<grid, 128, 0, st>>>(seqs, forms, n_forms, mods, raw, kept_index, kept_count, rows, mod_table, lists);
     }
     return 3;
 }

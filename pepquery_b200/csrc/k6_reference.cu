@@ -293,6 +293,7 @@ template <class F> bool select_flagged(const uint8_t* flags, uint32_t n, uint32_
 bool upload_target_keys_for_reference(cudaStream_t st, const std::vector<std::string>& targets, RefDeviceTable& T, std::string& err) {
     std::vector<uint64_t> tk;
     std::vector<std::string> ts(targets);
+    for (std::string& s : ts) for (char& c : s) if (c == 'I') c = 'L';      // DatabaseInput.add_target_peptides (pg/DatabaseInput.java:47-51): the digest is I -> L folded
     std::sort(ts.begin(), ts.end());
     ts.erase(std::unique(ts.begin(), ts.end()), ts.end());
     for (const std::string& s : ts) {

@@ -16,6 +16,7 @@
 #include <cub/cub.cuh>
 
 #include "pq_internal.h"
+#include "k_cells.cuh"
 
 namespace pq {
 
@@ -160,12 +161,17 @@ __global__ void k7_gather_comp(const pq_competitor* __restrict__ in, const uint3
 }
 
 __global__ void k7_flag_valid(const DevPsm* __restrict__ psms, uint32_t n, const int32_t* __restrict__ seq_of_form, uint8_t* __restrict__ seq_flag,
-                              uint8_t* __restrict__ form_flag, uint8_t* __restrict__ valid_flag, uint32_t* __restrict__ n_valid) {
+                              uint32_t* __restrict__ form_flag, uint8_t* __restrict__ valid_flag, uint32_t* __restrict__ n_valid) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = i < n ? psms[i].valid : 0;
     if (i < n) {
         valid_flag[i] = v ? 1 : 0;
-        if (v) { int32_t f = psms[i].form; form_flag[f] = 1; seq_flag[seq_of_form[f]] = 1; }
+        if (v) {
+            int32_t f = psms[i].form;
+            const int z = psms[i].charge;                                       // fragment charges 1 .. z-1 (JMatch.java:398-407)
+            atomicMax(&form_flag[f], (uint32_t)min(max(z - 1, 1), 255));
+            seq_flag[seq_of_form[f]] = 1;
+        }
     }
     const uint32_t b = __ballot_sync(0xffffffffu, v != 0);             // still-valid PSMs, one atomic per warp
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_valid, (uint32_t)__popc(b));
@@ -217,8 +223,10 @@ __global__ void k7_shuffle_plans(const uint8_t* __restrict__ seq_flag, TargetAux
 
 // Single CTA: compacts the flagged sequences / forms and lays out their shuffle rows (exclusive scans).
 constexpr int kLayoutThreads = 1024;
+struct Tri { uint32_t n, rows; unsigned long long units; };
+struct AddTri { __device__ Tri operator()(const Tri& a, const Tri& b) const { return Tri{a.n + b.n, a.rows + b.rows, a.units + b.units}; } };
 __global__ void __launch_bounds__(kLayoutThreads)
-k7_shuffle_layout(const uint8_t* __restrict__ seq_flag, const uint8_t* __restrict__ form_flag, const uint8_t* __restrict__ valid_flag, uint32_t n_psm,
+k7_shuffle_layout(const uint8_t* __restrict__ seq_flag, const uint32_t* __restrict__ form_flag, const uint8_t* __restrict__ valid_flag, uint32_t n_psm,
                   const ShuffleSeq* __restrict__ plans, TargetAux A, uint32_t* __restrict__ seq_slot, uint32_t* __restrict__ form_slot,
                   uint32_t* __restrict__ row_base, ShuffleSeq* __restrict__ seqs, ShuffleForm* __restrict__ forms, ShuffleTotals* __restrict__ totals) {
     typedef cub::BlockScan<uint2, kLayoutThreads> Scan;
@@ -239,27 +247,37 @@ k7_shuffle_layout(const uint8_t* __restrict__ seq_flag, const uint8_t* __restric
         if (threadIdx.x == 0) carry = make_uint2(c.x + tot.x, c.y + tot.y);
         __syncthreads();
     }
-    if (threadIdx.x == 0) { totals->n_seqs = carry.x; totals->raw_rows = carry.y; carry = make_uint2(0u, 0u); }
+    if (threadIdx.x == 0) { totals->n_seqs = carry.x; totals->raw_rows = carry.y; }
+    __syncthreads();
+    // forms: slot, first shuffle row, first cell-list unit (k_cells.cuh)
+    typedef cub::BlockScan<Tri, kLayoutThreads> ScanTri;
+    __shared__ typename ScanTri::TempStorage tmp3;
+    __shared__ Tri carry3;
+    if (threadIdx.x == 0) carry3 = Tri{0u, 0u, 0ull};
     __syncthreads();
     for (uint32_t base = 0; base < A.n_forms; base += kLayoutThreads) {
         uint32_t fi = base + threadIdx.x;
-        bool f = fi < A.n_forms && form_flag[fi];
+        const uint32_t nch = fi < A.n_forms ? form_flag[fi] : 0u;
+        const bool f = nch != 0u;
         int32_t sq = f ? A.seq_of_form[fi] : 0;
-        uint2 v = make_uint2(f ? 1u : 0u, f ? plans[sq].num : 0u), ex, tot;
-        Scan(tmp).ExclusiveScan(v, ex, make_uint2(0u, 0u), Add(), tot);
-        uint2 c = carry;
-        if (fi < A.n_forms) { form_slot[fi] = c.x + ex.x; row_base[fi] = c.y + ex.y; }
+        const uint32_t num = f ? plans[sq].num : 0u, len = f ? plans[sq].len : 0u;
+        const uint32_t lch = min(nch, (uint32_t)kListMaxCharge), chunks = f ? list_chunks_side((int)len, (int)lch) : 0u;
+        Tri v{f ? 1u : 0u, num, (unsigned long long)num * (2ull * chunks)}, ex, tot;
+        ScanTri(tmp3).ExclusiveScan(v, ex, Tri{0u, 0u, 0ull}, AddTri(), tot);
+        Tri c = carry3;
+        if (fi < A.n_forms) { form_slot[fi] = c.n + ex.n; row_base[fi] = c.rows + ex.rows; }
         if (f) {
             ShuffleForm F;
-            F.seq_slot = seq_slot[sq]; F.row_base = c.y + ex.y; F.n_mods = A.form_mods[fi].n_mods;
+            F.seq_slot = seq_slot[sq]; F.row_base = c.rows + ex.rows; F.n_mods = A.form_mods[fi].n_mods;
             for (int i = 0; i < PQ_MAX_FORM_MODS; ++i) F.mod[i] = A.form_mods[fi].mod[i];
-            forms[c.x + ex.x] = F;
+            F.len = len; F.list_nch = lch; F.list_chunks = chunks; F.pad = 0; F.list_base = c.units + ex.units;
+            forms[c.n + ex.n] = F;
         }
         __syncthreads();
-        if (threadIdx.x == 0) carry = make_uint2(c.x + tot.x, c.y + tot.y);
+        if (threadIdx.x == 0) carry3 = Tri{c.n + tot.n, c.rows + tot.rows, c.units + tot.units};
         __syncthreads();
     }
-    if (threadIdx.x == 0) { totals->n_forms = carry.x; totals->out_rows = carry.y; }       // totals->n_valid: counted by k7_flag_valid
+    if (threadIdx.x == 0) { totals->n_forms = carry3.n; totals->out_rows = carry3.rows; totals->list_units = carry3.units; }       // totals->n_valid: counted by k7_flag_valid
     (void)valid_flag; (void)n_psm;
 }
 
@@ -329,6 +347,7 @@ __global__ void k7_export(const DevPsm* __restrict__ psms, const uint32_t* __res
     pq_psm q;
     q.spectrum = p.spectrum; q.form = p.form; q.score = p.score; q.exp_mass = p.exp_mass; q.pep_mass = p.pep_mass; q.tol_ppm = tol_ppm_of(p);
     q.isotope_error = p.iso; q.count_b = p.ca; q.count_y = p.cb; q.n_db = p.n_db; q.total_db = p.total_db; q.n_random = p.n_random;
+    if (p.rank >= 2) { q.n_db = -1; q.total_db = -1; }       // psm_rank.txt: RankPSM.rankPSMs rewrites both for rank >= 2 (pg/RankPSM.java:89-92)
     q.total_random = p.total_random; q.valid = p.valid; q.p_value = p.p_value; q.rank = p.rank; q.n_ptm = p.n_ptm; q.confident = p.confident; q.reserved = 0;
     out[j] = q;
 }
@@ -409,7 +428,7 @@ int launch_gather_comp(const pq_competitor* in, const uint32_t* idx, uint32_t n,
     k7_gather_comp<<<blocks(n), 256, 0, st>>>(in, idx, n, out);
     return 1;
 }
-int launch_flag_valid(const DevPsm* psms, uint32_t n, const int32_t* seq_of_form, uint8_t* seq_flag, uint8_t* form_flag, uint8_t* valid_flag,
+int launch_flag_valid(const DevPsm* psms, uint32_t n, const int32_t* seq_of_form, uint8_t* seq_flag, uint32_t* form_flag, uint8_t* valid_flag,
                       ShuffleTotals* totals /* zeroed by the caller */, cudaStream_t st) {
     if (!n) return 0;
     k7_flag_valid<<<blocks(n), 256, 0, st>>>(psms, n, seq_of_form, seq_flag, form_flag, valid_flag, &totals->n_valid);
@@ -420,7 +439,7 @@ int launch_shuffle_plans(const uint8_t* seq_flag, const TargetAux& A, int32_t n_
     k7_shuffle_plans<<<blocks(A.n_seq, 64), 64, 0, st>>>(seq_flag, A, n_random, plans);
     return 1;
 }
-int launch_shuffle_layout(const uint8_t* seq_flag, const uint8_t* form_flag, const uint8_t* valid_flag, uint32_t n_psm, const ShuffleSeq* plans, const TargetAux& A,
+int launch_shuffle_layout(const uint8_t* seq_flag, const uint32_t* form_flag, const uint8_t* valid_flag, uint32_t n_psm, const ShuffleSeq* plans, const TargetAux& A,
                           uint32_t* seq_slot, uint32_t* form_slot, uint32_t* row_base, ShuffleSeq* seqs, ShuffleForm* forms, ShuffleTotals* totals, cudaStream_t st) {
     k7_shuffle_layout<<<1, kLayoutThreads, 0, st>>>(seq_flag, form_flag, valid_flag, n_psm, plans, A, seq_slot, form_slot, row_base, seqs, forms, totals);
     return 1;

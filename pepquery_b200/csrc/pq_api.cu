@@ -108,7 +108,8 @@ struct pq_ctx {
         return a;
     }
     // shuffles
-    DevBuf sh_seqs, sh_forms, sh_raw, sh_kidx, sh_kcnt, sh_rows, sh_pred;
+    DevBuf sh_seqs, sh_forms, sh_raw, sh_kidx, sh_kcnt, sh_rows, sh_pred, sh_lists;
+    bool have_lists = false;
     DevBuf sh_plans, sh_seq_flag, sh_form_flag, sh_valid_flag, sh_seq_slot, sh_form_slot, sh_row_base, sh_totals, sh_list, sh_order, sh_keys, sh_keys2;
     bool have_shuffles = false;
     // results
@@ -199,6 +200,7 @@ int32_t run_score(pq_ctx* ctx, JobKind kind, uint32_t n_jobs, const int32_t* row
     L.row_pred = row_pred;
     L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>();
     L.hit_capacity = hit_capacity; L.max_blob_bytes = ctx->max_blob; L.job_counter = ctx->d_scalars.as<uint32_t>() + 12;
+    if (kind == kJobShuffles && ctx->have_lists) { L.sh_forms = ctx->sh_forms.as<ShuffleForm>(); L.form_slot = ctx->sh_form_slot.as<uint32_t>(); L.lists = ctx->sh_lists.as<uint4>(); }
     ScoreConfig cfg = score_config(ctx, check_window);
     {
         int si = kind == kJobTargets ? 0 : kind == kJobCompetitors ? 1 : kind == kJobShuffles ? 2 : 3;
@@ -974,7 +976,9 @@ int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off,
     digest_proteins(ctx->P, ctx->codes.residue_mass, n_proteins, off, res, R.seqs, threads);
     mk.mark("digest + unique + sort");
     {   // DatabaseInput.protein_digest(db, target_peptides) removes the target sequences (:480-488)
-        std::vector<std::string> t(ctx->targets.seqs); std::sort(t.begin(), t.end());
+        std::vector<std::string> t(ctx->targets.seqs);
+        for (std::string& s : t) for (char& c : s) if (c == 'I') c = 'L';      // add_target_peptides folds I -> L (pg/DatabaseInput.java:47-51)
+        std::sort(t.begin(), t.end());
         R.seqs.erase(std::remove_if(R.seqs.begin(), R.seqs.end(), [&](const std::string& s) { return std::binary_search(t.begin(), t.end(), s); }), R.seqs.end());
     }
     // GeneratePeptideformWorker.set_mass_range over the matched spectra (GeneratePeptideformWorker.java:40-52)
@@ -1109,19 +1113,19 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
     const TargetAux A = ctx->aux();
     const size_t nseq = A.n_seq, nform = A.n_forms;
     // StatisticScoreCalc.run (:22-41): sequences with at least one still-valid PSM get shuffles
-    CU(ctx->sh_seq_flag.reserve(nseq + 64)); CU(ctx->sh_form_flag.reserve(nform + 64)); CU(ctx->sh_valid_flag.reserve((size_t)n_psm + 64));
+    CU(ctx->sh_seq_flag.reserve(nseq + 64)); CU(ctx->sh_form_flag.reserve(nform * 4 + 64)); CU(ctx->sh_valid_flag.reserve((size_t)n_psm + 64));
     CU(ctx->sh_plans.reserve(nseq * sizeof(ShuffleSeq))); CU(ctx->sh_seqs.reserve(nseq * sizeof(ShuffleSeq))); CU(ctx->sh_forms.reserve(nform * sizeof(ShuffleForm)));
     CU(ctx->sh_seq_slot.reserve(nseq * 4 + 64)); CU(ctx->sh_form_slot.reserve(nform * 4 + 64)); CU(ctx->sh_row_base.reserve(nform * 4 + 64));
     CU(ctx->sh_totals.reserve(64)); CU(ctx->sh_kcnt.reserve(nseq * 4 + 64));
-    CU(cudaMemsetAsync(ctx->sh_seq_flag.p, 0, nseq, st)); CU(cudaMemsetAsync(ctx->sh_form_flag.p, 0, nform, st));
+    CU(cudaMemsetAsync(ctx->sh_seq_flag.p, 0, nseq, st)); CU(cudaMemsetAsync(ctx->sh_form_flag.p, 0, nform * 4, st));
     ShuffleTotals tot; memset(&tot, 0, sizeof tot);
     {
         Timer t(ctx, &ctx->cnt.ms_shuffle);
         CU(cudaMemsetAsync(ctx->sh_totals.p, 0, sizeof(ShuffleTotals), st));
-        int k = launch_flag_valid(ctx->d_psm.as<DevPsm>(), n_psm, A.seq_of_form, ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint8_t>(), ctx->sh_valid_flag.as<uint8_t>(),
+        int k = launch_flag_valid(ctx->d_psm.as<DevPsm>(), n_psm, A.seq_of_form, ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint32_t>(), ctx->sh_valid_flag.as<uint8_t>(),
                                   ctx->sh_totals.as<ShuffleTotals>(), st);
         k += launch_shuffle_plans(ctx->sh_seq_flag.as<uint8_t>(), A, ctx->P.n_random, ctx->sh_plans.as<ShuffleSeq>(), st);
-        k += launch_shuffle_layout(ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint8_t>(), ctx->sh_valid_flag.as<uint8_t>(), n_psm, ctx->sh_plans.as<ShuffleSeq>(), A,
+        k += launch_shuffle_layout(ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint32_t>(), ctx->sh_valid_flag.as<uint8_t>(), n_psm, ctx->sh_plans.as<ShuffleSeq>(), A,
                                    ctx->sh_seq_slot.as<uint32_t>(), ctx->sh_form_slot.as<uint32_t>(), ctx->sh_row_base.as<uint32_t>(), ctx->sh_seqs.as<ShuffleSeq>(),
                                    ctx->sh_forms.as<ShuffleForm>(), ctx->sh_totals.as<ShuffleTotals>(), st);
         ctx->cnt.other_kernel_launches += (uint64_t)k;
@@ -1136,11 +1140,14 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
     CU(ctx->sh_raw.reserve((size_t)std::max(raw_rows, 1u) * kRowBytes)); CU(ctx->sh_kidx.reserve((size_t)std::max(raw_rows, 1u) * 4));
     CU(ctx->sh_rows.reserve((size_t)std::max(out_rows, 1u) * kRowBytes));
     if (ctx->P.score_method == 2) { CU(ctx->sh_pred.reserve((size_t)std::max(out_rows, 1u) * 8)); CU(cudaMemsetAsync(ctx->sh_rows.p, 0, (size_t)out_rows * kRowBytes, st)); }
+    // cell lists of the shuffle rows (k_cells.cuh): only the bounded count pass reads them
+    ctx->have_lists = !score_config(ctx, 0).score_all && tot.list_units > 0 && !getenv("PQ_NO_CELL_LISTS");
+    if (ctx->have_lists && ctx->sh_lists.reserve((size_t)tot.list_units * 16) != cudaSuccess) { cudaGetLastError(); ctx->have_lists = false; }      // no room: K1 walks the ladders
     {
         Timer t(ctx, &ctx->cnt.ms_shuffle);
         int k = launch_shuffles(ctx->sh_seqs.as<ShuffleSeq>(), tot.n_seqs, ctx->sh_forms.as<ShuffleForm>(), tot.n_forms,
                                 ctx->d_shufmods.as<ShuffleMods>(), ctx->sh_raw.as<uint8_t>(), ctx->sh_kidx.as<uint32_t>(), ctx->sh_kcnt.as<uint32_t>(),
-                                ctx->sh_rows.as<uint8_t>(), max_num, ctx->P.shuffle_seed, st);
+                                ctx->sh_rows.as<uint8_t>(), max_num, ctx->P.shuffle_seed, ctx->d_mods.as<ModTable>(), ctx->have_lists ? ctx->sh_lists.as<uint4>() : nullptr, st);
         if (ctx->P.score_method == 2) k += launch_predict(ctx->sh_rows.as<uint8_t>(), out_rows, ctx->d_mods.as<ModTable>(), ctx->P.itol, ctx->sh_pred.as<int32_t>(), st);
         ctx->cnt.other_kernel_launches += (uint64_t)k;
     }
@@ -1173,6 +1180,8 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
     CU(cudaGetLastError());
     mk.mark("jobs + score (launch)");
     (void)T;
+    CU(cudaStreamSynchronize(st));            // synchronous at return (header contract): a kernel fault surfaces here, not in a later call
+    mk.mark("wait");
     ctx->step_done = 4;
     return PQ_OK;
 }
@@ -1213,6 +1222,7 @@ int32_t pq_rank_and_validate(pq_ctx* ctx) {
     // rank inside each spectrum segment (pg/RankPSM.java:107-149) + CParameter.passed_psm_validation, on the device
     ctx->cnt.other_kernel_launches += (uint64_t)launch_rank(ctx->d_psm.as<DevPsm>(), ctx->n_psm, ctx->d_seg_start.as<uint32_t>(), ctx->st);
     CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->st));
     return PQ_OK;
 }
 

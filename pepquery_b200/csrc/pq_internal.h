@@ -94,6 +94,7 @@ struct ScoreConfig {
     int32_t score_all;        // Step 4: compute every shuffle's score in full (no upper-bound decision)
 };
 
+struct ShuffleForm;
 struct ScoreLaunch {
     uint32_t n_codes = kMaxCodes;   // residue codes in use (26 letters + the (residue, modification) pairs of this search)
     JobKind kind;
@@ -109,6 +110,8 @@ struct ScoreLaunch {
     double* pair_score; int32_t* pair_a; int32_t* pair_b;  // kJobPairs: per-candidate outputs
     uint32_t max_blob_bytes;
     uint32_t* job_counter;                                 // device word, zeroed by the launcher: next job to hand out
+    // Step 4: cell lists of the shuffle rows (k_cells.cuh); null = walk the ladder in the count pass
+    const ShuffleForm* sh_forms; const uint32_t* form_slot; const uint4* lists;
     // Step 5
     double ptm_delta; int32_t ptm_position; int32_t ptm_residue_code;
 };
@@ -140,6 +143,12 @@ struct ShuffleForm {           // one per target form that needs shuffles
     uint32_t row_base;         // first output row
     uint32_t n_mods;
     int8_t   mod[PQ_MAX_FORM_MODS];   // modification ids (index into ShuffleMods), target list order
+    // cell lists of the form's shuffle rows (k_cells.cuh): row k at lists + (list_base + k * 2 * list_chunks) 16-byte units
+    uint32_t len;              // peptide length L
+    uint32_t list_nch;         // fragment charges held in the lists (1..kListMaxCharge): the largest a still-valid PSM of the form needs
+    uint32_t list_chunks;      // units per side
+    uint32_t pad;
+    uint64_t list_base;
 };
 struct ShuffleMods {           // the search's modifications as K2 needs them
     int32_t n_mods;            // var then fixed
@@ -152,7 +161,7 @@ struct ShuffleMods {           // the search's modifications as K2 needs them
 };
 int launch_shuffles(const ShuffleSeq* seqs, uint32_t n_seqs, const ShuffleForm* forms, uint32_t n_forms,
                     const ShuffleMods* mods, uint8_t* raw /* n_seqs*num*64 */, uint32_t* kept_index, uint32_t* kept_count,
-                    uint8_t* rows, uint32_t max_num, int64_t shuffle_seed, cudaStream_t st);
+                    uint8_t* rows, uint32_t max_num, int64_t shuffle_seed, const ModTable* table, uint4* lists /* may be null */, cudaStream_t st);
 
 // packing helpers (k3_window.cu)
 int launch_precursor_mass(int64_t n, const double* prec_mz, const int32_t* charge, double* mass, uint64_t* key, int32_t* idx, cudaStream_t st);
@@ -202,7 +211,7 @@ struct SegAgg {                 // Step-3 result per matched spectrum
 };
 struct DevCounters { unsigned long long pairs[4]; unsigned long long bytes[4]; unsigned long long bounded; };
 struct FormMods { uint32_t n_mods; int8_t mod[PQ_MAX_FORM_MODS]; };     // a target form's modifications, list order
-struct ShuffleTotals { uint32_t n_seqs, raw_rows, n_forms, out_rows, n_valid; };
+struct ShuffleTotals { uint32_t n_seqs, raw_rows, n_forms, out_rows, n_valid, pad; uint64_t list_units; };
 
 struct TargetAux {              // per-target-table device arrays
     const uint32_t* form_of_row;      // [rows]  mass-sorted row -> public form
@@ -225,10 +234,10 @@ int launch_step3_aggregate(const JobResult* res, uint32_t n_seg, int n_iso, cons
 int launch_comp3_rows(const Hit* hits, uint32_t nh, const SegAgg* agg, uint32_t n_seg, const uint32_t* seg_start, const DevPsm* psms,
                       const int32_t* caller_index, const double* r_mass, pq_competitor* rows, uint64_t* keys, uint32_t* idx, uint32_t* count, cudaStream_t st);
 int launch_gather_comp(const pq_competitor* in, const uint32_t* idx, uint32_t n, pq_competitor* out, cudaStream_t st);
-int launch_flag_valid(const DevPsm* psms, uint32_t n, const int32_t* seq_of_form, uint8_t* seq_flag, uint8_t* form_flag, uint8_t* valid_flag,
-                      ShuffleTotals* totals /* zeroed by the caller */, cudaStream_t st);
+int launch_flag_valid(const DevPsm* psms, uint32_t n, const int32_t* seq_of_form, uint8_t* seq_flag, uint32_t* form_flag /* largest fragment-charge count of a valid PSM, 0 = none */,
+                      uint8_t* valid_flag, ShuffleTotals* totals /* zeroed by the caller */, cudaStream_t st);
 int launch_shuffle_plans(const uint8_t* seq_flag, const TargetAux& A, int32_t n_random, ShuffleSeq* plans, cudaStream_t st);
-int launch_shuffle_layout(const uint8_t* seq_flag, const uint8_t* form_flag, const uint8_t* valid_flag, uint32_t n_psm, const ShuffleSeq* plans, const TargetAux& A,
+int launch_shuffle_layout(const uint8_t* seq_flag, const uint32_t* form_flag, const uint8_t* valid_flag, uint32_t n_psm, const ShuffleSeq* plans, const TargetAux& A,
                           uint32_t* seq_slot, uint32_t* form_slot, uint32_t* row_base, ShuffleSeq* seqs, ShuffleForm* forms, ShuffleTotals* totals, cudaStream_t st);
 int launch_step4_jobs(const DevPsm* psms, const uint32_t* order, uint32_t n_valid, const uint32_t* form_slot, const ShuffleForm* forms, const uint32_t* kept_count,
                       Job* jobs, cudaStream_t st);

@@ -3,12 +3,12 @@
 In PepQuery the Java host imports Unimod itself (ModificationDB.importPTMsFromUnimod,
 OpenModificationSearch/ModificationDB.java:334-533) and would pass the resolved table through the shim.  For tests and
 the bench the same table is derived from the reference's resources/unimod.xml by tools/make_golden.py and committed as
-tests/golden/unimod_ptms.tsv (record_id, title, site, position, classification, mono_mass)."""
+pepquery_b200/data/unimod_ptms.tsv (record_id, title, site, position, classification, mono_mass)."""
 import os
 
 from . import _abi
 
-_DEFAULT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "unimod_ptms.tsv")
+_DEFAULT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "unimod_ptms.tsv")
 
 _POS = {
     ("Anywhere", True): _abi.PQ_MOD_ANYWHERE,

@@ -259,6 +259,64 @@ def test_rank_ties_fall_back_to_the_peptide_string():
     assert all(sorted(int(x["rank"]) for x in v) == list(range(1, len(v) + 1)) for v in by_spec.values())
 
 
+def _targets_with_a_planted_isoleucine(prot, tgt, params):
+    """The synthetic targets plus digest peptides of the database itself spelt with I for L (the digest is I -> L folded,
+    DigestProteinWorker.java:66-70; the reference folds the targets too before it subtracts them, DatabaseInput.java:47-51)."""
+    from oracle import pq_oracle
+    o = pq_oracle.Oracle(params); o.set_targets(*tgt)
+    empty = dict(prec_mz=np.zeros(0), charge=np.zeros(0, dtype=np.int32), peak_off=np.zeros(1, dtype=np.uint64), mz=np.zeros(0), inten=np.zeros(0))
+    o.load_spectra(empty); o.step2(); o.build_reference(*prot)
+    planted = [s.replace("L", "I", 1) for s in o.reference_sequences() if "L" in s and 8 <= len(s) <= 20][:6]
+    assert len(planted) == 6
+    toff, tres = tgt
+    seqs = [bytes(tres[int(toff[i]):int(toff[i + 1])]).decode() for i in range(len(toff) - 1)] + planted
+    off = np.cumsum([0] + [len(s) for s in seqs]).astype(np.uint32)
+    return (off, np.frombuffer("".join(seqs).encode(), dtype=np.uint8).copy()), planted
+
+
+@pytest.mark.parametrize("host_reference", [False, True])
+def test_target_with_isoleucine_is_removed_from_the_reference(host_reference, monkeypatch):
+    """A target that contains I and is (I -> L folded) a digest peptide of the database must not compete with itself in
+    Step 3 (DatabaseInput.add_target_peptides, pg/DatabaseInput.java:47-51 + protein_digest :480-488)."""
+    if host_reference:
+        monkeypatch.setenv("PQ_HOST_REFERENCE", "1")
+    prot = synth.proteins(300)
+    p = _abi.default_params(n_random=100)
+    tgt, planted = _targets_with_a_planted_isoleucine(prot, synth.targets(20), p)
+    sp = synth.spectra(900, tgt, prot)
+    g, o, got = full_compare(p, sp, tgt, prot)
+    fg, _ = g.target_forms()
+    hit = [r for r in got if fg[int(r["form"])].seq.decode() in planted]
+    assert len(hit) >= 3                                           # spectra of the planted peptides were matched ...
+    assert any(int(r["n_db"]) == 0 for r in hit)                   # ... and the peptide does not beat itself from the reference side
+    refs = {bytes(f.seq).split(b"\0")[0].decode() for f in g.reference_forms()[0][:g.reference_forms()[1]]}
+    assert not any(s.replace("I", "L") in refs for s in planted)
+
+
+@pytest.mark.parametrize("method", [1, 2])
+def test_cell_lists_decide_like_the_ladder_walk(method, monkeypatch):
+    """Step-4 count pass from the rows' cell lists (written by K2, k_cells.cuh) against the ladder walk inside K1
+    (PQ_NO_CELL_LISTS) and against every shuffle scored in full: same records, same number of shuffles decided by the bound.
+    Charges 2-4 (1-3 fragment charges) and lengths 8-25 are all in the synthetic mix; one long and one short target are added."""
+    prot = synth.proteins(600)
+    toff, tres = synth.targets(60)
+    seqs = [bytes(tres[int(toff[i]):int(toff[i + 1])]).decode() for i in range(len(toff) - 1)] + ["ACDEFGHK", "MCDEFGHLMNPQSTVWYACDEFGHLMNPQSTVWYACDEFMK", "GASPVTCK"]
+    off = np.cumsum([0] + [len(s) for s in seqs]).astype(np.uint32)
+    tgt = (off, np.frombuffer("".join(seqs).encode(), dtype=np.uint8).copy())
+    sp = synth.spectra(3000, tgt, prot)
+    p = _abi.default_params(n_random=300, score_method=method)
+    g, o, got = full_compare(p, sp, tgt, prot)
+    c = g.counters()
+    assert c.pairs_step4_bounded > 0.5 * c.pairs_step4
+    monkeypatch.setenv("PQ_NO_CELL_LISTS", "1")
+    g2 = run_gpu(p, sp, tgt, prot)
+    c2 = g2.counters()
+    assert g2.psms().tobytes() == got.tobytes() and c2.pairs_step4_bounded == c.pairs_step4_bounded and c2.pairs_step4 == c.pairs_step4
+    monkeypatch.delenv("PQ_NO_CELL_LISTS")
+    g3 = run_gpu(_abi.default_params(n_random=300, score_method=method, score_all_shuffles=1), sp, tgt, prot)
+    assert g3.psms().tobytes() == got.tobytes() and g3.counters().pairs_step4_bounded == 0
+
+
 @pytest.mark.parametrize("enzyme", [2, 5, 6, 9, 11, 12, 16, 17])
 def test_enzymes(data, enzyme):
     """K6's digest with other cleavage rules of the reference's -e table (cut after / cut before / blocked by the next

@@ -5,7 +5,8 @@ reference tree at /root/reference, which does not exist on the GPU box):
 
   mod_masses.json        name -> monoisotopic mass, from the reference's resources/top_modifications.tsv (the only numeric
                          ground truth the reference tree ships; it pins the compomics atom masses)
-  unimod_ptms.tsv        the Step-5 PTM specificities derived from resources/unimod.xml with the filters of
+  ../pepquery_b200/data/unimod_ptms.tsv
+                         the Step-5 PTM specificities derived from resources/unimod.xml with the filters of
                          ModificationDB.importPTMsFromUnimod (OpenModificationSearch/ModificationDB.java:334-533)
   oracle_vectors.json    outputs of the CPU oracle on a small seeded search (regression anchor for the oracle itself and the
                          fixture the GPU tests replay without needing the oracle build)
@@ -47,7 +48,7 @@ def unimod_ptms():
         for sp in mod.findall("u:specificity", ns):
             cls = sp.get("classification")
             rows.append((rid, title, sp.get("site"), sp.get("position"), cls, mono))
-    with open(os.path.join(OUT, "unimod_ptms.tsv"), "w") as f:
+    with open(os.path.join(ROOT, "pepquery_b200", "data", "unimod_ptms.tsv"), "w") as f:
         f.write("record_id\ttitle\tsite\tposition\tclassification\tmono_mass\n")
         for r in rows:
             f.write("%d\t%s\t%s\t%s\t%s\t%r\n" % r)
