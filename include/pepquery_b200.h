@@ -107,7 +107,12 @@ typedef struct pq_params {
                                    every usable spectrum, chunk by chunk while the next chunk of peaks is still crossing
                                    PCIe, so the upload hides it.  0: pq_step2_match_targets prepares only the spectra that
                                    have a target in their precursor window (less HBM, nothing overlapped).  Same results */
-    int32_t reserved0;
+    int32_t candidate_first;    /* 1 (default): when pq_set_targets came before pq_load_spectra and the m/z and intensity arrays are in
+                                   pinned (page-locked, device-mapped) memory, only spectra with a target form in their precursor window
+                                   have their peaks moved to the device (the only ones Steps 2-5 read; the reference keeps exactly
+                                   those in SpectraInput.spectraMap, pg/SpectraInput.java:243-254): a kernel gathers them from the
+                                   caller's arrays over PCIe.  A later pq_set_targets with other targets then needs a new
+                                   pq_load_spectra (PQ_ERR_STATE otherwise).  0: every peak is uploaded.  Same results */
 } pq_params;
 
 /* One peptide form (sequence + placed modifications) as the caller sees it. */
@@ -142,7 +147,7 @@ typedef struct pq_psm {
     int32_t rank;               /* pg/RankPSM.java:36-148, 1-based within the spectrum                 */
     int32_t n_ptm;              /* Step 5: PTM forms scoring > (>= with hc) the target; -1 = not run   */
     int32_t confident;          /* CParameter.passed_psm_validation(len,p,n_db,rank,n_ptm)             */
-    int32_t reserved;
+    int32_t charge;             /* precursor charge the PSM was scored with (2 or 3 for a spectrum loaded with charge 0) */
 } pq_psm;
 
 /* Row of detail.txt / ptm.txt: a competitor that matched a target spectrum. */
@@ -191,12 +196,16 @@ int32_t pq_create(const pq_params* params, pq_ctx** out);
 int32_t pq_destroy(pq_ctx* ctx);
 
 /* Spectrum loader.  Replaces the MGF->task loop of pg/SpectraInput.java:142-198 (readMSMSfast):
- * packs peak lists into precursor-mass-sorted CSR device arrays with a 0.1-Da bucket index.
- * Peaks may be in any order; spectra with n_peaks <= min_peaks are kept but never scored
- * (SpectraInput.java:183).  charge[i] must be >= 1.  The upload runs in chunks and hides work that does not depend on the
- * matched spectra (spectrum preparation with prepare_at_load; the target table when pq_set_targets came first; the digest of
- * a database handed over by pq_stage_reference); with all five arrays in pinned host memory it starts before the offsets
- * have been validated.  A load that fails leaves the context without spectra. */
+ * packs peak lists into precursor-mass-sorted CSR device arrays; a precursor window is a binary search on the sorted masses
+ * followed by the reference's exact predicate (0.1-Da bucket within +-1 and |delta| <= tol) per candidate.
+ * Peaks may be in any order; spectra with n_peaks <= min_peaks are kept but never scored (SpectraInput.java:183).
+ * charge[i] >= 1, or 0 for a spectrum without a charge: it is searched as z = 2 and, only if that saves no PSM, as z = 3
+ * (pg/FindCandidateSpectraAndScoreWorker.java:96-228); pq_psm.charge tells which.
+ * With pq_set_targets called first and the m/z and intensity arrays in pinned memory only the spectra that have a target in
+ * their precursor window are moved to the device (pq_params.candidate_first); otherwise every peak is uploaded in chunks.
+ * Either way the work that does not depend on the matched spectra runs under the transfer (spectrum preparation with
+ * prepare_at_load; the digest of a database handed over by pq_stage_reference).  A load that fails leaves the context
+ * without spectra and with nothing in flight. */
 int32_t pq_load_spectra(pq_ctx* ctx, int64_t n_spectra, const double* precursor_mz, const int32_t* charge,
                         const uint64_t* peak_offset /* n+1 */, const double* mz, const double* intensity);
 
@@ -209,8 +218,8 @@ int32_t pq_get_target_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int64_t
 /* Reference database.  Replaces DatabaseInput.generate_reference_peptide_index
  * (pg/DatabaseInput.java:402-556) + DigestProteinWorker.run (OpenModificationSearch/DigestProteinWorker.java:64-137)
  * + GeneratePeptideformWorker.run (:25-52): digest, I->L, unique, minus targets, isoforms, mass window,
- * mass-sorted device table with 0.1-Da buckets.  Call after pq_step2 (the mass window is taken from the
- * matched spectra, GeneratePeptideformWorker.set_mass_range). */
+ * mass-sorted device table (window lookup = binary search + the exact +-1-bucket predicate).  Call after pq_step2 (the mass
+ * window is taken from the matched spectra, GeneratePeptideformWorker.set_mass_range). */
 int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* seq_offset /* n+1 */, const char* residues);
 /* Optional: hand the protein database over early (any time before pq_build_reference).  The bytes go to the device at once; the
  * part of the index build that does not depend on the spectra — digestion, unique sequences, minus the targets
@@ -236,9 +245,6 @@ int32_t pq_rank_and_validate(pq_ctx* ctx);
 int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms);
 
 int32_t pq_get_psms(pq_ctx* ctx, pq_psm* out, int64_t capacity, int64_t* n_psms);
-/* Multi-GPU gather (SURVEY.md 8e): exports the PSM records (same layout and order as pq_get_psms) into a device buffer
- * owned by the context and returns its device address, so that the one collective of the path (NCCL gather of per-shard
- * PSM records) reads them without a host round trip.  The address stays valid until the next call on this context. */
 /* Step-1 novelty filter (pg/InputProcessor.java:379-448 with the default FM-index mapping, pg/PepMapping.java:60-107):
  * nhit[i] = 1 when target sequence i occurs as a substring of some protein of the reference database, I and L
  * indistinguishable, case ignored; 0 otherwise.  Exact substring semantics (not digest membership).  Independent of the
@@ -250,6 +256,9 @@ int32_t pq_find_in_proteome(pq_ctx* ctx, int32_t n_seq, const uint32_t* seq_offs
  * pair per PSM in pq_get_psms order: score minus the best detail.txt (Step 3) / ptm.txt (Step 5) row of the same spectrum;
  * the plain score where the spectrum has no such row or the step has not run.  NULL outputs: only n_psms is written. */
 int32_t pq_get_delta_scores(pq_ctx* ctx, double* ref_delta_score, double* mod_delta_score, int64_t capacity, int64_t* n_psms);
+/* Multi-GPU gather (SURVEY.md 8e): exports the PSM records (same layout and order as pq_get_psms) into a device buffer
+ * owned by the context and returns its device address, so that the one collective of the path (NCCL gather of per-shard
+ * PSM records) reads them without a host round trip.  The address stays valid until the next call on this context. */
 int32_t pq_export_psms_device(pq_ctx* ctx, uint64_t* device_address, int64_t* n_psms);
 int32_t pq_get_competitors(pq_ctx* ctx, int32_t step /* 3 or 5 */, pq_competitor* out, int64_t capacity, int64_t* n_rows);
 /* Shuffled sequences of one target sequence, in generation order (for parity checks of the RNG stream). */

@@ -236,8 +236,16 @@ struct Peptide {
 };
 struct Spectrum {
     double prec_mz = 0.0;
-    int charge = 0;
+    int charge = 0;                        // charge in use (a spectrum without CHARGE gets 2, then 3: FindCandidate...java:96-228)
+    int given_charge = 0;                  // as loaded; 0 = the MGF block had no CHARGE line
     std::vector<double> mz, inten;         // file order
+};
+// "Hoisted" cost model (bench.py cpu_baseline): everything scorePeptide2Spectrum derives from the spectrum alone, computed
+// once per spectrum instead of once per pair.  Same functions, same results; the as-written model is the default.
+struct Prepared {
+    double limit = 0.0; std::vector<int> order; std::vector<double> smz;      // annotator: matchable peaks, m/z ascending
+    std::unordered_map<double, double> peakSet;                               // hyperscore survivors: m/z -> normalised intensity
+    bool mvh_ok = false; std::unordered_map<double, int> peakCls; int classCounts[4] = {0, 0, 0, 0}; int npk = 0;   // MVH
 };
 struct Params {
     pq_params p;
@@ -385,23 +393,29 @@ static double intensity_limit(const Spectrum& sp, double frac) {
 }
 
 // JMatch.getSpectrumAnnotation (PSMMatch/JMatch.java:388-466) -> PeptideSpectrumAnnotator on the RAW spectrum.
-static std::vector<IonMatch> annotate(const Params& P, const Peptide& pep, const Spectrum& sp) {
+static void annotator_index(const Spectrum& sp, double& limit, std::vector<int>& order, std::vector<double>& smz) {
+    limit = intensity_limit(sp, 0.05);             // JMatch.java:427,430 (intensityLimit 0.05, percentile)
+    // SpectrumIndex: built per annotator call in the reference (new PeptideSpectrumAnnotator per pair); here the
+    // matchable peaks (intensity >= limit, A2) in ascending m/z (stable), searched by bisection.
+    order.clear();
+    for (size_t i = 0; i < sp.mz.size(); ++i) if (sp.inten[i] >= limit) order.push_back((int)i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return sp.mz[a] < sp.mz[c]; });
+    smz.resize(order.size());
+    for (size_t i = 0; i < order.size(); ++i) smz[i] = sp.mz[order[i]];
+}
+static std::vector<IonMatch> annotate(const Params& P, const Peptide& pep, const Spectrum& sp, const Prepared* H = nullptr) {
     std::vector<IonMatch> out;
     int z = sp.charge;
     std::vector<int> charges;                      // JMatch.java:398-407
     if (z == 1) charges.push_back(1); else for (int c = 1; c < z; ++c) charges.push_back(c);
-    double limit = intensity_limit(sp, 0.05);      // JMatch.java:427,430 (intensityLimit 0.05, percentile)
     std::vector<double> b, y;
     fragment_masses(P, pep, b, y);
     int L = (int)pep.seq.size();
     double itol = P.p.itol;
-    // SpectrumIndex: built per annotator call in the reference (new PeptideSpectrumAnnotator per pair); here the
-    // matchable peaks (intensity >= limit, A2) in ascending m/z (stable), searched by bisection.
-    std::vector<int> order;
-    for (size_t i = 0; i < sp.mz.size(); ++i) if (sp.inten[i] >= limit) order.push_back((int)i);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return sp.mz[a] < sp.mz[c]; });
-    std::vector<double> smz(order.size());
-    for (size_t i = 0; i < order.size(); ++i) smz[i] = sp.mz[order[i]];
+    double limit_l; std::vector<int> order_l; std::vector<double> smz_l;
+    if (!H) annotator_index(sp, limit_l, order_l, smz_l);
+    const std::vector<int>& order = H ? H->order : order_l;
+    const std::vector<double>& smz = H ? H->smz : smz_l;
     for (int type = 0; type < 2; ++type) {         // A5: b then y
         const std::vector<double>& m = type == 0 ? b : y;
         for (int num = 1; num <= L - 1; ++num) {
@@ -512,16 +526,21 @@ struct JMatch {
 struct Score { double score = 0.0; int a = 0; int b = 0; bool died = false; };
 
 // HyperscoreMatch.calcHyperScore (PSMMatch/HyperscoreMatch.java:61-187)
-static Score calc_hyperscore(const Params& P, const Peptide& pep, const Spectrum& sp) {
+static void hyperscore_peak_set(const Params& P, const Spectrum& sp, std::unordered_map<double, double>& peakSet) {
     JMatch m(P, sp);
-    std::vector<IonMatch> matches = annotate(P, pep, sp);               // initialize(false,2) -> getSpectrumAnnotation
     m.js.resetPeaks();
     // SpectrumPreProcessing :47-59
     m.isotopePass(0.95); m.removeParentPeak(); m.removeLowMasses(); m.removeLowIntensityPeak();
     m.isotopePass(1.5); m.filterByPeakCount(50); m.normalizePeaks(100.0);
-    std::unordered_map<double, double> peakSet;                         // :71-78
+    peakSet.clear();                                                    // :71-78
     m.js.getPeaks(); m.js.sortByMZ();
     for (auto& p : m.js.getPeaks()) peakSet[p.mz] = p.inten;
+}
+static Score calc_hyperscore(const Params& P, const Peptide& pep, const Spectrum& sp, const Prepared* H = nullptr) {
+    std::vector<IonMatch> matches = annotate(P, pep, sp, H);            // initialize(false,2) -> getSpectrumAnnotation
+    std::unordered_map<double, double> peakSet_l;
+    if (!H) hyperscore_peak_set(P, sp, peakSet_l);
+    const std::unordered_map<double, double>& peakSet = H ? H->peakSet : peakSet_l;
     std::unordered_set<double> used;
     int cb = 0, cy = 0; double dScore = 0.0;
     for (const IonMatch& im : matches) {                                // :89-147
@@ -550,16 +569,15 @@ static double ln_combin(int n, int k, bool& died) {                     // :91-1
     if (n < k) { died = true; return 0; }    // commons-math throws -> the pool task dies; treated as "not scored"
     return factorial_log(n) - factorial_log(n - k) - factorial_log(k);
 }
-static Score calc_mvh(const Params& P, const Peptide& pep, const Spectrum& sp) {
+// the spectrum-only part of calcMVH: false = fewer than 7 peaks survive (mvh stays 0.0)
+static bool mvh_peak_classes(const Params& P, const Spectrum& sp, std::unordered_map<double, int>& peakCls, int classCounts[4], int& npk) {
     JMatch m(P, sp);
-    std::vector<IonMatch> matches = annotate(P, pep, sp);               // initialize(false,3)
-    Score r;
     m.js.resetPeaks();
     // SpectrumPreProcessing :76-89
     m.filterPeakByRange(200.0, 2000.0); m.removeParentPeak(); m.filterByTIC(); m.isotopePass(0.95); m.filterByPeakCount(300);
     {   // classifyPeakIntensities :46-73
         int total = (int)m.js.getPeaks().size();
-        if (total < 7) return r;                                        // mvh stays 0.0
+        if (total < 7) return false;
         int npeak = (int)std::floor(1.0 * total / 7.0);
         m.js.sortByIntensity();
         auto& v = m.js.getPeaks();
@@ -568,6 +586,21 @@ static Score calc_mvh(const Params& P, const Peptide& pep, const Spectrum& sp) {
         for (int i = total - 1 - n1; i >= total - n1 - n2; --i) v[i].cls = 1;
         for (int i = total - 1 - n1 - n2; i >= 0; --i) v[i].cls = 2;
     }
+    peakCls.clear();                                                    // :234-241
+    for (int i = 0; i < 4; ++i) classCounts[i] = 0;
+    for (auto& p : m.js.getPeaks()) { peakCls[p.mz] = p.cls; classCounts[p.cls]++; }
+    npk = (int)m.js.getPeaks().size();
+    classCounts[3] = (int)(java_round((int)(2000.0 - 200.0) / (P.p.itol * 2.0)) - npk);   // :242-244
+    return true;
+}
+static Score calc_mvh(const Params& P, const Peptide& pep, const Spectrum& sp, const Prepared* H = nullptr) {
+    std::vector<IonMatch> matches = annotate(P, pep, sp, H);            // initialize(false,3)
+    Score r;
+    std::unordered_map<double, int> peakCls_l; int classCounts_l[4]; int npk_l = 0;
+    if (H ? !H->mvh_ok : !mvh_peak_classes(P, sp, peakCls_l, classCounts_l, npk_l)) return r;      // mvh stays 0.0
+    const std::unordered_map<double, int>& peakCls = H ? H->peakCls : peakCls_l;
+    const int* classCounts = H ? H->classCounts : classCounts_l;
+    const int npk = H ? H->npk : npk_l;
     // predicted peaks :150-227
     std::vector<double> b, y;
     fragment_masses(P, pep, b, y);
@@ -603,11 +636,6 @@ static Score calc_mvh(const Params& P, const Peptide& pep, const Spectrum& sp) {
         r.died = true;   // val[0] on an empty array throws in the reference
         return r;
     }
-    std::unordered_map<double, int> peakCls;                            // :234-241
-    int classCounts[4] = {0, 0, 0, 0};
-    for (auto& p : m.js.getPeaks()) { peakCls[p.mz] = p.cls; classCounts[p.cls]++; }
-    int npk = (int)m.js.getPeaks().size();
-    classCounts[3] = (int)(java_round((int)(2000.0 - 200.0) / (P.p.itol * 2.0)) - npk);   // :242-244
     int key[4] = {0, 0, 0, 0};
     std::unordered_set<double> used;
     for (const IonMatch& im : matches) {                                // :246-279
@@ -630,9 +658,14 @@ static Score calc_mvh(const Params& P, const Peptide& pep, const Spectrum& sp) {
 }
 
 // PeptideSearchMT.scorePeptide2Spectrum (pg/PeptideSearchMT.java:1144-1251)
-static Score score_peptide_to_spectrum(const Params& P, const Peptide& pep, const Spectrum& sp) {
-    if (P.p.score_method == 2) return calc_mvh(P, pep, sp);
-    return calc_hyperscore(P, pep, sp);
+static Score score_peptide_to_spectrum(const Params& P, const Peptide& pep, const Spectrum& sp, const Prepared* H = nullptr) {
+    if (P.p.score_method == 2) return calc_mvh(P, pep, sp, H);
+    return calc_hyperscore(P, pep, sp, H);
+}
+static void prepare_spectrum(const Params& P, const Spectrum& sp, Prepared& H) {
+    annotator_index(sp, H.limit, H.order, H.smz);
+    if (P.p.score_method == 2) H.mvh_ok = mvh_peak_classes(P, sp, H.peakCls, H.classCounts, H.npk);
+    else hyperscore_peak_set(P, sp, H.peakSet);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -772,7 +805,7 @@ struct RefForm { Peptide pep; double mass; int seq_index; };
 // The search context (Steps 2-5)
 // ---------------------------------------------------------------------------------------------------
 struct Psm {
-    int spectrum, form; Score sc; double exp_mass, pep_mass; int iso;
+    int spectrum, form; Score sc; double exp_mass, pep_mass; int iso; int charge = 0;
     int n_db = 0, total_db = 0, n_random = -1, total_random = -1; bool valid = true; double p_value = 100.0;
     int rank = 0, n_ptm = -1, confident = 0;
 };
@@ -790,6 +823,15 @@ struct Ctx {
     uint64_t pairs[4] = {0, 0, 0, 0};
     int threads = 1;
     std::string err;
+    // cost model of the CPU baseline: false = as written (pre-processing per pair), true = hoisted (once per spectrum)
+    bool hoisted = false;
+    std::vector<Prepared> prep;                           // hoisted: per spectrum, filled by Step 2 for the spectra it scores
+    // GeneratePeptideformWorker mass range forced by the caller (sampled-parity tests: the window of a larger run)
+    bool forced_window = false; double forced_lo = 0.0, forced_hi = 0.0;
+    // SpectraInput.pep2targeted_spectra (PSMT:264-309): target sequence -> spectra it may be scored against, with the PSM status
+    std::vector<std::pair<int, int>> targeted;            // (target sequence index, spectrum index) in the caller's order
+    std::map<std::string, std::map<int, int>> pep2targeted;   // sequence -> spectrum -> PsmType (0 no_spectrum_match, 1 spectrum_matched)
+    const Prepared* H(int si) const { return hoisted ? &prep[(size_t)si] : nullptr; }
 };
 
 static double precursor_mass(const Spectrum& s) { return s.prec_mz * s.charge - s.charge * g_a.proton; }   // Precursor.getMass
@@ -813,35 +855,58 @@ template <class F> static void parallel_for(int threads, int64_t n, F f) {
     for (auto& t : th) t.join();
 }
 
-// Step 2: FindCandidateSpectraAndScoreWorker.run (pg/FindCandidateSpectraAndScoreWorker.java:33-100)
+// Step 2: FindCandidateSpectraAndScoreWorker.run (pg/FindCandidateSpectraAndScoreWorker.java:33-229)
 static void step2(Ctx& C) {
     const Params& P = C.P;
     std::map<long, std::vector<int>> pIndex;                            // SpectraInput.java:96-109
     for (size_t f = 0; f < C.target_forms.size(); ++f) pIndex[java_round(C.target_form_mass[f] * 10.0)].push_back((int)f);
     std::vector<std::vector<Psm>> per(C.spectra.size());
     std::vector<uint64_t> cnt(C.spectra.size(), 0);
+    if (C.hoisted) C.prep.assign(C.spectra.size(), Prepared());
+    for (auto& kv : C.pep2targeted) for (auto& st : kv.second) st.second = 0;      // PsmType.no_spectrum_match
+    for (auto& sp : C.spectra) sp.charge = sp.given_charge;
+    std::vector<std::vector<std::pair<const std::string*, int>>> touched(C.spectra.size());     // targeted pairs seen in a window
     parallel_for(C.threads, (int64_t)C.spectra.size(), [&](int64_t si) {
-        const Spectrum& sp = C.spectra[si];
+        Spectrum& sp = C.spectra[si];
         if ((int)sp.mz.size() <= P.p.min_peaks) return;                 // SpectraInput.java:183
-        double exp_mass = precursor_mass(sp);
-        for (auto& im : isotope_masses(P, exp_mass)) {
-            double mass = im.first;
-            long va = java_round(mass * 10.0);
-            for (long i = va - 1; i <= va + 1; ++i) {
-                auto it = pIndex.find(i);
-                if (it == pIndex.end()) continue;
-                for (int f : it->second) {
-                    if (!in_window(P, C.target_form_mass[f], mass)) continue;
-                    Score sc = score_peptide_to_spectrum(P, C.target_forms[f], sp);
-                    cnt[si]++;
-                    if (!sc.died && sc.score > P.p.min_score) {
-                        Psm p; p.spectrum = (int)si; p.form = f; p.sc = sc; p.exp_mass = mass; p.pep_mass = C.target_form_mass[f]; p.iso = im.second;
-                        per[si].push_back(p);
+        // one pass of the window loop with the precursor charge set to z; returns whether a PSM was saved
+        auto pass = [&](int z, bool update_status) -> bool {
+            sp.charge = z;
+            bool prepared = false, find = false;
+            double exp_mass = precursor_mass(sp);
+            for (auto& im : isotope_masses(P, exp_mass)) {
+                double mass = im.first;
+                long va = java_round(mass * 10.0);
+                for (long i = va - 1; i <= va + 1; ++i) {
+                    auto it = pIndex.find(i);
+                    if (it == pIndex.end()) continue;
+                    for (int f : it->second) {
+                        if (!in_window(P, C.target_form_mass[f], mass)) continue;
+                        if (!C.pep2targeted.empty()) {                  // :60-74
+                            const std::string& seq = C.target_forms[f].seq;
+                            auto pt = C.pep2targeted.find(seq);
+                            if (pt != C.pep2targeted.end()) {
+                                if (!pt->second.count((int)si)) continue;                       // not a spectrum named for this peptide
+                                if (update_status) touched[si].push_back({&pt->first, (int)si});  // PsmType.spectrum_matched
+                            }
+                        }
+                        if (C.hoisted && !prepared) { prepare_spectrum(P, sp, C.prep[(size_t)si]); prepared = true; }
+                        Score sc = score_peptide_to_spectrum(P, C.target_forms[f], sp, C.H((int)si));
+                        cnt[si]++;
+                        if (!sc.died && sc.score > P.p.min_score) {
+                            Psm p; p.spectrum = (int)si; p.form = f; p.sc = sc; p.exp_mass = mass; p.pep_mass = C.target_form_mass[f]; p.iso = im.second; p.charge = z;
+                            per[si].push_back(p);
+                            find = true;
+                        }
                     }
                 }
             }
-        }
+            return find;
+        };
+        if (sp.given_charge >= 1) pass(sp.given_charge, true);
+        else if (!pass(2, false)) pass(3, false);                       // no CHARGE: z = 2, and z = 3 only if z = 2 saved nothing (:96-228)
     });
+    for (auto& v : touched) for (auto& t : v) C.pep2targeted[*t.first][t.second] = 1;
     C.psms.clear();
     for (size_t si = 0; si < per.size(); ++si) { C.pairs[0] += cnt[si]; for (auto& p : per[si]) C.psms.push_back(p); }
     std::stable_sort(C.psms.begin(), C.psms.end(), [](const Psm& a, const Psm& b) { return a.spectrum != b.spectrum ? a.spectrum < b.spectrum : a.form < b.form; });
@@ -863,6 +928,7 @@ static void build_reference(Ctx& C, const std::vector<std::string>& proteins) {
     for (auto& p : C.psms) matched.insert(p.spectrum);
     for (int si : matched) { double m = precursor_mass(C.spectra[si]); mn = std::min(mn, m); mx = std::max(mx, m); }
     double min_mass = mn - 250.0 - 5.0, max_mass = mx + 250.0 + 5.0;    // ModificationDB.leftMass/rightMass = -250/250
+    if (C.forced_window) { min_mass = C.forced_lo; max_mass = C.forced_hi; }
     C.ref_seqs.assign(seqs.begin(), seqs.end());
     C.ref_forms.clear();
     for (size_t si = 0; si < C.ref_seqs.size(); ++si) {
@@ -905,7 +971,7 @@ static void step3(Ctx& C) {
                     if (in_window(P, pm, mass)) {
                         spectra_matched = true;
                         R.n_matched++;
-                        Score sc = score_peptide_to_spectrum(P, C.ref_forms[rf].pep, sp);
+                        Score sc = score_peptide_to_spectrum(P, C.ref_forms[rf].pep, sp, C.H(si));
                         R.pairs++;
                         double tmp = sc.score;
                         pq_competitor row{si, rf, -1, -1, tmp, pm};
@@ -948,7 +1014,7 @@ static void step4(Ctx& C) {
         int nRand = 0;
         for (const std::string& rs : rp) {
             Peptide rpep = get_modification_peptide(P, C.target_forms[p.form], rs);
-            Score sc = score_peptide_to_spectrum(P, rpep, sp);
+            Score sc = score_peptide_to_spectrum(P, rpep, sp, C.H(p.spectrum));
             cnt[wi]++;
             if (sc.score >= p.sc.score) nRand++;
         }
@@ -1052,7 +1118,7 @@ static void step5(Ctx& C, const std::vector<pq_ptm>& ptms) {
                         for (int site : possible_sites(base_pep.seq, M)) {
                             if (occupied.count(site)) continue;
                             Peptide mp = base_pep; mp.mods.push_back({base + (int)ti2, site});
-                            Score sc = score_peptide_to_spectrum(PX, mp, sp);
+                            Score sc = score_peptide_to_spectrum(PX, mp, sp, C.H(si));
                             R.pairs++;
                             if (sc.score >= P.p.min_score) R.rows.push_back({si, rf, (int)ti2, site, sc.score, pep_mass});
                             if (P.p.fast) {
@@ -1166,7 +1232,7 @@ int32_t orc_load_spectra(orc_ctx* o, int64_t n, const double* pmz, const int32_t
     o->c.spectra.resize(n);
     for (int64_t i = 0; i < n; ++i) {
         Spectrum& s = o->c.spectra[i];
-        s.prec_mz = pmz[i]; s.charge = charge[i];
+        s.prec_mz = pmz[i]; s.charge = charge[i]; s.given_charge = charge[i];
         s.mz.assign(mz + off[i], mz + off[i + 1]); s.inten.assign(inten + off[i], inten + off[i + 1]);
     }
     return 0;
@@ -1228,7 +1294,7 @@ int32_t orc_get_psms(orc_ctx* o, pq_psm* out, int64_t cap, int64_t* n) {
         q.tol_ppm = tol_ppm_of(p); q.isotope_error = p.iso; q.count_b = p.sc.a; q.count_y = p.sc.b;
         q.n_db = p.n_db; q.total_db = p.total_db; q.n_random = p.n_random; q.total_random = p.total_random;
         if (p.rank >= 2) { q.n_db = -1; q.total_db = -1; }                  // psm_rank.txt: RankPSM.rankPSMs (pg/RankPSM.java:89-92)
-        q.valid = p.valid ? 1 : 0; q.p_value = p.p_value; q.rank = p.rank; q.n_ptm = p.n_ptm; q.confident = p.confident;
+        q.valid = p.valid ? 1 : 0; q.p_value = p.p_value; q.rank = p.rank; q.n_ptm = p.n_ptm; q.confident = p.confident; q.charge = p.charge;
     }
     return 0;
 }
@@ -1275,6 +1341,48 @@ int32_t orc_find_in_proteome(int32_t n_seq, const uint32_t* seq_off, const char*
         std::string q; for (uint32_t k = seq_off[t]; k < seq_off[t + 1]; ++k) q.push_back(fold(res[k]));
         nhit[t] = 0;
         for (const std::string& p : prots) if (p.find(q) != std::string::npos) { nhit[t] = 1; break; }
+    }
+    return 0;
+}
+// cost model of the timed baseline: 0 = as written (pre-processing redone per pair), 1 = hoisted (once per spectrum)
+int32_t orc_set_cost_model(orc_ctx* o, int32_t hoisted) { o->c.hoisted = hoisted != 0; return 0; }
+// force the mass range of the reference table (open interval), e.g. the range of a larger run a sample is compared with
+int32_t orc_set_reference_window(orc_ctx* o, int32_t on, double lo, double hi) { o->c.forced_window = on != 0; o->c.forced_lo = lo; o->c.forced_hi = hi; return 0; }
+// SpectraInput.pep2targeted_spectra (PSMT:264-309): pairs (target sequence, spectrum); n = 0 clears the list
+int32_t orc_set_targeted_psms(orc_ctx* o, int64_t n, const int32_t* target_seq, const int32_t* spectrum) {
+    Ctx& C = o->c;
+    C.targeted.clear(); C.pep2targeted.clear();
+    for (int64_t i = 0; i < n; ++i) {
+        if (target_seq[i] < 0 || (size_t)target_seq[i] >= C.target_seqs.size()) return PQ_ERR_BAD_ARG;
+        C.targeted.push_back({target_seq[i], spectrum[i]});
+        C.pep2targeted[C.target_seqs[(size_t)target_seq[i]]][spectrum[i]] = 0;
+    }
+    return 0;
+}
+// PeptideSearchMT.export_targeted_psm_status (PSMT:1484-1589) + TargetedPSM.get_psm_status (pg/TargetedPSM.java:29-46): one
+// PsmType ordinal per targeted pair (0 no_spectrum_match, 2 low_score, 3 high_p_value, 4 better_ref_pep, 5 better_ref_pep_with_mod,
+// 6 not_top_rank, 7 confident; 8 invalid_peptide is the Java host's call, it owns the Step-1 verdict).
+int32_t orc_get_targeted_status(orc_ctx* o, int32_t* out, int64_t cap, int64_t* n) {
+    Ctx& C = o->c; *n = (int64_t)C.targeted.size();
+    if (!out) return 0;
+    if (cap < *n) return PQ_ERR_CAPACITY;
+    std::map<std::pair<std::string, int>, const Psm*> best;             // (peptide, spectrum) -> row with the highest rank (:1513-1527)
+    for (const Psm& p : C.psms) {
+        auto key = std::make_pair(C.target_forms[(size_t)p.form].seq, p.spectrum);
+        auto it = best.find(key);
+        if (it == best.end() || it->second->rank > p.rank) best[key] = &p;
+    }
+    for (size_t i = 0; i < C.targeted.size(); ++i) {
+        const std::string& seq = C.target_seqs[(size_t)C.targeted[i].first];
+        auto it = best.find(std::make_pair(seq, C.targeted[i].second));
+        if (it != best.end()) {
+            const Psm& p = *it->second;
+            const int len = (int)seq.size();
+            const bool pv = (len <= 8 && p.p_value <= 0.05) || (len > 8 && p.p_value <= 0.01);      // passed_p_value_validation
+            out[i] = p.rank >= 2 ? 6 : (p.n_db >= 1 ? 4 : (!pv ? 3 : (p.n_ptm >= 1 ? 5 : 7)));
+        } else {
+            out[i] = C.pep2targeted[seq][C.targeted[i].second] == 0 ? 0 : 2;
+        }
     }
     return 0;
 }

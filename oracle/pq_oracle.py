@@ -158,6 +158,27 @@ class Oracle:
         self.L.orc_get_delta_scores(self.h, _p(a), _p(b), C.c_int64(n.value), C.byref(n))
         return a[:n.value], b[:n.value]
 
+    def set_cost_model(self, hoisted):
+        """False: as written (spectrum pre-processing redone per pair, like scorePeptide2Spectrum); True: hoisted (once per spectrum)."""
+        self.L.orc_set_cost_model(self.h, C.c_int32(1 if hoisted else 0))
+
+    def set_reference_window(self, lo, hi):
+        """Forces the (open) mass range of the reference table instead of taking it from the matched spectra."""
+        self.L.orc_set_reference_window(self.h, C.c_int32(1), C.c_double(lo), C.c_double(hi))
+
+    def set_targeted_psms(self, target_seq, spectrum):
+        """SpectraInput.pep2targeted_spectra: (target sequence index, spectrum index) pairs; call after set_targets."""
+        a = np.ascontiguousarray(target_seq, dtype=np.int32); b = np.ascontiguousarray(spectrum, dtype=np.int32)
+        rc = self.L.orc_set_targeted_psms(self.h, C.c_int64(len(a)), _p(a), _p(b))
+        assert rc == 0
+
+    def targeted_status(self):
+        n = C.c_int64()
+        self.L.orc_get_targeted_status(self.h, None, C.c_int64(0), C.byref(n))
+        out = np.zeros(max(1, n.value), dtype=np.int32)
+        self.L.orc_get_targeted_status(self.h, _p(out), C.c_int64(n.value), C.byref(n))
+        return out[:n.value]
+
     def pairs(self):
         out = np.zeros(4, dtype=np.uint64)
         self.L.orc_get_pairs(self.h, _p(out))

@@ -441,14 +441,14 @@ __device__ __forceinline__ bool below_score_bound(const uint32_t* codes, const B
 // The same decision from the row's cell lists (k_cells.cuh): K2 walked the ladder once when it wrote the row; here every
 // (ion, fragment charge) is one 2-byte entry — the byte offset of its cell in the staged spectrum's table, whose top bit says
 // "nothing can be claimed in this cell".  n entries per side, eight per 16-byte unit.
-__device__ __forceinline__ uint32_t count_clean_list(const uint4* __restrict__ p, uint32_t n, uint32_t cells_s) {
+__device__ __forceinline__ uint32_t count_clean_list(const uint4* __restrict__ p, size_t stride, uint32_t n, uint32_t cells_s) {
     uint32_t clean = 0;
     auto word = [&](uint32_t w) { clean += (lds_u16(cells_s + (w & 0xFFFFu)) >> 15) + (lds_u16(cells_s + (w >> 16)) >> 15); };
     const uint32_t full = n >> 3, rem = n & 7u;
 #pragma unroll 2
-    for (uint32_t i = 0; i < full; ++i) { const uint4 q = __ldg(p + i); word(q.x); word(q.y); word(q.z); word(q.w); }
+    for (uint32_t i = 0; i < full; ++i) { const uint4 q = __ldg(p + (size_t)i * stride); word(q.x); word(q.y); word(q.z); word(q.w); }
     if (rem) {
-        const uint4 q = __ldg(p + full);
+        const uint4 q = __ldg(p + (size_t)full * stride);
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (uint32_t j = 0; j < 7; ++j)
@@ -457,14 +457,14 @@ __device__ __forceinline__ uint32_t count_clean_list(const uint4* __restrict__ p
     return clean;
 }
 template <int METHOD>
-__device__ __forceinline__ bool below_score_bound_lists(const uint4* __restrict__ row_lists, uint32_t chunks_side, uint32_t n_side, const BlobView& B,
+__device__ __forceinline__ bool below_score_bound_lists(const uint4* __restrict__ row_lists, size_t stride, uint32_t chunks_side, uint32_t n_side, const BlobView& B,
                                                         const double* log10_fact, double cutoff, const double* ln_fact, int32_t predicted) {
     if (!(cutoff > 0.0)) return false;
     const int pre = bound_precheck<METHOD>(B, predicted);
     if (pre >= 0) return pre != 0;
     const uint32_t cells_s = smem_addr(B.cells);
-    const uint32_t nb = n_side - count_clean_list(row_lists, n_side, cells_s);
-    const uint32_t ny = n_side - count_clean_list(row_lists + chunks_side, n_side, cells_s);
+    const uint32_t nb = n_side - count_clean_list(row_lists, stride, n_side, cells_s);
+    const uint32_t ny = n_side - count_clean_list(row_lists + (size_t)chunks_side * stride, stride, n_side, cells_s);
     return bound_below_cutoff<METHOD>(B, (int)min(nb, 0xFFFFu), (int)min(ny, 0xFFFFu), log10_fact, cutoff, ln_fact, predicted);
 }
 

@@ -310,7 +310,7 @@ __global__ void k2_place_mods(const ShuffleSeq* __restrict__ seqs, const Shuffle
         dst[0] = make_uint4(w[0], w[1], w[2], w[3]); dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
         dst[2] = make_uint4(w[8], w[9], w[10], w[11]); dst[3] = make_uint4(w[12], w[13], w[14], w[15]);
         // the spectrum-independent half of K1's Step-4 count pass: the cell of every (ion, fragment charge) of this row (k_cells.cuh)
-        if (lists) write_cell_lists(b, table, (int)F.list_nch, lists + F.list_base + (size_t)k * (2u * F.list_chunks), F.list_chunks);
+        if (lists) write_cell_lists(b, table, (int)F.list_nch, lists + F.list_base + k, F.list_chunks, (size_t)F.list_rows);
     }
 }
 

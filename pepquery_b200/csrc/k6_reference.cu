@@ -176,7 +176,7 @@ __global__ void k6_set_u32(uint32_t* p, uint32_t v) { *p = v; }
 template <bool FILL>
 __global__ void k6_expand(const uint32_t* __restrict__ uniq, uint32_t n_uniq, const uint32_t* __restrict__ pos, const uint32_t* __restrict__ len,
                           const uint8_t* __restrict__ res, ExpandCfg C, uint32_t* __restrict__ count, const uint32_t* __restrict__ form_off,
-                          uint8_t* __restrict__ rows, double* __restrict__ mass_out, uint32_t* __restrict__ seq_id) {
+                          uint8_t* __restrict__ rows, double* __restrict__ mass_out, uint32_t* __restrict__ seq_id, FormMods* __restrict__ fm_out = nullptr) {
     uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_uniq) return;
     const uint32_t c = uniq[u];
@@ -232,6 +232,16 @@ __global__ void k6_expand(const uint32_t* __restrict__ uniq, uint32_t n_uniq, co
                         dst[0] = make_uint4(w[0], w[1], w[2], w[3]); dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
                         dst[2] = make_uint4(w[8], w[9], w[10], w[11]); dst[3] = make_uint4(w[12], w[13], w[14], w[15]);
                         mass_out[out0 + emitted] = mass; seq_id[out0 + emitted] = u;
+                        if (fm_out) {        // the form's modification list in the reference's order: the variable picks, then the fixed mods (PeptideInput.java:141-179, 213-237)
+                            FormMods fm; fm.n_mods = 0;
+                            for (int i = 0; i < PQ_MAX_FORM_MODS; ++i) { fm.mod[i] = 0; fm.site[i] = 0; }
+                            for (int i = 0; i < kk; ++i) { fm.mod[fm.n_mods] = (int8_t)slot_mod[pick[i]]; fm.site[fm.n_mods] = slot_site[pick[i]]; ++fm.n_mods; }
+                            for (int f = 0; f < C.n_fixed; ++f) {
+                                uint64_t m = fixed_sites[f];
+                                while (m && fm.n_mods < PQ_MAX_FORM_MODS) { int site = __ffsll((long long)m) - 1; m &= m - 1; fm.mod[fm.n_mods] = (int8_t)(C.n_var + f); fm.site[fm.n_mods] = (uint8_t)site; ++fm.n_mods; }
+                            }
+                            fm_out[out0 + emitted] = fm;
+                        }
                     }
                     ++emitted;
                 }
@@ -462,6 +472,86 @@ bool expand_reference_on_device(cudaStream_t st, const pq_params& P, const Codes
     k6_gather_rows<<<(n_forms * 4 + 255) / 256, 256, 0, st>>>(d_idx2.as<uint32_t>(), n_forms, d_rows.as<uint8_t>(), d_mass.as<double>(), d_seq.as<uint32_t>(),
                                                               T.rows->as<uint8_t>(), T.mass->as<double>(), T.seq_id.as<uint32_t>());
     RB(cudaStreamSynchronize(st));
+    RB(cudaGetLastError());
+    *launches += 8;
+    return true;
+}
+
+__global__ void k6_u32_to_i32(const uint32_t* __restrict__ in, uint32_t n, int32_t* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)in[i];
+}
+__global__ void k6_gather_target_rows(const uint32_t* __restrict__ order, uint32_t n, const uint8_t* __restrict__ rows_in, const double* __restrict__ mass_in,
+                                      uint8_t* __restrict__ rows, double* __restrict__ mass) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t i = t >> 2, q = t & 3;
+    if (i >= n) return;
+    uint32_t s = order[i];
+    reinterpret_cast<uint4*>(rows)[(size_t)i * 4 + q] = reinterpret_cast<const uint4*>(rows_in)[(size_t)s * 4 + q];
+    if (q == 0) mass[i] = mass_in[s];
+}
+
+// The TARGET peptide table on the device: CreatePeptideInputWorker -> PeptideInput.calcPeptideIsoforms (pg/PeptideInput.java:114-237)
+// with the same expansion kernel as the reference table, every form kept (no mass window), then a stable mass sort.
+// Public form order = generation order (sequence order, then calcPeptideIsoforms order); device row order = mass order;
+// form_of_row translates.  flat = the sequences back to back (letters 'A'..'Z'), off[n_seq + 1].
+bool build_target_table_on_device(cudaStream_t st, const Codes& codes, uint32_t n_seq, const uint32_t* off, const char* flat, TargetDeviceTable& T,
+                                  uint64_t* launches, std::string& err) {
+    T.n_forms = 0;
+    if (n_seq == 0) return true;
+    const uint32_t total = off[n_seq];
+    DevBuf& d_res = T.w[0]; DevBuf& d_pos = T.w[1]; DevBuf& d_len = T.w[2]; DevBuf& d_ident = T.w[3]; DevBuf& d_count = T.w[4]; DevBuf& d_foff = T.w[5];
+    DevBuf& d_rows = T.w[6]; DevBuf& d_mass = T.w[7]; DevBuf& d_seq = T.w[8]; DevBuf& d_mkey = T.w[9]; DevBuf& d_mkey2 = T.w[10]; DevBuf& d_idx = T.w[11]; DevBuf& tmp = T.w[12];
+    std::vector<uint32_t> h((size_t)n_seq * 3);                  // pos | len | identity
+    std::vector<uint8_t> letters(total);
+    for (uint32_t i = 0; i < n_seq; ++i) { h[i] = off[i]; h[n_seq + i] = off[i + 1] - off[i]; h[2 * (size_t)n_seq + i] = i; }
+    for (uint32_t i = 0; i < total; ++i) letters[i] = (uint8_t)(flat[i] - 'A');
+    RB(d_res.reserve(total + 64)); RB(d_pos.reserve((size_t)n_seq * 12)); RB(T.seq_off->reserve(((size_t)n_seq + 1) * 4)); RB(T.seq_letters->reserve(total + 64));
+    RB(cudaMemcpyAsync(d_res.p, flat, total, cudaMemcpyHostToDevice, st));
+    RB(cudaMemcpyAsync(d_pos.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st));
+    RB(cudaMemcpyAsync(T.seq_off->p, off, ((size_t)n_seq + 1) * 4, cudaMemcpyHostToDevice, st));
+    RB(cudaMemcpyAsync(T.seq_letters->p, letters.data(), total, cudaMemcpyHostToDevice, st));
+    const uint32_t* pos = d_pos.as<uint32_t>(); const uint32_t* len = pos + n_seq; const uint32_t* ident = pos + 2 * (size_t)n_seq;
+    (void)d_len; (void)d_ident;
+    ExpandCfg ec; memset(&ec, 0, sizeof ec);
+    ec.n_var = codes.n_var; ec.n_fixed = codes.n_fixed; ec.max_var = codes.max_var; ec.lo = -1.0; ec.hi = 1.7976931348623157e308;
+    for (int m = 0; m < codes.n_var + codes.n_fixed; ++m) {
+        ec.position[m] = codes.mods[(size_t)m].position; ec.residue_mask[m] = codes.mods[(size_t)m].residue_mask; ec.delta[m] = codes.mods[(size_t)m].delta;
+        memcpy(ec.code_of[m], codes.shuffle.code_of[m], 26); ec.term_code[m] = codes.shuffle.term_code[m];
+    }
+    for (int i = 0; i < 26; ++i) ec.residue_mass[i] = codes.residue_mass[i];
+    RB(d_count.reserve(((size_t)n_seq + 2) * 4)); RB(d_foff.reserve(((size_t)n_seq + 2) * 4));
+    RB(cudaMemsetAsync(d_count.as<uint32_t>() + n_seq, 0, 4, st));
+    k6_expand<false><<<(n_seq + 127) / 128, 128, 0, st>>>(ident, n_seq, pos, len, d_res.as<uint8_t>(), ec, d_count.as<uint32_t>(), nullptr, nullptr, nullptr, nullptr);
+    {
+        size_t bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, bytes, d_count.as<uint32_t>(), d_foff.as<uint32_t>(), (int)n_seq + 1, st);
+        RB(tmp.reserve(bytes + 64));
+        RB(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, d_count.as<uint32_t>(), d_foff.as<uint32_t>(), (int)n_seq + 1, st));
+    }
+    uint32_t n_forms = 0;
+    RB(cudaMemcpyAsync(&n_forms, d_foff.as<uint32_t>() + n_seq, 4, cudaMemcpyDeviceToHost, st));
+    RB(cudaStreamSynchronize(st));           // also: the host staging vectors above are free again
+    *launches += 3;
+    T.n_forms = n_forms;
+    if (n_forms == 0) return true;
+    RB(d_rows.reserve((size_t)n_forms * kRowBytes)); RB(d_mass.reserve((size_t)n_forms * 8)); RB(d_seq.reserve((size_t)n_forms * 4));
+    RB(T.form_mods->reserve((size_t)n_forms * sizeof(FormMods))); RB(T.seq_of_form->reserve((size_t)n_forms * 4)); RB(T.form_of_row->reserve((size_t)n_forms * 4));
+    RB(T.rows->reserve((size_t)n_forms * kRowBytes)); RB(T.mass->reserve((size_t)n_forms * 8));
+    k6_expand<true><<<(n_seq + 127) / 128, 128, 0, st>>>(ident, n_seq, pos, len, d_res.as<uint8_t>(), ec, nullptr, d_foff.as<uint32_t>(), d_rows.as<uint8_t>(),
+                                                         d_mass.as<double>(), d_seq.as<uint32_t>(), T.form_mods->as<FormMods>());
+    k6_u32_to_i32<<<(n_forms + 255) / 256, 256, 0, st>>>(d_seq.as<uint32_t>(), n_forms, T.seq_of_form->as<int32_t>());
+    // stable sort by mass: equal masses keep generation order
+    RB(d_mkey.reserve((size_t)n_forms * 8)); RB(d_mkey2.reserve((size_t)n_forms * 8)); RB(d_idx.reserve((size_t)n_forms * 4));
+    k6_mass_keys<<<(n_forms + 255) / 256, 256, 0, st>>>(d_mass.as<double>(), n_forms, d_mkey.as<uint64_t>(), d_idx.as<uint32_t>());
+    {
+        size_t bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_mkey.as<uint64_t>(), d_mkey2.as<uint64_t>(), d_idx.as<uint32_t>(), T.form_of_row->as<uint32_t>(), (int)n_forms, 0, 64, st);
+        RB(tmp.reserve(bytes + 64));
+        RB(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_mkey.as<uint64_t>(), d_mkey2.as<uint64_t>(), d_idx.as<uint32_t>(), T.form_of_row->as<uint32_t>(), (int)n_forms, 0, 64, st));
+    }
+    k6_gather_target_rows<<<(n_forms * 4 + 255) / 256, 256, 0, st>>>(T.form_of_row->as<uint32_t>(), n_forms, d_rows.as<uint8_t>(), d_mass.as<double>(),
+                                                                     T.rows->as<uint8_t>(), T.mass->as<double>());
     RB(cudaGetLastError());
     *launches += 8;
     return true;

@@ -44,7 +44,7 @@ __global__ void k7_build_psms(const Hit* __restrict__ hits, const uint32_t* __re
     p.charge = sp.charge[h.spectrum]; p.iso = h.iso; p.len = (int32_t)t_rows[(size_t)h.cand * kRowBytes];
     p.score = h.score; p.exp_mass = h.mass; p.pep_mass = t_mass[h.cand]; p.p_value = 100.0;
     p.ca = h.count_a; p.cb = h.count_b; p.n_db = 0; p.total_db = 0; p.n_random = -1; p.total_random = -1; p.valid = 1; p.rank = 0; p.n_ptm = -1; p.confident = 0;
-    p.seg = 0; p.strrank = A.strrank[p.form];
+    p.seg = 0; p.pad = 0;
     psms[i] = p;
     head[i] = (i == 0 || hits[idx[i - 1]].spectrum != h.spectrum) ? 1u : 0u;
 }
@@ -66,13 +66,13 @@ __global__ void k7_out_keys(const DevPsm* __restrict__ psms, uint32_t n, uint64_
     idx[i] = i;
 }
 
-__global__ void k7_job_counters(const Job* __restrict__ jobs, const JobResult* __restrict__ res, uint32_t n, const uint64_t* __restrict__ sp_off, int which,
-                                DevCounters* __restrict__ c) {
+__global__ void k7_job_counters(const Job* __restrict__ jobs, const JobResult* __restrict__ res, uint32_t n, const uint32_t* __restrict__ sp_npeaks, int which,
+                                DevCounters* __restrict__ c, const uint8_t* __restrict__ skip_job) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long pairs = 0, bytes = 0, bounded = 0;
-    if (i < n) {
+    if (i < n && !(skip_job && skip_job[i])) {
         int32_t s = jobs[i].spectrum;
-        unsigned long long P = sp_off[s + 1] - sp_off[s];
+        unsigned long long P = sp_npeaks[s];
         pairs = res[i].n_in_window; bounded = res[i].pad;
         bytes = pairs * (16ull * P + 96ull);
     }
@@ -270,7 +270,7 @@ k7_shuffle_layout(const uint8_t* __restrict__ seq_flag, const uint32_t* __restri
             ShuffleForm F;
             F.seq_slot = seq_slot[sq]; F.row_base = c.rows + ex.rows; F.n_mods = A.form_mods[fi].n_mods;
             for (int i = 0; i < PQ_MAX_FORM_MODS; ++i) F.mod[i] = A.form_mods[fi].mod[i];
-            F.len = len; F.list_nch = lch; F.list_chunks = chunks; F.pad = 0; F.list_base = c.units + ex.units;
+            F.len = len; F.list_nch = lch; F.list_chunks = chunks; F.list_rows = num; F.list_base = c.units + ex.units;
             forms[c.n + ex.n] = F;
         }
         __syncthreads();
@@ -312,17 +312,41 @@ __global__ void k7_step4_apply(const Job* __restrict__ jobs, const JobResult* __
 
 __device__ __forceinline__ double tol_ppm_of(const DevPsm& p) { return __ddiv_rn(__dmul_rn(1.0e6, __dsub_rn(p.pep_mass, p.exp_mass)), p.pep_mass); }
 
+// Order of the texts "peptide|modification" of two target forms (RankPSMCompare's last key, pg/RankPSM.java:139-147; the
+// modification text is ModificationDB.getModificationString, "id@site[%.4f]" joined by ';', "-" without modifications).
+// Compared without building the strings: the sequences letter by letter — where one is a proper prefix of the other its '|'
+// (0x7C) meets a letter, so the SHORTER one is greater —, then the modification lists piece by piece.  Every piece ends in
+// the only ']' it contains, so no piece is a prefix of another and the first differing piece decides by its own text order
+// (piece_rank, from the host); a list that ends first is a proper prefix and sorts first; "-" sorts before every piece.
+__device__ __forceinline__ int form_text_cmp(const TargetAux& A, int32_t fa, int32_t fb) {
+    if (fa == fb) return 0;
+    const int32_t qa = A.seq_of_form[fa], qb = A.seq_of_form[fb];
+    if (qa != qb) {
+        const uint8_t* x = A.seq_letters + A.seq_off[qa]; const uint8_t* y = A.seq_letters + A.seq_off[qb];
+        const uint32_t lx = A.seq_off[qa + 1] - A.seq_off[qa], ly = A.seq_off[qb + 1] - A.seq_off[qb], m = min(lx, ly);
+        for (uint32_t i = 0; i < m; ++i) if (x[i] != y[i]) return x[i] < y[i] ? -1 : 1;
+        if (lx != ly) return lx > ly ? -1 : 1;
+    }
+    const FormMods& ma = A.form_mods[fa]; const FormMods& mb = A.form_mods[fb];
+    const uint32_t m = min(ma.n_mods, mb.n_mods);
+    for (uint32_t i = 0; i < m; ++i) {
+        const uint16_t ra = A.piece_rank[(uint32_t)ma.mod[i] * 64u + ma.site[i]], rb = A.piece_rank[(uint32_t)mb.mod[i] * 64u + mb.site[i]];
+        if (ra != rb) return ra < rb ? -1 : 1;
+    }
+    if (ma.n_mods != mb.n_mods) return ma.n_mods < mb.n_mods ? -1 : 1;
+    return 0;
+}
+
 // a sorts before b (RankPSMCompare: score desc, p-value asc, |tol_ppm| asc, "peptide|modification" asc)
-__device__ __forceinline__ int rank_cmp(const DevPsm& a, const DevPsm& b) {
+__device__ __forceinline__ int rank_cmp(const DevPsm& a, const DevPsm& b, const TargetAux& A) {
     if (a.score != b.score) return a.score > b.score ? -1 : 1;
     if (a.p_value != b.p_value) return a.p_value < b.p_value ? -1 : 1;
     double ta = fabs(tol_ppm_of(a)), tb = fabs(tol_ppm_of(b));
     if (ta != tb) return ta < tb ? -1 : 1;
-    if (a.strrank != b.strrank) return a.strrank < b.strrank ? -1 : 1;
-    return 0;
+    return form_text_cmp(A, a.form, b.form);
 }
 
-__global__ void k7_rank(DevPsm* __restrict__ psms, uint32_t n, const uint32_t* __restrict__ seg_start) {
+__global__ void k7_rank(DevPsm* __restrict__ psms, uint32_t n, const uint32_t* __restrict__ seg_start, TargetAux A) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const DevPsm me = psms[i];
@@ -330,7 +354,7 @@ __global__ void k7_rank(DevPsm* __restrict__ psms, uint32_t n, const uint32_t* _
     int32_t rank = 1;
     for (uint32_t j = a; j < b; ++j) {
         if (j == i) continue;
-        int c = rank_cmp(psms[j], me);
+        int c = rank_cmp(psms[j], me, A);
         if (c < 0 || (c == 0 && j < i)) ++rank;          // stable: equal keys keep table order
     }
     bool pv = (me.len <= 8 && me.p_value <= 0.05) || (me.len > 8 && me.p_value <= 0.01);       // CParameter.java:913-940
@@ -348,7 +372,7 @@ __global__ void k7_export(const DevPsm* __restrict__ psms, const uint32_t* __res
     q.spectrum = p.spectrum; q.form = p.form; q.score = p.score; q.exp_mass = p.exp_mass; q.pep_mass = p.pep_mass; q.tol_ppm = tol_ppm_of(p);
     q.isotope_error = p.iso; q.count_b = p.ca; q.count_y = p.cb; q.n_db = p.n_db; q.total_db = p.total_db; q.n_random = p.n_random;
     if (p.rank >= 2) { q.n_db = -1; q.total_db = -1; }       // psm_rank.txt: RankPSM.rankPSMs rewrites both for rank >= 2 (pg/RankPSM.java:89-92)
-    q.total_random = p.total_random; q.valid = p.valid; q.p_value = p.p_value; q.rank = p.rank; q.n_ptm = p.n_ptm; q.confident = p.confident; q.reserved = 0;
+    q.total_random = p.total_random; q.valid = p.valid; q.p_value = p.p_value; q.rank = p.rank; q.n_ptm = p.n_ptm; q.confident = p.confident; q.charge = p.charge;
     out[j] = q;
 }
 
@@ -399,9 +423,10 @@ bool psm_table_from_hits(const Hit* hits, uint32_t nh, const SpectraView& sp, co
     return true;
 }
 
-int launch_job_counters(const Job* jobs, const JobResult* res, uint32_t n_jobs, const uint64_t* sp_off, int which, DevCounters* c, cudaStream_t st) {
+int launch_job_counters(const Job* jobs, const JobResult* res, uint32_t n_jobs, const uint32_t* sp_npeaks, int which, DevCounters* c, cudaStream_t st,
+                        const uint8_t* skip_job) {
     if (!n_jobs) return 0;
-    k7_job_counters<<<blocks(n_jobs), 256, 0, st>>>(jobs, res, n_jobs, sp_off, which, c);
+    k7_job_counters<<<blocks(n_jobs), 256, 0, st>>>(jobs, res, n_jobs, sp_npeaks, which, c, skip_job);
     return 1;
 }
 int launch_step3_jobs(const DevPsm* psms, const uint32_t* seg_start, uint32_t n_seg, const double* r_mass, uint32_t n_rows, const WindowConfig& W,
@@ -460,9 +485,9 @@ int launch_step4_apply(const Job* jobs, const JobResult* res, const uint32_t* or
     k7_step4_apply<<<blocks(n_valid), 256, 0, st>>>(jobs, res, order, n_valid, psms);
     return 1;
 }
-int launch_rank(DevPsm* psms, uint32_t n, const uint32_t* seg_start, cudaStream_t st) {
+int launch_rank(DevPsm* psms, uint32_t n, const uint32_t* seg_start, const TargetAux& A, cudaStream_t st) {
     if (!n) return 0;
-    k7_rank<<<blocks(n), 256, 0, st>>>(psms, n, seg_start);
+    k7_rank<<<blocks(n), 256, 0, st>>>(psms, n, seg_start, A);
     return 1;
 }
 int launch_export_psms(const DevPsm* psms, const uint32_t* out_perm, uint32_t n, pq_psm* out, cudaStream_t st) {

@@ -7,11 +7,13 @@
 // spectra.  So the kernel that WRITES a row (K2 for shuffles) also writes, once, the cell of every (ion, fragment charge):
 // K1's count pass then is "load entry, test one flag of the staged spectrum, add".
 //
-// Layout of one row's lists (16-byte units, `chunks_side` units per side):
+// One row's lists = 2 * chunks_side 16-byte units of eight u16 entries:
 //   side 0 (b ions) | side 1 (y ions); inside a side: charge 1 ions k = 1..L-1, charge 2 ions k = 2..L-1, charge 3 ions
 //   k = 3..L-1 (A6: fragment charge c needs c <= ion number), concatenated, the tail of the last unit padded.
-//   entry = u16 byte offset of the cell in BlobLayout::cells = 2 * cell_filter(m/z).
+//   entry = byte offset of the cell in BlobLayout::cells = 2 * cell_filter(m/z).
 // A job with nch = precursor charge - 1 fragment charges reads the first T(nch) = sum_{c<=nch} max(L - c, 0) entries of each side.
+// The rows of one peptide form are stored unit-major: unit u of row k at base + u * stride + k (stride = rows reserved for the
+// form), so the 32 rows a warp of K1 (one thread per row) reads, and a warp of K2 writes, are 512 contiguous bytes per unit.
 #pragma once
 #include "pq_common.h"
 
@@ -28,12 +30,12 @@ PQ_HD uint32_t list_chunks_side(int L, int nch_max) { return (list_entries(L, nc
 
 #ifdef __CUDACC__
 // Writes both sides of one row's lists.  `row` = the 64 row bytes (any address space), M = the search's residue table.
-__device__ __forceinline__ void write_cell_lists(const uint8_t* row, const ModTable* __restrict__ M, int nch_max, uint4* __restrict__ dst,
-                                                 uint32_t chunks_side) {
+__device__ __forceinline__ void write_cell_lists(const uint8_t* row, const ModTable* __restrict__ M, int nch_max, uint4* __restrict__ dst /* unit 0 of this row */,
+                                                 uint32_t chunks_side, size_t stride) {
     const int L = (int)row[0];
     for (int side = 0; side < 2; ++side) {
         unsigned long long lo = 0ull, hi = 0ull; int fill = 0;            // eight u16 entries = one 16-byte unit
-        uint4* out = dst + (size_t)side * chunks_side;
+        uint4* out = dst + (size_t)side * chunks_side * stride;
         for (int c = 1; c <= nch_max; ++c) {
             double acc = side == 0 ? M->nterm[row[1]] : M->cterm[row[2]];
             for (int k = 1; k <= L - 1; ++k) {
@@ -47,7 +49,7 @@ __device__ __forceinline__ void write_cell_lists(const uint8_t* row, const ModTa
                 else t = __ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0);
                 const uint32_t e = 2u * cell_filter(t);
                 if (fill < 4) lo |= (unsigned long long)e << (16 * fill); else hi |= (unsigned long long)e << (16 * (fill - 4));
-                if (++fill == 8) { *out++ = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)); lo = hi = 0ull; fill = 0; }
+                if (++fill == 8) { *out = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)); out += stride; lo = hi = 0ull; fill = 0; }
             }
         }
         if (fill) *out = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));      // padding entries are offset 0: readable, never counted

@@ -49,7 +49,7 @@ struct PeptideTable {               // a mass-sorted candidate table resident on
 struct TargetOrder { std::vector<uint32_t> row_of_form, form_of_row; };   // public (generation) order <-> device (mass) order
 
 struct HostPsm {           // host mirror of a DevPsm (Step 5 only)
-    int32_t spectrum_sorted, spectrum, form; uint32_t blob;
+    int32_t spectrum_sorted, spectrum, form, len; uint32_t blob;
     double score; int32_t charge, n_db, rank, n_ptm; double p_value;
 };
 
@@ -71,20 +71,26 @@ struct pq_ctx {
     DevBuf d_mods, d_l10, d_lnf, d_shufmods;
     std::vector<double> ln_fact; double log10_fact[130];    // [0..64] log10(n!), [65..129] log10(100 n) (upper-bound table of K1)
     // spectra
-    int64_t nS = 0; uint32_t max_peaks = 0;
-    DevBuf s_prec, s_charge, s_mass, s_off, s_mz, s_in, s_caller, ld[9];
-    std::vector<int32_t> h_caller; std::vector<double> h_mass; std::vector<int32_t> h_charge; std::vector<uint32_t> h_npeaks;
+    int64_t nS = 0;                          // (virtual) spectra on the device: the caller's, plus one more per charge-less spectrum (its z = 3 reading)
+    int64_t nCaller = 0, nZero = 0; uint32_t max_peaks = 0;
+    DevBuf s_prec, s_charge, s_mass, s_off, s_mz, s_in, s_caller, s_npeaks, s_alias, s_vid, s_res, ld[12];
+    std::vector<int32_t> h_caller; std::vector<double> h_mass; std::vector<int32_t> h_charge; std::vector<uint32_t> h_npeaks; std::vector<uint8_t> h_resident, h_alias;
     bool host_spectra_valid = false;
+    // which spectra have their peaks in HBM: 0 = all (full upload); 1 = candidate-first (only those with a target in their precursor
+    // window when they were loaded: s_res flags, prep_id = rank among them)
+    int residency = 0; uint64_t targets_epoch = 0, loaded_epoch = 0; uint32_t n_resident = 0;
     SpectraView view() const {
         SpectraView v; v.n = nS; v.prec_mz = s_prec.as<double>(); v.charge = s_charge.as<int32_t>(); v.mass = s_mass.as<double>();
         v.off = s_off.as<uint64_t>(); v.mz = s_mz.as<double>(); v.inten = s_in.as<double>(); v.caller_index = s_caller.as<int32_t>();
+        v.npeaks = s_npeaks.as<uint32_t>(); v.alias = s_alias.as<uint8_t>();
         return v;
     }
     // prepared spectra
-    DevBuf blobs, blob_off, blob_len, prep_id, prep_list, need, scratch, scan_tmp;
+    DevBuf blobs, blob_off, blob_len, prep_id, prep_list, need, scratch, scan_tmp, pp_blobs, pp_blob_off, pp_blob_len;
     uint32_t n_prepared = 0; uint32_t max_blob = 0;
-    bool prepared_at_load = false;           // blobs hold every usable spectrum, blob id = caller index (prepare_at_load)
-    DevBuf s_inv;                            // caller index -> mass-sorted position
+    bool prepared_at_load = false;           // blobs were written by pq_load_spectra: blob id = virtual id (full upload) or rank among the resident spectra (candidate-first)
+    DevBuf s_inv;                            // virtual id -> mass-sorted position
+    DevBuf d_zero;                           // caller indices of the charge-less spectra, ascending
     // tables
     PeptideTable targets, reference;
     TargetOrder order;
@@ -92,7 +98,7 @@ struct pq_ctx {
     bool ref_staged = false, ref_digested = false;      // pq_stage_reference: proteins on the device / digest done (valid for the current targets)
     int step_done = 0;
     // work buffers
-    DevBuf jobs, jobs2, results, hits, hit_count, njobs;
+    DevBuf jobs, jobs2, results, hits, hit_count, njobs, hits_f, z_hit, z_skip, z_keep;
     // device-resident PSM table (K7)
     DevBuf d_psm, d_seg_start, d_out_perm, d_scalars, d_counters, d_agg, hits3, d_export, d_delta, d_modkey, d_modbest;
     DevBuf k_key_a, k_key_b, k_idx_a, k_idx_b, k_head;
@@ -100,11 +106,13 @@ struct pq_ctx {
     DevBuf c_rows, c_rows2, c_keys, c_keys2, c_idx, c_idx2;
     double psm_mass_lo = 0.0, psm_mass_hi = 0.0;
     // target-table side arrays on the device
-    DevBuf t_form_of_row, t_seq_of_form, t_strrank, t_form_mods, t_seq_off, t_seq_letters;
+    DevBuf t_form_of_row, t_seq_of_form, t_piece_rank, t_form_mods, t_seq_off, t_seq_letters;
+    TargetDeviceTable tdev; bool target_table_ready = false; uint32_t n_target_forms = 0;
+    std::vector<uint32_t> t_off; std::string t_flat;      // the target sequences back to back, as given
     TargetAux aux() const {
-        TargetAux a; a.form_of_row = t_form_of_row.as<uint32_t>(); a.seq_of_form = t_seq_of_form.as<int32_t>(); a.strrank = t_strrank.as<uint32_t>();
+        TargetAux a; a.form_of_row = t_form_of_row.as<uint32_t>(); a.seq_of_form = t_seq_of_form.as<int32_t>(); a.piece_rank = t_piece_rank.as<uint16_t>();
         a.form_mods = t_form_mods.as<FormMods>(); a.seq_off = t_seq_off.as<uint32_t>(); a.seq_letters = t_seq_letters.as<uint8_t>();
-        a.n_seq = (uint32_t)targets.seqs.size(); a.n_forms = (uint32_t)targets.forms.size();
+        a.n_seq = (uint32_t)targets.seqs.size(); a.n_forms = n_target_forms;
         return a;
     }
     // shuffles
@@ -283,16 +291,18 @@ int32_t copy_to_caller(pq_ctx* ctx, void* dst, const void* src, size_t bytes) {
 int32_t ensure_host_spectra(pq_ctx* ctx) {
     if (ctx->host_spectra_valid) return PQ_OK;
     const int64_t n = ctx->nS;
-    ctx->h_caller.resize(n); ctx->h_mass.resize(n); ctx->h_charge.resize(n); ctx->h_npeaks.resize(n);
+    ctx->h_caller.resize(n); ctx->h_mass.resize(n); ctx->h_charge.resize(n); ctx->h_npeaks.resize(n); ctx->h_resident.resize(n); ctx->h_alias.resize(n);
     if (n) {
         std::vector<uint64_t> off((size_t)n + 1);
         CU(cudaMemcpyAsync(ctx->h_caller.data(), ctx->s_caller.p, n * 4, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaMemcpyAsync(ctx->h_mass.data(), ctx->s_mass.p, n * 8, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaMemcpyAsync(ctx->h_charge.data(), ctx->s_charge.p, n * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(ctx->h_npeaks.data(), ctx->s_npeaks.p, n * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(ctx->h_alias.data(), ctx->s_alias.p, n, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaMemcpyAsync(off.data(), ctx->s_off.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));
-        ctx->cnt.d2h_bytes += (uint64_t)n * 24 + 8;
-        for (int64_t i = 0; i < n; ++i) ctx->h_npeaks[i] = (uint32_t)(off[i + 1] - off[i]);
+        ctx->cnt.d2h_bytes += (uint64_t)n * 29 + 8;
+        for (int64_t i = 0; i < n; ++i) ctx->h_resident[i] = (ctx->h_npeaks[i] == 0 || off[i + 1] > off[i]) ? 1 : 0;     // candidate-first: only some spectra have their peaks here
     }
     ctx->host_spectra_valid = true;
     return PQ_OK;
@@ -312,7 +322,7 @@ void pq_default_params(pq_params* p) {
     p->tol = 10.0; p->tol_ppm = 1; p->score_method = 1; p->itol = 0.6; p->min_score = 12.0; p->min_peaks = 10;
     p->n_isotope = 1; p->isotope[0] = 0; p->max_var_mods = 3; p->max_mods_per_aa = 1; p->n_random = 1000;
     p->enzyme = 1; p->max_missed = 2; p->min_len = 7; p->max_len = 45; p->min_mass = 500.0; p->max_mass = 10000.0;
-    p->shuffle_seed = 12457; p->mod_seed = 2022; p->prepare_at_load = 1;
+    p->shuffle_seed = 12457; p->mod_seed = 2022; p->prepare_at_load = 1; p->candidate_first = 1;
     p->n_fixed = 1; p->fixed[0].id = 1; p->fixed[0].position = PQ_MOD_ANYWHERE; strcpy(p->fixed[0].residues, "C"); p->fixed[0].delta = 57.02146372057;
     p->n_var = 1; p->var[0].id = 2; p->var[0].position = PQ_MOD_ANYWHERE; strcpy(p->var[0].residues, "M"); p->var[0].delta = 15.99491461956;
     p->var[0].neutral_loss = 63.99828574784;
@@ -354,6 +364,21 @@ int32_t pq_create(const pq_params* params, pq_ctx** out) {
         cudaMemcpy(ctx->d_l10.p, ctx->log10_fact, 130 * 8, cudaMemcpyHostToDevice);
         cudaMemcpy(ctx->d_lnf.p, ctx->ln_fact.data(), ctx->ln_fact.size() * 8, cudaMemcpyHostToDevice);
         ok = cudaMemcpy(ctx->d_shufmods.p, &ctx->codes.shuffle, sizeof(ShuffleMods), cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (ok) {
+        // text order of the pieces "id@site[delta]" of ModificationDB.getModificationString (:1695-1708): the last key of RankPSMCompare
+        const int nm = ctx->codes.n_var + ctx->codes.n_fixed;
+        std::vector<std::string> piece((size_t)std::max(nm, 1) * 64);
+        std::vector<uint32_t> ord(piece.size());
+        for (int m = 0; m < nm; ++m) for (int site = 0; site < 64; ++site) {
+            char buf[96]; snprintf(buf, sizeof buf, "%d@%d[%.4f]", ctx->codes.mods[(size_t)m].id, site, ctx->codes.mods[(size_t)m].delta);
+            piece[(size_t)m * 64 + site] = buf;
+        }
+        std::iota(ord.begin(), ord.end(), 0u);
+        std::sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return piece[a] < piece[b]; });
+        std::vector<uint16_t> rank(piece.size(), 0); uint16_t r = 0;
+        for (size_t k = 0; k < ord.size(); ++k) { if (k && piece[ord[k]] != piece[ord[k - 1]]) ++r; rank[ord[k]] = r; }
+        ok = ctx->t_piece_rank.reserve(rank.size() * 2) == cudaSuccess && cudaMemcpy(ctx->t_piece_rank.p, rank.data(), rank.size() * 2, cudaMemcpyHostToDevice) == cudaSuccess;
     }
     if (!ok) { delete ctx; return fail(nullptr, PQ_ERR_CUDA, "device allocation failed"); }
     *out = ctx;
@@ -416,184 +441,261 @@ int32_t pq_reset_counters(pq_ctx* ctx) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// pq_load_spectra.  Two ways for the peaks to reach HBM:
+//   candidate-first (targets known, all five caller arrays in pinned, device-mapped memory, pq_params.candidate_first): the 28
+//     bytes per spectrum of precursor data go up first, the spectra are ordered by mass and the precursor windows of the target
+//     table are enumerated (K3); only spectra with a target in their window are ever read again — by Steps 2-5 here, by
+//     SpectraInput.spectraMap in the reference (pg/SpectraInput.java:243-254) — so only their peaks cross PCIe: a gather kernel
+//     reads them straight from the caller's arrays into the mass-sorted CSR, chunk by chunk, K0 following each chunk.
+//   full upload (pageable buffers, or no targets yet): every peak crosses in 64 MB chunks on a copy stream, the compute stream
+//     follows chunk by chunk (copy into the sorted CSR, K0 with prepare_at_load).
 int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int32_t* charge, const uint64_t* off,
                         const double* mz, const double* inten) {
     if (!ctx || n < 0 || (n > 0 && (!prec_mz || !charge || !off || !mz || !inten))) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
-    if (n > 0x7fffffffLL / PQ_MAX_ISOTOPE) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many spectra for one context");
     cudaSetDevice(ctx->P.device);
     Marks mk("load_spectra");
-    const uint64_t total = n ? off[n] : 0;
     cudaStream_t st = ctx->st, sc = ctx->st_copy;
-    // staging buffers live in the context: a reload of the same size allocates nothing
+    // whatever goes wrong from here on, the context ends up without spectra and with nothing in flight
+    auto fail_load = [&](int32_t code, const std::string& msg) -> int32_t {
+        cudaStreamSynchronize(sc); cudaStreamSynchronize(st); cudaStreamSynchronize(ctx->st_aux); cudaGetLastError();
+        ctx->nS = 0; ctx->nCaller = 0; ctx->nZero = 0; ctx->max_peaks = 0; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0; ctx->prepared_at_load = false;
+        ctx->residency = 0; ctx->n_resident = 0; ctx->cnt.spectra_loaded = 0; ctx->cnt.spectra_usable = 0; ctx->host_spectra_valid = false;
+        return fail(ctx, code, msg);
+    };
+#define CL(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_load(PQ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+    // spectra without a charge (0) are searched as z = 2 and, failing that, z = 3: each is two virtual spectra
+    std::vector<int32_t> zeros;
+    for (int64_t i = 0; i < n; ++i) { if (charge[i] < 0) return fail_load(PQ_ERR_BAD_ARG, "charge must be >= 0 (0 = no charge given)"); if (charge[i] == 0) zeros.push_back((int32_t)i); }
+    const int64_t n0 = (int64_t)zeros.size(), nv = n + n0;
+    if (nv > 0x7fffffffLL / PQ_MAX_ISOTOPE) return fail_load(PQ_ERR_UNSUPPORTED, "too many spectra for one context");
+    ctx->nS = 0; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0; ctx->prepared_at_load = false; ctx->residency = 0; ctx->host_spectra_valid = false;
+    ctx->cnt.spectra_loaded = 0; ctx->cnt.spectra_usable = 0;
+    if (n == 0) { ctx->nCaller = 0; ctx->nZero = 0; ctx->max_peaks = 0; return PQ_OK; }
+    const uint64_t total = off[n];
     DevBuf& in_prec = ctx->ld[0]; DevBuf& in_charge = ctx->ld[1]; DevBuf& in_off = ctx->ld[2]; DevBuf& in_mz = ctx->ld[3]; DevBuf& in_in = ctx->ld[4];
-    DevBuf& in_mass = ctx->ld[5]; DevBuf& key = ctx->ld[6]; DevBuf& key2 = ctx->ld[7]; DevBuf& idx = ctx->ld[8];
-    if (n > 0) {
-        CU(in_prec.reserve(n * 8)); CU(in_charge.reserve(n * 4)); CU(in_off.reserve((n + 1) * 8));
-        CU(in_mz.reserve(std::max<uint64_t>(total, 1) * 8)); CU(in_in.reserve(std::max<uint64_t>(total, 1) * 8));
-        CU(in_mass.reserve(n * 8)); CU(key.reserve(n * 8)); CU(key2.reserve(n * 8)); CU(idx.reserve(n * 4));
-        CU(ctx->s_prec.reserve(n * 8)); CU(ctx->s_charge.reserve(n * 4)); CU(ctx->s_mass.reserve(n * 8)); CU(ctx->s_off.reserve((n + 1) * 8));
-        CU(ctx->s_mz.reserve(std::max<uint64_t>(total, 1) * 8)); CU(ctx->s_in.reserve(std::max<uint64_t>(total, 1) * 8)); CU(ctx->s_caller.reserve(n * 4));
-        CU(ctx->scratch.reserve((n + 1) * 8));
+    DevBuf& in_mass = ctx->ld[5]; DevBuf& key = ctx->ld[6]; DevBuf& key2 = ctx->ld[7]; DevBuf& idx = ctx->ld[8]; DevBuf& in_vz = ctx->ld[9];
+    CL(in_prec.reserve(n * 8)); CL(in_charge.reserve(n * 4)); CL(in_off.reserve((n + 1) * 8)); CL(ctx->d_zero.reserve((size_t)n0 * 4 + 64));
+    CL(in_mass.reserve(nv * 8)); CL(in_vz.reserve(nv * 4)); CL(key.reserve(nv * 8)); CL(key2.reserve(nv * 8)); CL(idx.reserve(nv * 4));
+    CL(ctx->s_prec.reserve(nv * 8)); CL(ctx->s_charge.reserve(nv * 4)); CL(ctx->s_mass.reserve(nv * 8)); CL(ctx->s_off.reserve((nv + 1) * 8));
+    CL(ctx->s_caller.reserve(nv * 4)); CL(ctx->s_vid.reserve(nv * 4)); CL(ctx->s_npeaks.reserve(nv * 4)); CL(ctx->s_alias.reserve(nv + 64)); CL(ctx->s_inv.reserve(nv * 4));
+    CL(ctx->scratch.reserve((nv + 2) * 8));
+    // pinned + device-mapped caller arrays?
+    auto dev_ptr = [](const void* p) -> const void* {
+        cudaPointerAttributes a; if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (a.type != cudaMemoryTypeHost) return nullptr;
+        void* d = nullptr; if (cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return d;
+    };
+    const void* d_h_mz = dev_ptr(mz); const void* d_h_in = dev_ptr(inten);
+    const bool pinned_all = d_h_mz && d_h_in;                     // only the peak arrays are read in place; the precursor arrays are copied
+    const bool want_cf = ctx->P.candidate_first != 0 && getenv("PQ_LOAD_FULL") == nullptr;
+    const bool cf = want_cf && ctx->have_targets && !ctx->targets.seqs.empty() && pinned_all;
+    const bool digest_here = ctx->ref_staged && !ctx->ref_digested && ctx->have_targets;
+    if (digest_here) {          // the target keys of a staged reference digest go up before the copy engine fills with spectra
+        std::string err;
+        if (!upload_target_keys_for_reference(st, ctx->targets.seqs, ctx->reference.dev, err)) return fail_load(PQ_ERR_CUDA, "reference digest: " + err);
     }
-    // The peaks cross PCIe in chunks of whole spectra (caller order) on a second stream; the compute stream follows chunk by
-    // chunk: copy into the mass-sorted CSR and, with prepare_at_load, K0 for the chunk, while the next chunk is in flight.
+    int k_launch = 0;
+    // ---- precursor arrays, neutral masses, the mass order, the sorted precursor arrays ----
+    CL(cudaMemcpyAsync(in_prec.p, prec_mz, n * 8, cudaMemcpyHostToDevice, st));
+    CL(cudaMemcpyAsync(in_charge.p, charge, n * 4, cudaMemcpyHostToDevice, st));
+    CL(cudaMemcpyAsync(in_off.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n0) CL(cudaMemcpyAsync(ctx->d_zero.p, zeros.data(), (size_t)n0 * 4, cudaMemcpyHostToDevice, st));
+    {
+        Timer t(ctx, &ctx->cnt.ms_prepare);
+        k_launch += launch_virtual_meta(nv, n, in_prec.as<double>(), in_charge.as<int32_t>(), ctx->d_zero.as<int32_t>(), in_mass.as<double>(), in_vz.as<int32_t>(),
+                                        key.as<uint64_t>(), idx.as<int32_t>(), st);
+        size_t tmp = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp, key.as<uint64_t>(), key2.as<uint64_t>(), idx.as<int32_t>(), ctx->s_vid.as<int32_t>(), (int)nv, 0, 64, st);
+        CL(ctx->scan_tmp.reserve(tmp + 64));
+        CL(cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, tmp, key.as<uint64_t>(), key2.as<uint64_t>(), idx.as<int32_t>(), ctx->s_vid.as<int32_t>(), (int)nv, 0, 64, st));
+        k_launch += launch_gather_meta(nv, n, ctx->s_vid.as<int32_t>(), in_prec.as<double>(), in_charge.as<int32_t>(), ctx->d_zero.as<int32_t>(), in_vz.as<int32_t>(),
+                                       in_mass.as<double>(), in_off.as<uint64_t>(), ctx->s_prec.as<double>(), ctx->s_charge.as<int32_t>(), ctx->s_mass.as<double>(),
+                                       ctx->s_caller.as<int32_t>(), ctx->s_npeaks.as<uint32_t>(), ctx->s_alias.as<uint8_t>(), st);
+        k_launch += launch_invert_order(nv, ctx->s_vid.as<int32_t>(), ctx->s_inv.as<int32_t>(), st);
+        k_launch += 4;
+    }
+    mk.mark("precursor arrays + sort queued");
+    // ---- the offsets are validated on the host while that runs; the full upload cuts its chunks in the same walk ----
     uint64_t chunk_peaks = 4u << 20;                                 // 64 MB of m/z + intensity per chunk
     if (const char* e = getenv("PQ_LOAD_CHUNK_PEAKS")) { long long v = atoll(e); if (v > 0) chunk_peaks = (uint64_t)v; }   // tests: many small chunks
-    {
-        const size_t max_chunks = (size_t)(total / chunk_peaks) + 2;
-        while (ctx->chunk_ev.size() < max_chunks) { cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
-    }
-    // Pinned caller buffers: every copy below is asynchronous, so the upload starts at once — the precursor arrays first, then
-    // each chunk of peaks as soon as the walk over the offsets (validation + chunk boundaries) has passed it.  Pageable
-    // precursor arrays are staged by the driver; kernels queued behind such a copy were seen to wait for every chunk queued
-    // in between (60 ms per load instead of 36 ms), so in that case the chunks are queued after the precursor kernels.
-    auto is_pinned = [](const void* p) { cudaPointerAttributes a; if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; } return a.type == cudaMemoryTypeHost; };
-    const bool early_copies = n > 0 && is_pinned(prec_mz) && is_pinned(charge) && is_pinned(off) && is_pinned(mz) && is_pinned(inten) && !getenv("PQ_LOAD_LATE_COPIES");
-    // the target keys of a staged reference digest go up before the copy engine fills with spectra
-    const bool digest_here = n > 0 && ctx->ref_staged && !ctx->ref_digested && ctx->have_targets;
-    if (digest_here) {
-        std::string err;
-        if (!upload_target_keys_for_reference(st, ctx->targets.seqs, ctx->reference.dev, err)) return fail(ctx, PQ_ERR_CUDA, "reference digest: " + err);
-    }
-    int meta_launches = 0;
-    auto precursor_kernels = [&]() -> int32_t {      // neutral masses, the mass order, the sorted precursor arrays and peak offsets
-        Timer t(ctx, &ctx->cnt.ms_prepare);
-        meta_launches += launch_precursor_mass(n, in_prec.as<double>(), in_charge.as<int32_t>(), in_mass.as<double>(), key.as<uint64_t>(), idx.as<int32_t>(), st);
-        size_t tmp = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp, key.as<uint64_t>(), key2.as<uint64_t>(), idx.as<int32_t>(), ctx->s_caller.as<int32_t>(), (int)n, 0, 64, st);
-        CU(ctx->scan_tmp.reserve(tmp + 64));
-        CU(cub::DeviceRadixSort::SortPairs(ctx->scan_tmp.p, tmp, key.as<uint64_t>(), key2.as<uint64_t>(), idx.as<int32_t>(), ctx->s_caller.as<int32_t>(), (int)n, 0, 64, st));
-        uint64_t* counts = ctx->scratch.as<uint64_t>();
-        meta_launches += launch_gather_meta(n, ctx->s_caller.as<int32_t>(), in_prec.as<double>(), in_charge.as<int32_t>(), in_mass.as<double>(), in_off.as<uint64_t>(),
-                                            ctx->s_prec.as<double>(), ctx->s_charge.as<int32_t>(), ctx->s_mass.as<double>(), counts, st);
-        CU(cudaMemsetAsync(counts + n, 0, 8, st));
-        return scan_exclusive(ctx, counts, ctx->s_off.as<uint64_t>(), (int)n + 1);
-    };
-    if (early_copies) {
-        // the precursor arrays and the kernels that consume them are queued BEFORE the first chunk (kernels first queued behind
-        // the chunk copies were held back until the last chunk had landed: 60 ms per load); the walk over the offsets below
-        // validates while they run
-        CU(cudaMemcpyAsync(in_prec.p, prec_mz, n * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(in_charge.p, charge, n * 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(in_off.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-        int32_t rc = precursor_kernels();
-        if (rc) return rc;
-    }
     std::vector<int64_t> cut; cut.push_back(0);
-    auto copy_chunk = [&](size_t c) -> int32_t {
-        const uint64_t a = off[cut[c]], b = off[cut[c + 1]];
-        if (b > a) {
-            CU(cudaMemcpyAsync(in_mz.as<double>() + a, mz + a, (b - a) * 8, cudaMemcpyHostToDevice, sc));
-            CU(cudaMemcpyAsync(in_in.as<double>() + a, inten + a, (b - a) * 8, cudaMemcpyHostToDevice, sc));
-        }
-        CU(cudaEventRecord(ctx->chunk_ev[c], sc));
-        return PQ_OK;
-    };
-    uint32_t maxp = 0; uint64_t usable = 0;
+    uint32_t maxp = 0; uint64_t usable = 0, alias_peaks = 0;
     {
-        const char* bad = nullptr; int32_t bad_rc = PQ_OK;
-        uint64_t next = (n ? off[0] : 0) + chunk_peaks;
+        uint64_t next = off[0] + chunk_peaks;
         for (int64_t i = 0; i < n; ++i) {
-            if (off[i + 1] < off[i]) { bad = "peak offsets must be non-decreasing"; bad_rc = PQ_ERR_BAD_ARG; break; }
+            if (off[i + 1] < off[i] || off[i + 1] > total) return fail_load(PQ_ERR_BAD_ARG, "peak offsets must be non-decreasing");
             const uint64_t c = off[i + 1] - off[i];
-            if (c > 4096) { bad = "more than 4096 peaks in one spectrum"; bad_rc = PQ_ERR_UNSUPPORTED; break; }
-            if (charge[i] < 1) { bad = "charge must be >= 1"; bad_rc = PQ_ERR_BAD_ARG; break; }
+            if (c > 4096) return fail_load(PQ_ERR_UNSUPPORTED, "more than 4096 peaks in one spectrum");
             if (c > maxp) maxp = (uint32_t)c;
             if ((int64_t)c > (int64_t)ctx->P.min_peaks) ++usable;
-            if (i + 1 < n && off[i + 1] >= next) {                   // spectra cut.back() .. i form a chunk
-                cut.push_back(i + 1); next = off[i + 1] + chunk_peaks;
-                if (early_copies) { int32_t rc = copy_chunk(cut.size() - 2); if (rc) return rc; }
-            }
+            if (charge[i] == 0) alias_peaks += c;
+            if (i + 1 < n && off[i + 1] >= next) { cut.push_back(i + 1); next = off[i + 1] + chunk_peaks; }
         }
-        if (bad) {
-            // the early path has already overwritten staging and sorted precursor arrays: the context is left without spectra
-            if (early_copies) { cudaStreamSynchronize(sc); cudaStreamSynchronize(st); }
-            ctx->nS = 0; ctx->max_peaks = 0; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0; ctx->prepared_at_load = false;
-            ctx->cnt.spectra_loaded = 0; ctx->cnt.spectra_usable = 0;
-            return fail(ctx, bad_rc, bad);
-        }
-        if (n > 0) { cut.push_back(n); if (early_copies) { int32_t rc = copy_chunk(cut.size() - 2); if (rc) return rc; } }
+        cut.push_back(n);
     }
     const size_t n_chunks = cut.size() - 1;
-    ctx->nS = n; ctx->max_peaks = maxp; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0;
+    ctx->nS = nv; ctx->nCaller = n; ctx->nZero = n0; ctx->max_peaks = maxp;
     ctx->cnt.spectra_loaded = (uint64_t)n; ctx->cnt.spectra_usable = usable;
-    if (n == 0) return PQ_OK;
-    mk.mark("validate + reserve (+ early copies)");
-    if (!early_copies) {
-        CU(cudaMemcpyAsync(in_prec.p, prec_mz, n * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(in_charge.p, charge, n * 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(in_off.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    }
-    auto enqueue_copies = [&]() -> int32_t {
-        if (early_copies) return PQ_OK;                              // already on their way
-        for (size_t c = 0; c < n_chunks; ++c) { int32_t rc = copy_chunk(c); if (rc) return rc; }
-        return PQ_OK;
-    };
-    ctx->cnt.h2d_bytes += (uint64_t)n * 28 + 8 + total * 16;
-    ctx->prepared_at_load = false;
-
-    {
-        Timer t(ctx, &ctx->cnt.ms_prepare);
-        int k = 0;
-        int32_t rc = PQ_OK;
-        if (!early_copies) { rc = precursor_kernels(); if (rc) return rc; }
-        k += meta_launches;
-        // The peak copies are queued only now (pageable precursor arrays, see above): queued ahead of the kernels above they held those kernels back until the last
-        // chunk had landed (measured: 60 ms per load instead of 36 ms), so the small precursor work goes first.
-        mk.mark("precursor arrays + sort queued");
-        rc = enqueue_copies();
-        if (rc) return rc;
-        mk.mark("chunk copies queued");
-        CU(ctx->s_inv.reserve(n * 4));
-        k += launch_invert_order(n, ctx->s_caller.as<int32_t>(), ctx->s_inv.as<int32_t>(), st);
-        SpectraView sp = ctx->view();
-        // prepare_at_load: blob i belongs to caller spectrum i (the list K0 walks is the inverse order), sizes from the peak counts
-        bool eager = ctx->P.prepare_at_load != 0 && getenv("PQ_PREPARE_AT_STEP2") == nullptr;
-        PrepConfig pc; pc.itol = ctx->P.itol; pc.method = ctx->P.score_method;
-        pc.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (ctx->P.itol * 2.0));
-        if (eager) {
-            CU(ctx->blob_off.reserve((size_t)(n + 2) * 8)); CU(ctx->blob_len.reserve((size_t)(n + 2) * 4));
-            CU(ctx->prep_list.reserve((size_t)(n + 2) * 8));
-            uint64_t* sizes = ctx->prep_list.as<uint64_t>();
-            k += launch_blob_sizes(sp, ctx->s_inv.as<int32_t>(), (int32_t)n, sizes, st);
-            rc = scan_exclusive(ctx, sizes, ctx->blob_off.as<uint64_t>(), (int)n + 1);
-            if (rc) return rc;
-            uint64_t total_blob = 0;
-            CU(cudaMemcpyAsync(&total_blob, ctx->blob_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            if (ctx->blobs.cap < total_blob + 256) {                // growing: only if it fits beside what is still to come
+    mk.mark("offset walk");
+    PrepConfig pc; pc.itol = ctx->P.itol; pc.method = ctx->P.score_method;
+    pc.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (ctx->P.itol * 2.0));
+    bool eager = ctx->P.prepare_at_load != 0 && getenv("PQ_PREPARE_AT_STEP2") == nullptr;
+    SpectraView sp = ctx->view();
+    if (cf) {
+        // ---- candidate-first: target table -> precursor windows -> the spectra worth bringing over ----
+        int32_t rc = finalize_targets(ctx);                          // device build of the target table (k6), queued on st
+        if (rc) return fail_load(rc, ctx->err);
+        rc = ensure_counters(ctx); if (rc) return fail_load(rc, ctx->err);
+        PeptideTable& T = ctx->targets;
+        CL(ctx->s_res.reserve((size_t)(nv + 1) * 4)); CL(ctx->prep_id.reserve((size_t)(nv + 1) * 4)); CL(ctx->prep_list.reserve((size_t)(nv + 2) * 8));
+        CL(ctx->njobs.reserve(64)); CL(ctx->jobs.reserve((size_t)nv * ctx->P.n_isotope * sizeof(Job)));
+        CL(cudaMemsetAsync(ctx->njobs.p, 0, 16, st)); CL(cudaMemsetAsync(ctx->s_res.p, 0, (size_t)(nv + 1) * 4, st));
+        WindowConfig W; W.tol = ctx->P.tol; W.tol_ppm = ctx->P.tol_ppm; W.n_isotope = ctx->P.n_isotope; W.min_peaks = ctx->P.min_peaks;
+        for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) W.isotope[i] = ctx->P.isotope[i];
+        struct { uint32_t n_res; uint32_t pad; uint64_t res_peaks; uint64_t blob_bytes; } hn = {0, 0, 0, 0};
+        {
+            Timer t(ctx, &ctx->cnt.ms_window);
+            if (T.n()) k_launch += launch_enumerate_targets(sp, T.mass.as<double>(), (uint32_t)T.n(), W, ctx->jobs.as<Job>(), ctx->njobs.as<uint32_t>(), ctx->s_res.as<int32_t>(), st);
+            rc = scan_exclusive(ctx, ctx->s_res.as<int32_t>(), ctx->prep_id.as<int32_t>(), (int)nv + 1);                 // rank among the resident spectra = blob id
+            if (rc) return fail_load(rc, ctx->err);
+            size_t tmp = 0;
+            cub::CountingInputIterator<int32_t> iota(0);
+            uint32_t* d_nsel = ctx->njobs.as<uint32_t>() + 1;
+            cub::DeviceSelect::Flagged(nullptr, tmp, iota, ctx->s_res.as<int32_t>(), ctx->prep_list.as<int32_t>(), d_nsel, (int)nv, st);
+            CL(ctx->scan_tmp.reserve(tmp + 64));
+            CL(cub::DeviceSelect::Flagged(ctx->scan_tmp.p, tmp, iota, ctx->s_res.as<int32_t>(), ctx->prep_list.as<int32_t>(), d_nsel, (int)nv, st));
+            k_launch += launch_resident_counts(nv, ctx->s_npeaks.as<uint32_t>(), ctx->s_res.as<int32_t>(), ctx->scratch.as<uint64_t>(), st);
+            rc = scan_exclusive(ctx, ctx->scratch.as<uint64_t>(), ctx->s_off.as<uint64_t>(), (int)nv + 1);
+            if (rc) return fail_load(rc, ctx->err);
+            k_launch += 4;
+        }
+        CL(cudaMemcpyAsync(&hn.n_res, ctx->prep_id.as<int32_t>() + nv, 4, cudaMemcpyDeviceToHost, st));
+        CL(cudaMemcpyAsync(&hn.res_peaks, ctx->s_off.as<uint64_t>() + nv, 8, cudaMemcpyDeviceToHost, st));
+        CL(cudaStreamSynchronize(st));
+        ctx->cnt.d2h_bytes += 12;
+        mk.mark("target table + windows (waits for the precursor sort)");
+        const uint32_t n_res = hn.n_res;
+        CL(ctx->s_mz.reserve(std::max<uint64_t>(hn.res_peaks, 1) * 8)); CL(ctx->s_in.reserve(std::max<uint64_t>(hn.res_peaks, 1) * 8));
+        sp = ctx->view();
+        ctx->residency = 1; ctx->n_resident = n_res; ctx->loaded_epoch = ctx->targets_epoch;
+        ctx->cnt.h2d_bytes += (uint64_t)n * 28 + 8 + (uint64_t)n0 * 4 + hn.res_peaks * 16;
+        if (n_res) {
+            // blob offsets of the resident spectra (blob id = rank in prep_list)
+            CL(ctx->blob_off.reserve((size_t)(n_res + 2) * 8)); CL(ctx->blob_len.reserve((size_t)(n_res + 2) * 4));
+            uint64_t* sizes = ctx->scratch.as<uint64_t>();
+            k_launch += launch_blob_sizes(sp, ctx->prep_list.as<int32_t>(), (int32_t)n_res, sizes, st);
+            rc = scan_exclusive(ctx, sizes, ctx->blob_off.as<uint64_t>(), (int)n_res + 1);
+            if (rc) return fail_load(rc, ctx->err);
+            CL(cudaMemcpyAsync(&hn.blob_bytes, ctx->blob_off.as<uint64_t>() + n_res, 8, cudaMemcpyDeviceToHost, st));
+            CL(cudaStreamSynchronize(st));
+            if (eager && ctx->blobs.cap < hn.blob_bytes + 256) {
                 size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
-                if ((double)(total_blob + 256 - ctx->blobs.cap) > 0.6 * (double)free_b) eager = false;
+                if ((double)(hn.blob_bytes + 256 - ctx->blobs.cap) > 0.6 * (double)free_b) eager = false;
             }
-            if (eager && ctx->blobs.reserve(total_blob + 256) != cudaSuccess) { cudaGetLastError(); eager = false; }
+            if (eager && ctx->blobs.reserve(hn.blob_bytes + 256) != cudaSuccess) { cudaGetLastError(); eager = false; }
+            // the peaks of the resident spectra, chunk by chunk (mass order): gather from the caller's arrays on the copy stream, K0 behind it
+            int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->P.device);
+            uint32_t chunk_spectra = 32768;
+            if (const char* e = getenv("PQ_LOAD_CHUNK_SPECTRA")) { long long v = atoll(e); if (v > 0) chunk_spectra = (uint32_t)v; }
+            const size_t nck = ((size_t)n_res + chunk_spectra - 1) / chunk_spectra;
+            while (ctx->chunk_ev.size() < nck + 1) { cudaEvent_t e; CL(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+            if (!ctx->meta_ev) CL(cudaEventCreateWithFlags(&ctx->meta_ev, cudaEventDisableTiming));
+            CL(cudaEventRecord(ctx->meta_ev, st));
+            CL(cudaStreamWaitEvent(sc, ctx->meta_ev, 0));
+            Timer t(ctx, &ctx->cnt.ms_prepare);
+            for (size_t c = 0; c < nck; ++c) {
+                const uint32_t a = (uint32_t)(c * chunk_spectra), cnt = std::min(chunk_spectra, n_res - a);
+                k_launch += launch_gather_peaks_from_host(ctx->prep_list.as<int32_t>() + a, (int32_t)cnt, ctx->s_caller.as<int32_t>(), in_off.as<uint64_t>(),
+                                                          ctx->s_off.as<uint64_t>(), static_cast<const double*>(d_h_mz), static_cast<const double*>(d_h_in),
+                                                          ctx->s_mz.as<double>(), ctx->s_in.as<double>(), sms, sc);
+                CL(cudaEventRecord(ctx->chunk_ev[c], sc));
+                CL(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
+                if (eager)
+                    k_launch += launch_prepare(sp, ctx->prep_list.as<int32_t>() + a, (int32_t)cnt, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>() + a,
+                                               ctx->blob_len.as<uint32_t>() + a, ctx->max_peaks, st);
+            }
+            if (eager) { ctx->prepared_at_load = true; ctx->n_prepared = n_res; ctx->cnt.spectra_prepared = n_res; ctx->max_blob = blob_bytes(ctx->max_peaks); }
         }
+        mk.mark("gather + K0 queued");
+    } else {
+        // ---- full upload: every peak, in chunks of whole caller spectra ----
+        const uint64_t total_sorted = total + alias_peaks;
+        CL(in_mz.reserve(std::max<uint64_t>(total, 1) * 8)); CL(in_in.reserve(std::max<uint64_t>(total, 1) * 8));
+        CL(ctx->s_mz.reserve(std::max<uint64_t>(total_sorted, 1) * 8)); CL(ctx->s_in.reserve(std::max<uint64_t>(total_sorted, 1) * 8));
+        sp = ctx->view();
+        while (ctx->chunk_ev.size() < n_chunks + 1) { cudaEvent_t e; CL(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
+        {
+            Timer t(ctx, &ctx->cnt.ms_prepare);
+            k_launch += launch_resident_counts(nv, ctx->s_npeaks.as<uint32_t>(), nullptr, ctx->scratch.as<uint64_t>(), st);
+            int32_t rc = scan_exclusive(ctx, ctx->scratch.as<uint64_t>(), ctx->s_off.as<uint64_t>(), (int)nv + 1);
+            if (rc) return fail_load(rc, ctx->err);
+        }
+        // The peak copies are queued after the small precursor work: queued ahead of it (pageable precursor arrays are staged by the
+        // driver) they were seen to hold those kernels back until the last chunk had landed (60 ms per load instead of 36 ms).
         for (size_t c = 0; c < n_chunks; ++c) {
-            CU(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
-            const int64_t a = cut[c], cnt = cut[c + 1] - cut[c];
-            k += launch_gather_peaks_by_caller(a, cnt, ctx->s_inv.as<int32_t>(), in_off.as<uint64_t>(), ctx->s_off.as<uint64_t>(), in_mz.as<double>(),
-                                               in_in.as<double>(), ctx->s_mz.as<double>(), ctx->s_in.as<double>(), st);
-            if (eager)
-                k += launch_prepare(sp, ctx->s_inv.as<int32_t>() + a, (int32_t)cnt, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>() + a,
-                                    ctx->blob_len.as<uint32_t>() + a, ctx->max_peaks, st, (uint32_t)std::max(ctx->P.min_peaks + 1, 0));
+            const uint64_t a = off[cut[c]], b = off[cut[c + 1]];
+            if (b > a) {
+                CL(cudaMemcpyAsync(in_mz.as<double>() + a, mz + a, (b - a) * 8, cudaMemcpyHostToDevice, sc));
+                CL(cudaMemcpyAsync(in_in.as<double>() + a, inten + a, (b - a) * 8, cudaMemcpyHostToDevice, sc));
+            }
+            CL(cudaEventRecord(ctx->chunk_ev[c], sc));
         }
-        if (eager) {
-            ctx->prepared_at_load = true; ctx->n_prepared = (uint32_t)n; ctx->cnt.spectra_prepared = usable;
-            ctx->max_blob = blob_bytes(ctx->max_peaks);
+        mk.mark("chunk copies queued");
+        ctx->cnt.h2d_bytes += (uint64_t)n * 28 + 8 + (uint64_t)n0 * 4 + total * 16;
+        ctx->residency = 0; ctx->n_resident = (uint32_t)nv;
+        {
+            Timer t(ctx, &ctx->cnt.ms_prepare);
+            // prepare_at_load: blob v belongs to virtual spectrum v (the list K0 walks is s_inv), sizes from the peak counts
+            if (eager) {
+                CL(ctx->blob_off.reserve((size_t)(nv + 2) * 8)); CL(ctx->blob_len.reserve((size_t)(nv + 2) * 4));
+                CL(ctx->prep_list.reserve((size_t)(nv + 2) * 8));
+                uint64_t* sizes = ctx->prep_list.as<uint64_t>();
+                k_launch += launch_blob_sizes(sp, ctx->s_inv.as<int32_t>(), (int32_t)nv, sizes, st);
+                int32_t rc = scan_exclusive(ctx, sizes, ctx->blob_off.as<uint64_t>(), (int)nv + 1);
+                if (rc) return fail_load(rc, ctx->err);
+                uint64_t total_blob = 0;
+                CL(cudaMemcpyAsync(&total_blob, ctx->blob_off.as<uint64_t>() + nv, 8, cudaMemcpyDeviceToHost, st));
+                CL(cudaStreamSynchronize(st));
+                if (ctx->blobs.cap < total_blob + 256) {                // growing: only if it fits beside what is still to come
+                    size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+                    if ((double)(total_blob + 256 - ctx->blobs.cap) > 0.6 * (double)free_b) eager = false;
+                }
+                if (eager && ctx->blobs.reserve(total_blob + 256) != cudaSuccess) { cudaGetLastError(); eager = false; }
+            }
+            size_t z_lo = 0;                                             // charge-less spectra (ascending caller index) of the chunks seen so far
+            for (size_t c = 0; c < n_chunks; ++c) {
+                CL(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
+                const int64_t a = cut[c], cnt = cut[c + 1] - cut[c];
+                size_t z_hi = z_lo; while (z_hi < zeros.size() && zeros[z_hi] < cut[c + 1]) ++z_hi;
+                // the chunk's spectra are virtual a .. a+cnt-1, their z = 3 readings virtual n+z_lo .. n+z_hi-1
+                const int64_t first[2] = {a, n + (int64_t)z_lo}, count[2] = {cnt, (int64_t)(z_hi - z_lo)};
+                for (int part = 0; part < 2; ++part) {
+                    if (count[part] <= 0) continue;
+                    k_launch += launch_gather_peaks_by_virtual(first[part], count[part], n, ctx->d_zero.as<int32_t>(), ctx->s_inv.as<int32_t>(), in_off.as<uint64_t>(),
+                                                               ctx->s_off.as<uint64_t>(), in_mz.as<double>(), in_in.as<double>(), ctx->s_mz.as<double>(), ctx->s_in.as<double>(), st);
+                    if (eager)
+                        k_launch += launch_prepare(sp, ctx->s_inv.as<int32_t>() + first[part], (int32_t)count[part], pc, ctx->blobs.as<uint8_t>(),
+                                                   ctx->blob_off.as<uint64_t>() + first[part], ctx->blob_len.as<uint32_t>() + first[part], ctx->max_peaks, st,
+                                                   (uint32_t)std::max(ctx->P.min_peaks + 1, 0));
+                }
+                z_lo = z_hi;
+            }
+            if (eager) { ctx->prepared_at_load = true; ctx->n_prepared = (uint32_t)nv; ctx->cnt.spectra_prepared = usable; ctx->max_blob = blob_bytes(ctx->max_peaks); }
         }
-        ctx->cnt.other_kernel_launches += (uint64_t)k + 4;
+        mk.mark("chunk work queued");
     }
-    CU(cudaGetLastError());
-    mk.mark("chunk work queued");
+    ctx->cnt.other_kernel_launches += (uint64_t)k_launch;
+    CL(cudaGetLastError());
     // a protein database staged before the spectra (pq_stage_reference): its digest does not depend on them and runs now, on a
-    // third stream, beside the chunk work above
-    if (ctx->ref_staged && !ctx->ref_digested && ctx->have_targets) { int32_t rc = digest_staged_reference(ctx, ctx->st_aux); if (rc) return rc; }
-    // targets given before the spectra: their expansion, sort and encoding (host work) overlap the upload
+    // third stream, beside the work above
+    if (digest_here) { int32_t rc = digest_staged_reference(ctx, ctx->st_aux); if (rc) return fail_load(rc, ctx->err); }
     mk.mark("digest (staged reference)");
-    if (ctx->have_targets) { int32_t rc = finalize_targets(ctx); if (rc) return rc; }
-    mk.mark("target table");
-    CU(cudaStreamSynchronize(st));
+    // targets given before the spectra: their table is built while the peaks are on their way (device work, a few launches)
+    if (ctx->have_targets && !cf) { int32_t rc = finalize_targets(ctx); if (rc) return fail_load(rc, ctx->err); }
+    CL(cudaStreamSynchronize(st)); CL(cudaStreamSynchronize(sc));
     mk.mark("wait for the upload");
-    ctx->host_spectra_valid = false;          // host mirrors (Step 5, pq_score_pairs) are pulled on first use
+#undef CL
     return PQ_OK;
 }
 
@@ -607,17 +709,18 @@ int32_t pq_set_targets(pq_ctx* ctx, int32_t n_seq, const uint32_t* off, const ch
     if (!ctx || n_seq < 0 || (n_seq > 0 && (!off || !res))) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
     cudaSetDevice(ctx->P.device);
     PeptideTable& T = ctx->targets;
-    T.seqs.clear(); T.forms.clear();
+    T.seqs.clear(); T.forms.clear(); ctx->t_off.assign(1, 0u); ctx->t_flat.clear();
+    ctx->have_targets = false; ctx->target_table_ready = false; ctx->n_target_forms = 0; ++ctx->targets_epoch;
     for (int32_t i = 0; i < n_seq; ++i) {
+        if (off[i + 1] < off[i]) return fail(ctx, PQ_ERR_BAD_ARG, "target offsets must be non-decreasing");
         std::string s(res + off[i], res + off[i + 1]);
         if (s.size() < 2 || s.size() > (size_t)kMaxLen) return fail(ctx, PQ_ERR_UNSUPPORTED, "target length must be 2..60: " + s);
         for (char c : s) if (c < 'A' || c > 'Z' || ctx->codes.residue_mass[c - 'A'] == 0.0) return fail(ctx, PQ_ERR_BAD_ARG, "target has a non-standard residue: " + s);
-        T.seqs.push_back(s);
+        T.seqs.push_back(s); ctx->t_flat += s; ctx->t_off.push_back((uint32_t)ctx->t_flat.size());
     }
-    // The isoform expansion, the mass-sorted device table and its side arrays are host work that the next pq_load_spectra
-    // (while the peaks cross PCIe) or, failing that, pq_step2_match_targets does: finalize_targets().
+    // The isoform expansion and the mass-sorted device table are built on the device by the next pq_load_spectra (it needs the
+    // target masses to decide which spectra to bring over) or, failing that, by pq_step2_match_targets: finalize_targets().
     ctx->forms_expanded = false; ctx->cnt.target_forms = 0; ctx->ref_digested = false;     // the digest is 'minus the targets'
-    ctx->order.form_of_row.clear(); ctx->order.row_of_form.clear();
     ctx->have_targets = true; ctx->step_done = 0; reset_psm_state(ctx);
     return PQ_OK;
 }
@@ -647,109 +750,28 @@ void ensure_forms(pq_ctx* ctx) {
     ctx->forms_expanded = true;
 }
 
+// The target table (PeptideInput.calcPeptideIsoforms for every target, mass-sorted rows, side arrays of K7) is built on the
+// device (k6_reference.cu, build_target_table_on_device).  Queued on the context stream; synchronised once inside (form count).
 int32_t finalize_targets(pq_ctx* ctx) {
+    if (ctx->target_table_ready) return PQ_OK;
     PeptideTable& T = ctx->targets;
-    TargetOrder& O = ctx->order;
-    ensure_forms(ctx);
-    if (!O.form_of_row.empty() && O.form_of_row.size() == T.forms.size() && T.rows.p) return PQ_OK;
-    const size_t n = T.forms.size();
     Marks mk("finalize_targets");
-    std::vector<uint32_t> ord(n);
-    std::iota(ord.begin(), ord.end(), 0u);
-    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return T.forms[a].mass < T.forms[b].mass; });
-    mk.mark("sort by mass");
-    O.form_of_row = ord; O.row_of_form.assign(n, 0);
-    for (size_t r = 0; r < n; ++r) O.row_of_form[ord[r]] = (uint32_t)r;
-    // all host work first, one batch of uploads and one synchronisation at the end: called from pq_load_spectra this runs
-    // while the peaks are still crossing PCIe
-    std::vector<uint8_t> rows(n * kRowBytes);
-    T.h_mass.resize(n);     // sorted masses (row order)
-    for (size_t r = 0; r < n; ++r) {
-        const FormRec& f = T.forms[ord[r]];
-        if (!ctx->codes.encode_row(T.seqs[(size_t)f.seq], f, rows.data() + r * kRowBytes)) {
-            O.form_of_row.clear(); O.row_of_form.clear();
-            return fail(ctx, PQ_ERR_UNSUPPORTED, "peptide form cannot be encoded (length > 60 or two modifications on one site): " + T.seqs[(size_t)f.seq]);
-        }
-        T.h_mass[r] = f.mass;
-    }
-    mk.mark("encode");
-    // side arrays of the device pipeline (K7): row -> public form, form -> sequence, the form's modification list,
-    // rank of "sequence|modification" among the forms (RankPSMCompare's last tie-break), the target letters
-    const size_t nseq = T.seqs.size();
-    std::vector<int32_t> seq_of_form(n); std::vector<FormMods> fm(n); std::vector<uint32_t> strrank(n, 0);
-    for (size_t f = 0; f < n; ++f) {
-        seq_of_form[f] = T.forms[f].seq;
-        memset(&fm[f], 0, sizeof(FormMods)); fm[f].n_mods = T.forms[f].n;
-        for (int i = 0; i < T.forms[f].n; ++i) fm[f].mod[i] = T.forms[f].mod[i];
-    }
-    {
-        // rank of "sequence|modification string" (RankPSMCompare's last tie-break).  The forms of one sequence are contiguous
-        // (generation order), '|' sorts above every letter, and the "%d@%d[%.4f]" pieces repeat: sort the distinct
-        // sequences once under the "a proper prefix sorts after its extensions" rule, then each sequence's forms by their
-        // modification strings built from cached pieces.
-        std::vector<std::string> piece((size_t)(ctx->codes.n_var + ctx->codes.n_fixed) * 64);
-        auto piece_of = [&](int m, int site) -> const std::string& {
-            std::string& p = piece[(size_t)m * 64 + (size_t)site];
-            if (p.empty()) { char buf[96]; snprintf(buf, sizeof buf, "%d@%d[%.4f]", ctx->codes.mods[(size_t)m].id, site, ctx->codes.mods[(size_t)m].delta); p = buf; }
-            return p;
-        };
-        std::vector<std::string> mods(n);
-        for (size_t f = 0; f < n; ++f) {
-            const FormRec& fr = T.forms[f];
-            if (fr.n == 0) { mods[f] = "-"; continue; }
-            std::string& ms = mods[f];
-            for (int i = 0; i < fr.n; ++i) { if (i) ms += ';'; ms += piece_of(fr.mod[i], fr.site[i]); }
-        }
-        auto seq_less = [&](uint32_t a, uint32_t b) {        // "A|" vs "B|": the first difference decides; a proper prefix meets '|' > letter
-            const std::string& x = T.seqs[a]; const std::string& y = T.seqs[b];
-            const size_t m = std::min(x.size(), y.size());
-            int c = memcmp(x.data(), y.data(), m);
-            if (c) return c < 0;
-            return x.size() > y.size();
-        };
-        std::vector<uint32_t> sq(nseq); std::iota(sq.begin(), sq.end(), 0u);
-        std::sort(sq.begin(), sq.end(), seq_less);
-        // forms of each sequence (contiguous runs of T.forms)
-        std::vector<uint32_t> first(nseq + 1, 0);
-        for (size_t f = 0; f < n; ++f) first[(size_t)T.forms[f].seq + 1]++;
-        for (size_t q = 0; q < nseq; ++q) first[q + 1] += first[q];
-        uint32_t r = 0; bool any = false;
-        const std::string* prev_seq = nullptr; const std::string* prev_mod = nullptr;
-        std::vector<uint32_t> fo;
-        for (size_t k = 0; k < nseq; ++k) {
-            const uint32_t q = sq[k];
-            fo.assign(first[q + 1] - first[q], 0u); std::iota(fo.begin(), fo.end(), first[q]);
-            std::sort(fo.begin(), fo.end(), [&](uint32_t a, uint32_t b) { return mods[a] < mods[b]; });
-            for (uint32_t f : fo) {
-                if (any && !(*prev_seq == T.seqs[q] && *prev_mod == mods[f])) ++r;      // equal keys (a sequence given twice) share a rank
-                strrank[f] = r; any = true; prev_seq = &T.seqs[q]; prev_mod = &mods[f];
-            }
-        }
-    }
-    mk.mark("form aux + string ranks");
-    std::vector<uint32_t> soff(nseq + 1, 0); std::vector<uint8_t> letters;
-    for (size_t q = 0; q < nseq; ++q) { for (char c : T.seqs[q]) letters.push_back((uint8_t)(c - 'A')); soff[q + 1] = (uint32_t)letters.size(); }
-    CU(ctx->t_form_of_row.reserve(std::max<size_t>(n * 4, 64))); CU(ctx->t_seq_of_form.reserve(std::max<size_t>(n * 4, 64)));
-    CU(ctx->t_strrank.reserve(std::max<size_t>(n * 4, 64))); CU(ctx->t_form_mods.reserve(std::max<size_t>(n * sizeof(FormMods), 64)));
-    CU(ctx->t_seq_off.reserve((nseq + 1) * 4)); CU(ctx->t_seq_letters.reserve(std::max<size_t>(letters.size(), 64)));
-    cudaStream_t st = ctx->st;
-    CU(T.rows.reserve(std::max<size_t>(rows.size(), 64)));
-    CU(T.mass.reserve(std::max<size_t>(n * 8, 64)));
-    CU(cudaMemcpyAsync(T.rows.p, rows.data(), rows.size(), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(T.mass.p, T.h_mass.data(), n * 8, cudaMemcpyHostToDevice, st));
+    TargetDeviceTable& D = ctx->tdev;
+    D.rows = &T.rows; D.mass = &T.mass; D.form_of_row = &ctx->t_form_of_row; D.seq_of_form = &ctx->t_seq_of_form; D.form_mods = &ctx->t_form_mods;
+    D.seq_off = &ctx->t_seq_off; D.seq_letters = &ctx->t_seq_letters;
+    std::string err; uint64_t launches = 0;
+    if (!build_target_table_on_device(ctx->st, ctx->codes, (uint32_t)T.seqs.size(), ctx->t_off.data(), ctx->t_flat.data(), D, &launches, err))
+        return fail(ctx, PQ_ERR_CUDA, "target table: " + err);
+    ctx->cnt.other_kernel_launches += launches;
+    const size_t n = D.n_forms;
+    ctx->n_target_forms = D.n_forms; T.n_rows = n; T.device_built = true; ctx->cnt.target_forms = n;
+    ctx->cnt.h2d_bytes += ctx->t_flat.size() * 2 + T.seqs.size() * 16 + 4;
     if (ctx->P.score_method == 2 && n > 0) {
         CU(T.pred.reserve(n * 8));
-        ctx->cnt.other_kernel_launches += (uint64_t)launch_predict(T.rows.as<uint8_t>(), (uint32_t)n, ctx->d_mods.as<ModTable>(), ctx->P.itol, T.pred.as<int32_t>(), st);
+        ctx->cnt.other_kernel_launches += (uint64_t)launch_predict(T.rows.as<uint8_t>(), (uint32_t)n, ctx->d_mods.as<ModTable>(), ctx->P.itol, T.pred.as<int32_t>(), ctx->st);
     }
-    ctx->cnt.h2d_bytes += rows.size() + n * 8;
-    CU(cudaMemcpyAsync(ctx->t_form_of_row.p, O.form_of_row.data(), n * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->t_seq_of_form.p, seq_of_form.data(), n * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->t_strrank.p, strrank.data(), n * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->t_form_mods.p, fm.data(), n * sizeof(FormMods), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->t_seq_off.p, soff.data(), (nseq + 1) * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->t_seq_letters.p, letters.data(), letters.size(), cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));
-    ctx->cnt.h2d_bytes += n * (12 + sizeof(FormMods)) + (nseq + 1) * 4 + letters.size();
+    mk.mark("device build (queued)");
+    ctx->target_table_ready = true;
     return PQ_OK;
 }
 }  // namespace
@@ -785,41 +807,59 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     if (n == 0 || T.n() == 0) { ctx->step_done = 2; return PQ_OK; }
     cudaStream_t st = ctx->st;
     const uint32_t job_cap = (uint32_t)(n * ctx->P.n_isotope);
+    const bool cf = ctx->residency == 1;
     CU(ctx->jobs.reserve((size_t)job_cap * sizeof(Job)));
     CU(ctx->njobs.reserve(64));
     CU(ctx->need.reserve((size_t)(n + 1) * 4));
-    CU(ctx->prep_id.reserve((size_t)(n + 1) * 4));
-    CU(ctx->prep_list.reserve((size_t)(n + 1) * 4));
-    CU(cudaMemsetAsync(ctx->njobs.p, 0, 16, st));
+    if (!cf) { CU(ctx->prep_id.reserve((size_t)(n + 1) * 4)); CU(ctx->prep_list.reserve((size_t)(n + 1) * 4)); }
+    CU(cudaMemsetAsync(ctx->njobs.p, 0, 32, st));
     CU(cudaMemsetAsync(ctx->need.p, 0, (size_t)(n + 1) * 4, st));
     WindowConfig W; W.tol = ctx->P.tol; W.tol_ppm = ctx->P.tol_ppm; W.n_isotope = ctx->P.n_isotope; W.min_peaks = ctx->P.min_peaks;
     for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) W.isotope[i] = ctx->P.isotope[i];
     SpectraView sp = ctx->view();
-    struct { uint32_t njobs, nprep; unsigned long long cand; } hn = {0, 0, 0};
+    struct { uint32_t njobs, nprep; unsigned long long cand; uint32_t missing, pad; } hn = {0, 0, 0, 0, 0};
     int32_t h_nprep = 0;
     {
         Timer t(ctx, &ctx->cnt.ms_window);
         int k = launch_enumerate_targets(sp, T.mass.as<double>(), (uint32_t)T.n(), W, ctx->jobs.as<Job>(), ctx->njobs.as<uint32_t>(), ctx->need.as<int32_t>(), st);
-        rc = scan_exclusive(ctx, ctx->need.as<int32_t>(), ctx->prep_id.as<int32_t>(), (int)n + 1);
-        if (rc) return rc;
+        if (cf) k += launch_count_missing(n, ctx->need.as<int32_t>(), ctx->s_res.as<int32_t>(), ctx->njobs.as<uint32_t>() + 4, st);
+        else { rc = scan_exclusive(ctx, ctx->need.as<int32_t>(), ctx->prep_id.as<int32_t>(), (int)n + 1); if (rc) return rc; }
         ctx->cnt.other_kernel_launches += (uint64_t)k + 1;
     }
-    CU(cudaMemcpyAsync(&hn, ctx->njobs.p, 16, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(&h_nprep, ctx->prep_id.as<int32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&hn, ctx->njobs.p, 24, cudaMemcpyDeviceToHost, st));
+    if (!cf) CU(cudaMemcpyAsync(&h_nprep, ctx->prep_id.as<int32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    ctx->cnt.d2h_bytes += 20;
+    ctx->cnt.d2h_bytes += 28;
     const uint32_t h_njobs = hn.njobs;
     const uint64_t cand = hn.cand;
     mk.mark("enumerate");
+    if (cf && hn.missing)
+        return fail(ctx, PQ_ERR_STATE, "the spectra were loaded candidate-first for another target list: " + std::to_string(hn.missing) +
+                                       " spectra in the precursor windows of the present targets have no peaks on the device; call pq_load_spectra again");
     if (h_njobs == 0) { ctx->step_done = 2; return PQ_OK; }
     if (cand > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-2 candidates for one launch");
     // list of spectra to prepare (ascending sorted index) + blob offsets
     {
         Timer t(ctx, &ctx->cnt.ms_prepare);
         int k = 0;
-        if (ctx->prepared_at_load) {
-            // every usable spectrum was prepared during the upload; blob id = caller index
-            k += launch_fix_job_blobs(ctx->jobs.as<Job>(), h_njobs, ctx->s_caller.as<int32_t>(), st);
+        PrepConfig pc; pc.itol = ctx->P.itol; pc.method = ctx->P.score_method;
+        pc.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (ctx->P.itol * 2.0));
+        if (cf) {
+            // candidate-first: the resident spectra are the ones with a target in their window; blob id = rank among them (prep_id of the load)
+            if (!ctx->prepared_at_load && ctx->n_resident) {          // prepare_at_load = 0: K0 runs here, once per load
+                uint64_t total_blob = 0;
+                CU(cudaMemcpyAsync(&total_blob, ctx->blob_off.as<uint64_t>() + ctx->n_resident, 8, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                CU(ctx->blobs.reserve(total_blob + 256));
+                k += launch_prepare(sp, ctx->prep_list.as<int32_t>(), (int32_t)ctx->n_resident, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(),
+                                    ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st);
+                ctx->n_prepared = ctx->n_resident; ctx->cnt.spectra_prepared = ctx->n_resident; ctx->max_blob = blob_bytes(ctx->max_peaks);
+                if (ctx->P.prepare_at_load != 0) ctx->prepared_at_load = true;      // (the load could not reserve the blobs then; they exist now)
+            }
+            k += launch_fix_job_blobs(ctx->jobs.as<Job>(), h_njobs, ctx->prep_id.as<int32_t>(), st);
+        } else if (ctx->prepared_at_load) {
+            // every usable spectrum was prepared during the upload; blob id = virtual id
+            k += launch_fix_job_blobs(ctx->jobs.as<Job>(), h_njobs, ctx->s_vid.as<int32_t>(), st);
         } else {
         size_t tmp = 0;
         cub::CountingInputIterator<int32_t> iota(0);
@@ -835,8 +875,6 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
         CU(cudaMemcpyAsync(&total_blob, ctx->blob_off.as<uint64_t>() + h_nprep, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(ctx->blobs.reserve(total_blob + 256));
-        PrepConfig pc; pc.itol = ctx->P.itol; pc.method = ctx->P.score_method;
-        pc.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (ctx->P.itol * 2.0));
         k += launch_prepare(sp, ctx->prep_list.as<int32_t>(), h_nprep, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(), ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st);
         k += launch_fix_job_blobs(ctx->jobs.as<Job>(), h_njobs, ctx->prep_id.as<int32_t>(), st);
         ctx->n_prepared = (uint32_t)h_nprep; ctx->cnt.spectra_prepared = (uint64_t)h_nprep;
@@ -857,17 +895,39 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     mk.mark("prepare launch");
     rc = run_score(ctx, kJobTargets, h_njobs, T.pred.as<int32_t>(), T.rows.as<uint8_t>(), T.mass.as<double>(), (uint32_t)cand, 1);
     if (rc) return rc;
-    ctx->cnt.other_kernel_launches += (uint64_t)launch_job_counters(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), h_njobs, sp.off, 0, ctx->d_counters.as<DevCounters>(), st);
     uint32_t nh = 0;
     CU(cudaMemcpyAsync(&nh, ctx->hit_count.p, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->cnt.d2h_bytes += 4;
     mk.mark("score (waits for K0 + K1)");
+    const Hit* hits = ctx->hits.as<Hit>();
+    const uint8_t* skip_job = nullptr;
+    if (ctx->nZero > 0) {
+        // spectra loaded without a charge: the z = 3 reading only counts when the z = 2 reading saved no PSM
+        // (FindCandidateSpectraAndScoreWorker.java:96-228): drop its hits and its pair count otherwise
+        CU(ctx->z_hit.reserve((size_t)n + 64)); CU(ctx->z_skip.reserve((size_t)h_njobs + 64)); CU(ctx->z_keep.reserve((size_t)nh + 64)); CU(ctx->hits_f.reserve(((size_t)nh + 1) * sizeof(Hit)));
+        CU(cudaMemsetAsync(ctx->z_hit.p, 0, (size_t)n, st));
+        int k = launch_chargeless_filter(hits, nh, ctx->jobs.as<Job>(), h_njobs, sp, ctx->nCaller, ctx->d_zero.as<int32_t>(), ctx->s_vid.as<int32_t>(), ctx->s_inv.as<int32_t>(),
+                                         ctx->z_hit.as<uint8_t>(), ctx->z_skip.as<uint8_t>(), ctx->z_keep.as<uint8_t>(), st);
+        if (nh) {
+            size_t tmp = 0;
+            uint32_t* d_cnt = ctx->njobs.as<uint32_t>() + 6;
+            cub::DeviceSelect::Flagged(nullptr, tmp, hits, ctx->z_keep.as<uint8_t>(), ctx->hits_f.as<Hit>(), d_cnt, (int)nh, st);
+            CU(ctx->scan_tmp.reserve(tmp + 64));
+            CU(cub::DeviceSelect::Flagged(ctx->scan_tmp.p, tmp, hits, ctx->z_keep.as<uint8_t>(), ctx->hits_f.as<Hit>(), d_cnt, (int)nh, st));
+            CU(cudaMemcpyAsync(&nh, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            hits = ctx->hits_f.as<Hit>();
+        }
+        skip_job = ctx->z_skip.as<uint8_t>();
+        ctx->cnt.other_kernel_launches += (uint64_t)k + 2;
+    }
+    ctx->cnt.other_kernel_launches += (uint64_t)launch_job_counters(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), h_njobs, sp.npeaks, 0, ctx->d_counters.as<DevCounters>(), st, skip_job);
     // hits -> PSM table in (mass-sorted spectrum, form) order, spectrum segments, caller-order permutation: all on the device
     if (nh) {
         CU(ctx->d_psm.reserve((size_t)nh * sizeof(DevPsm))); CU(ctx->d_seg_start.reserve(((size_t)nh + 2) * 4)); CU(ctx->d_out_perm.reserve((size_t)nh * 4));
         std::string err; int launches = 0;
-        if (!psm_table_from_hits(ctx->hits.as<Hit>(), nh, sp, T.mass.as<double>(), T.rows.as<uint8_t>(), ctx->aux(), ctx->k_key_a, ctx->k_key_b, ctx->k_idx_a,
+        if (!psm_table_from_hits(hits, nh, sp, T.mass.as<double>(), T.rows.as<uint8_t>(), ctx->aux(), ctx->k_key_a, ctx->k_key_b, ctx->k_idx_a,
                                  ctx->k_idx_b, ctx->k_head, ctx->scan_tmp, ctx->d_psm.as<DevPsm>(), ctx->d_seg_start.as<uint32_t>(),
                                  ctx->d_scalars.as<uint32_t>(), ctx->d_out_perm.as<uint32_t>(), st, &launches, err))
             return fail(ctx, PQ_ERR_CUDA, "psm table: " + err);
@@ -1082,7 +1142,7 @@ int32_t pq_step3_competitors(pq_ctx* ctx) {
     if (cand > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-3 candidates for one launch");
     int32_t rc = run_score(ctx, kJobCompetitors, n_jobs, R.pred.as<int32_t>(), R.rows.as<uint8_t>(), R.mass.as<double>(), (uint32_t)std::max<unsigned long long>(cand, 1), 1);
     if (rc) return rc;
-    int k = launch_job_counters(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), n_jobs, ctx->s_off.as<uint64_t>(), 1, ctx->d_counters.as<DevCounters>(), st);
+    int k = launch_job_counters(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), n_jobs, ctx->s_npeaks.as<uint32_t>(), 1, ctx->d_counters.as<DevCounters>(), st);
     k += launch_step3_aggregate(ctx->results.as<JobResult>(), n_seg, ctx->P.n_isotope, ctx->d_seg_start.as<uint32_t>(), ctx->d_psm.as<DevPsm>(), ctx->d_agg.as<SegAgg>(), st);
     ctx->cnt.other_kernel_launches += (uint64_t)k;
     // detail rows stay on the device until pq_get_competitors(3) asks for them: keep this launch's hit rows
@@ -1174,7 +1234,7 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
     ctx->cnt.other_kernel_launches += (uint64_t)k + 4;
     rc = run_score(ctx, kJobShuffles, n_valid, ctx->sh_pred.as<int32_t>(), ctx->sh_rows.as<uint8_t>(), nullptr, 1, 0);
     if (rc) return rc;
-    k = launch_job_counters(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), n_valid, ctx->s_off.as<uint64_t>(), 2, ctx->d_counters.as<DevCounters>(), st);
+    k = launch_job_counters(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), n_valid, ctx->s_npeaks.as<uint32_t>(), 2, ctx->d_counters.as<DevCounters>(), st);
     k += launch_step4_apply(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), ctx->sh_order.as<uint32_t>(), n_valid, ctx->d_psm.as<DevPsm>(), st);
     ctx->cnt.other_kernel_launches += (uint64_t)k;
     CU(cudaGetLastError());
@@ -1220,7 +1280,7 @@ int32_t pq_rank_and_validate(pq_ctx* ctx) {
     if (!ctx) return PQ_ERR_BAD_ARG;
     cudaSetDevice(ctx->P.device);
     // rank inside each spectrum segment (pg/RankPSM.java:107-149) + CParameter.passed_psm_validation, on the device
-    ctx->cnt.other_kernel_launches += (uint64_t)launch_rank(ctx->d_psm.as<DevPsm>(), ctx->n_psm, ctx->d_seg_start.as<uint32_t>(), ctx->st);
+    ctx->cnt.other_kernel_launches += (uint64_t)launch_rank(ctx->d_psm.as<DevPsm>(), ctx->n_psm, ctx->d_seg_start.as<uint32_t>(), ctx->aux(), ctx->st);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->st));
     return PQ_OK;
@@ -1371,7 +1431,7 @@ int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms) {
         ctx->psms.resize(ctx->n_psm);
         for (size_t i = 0; i < hp.size(); ++i) {
             const DevPsm& d = hp[i]; HostPsm& h = ctx->psms[i];
-            h.spectrum_sorted = d.spectrum_sorted; h.spectrum = d.spectrum; h.form = d.form; h.blob = d.blob; h.score = d.score; h.charge = d.charge;
+            h.spectrum_sorted = d.spectrum_sorted; h.spectrum = d.spectrum; h.form = d.form; h.len = d.len; h.blob = d.blob; h.score = d.score; h.charge = d.charge;
             h.n_db = d.n_db; h.rank = d.rank; h.n_ptm = d.n_ptm; h.p_value = d.p_value;
         }
     }
@@ -1380,7 +1440,7 @@ int32_t pq_step5_ptm(pq_ctx* ctx, int32_t n_ptm, const pq_ptm* ptms) {
     for (size_t i = 0; i < ctx->psms.size(); ++i) {
         HostPsm& p = ctx->psms[i];
         p.n_ptm = -1;
-        int len = (int)T.seqs[(size_t)T.forms[(size_t)p.form].seq].size();
+        int len = p.len;
         bool pv = (len <= 8 && p.p_value <= 0.05) || (len > 8 && p.p_value <= 0.01);
         if (pv && p.n_db == 0 && p.rank == 1) val.push_back(i);
     }
@@ -1482,13 +1542,18 @@ int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_ind
     { int32_t rc0 = ensure_counters(ctx); if (rc0) return rc0; rc0 = ensure_host_spectra(ctx); if (rc0) return rc0; }
     cudaStream_t st = ctx->st;
     const int64_t n = ctx->nS;
-    // caller index -> sorted index
-    std::vector<int32_t> sorted_of(n, -1);
-    for (int64_t i = 0; i < n; ++i) sorted_of[(size_t)ctx->h_caller[i]] = (int32_t)i;
+    // caller index -> sorted index (a spectrum loaded without a charge is scored as its z = 2 reading)
+    std::vector<int32_t> sorted_of((size_t)ctx->nCaller, -1);
+    for (int64_t i = 0; i < n; ++i) if (ctx->h_alias[(size_t)i] != 2) sorted_of[(size_t)ctx->h_caller[i]] = (int32_t)i;
     // group pairs by spectrum; rows in that order
     std::vector<uint32_t> order((size_t)n_pairs);
     std::iota(order.begin(), order.end(), 0u);
-    for (int64_t i = 0; i < n_pairs; ++i) if (spectrum_index[i] < 0 || spectrum_index[i] >= n) return fail(ctx, PQ_ERR_BAD_ARG, "spectrum index out of range");
+    for (int64_t i = 0; i < n_pairs; ++i) {
+        if (spectrum_index[i] < 0 || spectrum_index[i] >= ctx->nCaller) return fail(ctx, PQ_ERR_BAD_ARG, "spectrum index out of range");
+        if (!ctx->h_resident[(size_t)sorted_of[(size_t)spectrum_index[i]]])
+            return fail(ctx, PQ_ERR_STATE, "the peaks of spectrum " + std::to_string(spectrum_index[i]) + " are not on the device (candidate-first load: only spectra with a "
+                                           "target in their precursor window were brought over); load with pq_params.candidate_first = 0 to score arbitrary pairs");
+    }
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return sorted_of[(size_t)spectrum_index[a]] < sorted_of[(size_t)spectrum_index[b]]; });
     std::vector<uint8_t> rows((size_t)n_pairs * kRowBytes);
     std::vector<int32_t> pred;
@@ -1514,33 +1579,32 @@ int32_t pq_score_pairs(pq_ctx* ctx, int64_t n_pairs, const int32_t* spectrum_ind
     CU(cudaMemcpyAsync(d_rows.p, rows.data(), rows.size(), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(d_list.p, list.data(), list.size() * 4, cudaMemcpyHostToDevice, st));
     SpectraView sp = ctx->view();
-    // this call owns the prepared-spectrum pool: invalidate the step pipeline's blobs
-    ctx->step_done = std::min(ctx->step_done, 1); ctx->n_prepared = 0; ctx->prepared_at_load = false;   // the blobs are re-used below
-    CU(ctx->scratch.reserve((list.size() + 2) * 8)); CU(ctx->blob_off.reserve((list.size() + 2) * 8)); CU(ctx->blob_len.reserve((list.size() + 2) * 4));
+    // the call prepares its spectra into its own blob pool: the step pipeline's blobs stay as they are
+    DevBuf& p_blobs = ctx->pp_blobs; DevBuf& p_off = ctx->pp_blob_off; DevBuf& p_len = ctx->pp_blob_len;
+    CU(ctx->scratch.reserve((list.size() + 2) * 8)); CU(p_off.reserve((list.size() + 2) * 8)); CU(p_len.reserve((list.size() + 2) * 4));
     launch_blob_sizes(sp, d_list.as<int32_t>(), (int32_t)list.size(), ctx->scratch.as<uint64_t>(), st);
-    int32_t rc = scan_exclusive(ctx, ctx->scratch.as<uint64_t>(), ctx->blob_off.as<uint64_t>(), (int)list.size() + 1);
+    int32_t rc = scan_exclusive(ctx, ctx->scratch.as<uint64_t>(), p_off.as<uint64_t>(), (int)list.size() + 1);
     if (rc) return rc;
     uint64_t total_blob = 0;
-    CU(cudaMemcpyAsync(&total_blob, ctx->blob_off.as<uint64_t>() + list.size(), 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&total_blob, p_off.as<uint64_t>() + list.size(), 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    CU(ctx->blobs.reserve(total_blob + 256));
+    CU(p_blobs.reserve(total_blob + 256));
     PrepConfig pc; pc.itol = ctx->P.itol; pc.method = ctx->P.score_method;
     pc.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (ctx->P.itol * 2.0));
     {
         Timer t(ctx, &ctx->cnt.ms_prepare);
-        ctx->cnt.other_kernel_launches += (uint64_t)launch_prepare(sp, d_list.as<int32_t>(), (int32_t)list.size(), pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(), ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st) + 2;
+        ctx->cnt.other_kernel_launches += (uint64_t)launch_prepare(sp, d_list.as<int32_t>(), (int32_t)list.size(), pc, p_blobs.as<uint8_t>(), p_off.as<uint64_t>(), p_len.as<uint32_t>(), ctx->max_peaks, st) + 2;
     }
-    ctx->max_blob = blob_bytes(ctx->max_peaks);
     CU(ctx->jobs.reserve(hj.size() * sizeof(Job)));
     CU(cudaMemcpyAsync(ctx->jobs.p, hj.data(), hj.size() * sizeof(Job), cudaMemcpyHostToDevice, st));
     CU(ctx->results.reserve(hj.size() * sizeof(JobResult))); CU(ctx->hits.reserve(64)); CU(ctx->hit_count.reserve(64));
     CU(cudaMemsetAsync(ctx->hit_count.p, 0, 4, st));
     ScoreLaunch L; memset(&L, 0, sizeof L);
     L.kind = kJobPairs; L.jobs = ctx->jobs.as<Job>(); L.n_jobs = (uint32_t)hj.size();
-    L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>(); L.blob_len = ctx->blob_len.as<uint32_t>(); L.rows = d_rows.as<uint8_t>(); L.row_mass = nullptr;
+    L.blobs = p_blobs.as<uint8_t>(); L.blob_off = p_off.as<uint64_t>(); L.blob_len = p_len.as<uint32_t>(); L.rows = d_rows.as<uint8_t>(); L.row_mass = nullptr;
     L.mods = ctx->d_mods.as<ModTable>(); L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>(); L.row_pred = nullptr; L.n_codes = (uint32_t)ctx->codes.n_codes;
     L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>(); L.hit_capacity = 0;
-    L.pair_score = d_score.as<double>(); L.pair_a = d_a.as<int32_t>(); L.pair_b = d_b.as<int32_t>(); L.max_blob_bytes = ctx->max_blob; L.job_counter = ctx->d_scalars.as<uint32_t>() + 12;
+    L.pair_score = d_score.as<double>(); L.pair_a = d_a.as<int32_t>(); L.pair_b = d_b.as<int32_t>(); L.max_blob_bytes = blob_bytes(ctx->max_peaks); L.job_counter = ctx->d_scalars.as<uint32_t>() + 12;
     if (ctx->P.score_method == 2) {
         CU(d_pred.reserve((size_t)n_pairs * 8));
         ctx->cnt.other_kernel_launches += (uint64_t)launch_predict(d_rows.as<uint8_t>(), (uint32_t)n_pairs, ctx->d_mods.as<ModTable>(), ctx->P.itol, d_pred.as<int32_t>(), st);

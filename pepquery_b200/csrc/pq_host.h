@@ -73,6 +73,16 @@ bool expand_reference_on_device(cudaStream_t st, const pq_params& P, const Codes
 bool build_reference_on_device(cudaStream_t st, const pq_params& P, const Codes& codes, int32_t n_proteins, const uint64_t* off, const char* res,
                                const std::vector<std::string>& targets, double lo, double hi, RefDeviceTable& T, uint64_t* launches, std::string& err);
 
+// The target table as K6 builds it on the device; the pointers name the context's buffers.
+struct TargetDeviceTable {
+    DevBuf* rows = nullptr; DevBuf* mass = nullptr; DevBuf* form_of_row = nullptr; DevBuf* seq_of_form = nullptr; DevBuf* form_mods = nullptr;
+    DevBuf* seq_off = nullptr; DevBuf* seq_letters = nullptr;
+    DevBuf w[13];
+    uint32_t n_forms = 0;
+};
+bool build_target_table_on_device(cudaStream_t st, const Codes& codes, uint32_t n_seq, const uint32_t* off, const char* flat, TargetDeviceTable& T,
+                                  uint64_t* launches, std::string& err);
+
 // Group order + round count of PeptideInput.generateRandomPeptidesFast (pg/PeptideInput.java:387-422).
 void shuffle_plan(const std::string& seq, int n_random, ShuffleSeq& out);
 

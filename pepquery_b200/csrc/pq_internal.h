@@ -29,14 +29,16 @@ struct DevBuf {
 
 // Spectra as they sit in HBM: CSR peak arrays in precursor-mass order (SURVEY.md §8 a15 / north_star item 1).
 struct SpectraView {
-    int64_t n;                    // spectra
+    int64_t n;                    // (virtual) spectra: a spectrum loaded without a charge counts twice, as z = 2 and as z = 3
     const double* prec_mz;        // [n] sorted by neutral mass
-    const int32_t* charge;        // [n]
+    const int32_t* charge;        // [n] charge in use
     const double* mass;           // [n] neutral precursor mass  mz*z - z*proton, ascending
-    const uint64_t* off;          // [n+1] peak offsets
+    const uint64_t* off;          // [n+1] peak offsets into mz / inten; a spectrum whose peaks are not resident has length 0 here
     const double* mz;             // peaks, file order inside a spectrum
     const double* inten;
     const int32_t* caller_index;  // [n] sorted position -> index in the caller's order
+    const uint32_t* npeaks;       // [n] peak count of the spectrum (resident or not)
+    const uint8_t* alias;         // [n] 0: charge given; 1: charge-less searched as z = 2; 2: charge-less searched as z = 3
 };
 
 struct PrepConfig {
@@ -143,11 +145,11 @@ struct ShuffleForm {           // one per target form that needs shuffles
     uint32_t row_base;         // first output row
     uint32_t n_mods;
     int8_t   mod[PQ_MAX_FORM_MODS];   // modification ids (index into ShuffleMods), target list order
-    // cell lists of the form's shuffle rows (k_cells.cuh): row k at lists + (list_base + k * 2 * list_chunks) 16-byte units
+    // cell lists of the form's shuffle rows (k_cells.cuh), unit-major: unit u of row k at lists[list_base + u * list_rows + k]
     uint32_t len;              // peptide length L
     uint32_t list_nch;         // fragment charges held in the lists (1..kListMaxCharge): the largest a still-valid PSM of the form needs
     uint32_t list_chunks;      // units per side
-    uint32_t pad;
+    uint32_t list_rows;        // rows reserved (= rounds planned for the sequence)
     uint64_t list_base;
 };
 struct ShuffleMods {           // the search's modifications as K2 needs them
@@ -164,14 +166,20 @@ int launch_shuffles(const ShuffleSeq* seqs, uint32_t n_seqs, const ShuffleForm* 
                     uint8_t* rows, uint32_t max_num, int64_t shuffle_seed, const ModTable* table, uint4* lists /* may be null */, cudaStream_t st);
 
 // packing helpers (k3_window.cu)
-int launch_precursor_mass(int64_t n, const double* prec_mz, const int32_t* charge, double* mass, uint64_t* key, int32_t* idx, cudaStream_t st);
-int launch_gather_meta(int64_t n, const int32_t* order, const double* prec_mz_in, const int32_t* charge_in, const double* mass_in,
-                       const uint64_t* off_in, double* prec_mz, int32_t* charge, double* mass, uint64_t* count, cudaStream_t st);
-int launch_gather_peaks(int64_t n, const int32_t* order, const uint64_t* off_in, const uint64_t* off_out, const double* mz_in,
-                        const double* in_in, double* mz_out, double* in_out, cudaStream_t st);
+int launch_virtual_meta(int64_t nv, int64_t n, const double* prec_mz, const int32_t* charge, const int32_t* zero_idx, double* mass, int32_t* vz,
+                        uint64_t* key, int32_t* idx, cudaStream_t st);
+int launch_gather_meta(int64_t nv, int64_t n, const int32_t* order, const double* prec_mz_in, const int32_t* charge_in, const int32_t* zero_idx,
+                       const int32_t* vz, const double* mass_in, const uint64_t* off_in, double* prec_mz, int32_t* charge, double* mass,
+                       int32_t* caller, uint32_t* npeaks, uint8_t* alias, cudaStream_t st);
+int launch_resident_counts(int64_t nv, const uint32_t* npeaks, const int32_t* resident, uint64_t* count, cudaStream_t st);
+int launch_gather_peaks_from_host(const int32_t* list, int32_t n_list, const int32_t* caller, const uint64_t* off_in, const uint64_t* off_out,
+                                  const double* h_mz, const double* h_in, double* mz_out, double* in_out, int sms, cudaStream_t st);
 int launch_invert_order(int64_t n, const int32_t* order, int32_t* inv, cudaStream_t st);
-int launch_gather_peaks_by_caller(int64_t first, int64_t count, const int32_t* inv, const uint64_t* off_in, const uint64_t* off_out,
-                                  const double* mz_in, const double* in_in, double* mz_out, double* in_out, cudaStream_t st);
+int launch_gather_peaks_by_virtual(int64_t first, int64_t count, int64_t n, const int32_t* zero_idx, const int32_t* inv, const uint64_t* off_in,
+                                   const uint64_t* off_out, const double* mz_in, const double* in_in, double* mz_out, double* in_out, cudaStream_t st);
+int launch_count_missing(int64_t n, const int32_t* need, const int32_t* resident, uint32_t* out, cudaStream_t st);
+int launch_chargeless_filter(const Hit* hits, uint32_t nh, const Job* jobs, uint32_t n_jobs, const SpectraView& sp, int64_t n_caller, const int32_t* zero_idx,
+                             const int32_t* vid, const int32_t* inv, uint8_t* has_hit /* zeroed */, uint8_t* skip_job, uint8_t* keep_hit, cudaStream_t st);
 int launch_blob_sizes(const SpectraView& sp, const int32_t* list, int32_t n_list, uint64_t* sizes, cudaStream_t st);
 int launch_fix_job_blobs(Job* jobs, uint32_t n_jobs, const int32_t* prep_id, cudaStream_t st);
 int launch_job_keys(const Job* jobs, uint32_t n, uint64_t* key, uint32_t* idx, cudaStream_t st);
@@ -202,7 +210,7 @@ struct DevPsm {
     double   score, exp_mass, pep_mass, p_value;
     int32_t  ca, cb, n_db, total_db, n_random, total_random, valid, rank, n_ptm, confident;
     uint32_t seg;               // spectrum segment (PSMs of one spectrum are contiguous)
-    uint32_t strrank;           // rank of "sequence|modification" among the target forms (RankPSM tie-break)
+    uint32_t pad;
 };
 struct SegAgg {                 // Step-3 result per matched spectrum
     int32_t matched, better;
@@ -210,13 +218,13 @@ struct SegAgg {                 // Step-3 result per matched spectrum
     uint32_t best_row, pad;
 };
 struct DevCounters { unsigned long long pairs[4]; unsigned long long bytes[4]; unsigned long long bounded; };
-struct FormMods { uint32_t n_mods; int8_t mod[PQ_MAX_FORM_MODS]; };     // a target form's modifications, list order
+struct FormMods { uint32_t n_mods; int8_t mod[PQ_MAX_FORM_MODS]; uint8_t site[PQ_MAX_FORM_MODS]; };     // a target form's modifications, reference list order
 struct ShuffleTotals { uint32_t n_seqs, raw_rows, n_forms, out_rows, n_valid, pad; uint64_t list_units; };
 
 struct TargetAux {              // per-target-table device arrays
     const uint32_t* form_of_row;      // [rows]  mass-sorted row -> public form
     const int32_t*  seq_of_form;      // [forms]
-    const uint32_t* strrank;          // [forms]
+    const uint16_t* piece_rank;       // [(var + fixed mods) * 64]: rank of the text "id@site[delta]" among all such pieces (RankPSM string tie-break)
     const FormMods* form_mods;        // [forms]
     const uint32_t* seq_off;          // [seqs+1]
     const uint8_t*  seq_letters;      // letter codes 0..25
@@ -227,7 +235,8 @@ struct TargetAux {              // per-target-table device arrays
 bool psm_table_from_hits(const Hit* hits, uint32_t nh, const SpectraView& sp, const double* t_mass, const uint8_t* t_rows, const TargetAux& A,
                          DevBuf& key_a, DevBuf& key_b, DevBuf& idx_a, DevBuf& idx_b, DevBuf& head, DevBuf& tmp,
                          DevPsm* psms, uint32_t* seg_start, uint32_t* d_nseg, uint32_t* out_perm, cudaStream_t st, int* launches, std::string& err);
-int launch_job_counters(const Job* jobs, const JobResult* res, uint32_t n_jobs, const uint64_t* sp_off, int which, DevCounters* c, cudaStream_t st);
+int launch_job_counters(const Job* jobs, const JobResult* res, uint32_t n_jobs, const uint32_t* sp_npeaks, int which, DevCounters* c, cudaStream_t st,
+                        const uint8_t* skip_job = nullptr);
 int launch_step3_jobs(const DevPsm* psms, const uint32_t* seg_start, uint32_t n_seg, const double* r_mass, uint32_t n_rows, const WindowConfig& W,
                       const double* sp_mass, Job* jobs, SegAgg* agg, unsigned long long* total_cand, cudaStream_t st);
 int launch_step3_aggregate(const JobResult* res, uint32_t n_seg, int n_iso, const uint32_t* seg_start, DevPsm* psms, SegAgg* agg, cudaStream_t st);
@@ -243,7 +252,7 @@ int launch_step4_jobs(const DevPsm* psms, const uint32_t* order, uint32_t n_vali
                       Job* jobs, cudaStream_t st);
 int launch_step4_apply(const Job* jobs, const JobResult* res, const uint32_t* order, uint32_t n_valid, DevPsm* psms, cudaStream_t st);
 int launch_psm_form_keys(const DevPsm* psms, const uint32_t* list, uint32_t n, uint32_t* keys, cudaStream_t st);
-int launch_rank(DevPsm* psms, uint32_t n, const uint32_t* seg_start, cudaStream_t st);
+int launch_rank(DevPsm* psms, uint32_t n, const uint32_t* seg_start, const TargetAux& A, cudaStream_t st);
 int launch_export_psms(const DevPsm* psms, const uint32_t* out_perm, uint32_t n, pq_psm* out, cudaStream_t st);
 // Step-1 novelty filter (k8_novelty.cu): nhit[i] = 1 when target i occurs in a protein (I = L); false + err on refusal / CUDA error
 bool find_in_proteome(int32_t n_seq, const uint32_t* seq_off, const char* res, int32_t n_prot, const uint64_t* prot_off, const char* prot_res,

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 REL = 1e-6      # north_star: "hyperscore/MVH within 1e-6 relative"
 INT_FIELDS = ("spectrum", "form", "count_b", "count_y", "isotope_error", "n_db", "total_db", "n_random", "total_random", "valid",
-              "rank", "confident")
+              "rank", "confident", "charge")
 
 
 def run_gpu(params, sp, tgt, prot, steps=4):
@@ -677,7 +677,8 @@ def test_large_size_properties(large):
     assert a.tobytes() == b.tobytes()
     # (2) internal consistency of the decisions (A.10)
     ev = a["n_random"] >= 0
-    assert np.array_equal(a["valid"] == 1, a["n_db"] == 0)
+    top = a["rank"] == 1                                    # psm_rank.txt carries n_db = total_db = -1 for rank >= 2 (RankPSM.java:89-92)
+    assert np.array_equal(a["valid"][top] == 1, a["n_db"][top] == 0) and np.all(a["n_db"][~top] == -1) and np.all(a["total_db"][~top] == -1)
     assert np.array_equal(ev, a["valid"] == 1)
     assert np.all(a["n_random"][ev] <= a["total_random"][ev]) and np.all(a["total_random"][ev] <= 1000)
     assert np.array_equal(a["p_value"][ev], (a["n_random"][ev] + 1.0) / (a["total_random"][ev] + 1.0))
@@ -835,3 +836,121 @@ def test_pinned_caller_buffers(data, chunk, monkeypatch):
         g.load_spectra(bad)
     g.load_spectra(spp); g.step2(); g.build_reference(); g.step3(); g.step4(); g.rank()
     assert g.psms().tobytes() == ref.psms().tobytes()
+
+
+def _pinned_copy(sp, keep):
+    import torch
+
+    def pin(arr):
+        t = torch.empty(max(1, (arr.nbytes + 7) // 8), dtype=torch.float64, pin_memory=True); keep.append(t)
+        out = t.numpy().view(np.uint8)[:arr.nbytes].view(arr.dtype)
+        out[:] = arr
+        return out
+    return {k: pin(v) for k, v in sp.items()}
+
+
+@pytest.mark.parametrize("method,at_load,chunk", [(1, 1, None), (1, 1, "97"), (1, 0, None), (2, 1, "1000"), (2, 0, "97")])
+def test_candidate_first_load(data, method, at_load, chunk, monkeypatch):
+    """Targets before the spectra + pinned peak arrays: only spectra with a target form in their precursor window have their peaks
+    gathered over PCIe (pq_params.candidate_first; the reference keeps exactly those, pg/SpectraInput.java:243-254).  Same records,
+    detail rows and pair counts as the full upload and as the oracle; fewer bytes cross; what is not resident is refused, not guessed."""
+    prot, tgt, sp = data
+    keep = []
+    spp = _pinned_copy(sp, keep)
+    if chunk:
+        monkeypatch.setenv("PQ_LOAD_CHUNK_SPECTRA", chunk)
+    p = _abi.default_params(n_random=60, score_method=method, prepare_at_load=at_load)
+    o = run_oracle(p, sp, tgt, prot)
+    want = o.psms()
+
+    def search(g):
+        g.step2(); g.build_reference(*prot); g.step3(); g.step4(); g.rank()
+        return g.psms(), np.sort(g.competitors(3), order=["spectrum", "ref_form"]), g.counters()
+    g = Search(p)
+    g.set_targets(*tgt); g.load_spectra(spp)
+    got, comp, c = search(g)
+    assert_psms_equal(got, want)
+    assert [c.pairs_step2, c.pairs_step3, c.pairs_step4] == [int(x) for x in o.pairs()[:3]]
+    # the full upload of the same buffers (PQ_LOAD_FULL) moves every peak and gives the same bytes back
+    monkeypatch.setenv("PQ_LOAD_FULL", "1")
+    f = Search(p)
+    f.set_targets(*tgt); f.load_spectra(spp)
+    got_f, comp_f, cf_ = search(f)
+    monkeypatch.delenv("PQ_LOAD_FULL")
+    assert got.tobytes() == got_f.tobytes() and comp.tobytes() == comp_f.tobytes()
+    total_bytes = 16 * int(sp["peak_off"][-1])
+    assert c.h2d_bytes < cf_.h2d_bytes and cf_.h2d_bytes >= total_bytes > c.h2d_bytes
+    matched = len(np.unique(got["spectrum"]))
+    assert matched <= c.spectra_prepared < cf_.spectra_loaded
+    # a second pass over the resident data: identical
+    got2, comp2, _ = search(g)
+    assert got2.tobytes() == got.tobytes() and comp2.tobytes() == comp.tobytes()
+    # pairs: resident spectra score, the others are refused
+    fg, nf = g.target_forms()
+    s_in = int(got["spectrum"][0])
+    sc, a, b = g.score_pairs([s_in], (_abi.pq_form * 1)(fg[int(got["form"][0])]), 1)
+    assert a[0] == got["count_b"][0] and b[0] == got["count_y"][0] and np.isclose(sc[0], got["score"][0], rtol=REL)
+    hit = set(int(x) for x in got["spectrum"])
+    npk = np.diff(sp["peak_off"].astype(np.int64))
+    cold = [i for i in range(len(npk)) if i not in hit and npk[i] > p.min_peaks]
+    refused = 0
+    for i in cold[:200]:
+        try:
+            g.score_pairs([i], (_abi.pq_form * 1)(fg[0]), 1)
+        except PepQueryError as e:
+            assert e.code == _abi.PQ_ERR_STATE
+            refused += 1
+    assert refused > 0
+    got3, _, _ = search(g)                                   # ... and scoring pairs left the search state alone
+    assert got3.tobytes() == got.tobytes()
+    # other targets on the same load: refused until the spectra are loaded again
+    seqs2 = [q for q in o.reference_sequences() if 8 <= len(q) <= 25][:400]      # peptides of the database: many spectra were made from them
+    off2 = np.cumsum([0] + [len(q) for q in seqs2]).astype(np.uint32)
+    tgt2 = (off2, np.frombuffer("".join(seqs2).encode(), dtype=np.uint8).copy())
+    g.set_targets(*tgt2)
+    with pytest.raises(PepQueryError) as ei:
+        g.step2()
+    assert ei.value.code == _abi.PQ_ERR_STATE
+    g.load_spectra(spp)
+    got4, _, _ = search(g)
+    o2 = run_oracle(p, sp, tgt2, prot)
+    assert_psms_equal(got4, o2.psms())
+
+
+@pytest.mark.parametrize("mode", ["full", "candidate_first"])
+@pytest.mark.parametrize("method", [1, 2])
+def test_spectra_without_a_charge(data, mode, method):
+    """charge = 0 (an MGF block without CHARGE): searched as z = 2, and as z = 3 only when z = 2 saved no PSM
+    (pg/FindCandidateSpectraAndScoreWorker.java:96-228); the PSM carries the charge it was scored with and Steps 3-5 use it."""
+    prot, tgt, sp = data
+    sp0 = {k: v.copy() for k, v in sp.items()}
+    true_z = sp["charge"].copy()
+    blank = (np.arange(len(true_z)) % 3) == 0
+    sp0["charge"][blank] = 0
+    p = _abi.default_params(n_random=60, score_method=method)
+    o = run_oracle(p, sp0, tgt, prot)
+    want = o.psms()
+    keep = []
+    g = Search(p)
+    if mode == "full":
+        g.load_spectra(sp0); g.set_targets(*tgt)
+    else:
+        g.set_targets(*tgt); g.load_spectra(_pinned_copy(sp0, keep))
+    g.step2(); g.build_reference(*prot); g.step3(); g.step4(); g.rank()
+    got = g.psms()
+    assert_psms_equal(got, want)
+    c = g.counters()
+    assert [c.pairs_step2, c.pairs_step3, c.pairs_step4] == [int(x) for x in o.pairs()[:3]]
+    m = blank[got["spectrum"]]
+    assert m.sum() > 20 and set(np.unique(got["charge"][m])) <= {2, 3} and (got["charge"][m] == 3).sum() > 0
+    assert np.array_equal(got["charge"][~m], true_z[got["spectrum"][~m]])
+    co = np.sort(o.competitors(3), order=["spectrum", "ref_form"]); cg = np.sort(g.competitors(3), order=["spectrum", "ref_form"])
+    assert np.array_equal(co["spectrum"], cg["spectrum"]) and np.array_equal(co["ref_form"], cg["ref_form"])
+    # Step 5 on top (uses the stored charge)
+    from pepquery_b200 import unimod
+    ptms = unimod.load_ptms()[:150]
+    g.step5(ptms); o.step5(ptms)
+    assert_psms_equal(g.psms(), o.psms())
+    with pytest.raises(PepQueryError):
+        bad = {k: v.copy() for k, v in sp.items()}; bad["charge"][5] = -1
+        Search(p).load_spectra(bad)

@@ -67,7 +67,7 @@ def oracle_vectors():
         o = pq_oracle.Oracle(p, threads=4)
         o.load_spectra(sp); o.set_targets(*tgt); o.step2(); o.build_reference(*prot); o.step3(); o.step4(); o.rank()
         ps = o.psms()
-        out["method%d" % method] = {f: ps[f].tolist() for f in ps.dtype.names if f != "reserved"}
+        out["method%d" % method] = {f: ps[f].tolist() for f in ps.dtype.names}
         out["method%d" % method]["pairs"] = [int(x) for x in o.pairs()]
         _, nref = o.reference_forms()
         out["method%d" % method]["reference_forms"] = nref
