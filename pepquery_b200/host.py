@@ -204,10 +204,15 @@ class Search:
         self._ck(self.L.pq_get_delta_scores(self.h, _p(a), _p(b), C.c_int64(n.value), C.byref(n)))
         return a[:n.value], b[:n.value]
 
-    def competitors(self, step=3):
+    def competitors(self, step=3, out=None):
+        """detail.txt (step 3) / ptm.txt (step 5) rows.  `out`: optional uint8 buffer (e.g. pinned memory) to fill."""
         n = C.c_int64()
         self._ck(self.L.pq_get_competitors(self.h, C.c_int32(step), None, C.c_int64(0), C.byref(n)))
-        arr = np.empty(max(1, n.value), dtype=competitor_dtype())
+        dt = competitor_dtype()
+        if out is None or n.value * dt.itemsize > out.nbytes:
+            arr = np.empty(max(1, n.value), dtype=dt)
+        else:
+            arr = np.frombuffer(out, dtype=dt, count=max(1, n.value))
         self._ck(self.L.pq_get_competitors(self.h, C.c_int32(step), _p(arr), C.c_int64(n.value), C.byref(n)))
         return arr[:n.value]
 

@@ -43,7 +43,9 @@ def take_shard(sp, bounds, rank):
     counts = (off[sel + 1] - off[sel]).astype(np.uint64)
     new_off = np.zeros(len(sel) + 1, dtype=np.uint64)
     np.cumsum(counts, out=new_off[1:])
-    idx = np.concatenate([np.arange(int(off[s]), int(off[s + 1])) for s in sel]) if len(sel) else np.zeros(0, dtype=np.int64)
+    # peak indices of the selected spectra: for every output peak, its spectrum's first input peak + its position inside it
+    total = int(new_off[-1])
+    idx = (np.repeat(off[sel].astype(np.int64) - new_off[:-1].astype(np.int64), counts.astype(np.int64)) + np.arange(total, dtype=np.int64)) if total else np.zeros(0, dtype=np.int64)
     sub = dict(prec_mz=np.ascontiguousarray(sp["prec_mz"][sel]), charge=np.ascontiguousarray(sp["charge"][sel]), peak_off=new_off,
                mz=np.ascontiguousarray(sp["mz"][idx]), inten=np.ascontiguousarray(sp["inten"][idx]))
     return sub, sel.astype(np.int64)

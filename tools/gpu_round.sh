@@ -12,6 +12,10 @@ for a in "$@"; do
         timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/sanitizer_${tool}_$TAG.log 2>&1; echo "$tool rc=$?"; tail -4 gpurun_out/sanitizer_${tool}_$TAG.log
       done;;
     ncu)
-      ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 1 --no-cpu --e2e-steps 0 > gpurun_out/ncu_l_$TAG.log 2>&1; echo "ncu list rc=$?";;
+      ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 1 --no-cpu --e2e-steps 0 --no-configs > gpurun_out/ncu_l_$TAG.log 2>&1; echo "ncu list rc=$?";;
+    ncufull)
+      ncu --set full --clock-control none --import-source on -k regex:k1_score_kernel -s 4 -c 2 -f -o gpurun_out/prof_$TAG python bench.py --steps 1 --warmup 1 --no-cpu --e2e-steps 0 --no-configs > gpurun_out/ncu_f_$TAG.log 2>&1; echo "ncu full rc=$?";;
+    load)
+      python tools/prof_load2.py > gpurun_out/load_$TAG.log 2>&1; echo "load rc=$?"; cat gpurun_out/load_$TAG.log | tail -12;;
   esac
 done
