@@ -166,7 +166,8 @@ __device__ __forceinline__ uint32_t count_lt(const double* a, uint32_t n, double
 template <int kPrepWarps, int METHOD>
 __global__ void __launch_bounds__(32 * kPrepWarps)
 k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_list, PrepConfig cfg, uint8_t* __restrict__ blobs,
-                  const uint64_t* __restrict__ blob_off, uint32_t* __restrict__ blob_len, uint32_t cap, uint32_t p_lo, uint32_t p_hi) {
+                  const uint64_t* __restrict__ blob_off, uint32_t* __restrict__ blob_len, uint32_t cap, uint32_t p_lo, uint32_t p_hi,
+                  const int32_t* __restrict__ blob_index /* null: blob of list item i is blob i; else blob_index[spectrum] */) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ double s_val[kPrepWarps][kValSlots];
     __shared__ double s_d[kPrepWarps][4];
@@ -442,7 +443,8 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         }
         __syncwarp();
         const BlobLayout BL = blob_layout(E);
-        uint8_t* blob = blobs + blob_off[item];
+        const int32_t bi = blob_index ? blob_index[s] : item;
+        uint8_t* blob = blobs + blob_off[bi];
         double* g_ev = reinterpret_cast<double*>(blob + BL.ev);
         uint16_t* g_ans = reinterpret_cast<uint16_t*>(blob + BL.ans);
         double* g_pmz = reinterpret_cast<double*>(blob + BL.pmz);
@@ -631,7 +633,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             for (int c = 0; c < 4; ++c) h.cls_count[c] = METHOD == 2 ? s_cls[warp][c] : 0;
             h.total_bytes = BL.total; h.raw_peaks = P; h.pad[0] = h.pad[1] = 0;
             *reinterpret_cast<BlobHeader*>(blob) = h;
-            blob_len[item] = BL.total;
+            blob_len[bi] = BL.total;
         }
         __syncwarp();
     }
@@ -640,7 +642,8 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
 }  // namespace
 
 int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, const PrepConfig& cfg, uint8_t* blobs,
-                   const uint64_t* blob_off, uint32_t* blob_len, uint32_t max_peaks, cudaStream_t st, uint32_t min_peaks) {
+                   const uint64_t* blob_off, uint32_t* blob_len, uint32_t max_peaks, cudaStream_t st, uint32_t min_peaks, const int32_t* blob_index,
+                   int leave_blocks_per_sm) {
     if (n_list <= 0) return 0;
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int launched = 0;
@@ -650,9 +653,10 @@ int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, c
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * warps, smem);
+        per_sm -= leave_blocks_per_sm;               // room for a kernel of another stream (the candidate-first gather) beside this persistent grid
         if (per_sm < 1) per_sm = 1;
         int grid = sms * per_sm; int need = (n_list + warps - 1) / warps; if (grid > need) grid = need;
-        kernel<<<grid, 32 * warps, smem, st>>>(sp, list, n_list, cfg, blobs, blob_off, blob_len, cap, p_lo, p_hi);
+        kernel<<<grid, 32 * warps, smem, st>>>(sp, list, n_list, cfg, blobs, blob_off, blob_len, cap, p_lo, p_hi, blob_index);
         ++launched;
     };
     // size class 1: up to 256 peaks (the common case), four spectra per CTA; size class 2: the rest, capacity = next power of two

@@ -90,6 +90,7 @@ struct pq_ctx {
     uint32_t n_prepared = 0; uint32_t max_blob = 0;
     bool prepared_at_load = false;           // blobs were written by pq_load_spectra: blob id = virtual id (full upload) or rank among the resident spectra (candidate-first)
     DevBuf s_inv;                            // virtual id -> mass-sorted position
+    DevBuf gather_list;                      // candidate-first: the resident spectra (sorted positions) in caller order
     DevBuf d_zero;                           // caller indices of the charge-less spectra, ascending
     // tables
     PeptideTable targets, reference;
@@ -568,7 +569,13 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
             k_launch += launch_resident_counts(nv, ctx->s_npeaks.as<uint32_t>(), ctx->s_res.as<int32_t>(), ctx->scratch.as<uint64_t>(), st);
             rc = scan_exclusive(ctx, ctx->scratch.as<uint64_t>(), ctx->s_off.as<uint64_t>(), (int)nv + 1);
             if (rc) return fail_load(rc, ctx->err);
-            k_launch += 4;
+            // the same spectra in CALLER order (ascending host address): the order the gather reads them in
+            CL(ctx->z_keep.reserve((size_t)nv + 64)); CL(ctx->gather_list.reserve((size_t)(nv + 2) * 4));
+            k_launch += launch_flags_by_virtual(nv, ctx->s_inv.as<int32_t>(), ctx->s_res.as<int32_t>(), ctx->z_keep.as<uint8_t>(), st);
+            cub::DeviceSelect::Flagged(nullptr, tmp, ctx->s_inv.as<int32_t>(), ctx->z_keep.as<uint8_t>(), ctx->gather_list.as<int32_t>(), d_nsel, (int)nv, st);
+            CL(ctx->scan_tmp.reserve(tmp + 64));
+            CL(cub::DeviceSelect::Flagged(ctx->scan_tmp.p, tmp, ctx->s_inv.as<int32_t>(), ctx->z_keep.as<uint8_t>(), ctx->gather_list.as<int32_t>(), d_nsel, (int)nv, st));
+            k_launch += 6;
         }
         CL(cudaMemcpyAsync(&hn.n_res, ctx->prep_id.as<int32_t>() + nv, 4, cudaMemcpyDeviceToHost, st));
         CL(cudaMemcpyAsync(&hn.res_peaks, ctx->s_off.as<uint64_t>() + nv, 8, cudaMemcpyDeviceToHost, st));
@@ -606,14 +613,14 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
             Timer t(ctx, &ctx->cnt.ms_prepare);
             for (size_t c = 0; c < nck; ++c) {
                 const uint32_t a = (uint32_t)(c * chunk_spectra), cnt = std::min(chunk_spectra, n_res - a);
-                k_launch += launch_gather_peaks_from_host(ctx->prep_list.as<int32_t>() + a, (int32_t)cnt, ctx->s_caller.as<int32_t>(), in_off.as<uint64_t>(),
+                k_launch += launch_gather_peaks_from_host(ctx->gather_list.as<int32_t>() + a, (int32_t)cnt, ctx->s_caller.as<int32_t>(), in_off.as<uint64_t>(),
                                                           ctx->s_off.as<uint64_t>(), static_cast<const double*>(d_h_mz), static_cast<const double*>(d_h_in),
                                                           ctx->s_mz.as<double>(), ctx->s_in.as<double>(), sms, sc);
                 CL(cudaEventRecord(ctx->chunk_ev[c], sc));
                 CL(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
-                if (eager)
-                    k_launch += launch_prepare(sp, ctx->prep_list.as<int32_t>() + a, (int32_t)cnt, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>() + a,
-                                               ctx->blob_len.as<uint32_t>() + a, ctx->max_peaks, st);
+                if (eager)          // blob id = rank in mass order (prep_id); one K0 block per SM less than would fit: the next chunk's gather runs beside it
+                    k_launch += launch_prepare(sp, ctx->gather_list.as<int32_t>() + a, (int32_t)cnt, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(),
+                                               ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st, 0, ctx->prep_id.as<int32_t>(), 1);
             }
             if (eager) { ctx->prepared_at_load = true; ctx->n_prepared = n_res; ctx->cnt.spectra_prepared = n_res; ctx->max_blob = blob_bytes(ctx->max_peaks); }
         }

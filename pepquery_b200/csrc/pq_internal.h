@@ -120,7 +120,8 @@ struct ScoreLaunch {
 
 // kernel launchers (each returns the number of kernels it launched; errors via cudaGetLastError by the caller)
 int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, const PrepConfig& cfg, uint8_t* blobs,
-                   const uint64_t* blob_off, uint32_t* blob_len, uint32_t max_peaks, cudaStream_t st, uint32_t min_peaks = 0);
+                   const uint64_t* blob_off, uint32_t* blob_len, uint32_t max_peaks, cudaStream_t st, uint32_t min_peaks = 0,
+                   const int32_t* blob_index = nullptr, int leave_blocks_per_sm = 0);
 int launch_score(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st);
 
 // Step-2 window enumeration on device: for every usable spectrum x isotope error, the run of target rows whose mass
@@ -171,6 +172,7 @@ int launch_virtual_meta(int64_t nv, int64_t n, const double* prec_mz, const int3
 int launch_gather_meta(int64_t nv, int64_t n, const int32_t* order, const double* prec_mz_in, const int32_t* charge_in, const int32_t* zero_idx,
                        const int32_t* vz, const double* mass_in, const uint64_t* off_in, double* prec_mz, int32_t* charge, double* mass,
                        int32_t* caller, uint32_t* npeaks, uint8_t* alias, cudaStream_t st);
+int launch_flags_by_virtual(int64_t nv, const int32_t* inv, const int32_t* flag_sorted, uint8_t* flag_virtual, cudaStream_t st);
 int launch_resident_counts(int64_t nv, const uint32_t* npeaks, const int32_t* resident, uint64_t* count, cudaStream_t st);
 int launch_gather_peaks_from_host(const int32_t* list, int32_t n_list, const int32_t* caller, const uint64_t* off_in, const uint64_t* off_out,
                                   const double* h_mz, const double* h_in, double* mz_out, double* in_out, int sms, cudaStream_t st);
