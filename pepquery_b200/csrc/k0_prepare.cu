@@ -167,7 +167,8 @@ template <int kPrepWarps, int METHOD>
 __global__ void __launch_bounds__(32 * kPrepWarps)
 k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_list, PrepConfig cfg, uint8_t* __restrict__ blobs,
                   const uint64_t* __restrict__ blob_off, uint32_t* __restrict__ blob_len, uint32_t cap, uint32_t p_lo, uint32_t p_hi,
-                  const int32_t* __restrict__ blob_index /* null: blob of list item i is blob i; else blob_index[spectrum] */) {
+                  const int32_t* __restrict__ blob_index /* null: blob of list item i is blob i; else blob_index[spectrum] */,
+                  uint32_t* __restrict__ work_counter /* null: items by static stride; else the next unclaimed item (zeroed by the launcher) */) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ double s_val[kPrepWarps][kValSlots];
     __shared__ double s_d[kPrepWarps][4];
@@ -185,8 +186,16 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
     const double itol = cfg.itol;
 
     const int32_t total_warps = (int32_t)gridDim.x * kPrepWarps;
+    // Work is handed out warp by warp from a counter when there is one: spectra differ 10x in cost and a launch covers one upload
+    // chunk, so with a static stride every launch ended on its unluckiest warp.
+    auto next_item = [&](int32_t cur) -> int32_t {
+        if (!work_counter) return cur < 0 ? (int32_t)blockIdx.x * kPrepWarps + warp : cur + total_warps;
+        int32_t v = 0;
+        if (lane == 0) v = (int32_t)atomicAdd(work_counter, 1u);
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
     #pragma unroll 1
-    for (int32_t item = (int32_t)blockIdx.x * kPrepWarps + warp; item < n_list; item += total_warps) {
+    for (int32_t item = next_item(-1); item < n_list; item = next_item(item)) {
         const int32_t s = list[item];
         const uint64_t base = sp.off[s];
         const uint32_t P = (uint32_t)(sp.off[s + 1] - base);
@@ -643,7 +652,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
 
 int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, const PrepConfig& cfg, uint8_t* blobs,
                    const uint64_t* blob_off, uint32_t* blob_len, uint32_t max_peaks, cudaStream_t st, uint32_t min_peaks, const int32_t* blob_index,
-                   int leave_blocks_per_sm) {
+                   int leave_blocks_per_sm, uint32_t* work_counters /* one zeroed word per kernel this call may launch (4), or null */) {
     if (n_list <= 0) return 0;
     int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int launched = 0;
@@ -656,7 +665,8 @@ int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, c
         per_sm -= leave_blocks_per_sm;               // room for a kernel of another stream (the candidate-first gather) beside this persistent grid
         if (per_sm < 1) per_sm = 1;
         int grid = sms * per_sm; int need = (n_list + warps - 1) / warps; if (grid > need) grid = need;
-        kernel<<<grid, 32 * warps, smem, st>>>(sp, list, n_list, cfg, blobs, blob_off, blob_len, cap, p_lo, p_hi, blob_index);
+        kernel<<<grid, 32 * warps, smem, st>>>(sp, list, n_list, cfg, blobs, blob_off, blob_len, cap, p_lo, p_hi, blob_index,
+                                               work_counters ? work_counters + launched : nullptr);
         ++launched;
     };
     // size class 1: up to 256 peaks (the common case), four spectra per CTA; size class 2: the rest, capacity = next power of two

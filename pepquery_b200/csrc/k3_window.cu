@@ -5,6 +5,8 @@
 // Enumeration replaces the 0.1-Da HashMap probe of FindCandidateSpectraAndScoreWorker.run
 // (pg/FindCandidateSpectraAndScoreWorker.java:33-58): a conservative run of mass-sorted target rows per
 // (spectrum, isotope error); K1 applies the exact bucket + tolerance predicate to every row of the run.
+#include <cstdlib>
+
 #include "pq_internal.h"
 
 namespace pq {
@@ -240,7 +242,11 @@ int launch_resident_counts(int64_t nv, const uint32_t* npeaks, const int32_t* re
 int launch_gather_peaks_from_host(const int32_t* list, int32_t n_list, const int32_t* caller, const uint64_t* off_in, const uint64_t* off_out,
                                   const double* h_mz, const double* h_in, double* mz_out, double* in_out, int sms, cudaStream_t st) {
     if (n_list <= 0) return 0;
-    int grid = sms * 2; int need = (n_list + 3) / 4; if (grid > need) grid = need;      // small CTAs: they run beside K0's persistent grid
+    // A FEW CTAs only: reads of host memory stay ~2 us in an SM's miss queues, and K0 running on the same SM was seen to slow down
+    // 3-4x; PCIe needs only some hundred KB in flight, so the gather occupies a fraction of the SMs and leaves the rest to K0.
+    int grid = 32; (void)sms;
+    if (const char* e = getenv("PQ_GATHER_CTAS")) { int v = atoi(e); if (v > 0) grid = v; }
+    int need = (n_list + 3) / 4; if (grid > need) grid = need;
     k_gather_peaks_from_host<<<grid, 128, 0, st>>>(list, n_list, caller, off_in, off_out, h_mz, h_in, mz_out, in_out);
     return 1;
 }

@@ -91,6 +91,7 @@ struct pq_ctx {
     bool prepared_at_load = false;           // blobs were written by pq_load_spectra: blob id = virtual id (full upload) or rank among the resident spectra (candidate-first)
     DevBuf s_inv;                            // virtual id -> mass-sorted position
     DevBuf gather_list;                      // candidate-first: the resident spectra (sorted positions) in caller order
+    DevBuf k0_counters;                      // work hand-out words of the per-chunk K0 launches
     DevBuf d_zero;                           // caller indices of the charge-less spectra, ascending
     // tables
     PeptideTable targets, reference;
@@ -492,8 +493,8 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
     const bool want_cf = ctx->P.candidate_first != 0 && getenv("PQ_LOAD_FULL") == nullptr;
     const bool cf = want_cf && ctx->have_targets && !ctx->targets.seqs.empty() && pinned_all;
     const bool digest_here = ctx->ref_staged && !ctx->ref_digested && ctx->have_targets;
-    if (digest_here) {          // the target keys of a staged reference digest go up before the copy engine fills with spectra
-        std::string err;
+    if (digest_here && !cf) {   // full upload: the target keys of a staged reference digest go up before the copy engine fills with spectra
+        std::string err;        // (candidate-first moves the peaks with a kernel: the keys go up on the digest's own stream, later)
         if (!upload_target_keys_for_reference(st, ctx->targets.seqs, ctx->reference.dev, err)) return fail_load(PQ_ERR_CUDA, "reference digest: " + err);
     }
     int k_launch = 0;
@@ -608,19 +609,34 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
             const size_t nck = ((size_t)n_res + chunk_spectra - 1) / chunk_spectra;
             while (ctx->chunk_ev.size() < nck + 1) { cudaEvent_t e; CL(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
             if (!ctx->meta_ev) CL(cudaEventCreateWithFlags(&ctx->meta_ev, cudaEventDisableTiming));
+            CL(ctx->k0_counters.reserve((nck + 1) * 16)); CL(cudaMemsetAsync(ctx->k0_counters.p, 0, (nck + 1) * 16, st));
             CL(cudaEventRecord(ctx->meta_ev, st));
             CL(cudaStreamWaitEvent(sc, ctx->meta_ev, 0));
             Timer t(ctx, &ctx->cnt.ms_prepare);
+            const bool trace = getenv("PQ_LOAD_TRACE") != nullptr;          // diagnostic: when did every chunk's gather / K0 finish?
+            std::vector<cudaEvent_t> tr_g, tr_k; cudaEvent_t tr0 = nullptr;
+            if (trace) { cudaEventCreate(&tr0); cudaEventRecord(tr0, sc); }
             for (size_t c = 0; c < nck; ++c) {
                 const uint32_t a = (uint32_t)(c * chunk_spectra), cnt = std::min(chunk_spectra, n_res - a);
                 k_launch += launch_gather_peaks_from_host(ctx->gather_list.as<int32_t>() + a, (int32_t)cnt, ctx->s_caller.as<int32_t>(), in_off.as<uint64_t>(),
                                                           ctx->s_off.as<uint64_t>(), static_cast<const double*>(d_h_mz), static_cast<const double*>(d_h_in),
                                                           ctx->s_mz.as<double>(), ctx->s_in.as<double>(), sms, sc);
                 CL(cudaEventRecord(ctx->chunk_ev[c], sc));
+                if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sc); tr_g.push_back(e); }
                 CL(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
                 if (eager)          // blob id = rank in mass order (prep_id); one K0 block per SM less than would fit: the next chunk's gather runs beside it
                     k_launch += launch_prepare(sp, ctx->gather_list.as<int32_t>() + a, (int32_t)cnt, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(),
-                                               ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st, 0, ctx->prep_id.as<int32_t>(), 1);
+                                               ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st, 0, ctx->prep_id.as<int32_t>(), 1, ctx->k0_counters.as<uint32_t>() + 4 * c);
+                if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tr_k.push_back(e); }
+            }
+            if (trace) {
+                cudaStreamSynchronize(sc); cudaStreamSynchronize(st);
+                for (size_t c = 0; c < tr_g.size(); ++c) {
+                    float g = 0, k = 0; cudaEventElapsedTime(&g, tr0, tr_g[c]); cudaEventElapsedTime(&k, tr0, tr_k[c]);
+                    fprintf(stderr, "[pq] load trace: chunk %3zu gather done %8.3f ms  K0 done %8.3f ms\n", c, g, k);
+                    cudaEventDestroy(tr_g[c]); cudaEventDestroy(tr_k[c]);
+                }
+                cudaEventDestroy(tr0);
             }
             if (eager) { ctx->prepared_at_load = true; ctx->n_prepared = n_res; ctx->cnt.spectra_prepared = n_res; ctx->max_blob = blob_bytes(ctx->max_peaks); }
         }
@@ -696,7 +712,10 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
     CL(cudaGetLastError());
     // a protein database staged before the spectra (pq_stage_reference): its digest does not depend on them and runs now, on a
     // third stream, beside the work above
-    if (digest_here) { int32_t rc = digest_staged_reference(ctx, ctx->st_aux); if (rc) return fail_load(rc, ctx->err); }
+    if (digest_here) {
+        if (cf) { std::string err; if (!upload_target_keys_for_reference(ctx->st_aux, ctx->targets.seqs, ctx->reference.dev, err)) return fail_load(PQ_ERR_CUDA, "reference digest: " + err); }
+        int32_t rc = digest_staged_reference(ctx, ctx->st_aux); if (rc) return fail_load(rc, ctx->err);
+    }
     mk.mark("digest (staged reference)");
     // targets given before the spectra: their table is built while the peaks are on their way (device work, a few launches)
     if (ctx->have_targets && !cf) { int32_t rc = finalize_targets(ctx); if (rc) return fail_load(rc, ctx->err); }

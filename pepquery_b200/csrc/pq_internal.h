@@ -121,7 +121,7 @@ struct ScoreLaunch {
 // kernel launchers (each returns the number of kernels it launched; errors via cudaGetLastError by the caller)
 int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, const PrepConfig& cfg, uint8_t* blobs,
                    const uint64_t* blob_off, uint32_t* blob_len, uint32_t max_peaks, cudaStream_t st, uint32_t min_peaks = 0,
-                   const int32_t* blob_index = nullptr, int leave_blocks_per_sm = 0);
+                   const int32_t* blob_index = nullptr, int leave_blocks_per_sm = 0, uint32_t* work_counters = nullptr);
 int launch_score(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st);
 
 // Step-2 window enumeration on device: for every usable spectrum x isotope error, the run of target rows whose mass

@@ -11,10 +11,14 @@ def pinned(n):
     t = torch.empty(int(n), dtype=torch.float64, pin_memory=True); keep.append(t); return t.numpy()
 prot, tgt, sp = bench.make_inputs(a, 0, 1, pinned)
 spg = {k: np.array(v) for k, v in sp.items()}
-modes = [("cf", {}, 1, sp), ("cf no K0 in load", {}, 0, sp), ("cf chunk 8192", {"PQ_LOAD_CHUNK_SPECTRA": "8192"}, 1, sp), ("cf chunk 131072", {"PQ_LOAD_CHUNK_SPECTRA": "131072"}, 1, sp),
+modes = [("cf", {}, 1, sp), ("g8", {"PQ_GATHER_CTAS": "8"}, 1, sp), ("g16", {"PQ_GATHER_CTAS": "16"}, 1, sp), ("g64", {"PQ_GATHER_CTAS": "64"}, 1, sp), ("g148", {"PQ_GATHER_CTAS": "148"}, 1, sp),
+         ("g16 noK0", {"PQ_GATHER_CTAS": "16"}, 0, sp), ("g64 c131072", {"PQ_GATHER_CTAS": "64", "PQ_LOAD_CHUNK_SPECTRA": "131072"}, 1, sp), ("cf no K0 in load", {}, 0, sp), ("cf chunk 8192", {"PQ_LOAD_CHUNK_SPECTRA": "8192"}, 1, sp), ("cf chunk 131072", {"PQ_LOAD_CHUNK_SPECTRA": "131072"}, 1, sp),
          ("cf one chunk", {"PQ_LOAD_CHUNK_SPECTRA": "100000000"}, 1, sp), ("full pinned", {"PQ_LOAD_FULL": "1"}, 1, sp), ("full pageable", {}, 1, spg)]
+only = os.environ.get("PROF_MODES")
 for name, env, at_load, spx in modes:
-    for k in ("PQ_LOAD_CHUNK_SPECTRA", "PQ_LOAD_FULL"): os.environ.pop(k, None)
+    if only and name not in only.split(","):
+        continue
+    for k in ("PQ_LOAD_CHUNK_SPECTRA", "PQ_LOAD_FULL", "PQ_GATHER_CTAS"): os.environ.pop(k, None)
     os.environ.update(env)
     g = Search(_abi.default_params(n_random=1000, prepare_at_load=at_load))
     rows = []
