@@ -113,6 +113,12 @@ typedef struct pq_params {
                                    those in SpectraInput.spectraMap, pg/SpectraInput.java:243-254): a kernel gathers them from the
                                    caller's arrays over PCIe.  A later pq_set_targets with other targets then needs a new
                                    pq_load_spectra (PQ_ERR_STATE otherwise).  0: every peak is uploaded.  Same results */
+    int32_t search_at_load;     /* 1 (default): when pq_load_spectra can tell everything a search needs — targets set, the database handed
+                                   over by pq_stage_reference, candidate-first upload — it also runs Steps 2-4 on each part of the spectra as
+                                   soon as that part has arrived, beside the rest of the upload.  pq_step2_match_targets,
+                                   pq_build_reference(ctx, 0, NULL, NULL), pq_step3_competitors and pq_step4_shuffles then return what is
+                                   already there.  0: every step runs when it is called.  Same results */
+    int32_t reserved1;
 } pq_params;
 
 /* One peptide form (sequence + placed modifications) as the caller sees it. */

@@ -46,7 +46,8 @@ class pq_params(C.Structure):
                 ("n_fixed", C.c_int32), ("n_var", C.c_int32),
                 ("fixed", pq_mod * PQ_MAX_MODS), ("var", pq_mod * PQ_MAX_MODS),
                 ("device", C.c_int32), ("score_all_shuffles", C.c_int32),
-                ("prepare_at_load", C.c_int32), ("candidate_first", C.c_int32)]
+                ("prepare_at_load", C.c_int32), ("candidate_first", C.c_int32),
+                ("search_at_load", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class pq_form(C.Structure):
@@ -111,7 +112,7 @@ def default_params(fixed=(CARBAMIDOMETHYL_C,), var=(OXIDATION_M,), **over):
     p.n_isotope = 1; p.isotope[0] = 0
     p.max_var_mods = 3; p.max_mods_per_aa = 1; p.fast = 0; p.hc = 0; p.n_random = 1000
     p.enzyme = 1; p.max_missed = 2; p.min_len = 7; p.max_len = 45; p.min_mass = 500.0; p.max_mass = 10000.0
-    p.shuffle_seed = 12457; p.mod_seed = 2022; p.prepare_at_load = 1; p.candidate_first = 1
+    p.shuffle_seed = 12457; p.mod_seed = 2022; p.prepare_at_load = 1; p.candidate_first = 1; p.search_at_load = 1
     p.n_fixed = len(fixed); p.n_var = len(var)
     for i, m in enumerate(fixed):
         p.fixed[i] = make_mod(**m)

@@ -177,6 +177,14 @@ __global__ void k7_flag_valid(const DevPsm* __restrict__ psms, uint32_t n, const
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_valid, (uint32_t)__popc(b));
 }
 
+__global__ void k7_valid_flags(const DevPsm* __restrict__ psms, uint32_t n, uint8_t* __restrict__ valid_flag, uint32_t* __restrict__ n_valid) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = i < n ? psms[i].valid : 0;
+    if (i < n) valid_flag[i] = v ? 1 : 0;
+    const uint32_t b = __ballot_sync(0xffffffffu, v != 0);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_valid, (uint32_t)__popc(b));
+}
+
 __device__ unsigned long long choose_u64(int n, int k) {
     if (k < 0 || k > n) return 0ull;
     if (k > n - k) k = n - k;
@@ -400,7 +408,119 @@ __global__ void k7_set_nptm(DevPsm* __restrict__ psms, uint32_t n, const int32_t
 
 inline unsigned blocks(uint32_t n, int per = 256) { return (n + per - 1) / per; }
 
+// ---- merging the parts of a search that ran while the spectra were still arriving (pq_load_spectra, search_at_load) ----
+__global__ void k7_merge_psms(const DevPsm* __restrict__ in, uint32_t n, uint32_t seg_off, DevPsm* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DevPsm p = in[i]; p.seg += seg_off; out[i] = p;
+}
+__global__ void k7_merge_segs(const uint32_t* __restrict__ seg_start_in, const SegAgg* __restrict__ agg_in, uint32_t n_seg, uint32_t psm_off, uint32_t row_off,
+                              uint32_t* __restrict__ seg_start_out, SegAgg* __restrict__ agg_out, uint32_t end_value, int last) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_seg) return;
+    seg_start_out[i] = seg_start_in[i] + psm_off;
+    if (agg_in) { SegAgg g = agg_in[i]; if (g.best_row != 0xffffffffu) g.best_row -= row_off; agg_out[i] = g; }
+    if (last && i == n_seg - 1) seg_start_out[n_seg] = end_value;
+}
+__global__ void k7_merge_hits(const Hit* __restrict__ in, uint32_t n, uint32_t row_off, Hit* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Hit h = in[i]; h.cand -= row_off; out[i] = h;
+}
+// Step-2 jobs of a search at load: key = (part of the job's spectrum, charge, first target row, rows); rank_in_upload[s] = position of
+// sorted spectrum s in the order the upload brings the spectra over, part = rank / part_spectra
+__global__ void k7_part_job_keys(const Job* __restrict__ jobs, uint32_t n, const uint32_t* __restrict__ rank_in_upload, uint32_t part_spectra,
+                                 uint64_t* __restrict__ key, uint32_t* __restrict__ idx) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Job& J = jobs[i];
+    uint64_t part = rank_in_upload[J.spectrum] / part_spectra, z = (uint64_t)min(max(J.charge, 0), 15);
+    key[i] = (part << 52) | (z << 48) | ((uint64_t)(J.cand_begin & 0xFFFFFFFFFFull) << 8) | (uint64_t)min(J.cand_count, 255u);
+    idx[i] = i;
+}
+__global__ void k7_part_bounds(const uint64_t* __restrict__ sorted_key, uint32_t n, uint32_t n_parts, uint32_t* __restrict__ first /* [n_parts + 1] */) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > n_parts) return;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((sorted_key[mid] >> 52) < (uint64_t)p) lo = mid + 1; else hi = mid; }
+    first[p] = lo;
+}
+// candidate rows of the Step-2 jobs of every part (sizes the parts' hit buffers)
+__global__ void k7_part_cand(const Job* __restrict__ jobs, uint32_t n, const uint64_t* __restrict__ sorted_key, unsigned long long* __restrict__ cand /* [n_parts] zeroed */) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&cand[(uint32_t)(sorted_key[i] >> 52)], (unsigned long long)jobs[i].cand_count);
+}
+// rows of a mass-sorted table inside the open window (lo, hi): [a, b)
+__global__ void k7_window_rows(const double* __restrict__ mass, uint32_t n, double lo, double hi, uint32_t* __restrict__ ab) {
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t l = 0, h = n;
+    while (l < h) { uint32_t m = (l + h) >> 1; if (mass[m] <= lo) l = m + 1; else h = m; }
+    ab[0] = l;
+    l = 0; h = n;
+    while (l < h) { uint32_t m = (l + h) >> 1; if (mass[m] < hi) l = m + 1; else h = m; }
+    ab[1] = l;
+}
+__global__ void k7_scatter_rank(const int32_t* __restrict__ list, uint32_t n, uint32_t* __restrict__ rank) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rank[list[i]] = i;
+}
+__global__ void k7_fill_u8(uint8_t* p, uint32_t n, uint8_t v) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+__global__ void k7_fill_u32(uint32_t* p, uint32_t n, uint32_t v) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
 }  // namespace
+
+int launch_merge_psms(const DevPsm* in, uint32_t n, uint32_t seg_off, DevPsm* out, cudaStream_t st) {
+    if (!n) return 0;
+    k7_merge_psms<<<blocks(n), 256, 0, st>>>(in, n, seg_off, out);
+    return 1;
+}
+int launch_merge_segs(const uint32_t* seg_start_in, const SegAgg* agg_in, uint32_t n_seg, uint32_t psm_off, uint32_t row_off, uint32_t* seg_start_out, SegAgg* agg_out,
+                      uint32_t end_value, int last, cudaStream_t st) {
+    if (!n_seg) return 0;
+    k7_merge_segs<<<blocks(n_seg), 256, 0, st>>>(seg_start_in, agg_in, n_seg, psm_off, row_off, seg_start_out, agg_out, end_value, last);
+    return 1;
+}
+int launch_merge_hits(const Hit* in, uint32_t n, uint32_t row_off, Hit* out, cudaStream_t st) {
+    if (!n) return 0;
+    k7_merge_hits<<<blocks(n), 256, 0, st>>>(in, n, row_off, out);
+    return 1;
+}
+int launch_part_job_keys(const Job* jobs, uint32_t n, const uint32_t* rank_in_upload, uint32_t part_spectra, uint64_t* key, uint32_t* idx, cudaStream_t st) {
+    if (!n) return 0;
+    k7_part_job_keys<<<blocks(n), 256, 0, st>>>(jobs, n, rank_in_upload, part_spectra, key, idx);
+    return 1;
+}
+int launch_part_bounds(const uint64_t* sorted_key, uint32_t n, uint32_t n_parts, uint32_t* first, cudaStream_t st) {
+    k7_part_bounds<<<blocks(n_parts + 1), 256, 0, st>>>(sorted_key, n, n_parts, first);
+    return 1;
+}
+int launch_part_cand(const Job* jobs, uint32_t n, const uint64_t* sorted_key, unsigned long long* cand, cudaStream_t st) {
+    if (!n) return 0;
+    k7_part_cand<<<blocks(n), 256, 0, st>>>(jobs, n, sorted_key, cand);
+    return 1;
+}
+int launch_window_rows(const double* mass, uint32_t n, double lo, double hi, uint32_t* ab, cudaStream_t st) {
+    k7_window_rows<<<1, 32, 0, st>>>(mass, n, lo, hi, ab);
+    return 1;
+}
+int launch_scatter_rank(const int32_t* list, uint32_t n, uint32_t* rank, cudaStream_t st) {
+    if (!n) return 0;
+    k7_scatter_rank<<<blocks(n), 256, 0, st>>>(list, n, rank);
+    return 1;
+}
+int launch_fill_u8(uint8_t* p, uint32_t n, uint8_t v, cudaStream_t st) { if (!n) return 0; k7_fill_u8<<<blocks(n), 256, 0, st>>>(p, n, v); return 1; }
+int launch_fill_u32(uint32_t* p, uint32_t n, uint32_t v, cudaStream_t st) { if (!n) return 0; k7_fill_u32<<<blocks(n), 256, 0, st>>>(p, n, v); return 1; }
+bool build_out_perm(const DevPsm* psms, uint32_t n, DevBuf& key_a, DevBuf& key_b, DevBuf& idx_a, DevBuf& tmp, uint32_t* out_perm, cudaStream_t st, std::string& err) {
+    if (!n) return true;
+    RB(key_a.reserve((size_t)n * 8)); RB(key_b.reserve((size_t)n * 8)); RB(idx_a.reserve((size_t)n * 4));
+    size_t b1 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, key_a.as<uint64_t>(), key_b.as<uint64_t>(), idx_a.as<uint32_t>(), out_perm, (int)n, 0, 64, st);
+    RB(tmp.reserve(b1 + 64));
+    k7_out_keys<<<blocks(n), 256, 0, st>>>(psms, n, key_a.as<uint64_t>(), idx_a.as<uint32_t>());
+    RB(cub::DeviceRadixSort::SortPairs(tmp.p, b1, key_a.as<uint64_t>(), key_b.as<uint64_t>(), idx_a.as<uint32_t>(), out_perm, (int)n, 0, 64, st));
+    RB(cudaGetLastError());
+    return true;
+}
 
 bool psm_table_from_hits(const Hit* hits, uint32_t nh, const SpectraView& sp, const double* t_mass, const uint8_t* t_rows, const TargetAux& A,
                          DevBuf& key_a, DevBuf& key_b, DevBuf& idx_a, DevBuf& idx_b, DevBuf& head, DevBuf& tmp,
@@ -416,8 +536,10 @@ bool psm_table_from_hits(const Hit* hits, uint32_t nh, const SpectraView& sp, co
     k7_build_psms<<<blocks(nh), 256, 0, st>>>(hits, idx_b.as<uint32_t>(), nh, sp, t_mass, t_rows, A, psms, head.as<uint32_t>());
     RB(cub::DeviceScan::InclusiveSum(tmp.p, b2, head.as<uint32_t>(), idx_a.as<uint32_t>(), (int)nh, st));
     k7_set_segments<<<blocks(nh), 256, 0, st>>>(head.as<uint32_t>(), idx_a.as<uint32_t>(), nh, psms, seg_start, d_nseg);
-    k7_out_keys<<<blocks(nh), 256, 0, st>>>(psms, nh, key_a.as<uint64_t>(), idx_a.as<uint32_t>());
-    RB(cub::DeviceRadixSort::SortPairs(tmp.p, b1, key_a.as<uint64_t>(), key_b.as<uint64_t>(), idx_a.as<uint32_t>(), out_perm, (int)nh, 0, 64, st));
+    if (out_perm) {
+        k7_out_keys<<<blocks(nh), 256, 0, st>>>(psms, nh, key_a.as<uint64_t>(), idx_a.as<uint32_t>());
+        RB(cub::DeviceRadixSort::SortPairs(tmp.p, b1, key_a.as<uint64_t>(), key_b.as<uint64_t>(), idx_a.as<uint32_t>(), out_perm, (int)nh, 0, 64, st));
+    }
     RB(cudaGetLastError());
     *launches += 4 + 3 * 5 + 2;
     return true;
@@ -457,6 +579,11 @@ int launch_flag_valid(const DevPsm* psms, uint32_t n, const int32_t* seq_of_form
                       ShuffleTotals* totals /* zeroed by the caller */, cudaStream_t st) {
     if (!n) return 0;
     k7_flag_valid<<<blocks(n), 256, 0, st>>>(psms, n, seq_of_form, seq_flag, form_flag, valid_flag, &totals->n_valid);
+    return 1;
+}
+int launch_valid_flags(const DevPsm* psms, uint32_t n, uint8_t* valid_flag, uint32_t* n_valid /* zeroed by the caller */, cudaStream_t st) {
+    if (!n) return 0;
+    k7_valid_flags<<<blocks(n), 256, 0, st>>>(psms, n, valid_flag, n_valid);
     return 1;
 }
 int launch_shuffle_plans(const uint8_t* seq_flag, const TargetAux& A, int32_t n_random, ShuffleSeq* plans, cudaStream_t st) {

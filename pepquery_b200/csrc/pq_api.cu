@@ -14,6 +14,7 @@
 #include <cub/cub.cuh>
 
 #include "pq_host.h"
+#include "k_cells.cuh"
 
 using namespace pq;
 
@@ -92,6 +93,7 @@ struct pq_ctx {
     DevBuf s_inv;                            // virtual id -> mass-sorted position
     DevBuf gather_list;                      // candidate-first: the resident spectra (sorted positions) in caller order
     DevBuf k0_counters;                      // work hand-out words of the per-chunk K0 launches
+    std::vector<cudaEvent_t> k0_ev;           // K0 of upload chunk c has finished
     DevBuf d_zero;                           // caller indices of the charge-less spectra, ascending
     // tables
     PeptideTable targets, reference;
@@ -120,6 +122,18 @@ struct pq_ctx {
     // shuffles
     DevBuf sh_seqs, sh_forms, sh_raw, sh_kidx, sh_kcnt, sh_rows, sh_pred, sh_lists;
     bool have_lists = false;
+    bool shuffles_all = false; uint64_t shuffles_epoch = 0;      // shuffles exist for EVERY target form of that target list (search at load)
+    // search at load: the parts of the PSM table, the superset reference table, what pq_step2/3/4 may hand back without working
+    struct PartBufs {
+        DevBuf jobs, results, hits, hit_count, psm, seg_start, agg, hits3, valid_flag, list, order, keys, keys2, key_a, key_b, idx_a, idx_b, head, tmp, scal;
+        uint32_t n_psm = 0, n_seg = 0, nh3 = 0; int32_t s_first = 0, s_last = 0;
+    };
+    std::vector<PartBufs> parts;
+    PeptideTable ref_super; uint32_t super_rows = 0; bool super_ready = false;
+    bool pending_step[5] = {false, false, false, false, false};   // [2..4]: results of that step are already in the PSM table
+    bool pending_ref = false;                                      // pq_build_reference(NULL) only has to cut the table out of the superset
+    cudaStream_t st_part = nullptr;
+    DevBuf up_rank, part_first, super_seq;
     DevBuf sh_plans, sh_seq_flag, sh_form_flag, sh_valid_flag, sh_seq_slot, sh_form_slot, sh_row_base, sh_totals, sh_list, sh_order, sh_keys, sh_keys2;
     bool have_shuffles = false;
     // results
@@ -143,6 +157,13 @@ void flush_timers(pq_ctx* c);
 int32_t finalize_targets(pq_ctx* ctx);
 void ensure_forms(pq_ctx* ctx);
 int32_t digest_staged_reference(pq_ctx* ctx, cudaStream_t st, bool count_time = true);
+// What pq_load_spectra hands to search_at_load: the Step-2 jobs its window enumeration left in ctx->jobs, the order the spectra
+// arrive in (gather_list, chunks of chunk_spectra, one K0-done event per chunk) and how many chunks make a part.
+struct LoadPlan {
+    uint32_t n_jobs; unsigned long long cand; uint32_t n_res; uint32_t chunk_spectra; size_t n_chunks; const std::vector<cudaEvent_t>* k0_done;
+};
+
+int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan);
 
 Timer::Timer(pq_ctx* c_, double* t, double* t2) : c(c_), acc(t), acc2(t2) {
     auto get = [&]() { cudaEvent_t e; if (!c->free_events.empty()) { e = c->free_events.back(); c->free_events.pop_back(); } else cudaEventCreate(&e); return e; };
@@ -195,30 +216,41 @@ ScoreConfig score_config(const pq_ctx* c, int check_window) {
     return s;
 }
 
-// run K1 over a job list that already sits in ctx->jobs; fills results (+hits)
-int32_t run_score(pq_ctx* ctx, JobKind kind, uint32_t n_jobs, const int32_t* row_pred, const uint8_t* rows, const double* row_mass,
-                  uint32_t hit_capacity, int check_window) {
-    CU(ctx->results.reserve(std::max<size_t>((size_t)n_jobs * sizeof(JobResult), 64)));
-    CU(ctx->hits.reserve(std::max<size_t>((size_t)hit_capacity * sizeof(Hit), 64)));
-    CU(ctx->hit_count.reserve(64));
-    CU(cudaMemsetAsync(ctx->hit_count.p, 0, 4, ctx->st));
+// where one K1 launch reads its jobs and leaves its results
+struct ScoreIO {
+    cudaStream_t st; const Job* jobs; DevBuf* results; DevBuf* hits; DevBuf* hit_count; uint32_t* job_counter; bool timed;
+};
+// run K1 over a job list; fills results (+hits)
+int32_t run_score_io(pq_ctx* ctx, const ScoreIO& io, JobKind kind, uint32_t n_jobs, const int32_t* row_pred, const uint8_t* rows, const double* row_mass,
+                     uint32_t hit_capacity, int check_window) {
+    CU(io.results->reserve(std::max<size_t>((size_t)n_jobs * sizeof(JobResult), 64)));
+    CU(io.hits->reserve(std::max<size_t>((size_t)hit_capacity * sizeof(Hit), 64)));
+    CU(io.hit_count->reserve(64));
+    CU(cudaMemsetAsync(io.hit_count->p, 0, 4, io.st));
     ScoreLaunch L; memset(&L, 0, sizeof L);
-    L.kind = kind; L.jobs = ctx->jobs.as<Job>(); L.n_jobs = n_jobs;
+    L.kind = kind; L.jobs = io.jobs; L.n_jobs = n_jobs;
     L.blobs = ctx->blobs.as<uint8_t>(); L.blob_off = ctx->blob_off.as<uint64_t>(); L.blob_len = ctx->blob_len.as<uint32_t>();
     L.rows = rows; L.row_mass = row_mass; L.mods = ctx->d_mods.as<ModTable>(); L.n_codes = (uint32_t)ctx->codes.n_codes;
     L.log10_fact = ctx->d_l10.as<double>(); L.ln_fact = ctx->d_lnf.as<double>();
     L.row_pred = row_pred;
-    L.results = ctx->results.as<JobResult>(); L.hits = ctx->hits.as<Hit>(); L.hit_count = ctx->hit_count.as<uint32_t>();
-    L.hit_capacity = hit_capacity; L.max_blob_bytes = ctx->max_blob; L.job_counter = ctx->d_scalars.as<uint32_t>() + 12;
+    L.results = io.results->as<JobResult>(); L.hits = io.hits->as<Hit>(); L.hit_count = io.hit_count->as<uint32_t>();
+    L.hit_capacity = hit_capacity; L.max_blob_bytes = ctx->max_blob; L.job_counter = io.job_counter;
     if (kind == kJobShuffles && ctx->have_lists) { L.sh_forms = ctx->sh_forms.as<ShuffleForm>(); L.form_slot = ctx->sh_form_slot.as<uint32_t>(); L.lists = ctx->sh_lists.as<uint4>(); }
     ScoreConfig cfg = score_config(ctx, check_window);
-    {
-        int si = kind == kJobTargets ? 0 : kind == kJobCompetitors ? 1 : kind == kJobShuffles ? 2 : 3;
+    const int si = kind == kJobTargets ? 0 : kind == kJobCompetitors ? 1 : kind == kJobShuffles ? 2 : 3;
+    if (io.timed) {
         Timer t(ctx, &ctx->cnt.ms_score, &ctx->cnt.ms_score_step[si]);
-        ctx->cnt.score_kernel_launches += (uint64_t)launch_score(L, cfg, ctx->st);
+        ctx->cnt.score_kernel_launches += (uint64_t)launch_score(L, cfg, io.st);
+    } else {
+        ctx->cnt.score_kernel_launches += (uint64_t)launch_score(L, cfg, io.st);
     }
     CU(cudaGetLastError());
     return PQ_OK;
+}
+int32_t run_score(pq_ctx* ctx, JobKind kind, uint32_t n_jobs, const int32_t* row_pred, const uint8_t* rows, const double* row_mass,
+                  uint32_t hit_capacity, int check_window) {
+    ScoreIO io{ctx->st, ctx->jobs.as<Job>(), &ctx->results, &ctx->hits, &ctx->hit_count, ctx->d_scalars.as<uint32_t>() + 12, true};
+    return run_score_io(ctx, io, kind, n_jobs, row_pred, rows, row_mass, hit_capacity, check_window);
 }
 
 template <class T> int32_t scan_exclusive(pq_ctx* ctx, const T* in, T* out, int n) {
@@ -310,7 +342,7 @@ int32_t ensure_host_spectra(pq_ctx* ctx) {
     return PQ_OK;
 }
 
-void reset_psm_state(pq_ctx* ctx) { ctx->n_psm = 0; ctx->n_seg = 0; ctx->nh3 = 0; ctx->comp3_ready = false; ctx->comp3_n = 0; ctx->have_shuffles = false; ctx->psms.clear(); ctx->comp5.clear(); }
+void reset_psm_state(pq_ctx* ctx) { for (bool& b : ctx->pending_step) b = false; ctx->pending_ref = false; ctx->n_psm = 0; ctx->n_seg = 0; ctx->nh3 = 0; ctx->comp3_ready = false; ctx->comp3_n = 0; ctx->have_shuffles = false; ctx->psms.clear(); ctx->comp5.clear(); }
 
 }  // namespace
 
@@ -324,7 +356,7 @@ void pq_default_params(pq_params* p) {
     p->tol = 10.0; p->tol_ppm = 1; p->score_method = 1; p->itol = 0.6; p->min_score = 12.0; p->min_peaks = 10;
     p->n_isotope = 1; p->isotope[0] = 0; p->max_var_mods = 3; p->max_mods_per_aa = 1; p->n_random = 1000;
     p->enzyme = 1; p->max_missed = 2; p->min_len = 7; p->max_len = 45; p->min_mass = 500.0; p->max_mass = 10000.0;
-    p->shuffle_seed = 12457; p->mod_seed = 2022; p->prepare_at_load = 1; p->candidate_first = 1;
+    p->shuffle_seed = 12457; p->mod_seed = 2022; p->prepare_at_load = 1; p->candidate_first = 1; p->search_at_load = 1;
     p->n_fixed = 1; p->fixed[0].id = 1; p->fixed[0].position = PQ_MOD_ANYWHERE; strcpy(p->fixed[0].residues, "C"); p->fixed[0].delta = 57.02146372057;
     p->n_var = 1; p->var[0].id = 2; p->var[0].position = PQ_MOD_ANYWHERE; strcpy(p->var[0].residues, "M"); p->var[0].delta = 15.99491461956;
     p->var[0].neutral_loss = 63.99828574784;
@@ -351,7 +383,8 @@ int32_t pq_create(const pq_params* params, pq_ctx** out) {
     if (!ctx->codes.init(*params, err)) { delete ctx; return fail(nullptr, PQ_ERR_UNSUPPORTED, err); }
     if (cudaSetDevice(params->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->st_aux, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->st_aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->st_part, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx; return fail(nullptr, PQ_ERR_CUDA, "cannot initialise device");
     }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->uev0); cudaEventCreate(&ctx->uev1);
@@ -399,8 +432,10 @@ int32_t pq_destroy(pq_ctx* ctx) {
     if (ctx->uev0) cudaEventDestroy(ctx->uev0);
     if (ctx->uev1) cudaEventDestroy(ctx->uev1);
     for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->k0_ev) cudaEventDestroy(e);
     if (ctx->meta_ev) cudaEventDestroy(ctx->meta_ev);
     cudaStream_t st = ctx->st, st_copy = ctx->st_copy, st_aux = ctx->st_aux;
+    if (ctx->st_part) { cudaStreamSynchronize(ctx->st_part); cudaStreamDestroy(ctx->st_part); }
     delete ctx;
     if (st) cudaStreamDestroy(st);
     if (st_copy) cudaStreamDestroy(st_copy);
@@ -543,6 +578,7 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
     PrepConfig pc; pc.itol = ctx->P.itol; pc.method = ctx->P.score_method;
     pc.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (ctx->P.itol * 2.0));
     bool eager = ctx->P.prepare_at_load != 0 && getenv("PQ_PREPARE_AT_STEP2") == nullptr;
+    bool stream_search = false, searched = false; size_t n_chunks_cf = 0; uint32_t chunk_spectra_cf = 0;
     SpectraView sp = ctx->view();
     if (cf) {
         // ---- candidate-first: target table -> precursor windows -> the spectra worth bringing over ----
@@ -578,10 +614,12 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
             CL(cub::DeviceSelect::Flagged(ctx->scan_tmp.p, tmp, ctx->s_inv.as<int32_t>(), ctx->z_keep.as<uint8_t>(), ctx->gather_list.as<int32_t>(), d_nsel, (int)nv, st));
             k_launch += 6;
         }
+        struct { uint32_t njobs, nsel; unsigned long long cand; } hj = {0, 0, 0};
         CL(cudaMemcpyAsync(&hn.n_res, ctx->prep_id.as<int32_t>() + nv, 4, cudaMemcpyDeviceToHost, st));
         CL(cudaMemcpyAsync(&hn.res_peaks, ctx->s_off.as<uint64_t>() + nv, 8, cudaMemcpyDeviceToHost, st));
+        CL(cudaMemcpyAsync(&hj, ctx->njobs.p, 16, cudaMemcpyDeviceToHost, st));
         CL(cudaStreamSynchronize(st));
-        ctx->cnt.d2h_bytes += 12;
+        ctx->cnt.d2h_bytes += 28;
         mk.mark("target table + windows (waits for the precursor sort)");
         const uint32_t n_res = hn.n_res;
         CL(ctx->s_mz.reserve(std::max<uint64_t>(hn.res_peaks, 1) * 8)); CL(ctx->s_in.reserve(std::max<uint64_t>(hn.res_peaks, 1) * 8));
@@ -612,6 +650,10 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
             CL(ctx->k0_counters.reserve((nck + 1) * 16)); CL(cudaMemsetAsync(ctx->k0_counters.p, 0, (nck + 1) * 16, st));
             CL(cudaEventRecord(ctx->meta_ev, st));
             CL(cudaStreamWaitEvent(sc, ctx->meta_ev, 0));
+            // search while loading?  everything a search needs must be known now, and K0 must run here
+            stream_search = eager && ctx->P.search_at_load != 0 && !getenv("PQ_NO_SEARCH_AT_LOAD") && ctx->ref_staged && n0 == 0 && ctx->P.n_random <= 20000;
+            if (stream_search) while (ctx->k0_ev.size() < nck + 1) { cudaEvent_t e; CL(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->k0_ev.push_back(e); }
+            n_chunks_cf = nck; chunk_spectra_cf = chunk_spectra;
             Timer t(ctx, &ctx->cnt.ms_prepare);
             const bool trace = getenv("PQ_LOAD_TRACE") != nullptr;          // diagnostic: when did every chunk's gather / K0 finish?
             std::vector<cudaEvent_t> tr_g, tr_k; cudaEvent_t tr0 = nullptr;
@@ -627,6 +669,7 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
                 if (eager)          // blob id = rank in mass order (prep_id); one K0 block per SM less than would fit: the next chunk's gather runs beside it
                     k_launch += launch_prepare(sp, ctx->gather_list.as<int32_t>() + a, (int32_t)cnt, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(),
                                                ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st, 0, ctx->prep_id.as<int32_t>(), 1, ctx->k0_counters.as<uint32_t>() + 4 * c);
+                if (stream_search) CL(cudaEventRecord(ctx->k0_ev[c], st));
                 if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tr_k.push_back(e); }
             }
             if (trace) {
@@ -641,6 +684,14 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
             if (eager) { ctx->prepared_at_load = true; ctx->n_prepared = n_res; ctx->cnt.spectra_prepared = n_res; ctx->max_blob = blob_bytes(ctx->max_peaks); }
         }
         mk.mark("gather + K0 queued");
+        if (stream_search && n_res) {
+            // Steps 2-4 part by part while the rest of the spectra are still arriving
+            LoadPlan plan{hj.njobs, hj.cand, n_res, chunk_spectra_cf, n_chunks_cf, &ctx->k0_ev};
+            ctx->cnt.other_kernel_launches += (uint64_t)k_launch; k_launch = 0;
+            rc = search_at_load(ctx, plan);
+            if (rc) return fail_load(rc, ctx->err);
+            searched = true;
+        }
     } else {
         // ---- full upload: every peak, in chunks of whole caller spectra ----
         const uint64_t total_sorted = total + alias_peaks;
@@ -712,7 +763,7 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
     CL(cudaGetLastError());
     // a protein database staged before the spectra (pq_stage_reference): its digest does not depend on them and runs now, on a
     // third stream, beside the work above
-    if (digest_here) {
+    if (digest_here && !searched) {
         if (cf) { std::string err; if (!upload_target_keys_for_reference(ctx->st_aux, ctx->targets.seqs, ctx->reference.dev, err)) return fail_load(PQ_ERR_CUDA, "reference digest: " + err); }
         int32_t rc = digest_staged_reference(ctx, ctx->st_aux); if (rc) return fail_load(rc, ctx->err);
     }
@@ -820,6 +871,7 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     if (!ctx) return PQ_ERR_BAD_ARG;
     if (!ctx->have_targets) return fail(ctx, PQ_ERR_STATE, "pq_set_targets first");
     cudaSetDevice(ctx->P.device);
+    if (ctx->pending_step[2]) { ctx->pending_step[2] = false; if (n_psms) *n_psms = (int64_t)ctx->n_psm; return PQ_OK; }      // searched while the spectra were loaded
     Marks mk("step2");
     int32_t rc = finalize_targets(ctx);
     if (rc) return rc;
@@ -1004,6 +1056,7 @@ int32_t pq_stage_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off,
     cudaSetDevice(ctx->P.device);
     auto t_begin = std::chrono::steady_clock::now();
     ctx->ref_staged = false; ctx->ref_digested = false; ctx->have_reference = false;
+    ctx->pending_ref = false; ctx->pending_step[3] = ctx->pending_step[4] = false; ctx->step_done = std::min(ctx->step_done, 2);      // results of another database
     std::string err;
     if (!upload_proteins_for_reference(ctx->st, n_proteins, off, res, ctx->reference.dev, err)) return fail(ctx, PQ_ERR_CUDA, "reference upload: " + err);
     ctx->cnt.h2d_bytes += (n_proteins ? off[n_proteins] : 0) + ((uint64_t)n_proteins + 1) * 8;
@@ -1017,6 +1070,8 @@ int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off,
     if (ctx->step_done < 2) return fail(ctx, PQ_ERR_STATE, "pq_step2_match_targets first (the reference mass window comes from the matched spectra)");
     const bool use_staged = n_proteins == 0 && !off && !res && ctx->ref_staged;      // the database handed over by pq_stage_reference
     cudaSetDevice(ctx->P.device);
+    if (use_staged && ctx->pending_ref && ctx->have_reference) { ctx->pending_ref = false; return PQ_OK; }      // cut out of the superset table when the spectra were loaded
+    ctx->pending_ref = false; ctx->pending_step[3] = ctx->pending_step[4] = false; ctx->step_done = std::min(ctx->step_done, 2);
     PeptideTable& R = ctx->reference;
     R.seqs.clear(); R.forms.clear(); R.have_mask = false; R.device_built = false; R.materialized = true;
     auto t_begin = std::chrono::steady_clock::now();
@@ -1139,6 +1194,8 @@ int32_t pq_step3_competitors(pq_ctx* ctx) {
     if (!ctx) return PQ_ERR_BAD_ARG;
     if (ctx->step_done < 2 || !ctx->have_reference) return fail(ctx, PQ_ERR_STATE, "pq_step2_match_targets and pq_build_reference first");
     cudaSetDevice(ctx->P.device);
+    if (ctx->pending_step[3]) { ctx->pending_step[3] = false; ctx->step_done = std::max(ctx->step_done, 3); return PQ_OK; }      // searched while the spectra were loaded
+    ctx->pending_step[4] = false; ctx->step_done = std::min(ctx->step_done, 3);
     Marks mk("step3");
     PeptideTable& R = ctx->reference;
     cudaStream_t st = ctx->st;
@@ -1185,33 +1242,45 @@ int32_t pq_step3_competitors(pq_ctx* ctx) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-int32_t pq_step4_shuffles(pq_ctx* ctx) {
-    if (!ctx) return PQ_ERR_BAD_ARG;
-    if (ctx->step_done < 2) return fail(ctx, PQ_ERR_STATE, "pq_step2_match_targets first");
-    cudaSetDevice(ctx->P.device);
-    cudaStream_t st = ctx->st;
-    Marks mk("step4");
-    PeptideTable& T = ctx->targets;
-    ctx->have_shuffles = false;
-    const uint32_t n_psm = ctx->n_psm;
-    if (n_psm == 0) { ctx->step_done = 4; return PQ_OK; }
-    if (ctx->P.n_random > 20000) return fail(ctx, PQ_ERR_UNSUPPORTED, "more than 20000 shuffles per peptide");
+}  // extern "C"
+
+namespace {
+
+template <class K, class V> int32_t sort_pairs_on(pq_ctx* ctx, cudaStream_t st, DevBuf& tmpbuf, const K* kin, K* kout, const V* vin, V* vout, int n, int end_bit) {
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, kin, kout, vin, vout, n, 0, end_bit, st);
+    CU(tmpbuf.reserve(tmp + 64));
+    CU(cub::DeviceRadixSort::SortPairs(tmpbuf.p, tmp, kin, kout, vin, vout, n, 0, end_bit, st));
+    return PQ_OK;
+}
+template <class F> int32_t select_iota_on(pq_ctx* ctx, cudaStream_t st, DevBuf& tmpbuf, const F* flags, uint32_t* out, uint32_t* d_count, int n) {
+    size_t tmp = 0;
+    cub::CountingInputIterator<uint32_t> iota(0);
+    cub::DeviceSelect::Flagged(nullptr, tmp, iota, flags, out, d_count, n, st);
+    CU(tmpbuf.reserve(tmp + 64));
+    CU(cub::DeviceSelect::Flagged(tmpbuf.p, tmp, iota, flags, out, d_count, n, st));
+    return PQ_OK;
+}
+
+// Shuffles (K2) for the sequences / forms flagged in sh_seq_flag / sh_form_flag — or, all = true, for every target form with
+// all three list charges: plans (group order, round count), layout, generation, de-duplication, modification placement, cell
+// lists, MVH predicted-peak counts.  Synchronises st once (sizes).
+int32_t generate_shuffles(pq_ctx* ctx, cudaStream_t st, bool all, ShuffleTotals& tot, bool timed) {
     const TargetAux A = ctx->aux();
     const size_t nseq = A.n_seq, nform = A.n_forms;
-    // StatisticScoreCalc.run (:22-41): sequences with at least one still-valid PSM get shuffles
-    CU(ctx->sh_seq_flag.reserve(nseq + 64)); CU(ctx->sh_form_flag.reserve(nform * 4 + 64)); CU(ctx->sh_valid_flag.reserve((size_t)n_psm + 64));
-    CU(ctx->sh_plans.reserve(nseq * sizeof(ShuffleSeq))); CU(ctx->sh_seqs.reserve(nseq * sizeof(ShuffleSeq))); CU(ctx->sh_forms.reserve(nform * sizeof(ShuffleForm)));
-    CU(ctx->sh_seq_slot.reserve(nseq * 4 + 64)); CU(ctx->sh_form_slot.reserve(nform * 4 + 64)); CU(ctx->sh_row_base.reserve(nform * 4 + 64));
-    CU(ctx->sh_totals.reserve(64)); CU(ctx->sh_kcnt.reserve(nseq * 4 + 64));
-    CU(cudaMemsetAsync(ctx->sh_seq_flag.p, 0, nseq, st)); CU(cudaMemsetAsync(ctx->sh_form_flag.p, 0, nform * 4, st));
-    ShuffleTotals tot; memset(&tot, 0, sizeof tot);
-    {
-        Timer t(ctx, &ctx->cnt.ms_shuffle);
+    if (all) {
+        CU(ctx->sh_seq_flag.reserve(nseq + 64)); CU(ctx->sh_form_flag.reserve(nform * 4 + 64));
+        CU(ctx->sh_plans.reserve(nseq * sizeof(ShuffleSeq))); CU(ctx->sh_seqs.reserve(nseq * sizeof(ShuffleSeq))); CU(ctx->sh_forms.reserve(nform * sizeof(ShuffleForm)));
+        CU(ctx->sh_seq_slot.reserve(nseq * 4 + 64)); CU(ctx->sh_form_slot.reserve(nform * 4 + 64)); CU(ctx->sh_row_base.reserve(nform * 4 + 64));
+        CU(ctx->sh_totals.reserve(64)); CU(ctx->sh_kcnt.reserve(nseq * 4 + 64));
+        launch_fill_u8(ctx->sh_seq_flag.as<uint8_t>(), (uint32_t)nseq, 1, st);
+        launch_fill_u32(ctx->sh_form_flag.as<uint32_t>(), (uint32_t)nform, (uint32_t)kListMaxCharge, st);
         CU(cudaMemsetAsync(ctx->sh_totals.p, 0, sizeof(ShuffleTotals), st));
-        int k = launch_flag_valid(ctx->d_psm.as<DevPsm>(), n_psm, A.seq_of_form, ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint32_t>(), ctx->sh_valid_flag.as<uint8_t>(),
-                                  ctx->sh_totals.as<ShuffleTotals>(), st);
-        k += launch_shuffle_plans(ctx->sh_seq_flag.as<uint8_t>(), A, ctx->P.n_random, ctx->sh_plans.as<ShuffleSeq>(), st);
-        k += launch_shuffle_layout(ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint32_t>(), ctx->sh_valid_flag.as<uint8_t>(), n_psm, ctx->sh_plans.as<ShuffleSeq>(), A,
+    }
+    {
+        cudaEvent_t dummy = nullptr; (void)dummy;
+        int k = launch_shuffle_plans(ctx->sh_seq_flag.as<uint8_t>(), A, ctx->P.n_random, ctx->sh_plans.as<ShuffleSeq>(), st);
+        k += launch_shuffle_layout(ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint32_t>(), nullptr, 0, ctx->sh_plans.as<ShuffleSeq>(), A,
                                    ctx->sh_seq_slot.as<uint32_t>(), ctx->sh_form_slot.as<uint32_t>(), ctx->sh_row_base.as<uint32_t>(), ctx->sh_seqs.as<ShuffleSeq>(),
                                    ctx->sh_forms.as<ShuffleForm>(), ctx->sh_totals.as<ShuffleTotals>(), st);
         ctx->cnt.other_kernel_launches += (uint64_t)k;
@@ -1219,9 +1288,8 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
     CU(cudaMemcpyAsync(&tot, ctx->sh_totals.p, sizeof tot, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     ctx->cnt.d2h_bytes += sizeof tot;
-    mk.mark("shuffle plans + layout");
-    ctx->have_shuffles = true;
-    if (tot.n_seqs == 0 || tot.n_valid == 0) { ctx->step_done = 4; return PQ_OK; }
+    ctx->have_shuffles = true; ctx->have_lists = false;
+    if (tot.n_seqs == 0) return PQ_OK;
     const uint32_t raw_rows = tot.raw_rows, out_rows = tot.out_rows, max_num = (uint32_t)std::max(ctx->P.n_random, 1);
     CU(ctx->sh_raw.reserve((size_t)std::max(raw_rows, 1u) * kRowBytes)); CU(ctx->sh_kidx.reserve((size_t)std::max(raw_rows, 1u) * 4));
     CU(ctx->sh_rows.reserve((size_t)std::max(out_rows, 1u) * kRowBytes));
@@ -1229,43 +1297,309 @@ int32_t pq_step4_shuffles(pq_ctx* ctx) {
     // cell lists of the shuffle rows (k_cells.cuh): only the bounded count pass reads them
     ctx->have_lists = !score_config(ctx, 0).score_all && tot.list_units > 0 && !getenv("PQ_NO_CELL_LISTS");
     if (ctx->have_lists && ctx->sh_lists.reserve((size_t)tot.list_units * 16) != cudaSuccess) { cudaGetLastError(); ctx->have_lists = false; }      // no room: K1 walks the ladders
-    {
-        Timer t(ctx, &ctx->cnt.ms_shuffle);
+    auto launch = [&]() {
         int k = launch_shuffles(ctx->sh_seqs.as<ShuffleSeq>(), tot.n_seqs, ctx->sh_forms.as<ShuffleForm>(), tot.n_forms,
                                 ctx->d_shufmods.as<ShuffleMods>(), ctx->sh_raw.as<uint8_t>(), ctx->sh_kidx.as<uint32_t>(), ctx->sh_kcnt.as<uint32_t>(),
                                 ctx->sh_rows.as<uint8_t>(), max_num, ctx->P.shuffle_seed, ctx->d_mods.as<ModTable>(), ctx->have_lists ? ctx->sh_lists.as<uint4>() : nullptr, st);
         if (ctx->P.score_method == 2) k += launch_predict(ctx->sh_rows.as<uint8_t>(), out_rows, ctx->d_mods.as<ModTable>(), ctx->P.itol, ctx->sh_pred.as<int32_t>(), st);
         ctx->cnt.other_kernel_launches += (uint64_t)k;
-    }
+    };
+    if (timed) { Timer t(ctx, &ctx->cnt.ms_shuffle); launch(); } else launch();
     CU(cudaGetLastError());
-    mk.mark("K2 shuffles (launch)");
-    // one job per valid PSM (StatisticScoreWorker), ordered by form so consecutive CTAs share shuffle rows in L2
-    const uint32_t n_valid = tot.n_valid;
-    CU(ctx->sh_list.reserve((size_t)n_valid * 4 + 64)); CU(ctx->sh_order.reserve((size_t)n_valid * 4 + 64));
-    CU(ctx->sh_keys.reserve((size_t)n_valid * 4 + 64)); CU(ctx->sh_keys2.reserve((size_t)n_valid * 4 + 64));
-    {
-        size_t tmp = 0;
-        cub::CountingInputIterator<uint32_t> iota(0);
-        uint32_t* d_cnt = ctx->d_scalars.as<uint32_t>() + 4;
-        cub::DeviceSelect::Flagged(nullptr, tmp, iota, ctx->sh_valid_flag.as<uint8_t>(), ctx->sh_list.as<uint32_t>(), d_cnt, (int)n_psm, st);
-        CU(ctx->scan_tmp.reserve(tmp + 64));
-        CU(cub::DeviceSelect::Flagged(ctx->scan_tmp.p, tmp, iota, ctx->sh_valid_flag.as<uint8_t>(), ctx->sh_list.as<uint32_t>(), d_cnt, (int)n_psm, st));
-    }
-    int k = launch_psm_form_keys(ctx->d_psm.as<DevPsm>(), ctx->sh_list.as<uint32_t>(), n_valid, ctx->sh_keys.as<uint32_t>(), st);
-    int32_t rc = sort_pairs(ctx, ctx->sh_keys.as<uint32_t>(), ctx->sh_keys2.as<uint32_t>(), ctx->sh_list.as<uint32_t>(), ctx->sh_order.as<uint32_t>(), (int)n_valid, 32);
+    return PQ_OK;
+}
+
+// Step-4 scoring of the still-valid PSMs of one PSM table (or part of one): one job per valid PSM (StatisticScoreWorker), ordered by
+// form so consecutive CTAs share shuffle rows in L2; K1 over the shuffle rows; p-values into the table.  Nothing is synchronised.
+struct Step4Work { DevBuf *valid_flag, *list, *order, *keys, *keys2, *jobs, *results, *hits, *hit_count, *tmp; uint32_t* d_cnt; uint32_t* job_counter; };
+int32_t step4_score(pq_ctx* ctx, cudaStream_t st, DevPsm* psms, uint32_t n_psm, uint32_t n_valid, const Step4Work& W, bool timed) {
+    if (!n_valid) return PQ_OK;
+    CU(W.list->reserve((size_t)n_valid * 4 + 64)); CU(W.order->reserve((size_t)n_valid * 4 + 64));
+    CU(W.keys->reserve((size_t)n_valid * 4 + 64)); CU(W.keys2->reserve((size_t)n_valid * 4 + 64));
+    int32_t rc = select_iota_on(ctx, st, *W.tmp, W.valid_flag->as<uint8_t>(), W.list->as<uint32_t>(), W.d_cnt, (int)n_psm);
     if (rc) return rc;
-    CU(ctx->jobs.reserve((size_t)n_valid * sizeof(Job)));
-    k += launch_step4_jobs(ctx->d_psm.as<DevPsm>(), ctx->sh_order.as<uint32_t>(), n_valid, ctx->sh_form_slot.as<uint32_t>(), ctx->sh_forms.as<ShuffleForm>(),
-                           ctx->sh_kcnt.as<uint32_t>(), ctx->jobs.as<Job>(), st);
+    int k = launch_psm_form_keys(psms, W.list->as<uint32_t>(), n_valid, W.keys->as<uint32_t>(), st);
+    rc = sort_pairs_on(ctx, st, *W.tmp, W.keys->as<uint32_t>(), W.keys2->as<uint32_t>(), W.list->as<uint32_t>(), W.order->as<uint32_t>(), (int)n_valid, 32);
+    if (rc) return rc;
+    CU(W.jobs->reserve((size_t)n_valid * sizeof(Job)));
+    k += launch_step4_jobs(psms, W.order->as<uint32_t>(), n_valid, ctx->sh_form_slot.as<uint32_t>(), ctx->sh_forms.as<ShuffleForm>(),
+                           ctx->sh_kcnt.as<uint32_t>(), W.jobs->as<Job>(), st);
     ctx->cnt.other_kernel_launches += (uint64_t)k + 4;
-    rc = run_score(ctx, kJobShuffles, n_valid, ctx->sh_pred.as<int32_t>(), ctx->sh_rows.as<uint8_t>(), nullptr, 1, 0);
+    ScoreIO io{st, W.jobs->as<Job>(), W.results, W.hits, W.hit_count, W.job_counter, timed};
+    rc = run_score_io(ctx, io, kJobShuffles, n_valid, ctx->sh_pred.as<int32_t>(), ctx->sh_rows.as<uint8_t>(), nullptr, 1, 0);
     if (rc) return rc;
-    k = launch_job_counters(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), n_valid, ctx->s_npeaks.as<uint32_t>(), 2, ctx->d_counters.as<DevCounters>(), st);
-    k += launch_step4_apply(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), ctx->sh_order.as<uint32_t>(), n_valid, ctx->d_psm.as<DevPsm>(), st);
+    k = launch_job_counters(W.jobs->as<Job>(), W.results->as<JobResult>(), n_valid, ctx->s_npeaks.as<uint32_t>(), 2, ctx->d_counters.as<DevCounters>(), st);
+    k += launch_step4_apply(W.jobs->as<Job>(), W.results->as<JobResult>(), W.order->as<uint32_t>(), n_valid, psms, st);
     ctx->cnt.other_kernel_launches += (uint64_t)k;
     CU(cudaGetLastError());
+    return PQ_OK;
+}
+
+// Steps 2-4 while the spectra are still arriving (pq_params.search_at_load).  The resident spectra are cut into parts in arrival
+// order; as soon as K0 has prepared a part, its Step 2 (targets), Step 3 (competitors from a reference table built for the mass
+// range of ALL resident spectra, a superset of the final one) and Step 4 (shuffles generated up front for every target form) run
+// on a stream of their own, beside the gather and K0 of the later parts.  The parts' PSM tables are then concatenated, the
+// reference table cut down to the mass window of the matched spectra (GeneratePeptideformWorker.java:40-52) and the row numbers
+// shifted accordingly: the context ends up exactly as after pq_step2 .. pq_step4 called one by one.
+int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan) {
+    Marks mk("search_at_load");
+    cudaStream_t sa = ctx->st_aux, sp_ = ctx->st_part;
+    PeptideTable& T = ctx->targets; PeptideTable& R = ctx->reference; PeptideTable& S = ctx->ref_super;
+    const int64_t nv = ctx->nS;
+    SpectraView sp = ctx->view();
+    // ---- reference: digest (if not done), superset expansion over the resident mass range ----
+    if (!ctx->ref_digested) {
+        std::string err;
+        if (!upload_target_keys_for_reference(sa, ctx->targets.seqs, R.dev, err)) return fail(ctx, PQ_ERR_CUDA, "reference digest: " + err);
+        int32_t rc = digest_staged_reference(ctx, sa); if (rc) return rc;
+    }
+    mk.mark("digest");
+    {
+        int32_t s_lo = 0, s_hi = 0; double m_lo = 0, m_hi = 0;
+        CU(cudaMemcpyAsync(&s_lo, ctx->prep_list.as<int32_t>(), 4, cudaMemcpyDeviceToHost, sa));
+        CU(cudaMemcpyAsync(&s_hi, ctx->prep_list.as<int32_t>() + (plan.n_res - 1), 4, cudaMemcpyDeviceToHost, sa));
+        CU(cudaStreamSynchronize(sa));
+        CU(cudaMemcpyAsync(&m_lo, ctx->s_mass.as<double>() + s_lo, 8, cudaMemcpyDeviceToHost, sa));
+        CU(cudaMemcpyAsync(&m_hi, ctx->s_mass.as<double>() + s_hi, 8, cudaMemcpyDeviceToHost, sa));
+        CU(cudaStreamSynchronize(sa));
+        std::string err; uint64_t launches = 0;
+        R.dev.rows = &S.rows; R.dev.mass = &S.mass;
+        std::swap(R.dev.seq_id, ctx->super_seq);
+        const bool ok = expand_reference_on_device(sa, ctx->P, ctx->codes, m_lo - 250.0 - 5.0, m_hi + 250.0 + 5.0, R.dev, &launches, err);
+        std::swap(R.dev.seq_id, ctx->super_seq);
+        R.dev.rows = &R.rows; R.dev.mass = &R.mass;
+        if (!ok) return fail(ctx, PQ_ERR_CUDA, "reference build: " + err);
+        ctx->cnt.other_kernel_launches += launches;
+        ctx->super_rows = R.dev.n_forms; R.dev.n_forms = 0;
+        if (ctx->P.score_method == 2 && ctx->super_rows) {
+            CU(S.pred.reserve((size_t)ctx->super_rows * 8));
+            ctx->cnt.other_kernel_launches += (uint64_t)launch_predict(S.rows.as<uint8_t>(), ctx->super_rows, ctx->d_mods.as<ModTable>(), ctx->P.itol, S.pred.as<int32_t>(), sa);
+        }
+    }
+    mk.mark("superset reference");
+    // ---- shuffles for every target form ----
+    if (!(ctx->shuffles_all && ctx->shuffles_epoch == ctx->targets_epoch && ctx->have_shuffles)) {
+        if (ctx->P.n_random > 20000) return fail(ctx, PQ_ERR_UNSUPPORTED, "more than 20000 shuffles per peptide");
+        ShuffleTotals tot; memset(&tot, 0, sizeof tot);
+        int32_t rc = generate_shuffles(ctx, sa, true, tot, false);
+        if (rc) return rc;
+        ctx->shuffles_all = true; ctx->shuffles_epoch = ctx->targets_epoch;
+    }
+    CU(cudaStreamSynchronize(sa));
+    mk.mark("shuffles for all forms");
+    // ---- the Step-2 jobs by part ----
+    const uint32_t n_jobs = plan.n_jobs;
+    const uint32_t chunks_per_part = 4;
+    const uint32_t part_spectra = plan.chunk_spectra * chunks_per_part;
+    const uint32_t n_parts = (plan.n_res + part_spectra - 1) / part_spectra;
+    if (ctx->parts.size() < n_parts) ctx->parts.resize(n_parts);
+    std::vector<uint32_t> first(n_parts + 1, 0); std::vector<unsigned long long> pcand(n_parts, 0);
+    if (n_jobs) {
+        CU(ctx->up_rank.reserve((size_t)nv * 4 + 64)); CU(ctx->part_first.reserve(((size_t)n_parts + 2) * 16));
+        CU(ctx->k_key_a.reserve((size_t)n_jobs * 8)); CU(ctx->k_key_b.reserve((size_t)n_jobs * 8)); CU(ctx->k_idx_a.reserve((size_t)n_jobs * 4)); CU(ctx->k_idx_b.reserve((size_t)n_jobs * 4));
+        CU(ctx->jobs2.reserve((size_t)n_jobs * sizeof(Job)));
+        int k = launch_scatter_rank(ctx->gather_list.as<int32_t>(), plan.n_res, ctx->up_rank.as<uint32_t>(), sp_);
+        k += launch_fix_job_blobs(ctx->jobs.as<Job>(), n_jobs, ctx->prep_id.as<int32_t>(), sp_);
+        k += launch_part_job_keys(ctx->jobs.as<Job>(), n_jobs, ctx->up_rank.as<uint32_t>(), part_spectra, ctx->k_key_a.as<uint64_t>(), ctx->k_idx_a.as<uint32_t>(), sp_);
+        int32_t rc = sort_pairs_on(ctx, sp_, ctx->scan_tmp, ctx->k_key_a.as<uint64_t>(), ctx->k_key_b.as<uint64_t>(), ctx->k_idx_a.as<uint32_t>(), ctx->k_idx_b.as<uint32_t>(), (int)n_jobs, 64);
+        if (rc) return rc;
+        k += launch_gather_jobs(ctx->jobs.as<Job>(), ctx->k_idx_b.as<uint32_t>(), n_jobs, ctx->jobs2.as<Job>(), sp_);
+        std::swap(ctx->jobs, ctx->jobs2);
+        uint32_t* d_first = ctx->part_first.as<uint32_t>();
+        unsigned long long* d_pc = reinterpret_cast<unsigned long long*>(ctx->part_first.as<uint8_t>() + ((size_t)n_parts + 2) * 8);
+        CU(cudaMemsetAsync(d_pc, 0, (size_t)n_parts * 8, sp_));
+        k += launch_part_bounds(ctx->k_key_b.as<uint64_t>(), n_jobs, n_parts, d_first, sp_);
+        k += launch_part_cand(ctx->jobs.as<Job>(), n_jobs, ctx->k_key_b.as<uint64_t>(), d_pc, sp_);
+        CU(cudaMemcpyAsync(first.data(), d_first, ((size_t)n_parts + 1) * 4, cudaMemcpyDeviceToHost, sp_));
+        CU(cudaMemcpyAsync(pcand.data(), d_pc, (size_t)n_parts * 8, cudaMemcpyDeviceToHost, sp_));
+        CU(cudaStreamSynchronize(sp_));
+        ctx->cnt.other_kernel_launches += (uint64_t)k + 3;
+    }
+    mk.mark("jobs by part");
+    WindowConfig W; W.tol = ctx->P.tol; W.tol_ppm = ctx->P.tol_ppm; W.n_isotope = ctx->P.n_isotope; W.min_peaks = ctx->P.min_peaks;
+    for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) W.isotope[i] = ctx->P.isotope[i];
+    const TargetAux A = ctx->aux();
+    uint64_t N = 0, NS = 0, NH3 = 0;
+    for (uint32_t p = 0; p < n_parts; ++p) {
+        pq_ctx::PartBufs& B = ctx->parts[p];
+        B.n_psm = 0; B.n_seg = 0; B.nh3 = 0;
+        const uint32_t j0 = first[p], nj = first[p + 1] - first[p];
+        // the part is complete when K0 has finished its last chunk
+        const size_t last_chunk = std::min<size_t>((size_t)(p + 1) * chunks_per_part, plan.n_chunks) - 1;
+        CU(cudaStreamWaitEvent(sp_, (*plan.k0_done)[last_chunk], 0));
+        if (!nj) continue;
+        if (pcand[p] > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-2 candidates for one launch");
+        CU(B.scal.reserve(256));
+        CU(cudaMemsetAsync(B.scal.p, 0, 256, sp_));
+        uint32_t* scal = B.scal.as<uint32_t>();
+        // ---- Step 2 ----
+        ScoreIO io2{sp_, ctx->jobs.as<Job>() + j0, &B.results, &B.hits, &B.hit_count, scal + 12, false};
+        int32_t rc = run_score_io(ctx, io2, kJobTargets, nj, T.pred.as<int32_t>(), T.rows.as<uint8_t>(), T.mass.as<double>(), (uint32_t)std::max<unsigned long long>(pcand[p], 1), 1);
+        if (rc) return rc;
+        uint32_t nh = 0;
+        CU(cudaMemcpyAsync(&nh, B.hit_count.p, 4, cudaMemcpyDeviceToHost, sp_));
+        CU(cudaStreamSynchronize(sp_));
+        ctx->cnt.other_kernel_launches += (uint64_t)launch_job_counters(ctx->jobs.as<Job>() + j0, B.results.as<JobResult>(), nj, sp.npeaks, 0, ctx->d_counters.as<DevCounters>(), sp_);
+        if (!nh) continue;
+        CU(B.psm.reserve((size_t)nh * sizeof(DevPsm))); CU(B.seg_start.reserve(((size_t)nh + 2) * 4));
+        {
+            std::string err; int launches = 0;
+            if (!psm_table_from_hits(B.hits.as<Hit>(), nh, sp, T.mass.as<double>(), T.rows.as<uint8_t>(), A, B.key_a, B.key_b, B.idx_a, B.idx_b, B.head, B.tmp,
+                                     B.psm.as<DevPsm>(), B.seg_start.as<uint32_t>(), scal, nullptr, sp_, &launches, err))
+                return fail(ctx, PQ_ERR_CUDA, "psm table: " + err);
+            ctx->cnt.other_kernel_launches += (uint64_t)launches;
+        }
+        uint32_t nseg = 0;
+        CU(cudaMemcpyAsync(&nseg, scal, 4, cudaMemcpyDeviceToHost, sp_));
+        CU(cudaMemcpyAsync(&B.s_first, &B.psm.as<DevPsm>()[0].spectrum_sorted, 4, cudaMemcpyDeviceToHost, sp_));
+        CU(cudaMemcpyAsync(&B.s_last, &B.psm.as<DevPsm>()[nh - 1].spectrum_sorted, 4, cudaMemcpyDeviceToHost, sp_));
+        CU(cudaStreamSynchronize(sp_));
+        B.n_psm = nh; B.n_seg = nseg;
+        // ---- Step 3 (superset table) ----
+        CU(B.agg.reserve((size_t)nseg * sizeof(SegAgg)));
+        if (ctx->super_rows == 0) {
+            CU(cudaMemsetAsync(B.agg.p, 0, (size_t)nseg * sizeof(SegAgg), sp_));
+        } else {
+            const uint32_t nj3 = nseg * (uint32_t)ctx->P.n_isotope;
+            CU(B.jobs.reserve((size_t)nj3 * sizeof(Job)));
+            unsigned long long* d_total = reinterpret_cast<unsigned long long*>(scal + 16);
+            ctx->cnt.other_kernel_launches += (uint64_t)launch_step3_jobs(B.psm.as<DevPsm>(), B.seg_start.as<uint32_t>(), nseg, S.mass.as<double>(), ctx->super_rows, W,
+                                                                          ctx->s_mass.as<double>(), B.jobs.as<Job>(), B.agg.as<SegAgg>(), d_total, sp_);
+            unsigned long long cand3 = 0;
+            CU(cudaMemcpyAsync(&cand3, d_total, 8, cudaMemcpyDeviceToHost, sp_));
+            CU(cudaStreamSynchronize(sp_));
+            if (cand3 > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-3 candidates for one launch");
+            ScoreIO io3{sp_, B.jobs.as<Job>(), &B.results, &B.hits, &B.hit_count, scal + 12, false};
+            rc = run_score_io(ctx, io3, kJobCompetitors, nj3, S.pred.as<int32_t>(), S.rows.as<uint8_t>(), S.mass.as<double>(), (uint32_t)std::max<unsigned long long>(cand3, 1), 1);
+            if (rc) return rc;
+            int k = launch_job_counters(B.jobs.as<Job>(), B.results.as<JobResult>(), nj3, sp.npeaks, 1, ctx->d_counters.as<DevCounters>(), sp_);
+            k += launch_step3_aggregate(B.results.as<JobResult>(), nseg, ctx->P.n_isotope, B.seg_start.as<uint32_t>(), B.psm.as<DevPsm>(), B.agg.as<SegAgg>(), sp_);
+            ctx->cnt.other_kernel_launches += (uint64_t)k;
+            uint32_t nh3 = 0;
+            CU(cudaMemcpyAsync(&nh3, B.hit_count.p, 4, cudaMemcpyDeviceToHost, sp_));
+            CU(cudaStreamSynchronize(sp_));
+            if (nh3) { CU(B.hits3.reserve((size_t)nh3 * sizeof(Hit))); CU(cudaMemcpyAsync(B.hits3.p, B.hits.p, (size_t)nh3 * sizeof(Hit), cudaMemcpyDeviceToDevice, sp_)); }
+            B.nh3 = nh3;
+        }
+        // ---- Step 4 ----
+        CU(B.valid_flag.reserve((size_t)nh + 64));
+        ctx->cnt.other_kernel_launches += (uint64_t)launch_valid_flags(B.psm.as<DevPsm>(), nh, B.valid_flag.as<uint8_t>(), scal + 5, sp_);
+        uint32_t n_valid = 0;
+        CU(cudaMemcpyAsync(&n_valid, scal + 5, 4, cudaMemcpyDeviceToHost, sp_));
+        CU(cudaStreamSynchronize(sp_));
+        Step4Work W4{&B.valid_flag, &B.list, &B.order, &B.keys, &B.keys2, &B.jobs, &B.results, &B.hits, &B.hit_count, &B.tmp, scal + 4, scal + 12};
+        rc = step4_score(ctx, sp_, B.psm.as<DevPsm>(), nh, n_valid, W4, false);
+        if (rc) return rc;
+        N += nh; NS += nseg; NH3 += B.nh3;
+    }
+    mk.mark("parts queued");
+    // ---- merge ----
+    ctx->n_psm = 0; ctx->n_seg = 0; ctx->nh3 = 0; ctx->comp3_ready = false; ctx->comp3_n = 0;
+    R.seqs.clear(); R.forms.clear(); R.have_mask = false; R.device_built = true; R.materialized = false; R.h_mass.clear(); R.n_rows = 0;
+    if (N) {
+        CU(ctx->d_psm.reserve((size_t)N * sizeof(DevPsm))); CU(ctx->d_seg_start.reserve(((size_t)NS + 2) * 4)); CU(ctx->d_out_perm.reserve((size_t)N * 4));
+        CU(ctx->d_agg.reserve((size_t)NS * sizeof(SegAgg))); CU(ctx->hits3.reserve(std::max<size_t>((size_t)NH3, 1) * sizeof(Hit)));
+        // mass window of the matched spectra -> rows [a, b) of the superset are the reference table
+        int32_t s_first = 0x7fffffff, s_last = -1;
+        for (uint32_t p = 0; p < n_parts; ++p) if (ctx->parts[p].n_psm) { s_first = std::min(s_first, ctx->parts[p].s_first); s_last = std::max(s_last, ctx->parts[p].s_last); }
+        CU(cudaMemcpyAsync(&ctx->psm_mass_lo, ctx->s_mass.as<double>() + s_first, 8, cudaMemcpyDeviceToHost, sp_));
+        CU(cudaMemcpyAsync(&ctx->psm_mass_hi, ctx->s_mass.as<double>() + s_last, 8, cudaMemcpyDeviceToHost, sp_));
+        CU(cudaStreamSynchronize(sp_));
+        uint32_t ab[2] = {0, 0};
+        if (ctx->super_rows) {
+            uint32_t* d_ab = ctx->part_first.as<uint32_t>();
+            launch_window_rows(S.mass.as<double>(), ctx->super_rows, ctx->psm_mass_lo - 250.0 - 5.0, ctx->psm_mass_hi + 250.0 + 5.0, d_ab, sp_);
+            CU(cudaMemcpyAsync(ab, d_ab, 8, cudaMemcpyDeviceToHost, sp_));
+            CU(cudaStreamSynchronize(sp_));
+        }
+        const uint32_t a = ab[0], nr = ab[1] - ab[0];
+        if (nr) {
+            CU(R.rows.reserve((size_t)nr * kRowBytes)); CU(R.mass.reserve((size_t)nr * 8)); CU(R.dev.seq_id.reserve((size_t)nr * 4));
+            CU(cudaMemcpyAsync(R.rows.p, S.rows.as<uint8_t>() + (size_t)a * kRowBytes, (size_t)nr * kRowBytes, cudaMemcpyDeviceToDevice, sp_));
+            CU(cudaMemcpyAsync(R.mass.p, S.mass.as<double>() + a, (size_t)nr * 8, cudaMemcpyDeviceToDevice, sp_));
+            CU(cudaMemcpyAsync(R.dev.seq_id.p, ctx->super_seq.as<uint32_t>() + a, (size_t)nr * 4, cudaMemcpyDeviceToDevice, sp_));
+            if (ctx->P.score_method == 2) { CU(R.pred.reserve((size_t)nr * 8)); CU(cudaMemcpyAsync(R.pred.p, S.pred.as<int32_t>() + 2 * (size_t)a, (size_t)nr * 8, cudaMemcpyDeviceToDevice, sp_)); }
+        }
+        R.n_rows = nr; R.dev.n_forms = nr;
+        uint32_t psm_off = 0, seg_off = 0, h3_off = 0; int k = 0;
+        for (uint32_t p = 0; p < n_parts; ++p) {
+            pq_ctx::PartBufs& B = ctx->parts[p];
+            if (!B.n_psm) continue;
+            const bool last = psm_off + B.n_psm == N;
+            k += launch_merge_psms(B.psm.as<DevPsm>(), B.n_psm, seg_off, ctx->d_psm.as<DevPsm>() + psm_off, sp_);
+            k += launch_merge_segs(B.seg_start.as<uint32_t>(), B.agg.as<SegAgg>(), B.n_seg, psm_off, a, ctx->d_seg_start.as<uint32_t>() + seg_off, ctx->d_agg.as<SegAgg>() + seg_off,
+                                   (uint32_t)N, last ? 1 : 0, sp_);
+            k += launch_merge_hits(B.hits3.as<Hit>(), B.nh3, a, ctx->hits3.as<Hit>() + h3_off, sp_);
+            psm_off += B.n_psm; seg_off += B.n_seg; h3_off += B.nh3;
+        }
+        std::string err;
+        if (!build_out_perm(ctx->d_psm.as<DevPsm>(), (uint32_t)N, ctx->k_key_a, ctx->k_key_b, ctx->k_idx_a, ctx->scan_tmp, ctx->d_out_perm.as<uint32_t>(), sp_, err))
+            return fail(ctx, PQ_ERR_CUDA, "psm table: " + err);
+        ctx->cnt.other_kernel_launches += (uint64_t)k + 6;
+        ctx->n_psm = (uint32_t)N; ctx->n_seg = (uint32_t)NS; ctx->nh3 = (uint32_t)NH3;
+    }
+    CU(cudaStreamSynchronize(sp_));
+    ctx->cnt.psms = ctx->n_psm;
+    ctx->cnt.reference_sequences = R.dev.n_unique; ctx->cnt.reference_forms = R.n_rows;
+    ctx->have_reference = true; ctx->have_shuffles = true;
+    ctx->step_done = 4;
+    ctx->pending_step[2] = ctx->pending_step[3] = ctx->pending_step[4] = true; ctx->pending_ref = true;
+    mk.mark("merge");
+    return PQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t pq_step4_shuffles(pq_ctx* ctx) {
+    if (!ctx) return PQ_ERR_BAD_ARG;
+    if (ctx->step_done < 2) return fail(ctx, PQ_ERR_STATE, "pq_step2_match_targets first");
+    cudaSetDevice(ctx->P.device);
+    if (ctx->pending_step[4]) { ctx->pending_step[4] = false; ctx->step_done = 4; return PQ_OK; }     // searched while the spectra were loaded
+    cudaStream_t st = ctx->st;
+    Marks mk("step4");
+    const uint32_t n_psm = ctx->n_psm;
+    if (n_psm == 0) { ctx->step_done = 4; return PQ_OK; }
+    if (ctx->P.n_random > 20000) return fail(ctx, PQ_ERR_UNSUPPORTED, "more than 20000 shuffles per peptide");
+    const TargetAux A = ctx->aux();
+    const size_t nseq = A.n_seq, nform = A.n_forms;
+    const bool pre = ctx->shuffles_all && ctx->shuffles_epoch == ctx->targets_epoch && ctx->have_shuffles;      // generated for every form already
+    CU(ctx->sh_valid_flag.reserve((size_t)n_psm + 64)); CU(ctx->sh_totals.reserve(64));
+    ShuffleTotals tot; memset(&tot, 0, sizeof tot);
+    uint32_t n_valid = 0;
+    if (!pre) {
+        // StatisticScoreCalc.run (:22-41): sequences with at least one still-valid PSM get shuffles
+        ctx->have_shuffles = false; ctx->shuffles_all = false;
+        CU(ctx->sh_seq_flag.reserve(nseq + 64)); CU(ctx->sh_form_flag.reserve(nform * 4 + 64));
+        CU(ctx->sh_plans.reserve(nseq * sizeof(ShuffleSeq))); CU(ctx->sh_seqs.reserve(nseq * sizeof(ShuffleSeq))); CU(ctx->sh_forms.reserve(nform * sizeof(ShuffleForm)));
+        CU(ctx->sh_seq_slot.reserve(nseq * 4 + 64)); CU(ctx->sh_form_slot.reserve(nform * 4 + 64)); CU(ctx->sh_row_base.reserve(nform * 4 + 64));
+        CU(ctx->sh_kcnt.reserve(nseq * 4 + 64));
+        CU(cudaMemsetAsync(ctx->sh_seq_flag.p, 0, nseq, st)); CU(cudaMemsetAsync(ctx->sh_form_flag.p, 0, nform * 4, st));
+        CU(cudaMemsetAsync(ctx->sh_totals.p, 0, sizeof(ShuffleTotals), st));
+        {
+            Timer t(ctx, &ctx->cnt.ms_shuffle);
+            ctx->cnt.other_kernel_launches += (uint64_t)launch_flag_valid(ctx->d_psm.as<DevPsm>(), n_psm, A.seq_of_form, ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint32_t>(),
+                                                                          ctx->sh_valid_flag.as<uint8_t>(), ctx->sh_totals.as<ShuffleTotals>(), st);
+        }
+        int32_t rc = generate_shuffles(ctx, st, false, tot, true);
+        if (rc) return rc;
+        n_valid = tot.n_valid;
+        mk.mark("shuffle plans + layout + K2 (launch)");
+        if (tot.n_seqs == 0 || n_valid == 0) { ctx->step_done = 4; return PQ_OK; }
+    } else {
+        uint32_t* d_nv = ctx->d_scalars.as<uint32_t>() + 5;
+        CU(cudaMemsetAsync(d_nv, 0, 4, st));
+        ctx->cnt.other_kernel_launches += (uint64_t)launch_valid_flags(ctx->d_psm.as<DevPsm>(), n_psm, ctx->sh_valid_flag.as<uint8_t>(), d_nv, st);
+        CU(cudaMemcpyAsync(&n_valid, d_nv, 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (n_valid == 0) { ctx->step_done = 4; return PQ_OK; }
+    }
+    Step4Work W{&ctx->sh_valid_flag, &ctx->sh_list, &ctx->sh_order, &ctx->sh_keys, &ctx->sh_keys2, &ctx->jobs, &ctx->results, &ctx->hits, &ctx->hit_count, &ctx->scan_tmp,
+                ctx->d_scalars.as<uint32_t>() + 4, ctx->d_scalars.as<uint32_t>() + 12};
+    int32_t rc = step4_score(ctx, st, ctx->d_psm.as<DevPsm>(), n_psm, n_valid, W, true);
+    if (rc) return rc;
     mk.mark("jobs + score (launch)");
-    (void)T;
     CU(cudaStreamSynchronize(st));            // synchronous at return (header contract): a kernel fault surfaces here, not in a later call
     mk.mark("wait");
     ctx->step_done = 4;

@@ -237,6 +237,19 @@ struct TargetAux {              // per-target-table device arrays
 bool psm_table_from_hits(const Hit* hits, uint32_t nh, const SpectraView& sp, const double* t_mass, const uint8_t* t_rows, const TargetAux& A,
                          DevBuf& key_a, DevBuf& key_b, DevBuf& idx_a, DevBuf& idx_b, DevBuf& head, DevBuf& tmp,
                          DevPsm* psms, uint32_t* seg_start, uint32_t* d_nseg, uint32_t* out_perm, cudaStream_t st, int* launches, std::string& err);
+// merging the parts of a search that ran during the upload (search_at_load)
+int launch_merge_psms(const DevPsm* in, uint32_t n, uint32_t seg_off, DevPsm* out, cudaStream_t st);
+int launch_merge_segs(const uint32_t* seg_start_in, const SegAgg* agg_in, uint32_t n_seg, uint32_t psm_off, uint32_t row_off, uint32_t* seg_start_out, SegAgg* agg_out,
+                      uint32_t end_value, int last, cudaStream_t st);
+int launch_merge_hits(const Hit* in, uint32_t n, uint32_t row_off, Hit* out, cudaStream_t st);
+int launch_part_job_keys(const Job* jobs, uint32_t n, const uint32_t* rank_in_upload, uint32_t part_spectra, uint64_t* key, uint32_t* idx, cudaStream_t st);
+int launch_part_bounds(const uint64_t* sorted_key, uint32_t n, uint32_t n_parts, uint32_t* first, cudaStream_t st);
+int launch_part_cand(const Job* jobs, uint32_t n, const uint64_t* sorted_key, unsigned long long* cand, cudaStream_t st);
+int launch_window_rows(const double* mass, uint32_t n, double lo, double hi, uint32_t* ab, cudaStream_t st);
+int launch_scatter_rank(const int32_t* list, uint32_t n, uint32_t* rank, cudaStream_t st);
+int launch_fill_u8(uint8_t* p, uint32_t n, uint8_t v, cudaStream_t st);
+int launch_fill_u32(uint32_t* p, uint32_t n, uint32_t v, cudaStream_t st);
+bool build_out_perm(const DevPsm* psms, uint32_t n, DevBuf& key_a, DevBuf& key_b, DevBuf& idx_a, DevBuf& tmp, uint32_t* out_perm, cudaStream_t st, std::string& err);
 int launch_job_counters(const Job* jobs, const JobResult* res, uint32_t n_jobs, const uint32_t* sp_npeaks, int which, DevCounters* c, cudaStream_t st,
                         const uint8_t* skip_job = nullptr);
 int launch_step3_jobs(const DevPsm* psms, const uint32_t* seg_start, uint32_t n_seg, const double* r_mass, uint32_t n_rows, const WindowConfig& W,
@@ -247,6 +260,7 @@ int launch_comp3_rows(const Hit* hits, uint32_t nh, const SegAgg* agg, uint32_t 
 int launch_gather_comp(const pq_competitor* in, const uint32_t* idx, uint32_t n, pq_competitor* out, cudaStream_t st);
 int launch_flag_valid(const DevPsm* psms, uint32_t n, const int32_t* seq_of_form, uint8_t* seq_flag, uint32_t* form_flag /* largest fragment-charge count of a valid PSM, 0 = none */,
                       uint8_t* valid_flag, ShuffleTotals* totals /* zeroed by the caller */, cudaStream_t st);
+int launch_valid_flags(const DevPsm* psms, uint32_t n, uint8_t* valid_flag, uint32_t* n_valid /* zeroed by the caller */, cudaStream_t st);
 int launch_shuffle_plans(const uint8_t* seq_flag, const TargetAux& A, int32_t n_random, ShuffleSeq* plans, cudaStream_t st);
 int launch_shuffle_layout(const uint8_t* seq_flag, const uint32_t* form_flag, const uint8_t* valid_flag, uint32_t n_psm, const ShuffleSeq* plans, const TargetAux& A,
                           uint32_t* seq_slot, uint32_t* form_slot, uint32_t* row_base, ShuffleSeq* seqs, ShuffleForm* forms, ShuffleTotals* totals, cudaStream_t st);

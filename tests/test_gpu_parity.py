@@ -954,3 +954,60 @@ def test_spectra_without_a_charge(data, mode, method):
     with pytest.raises(PepQueryError):
         bad = {k: v.copy() for k, v in sp.items()}; bad["charge"][5] = -1
         Search(p).load_spectra(bad)
+
+
+@pytest.mark.parametrize("method,chunk", [(1, None), (1, "60"), (2, "150")])
+def test_search_at_load(data, method, chunk, monkeypatch):
+    """pq_params.search_at_load: with the targets set and the database staged, pq_load_spectra runs Steps 2-4 on every part of the
+    spectra as soon as it has arrived (reference table first built for the mass range of all resident spectra, then cut down to
+    the matched-spectra window).  The step calls that follow hand back what is there.  Same PSMs, detail rows, pair counts,
+    reference table and delta scores as the oracle and as the same search run step by step; Step 5 works on top."""
+    from pepquery_b200 import unimod
+    prot, tgt, sp = data
+    keep = []
+    spp = _pinned_copy(sp, keep)
+    if chunk:
+        monkeypatch.setenv("PQ_LOAD_CHUNK_SPECTRA", chunk)           # parts of 4 chunks: many small parts
+    p = _abi.default_params(n_random=80, score_method=method)
+    o = run_oracle(p, sp, tgt, prot)
+    want = o.psms()
+
+    def staged_search(g):
+        g.set_targets(*tgt); g.stage_reference(*prot); g.load_spectra(spp)
+        n = g.step2(); g.build_reference(); g.step3(); g.step4(); g.rank()
+        return n
+    g = Search(p)
+    n = staged_search(g)
+    got = g.psms()
+    assert n == len(got)
+    assert_psms_equal(got, want)
+    c = g.counters()
+    assert [c.pairs_step2, c.pairs_step3, c.pairs_step4] == [int(x) for x in o.pairs()[:3]]
+    ro, nro = o.reference_forms(); rg, nrg = g.reference_forms()
+    assert nro == nrg and bytes(ro)[:nro * C.sizeof(_abi.pq_form)] == bytes(rg)[:nrg * C.sizeof(_abi.pq_form)]
+    co = np.sort(o.competitors(3), order=["spectrum", "ref_form"]); cg = np.sort(g.competitors(3), order=["spectrum", "ref_form"])
+    assert np.array_equal(co["spectrum"], cg["spectrum"]) and np.array_equal(co["ref_form"], cg["ref_form"]) and np.allclose(co["score"], cg["score"], rtol=REL, atol=0)
+    (gr, gm), (wr, wm) = g.delta_scores(), o.delta_scores()
+    assert np.allclose(gr, wr, rtol=REL, atol=1e-9)
+    # the same search step by step (search_at_load = 0) gives the same bytes
+    h = Search(_abi.default_params(n_random=80, score_method=method, search_at_load=0))
+    h.set_targets(*tgt); h.stage_reference(*prot); h.load_spectra(spp); h.step2(); h.build_reference(); h.step3(); h.step4(); h.rank()
+    assert h.psms().tobytes() == got.tobytes() and np.sort(h.competitors(3), order=["spectrum", "ref_form"]).tobytes() == cg.tobytes()
+    # the steps called again recompute on the resident data: identical
+    g.step2(); g.build_reference(); g.step3(); g.step4(); g.rank()
+    assert g.psms().tobytes() == got.tobytes()
+    # a second search on the same context
+    staged_search(g)
+    assert g.psms().tobytes() == got.tobytes()
+    # Step 5 on top of a search at load
+    ptms = unimod.load_ptms()[:120]
+    g.step5(ptms); o.step5(ptms)
+    assert_psms_equal(g.psms(), o.psms())
+    k5 = ["spectrum", "ref_form", "ptm", "ptm_site"]
+    r5o = np.sort(o.competitors(5), order=k5); r5g = np.sort(g.competitors(5), order=k5)
+    assert len(r5o) == len(r5g) and all(np.array_equal(r5o[k], r5g[k]) for k in k5)
+    # shuffles exist for every target in this mode; their strings are still the reference's
+    toff, tres = tgt
+    from oracle import pq_oracle
+    seq0 = bytes(tres[int(toff[0]):int(toff[1])]).decode()
+    assert g.shuffles(0, len(seq0)) == pq_oracle.shuffles(seq0, 80)
