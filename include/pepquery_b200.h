@@ -166,6 +166,19 @@ typedef struct pq_competitor {
     double  pep_mass;
 } pq_competitor;
 
+/* Status of a targeted PSM (pg/PsmType.java; TargetedPSM.get_psm_status, pg/TargetedPSM.java:29-46). */
+typedef enum pq_psm_type {
+    PQ_PSM_NO_SPECTRUM_MATCH = 0,        /* the peptide never met the spectrum in a precursor window                     */
+    PQ_PSM_SPECTRUM_MATCHED = 1,
+    PQ_PSM_LOW_SCORE = 2,                /* it did, but no form scored above min_score                                   */
+    PQ_PSM_HIGH_P_VALUE = 3,
+    PQ_PSM_BETTER_REF_PEP = 4,           /* n_db >= 1                                                                    */
+    PQ_PSM_BETTER_REF_PEP_WITH_MOD = 5,  /* n_ptm >= 1                                                                   */
+    PQ_PSM_NOT_TOP_RANK = 6,             /* rank >= 2                                                                    */
+    PQ_PSM_CONFIDENT = 7,
+    PQ_PSM_INVALID_PEPTIDE = 8           /* the Java host's call (it owns the Step-1 verdict); never returned from here  */
+} pq_psm_type;
+
 /* Unimod-like PTM specificity for Step 5 (OpenModificationSearch/ModificationDB.java:334-533). */
 typedef struct pq_ptm {
     int32_t id;
@@ -220,6 +233,17 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n_spectra, const double* precursor_
  * pq_load_spectra, else in pq_step2_match_targets / pq_get_target_forms). */
 int32_t pq_set_targets(pq_ctx* ctx, int32_t n_seq, const uint32_t* seq_offset /* n+1 */, const char* residues);
 int32_t pq_get_target_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int64_t* n_forms);
+/* Targeted PSMs.  Replaces SpectraInput.pep2targeted_spectra (filled at pg/PeptideSearchMT.java:264-309 when the peptide input names
+ * spectra): pairs (target sequence index, spectrum index in the pq_load_spectra order).  In Step 2 a target sequence that appears in
+ * the list is only scored against the spectra named for it (pg/FindCandidateSpectraAndScoreWorker.java:60-74, :126-134, :188-197);
+ * sequences that do not appear are unrestricted.  Call after pq_set_targets (which clears the list) and before
+ * pq_step2_match_targets; n_pairs = 0 clears it. */
+int32_t pq_set_targeted_psms(pq_ctx* ctx, int64_t n_pairs, const int32_t* target_seq, const int32_t* spectrum);
+/* One pq_psm_type per targeted pair, in the order they were given: PeptideSearchMT.export_targeted_psm_status
+ * (pg/PeptideSearchMT.java:1484-1589) from the ranked PSM table — the best-ranked row of (peptide sequence, spectrum) decides; without a
+ * row: LOW_SCORE when Step 2 saw the pair in a precursor window (a spectrum that came with a charge), else NO_SPECTRUM_MATCH.
+ * Call after pq_rank_and_validate (and pq_step5_ptm, if it runs). */
+int32_t pq_get_targeted_psm_status(pq_ctx* ctx, int32_t* type, int64_t capacity, int64_t* n_pairs);
 
 /* Reference database.  Replaces DatabaseInput.generate_reference_peptide_index
  * (pg/DatabaseInput.java:402-556) + DigestProteinWorker.run (OpenModificationSearch/DigestProteinWorker.java:64-137)

@@ -476,6 +476,19 @@ __device__ __forceinline__ bool below_score_bound_lists(const uint4* __restrict_
     return bound_below_cutoff<METHOD>(B, (int)min(nb, 0xFFFFu), (int)min(ny, 0xFFFFu), log10_fact, cutoff, ln_fact, predicted);
 }
 
+// Targeted PSM list in Step 2 (FindCandidateSpectraAndScoreWorker.java:60-74): false = the row's peptide names its spectra and this is
+// not one of them (the pair is not scored); a named pair on a spectrum that came with a charge is marked "seen" (:69-74).
+__device__ __forceinline__ bool targeted_allows(const TargetedView& V, uint32_t row, int32_t spectrum_sorted) {
+    const uint32_t seq = V.canon[V.seq_of_form[V.form_of_row[row]]];
+    if (!V.seq_listed[seq]) return true;
+    const uint64_t key = ((uint64_t)seq << 32) | (uint32_t)V.caller_index[spectrum_sorted];
+    uint32_t lo = 0, hi = V.n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (V.keys[mid] < key) lo = mid + 1; else hi = mid; }
+    if (lo >= V.n || V.keys[lo] != key) return false;
+    if (V.alias[spectrum_sorted] == 0) V.seen[lo] = 1;
+    return true;
+}
+
 // Precursor-window predicate exactly as DBSearchWorker.java:38-52 / FindCandidate...java:47-58:
 // bucket round(10*pepMass) within +-1 of round(10*mass) AND |pepMass - mass| (ppm of pepMass) <= tol.
 __device__ __forceinline__ bool in_window(double pm, double mass, long long va, const ScoreConfig& cfg) {

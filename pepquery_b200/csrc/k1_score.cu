@@ -163,6 +163,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
             if (active) {
                 load_row(row);
                 if (cfg.check_window) active = in_window(L.row_mass[row], J.mass, va, cfg);
+                if (active && L.tgt.n && L.kind == kJobTargets) active = targeted_allows(L.tgt, row, J.spectrum);
             }
             if (active) {
                 int32_t pred = 0;
@@ -249,6 +250,7 @@ k1_scatter_kernel(ScoreLaunch L, ScoreConfig cfg) {
         for (uint32_t c = 0; c < J.cand_count; ++c) {
             const uint32_t row = J.cand_begin + c;
             if (cfg.check_window && !in_window(L.row_mass[row], J.mass, va, cfg)) continue;
+            if (L.tgt.n && L.kind == kJobTargets && !targeted_allows(L.tgt, row, J.spectrum)) continue;
             const uint4* rp = reinterpret_cast<const uint4*>(L.rows + (size_t)row * kRowBytes);
             uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
             codes[0 * BLOCK] = q0.x; codes[1 * BLOCK] = q0.y; codes[2 * BLOCK] = q0.z; codes[3 * BLOCK] = q0.w;

@@ -401,6 +401,29 @@ __global__ void k7_delta_scores(const DevPsm* __restrict__ psms, const uint32_t*
     ref_delta[j] = r; mod_delta[j] = m;
 }
 
+// PeptideSearchMT.export_targeted_psm_status (pg/PeptideSearchMT.java:1484-1589): per targeted pair the best-ranked PSM row of
+// (peptide sequence, spectrum), then TargetedPSM.get_psm_status (pg/TargetedPSM.java:29-46) on that row
+__global__ void k7_targeted_best(const DevPsm* __restrict__ psms, uint32_t n, TargetedView V, unsigned long long* __restrict__ best) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevPsm& p = psms[i];
+    const uint32_t seq = V.canon[V.seq_of_form[p.form]];
+    if (!V.seq_listed[seq]) return;
+    const uint64_t key = ((uint64_t)seq << 32) | (uint32_t)p.spectrum;
+    uint32_t lo = 0, hi = V.n;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (V.keys[mid] < key) lo = mid + 1; else hi = mid; }
+    if (lo < V.n && V.keys[lo] == key) atomicMin(&best[lo], ((unsigned long long)(uint32_t)p.rank << 32) | i);
+}
+__global__ void k7_targeted_type(const DevPsm* __restrict__ psms, TargetedView V, const unsigned long long* __restrict__ best, int32_t* __restrict__ type) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= V.n) return;
+    const unsigned long long b = best[k];
+    if (b == ~0ull) { type[k] = V.seen[k] ? PQ_PSM_LOW_SCORE : PQ_PSM_NO_SPECTRUM_MATCH; return; }
+    const DevPsm& p = psms[(uint32_t)b];
+    const bool pv = (p.len <= 8 && p.p_value <= 0.05) || (p.len > 8 && p.p_value <= 0.01);       // CParameter.passed_p_value_validation
+    type[k] = p.rank >= 2 ? PQ_PSM_NOT_TOP_RANK : (p.n_db >= 1 ? PQ_PSM_BETTER_REF_PEP : (!pv ? PQ_PSM_HIGH_P_VALUE : (p.n_ptm >= 1 ? PQ_PSM_BETTER_REF_PEP_WITH_MOD : PQ_PSM_CONFIDENT)));
+}
+
 __global__ void k7_set_nptm(DevPsm* __restrict__ psms, uint32_t n, const int32_t* __restrict__ n_ptm) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) psms[i].n_ptm = n_ptm[i];
@@ -627,6 +650,14 @@ int launch_delta_scores(const DevPsm* psms, const uint32_t* out_perm, uint32_t n
     if (!n) return 0;
     k7_delta_scores<<<blocks(n), 256, 0, st>>>(psms, out_perm, n, agg, mod_key, mod_best, n_mod, ref_delta, mod_delta);
     return 1;
+}
+int launch_targeted_status(const DevPsm* psms, uint32_t n_psm, const TargetedView& V, unsigned long long* best, int32_t* type_sorted, cudaStream_t st) {
+    if (!V.n) return 0;
+    cudaMemsetAsync(best, 0xFF, (size_t)V.n * 8, st);
+    int k = 1;
+    if (n_psm) { k7_targeted_best<<<blocks(n_psm), 256, 0, st>>>(psms, n_psm, V, best); ++k; }
+    k7_targeted_type<<<blocks(V.n), 256, 0, st>>>(psms, V, best, type_sorted);
+    return k;
 }
 int launch_set_nptm(DevPsm* psms, uint32_t n, const int32_t* n_ptm, cudaStream_t st) {
     if (!n) return 0;

@@ -133,6 +133,15 @@ struct pq_ctx {
     bool pending_step[5] = {false, false, false, false, false};   // [2..4]: results of that step are already in the PSM table
     bool pending_ref = false;                                      // pq_build_reference(NULL) only has to cut the table out of the superset
     cudaStream_t st_part = nullptr;
+    // targeted PSM list (SpectraInput.pep2targeted_spectra)
+    DevBuf tg_keys, tg_listed, tg_canon, tg_seen, tg_best, tg_type; uint32_t n_targeted = 0; std::vector<uint32_t> tg_pos;     // tg_pos[i] = position of pair i in the sorted keys
+    TargetedView targeted_view() const {
+        TargetedView v; memset(&v, 0, sizeof v);
+        v.n = n_targeted; if (!n_targeted) return v;
+        v.keys = tg_keys.as<uint64_t>(); v.seq_listed = tg_listed.as<uint8_t>(); v.canon = tg_canon.as<uint32_t>(); v.seen = tg_seen.as<uint8_t>();
+        v.form_of_row = t_form_of_row.as<uint32_t>(); v.seq_of_form = t_seq_of_form.as<int32_t>(); v.caller_index = s_caller.as<int32_t>(); v.alias = s_alias.as<uint8_t>();
+        return v;
+    }
     DevBuf up_rank, part_first, super_seq;
     DevBuf sh_plans, sh_seq_flag, sh_form_flag, sh_valid_flag, sh_seq_slot, sh_form_slot, sh_row_base, sh_totals, sh_list, sh_order, sh_keys, sh_keys2;
     bool have_shuffles = false;
@@ -235,6 +244,7 @@ int32_t run_score_io(pq_ctx* ctx, const ScoreIO& io, JobKind kind, uint32_t n_jo
     L.row_pred = row_pred;
     L.results = io.results->as<JobResult>(); L.hits = io.hits->as<Hit>(); L.hit_count = io.hit_count->as<uint32_t>();
     L.hit_capacity = hit_capacity; L.max_blob_bytes = ctx->max_blob; L.job_counter = io.job_counter;
+    if (kind == kJobTargets) L.tgt = ctx->targeted_view();
     if (kind == kJobShuffles && ctx->have_lists) { L.sh_forms = ctx->sh_forms.as<ShuffleForm>(); L.form_slot = ctx->sh_form_slot.as<uint32_t>(); L.lists = ctx->sh_lists.as<uint4>(); }
     ScoreConfig cfg = score_config(ctx, check_window);
     const int si = kind == kJobTargets ? 0 : kind == kJobCompetitors ? 1 : kind == kJobShuffles ? 2 : 3;
@@ -651,7 +661,7 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
             CL(cudaEventRecord(ctx->meta_ev, st));
             CL(cudaStreamWaitEvent(sc, ctx->meta_ev, 0));
             // search while loading?  everything a search needs must be known now, and K0 must run here
-            stream_search = eager && ctx->P.search_at_load != 0 && !getenv("PQ_NO_SEARCH_AT_LOAD") && ctx->ref_staged && n0 == 0 && ctx->P.n_random <= 20000;
+            stream_search = eager && ctx->n_targeted == 0 && ctx->P.search_at_load != 0 && !getenv("PQ_NO_SEARCH_AT_LOAD") && ctx->ref_staged && n0 == 0 && ctx->P.n_random <= 20000;
             if (stream_search) while (ctx->k0_ev.size() < nck + 1) { cudaEvent_t e; CL(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->k0_ev.push_back(e); }
             n_chunks_cf = nck; chunk_spectra_cf = chunk_spectra;
             Timer t(ctx, &ctx->cnt.ms_prepare);
@@ -787,7 +797,7 @@ int32_t pq_set_targets(pq_ctx* ctx, int32_t n_seq, const uint32_t* off, const ch
     cudaSetDevice(ctx->P.device);
     PeptideTable& T = ctx->targets;
     T.seqs.clear(); T.forms.clear(); ctx->t_off.assign(1, 0u); ctx->t_flat.clear();
-    ctx->have_targets = false; ctx->target_table_ready = false; ctx->n_target_forms = 0; ++ctx->targets_epoch;
+    ctx->have_targets = false; ctx->target_table_ready = false; ctx->n_target_forms = 0; ++ctx->targets_epoch; ctx->n_targeted = 0; ctx->tg_pos.clear();
     for (int32_t i = 0; i < n_seq; ++i) {
         if (off[i + 1] < off[i]) return fail(ctx, PQ_ERR_BAD_ARG, "target offsets must be non-decreasing");
         std::string s(res + off[i], res + off[i + 1]);
@@ -855,6 +865,59 @@ int32_t finalize_targets(pq_ctx* ctx) {
 
 extern "C" {
 
+int32_t pq_set_targeted_psms(pq_ctx* ctx, int64_t n, const int32_t* target_seq, const int32_t* spectrum) {
+    if (!ctx || n < 0 || (n > 0 && (!target_seq || !spectrum))) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
+    if (!ctx->have_targets) return fail(ctx, PQ_ERR_STATE, "pq_set_targets first");
+    if (n > 0x7fffffffLL) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many targeted pairs");
+    cudaSetDevice(ctx->P.device);
+    ctx->n_targeted = 0; ctx->tg_pos.clear();
+    ctx->step_done = 0; reset_psm_state(ctx);                     // Step 2 has to run (again) with the list
+    if (n == 0) return PQ_OK;
+    const auto& seqs = ctx->targets.seqs;
+    const size_t nseq = seqs.size();
+    // the reference keys its map by the sequence text: targets given twice share one entry
+    std::vector<uint32_t> canon(nseq); std::unordered_map<std::string, uint32_t> first;
+    for (size_t i = 0; i < nseq; ++i) canon[i] = first.emplace(seqs[i], (uint32_t)i).first->second;
+    std::vector<uint64_t> keys((size_t)n); std::vector<uint8_t> listed(nseq, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        if (target_seq[i] < 0 || (size_t)target_seq[i] >= nseq || spectrum[i] < 0) return fail(ctx, PQ_ERR_BAD_ARG, "targeted pair " + std::to_string(i) + " out of range");
+        const uint32_t q = canon[(size_t)target_seq[i]];
+        keys[(size_t)i] = ((uint64_t)q << 32) | (uint32_t)spectrum[i]; listed[q] = 1;
+    }
+    std::vector<uint64_t> sorted(keys); std::sort(sorted.begin(), sorted.end()); sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+    ctx->tg_pos.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) ctx->tg_pos[(size_t)i] = (uint32_t)(std::lower_bound(sorted.begin(), sorted.end(), keys[(size_t)i]) - sorted.begin());
+    const size_t m = sorted.size();
+    CU(ctx->tg_keys.reserve(m * 8)); CU(ctx->tg_listed.reserve(nseq + 64)); CU(ctx->tg_canon.reserve(nseq * 4 + 64)); CU(ctx->tg_seen.reserve(m + 64));
+    CU(ctx->tg_best.reserve(m * 8)); CU(ctx->tg_type.reserve(m * 4));
+    CU(cudaMemcpyAsync(ctx->tg_keys.p, sorted.data(), m * 8, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->tg_listed.p, listed.data(), nseq, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemcpyAsync(ctx->tg_canon.p, canon.data(), nseq * 4, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaMemsetAsync(ctx->tg_seen.p, 0, m, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->cnt.h2d_bytes += m * 8 + nseq * 5;
+    ctx->n_targeted = (uint32_t)m;
+    return PQ_OK;
+}
+
+int32_t pq_get_targeted_psm_status(pq_ctx* ctx, int32_t* type, int64_t capacity, int64_t* n_pairs) {
+    if (!ctx || !n_pairs) return PQ_ERR_BAD_ARG;
+    *n_pairs = (int64_t)ctx->tg_pos.size();
+    if (!type) return PQ_OK;
+    if (capacity < *n_pairs) return fail(ctx, PQ_ERR_CAPACITY, "status buffer too small");
+    if (ctx->tg_pos.empty()) return PQ_OK;
+    if (ctx->step_done < 2) return fail(ctx, PQ_ERR_STATE, "pq_step2_match_targets first");
+    cudaSetDevice(ctx->P.device);
+    ctx->cnt.other_kernel_launches += (uint64_t)launch_targeted_status(ctx->d_psm.as<DevPsm>(), ctx->n_psm, ctx->targeted_view(), ctx->tg_best.as<unsigned long long>(),
+                                                                       ctx->tg_type.as<int32_t>(), ctx->st);
+    std::vector<int32_t> h(ctx->n_targeted);
+    CU(cudaMemcpyAsync(h.data(), ctx->tg_type.p, h.size() * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->cnt.d2h_bytes += h.size() * 4;
+    for (size_t i = 0; i < ctx->tg_pos.size(); ++i) type[i] = h[ctx->tg_pos[i]];
+    return PQ_OK;
+}
+
 int32_t pq_get_target_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int64_t* n_forms) {
     if (!ctx || !n_forms) return PQ_ERR_BAD_ARG;
     PeptideTable& T = ctx->targets;
@@ -892,6 +955,7 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     if (!cf) { CU(ctx->prep_id.reserve((size_t)(n + 1) * 4)); CU(ctx->prep_list.reserve((size_t)(n + 1) * 4)); }
     CU(cudaMemsetAsync(ctx->njobs.p, 0, 32, st));
     CU(cudaMemsetAsync(ctx->need.p, 0, (size_t)(n + 1) * 4, st));
+    if (ctx->n_targeted) CU(cudaMemsetAsync(ctx->tg_seen.p, 0, ctx->n_targeted, st));
     WindowConfig W; W.tol = ctx->P.tol; W.tol_ppm = ctx->P.tol_ppm; W.n_isotope = ctx->P.n_isotope; W.min_peaks = ctx->P.min_peaks;
     for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) W.isotope[i] = ctx->P.isotope[i];
     SpectraView sp = ctx->view();

@@ -97,6 +97,14 @@ struct ScoreConfig {
 };
 
 struct ShuffleForm;
+// SpectraInput.pep2targeted_spectra on the device: sorted keys (canonical target sequence << 32 | caller spectrum index)
+struct TargetedView {
+    const uint64_t* keys; uint32_t n;                 // n = 0: no list
+    const uint8_t* seq_listed;                        // [sequences] the (canonical) sequence appears in the list
+    const uint32_t* canon;                            // [sequences] first sequence with the same letters
+    uint8_t* seen;                                    // [n] the pair met in a precursor window (PsmType.spectrum_matched)
+    const uint32_t* form_of_row; const int32_t* seq_of_form; const int32_t* caller_index; const uint8_t* alias;
+};
 struct ScoreLaunch {
     uint32_t n_codes = kMaxCodes;   // residue codes in use (26 letters + the (residue, modification) pairs of this search)
     JobKind kind;
@@ -114,6 +122,7 @@ struct ScoreLaunch {
     uint32_t* job_counter;                                 // device word, zeroed by the launcher: next job to hand out
     // Step 4: cell lists of the shuffle rows (k_cells.cuh); null = walk the ladder in the count pass
     const ShuffleForm* sh_forms; const uint32_t* form_slot; const uint4* lists;
+    TargetedView tgt;                                      // Step 2: targeted PSM list
     // Step 5
     double ptm_delta; int32_t ptm_position; int32_t ptm_residue_code;
 };
@@ -276,6 +285,7 @@ bool find_in_proteome(int32_t n_seq, const uint32_t* seq_off, const char* res, i
 int launch_delta_scores(const DevPsm* psms, const uint32_t* out_perm, uint32_t n, const SegAgg* agg, const int32_t* mod_key, const double* mod_best,
                         uint32_t n_mod, double* ref_delta, double* mod_delta, cudaStream_t st);
 int launch_set_nptm(DevPsm* psms, uint32_t n, const int32_t* n_ptm, cudaStream_t st);
+int launch_targeted_status(const DevPsm* psms, uint32_t n_psm, const TargetedView& V, unsigned long long* best /* [V.n] scratch */, int32_t* type_sorted /* [V.n] */, cudaStream_t st);
 
 // MVH predicted-peak counts per row (k4_predict.cu): out[2*row] for precursor charge 2, out[2*row+1] otherwise
 int launch_predict(const uint8_t* rows, uint32_t n_rows, const ModTable* mods, double itol, int32_t* out, cudaStream_t st);

@@ -55,7 +55,7 @@ def load_library():
 
 # every symbol include/pepquery_b200.h declares
 EXPORTS = ["pq_version", "pq_last_error", "pq_default_params", "pq_create", "pq_destroy", "pq_load_spectra",
-           "pq_set_targets", "pq_get_target_forms", "pq_build_reference", "pq_stage_reference", "pq_get_reference_forms",
+           "pq_set_targets", "pq_set_targeted_psms", "pq_get_targeted_psm_status", "pq_get_target_forms", "pq_build_reference", "pq_stage_reference", "pq_get_reference_forms",
            "pq_step2_match_targets", "pq_step3_competitors", "pq_step4_shuffles", "pq_rank_and_validate",
            "pq_step5_ptm", "pq_get_psms", "pq_get_delta_scores", "pq_export_psms_device", "pq_get_competitors", "pq_get_shuffles", "pq_score_pairs",
            "pq_find_in_proteome", "pq_get_counters", "pq_reset_counters", "pq_event_record", "pq_event_elapsed_ms", "pq_parse_mgf"]
@@ -123,6 +123,19 @@ class Search:
 
     def set_targets(self, off, res):
         self._ck(self.L.pq_set_targets(self.h, C.c_int32(len(off) - 1), _p(off), _p(res)))
+
+    def set_targeted_psms(self, target_seq, spectrum):
+        """SpectraInput.pep2targeted_spectra: (target sequence index, spectrum index) pairs; after set_targets, before step2."""
+        a = np.ascontiguousarray(target_seq, dtype=np.int32); b = np.ascontiguousarray(spectrum, dtype=np.int32)
+        self._ck(self.L.pq_set_targeted_psms(self.h, C.c_int64(len(a)), _p(a), _p(b)))
+
+    def targeted_psm_status(self):
+        """One pq_psm_type per targeted pair (PeptideSearchMT.export_targeted_psm_status)."""
+        n = C.c_int64()
+        self._ck(self.L.pq_get_targeted_psm_status(self.h, None, C.c_int64(0), C.byref(n)))
+        out = np.zeros(max(1, n.value), dtype=np.int32)
+        self._ck(self.L.pq_get_targeted_psm_status(self.h, _p(out), C.c_int64(n.value), C.byref(n)))
+        return out[:n.value]
 
     def _forms(self, fn):
         n = C.c_int64()

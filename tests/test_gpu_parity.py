@@ -1011,3 +1011,49 @@ def test_search_at_load(data, method, chunk, monkeypatch):
     from oracle import pq_oracle
     seq0 = bytes(tres[int(toff[0]):int(toff[1])]).decode()
     assert g.shuffles(0, len(seq0)) == pq_oracle.shuffles(seq0, 80)
+
+
+def test_targeted_psms_and_their_status(data):
+    """pep2targeted_spectra (pg/PeptideSearchMT.java:264-309): a target that names its spectra is only scored against those
+    (FindCandidateSpectraAndScoreWorker.java:60-74); export_targeted_psm_status (PSMT:1484-1589) types every named pair."""
+    prot, tgt, sp = data
+    p = _abi.default_params(n_random=80)
+    base = run_oracle(p, sp, tgt, prot).psms()
+    fo_seq = None
+    from oracle import pq_oracle
+    o0 = pq_oracle.Oracle(p); o0.set_targets(*tgt); forms, nf = o0.target_forms()
+    seq_of_form = np.array([forms[i].seq_index for i in range(nf)])
+    # name, for some sequences with PSMs, half of their matched spectra plus a few spectra they never meet; leave the rest unrestricted
+    rng = np.random.default_rng(3)
+    seqs_with = np.unique(seq_of_form[base["form"]])
+    pairs = []
+    for q in seqs_with[::2]:
+        mine = np.unique(base["spectrum"][seq_of_form[base["form"]] == q])
+        for s in mine[::2]:
+            pairs.append((int(q), int(s)))
+        pairs.append((int(q), int(rng.integers(0, len(sp["prec_mz"])))))
+    pairs.append((int(seqs_with[1]), 3))              # a sequence named only for spectra it does not match
+    tq = np.array([a for a, _ in pairs], dtype=np.int32); ts = np.array([b for _, b in pairs], dtype=np.int32)
+    o = pq_oracle.Oracle(p, threads=8)
+    o.load_spectra(sp); o.set_targets(*tgt); o.set_targeted_psms(tq, ts)
+    o.step2(); o.build_reference(*prot); o.step3(); o.step4(); o.rank()
+    want = o.psms()
+    assert 0 < len(want) < len(base)
+    for mode in ("full", "candidate_first"):
+        g = Search(p)
+        keep = []
+        if mode == "full":
+            g.load_spectra(sp); g.set_targets(*tgt); g.set_targeted_psms(tq, ts)
+        else:
+            g.set_targets(*tgt); g.set_targeted_psms(tq, ts); g.stage_reference(*prot); g.load_spectra(_pinned_copy(sp, keep))
+        g.step2(); g.build_reference(*prot); g.step3(); g.step4(); g.rank()
+        got = g.psms()
+        assert_psms_equal(got, want)
+        c = g.counters()
+        assert [c.pairs_step2, c.pairs_step3, c.pairs_step4] == [int(x) for x in o.pairs()[:3]]
+        st_g, st_o = g.targeted_psm_status(), o.targeted_status()
+        assert np.array_equal(st_g, st_o)
+        assert {0, 7} <= set(st_g.tolist())          # pairs that never meet, confident pairs
+    # clearing the list gives the unrestricted search back
+    g.set_targeted_psms([], []); g.step2(); g.build_reference(*prot); g.step3(); g.step4(); g.rank()
+    assert_psms_equal(g.psms(), base)
