@@ -9,7 +9,7 @@
 //   cut flags      : a segment starts at a protein start or after K/R not followed by P (A10)
 //   candidates     : segment a joined with 0..max_missed following segments of the same protein, length / residue /
 //                    mass (H2O + residues, summed in order) filters                       (DigestProteinWorker.java:79-104)
-//   unique         : 5-bit-packed 240-bit keys, LSD radix sort (cub) = lexicographic order, run heads, minus the targets
+//   unique         : 5-bit-packed 300-bit keys (60 residues), LSD radix sort (cub) over the words in use = lexicographic order, run heads, minus the targets
 //   forms          : per unique sequence, all k-subsets (k <= max_var) of the variable (mod, site) slots in lexicographic
 //                    order, fixed modifications on the remaining sites, fixed-only form last; kept when
 //                    lo < mass < hi (the matched-spectra window +-255 Da)
@@ -27,7 +27,7 @@ namespace pq {
 
 namespace {
 
-constexpr int kKeyWords = 4;            // 48 residues x 5 bits
+constexpr int kKeyWords = 5;            // 60 residues x 5 bits (kMaxLen): twelve residues per 64-bit word
 constexpr int kMaxSlots = 64;
 
 struct ByteToU32 { __host__ __device__ uint32_t operator()(uint8_t b) const { return b; } };
@@ -105,7 +105,7 @@ __global__ void k6_pack_keys(const uint32_t* __restrict__ cand, uint32_t n_cand,
     if (i >= n_cand) return;
     uint32_t t = cand[i], a = t / per, mc = t % per;
     uint32_t b = starts[a], e = starts[a + mc + 1];
-    uint64_t k[kKeyWords] = {0, 0, 0, 0};
+    uint64_t k[kKeyWords] = {0, 0, 0, 0, 0};
     for (uint32_t j = b; j < e; ++j) {
         uint32_t r = j - b;
         k[r / 12] |= (uint64_t)(res[j] - 'A' + 1) << (59 - 5 * (r % 12));
@@ -298,7 +298,7 @@ template <class F> bool select_flagged(const uint8_t* flags, uint32_t n, uint32_
     (void)d_keep; (void)d_pos; (void)d_off;
 
 // Part 0: the raw protein bytes and offsets to the device (they are normalised there, DigestProteinWorker.java:66-70).
-// Sorted, unique 240-bit keys of the target sequences (the digest removes them, DatabaseInput.java:480-488).  A host-to-device
+// Sorted, unique 300-bit keys of the target sequences (the digest removes them, DatabaseInput.java:480-488).  A host-to-device
 // copy, so it is issued before the spectrum upload is queued, not from inside the digest.
 bool upload_target_keys_for_reference(cudaStream_t st, const std::vector<std::string>& targets, RefDeviceTable& T, std::string& err) {
     std::vector<uint64_t> tk;
@@ -307,8 +307,8 @@ bool upload_target_keys_for_reference(cudaStream_t st, const std::vector<std::st
     std::sort(ts.begin(), ts.end());
     ts.erase(std::unique(ts.begin(), ts.end()), ts.end());
     for (const std::string& s : ts) {
-        uint64_t k[kKeyWords] = {0, 0, 0, 0};
-        if (s.size() > 48) continue;
+        uint64_t k[kKeyWords] = {0, 0, 0, 0, 0};
+        if (s.size() > (size_t)kMaxLen) continue;
         for (size_t r = 0; r < s.size(); ++r) k[r / 12] |= (uint64_t)(s[r] - 'A' + 1) << (59 - 5 * (r % 12));
         for (int w = 0; w < kKeyWords; ++w) tk.push_back(k[w]);
     }
@@ -385,7 +385,7 @@ bool digest_reference_on_device(cudaStream_t st, const pq_params& P, const Codes
     RB(cudaStreamSynchronize(st));
     *launches += 6;
     if (n_cand == 0) return true;
-    // keys + lexicographic sort (LSD over the four 60-bit words)
+    // keys + lexicographic sort (LSD over the 60-bit words the longest allowed peptide needs)
     RB(d_keys.reserve((size_t)n_cand * 8 * kKeyWords)); RB(T.cand_pos.reserve((size_t)n_cand * 4)); RB(T.cand_len.reserve((size_t)n_cand * 4));
     RB(d_perm.reserve((size_t)n_cand * 4)); RB(d_perm2.reserve((size_t)n_cand * 4)); RB(d_tmpkey.reserve((size_t)n_cand * 8)); RB(d_tmpkey2.reserve((size_t)n_cand * 8));
     k6_pack_keys<<<(n_cand + 255) / 256, 256, 0, st>>>(d_cand.as<uint32_t>(), n_cand, T.starts.as<uint32_t>(), per, d_res, d_keys.as<uint64_t>(),

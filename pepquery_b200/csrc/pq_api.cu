@@ -7,7 +7,6 @@
 #include <map>
 #include <numeric>
 #include <string>
-#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -192,28 +191,6 @@ void flush_timers(pq_ctx* c) {
         c->free_events.push_back(t.a); c->free_events.push_back(t.b);
     }
     c->timers.clear();
-}
-
-int32_t upload_table(pq_ctx* ctx, PeptideTable& T) {
-    const size_t n = T.n();
-    std::vector<uint8_t> rows(n * kRowBytes);
-    T.h_mass.resize(n);
-    for (size_t i = 0; i < n; ++i) {
-        if (!ctx->codes.encode_row(T.seqs[(size_t)T.forms[i].seq], T.forms[i], rows.data() + i * kRowBytes))
-            return fail(ctx, PQ_ERR_UNSUPPORTED, "peptide form cannot be encoded (length > 60 or two modifications on one site): " + T.seqs[(size_t)T.forms[i].seq]);
-        T.h_mass[i] = T.forms[i].mass;
-    }
-    CU(T.rows.reserve(std::max<size_t>(rows.size(), 64)));
-    CU(T.mass.reserve(std::max<size_t>(n * 8, 64)));
-    CU(cudaMemcpyAsync(T.rows.p, rows.data(), rows.size(), cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaMemcpyAsync(T.mass.p, T.h_mass.data(), n * 8, cudaMemcpyHostToDevice, ctx->st));
-    if (ctx->P.score_method == 2 && n > 0) {
-        CU(T.pred.reserve(n * 8));
-        ctx->cnt.other_kernel_launches += (uint64_t)launch_predict(T.rows.as<uint8_t>(), (uint32_t)n, ctx->d_mods.as<ModTable>(), ctx->P.itol, T.pred.as<int32_t>(), ctx->st);
-    }
-    CU(cudaStreamSynchronize(ctx->st));
-    ctx->cnt.h2d_bytes += rows.size() + n * 8;
-    return PQ_OK;
 }
 
 ScoreConfig score_config(const pq_ctx* c, int check_window) {
@@ -787,11 +764,6 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-static void sort_table(PeptideTable& T) {
-    // mass ascending; equal masses keep (sequence, form) generation order (stable)
-    std::stable_sort(T.forms.begin(), T.forms.end(), [](const FormRec& a, const FormRec& b) { return a.mass < b.mass; });
-}
-
 int32_t pq_set_targets(pq_ctx* ctx, int32_t n_seq, const uint32_t* off, const char* res) {
     if (!ctx || n_seq < 0 || (n_seq > 0 && (!off || !res))) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
     cudaSetDevice(ctx->P.device);
@@ -1097,7 +1069,6 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
 }  // extern "C"
 
 namespace {
-bool device_reference_path(const pq_ctx* ctx) { return ctx->P.max_len <= 48 && !getenv("PQ_HOST_REFERENCE"); }
 
 // digest of the staged proteins (K6 part 1) on stream st; synchronised at return
 int32_t digest_staged_reference(pq_ctx* ctx, cudaStream_t st, bool count_time) {
@@ -1116,7 +1087,6 @@ extern "C" {
 
 int32_t pq_stage_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off, const char* res) {
     if (!ctx || n_proteins < 0 || (n_proteins > 0 && (!off || !res))) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
-    if (!device_reference_path(ctx)) return fail(ctx, PQ_ERR_UNSUPPORTED, "pq_stage_reference needs the device-built reference table (max_len <= 48)");
     cudaSetDevice(ctx->P.device);
     auto t_begin = std::chrono::steady_clock::now();
     ctx->ref_staged = false; ctx->ref_digested = false; ctx->have_reference = false;
@@ -1141,7 +1111,7 @@ int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off,
     auto t_begin = std::chrono::steady_clock::now();
     Marks mk("build_reference");
     if (!use_staged) { ctx->ref_staged = false; ctx->ref_digested = false; }
-    if (device_reference_path(ctx)) {
+    {
         // device path (K6): digest, unique, form expansion and the mass sort all run on the GPU
         double mn = 1.7976931348623157e308, mx = 0.0;      // GeneratePeptideformWorker.set_mass_range (:40-52)
         if (ctx->n_psm) { mn = ctx->psm_mass_lo; mx = ctx->psm_mass_hi; }
@@ -1177,47 +1147,6 @@ int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off,
         ctx->have_reference = true;
         return PQ_OK;
     }
-    int threads = (int)std::thread::hardware_concurrency(); if (threads < 1) threads = 1; if (threads > 32) threads = 32;
-    digest_proteins(ctx->P, ctx->codes.residue_mass, n_proteins, off, res, R.seqs, threads);
-    mk.mark("digest + unique + sort");
-    {   // DatabaseInput.protein_digest(db, target_peptides) removes the target sequences (:480-488)
-        std::vector<std::string> t(ctx->targets.seqs);
-        for (std::string& s : t) for (char& c : s) if (c == 'I') c = 'L';      // add_target_peptides folds I -> L (pg/DatabaseInput.java:47-51)
-        std::sort(t.begin(), t.end());
-        R.seqs.erase(std::remove_if(R.seqs.begin(), R.seqs.end(), [&](const std::string& s) { return std::binary_search(t.begin(), t.end(), s); }), R.seqs.end());
-    }
-    // GeneratePeptideformWorker.set_mass_range over the matched spectra (GeneratePeptideformWorker.java:40-52)
-    double mn = 1.7976931348623157e308, mx = 0.0;
-    if (ctx->n_psm) { mn = ctx->psm_mass_lo; mx = ctx->psm_mass_hi; }
-    const double lo = mn - 250.0 - 5.0, hi = mx + 250.0 + 5.0;
-    {
-        std::vector<std::vector<FormRec>> part((size_t)threads);
-        std::vector<std::thread> th;
-        const size_t ns = R.seqs.size();
-        for (int t = 0; t < threads; ++t) th.emplace_back([&, t]() {
-            std::vector<FormRec> tmp;
-            size_t a = ns * (size_t)t / (size_t)threads, b = ns * (size_t)(t + 1) / (size_t)threads;
-            for (size_t i = a; i < b; ++i) {
-                tmp.clear();
-                ctx->codes.expand_forms(R.seqs[i], (int32_t)i, tmp);
-                for (const FormRec& f : tmp) if (f.mass > lo && f.mass < hi) part[(size_t)t].push_back(f);
-            }
-        });
-        for (auto& t : th) t.join();
-        size_t tot = 0; for (auto& p : part) tot += p.size();
-        R.forms.reserve(tot);
-        for (auto& p : part) R.forms.insert(R.forms.end(), p.begin(), p.end());
-    }
-    mk.mark("expand forms");
-    sort_table(R);
-    mk.mark("sort by mass");
-    int32_t rc = upload_table(ctx, R);
-    mk.mark("encode + upload");
-    if (rc) return rc;
-    ctx->cnt.reference_sequences = R.seqs.size(); ctx->cnt.reference_forms = R.forms.size();
-    ctx->cnt.ms_host_reference += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-    ctx->have_reference = true;
-    return PQ_OK;
 }
 
 int32_t pq_get_reference_forms(pq_ctx* ctx, pq_form* out, int64_t capacity, int64_t* n_forms) {

@@ -4,7 +4,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <thread>
 #include <unordered_set>
 
 namespace pq {
@@ -212,96 +211,6 @@ bool enzyme_rule(int32_t index, EnzymeRule& out) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-void digest_proteins(const pq_params& p, const double* residue_mass, int32_t n_proteins, const uint64_t* off, const char* res,
-                     std::vector<std::string>& out, int threads) {
-    if (threads < 1) threads = 1;
-    EnzymeRule rule; if (!enzyme_rule(p.enzyme, rule)) enzyme_rule(1, rule);
-    std::vector<std::unordered_set<std::string>> part((size_t)threads);
-    auto work = [&](int t) {
-        std::string prot; std::vector<int> cut;
-        std::unordered_set<std::string>& set = part[(size_t)t];
-        for (int32_t pi = t; pi < n_proteins; pi += threads) {
-            prot.clear();
-            for (uint64_t k = off[pi]; k < off[pi + 1]; ++k) {     // upper-case, strip '*', I->L (DigestProteinWorker.java:66-70)
-                char c = res[k];
-                if (c >= 'a' && c <= 'z') c = (char)(c - 32);
-                if (c == '*') continue;
-                if (c == 'I') c = 'L';
-                prot.push_back(c);
-            }
-            const int n = (int)prot.size();
-            cut.clear(); cut.push_back(0);
-            for (int i = 0; i + 1 < n; ++i) {                      // compomics Enzyme.isCleavageSite (A10)
-                const char x = prot[i], y = prot[i + 1];
-                if (x < 'A' || x > 'Z' || y < 'A' || y > 'Z') continue;
-                if ((((rule.cut_after >> (x - 'A')) & 1u) && !((rule.block_next >> (y - 'A')) & 1u)) || ((rule.cut_before >> (y - 'A')) & 1u)) cut.push_back(i + 1);
-            }
-            cut.push_back(n);
-            const int nseg = (int)cut.size() - 1;
-            for (int a = 0; a < nseg; ++a) {
-                for (int mc = 0; mc <= p.max_missed && a + mc < nseg; ++mc) {
-                    const int b = cut[a], e = cut[a + mc + 1], len = e - b;
-                    if (len < p.min_len || len > p.max_len) continue;
-                    double mass = kWater; bool ok = true;
-                    for (int i = b; i < e; ++i) {
-                        char c = prot[i];
-                        if (c < 'A' || c > 'Z' || residue_mass[c - 'A'] == 0.0) { ok = false; break; }   // X and other ambiguity codes
-                        mass += residue_mass[c - 'A'];
-                    }
-                    if (!ok || mass < p.min_mass || mass > p.max_mass) continue;
-                    set.emplace(prot, (size_t)b, (size_t)len);
-                }
-            }
-        }
-    };
-    std::vector<std::thread> th;
-    for (int t = 0; t < threads; ++t) th.emplace_back(work, t);
-    for (auto& t : th) t.join();
-    for (int t = 1; t < threads; ++t) { part[0].insert(part[(size_t)t].begin(), part[(size_t)t].end()); part[(size_t)t].clear(); }
-    out.assign(part[0].begin(), part[0].end());
-    std::sort(out.begin(), out.end());
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-static int64_t choose(int n, int k) {
-    if (k < 0 || k > n) return 0;
-    if (k > n - k) k = n - k;
-    unsigned __int128 r = 1;
-    for (int i = 1; i <= k; ++i) r = r * (unsigned)(n - k + i) / (unsigned)i;
-    return (int64_t)r;
-}
-
-void shuffle_plan(const std::string& seq, int n_random, ShuffleSeq& out) {
-    memset(&out, 0, sizeof out);
-    const int L = (int)seq.size();
-    const int len = L - 1;
-    out.len = (uint32_t)L;
-    for (int i = 0; i < L && i < kMaxLen; ++i) out.seq[i] = (uint8_t)(seq[i] - 'A');
-    // java.util.HashMap<String,Integer> over single-character keys: hash = char code, table 16 slots doubling while
-    // size > 0.75*capacity, iteration = slot order, insertion order inside a slot; then a stable sort by count
-    // (pg/PeptideInput.java:387-400, pg/HashMapValueCompare.java).
-    int count[26] = {0}; int first_seen[26]; int n_keys = 0;
-    for (int i = 0; i < 26; ++i) first_seen[i] = -1;
-    for (int i = 0; i < len; ++i) { int c = seq[i] - 'A'; if (count[c]++ == 0) first_seen[c] = n_keys++; }
-    int cap = 16;
-    while (n_keys * 4 > cap * 3) cap *= 2;
-    struct E { int slot, seen, code, cnt; };
-    std::vector<E> es;
-    for (int c = 0; c < 26; ++c) if (count[c]) es.push_back({(c + 'A') & (cap - 1), first_seen[c], c, count[c]});
-    std::sort(es.begin(), es.end(), [](const E& a, const E& b) { return a.slot != b.slot ? a.slot < b.slot : a.seen < b.seen; });
-    std::stable_sort(es.begin(), es.end(), [](const E& a, const E& b) { return a.cnt < b.cnt; });
-    out.n_groups = (uint32_t)es.size();
-    int64_t nComb = 1; int rn = len;
-    for (size_t g = 0; g < es.size(); ++g) {
-        out.group_code[g] = (uint8_t)es[g].code; out.group_count[g] = (uint8_t)es[g].cnt;
-        int64_t c = choose(rn, es[g].cnt);
-        if (nComb >= 10000000) nComb = 10000000; else nComb = (int64_t)((uint64_t)nComb * (uint64_t)c);   // :402-418
-        rn -= es[g].cnt;
-    }
-    int num = (int64_t)n_random > nComb ? (int)nComb : n_random;                                           // :424
-    out.num = num < 0 ? 0u : (uint32_t)num;
-}
-
 void factorial_tables(double* log10_fact65, std::vector<double>& ln_fact, int count) {
     if (count < 65) count = 65;
     ln_fact.assign((size_t)count, 0.0);

@@ -51,11 +51,6 @@ struct Codes {
 struct EnzymeRule { uint32_t cut_after, cut_before, block_next; };
 bool enzyme_rule(int32_t index, EnzymeRule& out);          // false: unknown index or 0 (NoEnzyme, unspecific: not supported)
 
-// DigestProteinWorker.run (OpenModificationSearch/DigestProteinWorker.java:64-137) over all proteins; returns the unique
-// I->L sequences in lexicographic order.
-void digest_proteins(const pq_params& p, const double* residue_mass, int32_t n_proteins, const uint64_t* off, const char* res,
-                     std::vector<std::string>& out, int threads);
-
 // The reference table as K6 builds it on the device (k6_reference.cu).  rows/mass point at the table's DevBufs.
 struct RefDeviceTable {
     DevBuf residues, starts, cand_pos, cand_len, uniq, seq_id;   // normalised proteins, segment starts, candidate (pos,len), unique candidate ids (lexicographic), parent id per form
@@ -82,9 +77,6 @@ struct TargetDeviceTable {
 };
 bool build_target_table_on_device(cudaStream_t st, const Codes& codes, uint32_t n_seq, const uint32_t* off, const char* flat, TargetDeviceTable& T,
                                   uint64_t* launches, std::string& err);
-
-// Group order + round count of PeptideInput.generateRandomPeptidesFast (pg/PeptideInput.java:387-422).
-void shuffle_plan(const std::string& seq, int n_random, ShuffleSeq& out);
 
 // commons-math 2 MathUtils tables (A12): log10(n!) for n <= 64 and ln(n!) for n < count
 void factorial_tables(double* log10_fact65, std::vector<double>& ln_fact, int count);

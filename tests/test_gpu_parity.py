@@ -119,6 +119,8 @@ def test_default_search_mvh(data):
     dict(min_score=40.0),
     dict(max_var_mods=1),
     dict(max_missed=0, n_random=50),
+    dict(max_len=60, max_missed=3, n_random=40),         # digest keys of up to 60 residues (five 12-residue words)
+    dict(min_len=5, max_len=12, n_random=40),
     dict(fast=0, hc=1),
 ], ids=lambda d: ",".join("%s=%s" % kv for kv in d.items()))
 def test_parameter_variations(data, over):
@@ -274,12 +276,9 @@ def _targets_with_a_planted_isoleucine(prot, tgt, params):
     return (off, np.frombuffer("".join(seqs).encode(), dtype=np.uint8).copy()), planted
 
 
-@pytest.mark.parametrize("host_reference", [False, True])
-def test_target_with_isoleucine_is_removed_from_the_reference(host_reference, monkeypatch):
+def test_target_with_isoleucine_is_removed_from_the_reference():
     """A target that contains I and is (I -> L folded) a digest peptide of the database must not compete with itself in
     Step 3 (DatabaseInput.add_target_peptides, pg/DatabaseInput.java:47-51 + protein_digest :480-488)."""
-    if host_reference:
-        monkeypatch.setenv("PQ_HOST_REFERENCE", "1")
     prot = synth.proteins(300)
     p = _abi.default_params(n_random=100)
     tgt, planted = _targets_with_a_planted_isoleucine(prot, synth.targets(20), p)
