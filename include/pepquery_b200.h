@@ -118,7 +118,10 @@ typedef struct pq_params {
                                    soon as that part has arrived, beside the rest of the upload.  pq_step2_match_targets,
                                    pq_build_reference(ctx, 0, NULL, NULL), pq_step3_competitors and pq_step4_shuffles then return what is
                                    already there.  0: every step runs when it is called.  Same results */
-    int32_t reserved1;
+    int32_t library_mode;       /* 1: the spectra come from an indexed MS/MS library (pq_read_ms_library) and Step 2 applies the rules of
+                                   msio/MsLibrarySearchWorker.java:42-153 instead of FindCandidateSpectraAndScoreWorker's: a spectrum needs
+                                   n_peaks >= min_peaks (loadSpectra :239; > min_peaks otherwise) and a candidate only |mass error| <= tol
+                                   (CParameter.get_mass_error), without the +-1 rule on 0.1-Da buckets.  0 (default) */
 } pq_params;
 
 /* One peptide form (sequence + placed modifications) as the caller sees it. */
@@ -312,6 +315,16 @@ int32_t pq_event_elapsed_ms(pq_ctx* ctx, double* ms);
  * first call with NULL outputs returns the required sizes. */
 int32_t pq_parse_mgf(const char* text, uint64_t n_bytes, int64_t* n_spectra, uint64_t* n_peaks,
                      double* precursor_mz, int32_t* charge, uint64_t* peak_offset, double* mz, double* intensity);
+
+/* On-disk MS/MS library: a directory with one MGF per 0.1-Da bin of the neutral precursor mass,
+ * <round(10 * mass)>.mgf, as index/BuildMSlibrary.java:173-352 + index/IndexWorker.java:422-486 write it and
+ * msio/MsLibrarySearchWorker.java:42-153 reads it.  Returns the spectra with mass_lo <= mass <= mass_hi (the range of one GPU's
+ * shard of a sweep) of the bins round(10 mass_lo) .. round(10 mass_hi), bin by bin, as CSR arrays for pq_load_spectra, plus their
+ * TITLE texts (the identity of a library spectrum).  Spectra without a charge are ignored like the reference does.  Two-call
+ * pattern like pq_parse_mgf; plain-text bins only (the reference also accepts .gz / .xz, decompressed by the Java host). */
+int32_t pq_read_ms_library(const char* dir, double mass_lo, double mass_hi, int64_t* n_spectra, uint64_t* n_peaks, uint64_t* title_bytes,
+                           double* precursor_mz, int32_t* charge, uint64_t* peak_offset, double* mz, double* intensity,
+                           uint64_t* title_offset /* n+1 */, char* titles);
 
 #ifdef __cplusplus
 }

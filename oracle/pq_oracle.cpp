@@ -868,7 +868,8 @@ static void step2(Ctx& C) {
     std::vector<std::vector<std::pair<const std::string*, int>>> touched(C.spectra.size());     // targeted pairs seen in a window
     parallel_for(C.threads, (int64_t)C.spectra.size(), [&](int64_t si) {
         Spectrum& sp = C.spectra[si];
-        if ((int)sp.mz.size() <= P.p.min_peaks) return;                 // SpectraInput.java:183
+        if (P.p.library_mode ? (int)sp.mz.size() < P.p.min_peaks : (int)sp.mz.size() <= P.p.min_peaks) return;   // SpectraInput.java:183; library: MsLibrarySearchWorker.java:239
+        if (P.p.library_mode && sp.given_charge < 1) return;            // MsLibrarySearchWorker.java:234-236
         // one pass of the window loop with the precursor charge set to z; returns whether a PSM was saved
         auto pass = [&](int z, bool update_status) -> bool {
             sp.charge = z;
@@ -877,7 +878,10 @@ static void step2(Ctx& C) {
             for (auto& im : isotope_masses(P, exp_mass)) {
                 double mass = im.first;
                 long va = java_round(mass * 10.0);
-                for (long i = va - 1; i <= va + 1; ++i) {
+                // a library search (msio/MsLibrarySearchWorker.java:70-120) knows no buckets: every form with |mass error| <= tol
+                const double reach = P.p.tol_ppm ? P.p.tol * 1e-6 * (std::fabs(mass) + 1.0) * 1.01 + 1e-6 : P.p.tol * 1.01 + 1e-6;
+                const long k_lo = P.p.library_mode ? java_round((mass - reach) * 10.0) - 1 : va - 1, k_hi = P.p.library_mode ? java_round((mass + reach) * 10.0) + 1 : va + 1;
+                for (long i = k_lo; i <= k_hi; ++i) {
                     auto it = pIndex.find(i);
                     if (it == pIndex.end()) continue;
                     for (int f : it->second) {

@@ -47,7 +47,7 @@ class pq_params(C.Structure):
                 ("fixed", pq_mod * PQ_MAX_MODS), ("var", pq_mod * PQ_MAX_MODS),
                 ("device", C.c_int32), ("score_all_shuffles", C.c_int32),
                 ("prepare_at_load", C.c_int32), ("candidate_first", C.c_int32),
-                ("search_at_load", C.c_int32), ("reserved1", C.c_int32)]
+                ("search_at_load", C.c_int32), ("library_mode", C.c_int32)]
 
 
 class pq_form(C.Structure):

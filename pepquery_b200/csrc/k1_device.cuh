@@ -492,8 +492,10 @@ __device__ __forceinline__ bool targeted_allows(const TargetedView& V, uint32_t 
 // Precursor-window predicate exactly as DBSearchWorker.java:38-52 / FindCandidate...java:47-58:
 // bucket round(10*pepMass) within +-1 of round(10*mass) AND |pepMass - mass| (ppm of pepMass) <= tol.
 __device__ __forceinline__ bool in_window(double pm, double mass, long long va, const ScoreConfig& cfg) {
-    long long key = jround(__dmul_rn(pm, 10.0));
-    if (key < va - 1 || key > va + 1) return false;
+    if (!cfg.no_bucket) {
+        long long key = jround(__dmul_rn(pm, 10.0));
+        if (key < va - 1 || key > va + 1) return false;
+    }
     double del = fabs(__dsub_rn(pm, mass));
     if (cfg.tol_ppm) del = __ddiv_rn(__dmul_rn(__dmul_rn(1.0e6, 1.0), del), pm);
     return del <= cfg.tol;

@@ -130,7 +130,7 @@ __global__ void k_enumerate_targets(SpectraView sp, const double* __restrict__ t
     bool plain = cfg.n_isotope == 1 && cfg.isotope[0] == 0;           // CParameter.java:423-448
     if (!plain) m = __dsub_rn(m, __dmul_rn((double)cfg.isotope[ii], kIsotope));
     double w = cfg.tol_ppm ? cfg.tol * 1e-6 * (fabs(m) + 1.0) * 1.01 + 1e-6 : cfg.tol * 1.01 + 1e-6;
-    if (w > 0.2) w = 0.2;                                              // the +-1 bucket rule never reaches further
+    if (w > 0.2 && !cfg.no_bucket) w = 0.2;                            // the +-1 bucket rule never reaches further
     uint32_t lo = lower_bound_d(table_mass, n_rows, m - w);
     uint32_t hi = lower_bound_d(table_mass, n_rows, m + w);
     if (hi <= lo) return;

@@ -193,12 +193,21 @@ void flush_timers(pq_ctx* c) {
     c->timers.clear();
 }
 
+// spectra with n_peaks <= this are never scored: min_peaks (SpectraInput.java:183), one less for a library search (n_peaks >= min_peaks)
+int32_t min_peaks_eff(const pq_ctx* c) { return c->P.min_peaks - (c->P.library_mode ? 1 : 0); }
+WindowConfig window_config(const pq_ctx* c, bool step2) {
+    WindowConfig W; W.tol = c->P.tol; W.tol_ppm = c->P.tol_ppm; W.n_isotope = c->P.n_isotope; W.min_peaks = min_peaks_eff(c);
+    for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) W.isotope[i] = c->P.isotope[i];
+    W.no_bucket = step2 && c->P.library_mode ? 1 : 0;
+    return W;
+}
 ScoreConfig score_config(const pq_ctx* c, int check_window) {
     ScoreConfig s; s.itol = c->P.itol; s.tol = c->P.tol; s.tol_ppm = c->P.tol_ppm; s.method = c->P.score_method;
     s.min_score = c->P.min_score; s.fast = c->P.fast; s.hc = c->P.hc;
     s.mvh_bins = (int32_t)jround((double)(int)(2000.0 - 200.0) / (c->P.itol * 2.0));
     s.check_window = check_window;
     s.score_all = c->P.score_all_shuffles || getenv("PQ_SCORE_ALL_SHUFFLES") != nullptr;
+    s.no_bucket = 0;
     return s;
 }
 
@@ -224,6 +233,7 @@ int32_t run_score_io(pq_ctx* ctx, const ScoreIO& io, JobKind kind, uint32_t n_jo
     if (kind == kJobTargets) L.tgt = ctx->targeted_view();
     if (kind == kJobShuffles && ctx->have_lists) { L.sh_forms = ctx->sh_forms.as<ShuffleForm>(); L.form_slot = ctx->sh_form_slot.as<uint32_t>(); L.lists = ctx->sh_lists.as<uint4>(); }
     ScoreConfig cfg = score_config(ctx, check_window);
+    if (kind == kJobTargets && ctx->P.library_mode) cfg.no_bucket = 1;
     const int si = kind == kJobTargets ? 0 : kind == kJobCompetitors ? 1 : kind == kJobShuffles ? 2 : 3;
     if (io.timed) {
         Timer t(ctx, &ctx->cnt.ms_score, &ctx->cnt.ms_score_step[si]);
@@ -490,6 +500,7 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
     // spectra without a charge (0) are searched as z = 2 and, failing that, z = 3: each is two virtual spectra
     std::vector<int32_t> zeros;
     for (int64_t i = 0; i < n; ++i) { if (charge[i] < 0) return fail_load(PQ_ERR_BAD_ARG, "charge must be >= 0 (0 = no charge given)"); if (charge[i] == 0) zeros.push_back((int32_t)i); }
+    if (ctx->P.library_mode && !zeros.empty()) return fail_load(PQ_ERR_BAD_ARG, "library_mode: a library spectrum needs a charge (MsLibrarySearchWorker.java:234-236 ignores the others)");
     const int64_t n0 = (int64_t)zeros.size(), nv = n + n0;
     if (nv > 0x7fffffffLL / PQ_MAX_ISOTOPE) return fail_load(PQ_ERR_UNSUPPORTED, "too many spectra for one context");
     ctx->nS = 0; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0; ctx->prepared_at_load = false; ctx->residency = 0; ctx->host_spectra_valid = false;
@@ -552,7 +563,7 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
             const uint64_t c = off[i + 1] - off[i];
             if (c > 4096) return fail_load(PQ_ERR_UNSUPPORTED, "more than 4096 peaks in one spectrum");
             if (c > maxp) maxp = (uint32_t)c;
-            if ((int64_t)c > (int64_t)ctx->P.min_peaks) ++usable;
+            if ((int64_t)c > (int64_t)min_peaks_eff(ctx)) ++usable;
             if (charge[i] == 0) alias_peaks += c;
             if (i + 1 < n && off[i + 1] >= next) { cut.push_back(i + 1); next = off[i + 1] + chunk_peaks; }
         }
@@ -576,8 +587,7 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
         CL(ctx->s_res.reserve((size_t)(nv + 1) * 4)); CL(ctx->prep_id.reserve((size_t)(nv + 1) * 4)); CL(ctx->prep_list.reserve((size_t)(nv + 2) * 8));
         CL(ctx->njobs.reserve(64)); CL(ctx->jobs.reserve((size_t)nv * ctx->P.n_isotope * sizeof(Job)));
         CL(cudaMemsetAsync(ctx->njobs.p, 0, 16, st)); CL(cudaMemsetAsync(ctx->s_res.p, 0, (size_t)(nv + 1) * 4, st));
-        WindowConfig W; W.tol = ctx->P.tol; W.tol_ppm = ctx->P.tol_ppm; W.n_isotope = ctx->P.n_isotope; W.min_peaks = ctx->P.min_peaks;
-        for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) W.isotope[i] = ctx->P.isotope[i];
+        WindowConfig W = window_config(ctx, true);
         struct { uint32_t n_res; uint32_t pad; uint64_t res_peaks; uint64_t blob_bytes; } hn = {0, 0, 0, 0};
         {
             Timer t(ctx, &ctx->cnt.ms_window);
@@ -738,7 +748,7 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
                     if (eager)
                         k_launch += launch_prepare(sp, ctx->s_inv.as<int32_t>() + first[part], (int32_t)count[part], pc, ctx->blobs.as<uint8_t>(),
                                                    ctx->blob_off.as<uint64_t>() + first[part], ctx->blob_len.as<uint32_t>() + first[part], ctx->max_peaks, st,
-                                                   (uint32_t)std::max(ctx->P.min_peaks + 1, 0));
+                                                   (uint32_t)std::max(min_peaks_eff(ctx) + 1, 0));
                 }
                 z_lo = z_hi;
             }
@@ -928,8 +938,7 @@ int32_t pq_step2_match_targets(pq_ctx* ctx, int64_t* n_psms) {
     CU(cudaMemsetAsync(ctx->njobs.p, 0, 32, st));
     CU(cudaMemsetAsync(ctx->need.p, 0, (size_t)(n + 1) * 4, st));
     if (ctx->n_targeted) CU(cudaMemsetAsync(ctx->tg_seen.p, 0, ctx->n_targeted, st));
-    WindowConfig W; W.tol = ctx->P.tol; W.tol_ppm = ctx->P.tol_ppm; W.n_isotope = ctx->P.n_isotope; W.min_peaks = ctx->P.min_peaks;
-    for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) W.isotope[i] = ctx->P.isotope[i];
+    WindowConfig W = window_config(ctx, true);
     SpectraView sp = ctx->view();
     struct { uint32_t njobs, nprep; unsigned long long cand; uint32_t missing, pad; } hn = {0, 0, 0, 0, 0};
     int32_t h_nprep = 0;
@@ -1200,8 +1209,7 @@ int32_t pq_step3_competitors(pq_ctx* ctx) {
         ctx->step_done = 3;
         return PQ_OK;
     }
-    WindowConfig W; W.tol = ctx->P.tol; W.tol_ppm = ctx->P.tol_ppm; W.n_isotope = ctx->P.n_isotope; W.min_peaks = ctx->P.min_peaks;
-    for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) W.isotope[i] = ctx->P.isotope[i];
+    WindowConfig W = window_config(ctx, false);
     const uint32_t n_jobs = n_seg * (uint32_t)ctx->P.n_isotope;
     CU(ctx->jobs.reserve((size_t)n_jobs * sizeof(Job)));
     CU(ctx->d_agg.reserve((size_t)n_seg * sizeof(SegAgg)));
@@ -1409,8 +1417,7 @@ int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan) {
         ctx->cnt.other_kernel_launches += (uint64_t)k + 3;
     }
     mk.mark("jobs by part");
-    WindowConfig W; W.tol = ctx->P.tol; W.tol_ppm = ctx->P.tol_ppm; W.n_isotope = ctx->P.n_isotope; W.min_peaks = ctx->P.min_peaks;
-    for (int i = 0; i < PQ_MAX_ISOTOPE; ++i) W.isotope[i] = ctx->P.isotope[i];
+    WindowConfig W = window_config(ctx, false);
     const TargetAux A = ctx->aux();
     uint64_t N = 0, NS = 0, NH3 = 0;
     for (uint32_t p = 0; p < n_parts; ++p) {

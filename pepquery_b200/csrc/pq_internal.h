@@ -94,6 +94,7 @@ struct ScoreConfig {
     int32_t mvh_bins;
     int32_t check_window;     // candidates must pass the bucket + tolerance predicate (Steps 2, 3, 5)
     int32_t score_all;        // Step 4: compute every shuffle's score in full (no upper-bound decision)
+    int32_t no_bucket;        // Step 2 of a library search: only |mass error| <= tol, no +-1 rule on the 0.1-Da buckets (MsLibrarySearchWorker.java:118-120)
 };
 
 struct ShuffleForm;
@@ -135,7 +136,7 @@ int launch_score(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st);
 
 // Step-2 window enumeration on device: for every usable spectrum x isotope error, the run of target rows whose mass
 // can fall in the precursor window.  Fills jobs (capacity n_spectra * n_isotope) and returns the count through d_n_jobs.
-struct WindowConfig { double tol; int32_t tol_ppm; int32_t n_isotope; int32_t isotope[PQ_MAX_ISOTOPE]; int32_t min_peaks; };
+struct WindowConfig { double tol; int32_t tol_ppm; int32_t n_isotope; int32_t isotope[PQ_MAX_ISOTOPE]; int32_t min_peaks; int32_t no_bucket; };
 int launch_enumerate_targets(const SpectraView& sp, const double* table_mass, uint32_t n_rows, const WindowConfig& cfg,
                              Job* jobs, uint32_t* d_n_jobs, int32_t* need_prepare /* [n] flags */, cudaStream_t st);
 

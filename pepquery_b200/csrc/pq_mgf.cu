@@ -94,7 +94,7 @@ struct Out { double* prec; int32_t* charge; uint64_t* off; double* mz; double* i
 // The sequential state machine over [p, end): a chunk always starts at a BEGIN IONS line (or at the start of the text).
 // fill == nullptr: count only.  s0 / p0: index of the chunk's first spectrum / peak in the caller's arrays.
 void parse_chunk(const char* p, const char* end, const Out* fill, int64_t s0, uint64_t p0, int64_t* n_spec, uint64_t* n_peak) {
-    int64_t ns = 0; uint64_t np = 0;
+    int64_t ns = 0; uint64_t np = 0, np_begin = 0;
     bool in_ions = false; double pmz = 0.0; int32_t z = 0;
     while (p < end) {
         const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
@@ -118,7 +118,8 @@ void parse_chunk(const char* p, const char* end, const Out* fill, int64_t s0, ui
                     }
                 }
             } else if (c == 'B' && len >= 10 && !memcmp(q, "BEGIN IONS", 10)) {
-                in_ions = true; pmz = 0.0; z = 0;
+                if (in_ions) np = np_begin;                    // a block without END IONS: its peaks belong to no spectrum, drop them (both passes)
+                in_ions = true; pmz = 0.0; z = 0; np_begin = np;
                 if (fill) fill->off[s0 + ns] = p0 + np;
             } else if (c == 'E' && len >= 8 && !memcmp(q, "END IONS", 8)) {
                 if (in_ions) {
@@ -134,6 +135,7 @@ void parse_chunk(const char* p, const char* end, const Out* fill, int64_t s0, ui
         }
         p = eol + 1;
     }
+    if (in_ions) np = np_begin;                                // the text ends inside a block
     *n_spec = ns; *n_peak = np;
 }
 
@@ -191,5 +193,120 @@ extern "C" int32_t pq_parse_mgf(const char* text, uint64_t n_bytes, int64_t* n_s
         peak_offset[ns] = np;
     }
     *n_spectra = ns; *n_peaks = np;
+    return PQ_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// On-disk MS/MS library.  index/BuildMSlibrary + IndexWorker write one MGF per 0.1-Da bin of the neutral
+// precursor mass, <round(10 * mass)>.mgf (IndexWorker.java:422-486, BuildMSlibrary.getIntMass :349-352); msio/MsLibrarySearchWorker
+// reads the bins a peptide's precursor window touches (:70-99, loadSpectra :154-252: spectra without a charge are ignored, the
+// TITLE line is the spectrum's identity).  Here the reader takes a mass RANGE — the range a GPU's shard of a sweep covers — and
+// returns every spectrum of the bins round(10 lo) .. round(10 hi) whose mass lies inside it, in bin order then file order, as the
+// CSR arrays pq_load_spectra takes, plus the titles.
+#include <cstdio>
+#include <string>
+
+namespace {
+
+struct LibSpectra { std::vector<double> prec, mz, inten; std::vector<int32_t> charge; std::vector<uint64_t> off{0}; std::string titles; std::vector<uint64_t> toff{0}; };
+
+bool read_file(const std::string& path, std::string& out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+    out.resize(n > 0 ? (size_t)n : 0);
+    size_t got = n > 0 ? fread(&out[0], 1, (size_t)n, f) : 0;
+    fclose(f);
+    out.resize(got);
+    return true;
+}
+
+void parse_library_file(const std::string& text, double lo, double hi, LibSpectra& L) {
+    const char* p = text.data(); const char* end = p + text.size();
+    bool in_ions = false; double pmz = 0.0; int32_t z = 0; std::string title;
+    size_t peaks0 = L.mz.size();
+    while (p < end) {
+        const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p));
+        if (!eol) eol = end;
+        const char* q = p;
+        while (q < eol && (*q == ' ' || *q == '\t' || *q == '\r')) ++q;
+        const char* r = eol; while (r > q && (r[-1] == '\r' || r[-1] == ' ' || r[-1] == '\t')) --r;
+        const size_t len = (size_t)(r - q);
+        if (len > 0) {
+            const char c = *q;
+            if (in_ions && ((c >= '0' && c <= '9') || c == '.')) {
+                const char* e1 = q; double a;
+                if (!fast_number(e1, eol, a)) a = parse_double(q, eol, &e1);
+                if (e1 != q) {
+                    const char* t = e1; while (t < eol && (*t == ' ' || *t == '\t')) ++t;
+                    const char* e2 = t; double b = 0.0;
+                    if (t < eol && !fast_number(e2, eol, b)) b = parse_double(t, eol, &e2);
+                    L.mz.push_back(a); L.inten.push_back(e2 != t ? b : 0.0);
+                }
+            } else if (c == 'B' && len >= 10 && !memcmp(q, "BEGIN IONS", 10)) {
+                if (in_ions) { L.mz.resize(peaks0); L.inten.resize(peaks0); }
+                in_ions = true; pmz = 0.0; z = 0; title.clear(); peaks0 = L.mz.size();
+            } else if (c == 'E' && len >= 8 && !memcmp(q, "END IONS", 8)) {
+                if (in_ions) {
+                    const double mass = pmz * z - z * pq::kProton;                       // Precursor.getMass
+                    if (z >= 1 && mass >= lo && mass <= hi) {                           // MsLibrarySearchWorker.java:234-241
+                        L.prec.push_back(pmz); L.charge.push_back(z); L.off.push_back(L.mz.size());
+                        L.titles += title; L.toff.push_back(L.titles.size());
+                    } else { L.mz.resize(peaks0); L.inten.resize(peaks0); }
+                    in_ions = false;
+                }
+            } else if (in_ions && c == 'P' && len >= 8 && !memcmp(q, "PEPMASS=", 8)) {
+                const char* e; pmz = parse_double(q + 8, eol, &e);
+            } else if (in_ions && c == 'C' && len >= 7 && !memcmp(q, "CHARGE=", 7)) {
+                z = (int32_t)strtol(q + 7, nullptr, 10); if (z < 0) z = -z;
+            } else if (in_ions && c == 'T' && len >= 6 && !memcmp(q, "TITLE=", 6)) {
+                title.assign(q + 6, r);
+            }
+        }
+        p = eol + 1;
+    }
+    if (in_ions) { L.mz.resize(peaks0); L.inten.resize(peaks0); }
+}
+
+}  // namespace
+
+extern "C" int32_t pq_read_ms_library(const char* dir, double mass_lo, double mass_hi, int64_t* n_spectra, uint64_t* n_peaks, uint64_t* title_bytes,
+                                      double* precursor_mz, int32_t* charge, uint64_t* peak_offset, double* mz, double* intensity,
+                                      uint64_t* title_offset, char* titles) {
+    if (!dir || !n_spectra || !n_peaks || !title_bytes || !(mass_hi >= mass_lo) || !(mass_lo > -1e9) || mass_hi - mass_lo > 1e7) return PQ_ERR_BAD_ARG;
+    const bool fill = precursor_mz && charge && peak_offset && mz && intensity && title_offset && titles;
+    const long long b0 = pq::jround(mass_lo * 10.0), b1 = pq::jround(mass_hi * 10.0);
+    const size_t nb = (size_t)(b1 - b0 + 1);
+    std::vector<LibSpectra> part(nb);
+    int threads = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("PQ_MGF_THREADS")) threads = atoi(e);
+    threads = std::max(1, std::min(threads, 64));
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) th.emplace_back([&, t]() {
+        std::string text;
+        for (size_t k = (size_t)t; k < nb; k += (size_t)threads) {
+            const std::string path = std::string(dir) + "/" + std::to_string(b0 + (long long)k) + ".mgf";
+            if (!read_file(path, text)) continue;                                    // a bin nobody wrote to: no file (MsLibrarySearchWorker.java:203-206)
+            parse_library_file(text, mass_lo, mass_hi, part[k]);
+        }
+    });
+    for (auto& t : th) t.join();
+    int64_t ns = 0; uint64_t np = 0, tb = 0;
+    for (auto& L : part) { ns += (int64_t)L.prec.size(); np += L.mz.size(); tb += L.titles.size(); }
+    if (fill) {
+        if (ns > *n_spectra || np > *n_peaks || tb > *title_bytes) return PQ_ERR_CAPACITY;
+        int64_t s = 0; uint64_t pk = 0, t0 = 0;
+        for (auto& L : part) {
+            for (size_t i = 0; i < L.prec.size(); ++i) {
+                precursor_mz[s] = L.prec[i]; charge[s] = L.charge[i]; peak_offset[s] = pk + L.off[i]; title_offset[s] = t0 + L.toff[i]; ++s;
+            }
+            if (!L.mz.empty()) { memcpy(mz + pk, L.mz.data(), L.mz.size() * 8); memcpy(intensity + pk, L.inten.data(), L.inten.size() * 8); }
+            if (!L.titles.empty()) memcpy(titles + t0, L.titles.data(), L.titles.size());
+            pk += L.mz.size(); t0 += L.titles.size();
+        }
+        peak_offset[ns] = np; title_offset[ns] = tb;
+    }
+    *n_spectra = ns; *n_peaks = np; *title_bytes = tb;
     return PQ_OK;
 }

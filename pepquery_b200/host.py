@@ -58,7 +58,8 @@ EXPORTS = ["pq_version", "pq_last_error", "pq_default_params", "pq_create", "pq_
            "pq_set_targets", "pq_set_targeted_psms", "pq_get_targeted_psm_status", "pq_get_target_forms", "pq_build_reference", "pq_stage_reference", "pq_get_reference_forms",
            "pq_step2_match_targets", "pq_step3_competitors", "pq_step4_shuffles", "pq_rank_and_validate",
            "pq_step5_ptm", "pq_get_psms", "pq_get_delta_scores", "pq_export_psms_device", "pq_get_competitors", "pq_get_shuffles", "pq_score_pairs",
-           "pq_find_in_proteome", "pq_get_counters", "pq_reset_counters", "pq_event_record", "pq_event_elapsed_ms", "pq_parse_mgf"]
+           "pq_find_in_proteome", "pq_get_counters", "pq_reset_counters", "pq_event_record", "pq_event_elapsed_ms", "pq_parse_mgf",
+           "pq_read_ms_library"]
 
 
 def _p(a):
@@ -313,3 +314,60 @@ def parse_mgf(text):
     if rc != 0:
         raise PepQueryError(rc, "pq_parse_mgf")
     return sp
+
+
+def write_mgf(sp, titles=None, charge_line=True):
+    """CSR dict -> MGF text in the reference's own form (index/IndexWorker.asMgf :422-457): TITLE / PEPMASS / CHARGE, peaks as
+    "%.4f %.2f".  Test and tool helper (the reference's writers stay Java)."""
+    out = []
+    off = sp["peak_off"]
+    for i in range(len(sp["prec_mz"])):
+        out.append("BEGIN IONS\nTITLE=%s\nPEPMASS=%r 1.0\n" % (titles[i] if titles is not None else "s:%d:%d" % (i + 1, sp["charge"][i]), float(sp["prec_mz"][i])))
+        if charge_line and sp["charge"][i] > 0:
+            out.append("CHARGE=%d+\n" % sp["charge"][i])
+        a, b = int(off[i]), int(off[i + 1])
+        out.append("".join("%.4f %.2f\n" % (m, v) for m, v in zip(sp["mz"][a:b], sp["inten"][a:b])))
+        out.append("END IONS\n")
+    return "".join(out)
+
+
+def build_ms_library(sp, out_dir, titles=None):
+    """index/BuildMSlibrary + IndexWorker.save2file (:474-486): one MGF per 0.1-Da bin of the neutral precursor mass,
+    <round(10 * mass)>.mgf, spectra appended in input order.  Returns the titles it wrote."""
+    from .shard import precursor_mass
+    os.makedirs(out_dir, exist_ok=True)
+    mass = precursor_mass(sp["prec_mz"], sp["charge"].astype(np.float64))
+    bins = np.floor(mass * 10.0 + 0.5).astype(np.int64)                 # Math.round
+    if titles is None:
+        titles = ["run1:%d:%d" % (i + 1, sp["charge"][i]) for i in range(len(mass))]
+    files = {}
+    off = sp["peak_off"]
+    for i in range(len(mass)):
+        one = dict(prec_mz=sp["prec_mz"][i:i + 1], charge=sp["charge"][i:i + 1], peak_off=np.array([0, off[i + 1] - off[i]], dtype=np.uint64),
+                   mz=sp["mz"][int(off[i]):int(off[i + 1])], inten=sp["inten"][int(off[i]):int(off[i + 1])])
+        files.setdefault(int(bins[i]), []).append(write_mgf(one, [titles[i]]) + "\n")
+    for b, chunks in files.items():
+        with open(os.path.join(out_dir, "%d.mgf" % b), "w") as f:
+            f.write("".join(chunks))
+    return titles
+
+
+def read_ms_library(path, mass_lo, mass_hi):
+    """pq_read_ms_library: the spectra of an indexed MS/MS library with mass_lo <= neutral precursor mass <= mass_hi
+    (msio/MsLibrarySearchWorker.loadSpectra :154-252) -> (CSR dict, titles)."""
+    L = load_library()
+    ns, npk, tb = C.c_int64(0), C.c_uint64(0), C.c_uint64(0)
+    d = path.encode()
+    rc = L.pq_read_ms_library(d, C.c_double(mass_lo), C.c_double(mass_hi), C.byref(ns), C.byref(npk), C.byref(tb), None, None, None, None, None, None, None)
+    if rc != 0:
+        raise PepQueryError(rc, "pq_read_ms_library")
+    sp = dict(prec_mz=np.zeros(ns.value), charge=np.zeros(ns.value, dtype=np.int32), peak_off=np.zeros(ns.value + 1, dtype=np.uint64),
+              mz=np.zeros(npk.value), inten=np.zeros(npk.value))
+    toff = np.zeros(ns.value + 1, dtype=np.uint64); tbuf = C.create_string_buffer(max(1, tb.value))
+    rc = L.pq_read_ms_library(d, C.c_double(mass_lo), C.c_double(mass_hi), C.byref(ns), C.byref(npk), C.byref(tb), _p(sp["prec_mz"]), _p(sp["charge"]),
+                              _p(sp["peak_off"]), _p(sp["mz"]), _p(sp["inten"]), _p(toff), tbuf)
+    if rc != 0:
+        raise PepQueryError(rc, "pq_read_ms_library")
+    raw = tbuf.raw
+    titles = [raw[int(toff[i]):int(toff[i + 1])].decode() for i in range(ns.value)]
+    return sp, titles
