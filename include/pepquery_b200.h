@@ -231,6 +231,18 @@ int32_t pq_destroy(pq_ctx* ctx);
 int32_t pq_load_spectra(pq_ctx* ctx, int64_t n_spectra, const double* precursor_mz, const int32_t* charge,
                         const uint64_t* peak_offset /* n+1 */, const double* mz, const double* intensity);
 
+/* The same from MGF text (replaces the compomics MgfFileIterator loop of pg/SpectraInput.java:150-195): the text goes
+ * to the device in chunks and is parsed THERE — line starts, line classes, prefix scans for spectrum and peak indices, numbers through
+ * Clinger's exact fast path in FP64 (the same doubles as strtod / Double.parseDouble; the rare number of another shape is parsed by the
+ * host's strtod and patched in) — straight into the arrays pq_load_spectra would have been given; then the loader runs as above
+ * (candidate-first, search_at_load ...).  Spectra are numbered in file order; a block without CHARGE has charge 0.  Blocks must be well
+ * formed (every BEGIN IONS closed by END IONS); otherwise PQ_ERR_BAD_ARG, and pq_parse_mgf + pq_load_spectra take the file. */
+int32_t pq_load_mgf(pq_ctx* ctx, const char* text, uint64_t n_bytes, int64_t* n_spectra);
+/* The device parser alone, with pq_parse_mgf's contract (first call with NULL outputs returns the sizes, the second fills the caller's
+ * arrays — it re-uses what the first one parsed when given the same text).  Discards the spectra loaded in ctx. */
+int32_t pq_parse_mgf_device(pq_ctx* ctx, const char* text, uint64_t n_bytes, int64_t* n_spectra, uint64_t* n_peaks, double* precursor_mz,
+                            int32_t* charge, uint64_t* peak_offset, double* mz, double* intensity);
+
 /* Target peptides.  Replaces CreatePeptideInputWorker -> PeptideInput.calcPeptideIsoforms
  * (pg/PeptideInput.java:114-237): expands each sequence into its modification forms (lazily: under the next
  * pq_load_spectra, else in pq_step2_match_targets / pq_get_target_forms). */

@@ -142,6 +142,8 @@ struct pq_ctx {
         return v;
     }
     DevBuf up_rank, part_first, super_seq;
+    MgfDeviceWork mgf; void* mgf_host = nullptr; size_t mgf_host_cap = 0;
+    const char* mgf_cache_text = nullptr; uint64_t mgf_cache_bytes = 0; int64_t mgf_cache_ns = 0; uint64_t mgf_cache_np = 0;
     DevBuf sh_plans, sh_seq_flag, sh_form_flag, sh_valid_flag, sh_seq_slot, sh_form_slot, sh_row_base, sh_totals, sh_list, sh_order, sh_keys, sh_keys2;
     bool have_shuffles = false;
     // results
@@ -424,6 +426,8 @@ int32_t pq_destroy(pq_ctx* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     flush_timers(ctx);
+    if (ctx->mgf_host) cudaFreeHost(ctx->mgf_host);
+    for (cudaEvent_t e : ctx->mgf.ev) cudaEventDestroy(e);
     if (ctx->stage_host) { cudaFreeHost(ctx->stage_host); cudaEventDestroy(ctx->stage_ev[0]); cudaEventDestroy(ctx->stage_ev[1]); }
     for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
     if (ctx->uev0) cudaEventDestroy(ctx->uev0);
@@ -483,10 +487,89 @@ int32_t pq_reset_counters(pq_ctx* ctx) {
 //     reads them straight from the caller's arrays into the mass-sorted CSR, chunk by chunk, K0 following each chunk.
 //   full upload (pageable buffers, or no targets yet): every peak crosses in 64 MB chunks on a copy stream, the compute stream
 //     follows chunk by chunk (copy into the sorted CSR, K0 with prepare_at_load).
+static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, const int32_t* charge, const uint64_t* off,
+                                 const double* mz, const double* inten, bool peaks_on_device);
 int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int32_t* charge, const uint64_t* off,
                         const double* mz, const double* inten) {
     if (!ctx || n < 0 || (n > 0 && (!prec_mz || !charge || !off || !mz || !inten))) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
+    return load_spectra_impl(ctx, n, prec_mz, charge, off, mz, inten, false);
+}
+
+// MGF text -> spectra on the device -> the loader above (replaces the compomics MgfFileIterator loop of
+// SpectraInput.readMSMSfast, pg/SpectraInput.java:150-195).  The text is parsed on the GPU (pq_mgf.cu); the peaks never exist on the host.
+int32_t pq_load_mgf(pq_ctx* ctx, const char* text, uint64_t n_bytes, int64_t* n_spectra) {
+    if (!ctx || (!text && n_bytes) || !n_spectra) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
     cudaSetDevice(ctx->P.device);
+    Marks mk("load_mgf");
+    *n_spectra = 0;
+    int64_t ns = 0; uint64_t np = 0; uint64_t launches = 0; std::string err;
+    if (!parse_mgf_on_device(ctx->st, ctx->st_copy, text, n_bytes, ctx->mgf, ctx->ld[0], ctx->ld[1], ctx->ld[2], ctx->ld[3], ctx->ld[4], &ns, &np, &launches, err)) {
+        cudaStreamSynchronize(ctx->st_copy); cudaStreamSynchronize(ctx->st); cudaGetLastError();
+        return fail(ctx, err.find("malformed") != std::string::npos ? PQ_ERR_BAD_ARG : PQ_ERR_CUDA, "device MGF parser: " + err);
+    }
+    ctx->cnt.other_kernel_launches += launches; ctx->cnt.h2d_bytes += n_bytes;
+    mk.mark("parsed on the device");
+    // the 28 bytes per spectrum of precursor data come back to the host: the loader validates and cuts its chunks there
+    const size_t need = (size_t)ns * 20 + 64;
+    if (ctx->mgf_host_cap < need) {
+        if (ctx->mgf_host) cudaFreeHost(ctx->mgf_host);
+        ctx->mgf_host = nullptr; ctx->mgf_host_cap = 0;
+        CU(cudaHostAlloc(&ctx->mgf_host, need + need / 8, cudaHostAllocDefault));
+        ctx->mgf_host_cap = need + need / 8;
+    }
+    uint64_t* h_off = static_cast<uint64_t*>(ctx->mgf_host); double* h_prec = reinterpret_cast<double*>(h_off + ns + 1); int32_t* h_charge = reinterpret_cast<int32_t*>(h_prec + ns);
+    if (ns) {
+        CU(cudaMemcpyAsync(h_off, ctx->ld[2].p, ((size_t)ns + 1) * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(h_prec, ctx->ld[0].p, (size_t)ns * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(h_charge, ctx->ld[1].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        ctx->cnt.d2h_bytes += (uint64_t)ns * 20 + 8;
+    } else h_off[0] = 0;
+    int32_t rc = load_spectra_impl(ctx, ns, h_prec, h_charge, h_off, ctx->ld[3].as<double>(), ctx->ld[4].as<double>(), true);
+    if (rc) return rc;
+    *n_spectra = ns;
+    return PQ_OK;
+}
+
+// The device parser alone, results back on the host: pq_parse_mgf's contract (two calls: sizes, then fill), ~100x its speed.
+int32_t pq_parse_mgf_device(pq_ctx* ctx, const char* text, uint64_t n_bytes, int64_t* n_spectra, uint64_t* n_peaks, double* precursor_mz, int32_t* charge,
+                            uint64_t* peak_offset, double* mz, double* intensity) {
+    if (!ctx || (!text && n_bytes) || !n_spectra || !n_peaks) return fail(ctx, PQ_ERR_BAD_ARG, "null argument");
+    cudaSetDevice(ctx->P.device);
+    const bool fill = precursor_mz && charge && peak_offset && mz && intensity;
+    if (!(ctx->mgf_cache_text == text && ctx->mgf_cache_bytes == n_bytes && fill)) {        // the fill call re-uses what the size call parsed
+        ctx->mgf_cache_text = nullptr;
+        uint64_t launches = 0; std::string err;
+        ctx->nS = 0; ctx->nCaller = 0; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0; ctx->prepared_at_load = false; ctx->residency = 0;      // the loader's staging buffers are about to be overwritten
+        if (!parse_mgf_on_device(ctx->st, ctx->st_copy, text, n_bytes, ctx->mgf, ctx->ld[0], ctx->ld[1], ctx->ld[2], ctx->ld[3], ctx->ld[4], &ctx->mgf_cache_ns, &ctx->mgf_cache_np,
+                                 &launches, err)) {
+            cudaStreamSynchronize(ctx->st_copy); cudaStreamSynchronize(ctx->st); cudaGetLastError();
+            return fail(ctx, err.find("malformed") != std::string::npos ? PQ_ERR_BAD_ARG : PQ_ERR_CUDA, "device MGF parser: " + err);
+        }
+        ctx->cnt.other_kernel_launches += launches; ctx->cnt.h2d_bytes += n_bytes;
+        ctx->mgf_cache_text = text; ctx->mgf_cache_bytes = n_bytes;
+    }
+    const int64_t ns = ctx->mgf_cache_ns; const uint64_t np = ctx->mgf_cache_np;
+    if (fill) {
+        if (*n_spectra < ns || *n_peaks < np) return fail(ctx, PQ_ERR_CAPACITY, "spectrum buffers too small");
+        int32_t rc = PQ_OK;
+        if (ns) {
+            rc = copy_to_caller(ctx, precursor_mz, ctx->ld[0].p, (size_t)ns * 8); if (rc) return rc;
+            rc = copy_to_caller(ctx, charge, ctx->ld[1].p, (size_t)ns * 4); if (rc) return rc;
+            rc = copy_to_caller(ctx, peak_offset, ctx->ld[2].p, ((size_t)ns + 1) * 8); if (rc) return rc;
+        } else peak_offset[0] = 0;
+        if (np) { rc = copy_to_caller(ctx, mz, ctx->ld[3].p, (size_t)np * 8); if (rc) return rc; rc = copy_to_caller(ctx, intensity, ctx->ld[4].p, (size_t)np * 8); if (rc) return rc; }
+        ctx->cnt.d2h_bytes += (uint64_t)ns * 20 + 8 + np * 16;
+        ctx->mgf_cache_text = nullptr;
+    }
+    *n_spectra = ns; *n_peaks = np;
+    return PQ_OK;
+}
+
+static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, const int32_t* charge, const uint64_t* off,
+                                 const double* mz, const double* inten, bool peaks_on_device) {
+    cudaSetDevice(ctx->P.device);
+    ctx->mgf_cache_text = nullptr;
     Marks mk("load_spectra");
     cudaStream_t st = ctx->st, sc = ctx->st_copy;
     // whatever goes wrong from here on, the context ends up without spectra and with nothing in flight
@@ -521,7 +604,7 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
         void* d = nullptr; if (cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         return d;
     };
-    const void* d_h_mz = dev_ptr(mz); const void* d_h_in = dev_ptr(inten);
+    const void* d_h_mz = peaks_on_device ? mz : dev_ptr(mz); const void* d_h_in = peaks_on_device ? inten : dev_ptr(inten);      // (the MGF parser left the peaks in ld[3] / ld[4])
     const bool pinned_all = d_h_mz && d_h_in;                     // only the peak arrays are read in place; the precursor arrays are copied
     const bool want_cf = ctx->P.candidate_first != 0 && getenv("PQ_LOAD_FULL") == nullptr;
     const bool cf = want_cf && ctx->have_targets && !ctx->targets.seqs.empty() && pinned_all;
@@ -622,7 +705,7 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
         CL(ctx->s_mz.reserve(std::max<uint64_t>(hn.res_peaks, 1) * 8)); CL(ctx->s_in.reserve(std::max<uint64_t>(hn.res_peaks, 1) * 8));
         sp = ctx->view();
         ctx->residency = 1; ctx->n_resident = n_res; ctx->loaded_epoch = ctx->targets_epoch;
-        ctx->cnt.h2d_bytes += (uint64_t)n * 28 + 8 + (uint64_t)n0 * 4 + hn.res_peaks * 16;
+        ctx->cnt.h2d_bytes += (uint64_t)n * 28 + 8 + (uint64_t)n0 * 4 + (peaks_on_device ? 0 : hn.res_peaks * 16);
         if (n_res) {
             // blob offsets of the resident spectra (blob id = rank in prep_list)
             CL(ctx->blob_off.reserve((size_t)(n_res + 2) * 8)); CL(ctx->blob_len.reserve((size_t)(n_res + 2) * 4));
@@ -706,14 +789,14 @@ int32_t pq_load_spectra(pq_ctx* ctx, int64_t n, const double* prec_mz, const int
         // driver) they were seen to hold those kernels back until the last chunk had landed (60 ms per load instead of 36 ms).
         for (size_t c = 0; c < n_chunks; ++c) {
             const uint64_t a = off[cut[c]], b = off[cut[c + 1]];
-            if (b > a) {
+            if (b > a && !peaks_on_device) {
                 CL(cudaMemcpyAsync(in_mz.as<double>() + a, mz + a, (b - a) * 8, cudaMemcpyHostToDevice, sc));
                 CL(cudaMemcpyAsync(in_in.as<double>() + a, inten + a, (b - a) * 8, cudaMemcpyHostToDevice, sc));
             }
             CL(cudaEventRecord(ctx->chunk_ev[c], sc));
         }
         mk.mark("chunk copies queued");
-        ctx->cnt.h2d_bytes += (uint64_t)n * 28 + 8 + (uint64_t)n0 * 4 + total * 16;
+        ctx->cnt.h2d_bytes += (uint64_t)n * 28 + 8 + (uint64_t)n0 * 4 + (peaks_on_device ? 0 : total * 16);
         ctx->residency = 0; ctx->n_resident = (uint32_t)nv;
         {
             Timer t(ctx, &ctx->cnt.ms_prepare);

@@ -78,6 +78,12 @@ struct TargetDeviceTable {
 bool build_target_table_on_device(cudaStream_t st, const Codes& codes, uint32_t n_seq, const uint32_t* off, const char* flat, TargetDeviceTable& T,
                                   uint64_t* launches, std::string& err);
 
+// MGF text parsed on the device (pq_mgf.cu): work buffers kept in the context so that a second file allocates nothing
+struct MgfDeviceWork { DevBuf text, line_pos, type, delta, incl, pflag, pidx, hard, tmp, scal; std::vector<cudaEvent_t> ev; };
+struct ByteToU64 { __host__ __device__ uint64_t operator()(uint8_t b) const { return b; } };
+bool parse_mgf_on_device(cudaStream_t st, cudaStream_t sc, const char* text, uint64_t n_bytes, MgfDeviceWork& W, DevBuf& d_prec, DevBuf& d_charge,
+                         DevBuf& d_off, DevBuf& d_mz, DevBuf& d_in, int64_t* n_spectra, uint64_t* n_peaks, uint64_t* launches, std::string& err);
+
 // commons-math 2 MathUtils tables (A12): log10(n!) for n <= 64 and ln(n!) for n < count
 void factorial_tables(double* log10_fact65, std::vector<double>& ln_fact, int count);
 

@@ -310,3 +310,228 @@ extern "C" int32_t pq_read_ms_library(const char* dir, double mass_lo, double ma
     *n_spectra = ns; *n_peaks = np; *title_bytes = tb;
     return PQ_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// MGF text parsed ON THE DEVICE.  The text crosses PCIe in chunks; while later chunks are still on their way the
+// line starts of the chunks that have arrived are selected (cub).  Then, over the whole text at once: one thread per line
+// classifies it (peak line / BEGIN IONS / END IONS / PEPMASS= / CHARGE= / other), two prefix scans give every line its spectrum
+// and every peak line its peak index, and one thread per line writes its numbers straight into the caller-order CSR arrays on
+// the device.  Numbers take Clinger's exact fast path in FP64 — at most 18 digits collected in an integer below 2^53, one
+// correctly rounded IEEE division by an exactly representable power of ten (__ddiv_rn) — which gives the same double as strtod
+// / Double.parseDouble; the rare number of another shape (exponent, > 18 digits, "inf") is left to the host's strtod and
+// patched in afterwards.  Blocks must be well formed (every BEGIN IONS closed by END IONS): anything else is refused and the
+// caller takes the host parser.
+#include <cub/cub.cuh>
+
+#include "pq_host.h"
+
+namespace pq {
+namespace {
+
+enum : uint8_t { kLineOther = 0, kLinePeak = 1, kLineBegin = 2, kLineEnd = 3, kLinePepmass = 4, kLineCharge = 5 };
+
+struct GlobalLineStart {        // is the byte at global offset g the first of a line?  lo = first byte of the chunk (chunks begin at line starts)
+    const char* text; uint64_t lo;
+    __host__ __device__ bool operator()(uint64_t g) const { return g == lo || text[g - 1] == '\n'; }
+};
+struct AddBase { uint64_t base; __host__ __device__ uint64_t operator()(uint64_t i) const { return base + i; } };
+
+__device__ __forceinline__ bool d_blank(char c) { return c == ' ' || c == '\t' || c == '\r'; }
+
+__global__ void k_mgf_classify(const char* __restrict__ text, uint64_t n_bytes, const uint64_t* __restrict__ line_pos, uint64_t n_lines,
+                               uint8_t* __restrict__ type, int2* __restrict__ delta /* x: +1 BEGIN, y: +1 BEGIN / -1 END */) {
+    uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lines) return;
+    uint64_t p = line_pos[l];
+    const uint64_t end = l + 1 < n_lines ? line_pos[l + 1] : n_bytes;
+    while (p < end && d_blank(text[p])) ++p;
+    uint8_t t = kLineOther;
+    if (p < end) {
+        const char c = text[p];
+        const uint64_t len = end - p;
+        auto is = [&](const char* w, int n) { if (len < (uint64_t)n) return false; for (int i = 0; i < n; ++i) if (text[p + i] != w[i]) return false; return true; };
+        if ((c >= '0' && c <= '9') || (c == '.' && len > 1 && text[p + 1] >= '0' && text[p + 1] <= '9')) t = kLinePeak;
+        else if (c == 'B' && is("BEGIN IONS", 10)) t = kLineBegin;
+        else if (c == 'E' && is("END IONS", 8)) t = kLineEnd;
+        else if (c == 'P' && is("PEPMASS=", 8)) t = kLinePepmass;
+        else if (c == 'C' && is("CHARGE=", 7)) t = kLineCharge;
+    }
+    type[l] = t;
+    delta[l] = make_int2(t == kLineBegin ? 1 : 0, t == kLineBegin ? 1 : (t == kLineEnd ? -1 : 0));
+}
+struct AddInt2 { __host__ __device__ int2 operator()(const int2& a, const int2& b) const { return make_int2(a.x + b.x, a.y + b.y); } };
+
+// peak lines inside a block; the block state must stay in {0, 1}
+__global__ void k_mgf_peak_flags(const uint8_t* __restrict__ type, const int2* __restrict__ incl, uint64_t n_lines, uint8_t* __restrict__ pflag, uint32_t* __restrict__ bad) {
+    uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lines) return;
+    const int st = incl[l].y;
+    if (st < 0 || st > 1) atomicAdd(bad, 1u);
+    pflag[l] = (type[l] == kLinePeak && st == 1) ? 1 : 0;
+}
+
+// digits [. digits] with at most 18 digits, below 2^53, ended by a blank or the end of the line: value, next position.  false: another shape.
+__device__ __forceinline__ bool d_fast_number(const char* __restrict__ text, uint64_t& p, uint64_t end, double& v) {
+    const double pow10[19] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18};
+    uint64_t q = p; unsigned long long m = 0; int nd = 0, frac = 0;
+    while (q < end) { const unsigned d = (unsigned)(text[q] - '0'); if (d > 9u) break; m = m * 10ull + d; ++nd; ++q; }
+    if (q < end && text[q] == '.') {
+        ++q; const uint64_t f0 = q;
+        while (q < end) { const unsigned d = (unsigned)(text[q] - '0'); if (d > 9u) break; m = m * 10ull + d; ++q; }
+        frac = (int)(q - f0); nd += frac;
+    }
+    if (nd == 0 || nd > 18 || m >= (1ull << 53)) return false;
+    if (q < end) { const char c = text[q]; if (c != ' ' && c != '\t' && c != '\r' && c != '\n') return false; }
+    v = frac ? __ddiv_rn((double)m, pow10[frac]) : (double)m;
+    p = q;
+    return true;
+}
+
+struct HardNumber { uint64_t pos; uint64_t slot; uint32_t what; uint32_t pad; };      // what: 0 m/z, 1 intensity, 2 precursor m/z
+
+__global__ void k_mgf_fill(const char* __restrict__ text, uint64_t n_bytes, const uint64_t* __restrict__ line_pos, uint64_t n_lines,
+                           const uint8_t* __restrict__ type, const int2* __restrict__ incl, const uint8_t* __restrict__ pflag,
+                           const uint64_t* __restrict__ pidx, double* __restrict__ prec, int32_t* __restrict__ charge, uint64_t* __restrict__ off,
+                           double* __restrict__ mz, double* __restrict__ inten, HardNumber* __restrict__ hard, uint32_t* __restrict__ n_hard, uint32_t hard_cap) {
+    uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lines) return;
+    const uint8_t t = type[l];
+    if (t == kLineOther || t == kLineEnd) return;
+    uint64_t p = line_pos[l];
+    const uint64_t end = l + 1 < n_lines ? line_pos[l + 1] : n_bytes;
+    while (p < end && d_blank(text[p])) ++p;
+    const int64_t s = (int64_t)incl[l].x - 1;                       // spectrum of this line (index of the last BEGIN at or before it)
+    auto defer = [&](uint64_t pos, uint64_t slot, uint32_t what) { uint32_t k = atomicAdd(n_hard, 1u); if (k < hard_cap) hard[k] = HardNumber{pos, slot, what, 0u}; };
+    if (t == kLineBegin) { off[s] = pidx[l]; return; }
+    if (incl[l].y != 1 || s < 0) return;                            // outside a block
+    if (t == kLinePepmass) { uint64_t q = p + 8; while (q < end && (text[q] == ' ' || text[q] == '\t')) ++q; double v; if (d_fast_number(text, q, end, v)) prec[s] = v; else defer(p + 8, (uint64_t)s, 2u); return; }
+    if (t == kLineCharge) {
+        uint64_t q = p + 7; while (q < end && (text[q] == ' ' || text[q] == '\t')) ++q;
+        bool neg = false; if (q < end && (text[q] == '+' || text[q] == '-')) { neg = text[q] == '-'; ++q; }
+        int z = 0; while (q < end && (unsigned)(text[q] - '0') <= 9u && z < 100000) { z = z * 10 + (text[q] - '0'); ++q; }
+        (void)neg; charge[s] = z;                                   // "2+" -> 2, "2-" -> 2 (pq_parse_mgf takes the magnitude too)
+        return;
+    }
+    if (!pflag[l]) return;
+    const uint64_t k = pidx[l];
+    double a = 0.0, b = 0.0;
+    uint64_t q = p;
+    if (!d_fast_number(text, q, end, a)) { defer(p, k, 0u); defer(p, k, 1u); return; }      // the host parses the whole line
+    while (q < end && (text[q] == ' ' || text[q] == '\t')) ++q;
+    if (q < end && text[q] != '\r' && text[q] != '\n') { uint64_t q2 = q; if (!d_fast_number(text, q2, end, b)) { b = 0.0; defer(p, k, 1u); } }
+    mz[k] = a; inten[k] = b;
+}
+
+#define RB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
+
+}  // namespace
+
+bool parse_mgf_on_device(cudaStream_t st, cudaStream_t sc, const char* text, uint64_t n_bytes, MgfDeviceWork& W, DevBuf& d_prec, DevBuf& d_charge,
+                         DevBuf& d_off, DevBuf& d_mz, DevBuf& d_in, int64_t* n_spectra, uint64_t* n_peaks, uint64_t* launches, std::string& err) {
+    *n_spectra = 0; *n_peaks = 0;
+    if (n_bytes == 0) return true;
+    RB(W.text.reserve(n_bytes + 16));
+    char* d_text = W.text.as<char>();
+    // upper bound of the line count: a line is at least one byte; in practice ~16 bytes — reserve for n_bytes / 2 + 1 lines (a text of
+    // empty lines only would need more and is refused)
+    const uint64_t line_cap = n_bytes / 2 + 16;
+    RB(W.line_pos.reserve(line_cap * 8)); RB(W.scal.reserve(256));
+    RB(cudaMemsetAsync(W.scal.p, 0, 256, st));
+    const uint64_t chunk = 64ull << 20;
+    std::vector<uint64_t> cuts; cuts.push_back(0);
+    while (cuts.back() < n_bytes) {                                  // chunks end at a line end
+        uint64_t e = std::min(n_bytes, cuts.back() + chunk);
+        if (e < n_bytes) { const char* nl = (const char*)memchr(text + e, '\n', (size_t)(n_bytes - e)); e = nl ? (uint64_t)(nl - text) + 1 : n_bytes; }
+        cuts.push_back(e);
+    }
+    const size_t nc = cuts.size() - 1;
+    while (W.ev.size() < nc) { cudaEvent_t e; RB(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); W.ev.push_back(e); }
+    for (size_t c = 0; c < nc; ++c) {
+        RB(cudaMemcpyAsync(d_text + cuts[c], text + cuts[c], cuts[c + 1] - cuts[c], cudaMemcpyHostToDevice, sc));
+        RB(cudaEventRecord(W.ev[c], sc));
+    }
+    uint64_t n_lines = 0;
+    uint64_t* d_num = reinterpret_cast<uint64_t*>(W.scal.as<uint8_t>() + 64);
+    for (size_t c = 0; c < nc; ++c) {
+        RB(cudaStreamWaitEvent(st, W.ev[c], 0));
+        const uint64_t len = cuts[c + 1] - cuts[c];
+        if (n_lines + len / 1 > line_cap && n_lines + 16 > line_cap) { err = "too many lines for the reserved work space"; return false; }
+        cub::CountingInputIterator<uint64_t> iota(0);
+        cub::TransformInputIterator<uint64_t, AddBase, cub::CountingInputIterator<uint64_t>> pos_it(iota, AddBase{cuts[c]});
+        // select the global offsets of the line starts of this chunk
+        size_t bytes = 0;
+        GlobalLineStart gs{d_text, cuts[c]};
+        cub::DeviceSelect::If(nullptr, bytes, pos_it, W.line_pos.as<uint64_t>() + n_lines, d_num, (int64_t)len, gs, st);
+        RB(W.tmp.reserve(bytes + 64));
+        RB(cub::DeviceSelect::If(W.tmp.p, bytes, pos_it, W.line_pos.as<uint64_t>() + n_lines, d_num, (int64_t)len, gs, st));
+        uint64_t got = 0;
+        RB(cudaMemcpyAsync(&got, d_num, 8, cudaMemcpyDeviceToHost, st));
+        RB(cudaStreamSynchronize(st));
+        n_lines += got;
+        *launches += 3;
+        if (n_lines > line_cap) { err = "too many lines for the reserved work space"; return false; }
+    }
+    if (n_lines == 0) return true;
+    // classify, scan, count
+    RB(W.type.reserve(n_lines + 64)); RB(W.delta.reserve(n_lines * 8)); RB(W.incl.reserve(n_lines * 8)); RB(W.pflag.reserve(n_lines + 64)); RB(W.pidx.reserve((n_lines + 1) * 8));
+    const unsigned nb = (unsigned)((n_lines + 255) / 256);
+    k_mgf_classify<<<nb, 256, 0, st>>>(d_text, n_bytes, W.line_pos.as<uint64_t>(), n_lines, W.type.as<uint8_t>(), W.delta.as<int2>());
+    {
+        size_t bytes = 0;
+        cub::DeviceScan::InclusiveScan(nullptr, bytes, W.delta.as<int2>(), W.incl.as<int2>(), AddInt2(), (int64_t)n_lines, st);
+        RB(W.tmp.reserve(bytes + 64));
+        RB(cub::DeviceScan::InclusiveScan(W.tmp.p, bytes, W.delta.as<int2>(), W.incl.as<int2>(), AddInt2(), (int64_t)n_lines, st));
+    }
+    uint32_t* d_bad = W.scal.as<uint32_t>();
+    k_mgf_peak_flags<<<nb, 256, 0, st>>>(W.type.as<uint8_t>(), W.incl.as<int2>(), n_lines, W.pflag.as<uint8_t>(), d_bad);
+    {
+        size_t bytes = 0;
+        cub::TransformInputIterator<uint64_t, ByteToU64, const uint8_t*> pf(W.pflag.as<uint8_t>(), ByteToU64());
+        cub::DeviceScan::ExclusiveSum(nullptr, bytes, pf, W.pidx.as<uint64_t>(), (int64_t)n_lines + 1, st);
+        RB(W.tmp.reserve(bytes + 64));
+        RB(cub::DeviceScan::ExclusiveSum(W.tmp.p, bytes, pf, W.pidx.as<uint64_t>(), (int64_t)n_lines + 1, st));
+    }
+    struct { uint32_t bad; } hb = {0}; int2 last = make_int2(0, 0); uint64_t np = 0;
+    RB(cudaMemcpyAsync(&hb, d_bad, 4, cudaMemcpyDeviceToHost, st));
+    RB(cudaMemcpyAsync(&last, W.incl.as<int2>() + (n_lines - 1), 8, cudaMemcpyDeviceToHost, st));
+    RB(cudaMemcpyAsync(&np, W.pidx.as<uint64_t>() + n_lines, 8, cudaMemcpyDeviceToHost, st));
+    RB(cudaStreamSynchronize(st));
+    *launches += 6;
+    if (hb.bad || last.y != 0) { err = "malformed MGF blocks (a BEGIN IONS without its END IONS, or the reverse)"; return false; }
+    const int64_t ns = last.x;
+    *n_spectra = ns; *n_peaks = np;
+    if (ns == 0) return true;
+    RB(d_prec.reserve((size_t)ns * 8)); RB(d_charge.reserve((size_t)ns * 4)); RB(d_off.reserve(((size_t)ns + 1) * 8));
+    RB(d_mz.reserve(std::max<uint64_t>(np, 1) * 8)); RB(d_in.reserve(std::max<uint64_t>(np, 1) * 8));
+    RB(cudaMemsetAsync(d_prec.p, 0, (size_t)ns * 8, st)); RB(cudaMemsetAsync(d_charge.p, 0, (size_t)ns * 4, st));
+    const uint32_t hard_cap = 1u << 20;
+    RB(W.hard.reserve((size_t)hard_cap * sizeof(HardNumber)));
+    uint32_t* d_nhard = W.scal.as<uint32_t>() + 4;
+    k_mgf_fill<<<nb, 256, 0, st>>>(d_text, n_bytes, W.line_pos.as<uint64_t>(), n_lines, W.type.as<uint8_t>(), W.incl.as<int2>(), W.pflag.as<uint8_t>(), W.pidx.as<uint64_t>(),
+                                   d_prec.as<double>(), d_charge.as<int32_t>(), d_off.as<uint64_t>(), d_mz.as<double>(), d_in.as<double>(),
+                                   W.hard.as<HardNumber>(), d_nhard, hard_cap);
+    RB(cudaMemcpyAsync(d_off.as<uint64_t>() + ns, &np, 8, cudaMemcpyHostToDevice, st));
+    uint32_t n_hard = 0;
+    RB(cudaMemcpyAsync(&n_hard, d_nhard, 4, cudaMemcpyDeviceToHost, st));
+    RB(cudaStreamSynchronize(st));
+    RB(cudaGetLastError());
+    *launches += 2;
+    if (n_hard > hard_cap) { err = "too many numbers outside the fast path for the device parser"; return false; }
+    if (n_hard) {                                                    // the host's strtod decides the rare number of another shape
+        std::vector<HardNumber> h(n_hard);
+        RB(cudaMemcpyAsync(h.data(), W.hard.p, (size_t)n_hard * sizeof(HardNumber), cudaMemcpyDeviceToHost, st));
+        RB(cudaStreamSynchronize(st));
+        const char* end = text + n_bytes;
+        for (const HardNumber& x : h) {
+            const char* p = text + x.pos; const char* eol = (const char*)memchr(p, '\n', (size_t)(end - p)); if (!eol) eol = end;
+            const char* e1 = p; double a = ::parse_double(p, eol, &e1), v = a;
+            if (x.what == 1) { const char* t = e1; while (t < eol && (*t == ' ' || *t == '\t')) ++t; const char* e2 = t; double b = t < eol ? ::parse_double(t, eol, &e2) : 0.0; v = (e2 != t) ? b : 0.0; }
+            double* dst = x.what == 2 ? d_prec.as<double>() + x.slot : (x.what == 0 ? d_mz.as<double>() + x.slot : d_in.as<double>() + x.slot);
+            RB(cudaMemcpyAsync(dst, &v, 8, cudaMemcpyHostToDevice, st));
+            RB(cudaStreamSynchronize(st));
+        }
+    }
+    return true;
+}
+
+}  // namespace pq

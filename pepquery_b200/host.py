@@ -54,7 +54,7 @@ def load_library():
 
 
 # every symbol include/pepquery_b200.h declares
-EXPORTS = ["pq_version", "pq_last_error", "pq_default_params", "pq_create", "pq_destroy", "pq_load_spectra",
+EXPORTS = ["pq_version", "pq_last_error", "pq_default_params", "pq_create", "pq_destroy", "pq_load_spectra", "pq_load_mgf", "pq_parse_mgf_device",
            "pq_set_targets", "pq_set_targeted_psms", "pq_get_targeted_psm_status", "pq_get_target_forms", "pq_build_reference", "pq_stage_reference", "pq_get_reference_forms",
            "pq_step2_match_targets", "pq_step3_competitors", "pq_step4_shuffles", "pq_rank_and_validate",
            "pq_step5_ptm", "pq_get_psms", "pq_get_delta_scores", "pq_export_psms_device", "pq_get_competitors", "pq_get_shuffles", "pq_score_pairs",
@@ -121,6 +121,28 @@ class Search:
         n = len(sp["prec_mz"])
         self._ck(self.L.pq_load_spectra(self.h, C.c_int64(n), _p(sp["prec_mz"]), _p(sp["charge"]), _p(sp["peak_off"]),
                                         _p(sp["mz"]), _p(sp["inten"])))
+
+    def load_mgf(self, text):
+        """MGF text (bytes / uint8 array, e.g. in pinned memory) parsed on the device and loaded; -> number of spectra."""
+        n = C.c_int64()
+        if isinstance(text, (bytes, bytearray)):
+            self._ck(self.L.pq_load_mgf(self.h, text, C.c_uint64(len(text)), C.byref(n)))
+        else:
+            self._ck(self.L.pq_load_mgf(self.h, _p(text), C.c_uint64(text.nbytes), C.byref(n)))
+        return n.value
+
+    def parse_mgf_device(self, text):
+        """pq_parse_mgf_device: MGF text parsed on the GPU -> CSR dict on the host."""
+        raw = text if isinstance(text, (bytes, bytearray)) else None
+        ptr = raw if raw is not None else _p(text)
+        nb = len(raw) if raw is not None else text.nbytes
+        ns, npk = C.c_int64(0), C.c_uint64(0)
+        self._ck(self.L.pq_parse_mgf_device(self.h, ptr, C.c_uint64(nb), C.byref(ns), C.byref(npk), None, None, None, None, None))
+        sp = dict(prec_mz=np.zeros(ns.value), charge=np.zeros(ns.value, dtype=np.int32), peak_off=np.zeros(ns.value + 1, dtype=np.uint64),
+                  mz=np.zeros(npk.value), inten=np.zeros(npk.value))
+        self._ck(self.L.pq_parse_mgf_device(self.h, ptr, C.c_uint64(nb), C.byref(ns), C.byref(npk), _p(sp["prec_mz"]), _p(sp["charge"]), _p(sp["peak_off"]),
+                                            _p(sp["mz"]), _p(sp["inten"])))
+        return sp
 
     def set_targets(self, off, res):
         self._ck(self.L.pq_set_targets(self.h, C.c_int32(len(off) - 1), _p(off), _p(res)))

@@ -138,3 +138,17 @@ def planted_targets(prot, rng):
     off = np.zeros(len(seqs) + 1, dtype=np.uint32); off[1:] = np.cumsum([len(s) for s in seqs])
     res = np.frombuffer("".join(seqs).encode(), dtype=np.uint8).copy()
     return off, res, want
+
+
+def mgf_text(sp, out=None, threads=0):
+    """The spectra as MGF text in the reference's own form (IndexWorker.asMgf); the synthetic precursor m/z carry five decimals and
+    the peaks four / two, so parsing the text gives the arrays back bit for bit.  out: optional callable (nbytes) -> uint8 array
+    (e.g. pinned memory) to receive the text.  -> uint8 array."""
+    L = _lib()
+    L.syn_mgf_build.restype = C.c_int64; L.syn_mgf_copy.restype = C.c_int64
+    n = len(sp["prec_mz"])
+    size = L.syn_mgf_build(C.c_int64(n), _p(sp["prec_mz"]), _p(sp["charge"]), _p(sp["peak_off"]), _p(sp["mz"]), _p(sp["inten"]), C.c_int32(threads))
+    buf = out(size) if out is not None else np.empty(size, dtype=np.uint8)
+    got = L.syn_mgf_copy(_p(buf), C.c_int64(size))
+    assert got == size
+    return buf[:size]

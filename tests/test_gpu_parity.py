@@ -1056,3 +1056,73 @@ def test_targeted_psms_and_their_status(data):
     # clearing the list gives the unrestricted search back
     g.set_targeted_psms([], []); g.step2(); g.build_reference(*prot); g.step3(); g.step4(); g.rank()
     assert_psms_equal(g.psms(), base)
+
+
+def _dirty_mgf(sp):
+    """MGF text with everything a real file may carry: CRLF and blank lines, comments, header lines before the first block, extra keys,
+    numbers outside the fast path (exponents, 19+ digits, leading '.', '+' signs), a missing intensity, a block without CHARGE."""
+    import io
+    off = sp["peak_off"]; out = io.StringIO()
+    out.write("# produced by a test\nCOM=hello\n\nMASS=Monoisotopic\n")
+    for i in range(len(sp["prec_mz"])):
+        eol = "\r\n" if i % 5 == 0 else "\n"
+        out.write("BEGIN IONS" + eol + ("TITLE=t %d" % i) + eol)
+        if i % 7 == 3:
+            out.write("PEPMASS=%.17e" % sp["prec_mz"][i] + eol)            # exponent notation: the host's strtod decides
+        else:
+            out.write("PEPMASS=%r 12345.6" % float(sp["prec_mz"][i]) + eol)
+        if i % 11 != 4:
+            out.write(("CHARGE=%d+" % sp["charge"][i]) + (" and 5+" if i % 13 == 0 else "") + eol)
+        out.write("RTINSECONDS=12.5" + eol + "SCANS=%d" % i + eol)
+        a, b = int(off[i]), int(off[i + 1])
+        for k in range(a, b):
+            m, v = float(sp["mz"][k]), float(sp["inten"][k])
+            j = k - a
+            if j % 19 == 0: out.write("%.4f\t%.2f  " % (m, v) + eol)              # tab, trailing blanks
+            elif j % 23 == 1: out.write("%.12e %.2f" % (m, v) + eol)              # exponent
+            elif j % 29 == 2: out.write("%.4f" % m + eol)                         # no intensity
+            elif j % 31 == 3: out.write("%.20f %.2f" % (m, v) + eol)              # more than 18 digits
+            elif j % 37 == 4: out.write("  %.4f %.2f" % (m, v) + eol)             # leading blanks
+            else: out.write("%.4f %.2f" % (m, v) + eol)
+        if i % 17 == 0: out.write(".5 3" + eol + "\n")                            # leading '.'
+        out.write("END IONS" + eol + eol)
+    return out.getvalue().encode()
+
+
+def test_mgf_text_parsed_on_the_device(data):
+    """pq_parse_mgf_device / pq_load_mgf: every number equals the host parser's (= strtod = Double.parseDouble), the structure
+    (spectra, offsets, charges) is the same, a search from the text equals the search from the arrays; malformed blocks are refused."""
+    from pepquery_b200 import host
+    prot, tgt, sp = data
+    p = _abi.default_params(n_random=50)
+    g = Search(p)
+    for text in (bytes(synth.mgf_text(sp)), _dirty_mgf(sp)):
+        want = host.parse_mgf(text)
+        got = g.parse_mgf_device(text)
+        for k in ("prec_mz", "charge", "peak_off", "mz", "inten"):
+            assert np.array_equal(got[k], want[k]), k
+        assert len(want["prec_mz"]) == len(sp["prec_mz"])
+    assert np.array_equal(g.parse_mgf_device(bytes(synth.mgf_text(sp)))["mz"], sp["mz"])
+    # search from text == search from arrays (targets first: candidate-first gather from the parsed peaks on the device, search at load)
+    text = _dirty_mgf(sp)
+    want_sp = host.parse_mgf(text)
+    o = run_oracle(p, want_sp, tgt, prot)
+    for staged in (False, True):
+        a = Search(p)
+        a.set_targets(*tgt)
+        if staged:
+            a.stage_reference(*prot)
+        n = a.load_mgf(text)
+        assert n == len(want_sp["prec_mz"])
+        a.step2()
+        a.build_reference() if staged else a.build_reference(*prot)
+        a.step3(); a.step4(); a.rank()
+        assert_psms_equal(a.psms(), o.psms())
+    b = Search(p); assert b.load_mgf(text) == n; b.set_targets(*tgt); b.step2(); b.build_reference(*prot); b.step3(); b.step4(); b.rank()      # text first, targets later: full residency
+    assert_psms_equal(b.psms(), o.psms())
+    # empty text, text without blocks, malformed blocks
+    assert g.load_mgf(b"") == 0 and g.load_mgf(b"# nothing here\n\n") == 0
+    for bad in (b"BEGIN IONS\nPEPMASS=500\n100 1\nBEGIN IONS\nPEPMASS=600\n100 1\nEND IONS\n", b"END IONS\nBEGIN IONS\nEND IONS\n", b"BEGIN IONS\nPEPMASS=500\n100 1\n"):
+        with pytest.raises(PepQueryError) as ei:
+            g.load_mgf(bad)
+        assert ei.value.code == _abi.PQ_ERR_BAD_ARG

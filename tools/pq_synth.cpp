@@ -262,4 +262,39 @@ int64_t syn_spectra(int64_t n, uint64_t seed, int64_t first_index, double mass_l
     return (int64_t)peak_off[n];
 }
 
+
+// MGF text of a CSR spectrum set in the reference's own form (index/IndexWorker.asMgf, IndexWorker.java:431-457): one block per
+// spectrum, peaks as "%.4f %.2f".  Built by `threads` threads into a buffer the library owns: syn_mgf_build returns its size,
+// syn_mgf_copy copies it out and frees it.
+static std::vector<std::string> g_mgf_parts;
+int64_t syn_mgf_build(int64_t n, const double* prec_mz, const int32_t* charge, const uint64_t* off, const double* mz, const double* inten, int32_t threads) {
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = 1;
+    g_mgf_parts.assign((size_t)threads, std::string());
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) th.emplace_back([&, t]() {
+        std::string& out = g_mgf_parts[(size_t)t];
+        const int64_t a = n * t / threads, b = n * (t + 1) / threads;
+        out.reserve((size_t)((off[b] - off[a]) * 18 + (uint64_t)(b - a) * 96));
+        char buf[128];
+        for (int64_t i = a; i < b; ++i) {
+            int k = snprintf(buf, sizeof buf, "BEGIN IONS\nTITLE=syn:%lld:%d\nPEPMASS=%.5f 1.0\n", (long long)(i + 1), (int)charge[i], prec_mz[i]);
+            out.append(buf, (size_t)k);
+            if (charge[i] > 0) { k = snprintf(buf, sizeof buf, "CHARGE=%d+\n", (int)charge[i]); out.append(buf, (size_t)k); }
+            for (uint64_t p = off[i]; p < off[i + 1]; ++p) { k = snprintf(buf, sizeof buf, "%.4f %.2f\n", mz[p], inten[p]); out.append(buf, (size_t)k); }
+            out.append("END IONS\n\n");
+        }
+    });
+    for (auto& t : th) t.join();
+    int64_t total = 0;
+    for (auto& s2 : g_mgf_parts) total += (int64_t)s2.size();
+    return total;
+}
+int64_t syn_mgf_copy(char* dst, int64_t cap) {
+    int64_t w = 0;
+    for (auto& s2 : g_mgf_parts) { if (w + (int64_t)s2.size() > cap) return -1; memcpy(dst + w, s2.data(), s2.size()); w += (int64_t)s2.size(); }
+    g_mgf_parts.clear(); g_mgf_parts.shrink_to_fit();
+    return w;
+}
+
 }  // extern "C"
