@@ -334,6 +334,7 @@ struct GlobalLineStart {        // is the byte at global offset g the first of a
     const char* text; uint64_t lo;
     __host__ __device__ bool operator()(uint64_t g) const { return g == lo || text[g - 1] == '\n'; }
 };
+struct IsNewline { const char* text; __host__ __device__ uint64_t operator()(uint64_t g) const { return text[g] == '\n' ? 1ull : 0ull; } };
 struct AddBase { uint64_t base; __host__ __device__ uint64_t operator()(uint64_t i) const { return base + i; } };
 
 __device__ __forceinline__ bool d_blank(char c) { return c == ' ' || c == '\t' || c == '\r'; }
@@ -455,9 +456,19 @@ bool parse_mgf_on_device(cudaStream_t st, cudaStream_t sc, const char* text, uin
     for (size_t c = 0; c < nc; ++c) {
         RB(cudaStreamWaitEvent(st, W.ev[c], 0));
         const uint64_t len = cuts[c + 1] - cuts[c];
-        if (n_lines + len / 1 > line_cap && n_lines + 16 > line_cap) { err = "too many lines for the reserved work space"; return false; }
         cub::CountingInputIterator<uint64_t> iota(0);
         cub::TransformInputIterator<uint64_t, AddBase, cub::CountingInputIterator<uint64_t>> pos_it(iota, AddBase{cuts[c]});
+        {   // the chunk's line count first: the select below must not write past the reserved positions (a text of very short lines)
+            cub::TransformInputIterator<uint64_t, IsNewline, decltype(pos_it)> nl_it(pos_it, IsNewline{d_text});
+            size_t bytes = 0;
+            cub::DeviceReduce::Sum(nullptr, bytes, nl_it, d_num, (int64_t)len, st);
+            RB(W.tmp.reserve(bytes + 64));
+            RB(cub::DeviceReduce::Sum(W.tmp.p, bytes, nl_it, d_num, (int64_t)len, st));
+            uint64_t nl = 0;
+            RB(cudaMemcpyAsync(&nl, d_num, 8, cudaMemcpyDeviceToHost, st));
+            RB(cudaStreamSynchronize(st));
+            if (n_lines + nl + 1 > line_cap) { err = "too many lines for the reserved work space (lines shorter than two bytes on average)"; return false; }
+        }
         // select the global offsets of the line starts of this chunk
         size_t bytes = 0;
         GlobalLineStart gs{d_text, cuts[c]};
