@@ -412,6 +412,7 @@ def main():
             g.step2(); g.step3(); g.step4()
             return gather_psms(g)
         g.step3(); g.step4(); g.rank()
+        g.ms_ladder_once = g.counters().ms_ladder        # fragment-ladder tables of the reference rows: built with the table, not per step
         size_gather_buffers(g)
         for _ in range(max(warm, 1)):
             step()
@@ -476,7 +477,8 @@ def main():
                                         "physical DRAM bytes (ncu dram__bytes_read+write of this launch) over the live launch time"},
                 "profile": prof.get("source") if prof else "no committed ncu capture for this workload: traffic / issue not reported"}
     kernel_ms = {"k1_step2": c.ms_score_step[0] / a.steps, "k1_step3": c.ms_score_step[1] / a.steps, "k1_step4": k1_ms,
-                 "k0_prepare+pack": c.ms_prepare / a.steps, "k3_window": c.ms_window / a.steps, "k2_shuffle": c.ms_shuffle / a.steps}
+                 "k0_prepare+pack": c.ms_prepare / a.steps, "k3_window": c.ms_window / a.steps, "k2_shuffle": c.ms_shuffle / a.steps,
+                 "k1_ladder_tables_once": g.ms_ladder_once}
     bounded_step = float(c.pairs_step4_bounded) / a.steps
     g.close()
 

@@ -206,6 +206,7 @@ typedef struct pq_counters {
     double   ms_host_reference;         /* wall time of the reference-table build (digest + forms + upload)      */
     uint64_t pairs_step4_bounded;       /* Step-4 pairs decided by the score upper bound (subset of pairs_step4)   */
     uint64_t pairs_step5_bounded;       /* Step-5 pairs decided by the score upper bound (subset of pairs_step5)   */
+    double   ms_ladder;                 /* fragment-ladder tables of the reference rows (built once per reference table, read by Step 3) */
 } pq_counters;
 
 typedef struct pq_ctx pq_ctx;

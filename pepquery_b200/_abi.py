@@ -87,7 +87,8 @@ class pq_counters(C.Structure):
                 ("ms_shuffle", C.c_double), ("ms_total", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("ms_score_step", C.c_double * 4), ("bytes_score_step", C.c_uint64 * 4),
-                ("ms_host_reference", C.c_double), ("pairs_step4_bounded", C.c_uint64), ("pairs_step5_bounded", C.c_uint64)]
+                ("ms_host_reference", C.c_double), ("pairs_step4_bounded", C.c_uint64), ("pairs_step5_bounded", C.c_uint64),
+                ("ms_ladder", C.c_double)]
 
 
 # Modification constants pinned by the reference's resources/top_modifications.tsv (ids = -fixMod/-varMod numbers)

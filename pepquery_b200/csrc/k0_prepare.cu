@@ -633,6 +633,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             const uint16_t first = __ldcg(g_cells), last = __ldcg(g_cells + kCells - 1);
             if (!(first & kCellClean) && (last & kCellClean)) g_cells[kCells - 1] = (uint16_t)(last & ~kCellClean);
         }
+        if (lane == 1) *reinterpret_cast<uint4*>(g_cells + kCells) = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);      // the sentinel: always clean
         if (METHOD == 1) for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = k < nsurv ? val[k] : 0.0;
         else for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = 0.0;
         if (lane == 0) {

@@ -91,6 +91,48 @@ struct Extra { int32_t site; double delta; };   // Step 5: one extra modificatio
 
 struct PairScore { double score; int32_t a, b; };
 
+// The score from what the claims left behind (shared by the ladder-walking scorer below and the table-driven one of k1_ladder.cu).
+// METHOD 1: HyperscoreMatch.java:150-179; METHOD 2: MVHMatch.java:281-299.
+template <int METHOD>
+__device__ __forceinline__ PairScore finish_pair(const BlobView& B, int ca, int cb, double sum, int key0, int key1, int key2, int32_t predicted,
+                                                 const double* log10_fact, const double* ln_fact) {
+    PairScore r;
+    if (METHOD == 1) {
+        if (ca > 64) ca = 64;
+        if (cb > 64) cb = 64;
+        r.a = ca; r.b = cb;
+        if (ca == 0 && cb == 0) { r.score = 0.0; return r; }
+        double hs = jlog10(sum);
+        if (ca > 0 && cb > 0) hs = __dadd_rn(__dadd_rn(hs, log10_fact[ca]), log10_fact[cb]);
+        else if (cb > 0) hs = __dadd_rn(hs, log10_fact[cb]);
+        else hs = __dadd_rn(hs, log10_fact[ca]);
+        r.score = __dmul_rn(4.0, hs);
+    } else {
+        int matched = key0 + key1 + key2;
+        r.a = matched; r.b = predicted;
+        r.score = 0.0;
+        if (!(B.flags & 1u)) { r.a = 0; r.b = 0; return r; }     // fewer than 7 peaks survived: calcMVH returns before scoring
+        if (predicted <= 0) return r;
+        int key[4] = {key0, key1, key2, predicted - matched};
+        int N = (int)B.nsurv;
+        double mvh = 0.0; bool died = false;
+        for (int i = 0; i < 4; ++i) {
+            int n = B.cls[i], k = key[i];
+            if (n < 0 || k < 0) continue;
+            if (n < k) { died = true; continue; }
+            mvh = __dadd_rn(mvh, __dsub_rn(__dsub_rn(ln_fact[n], ln_fact[n - k]), ln_fact[k]));
+        }
+        int tb = B.cls[3] + N;
+        if (tb >= 0 && predicted >= 0) {
+            if (tb < predicted) died = true;
+            else mvh = __dsub_rn(mvh, __dsub_rn(__dsub_rn(ln_fact[tb], ln_fact[tb - predicted]), ln_fact[predicted]));
+        }
+        mvh = __dsub_rn(0.0, mvh);
+        r.score = died ? 0.0 : mvh;
+    }
+    return r;
+}
+
 template <int BLOCK>
 __device__ __forceinline__ uint32_t row_byte(const uint32_t* codes, int idx) {
     uint32_t w = codes[(idx >> 2) * BLOCK];
@@ -219,41 +261,7 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
     }
     flush();
 
-    PairScore r;
-    if (METHOD == 1) {
-        if (ca > 64) ca = 64;
-        if (cb > 64) cb = 64;
-        r.a = ca; r.b = cb;
-        if (ca == 0 && cb == 0) { r.score = 0.0; return r; }
-        double hs = jlog10(sum);
-        if (ca > 0 && cb > 0) hs = __dadd_rn(__dadd_rn(hs, log10_fact[ca]), log10_fact[cb]);
-        else if (cb > 0) hs = __dadd_rn(hs, log10_fact[cb]);
-        else hs = __dadd_rn(hs, log10_fact[ca]);
-        r.score = __dmul_rn(4.0, hs);
-    } else {
-        int matched = key0 + key1 + key2;
-        r.a = matched; r.b = predicted;
-        r.score = 0.0;
-        if (!(B.flags & 1u)) { r.a = 0; r.b = 0; return r; }     // fewer than 7 peaks survived: calcMVH returns before scoring
-        if (predicted <= 0) return r;
-        int key[4] = {key0, key1, key2, predicted - matched};
-        int N = (int)B.nsurv;
-        double mvh = 0.0; bool died = false;
-        for (int i = 0; i < 4; ++i) {
-            int n = B.cls[i], k = key[i];
-            if (n < 0 || k < 0) continue;
-            if (n < k) { died = true; continue; }
-            mvh = __dadd_rn(mvh, __dsub_rn(__dsub_rn(ln_fact[n], ln_fact[n - k]), ln_fact[k]));
-        }
-        int tb = B.cls[3] + N;
-        if (tb >= 0 && predicted >= 0) {
-            if (tb < predicted) died = true;
-            else mvh = __dsub_rn(mvh, __dsub_rn(__dsub_rn(ln_fact[tb], ln_fact[tb - predicted]), ln_fact[predicted]));
-        }
-        mvh = __dsub_rn(0.0, mvh);
-        r.score = died ? 0.0 : mvh;
-    }
-    return r;
+    return finish_pair<METHOD>(B, ca, cb, sum, key0, key1, key2, predicted, log10_fact, ln_fact);
 }
 
 template <int BLOCK, int METHOD, int TS = 1>

@@ -343,7 +343,9 @@ int launch_score(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) 
     if (L.n_jobs == 0) return 0;
     switch (L.kind) {
         case kJobShuffles: return launch_block<256>(L, cfg, st);
-        case kJobCompetitors: return launch_block<64>(L, cfg, st);
+        case kJobCompetitors:
+            if (L.lad && !getenv("PQ_STEP3_WALK")) return launch_score_ladder(L, cfg, st);
+            return launch_block<64>(L, cfg, st);
         case kJobTargets:
             if (!getenv("PQ_STEP2_STAGED")) return cfg.method == 2 ? launch_scatter<2>(L, cfg, st) : launch_scatter<1>(L, cfg, st);
             return launch_block<32>(L, cfg, st);

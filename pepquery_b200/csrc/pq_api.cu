@@ -39,6 +39,8 @@ struct PeptideTable {               // a mass-sorted candidate table resident on
     std::vector<FormRec> forms;     // mass ascending
     DevBuf rows, mass, pred, mask;
     bool have_mask = false;
+    DevBuf lad; uint32_t lad_stride = 0;   // precomputed fragment ladders of the rows (k1_ladder.cu), built before the first Step 3 over this table
+    bool have_lad = false;
     std::vector<double> h_mass;     // host copy for range searches
     RefDeviceTable dev;             // device-built table (reference only)
     bool device_built = false, materialized = true;
@@ -219,7 +221,7 @@ struct ScoreIO {
 };
 // run K1 over a job list; fills results (+hits)
 int32_t run_score_io(pq_ctx* ctx, const ScoreIO& io, JobKind kind, uint32_t n_jobs, const int32_t* row_pred, const uint8_t* rows, const double* row_mass,
-                     uint32_t hit_capacity, int check_window) {
+                     uint32_t hit_capacity, int check_window, const PeptideTable* ladders = nullptr) {
     CU(io.results->reserve(std::max<size_t>((size_t)n_jobs * sizeof(JobResult), 64)));
     CU(io.hits->reserve(std::max<size_t>((size_t)hit_capacity * sizeof(Hit), 64)));
     CU(io.hit_count->reserve(64));
@@ -233,6 +235,7 @@ int32_t run_score_io(pq_ctx* ctx, const ScoreIO& io, JobKind kind, uint32_t n_jo
     L.results = io.results->as<JobResult>(); L.hits = io.hits->as<Hit>(); L.hit_count = io.hit_count->as<uint32_t>();
     L.hit_capacity = hit_capacity; L.max_blob_bytes = ctx->max_blob; L.job_counter = io.job_counter;
     if (kind == kJobTargets) L.tgt = ctx->targeted_view();
+    if (kind == kJobCompetitors && ladders && ladders->have_lad) { L.lad = ladders->lad.as<uint4>(); L.lad_stride = ladders->lad_stride; }
     if (kind == kJobShuffles && ctx->have_lists) { L.sh_forms = ctx->sh_forms.as<ShuffleForm>(); L.form_slot = ctx->sh_form_slot.as<uint32_t>(); L.lists = ctx->sh_lists.as<uint4>(); }
     ScoreConfig cfg = score_config(ctx, check_window);
     if (kind == kJobTargets && ctx->P.library_mode) cfg.no_bucket = 1;
@@ -247,9 +250,23 @@ int32_t run_score_io(pq_ctx* ctx, const ScoreIO& io, JobKind kind, uint32_t n_jo
     return PQ_OK;
 }
 int32_t run_score(pq_ctx* ctx, JobKind kind, uint32_t n_jobs, const int32_t* row_pred, const uint8_t* rows, const double* row_mass,
-                  uint32_t hit_capacity, int check_window) {
+                  uint32_t hit_capacity, int check_window, const PeptideTable* ladders = nullptr) {
     ScoreIO io{ctx->st, ctx->jobs.as<Job>(), &ctx->results, &ctx->hits, &ctx->hit_count, ctx->d_scalars.as<uint32_t>() + 12, true};
-    return run_score_io(ctx, io, kind, n_jobs, row_pred, rows, row_mass, hit_capacity, check_window);
+    return run_score_io(ctx, io, kind, n_jobs, row_pred, rows, row_mass, hit_capacity, check_window, ladders);
+}
+// Step 3 reads the fragment ladders of the reference rows from a table written once per reference build (k1_ladder.cu)
+int32_t ensure_ladders(pq_ctx* ctx, PeptideTable& T, const uint8_t* rows, uint32_t n_rows, cudaStream_t st, bool timed) {
+    if (T.have_lad || n_rows == 0 || getenv("PQ_STEP3_WALK")) return PQ_OK;
+    std::string err; uint64_t launches = 0;
+    bool ok;
+    if (T.lad.reserve(16) != cudaSuccess) return fail(ctx, PQ_ERR_NOMEM, "ladder tables");
+    const int max_len = std::max(ctx->P.max_len, 1);      // reference rows come from the digest: min_len .. max_len residues
+    if (timed) { Timer t(ctx, &ctx->cnt.ms_ladder); ok = build_row_ladders(st, rows, n_rows, max_len, ctx->d_mods.as<ModTable>(), T.lad, &T.lad_stride, &launches, err); }
+    else ok = build_row_ladders(st, rows, n_rows, max_len, ctx->d_mods.as<ModTable>(), T.lad, &T.lad_stride, &launches, err);
+    if (!ok) return fail(ctx, PQ_ERR_CUDA, "ladder tables: " + err);
+    ctx->cnt.other_kernel_launches += launches;
+    T.have_lad = true;
+    return PQ_OK;
 }
 
 template <class T> int32_t scan_exclusive(pq_ctx* ctx, const T* in, T* out, int n) {
@@ -1199,7 +1216,7 @@ int32_t pq_build_reference(pq_ctx* ctx, int32_t n_proteins, const uint64_t* off,
     if (use_staged && ctx->pending_ref && ctx->have_reference) { ctx->pending_ref = false; return PQ_OK; }      // cut out of the superset table when the spectra were loaded
     ctx->pending_ref = false; ctx->pending_step[3] = ctx->pending_step[4] = false; ctx->step_done = std::min(ctx->step_done, 2);
     PeptideTable& R = ctx->reference;
-    R.seqs.clear(); R.forms.clear(); R.have_mask = false; R.device_built = false; R.materialized = true;
+    R.seqs.clear(); R.forms.clear(); R.have_mask = false; R.have_lad = false; R.device_built = false; R.materialized = true;
     auto t_begin = std::chrono::steady_clock::now();
     Marks mk("build_reference");
     if (!use_staged) { ctx->ref_staged = false; ctx->ref_digested = false; }
@@ -1307,7 +1324,9 @@ int32_t pq_step3_competitors(pq_ctx* ctx) {
     ctx->cnt.d2h_bytes += 8;
     mk.mark("build jobs");
     if (cand > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-3 candidates for one launch");
-    int32_t rc = run_score(ctx, kJobCompetitors, n_jobs, R.pred.as<int32_t>(), R.rows.as<uint8_t>(), R.mass.as<double>(), (uint32_t)std::max<unsigned long long>(cand, 1), 1);
+    int32_t rc = ensure_ladders(ctx, R, R.rows.as<uint8_t>(), (uint32_t)R.n(), st, true);
+    if (rc) return rc;
+    rc = run_score(ctx, kJobCompetitors, n_jobs, R.pred.as<int32_t>(), R.rows.as<uint8_t>(), R.mass.as<double>(), (uint32_t)std::max<unsigned long long>(cand, 1), 1, &R);
     if (rc) return rc;
     int k = launch_job_counters(ctx->jobs.as<Job>(), ctx->results.as<JobResult>(), n_jobs, ctx->s_npeaks.as<uint32_t>(), 1, ctx->d_counters.as<DevCounters>(), st);
     k += launch_step3_aggregate(ctx->results.as<JobResult>(), n_seg, ctx->P.n_isotope, ctx->d_seg_start.as<uint32_t>(), ctx->d_psm.as<DevPsm>(), ctx->d_agg.as<SegAgg>(), st);
@@ -1455,6 +1474,8 @@ int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan) {
         if (!ok) return fail(ctx, PQ_ERR_CUDA, "reference build: " + err);
         ctx->cnt.other_kernel_launches += launches;
         ctx->super_rows = R.dev.n_forms; R.dev.n_forms = 0;
+        S.have_lad = false;
+        { int32_t rc = ensure_ladders(ctx, S, S.rows.as<uint8_t>(), ctx->super_rows, sa, false); if (rc) return rc; }
         if (ctx->P.score_method == 2 && ctx->super_rows) {
             CU(S.pred.reserve((size_t)ctx->super_rows * 8));
             ctx->cnt.other_kernel_launches += (uint64_t)launch_predict(S.rows.as<uint8_t>(), ctx->super_rows, ctx->d_mods.as<ModTable>(), ctx->P.itol, S.pred.as<int32_t>(), sa);
@@ -1553,7 +1574,7 @@ int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan) {
             CU(cudaStreamSynchronize(sp_));
             if (cand3 > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-3 candidates for one launch");
             ScoreIO io3{sp_, B.jobs.as<Job>(), &B.results, &B.hits, &B.hit_count, scal + 12, false};
-            rc = run_score_io(ctx, io3, kJobCompetitors, nj3, S.pred.as<int32_t>(), S.rows.as<uint8_t>(), S.mass.as<double>(), (uint32_t)std::max<unsigned long long>(cand3, 1), 1);
+            rc = run_score_io(ctx, io3, kJobCompetitors, nj3, S.pred.as<int32_t>(), S.rows.as<uint8_t>(), S.mass.as<double>(), (uint32_t)std::max<unsigned long long>(cand3, 1), 1, &S);
             if (rc) return rc;
             int k = launch_job_counters(B.jobs.as<Job>(), B.results.as<JobResult>(), nj3, sp.npeaks, 1, ctx->d_counters.as<DevCounters>(), sp_);
             k += launch_step3_aggregate(B.results.as<JobResult>(), nseg, ctx->P.n_isotope, B.seg_start.as<uint32_t>(), B.psm.as<DevPsm>(), B.agg.as<SegAgg>(), sp_);
@@ -1578,7 +1599,7 @@ int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan) {
     mk.mark("parts queued");
     // ---- merge ----
     ctx->n_psm = 0; ctx->n_seg = 0; ctx->nh3 = 0; ctx->comp3_ready = false; ctx->comp3_n = 0;
-    R.seqs.clear(); R.forms.clear(); R.have_mask = false; R.device_built = true; R.materialized = false; R.h_mass.clear(); R.n_rows = 0;
+    R.seqs.clear(); R.forms.clear(); R.have_mask = false; R.have_lad = false; R.device_built = true; R.materialized = false; R.h_mass.clear(); R.n_rows = 0;
     if (N) {
         CU(ctx->d_psm.reserve((size_t)N * sizeof(DevPsm))); CU(ctx->d_seg_start.reserve(((size_t)NS + 2) * 4)); CU(ctx->d_out_perm.reserve((size_t)N * 4));
         CU(ctx->d_agg.reserve((size_t)NS * sizeof(SegAgg))); CU(ctx->hits3.reserve(std::max<size_t>((size_t)NH3, 1) * sizeof(Hit)));

@@ -38,7 +38,7 @@ struct ModTable {
 
 // ---- prepared spectrum blob (output of K0, input of K1) -----------------------------------------------------------
 // Everything K1 needs about one spectrum, contiguous and 16-byte aligned so one cp.async.bulk stages it:
-//   BlobHeader | ev f64[NE] | ans u16[NE pad 8] | pmz f64[E+1 pad 2] | pin f64[E pad 2] | pcode u16[E pad 8] | val f64[kValSlots] | cells u16[kCells]
+//   BlobHeader | ev f64[NE] | ans u16[NE pad 8] | pmz f64[E+1 pad 2] | pin f64[E pad 2] | pcode u16[E pad 8] | val f64[kValSlots] | cells u16[kCells + 8]
 //
 // The annotator's question "which matchable peak is the most intense one with |mz - t| <= itol" (JMatch.java:411-451,
 // A2-A4) has a piecewise-constant answer in t.  K0 inverts the predicate once per spectrum: for every matchable peak j
@@ -54,7 +54,8 @@ struct ModTable {
 //   pcode : claim code of each matchable peak: (class << 12) | survivor id (0xFFF = the peak did not survive pre-processing)
 //   val   : hyperscore: normalised intensity of survivor id; MVH: unused
 //   cells : cells[c] = index of the last event below the lower edge of cell c of the monotone m/z -> cell map,
-//           | kCellClean when the whole cell answers 0xFFFF (K1 then skips the event scan)
+//           | kCellClean when the whole cell answers 0xFFFF (K1 then skips the event scan); one more entry follows the table,
+//           always kCellClean: the precomputed cell lists of the reference rows (k1_ladder.cu) point unused slots at it
 constexpr int kCellShift = 11;                              // 512 cells per binade
 constexpr uint32_t kCellBase = 0x40600000u >> kCellShift;   // high word of 128.0
 constexpr int kCells = 5 * 512;                             // [128, 4096) Th; below / above clamp to the first / last cell
@@ -63,6 +64,8 @@ constexpr uint32_t kNoSurvivor = 0xFFFu;
 constexpr uint32_t kAnsNone = 0xFFFFu;
 constexpr uint32_t kAnsTie = 0x8000u;
 constexpr uint32_t kCellClean = 0x8000u;     // cells[] flag: every t of the cell answers kAnsNone (no event inside, nothing to claim at its lower edge)
+constexpr uint32_t kCellSentinel = 2u * kCells;   // byte offset of the always-clean entry behind the table
+constexpr int kLadderCharges = 3;                // fragment charges held in the precomputed ladders of the reference rows (k1_ladder.cu)
 
 struct BlobHeader {
     uint32_t n_peaks;        // E
@@ -87,7 +90,7 @@ PQ_HD BlobLayout blob_layout(uint32_t E) {
     L.pcode = L.pin + ((E * 8u + 15u) & ~15u);
     L.val = L.pcode + ((E * 2u + 15u) & ~15u);
     L.cells = L.val + kValSlots * 8u;
-    L.total = L.cells + kCells * 2u;
+    L.total = L.cells + kCells * 2u + 16u;                      // + the always-clean sentinel entry (padded to 16 bytes)
     return L;
 }
 PQ_HD uint32_t blob_bytes(uint32_t n_peaks) { return blob_layout(n_peaks).total; }

@@ -316,6 +316,29 @@ def test_cell_lists_decide_like_the_ladder_walk(method, monkeypatch):
     assert g3.psms().tobytes() == got.tobytes() and g3.counters().pairs_step4_bounded == 0
 
 
+@pytest.mark.parametrize("method", [1, 2])
+def test_ladder_tables_score_like_the_ladder_walk(data, method, monkeypatch):
+    """Step 3 from the precomputed fragment ladders of the reference rows (k1_ladder.cu) against the per-pair ladder walk of
+    k1_score.cu (PQ_STEP3_WALK) and against the oracle: same n_db / total_db, same detail rows, same bits in every score.
+    Some spectra are re-labelled with charge 5 and 6 (4 and 5 fragment charges: above what the tables hold, derived on the fly)."""
+    prot, tgt, sp = data
+    sp = {k: v.copy() for k, v in sp.items()}
+    z = sp["charge"].copy()
+    pick = np.arange(len(z)) % 7 == 3
+    newz = np.where(np.arange(len(z)) % 2 == 0, 5, 6)
+    mass = sp["prec_mz"] * z - z * 1.007276466812                      # keep the neutral mass, so the windows still hold candidates
+    sp["charge"] = np.where(pick, newz, z).astype(np.int32)
+    sp["prec_mz"] = np.where(pick, (mass + sp["charge"] * 1.007276466812) / sp["charge"], sp["prec_mz"])
+    p = _abi.default_params(n_random=50, score_method=method, min_score=0.0)
+    g, o, got = full_compare(p, sp, tgt, prot)
+    assert (got["charge"] >= 5).sum() >= 3 and g.counters().pairs_step3 > 1000, ((got["charge"] >= 5).sum(), g.counters().pairs_step3)
+    rows = np.sort(g.competitors(3), order=["spectrum", "ref_form"])
+    monkeypatch.setenv("PQ_STEP3_WALK", "1")
+    g2 = run_gpu(p, sp, tgt, prot)
+    assert g2.psms().tobytes() == got.tobytes()
+    assert np.sort(g2.competitors(3), order=["spectrum", "ref_form"]).tobytes() == rows.tobytes()
+
+
 @pytest.mark.parametrize("enzyme", [2, 5, 6, 9, 11, 12, 16, 17])
 def test_enzymes(data, enzyme):
     """K6's digest with other cleavage rules of the reference's -e table (cut after / cut before / blocked by the next
