@@ -123,12 +123,13 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
                 }
             };
             // cell lists of the job's shuffle rows (written by K2 with the rows): the count pass needs no ladder walk and no row
-            const uint4* job_lists = nullptr; size_t list_stride = 0; uint32_t list_chunks = 0, list_n = 0;
+            const uint4* job_lists = nullptr; size_t list_stride = 0; uint32_t list_chunks = 0, list_units = 0, list_n = 0;
             if (L.lists) {
                 const ShuffleForm& F = L.sh_forms[L.form_slot[J.aux]];
                 const int nch = J.charge <= 1 ? 1 : J.charge - 1;
                 if (nch <= (int)F.list_nch) {
                     list_chunks = F.list_chunks; list_stride = F.list_rows; list_n = list_entries((int)F.len, nch);
+                    list_units = (uint32_t)nch * list_stream_units((int)F.len);      // the first nch charge streams of each side
                     job_lists = L.lists + F.list_base;                     // unit u of row c of the job (= shuffle c of the form) at [u * list_stride + c]
                 }
             }
@@ -143,7 +144,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
                     int32_t pred = 0;
                     if (METHOD == 2) pred = L.row_pred[2 * ((size_t)J.cand_begin + c) + (J.charge == 2 ? 0 : 1)];
                     bool below;
-                    if (job_lists) below = below_score_bound_lists<METHOD>(job_lists + c, list_stride, list_chunks, list_n, B, s_l10, J.ref_score, L.ln_fact, pred);
+                    if (job_lists) below = below_score_bound_lists<METHOD>(job_lists + c, list_stride, list_chunks, list_units, list_n, B, s_l10, J.ref_score, L.ln_fact, pred);
                     else { load_row(J.cand_begin + c); below = below_score_bound<BLOCK, TS, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, s_l10, J.ref_score, L.ln_fact, pred); }
                     if (below) ++n_bound;
                     else s_surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)(c - s0);

@@ -94,6 +94,52 @@ k_gather_peaks_from_host(const int32_t* __restrict__ list, int32_t n_list, const
     }
 }
 
+// The same gather as ONE launch over all chunks: its few CTAs stay resident for the whole upload and count every finished chunk
+// in chunk_done[c] (release), so the upload never queues behind the persistent scoring kernels of the parts that are searched
+// meanwhile (seen in the timeline: every per-chunk gather launch waited up to 2 ms for a CTA slot; upload 35 ms instead of 22).
+// Consumers order themselves behind chunk c with k_wait_chunk on their own stream.
+__global__ void __launch_bounds__(128)
+k_gather_peaks_chunked(const int32_t* __restrict__ list, int32_t n_list, int32_t chunk, const int32_t* __restrict__ caller, const uint64_t* __restrict__ off_in,
+                       const uint64_t* __restrict__ off_out, const double* __restrict__ h_mz, const double* __restrict__ h_in,
+                       double* __restrict__ mz_out, double* __restrict__ in_out, uint32_t* __restrict__ chunk_done) {
+    const int lane = threadIdx.x & 31;
+    const int32_t warps = (int32_t)((gridDim.x * blockDim.x) >> 5);
+    const int32_t w0 = (int32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    int32_t c = 0;
+    for (int32_t first = 0; first < n_list; first += chunk, ++c) {
+        const int32_t last = min(first + chunk, n_list);
+        for (int32_t w = first + w0; w < last; w += warps) {
+            const int32_t s = list[w];
+            const int64_t src = caller[s];
+            const uint64_t a = off_in[src], cnt = off_in[src + 1] - a, b = off_out[s];
+            for (uint64_t k0 = 0; k0 < cnt; k0 += 128) {
+                double m[4], v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint64_t k = k0 + (uint64_t)(32 * j + lane);
+                    if (k < cnt) { m[j] = __ldcs(h_mz + a + k); v[j] = __ldcs(h_in + a + k); }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint64_t k = k0 + (uint64_t)(32 * j + lane);
+                    if (k < cnt) { mz_out[b + k] = m[j]; in_out[b + k] = v[j]; }
+                }
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(chunk_done + c, 1u);
+    }
+}
+__global__ void k_wait_chunk(const uint32_t* flag, uint32_t expected) {
+    uint32_t v;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= expected) break;
+        __nanosleep(500);
+    }
+}
+
 // full-upload path: peaks arrive in caller order chunk by chunk, so the copy is driven by the virtual id
 // (inv[v] = mass-sorted position of virtual spectrum v; src = the caller spectrum whose peaks it has)
 __global__ void k_invert_order(int64_t n, const int32_t* __restrict__ order, int32_t* __restrict__ inv) {
@@ -248,6 +294,24 @@ int launch_gather_peaks_from_host(const int32_t* list, int32_t n_list, const int
     if (const char* e = getenv("PQ_GATHER_CTAS")) { int v = atoi(e); if (v > 0) grid = v; }
     int need = (n_list + 3) / 4; if (grid > need) grid = need;
     k_gather_peaks_from_host<<<grid, 128, 0, st>>>(list, n_list, caller, off_in, off_out, h_mz, h_in, mz_out, in_out);
+    return 1;
+}
+int gather_grid(int32_t n_list) {
+    int grid = 32;
+    if (const char* e = getenv("PQ_GATHER_CTAS")) { int v = atoi(e); if (v > 0) grid = v; }
+    int need = (n_list + 3) / 4; if (grid > need) grid = need;
+    return grid < 1 ? 1 : grid;
+}
+int launch_gather_peaks_chunked(const int32_t* list, int32_t n_list, int32_t chunk, const int32_t* caller, const uint64_t* off_in, const uint64_t* off_out,
+                                const double* h_mz, const double* h_in, double* mz_out, double* in_out, uint32_t* chunk_done /* zeroed */, uint32_t* n_ctas, cudaStream_t st) {
+    if (n_list <= 0) { *n_ctas = 0; return 0; }
+    const int grid = gather_grid(n_list);
+    *n_ctas = (uint32_t)grid;
+    k_gather_peaks_chunked<<<grid, 128, 0, st>>>(list, n_list, chunk, caller, off_in, off_out, h_mz, h_in, mz_out, in_out, chunk_done);
+    return 1;
+}
+int launch_wait_chunk(const uint32_t* flag, uint32_t expected, cudaStream_t st) {
+    k_wait_chunk<<<1, 1, 0, st>>>(flag, expected);
     return 1;
 }
 int launch_invert_order(int64_t n, const int32_t* order, int32_t* inv, cudaStream_t st) {

@@ -119,6 +119,35 @@ __global__ void k6_gather_u64(const uint64_t* __restrict__ src, const uint32_t* 
     if (i < n) dst[i] = src[perm[i]];
 }
 
+// After ONE radix sort on the first key word (the first twelve residues): candidates that share it — mostly the same start
+// with more missed cleavages behind a long first piece — form short runs; the thread of a run's head puts the run in order of the
+// remaining words with a stable insertion sort, which leaves exactly the order the word-by-word LSD sort gives (equal keys keep
+// candidate order).  A run longer than kMaxRun raises *overflow: the caller then sorts word by word.
+constexpr uint32_t kMaxRun = 48;
+__device__ __forceinline__ bool tail_less(const uint64_t* __restrict__ keys, uint32_t n, int words, uint32_t a, uint32_t b) {      // words 1.. of candidate a < those of b
+    for (int w = 1; w < words; ++w) {
+        const uint64_t x = keys[(size_t)w * n + a], y = keys[(size_t)w * n + b];
+        if (x != y) return x < y;
+    }
+    return false;
+}
+__global__ void k6_order_runs(const uint64_t* __restrict__ word0_sorted, uint32_t* __restrict__ perm, const uint64_t* __restrict__ keys, uint32_t n, int words,
+                              uint32_t* __restrict__ overflow) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t k0 = word0_sorted[i];
+    if (i > 0 && word0_sorted[i - 1] == k0) return;                 // not a head
+    if (i + 1 >= n || word0_sorted[i + 1] != k0) return;            // a run of one
+    uint32_t len = 2;
+    while (i + len < n && word0_sorted[i + len] == k0) { if (++len > kMaxRun) { *overflow = 1u; return; } }
+    for (uint32_t a = 1; a < len; ++a) {                            // stable insertion sort of perm[i .. i+len)
+        const uint32_t c = perm[i + a];
+        uint32_t b = a;
+        while (b > 0 && tail_less(keys, n, words, c, perm[i + b - 1])) { perm[i + b] = perm[i + b - 1]; --b; }
+        perm[i + b] = c;
+    }
+}
+
 __device__ __forceinline__ int key_cmp(const uint64_t* keys, uint32_t n, uint32_t i, const uint64_t* tk) {
     for (int w = 0; w < kKeyWords; ++w) {
         uint64_t a = keys[(size_t)w * n + i], b = tk[w];
@@ -301,17 +330,22 @@ template <class F> bool select_flagged(const uint8_t* flags, uint32_t n, uint32_
 // Sorted, unique 300-bit keys of the target sequences (the digest removes them, DatabaseInput.java:480-488).  A host-to-device
 // copy, so it is issued before the spectrum upload is queued, not from inside the digest.
 bool upload_target_keys_for_reference(cudaStream_t st, const std::vector<std::string>& targets, RefDeviceTable& T, std::string& err) {
-    std::vector<uint64_t> tk;
-    std::vector<std::string> ts(targets);
-    for (std::string& s : ts) for (char& c : s) if (c == 'I') c = 'L';      // DatabaseInput.add_target_peptides (pg/DatabaseInput.java:47-51): the digest is I -> L folded
-    std::sort(ts.begin(), ts.end());
-    ts.erase(std::unique(ts.begin(), ts.end()), ts.end());
-    for (const std::string& s : ts) {
-        uint64_t k[kKeyWords] = {0, 0, 0, 0, 0};
+    // packed keys (left-aligned 5-bit letters, so tuple order = string order), I -> L folded like the digest
+    // (DatabaseInput.add_target_peptides, pg/DatabaseInput.java:47-51), sorted, unique
+    struct Key { uint64_t w[kKeyWords]; };
+    std::vector<Key> ks; ks.reserve(targets.size());
+    for (const std::string& s : targets) {
         if (s.size() > (size_t)kMaxLen) continue;
-        for (size_t r = 0; r < s.size(); ++r) k[r / 12] |= (uint64_t)(s[r] - 'A' + 1) << (59 - 5 * (r % 12));
-        for (int w = 0; w < kKeyWords; ++w) tk.push_back(k[w]);
+        Key k; for (int w = 0; w < kKeyWords; ++w) k.w[w] = 0;
+        for (size_t r = 0; r < s.size(); ++r) { const char c = s[r] == 'I' ? 'L' : s[r]; k.w[r / 12] |= (uint64_t)(c - 'A' + 1) << (59 - 5 * (r % 12)); }
+        ks.push_back(k);
     }
+    auto less = [](const Key& a, const Key& b) { for (int w = 0; w < kKeyWords; ++w) if (a.w[w] != b.w[w]) return a.w[w] < b.w[w]; return false; };
+    auto same = [](const Key& a, const Key& b) { for (int w = 0; w < kKeyWords; ++w) if (a.w[w] != b.w[w]) return false; return true; };
+    std::sort(ks.begin(), ks.end(), less);
+    ks.erase(std::unique(ks.begin(), ks.end(), same), ks.end());
+    std::vector<uint64_t> tk; tk.reserve(ks.size() * kKeyWords);
+    for (const Key& k : ks) for (int w = 0; w < kKeyWords; ++w) tk.push_back(k.w[w]);
     T.n_tkeys = (uint32_t)(tk.size() / kKeyWords);
     DevBuf& d_tk = T.w[10];
     RB(d_tk.reserve(tk.size() * 8 + 64));
@@ -396,13 +430,29 @@ bool digest_reference_on_device(cudaStream_t st, const pq_params& P, const Codes
         RB(tmp.reserve(bytes + 64));
         uint32_t* pa = d_perm.as<uint32_t>(); uint32_t* pb = d_perm2.as<uint32_t>();
         const int words_used = (P.max_len + 11) / 12;
-        for (int w = words_used - 1; w >= 0; --w) {
-            k6_gather_u64<<<(n_cand + 255) / 256, 256, 0, st>>>(d_keys.as<uint64_t>() + (size_t)w * n_cand, pa, n_cand, d_tmpkey.as<uint64_t>());
-            RB(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_tmpkey.as<uint64_t>(), d_tmpkey2.as<uint64_t>(), pa, pb, (int)n_cand, 4, 64, st));
-            std::swap(pa, pb);
+        // first word only, then the short runs of equal first words put in order by their heads (k6_order_runs)
+        uint32_t overflow = words_used > 1 && !getenv("PQ_DIGEST_LSD") ? 0u : 1u;
+        if (!overflow) {
+            RB(cudaMemsetAsync(d_cnt.as<uint32_t>() + 4, 0, 4, st));
+            RB(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_keys.as<uint64_t>(), d_tmpkey2.as<uint64_t>(), pa, pb, (int)n_cand, 4, 64, st));      // pa = identity: word 0 needs no gather
+            k6_order_runs<<<(n_cand + 255) / 256, 256, 0, st>>>(d_tmpkey2.as<uint64_t>(), pb, d_keys.as<uint64_t>(), n_cand, words_used, d_cnt.as<uint32_t>() + 4);
+            RB(cudaMemcpyAsync(&overflow, d_cnt.as<uint32_t>() + 4, 4, cudaMemcpyDeviceToHost, st));
+            RB(cudaStreamSynchronize(st));
             *launches += 5;
+            if (!overflow) RB(cudaMemcpyAsync(d_perm.p, pb, (size_t)n_cand * 4, cudaMemcpyDeviceToDevice, st));
         }
-        if (pa != d_perm.as<uint32_t>()) RB(cudaMemcpyAsync(d_perm.p, pa, (size_t)n_cand * 4, cudaMemcpyDeviceToDevice, st));
+        if (overflow) {      // long runs (a repetitive database) or one-word keys: least-significant word first, one stable radix sort per word
+            pa = d_perm.as<uint32_t>(); pb = d_perm2.as<uint32_t>();
+            if (words_used > 1) k6_pack_keys<<<(n_cand + 255) / 256, 256, 0, st>>>(d_cand.as<uint32_t>(), n_cand, T.starts.as<uint32_t>(), per, d_res, d_keys.as<uint64_t>(),
+                                                                                    T.cand_pos.as<uint32_t>(), T.cand_len.as<uint32_t>(), d_perm.as<uint32_t>());      // identity permutation again
+            for (int w = words_used - 1; w >= 0; --w) {
+                k6_gather_u64<<<(n_cand + 255) / 256, 256, 0, st>>>(d_keys.as<uint64_t>() + (size_t)w * n_cand, pa, n_cand, d_tmpkey.as<uint64_t>());
+                RB(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_tmpkey.as<uint64_t>(), d_tmpkey2.as<uint64_t>(), pa, pb, (int)n_cand, 4, 64, st));
+                std::swap(pa, pb);
+                *launches += 5;
+            }
+            if (pa != d_perm.as<uint32_t>()) RB(cudaMemcpyAsync(d_perm.p, pa, (size_t)n_cand * 4, cudaMemcpyDeviceToDevice, st));
+        }
     }
     const uint32_t n_t = T.n_tkeys;          // uploaded by upload_target_keys_for_reference
     (void)targets;

@@ -7,6 +7,7 @@
 #include <map>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -64,6 +65,7 @@ struct pq_ctx {
     cudaStream_t st = nullptr, st_copy = nullptr, st_aux = nullptr;
     std::vector<cudaEvent_t> chunk_ev;       // one per upload chunk of pq_load_spectra
     cudaEvent_t meta_ev = nullptr;           // precursor arrays of pq_load_spectra on the device
+    cudaEvent_t targets_ev = nullptr;        // target table of this load on the device (the early shuffle generation waits for it)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, uev0 = nullptr, uev1 = nullptr;
     void* stage_host = nullptr; cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     pq_counters cnt;
@@ -94,6 +96,7 @@ struct pq_ctx {
     DevBuf s_inv;                            // virtual id -> mass-sorted position
     DevBuf gather_list;                      // candidate-first: the resident spectra (sorted positions) in caller order
     DevBuf k0_counters;                      // work hand-out words of the per-chunk K0 launches
+    DevBuf chunk_done;                       // candidate-first gather: CTAs that have finished upload chunk c
     std::vector<cudaEvent_t> k0_ev;           // K0 of upload chunk c has finished
     DevBuf d_zero;                           // caller indices of the charge-less spectra, ascending
     // tables
@@ -169,6 +172,7 @@ void flush_timers(pq_ctx* c);
 int32_t finalize_targets(pq_ctx* ctx);
 void ensure_forms(pq_ctx* ctx);
 int32_t digest_staged_reference(pq_ctx* ctx, cudaStream_t st, bool count_time = true);
+int32_t generate_shuffles(pq_ctx* ctx, cudaStream_t st, bool all, ShuffleTotals& tot, bool timed, pq_counters* sink = nullptr);
 // What pq_load_spectra hands to search_at_load: the Step-2 jobs its window enumeration left in ctx->jobs, the order the spectra
 // arrive in (gather_list, chunks of chunk_spectra, one K0-done event per chunk) and how many chunks make a part.
 struct LoadPlan {
@@ -452,6 +456,7 @@ int32_t pq_destroy(pq_ctx* ctx) {
     for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->k0_ev) cudaEventDestroy(e);
     if (ctx->meta_ev) cudaEventDestroy(ctx->meta_ev);
+    if (ctx->targets_ev) cudaEventDestroy(ctx->targets_ev);
     cudaStream_t st = ctx->st, st_copy = ctx->st_copy, st_aux = ctx->st_aux;
     if (ctx->st_part) { cudaStreamSynchronize(ctx->st_part); cudaStreamDestroy(ctx->st_part); }
     delete ctx;
@@ -589,8 +594,14 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
     ctx->mgf_cache_text = nullptr;
     Marks mk("load_spectra");
     cudaStream_t st = ctx->st, sc = ctx->st_copy;
+    // The spectrum-independent work of a search that will run inside this call (search_at_load) — the digest of the staged protein
+    // database and the shuffles of every target form — is queued by a helper thread (both have host round trips for their sizes)
+    // while this thread sets up the upload: by the time the first spectra have arrived and are prepared, it is done.
+    struct EarlyWork { std::thread th; int32_t rc = PQ_OK; std::string err; uint64_t launches = 0, d2h = 0; bool digest = false, shuffles = false; } early;
     // whatever goes wrong from here on, the context ends up without spectra and with nothing in flight
     auto fail_load = [&](int32_t code, const std::string& msg) -> int32_t {
+        if (early.th.joinable()) early.th.join();
+        cudaStreamSynchronize(ctx->st_part);
         cudaStreamSynchronize(sc); cudaStreamSynchronize(st); cudaStreamSynchronize(ctx->st_aux); cudaGetLastError();
         ctx->nS = 0; ctx->nCaller = 0; ctx->nZero = 0; ctx->max_peaks = 0; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0; ctx->prepared_at_load = false;
         ctx->residency = 0; ctx->n_resident = 0; ctx->cnt.spectra_loaded = 0; ctx->cnt.spectra_usable = 0; ctx->host_spectra_valid = false;
@@ -631,6 +642,34 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
         if (!upload_target_keys_for_reference(st, ctx->targets.seqs, ctx->reference.dev, err)) return fail_load(PQ_ERR_CUDA, "reference digest: " + err);
     }
     int k_launch = 0;
+    const bool early_ok = cf && ctx->P.search_at_load != 0 && !getenv("PQ_NO_SEARCH_AT_LOAD") && !getenv("PQ_NO_EARLY_WORK") && ctx->ref_staged && ctx->n_targeted == 0 && n0 == 0 &&
+                          ctx->P.n_random <= 20000 && ctx->P.prepare_at_load != 0 && getenv("PQ_PREPARE_AT_STEP2") == nullptr;
+    if (early_ok) {
+        int32_t rc = finalize_targets(ctx);                          // the shuffle generator reads the target table's side arrays
+        if (rc) return fail_load(rc, ctx->err);
+        if (!ctx->targets_ev) CL(cudaEventCreateWithFlags(&ctx->targets_ev, cudaEventDisableTiming));
+        CL(cudaEventRecord(ctx->targets_ev, st));
+        const bool need_digest = !ctx->ref_digested;
+        const bool need_shuffles = !(ctx->shuffles_all && ctx->shuffles_epoch == ctx->targets_epoch && ctx->have_shuffles);
+        if (need_digest || need_shuffles) early.th = std::thread([ctx, &early, need_digest, need_shuffles]() {
+            cudaSetDevice(ctx->P.device);
+            if (need_digest) {
+                std::string err; uint64_t l = 0;
+                if (!upload_target_keys_for_reference(ctx->st_aux, ctx->targets.seqs, ctx->reference.dev, err) ||
+                    !digest_reference_on_device(ctx->st_aux, ctx->P, ctx->codes, ctx->targets.seqs, ctx->reference.dev, &l, err)) { early.rc = PQ_ERR_CUDA; early.err = "reference digest: " + err; return; }
+                early.launches += l; early.digest = true;
+            }
+            if (need_shuffles) {
+                if (cudaStreamWaitEvent(ctx->st_part, ctx->targets_ev, 0) != cudaSuccess) { early.rc = PQ_ERR_CUDA; early.err = "early shuffles: stream wait"; return; }
+                pq_counters c; memset(&c, 0, sizeof c);
+                ShuffleTotals tot; memset(&tot, 0, sizeof tot);
+                const int32_t rc = generate_shuffles(ctx, ctx->st_part, true, tot, false, &c);      // on the parts' stream: their Step 4 is ordered behind it
+                early.launches += c.other_kernel_launches; early.d2h += c.d2h_bytes;
+                if (rc) { early.rc = rc; return; }
+                early.shuffles = true;
+            }
+        });
+    }
     // ---- precursor arrays, neutral masses, the mass order, the sorted precursor arrays ----
     CL(cudaMemcpyAsync(in_prec.p, prec_mz, n * 8, cudaMemcpyHostToDevice, st));
     CL(cudaMemcpyAsync(in_charge.p, charge, n * 4, cudaMemcpyHostToDevice, st));
@@ -745,6 +784,7 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
             while (ctx->chunk_ev.size() < nck + 1) { cudaEvent_t e; CL(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->chunk_ev.push_back(e); }
             if (!ctx->meta_ev) CL(cudaEventCreateWithFlags(&ctx->meta_ev, cudaEventDisableTiming));
             CL(ctx->k0_counters.reserve((nck + 1) * 16)); CL(cudaMemsetAsync(ctx->k0_counters.p, 0, (nck + 1) * 16, st));
+            CL(ctx->chunk_done.reserve((nck + 1) * 4)); CL(cudaMemsetAsync(ctx->chunk_done.p, 0, (nck + 1) * 4, st));
             CL(cudaEventRecord(ctx->meta_ev, st));
             CL(cudaStreamWaitEvent(sc, ctx->meta_ev, 0));
             // search while loading?  everything a search needs must be known now, and K0 must run here
@@ -752,17 +792,29 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
             if (stream_search) while (ctx->k0_ev.size() < nck + 1) { cudaEvent_t e; CL(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ctx->k0_ev.push_back(e); }
             n_chunks_cf = nck; chunk_spectra_cf = chunk_spectra;
             Timer t(ctx, &ctx->cnt.ms_prepare);
-            const bool trace = getenv("PQ_LOAD_TRACE") != nullptr;          // diagnostic: when did every chunk's gather / K0 finish?
+            const bool trace_env = getenv("PQ_LOAD_TRACE") != nullptr;      // diagnostic: when did every chunk's gather / K0 finish?
+            const bool trace = trace_env;
             std::vector<cudaEvent_t> tr_g, tr_k; cudaEvent_t tr0 = nullptr;
             if (trace) { cudaEventCreate(&tr0); cudaEventRecord(tr0, sc); }
+            // one gather launch for the whole upload (its CTAs stay resident, chunk_done[c] counts the CTAs that have finished chunk c);
+            // PQ_GATHER_PER_CHUNK: one launch per chunk, ordered by events (the earlier form, for A/B runs)
+            const bool one_gather = getenv("PQ_GATHER_PER_CHUNK") == nullptr && !trace_env;
+            uint32_t gather_ctas = 0;
+            if (one_gather)
+                k_launch += launch_gather_peaks_chunked(ctx->gather_list.as<int32_t>(), (int32_t)n_res, (int32_t)chunk_spectra, ctx->s_caller.as<int32_t>(), in_off.as<uint64_t>(),
+                                                        ctx->s_off.as<uint64_t>(), static_cast<const double*>(d_h_mz), static_cast<const double*>(d_h_in),
+                                                        ctx->s_mz.as<double>(), ctx->s_in.as<double>(), ctx->chunk_done.as<uint32_t>(), &gather_ctas, sc);
             for (size_t c = 0; c < nck; ++c) {
                 const uint32_t a = (uint32_t)(c * chunk_spectra), cnt = std::min(chunk_spectra, n_res - a);
-                k_launch += launch_gather_peaks_from_host(ctx->gather_list.as<int32_t>() + a, (int32_t)cnt, ctx->s_caller.as<int32_t>(), in_off.as<uint64_t>(),
-                                                          ctx->s_off.as<uint64_t>(), static_cast<const double*>(d_h_mz), static_cast<const double*>(d_h_in),
-                                                          ctx->s_mz.as<double>(), ctx->s_in.as<double>(), sms, sc);
-                CL(cudaEventRecord(ctx->chunk_ev[c], sc));
-                if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sc); tr_g.push_back(e); }
-                CL(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
+                if (one_gather) k_launch += launch_wait_chunk(ctx->chunk_done.as<uint32_t>() + c, gather_ctas, st);
+                else {
+                    k_launch += launch_gather_peaks_from_host(ctx->gather_list.as<int32_t>() + a, (int32_t)cnt, ctx->s_caller.as<int32_t>(), in_off.as<uint64_t>(),
+                                                              ctx->s_off.as<uint64_t>(), static_cast<const double*>(d_h_mz), static_cast<const double*>(d_h_in),
+                                                              ctx->s_mz.as<double>(), ctx->s_in.as<double>(), sms, sc);
+                    CL(cudaEventRecord(ctx->chunk_ev[c], sc));
+                    if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sc); tr_g.push_back(e); }
+                    CL(cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0));
+                }
                 if (eager)          // blob id = rank in mass order (prep_id); one K0 block per SM less than would fit: the next chunk's gather runs beside it
                     k_launch += launch_prepare(sp, ctx->gather_list.as<int32_t>() + a, (int32_t)cnt, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(),
                                                ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st, 0, ctx->prep_id.as<int32_t>(), 1, ctx->k0_counters.as<uint32_t>() + 4 * c);
@@ -781,6 +833,12 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
             if (eager) { ctx->prepared_at_load = true; ctx->n_prepared = n_res; ctx->cnt.spectra_prepared = n_res; ctx->max_blob = blob_bytes(ctx->max_peaks); }
         }
         mk.mark("gather + K0 queued");
+        if (early.th.joinable()) early.th.join();
+        if (early.rc) return fail_load(early.rc, early.err.empty() ? ctx->err : early.err);
+        ctx->cnt.other_kernel_launches += early.launches; ctx->cnt.d2h_bytes += early.d2h;
+        if (early.digest) ctx->ref_digested = true;
+        if (early.shuffles) { ctx->shuffles_all = true; ctx->shuffles_epoch = ctx->targets_epoch; }
+        mk.mark("early work joined");
         if (stream_search && n_res) {
             // Steps 2-4 part by part while the rest of the spectra are still arriving
             LoadPlan plan{hj.njobs, hj.cand, n_res, chunk_spectra_cf, n_chunks_cf, &ctx->k0_ev};
@@ -860,7 +918,7 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
     CL(cudaGetLastError());
     // a protein database staged before the spectra (pq_stage_reference): its digest does not depend on them and runs now, on a
     // third stream, beside the work above
-    if (digest_here && !searched) {
+    if (digest_here && !searched && !ctx->ref_digested) {
         if (cf) { std::string err; if (!upload_target_keys_for_reference(ctx->st_aux, ctx->targets.seqs, ctx->reference.dev, err)) return fail_load(PQ_ERR_CUDA, "reference digest: " + err); }
         int32_t rc = digest_staged_reference(ctx, ctx->st_aux); if (rc) return fail_load(rc, ctx->err);
     }
@@ -1368,7 +1426,8 @@ template <class F> int32_t select_iota_on(pq_ctx* ctx, cudaStream_t st, DevBuf& 
 // Shuffles (K2) for the sequences / forms flagged in sh_seq_flag / sh_form_flag — or, all = true, for every target form with
 // all three list charges: plans (group order, round count), layout, generation, de-duplication, modification placement, cell
 // lists, MVH predicted-peak counts.  Synchronises st once (sizes).
-int32_t generate_shuffles(pq_ctx* ctx, cudaStream_t st, bool all, ShuffleTotals& tot, bool timed) {
+int32_t generate_shuffles(pq_ctx* ctx, cudaStream_t st, bool all, ShuffleTotals& tot, bool timed, pq_counters* sink) {
+    pq_counters& cnt = sink ? *sink : ctx->cnt;      // a helper thread counts into its own block
     const TargetAux A = ctx->aux();
     const size_t nseq = A.n_seq, nform = A.n_forms;
     if (all) {
@@ -1386,11 +1445,11 @@ int32_t generate_shuffles(pq_ctx* ctx, cudaStream_t st, bool all, ShuffleTotals&
         k += launch_shuffle_layout(ctx->sh_seq_flag.as<uint8_t>(), ctx->sh_form_flag.as<uint32_t>(), nullptr, 0, ctx->sh_plans.as<ShuffleSeq>(), A,
                                    ctx->sh_seq_slot.as<uint32_t>(), ctx->sh_form_slot.as<uint32_t>(), ctx->sh_row_base.as<uint32_t>(), ctx->sh_seqs.as<ShuffleSeq>(),
                                    ctx->sh_forms.as<ShuffleForm>(), ctx->sh_totals.as<ShuffleTotals>(), st);
-        ctx->cnt.other_kernel_launches += (uint64_t)k;
+        cnt.other_kernel_launches += (uint64_t)k;
     }
     CU(cudaMemcpyAsync(&tot, ctx->sh_totals.p, sizeof tot, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    ctx->cnt.d2h_bytes += sizeof tot;
+    cnt.d2h_bytes += sizeof tot;
     ctx->have_shuffles = true; ctx->have_lists = false;
     if (tot.n_seqs == 0) return PQ_OK;
     const uint32_t raw_rows = tot.raw_rows, out_rows = tot.out_rows, max_num = (uint32_t)std::max(ctx->P.n_random, 1);
@@ -1405,7 +1464,7 @@ int32_t generate_shuffles(pq_ctx* ctx, cudaStream_t st, bool all, ShuffleTotals&
                                 ctx->d_shufmods.as<ShuffleMods>(), ctx->sh_raw.as<uint8_t>(), ctx->sh_kidx.as<uint32_t>(), ctx->sh_kcnt.as<uint32_t>(),
                                 ctx->sh_rows.as<uint8_t>(), max_num, ctx->P.shuffle_seed, ctx->d_mods.as<ModTable>(), ctx->have_lists ? ctx->sh_lists.as<uint4>() : nullptr, st);
         if (ctx->P.score_method == 2) k += launch_predict(ctx->sh_rows.as<uint8_t>(), out_rows, ctx->d_mods.as<ModTable>(), ctx->P.itol, ctx->sh_pred.as<int32_t>(), st);
-        ctx->cnt.other_kernel_launches += (uint64_t)k;
+        cnt.other_kernel_launches += (uint64_t)k;
     };
     if (timed) { Timer t(ctx, &ctx->cnt.ms_shuffle); launch(); } else launch();
     CU(cudaGetLastError());

@@ -192,6 +192,10 @@ int launch_flags_by_virtual(int64_t nv, const int32_t* inv, const int32_t* flag_
 int launch_resident_counts(int64_t nv, const uint32_t* npeaks, const int32_t* resident, uint64_t* count, cudaStream_t st);
 int launch_gather_peaks_from_host(const int32_t* list, int32_t n_list, const int32_t* caller, const uint64_t* off_in, const uint64_t* off_out,
                                   const double* h_mz, const double* h_in, double* mz_out, double* in_out, int sms, cudaStream_t st);
+int launch_gather_peaks_chunked(const int32_t* list, int32_t n_list, int32_t chunk, const int32_t* caller, const uint64_t* off_in, const uint64_t* off_out,
+                                const double* h_mz, const double* h_in, double* mz_out, double* in_out, uint32_t* chunk_done /* zeroed, one word per chunk */,
+                                uint32_t* n_ctas, cudaStream_t st);
+int launch_wait_chunk(const uint32_t* flag, uint32_t expected, cudaStream_t st);      // the stream goes on once *flag >= expected
 int launch_invert_order(int64_t n, const int32_t* order, int32_t* inv, cudaStream_t st);
 int launch_gather_peaks_by_virtual(int64_t first, int64_t count, int64_t n, const int32_t* zero_idx, const int32_t* inv, const uint64_t* off_in,
                                    const uint64_t* off_out, const double* mz_in, const double* in_in, double* mz_out, double* in_out, cudaStream_t st);

