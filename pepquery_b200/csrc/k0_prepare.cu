@@ -634,6 +634,24 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             if (!(first & kCellClean) && (last & kCellClean)) g_cells[kCells - 1] = (uint16_t)(last & ~kCellClean);
         }
         if (lane == 1) *reinterpret_cast<uint4*>(g_cells + kCells) = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);      // the sentinel: always clean
+        // the clean flags once more as a bit map (pq_common.h: cbits), 32 cells per word
+        __syncwarp();
+        {
+            uint32_t* g_bits = reinterpret_cast<uint32_t*>(blob + BL.cbits);
+#pragma unroll 1
+            for (uint32_t w = lane; w < (uint32_t)kCells / 32; w += 32) {
+                const uint4* src = reinterpret_cast<const uint4*>(g_cells + 32 * w);
+                uint32_t bits = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 v = __ldcg(src + q);
+                    const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bits |= (((x[j] >> 15) & 1u) | ((x[j] >> 30) & 2u)) << (8 * q + 2 * j);
+                }
+                g_bits[w] = bits;
+            }
+        }
         if (METHOD == 1) for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = k < nsurv ? val[k] : 0.0;
         else for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = 0.0;
         if (lane == 0) {

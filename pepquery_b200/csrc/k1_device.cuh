@@ -33,7 +33,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 struct BlobView {
-    const double* ev; const uint16_t* ans; const double* pmz; const double* pin; const uint16_t* pcode; const double* val; const uint16_t* cells;
+    const double* ev; const uint16_t* ans; const double* pmz; const double* pin; const uint16_t* pcode; const double* val; const uint16_t* cells; const uint32_t* cbits;
     uint32_t E; uint32_t nsurv; uint32_t flags; int32_t cls[4];
 };
 __device__ __forceinline__ BlobView view_blob(const uint8_t* b) {
@@ -49,6 +49,7 @@ __device__ __forceinline__ BlobView view_blob(const uint8_t* b) {
     v.pcode = reinterpret_cast<const uint16_t*>(b + L.pcode);
     v.val = reinterpret_cast<const double*>(b + L.val);
     v.cells = reinterpret_cast<const uint16_t*>(b + L.cells);
+    v.cbits = reinterpret_cast<const uint32_t*>(b + L.cbits);
     return v;
 }
 
@@ -86,6 +87,8 @@ __device__ __forceinline__ uint32_t match_ion(const BlobView& B, double t, doubl
 }
 // Most theoretical m/z fall into cells where nothing can be claimed (kCellClean): one table load answers them.
 __device__ __forceinline__ bool ion_may_match(const BlobView& B, double t) { return reinterpret_cast<const int16_t*>(B.cells)[cell_filter(t)] >= 0; }   // kCellClean = sign bit
+// the same answer from the bit map (a blob read from global memory: 320 bytes instead of the 5 KB table)
+__device__ __forceinline__ bool ion_may_match_bits(const BlobView& B, double t) { const uint32_t c = cell_filter(t); return !((__ldg(B.cbits + (c >> 5)) >> (c & 31u)) & 1u); }
 
 struct Extra { int32_t site; double delta; };   // Step 5: one extra modification (site -1 = none)
 
@@ -146,7 +149,7 @@ __device__ __forceinline__ uint32_t row_byte(const uint32_t* codes, int idx) {
 // tab[code * TS] = {residue mass, modification mass} (one 16-byte shared-memory load per residue).  TS = 8: the table holds 8
 // copies of every entry, copy (lane & 7) at tab[code * 8 + (lane & 7)], and `tab` arrives offset by (lane & 7): the eight lanes
 // of a quarter-warp then hit eight different 16-byte bank groups whatever their residues are (no bank conflicts).
-template <int BLOCK, int METHOD, int NCH, int TS = 1>
+template <int BLOCK, int METHOD, int NCH, int TS = 1, bool BITS = false>
 __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this thread's column */, const BlobView& B,
                                                   const double2* tab, const double* ntd, const double* ctd,
                                                   int z, double itol, Extra ex,
@@ -164,6 +167,23 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
 
     // Claim in annotator order (A5): a surviving peak counts once, for the first ion that reaches it.
     // (A branch-free variant — a miss adding +0.0 — was measured slower on the Step-4 launch: most lanes miss.)
+    auto claim_value = [&](uint32_t code, bool is_b, double val_of_code) {      // METHOD 1 with B.val[code] already in hand
+        if (code == kAnsNone) return;
+        if (METHOD == 1) {
+            uint64_t bit = 1ull << code;
+            if (used & bit) return;
+            used |= bit;
+            if (is_b) ++ca; else ++cb;
+            sum = __dadd_rn(sum, val_of_code);
+        } else {
+            uint32_t sid = code & 0xFFFu;
+            uint32_t w = usedw[(sid >> 5) * BLOCK], bit = 1u << (sid & 31);
+            if (w & bit) return;
+            usedw[(sid >> 5) * BLOCK] = w | bit;
+            uint32_t c = (code >> 12) & 3u;
+            key0 += c == 0; key1 += c == 1; key2 += c == 2;
+        }
+    };
     auto claim = [&](uint32_t code, bool is_b) {
         if (code == kAnsNone) return;
         if (METHOD == 1) {
@@ -198,10 +218,33 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
     bool holding = METHOD == 1 && cutoff > 0.0;
     auto flush = [&]() {                                       // resolve everything queued, in ion order
         const int split = in_b ? qn : nb_q;
-        for (int i = 0; i < qn; ++i) claim(match_ion<METHOD>(B, q[i], itol), i < split);
+        if (BITS) {
+            // The blob sits in global memory (Step 2: a thread per spectrum): one ion's look-up is a chain of dependent misses
+            // (cell table -> events -> answer -> intensity), ~1 us each.  Four ions go through each stage together, so the misses
+            // of a stage overlap; the claims still happen one after the other in ion order.
+#pragma unroll 1
+            for (int i0 = 0; i0 < qn; i0 += 4) {
+                double t[4]; uint32_t k[4]; double e[4]; uint32_t a[4]; double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { t[u] = q[min(i0 + u, qn - 1)]; k[u] = __ldg(B.cells + cell_of(t[u])) & 0x7FFFu; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) e[u] = __ldg(B.ev + k[u] + 1);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { while (e[u] <= t[u]) { ++k[u]; e[u] = __ldg(B.ev + k[u] + 1); } a[u] = __ldg(B.ans + k[u]); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (a[u] >= kAnsTie && a[u] != kAnsNone) a[u] = match_ion_tie<METHOD>(B.pmz, B.pin, B.pcode, a[u] & 0xFFFu, t[u], itol);
+                    v[u] = (METHOD == 1 && a[u] != kAnsNone) ? __ldg(B.val + a[u]) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (i0 + u < qn) claim_value(a[u], i0 + u < split, v[u]);
+            }
+        } else {
+            for (int i = 0; i < qn; ++i) claim(match_ion<METHOD>(B, q[i], itol), i < split);
+        }
         qn = 0; nb_q = 0;
     };
-    auto push = [&](double t) { if (ion_may_match(B, t)) q[qn++] = t; };
+    auto push = [&](double t) { if (BITS ? ion_may_match_bits(B, t) : ion_may_match(B, t)) q[qn++] = t; };
     auto ion = [&](double m, int k) {
         push(__dadd_rn(m, kProton));
         if (nch >= 2 && k >= 2) push(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5));
@@ -264,15 +307,15 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
     return finish_pair<METHOD>(B, ca, cb, sum, key0, key1, key2, predicted, log10_fact, ln_fact);
 }
 
-template <int BLOCK, int METHOD, int TS = 1>
+template <int BLOCK, int METHOD, int TS = 1, bool BITS = false>
 __device__ __forceinline__ PairScore score_pair(const uint32_t* codes, const BlobView& B, const double2* tab, const double* ntd, const double* ctd,
                                                 int z, double itol, Extra ex, const double* log10_fact, const double* ln_fact, int32_t predicted,
                                                 uint32_t* usedw, double cutoff = 0.0) {
     switch (z) {                                  // fragment charges = precursor charge - 1, at least 1 (JMatch.java:398-407)
-        case 0: case 1: case 2: return score_pair_n<BLOCK, METHOD, 1, TS>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
-        case 3: return score_pair_n<BLOCK, METHOD, 2, TS>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
-        case 4: return score_pair_n<BLOCK, METHOD, 3, TS>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
-        default: return score_pair_n<BLOCK, METHOD, 0, TS>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
+        case 0: case 1: case 2: return score_pair_n<BLOCK, METHOD, 1, TS, BITS>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
+        case 3: return score_pair_n<BLOCK, METHOD, 2, TS, BITS>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
+        case 4: return score_pair_n<BLOCK, METHOD, 3, TS, BITS>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
+        default: return score_pair_n<BLOCK, METHOD, 0, TS, BITS>(codes, B, tab, ntd, ctd, z, itol, ex, log10_fact, ln_fact, predicted, usedw, cutoff);
     }
 }
 

@@ -261,7 +261,7 @@ k1_scatter_kernel(ScoreLaunch L, ScoreConfig cfg) {
             Extra ex; ex.site = -1; ex.delta = 0.0;
             int32_t pred = 0;
             if (METHOD == 2) pred = L.row_pred[2 * (size_t)row + (J.charge == 2 ? 0 : 1)];
-            PairScore ps = score_pair<BLOCK, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, pred, usedw, 0.0);
+            PairScore ps = score_pair<BLOCK, METHOD, 1, true>(codes, B, s_tab, s_nt, s_ct, J.charge, itol, ex, s_l10, L.ln_fact, pred, usedw, 0.0);      // ion filter from the blob's bit map
             ++n_in;
             if (ps.score > best) { best = ps.score; best_cand = row; }
             bool emit = false;

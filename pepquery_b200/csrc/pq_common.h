@@ -38,7 +38,7 @@ struct ModTable {
 
 // ---- prepared spectrum blob (output of K0, input of K1) -----------------------------------------------------------
 // Everything K1 needs about one spectrum, contiguous and 16-byte aligned so one cp.async.bulk stages it:
-//   BlobHeader | ev f64[NE] | ans u16[NE pad 8] | pmz f64[E+1 pad 2] | pin f64[E pad 2] | pcode u16[E pad 8] | val f64[kValSlots] | cells u16[kCells + 8]
+//   BlobHeader | ev f64[NE] | ans u16[NE pad 8] | pmz f64[E+1 pad 2] | pin f64[E pad 2] | pcode u16[E pad 8] | val f64[kValSlots] | cells u16[kCells + 8] | cbits u32[kCells / 32]
 //
 // The annotator's question "which matchable peak is the most intense one with |mz - t| <= itol" (JMatch.java:411-451,
 // A2-A4) has a piecewise-constant answer in t.  K0 inverts the predicate once per spectrum: for every matchable peak j
@@ -56,6 +56,9 @@ struct ModTable {
 //   cells : cells[c] = index of the last event below the lower edge of cell c of the monotone m/z -> cell map,
 //           | kCellClean when the whole cell answers 0xFFFF (K1 then skips the event scan); one more entry follows the table,
 //           always kCellClean: the precomputed cell lists of the reference rows (k1_ladder.cu) point unused slots at it
+//   cbits : the kCellClean flags of cells[] once more as a bit map (bit c of word c / 32): a kernel that reads the blob from
+//           global memory (Step 2, one or two pairs per spectrum) filters its ions from these 320 bytes instead of pulling the
+//           5 KB table through L2
 constexpr int kCellShift = 11;                              // 512 cells per binade
 constexpr uint32_t kCellBase = 0x40600000u >> kCellShift;   // high word of 128.0
 constexpr int kCells = 5 * 512;                             // [128, 4096) Th; below / above clamp to the first / last cell
@@ -79,7 +82,7 @@ struct BlobHeader {
 };
 static_assert(sizeof(BlobHeader) == 48, "BlobHeader must stay 16-byte aligned");
 
-struct BlobLayout { uint32_t ev, ans, pmz, pin, pcode, val, cells, total; };
+struct BlobLayout { uint32_t ev, ans, pmz, pin, pcode, val, cells, cbits, total; };
 PQ_HD BlobLayout blob_layout(uint32_t E) {
     BlobLayout L;
     const uint32_t ne = 2u * E + 2u;
@@ -90,7 +93,8 @@ PQ_HD BlobLayout blob_layout(uint32_t E) {
     L.pcode = L.pin + ((E * 8u + 15u) & ~15u);
     L.val = L.pcode + ((E * 2u + 15u) & ~15u);
     L.cells = L.val + kValSlots * 8u;
-    L.total = L.cells + kCells * 2u + 16u;                      // + the always-clean sentinel entry (padded to 16 bytes)
+    L.cbits = L.cells + kCells * 2u + 16u;                      // behind the always-clean sentinel entry (padded to 16 bytes)
+    L.total = L.cbits + kCells / 8u;
     return L;
 }
 PQ_HD uint32_t blob_bytes(uint32_t n_peaks) { return blob_layout(n_peaks).total; }
