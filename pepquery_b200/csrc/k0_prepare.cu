@@ -124,24 +124,40 @@ __device__ __noinline__ void isotope_pass_p(const double* mz, const double* in, 
 
 __device__ __forceinline__ void isotope_pass(const WarpMem& W, uint32_t P, double gap, int lane) { isotope_pass_p(W.mz, W.in, W.ord, W.keep, W.k2, W.aux, P, gap, lane); }
 
-// rank from the top among the kept entries by (intensity, m/z position): g = #kept j with I_j > I_i or (I_j == I_i and j > i)
-__device__ __noinline__ void top_rank_p(const uint8_t* keep, const double* in, const uint16_t* ord, uint32_t P, uint16_t* out, int lane) {
+// rank from the top among the kept entries by (intensity, m/z position): g = #kept j with I_j > I_i or (I_j == I_i and j > i).
+// The kept intensities are first compacted (cv, positions in cp; m/z order survives), so the quadratic part runs over the kept
+// entries only, one broadcast load per comparison partner, two ranked entries per lane and trip.
+__device__ __noinline__ void top_rank_p(const uint8_t* keep, const double* in, const uint16_t* ord, uint32_t P, uint16_t* out, int lane,
+                                        double* cv, uint16_t* cp) {
+    uint32_t K = 0;
     #pragma unroll 1
-    for (uint32_t i = lane; i < P; i += 32) {
-        uint32_t g = 0;
-        if (keep[i]) {
-            double vi = in[ord[i]];
-            for (uint32_t j = 0; j < P; ++j) {
-                if (!keep[j]) continue;
-                double vj = in[ord[j]];
-                g += (vj > vi || (vj == vi && j > i)) ? 1u : 0u;
-            }
+    for (uint32_t c0 = 0; c0 < P; c0 += 32) {
+        const uint32_t i = c0 + lane;
+        const bool k = i < P && keep[i];
+        const uint32_t bal = __ballot_sync(0xffffffffu, k);
+        if (i < P) out[i] = 0;
+        if (k) { const uint32_t pos = K + __popc(bal & ((1u << lane) - 1u)); cv[pos] = in[ord[i]]; cp[pos] = (uint16_t)i; }
+        K += __popc(bal);
+    }
+    __syncwarp();
+    #pragma unroll 1
+    for (uint32_t k0 = lane; k0 < K; k0 += 64) {
+        const uint32_t a = k0, b = k0 + 32;
+        const bool hb = b < K;
+        const double va = cv[a], vb = hb ? cv[b] : 0.0;
+        uint32_t ga = 0, gb = 0;
+        #pragma unroll 4
+        for (uint32_t j = 0; j < K; ++j) {
+            const double vj = cv[j];
+            ga += (vj > va || (vj == va && j > a)) ? 1u : 0u;
+            gb += (vj > vb || (vj == vb && j > b)) ? 1u : 0u;
         }
-        out[i] = (uint16_t)g;
+        out[cp[a]] = (uint16_t)ga;
+        if (hb) out[cp[b]] = (uint16_t)gb;
     }
     __syncwarp();
 }
-__device__ __forceinline__ void top_rank(const WarpMem& W, uint32_t P, uint16_t* out, int lane) { top_rank_p(W.keep, W.in, W.ord, P, out, lane); }
+__device__ __forceinline__ void top_rank(const WarpMem& W, uint32_t P, uint16_t* out, int lane) { top_rank_p(W.keep, W.in, W.ord, P, out, lane, W.da, W.cx); }      // da / cx are free whenever a rank is taken
 // keep only the `top` largest kept entries: JMatch.filterByPeakCount (:148-174)
 __device__ void keep_top(const WarpMem& W, uint32_t P, uint32_t top, int lane) {
     top_rank(W, P, W.aux, lane);
@@ -204,7 +220,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         const double prec_mz = sp.prec_mz[s];
         int z = sp.charge[s]; if (z == 0) z = 1;
 
-        bool sorted = true;
+        bool sorted = true, nonneg = true;
         #pragma unroll 1
         for (uint32_t i = lane; i < n; i += 32) {
             double m = i < P ? sp.mz[base + i] : inf;
@@ -212,8 +228,10 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             W.in[i] = i < P ? sp.inten[base + i] : inf;
             W.ord[i] = (uint16_t)i; W.ordI[i] = (uint16_t)i;
             if (i > 0 && i < P && !(sp.mz[base + i - 1] <= m)) sorted = false;
+            if (i < P && !(W.in[i] >= 0.0)) nonneg = false;
         }
         sorted = __all_sync(0xffffffffu, sorted);
+        nonneg = __all_sync(0xffffffffu, nonneg);
         __syncwarp();
         if (!sorted) warp_sort_idx(W.ord, W.mz, n, lane);          // stable m/z order (JSpectrum.sortPeaksByMZ)
 
@@ -225,7 +243,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             const double indexDouble = P > 1 ? __dmul_rn(0.05, (double)(P - 1)) : 0.0;
             const int index = (int)indexDouble;
             double valueAtIndex, valueNext = 0.0;
-            const bool extract = METHOD == 1 && P <= 256 && index + 2 <= 24;
+            const bool extract = METHOD == 1 && P <= 256 && index + 2 <= 24 && nonneg;
             if (!extract) {
                 warp_sort_idx(W.ordI, W.in, n, lane);              // stable intensity order (JSpectrum.sortPeaksByIntensity)
                 #pragma unroll 1
@@ -234,21 +252,37 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
                 valueAtIndex = W.da[index];
                 if (index + 1 < (int)P) valueNext = W.da[index + 1];
             } else {
-                uint32_t taken = 0;                                 // bit q: this lane's element lane + 32 q is already extracted
+                // Every lane sorts its own (up to eight) intensities in registers; a round then takes the warp minimum of the lanes'
+                // heads — non-negative doubles order like their bit patterns, so two 32-bit warp reductions (high word, then low
+                // word among the lanes that tie on it) find it — and the lane that held it moves on to its next value.  Ties may be
+                // taken in any order: only the values matter.
+                double v0 = inf, v1 = inf, v2 = inf, v3 = inf, v4 = inf, v5 = inf, v6 = inf, v7 = inf;
+                if ((uint32_t)lane < P) v0 = W.in[lane];
+                if ((uint32_t)lane + 32 < P) v1 = W.in[lane + 32];
+                if ((uint32_t)lane + 64 < P) v2 = W.in[lane + 64];
+                if ((uint32_t)lane + 96 < P) v3 = W.in[lane + 96];
+#define K0_CE(a, b) { const double lo_ = fmin(a, b), hi_ = fmax(a, b); a = lo_; b = hi_; }
+                if (P <= 128) { K0_CE(v0, v1) K0_CE(v2, v3) K0_CE(v0, v2) K0_CE(v1, v3) K0_CE(v1, v2) }
+                else {
+                    if ((uint32_t)lane + 128 < P) v4 = W.in[lane + 128];
+                    if ((uint32_t)lane + 160 < P) v5 = W.in[lane + 160];
+                    if ((uint32_t)lane + 192 < P) v6 = W.in[lane + 192];
+                    if ((uint32_t)lane + 224 < P) v7 = W.in[lane + 224];
+                    K0_CE(v0, v1) K0_CE(v2, v3) K0_CE(v4, v5) K0_CE(v6, v7) K0_CE(v0, v2) K0_CE(v1, v3) K0_CE(v4, v6) K0_CE(v5, v7)
+                    K0_CE(v1, v2) K0_CE(v5, v6) K0_CE(v0, v4) K0_CE(v3, v7) K0_CE(v1, v5) K0_CE(v2, v6) K0_CE(v1, v4) K0_CE(v3, v6)
+                    K0_CE(v2, v4) K0_CE(v3, v5) K0_CE(v3, v4)
+                }
+#undef K0_CE
                 valueAtIndex = 0.0;
                 #pragma unroll 1
                 for (int r = 0; r <= index + 1 && r < (int)P; ++r) {
-                    double best = inf; int bq = -1;
-                    for (uint32_t q = 0, i = lane; i < P; ++q, i += 32)
-                        if (!((taken >> q) & 1u)) { double v = W.in[i]; if (bq < 0 || v < best) { best = v; bq = (int)q; } }
-                    // warp minimum by (value, lane): ties may be taken in any order, only the values matter
-                    double mv = best; int ml = bq >= 0 ? lane : 64;
-                    #pragma unroll 1
-                    for (int o = 16; o > 0; o >>= 1) {
-                        double ov = __shfl_xor_sync(0xffffffffu, mv, o); int ol = __shfl_xor_sync(0xffffffffu, ml, o);
-                        if (ol < 64 && (ml >= 64 || ov < mv || (ov == mv && ol < ml))) { mv = ov; ml = ol; }
-                    }
-                    if (ml == lane) taken |= 1u << bq;
+                    const uint32_t hi = (uint32_t)__double2hiint(v0);
+                    const uint32_t mh = __reduce_min_sync(0xffffffffu, hi);
+                    const uint32_t lo = hi == mh ? (uint32_t)__double2loint(v0) : 0xFFFFFFFFu;
+                    const uint32_t ml = __reduce_min_sync(0xffffffffu, lo);
+                    const uint32_t ball = __ballot_sync(0xffffffffu, hi == mh && lo == ml);
+                    if (lane == __ffs((int)ball) - 1) { v0 = v1; v1 = v2; v2 = v3; v3 = v4; v4 = v5; v5 = v6; v6 = v7; v7 = inf; }
+                    const double mv = __hiloint2double((int)mh, (int)ml);
                     if (r == index) valueAtIndex = mv;
                     if (r == index + 1) valueNext = mv;
                 }
@@ -540,18 +574,16 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         if (lane == 0) { g_ev[0] = -inf; g_ans[0] = (uint16_t)kAnsNone; }
         // ---- merge neighbouring intervals with the same answer (a peak entering or leaving under a stronger one, windows of
         // peaks that did not survive pre-processing): only the change points stay, about half of the 2E events.  In-place
-        // left compaction, 32 events at a time (every lane reads its event before any lane writes).  The kept events also
-        // fill the per-cell histogram of the cell table below (shared memory the dead work arrays leave behind).
+        // left compaction, 32 events at a time (every lane reads its event before any lane writes).  The cell of every
+        // kept event is noted for the cell table below (shared memory the dead work arrays leave behind).
         // (Deciding "kept" while the events are created — comparing the window just below each event with the window at it —
         // avoids this read-back but measured slower: 17.2 vs 14.5 ms for K0.)
         __syncwarp();
-        // (every work array is dead once the events are in global memory: the histogram takes the warp's region from its start)
-        uint32_t* hist = reinterpret_cast<uint32_t*>(W.mz);                          // kCells u16 counters, two per word
-        uint32_t* none_bits = hist + kCells / 2;                                     // bit k: kept event k answers "nothing" (2E+2 bits)
-        #pragma unroll 1
-        for (uint32_t k = lane; k < (uint32_t)kCells / 2 + (NE + 31u) / 32u; k += 32) hist[k] = 0u;
-        __syncwarp();
-        if (lane == 0) none_bits[0] = 1u;                                            // the -inf sentinel
+        // (every work array is dead once the events are in global memory: the cell table is assembled at the start of the warp's
+        // region, the cell of every kept event — top bit: the event answers "nothing" — behind it)
+        uint16_t* cells_s = reinterpret_cast<uint16_t*>(W.mz);                       // kCells entries, copied out at the end
+        uint16_t* ecell = cells_s + kCells + 8;                                      // [kept]
+        if (lane == 0) ecell[0] = (uint16_t)kCellClean;                              // the -inf sentinel: below every cell, answers "nothing"
         uint32_t kept = 1;                                                           // slot 0 = the -inf sentinel
         {
             uint32_t prev_code = kAnsNone;
@@ -571,9 +603,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
                 if (keep) {
                     const uint32_t idx = kept + __popc(bal & ((1u << lane) - 1u));
                     g_ev[idx] = v; g_ans[idx] = (uint16_t)code;
-                    const int c = cell_of(v);
-                    atomicAdd(&hist[c >> 1], 1u << (16 * (c & 1)));
-                    if (code == kAnsNone) atomicOr(&none_bits[idx >> 5], 1u << (idx & 31));
+                    ecell[idx] = (uint16_t)((uint32_t)cell_of(v) | (code == kAnsNone ? kCellClean : 0u));
                 }
                 kept += __popc(bal);
                 __syncwarp();
@@ -583,75 +613,62 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
         if (lane == 0) { g_ev[kept] = inf; g_ans[kept] = (uint16_t)kAnsNone; }
         #pragma unroll 1
         for (uint32_t k = NE2 + lane; k < ((NE2 + 7u) & ~7u); k += 32) g_ans[k] = (uint16_t)kAnsNone;
-        // ---- cell table: cells[c] = number of real events below the lower edge of cell c (= index of the last of them).
-        // An event lies below the lower edge of exactly the cells above its own, so cells[] is the exclusive prefix sum of
-        // the per-cell event histogram.
+        // ---- cell table: cells[c] = number of real events below the lower edge of cell c (= index of the last of them), i.e.
+        // kept event k owns the cells above its own up to and including the cell of event k + 1 (the last event: up to the end of
+        // the table).  kCellClean: no event inside the cell and nothing to claim at its lower edge, i.e. every t of the cell
+        // answers "nothing" — all owned cells but the one event k + 1 lies in, when event k answers "nothing": K1 skips the event
+        // scan for such cells (most of the m/z axis).  One lane per event; the ranges tile the table, nothing needs clearing.
         __syncwarp();
-        {
-            constexpr uint32_t kPerLane = (uint32_t)kCells / 32;                       // 80 consecutive cells per lane
-            static_assert(kCells % (32 * 8) == 0, "cell table must split into uint4 chunks per lane");
-            const uint16_t* h16 = reinterpret_cast<const uint16_t*>(hist);
-            const uint4* h128 = reinterpret_cast<const uint4*>(h16 + lane * kPerLane);      // this lane's 80 counters = 10 x 16 bytes
-            uint32_t mine = 0;
-#pragma unroll
-            for (uint32_t k = 0; k < kPerLane / 8; ++k) {
-                const uint4 v = h128[k];
-                mine += (v.x & 0xFFFFu) + (v.x >> 16) + (v.y & 0xFFFFu) + (v.y >> 16) + (v.z & 0xFFFFu) + (v.z >> 16) + (v.w & 0xFFFFu) + (v.w >> 16);
+        #pragma unroll 1
+        for (uint32_t k0 = 0; k0 < kept; k0 += 32) {
+            const uint32_t k = k0 + lane;
+            uint32_t first_c = 1, end_c = 0, vb = 0, ve = 0, last = 0;
+            if (k < kept) {
+                const uint32_t ec = ecell[k];
+                last = k + 1 >= kept ? 1u : 0u;
+                first_c = k == 0 ? 0u : (ec & 0x7FFFu) + 1u;
+                end_c = last ? (uint32_t)kCells - 1u : (uint32_t)(ecell[k + 1] & 0x7FFFu);          // inclusive
+                vb = k | (ec & kCellClean); ve = k;
             }
-            uint32_t incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            uint32_t run = incl - mine;
-            // kCellClean: no event inside the cell and nothing to claim at its lower edge, i.e. every t of the cell answers
-            // "nothing": K1 skips the event scan for such cells (most of the m/z axis).  Eight cells per 16-byte store; a group
-            // without events (the usual case) is one value repeated.
-            auto word_of = [&](uint32_t here) -> uint32_t {
-                const uint32_t none = (none_bits[run >> 5] >> (run & 31)) & 1u;
-                const uint32_t w = run | ((here == 0u && none) ? kCellClean : 0u);
-                run += here;
-                return w;
-            };
-#pragma unroll 1
-            for (uint32_t k = 0; k < kPerLane / 8; ++k) {
-                const uint4 v = h128[k];
-                uint4 o;
-                if ((v.x | v.y | v.z | v.w) == 0u) {
-                    const uint32_t w = word_of(0u); const uint32_t ww = w | (w << 16);
-                    o = make_uint4(ww, ww, ww, ww);
-                } else {
-                    uint32_t a0 = word_of(v.x & 0xFFFFu), a1 = word_of(v.x >> 16), a2 = word_of(v.y & 0xFFFFu), a3 = word_of(v.y >> 16);
-                    uint32_t a4 = word_of(v.z & 0xFFFFu), a5 = word_of(v.z >> 16), a6 = word_of(v.w & 0xFFFFu), a7 = word_of(v.w >> 16);
-                    o = make_uint4(a0 | (a1 << 16), a2 | (a3 << 16), a4 | (a5 << 16), a6 | (a7 << 16));
-                }
-                reinterpret_cast<uint4*>(g_cells + lane * kPerLane)[k] = o;
+            const bool wide = end_c + 1u > first_c + 24u;              // a long stretch of the axis without events: the whole warp fills it
+            if (!wide) {
+                #pragma unroll 1
+                for (uint32_t c = first_c; c <= end_c; ++c) cells_s[c] = (uint16_t)((c < end_c || last) ? vb : ve);
+            }
+            uint32_t todo = __ballot_sync(0xffffffffu, wide);
+            #pragma unroll 1
+            while (todo) {
+                const int src = __ffs((int)todo) - 1;
+                todo &= todo - 1;
+                const uint32_t f = __shfl_sync(0xffffffffu, first_c, src), e = __shfl_sync(0xffffffffu, end_c, src);
+                const uint32_t b = __shfl_sync(0xffffffffu, vb, src), v = __shfl_sync(0xffffffffu, ve, src), l = __shfl_sync(0xffffffffu, last, src);
+                for (uint32_t c = f + lane; c <= e; c += 32) cells_s[c] = (uint16_t)((c < e || l) ? b : v);
             }
         }
+        __syncwarp();
         // cell_filter() sends every m/z outside the table to the last cell: it may only stay clean if cell 0 (all events below
         // 128 Th) is clean too
-        __syncwarp();
         if (lane == 0) {
-            const uint16_t first = __ldcg(g_cells), last = __ldcg(g_cells + kCells - 1);
-            if (!(first & kCellClean) && (last & kCellClean)) g_cells[kCells - 1] = (uint16_t)(last & ~kCellClean);
+            const uint16_t first = cells_s[0], last = cells_s[kCells - 1];
+            if (!(first & kCellClean) && (last & kCellClean)) cells_s[kCells - 1] = (uint16_t)(last & ~kCellClean);
         }
-        if (lane == 1) *reinterpret_cast<uint4*>(g_cells + kCells) = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);      // the sentinel: always clean
-        // the clean flags once more as a bit map (pq_common.h: cbits), 32 cells per word
         __syncwarp();
+        // copy-out, 16 bytes per lane and trip (coalesced), and the clean flags once more as a bit map (pq_common.h: cbits)
         {
+            static_assert(kCells % (32 * 8) == 0, "cell table must split into uint4 chunks per lane");
             uint32_t* g_bits = reinterpret_cast<uint32_t*>(blob + BL.cbits);
-#pragma unroll 1
-            for (uint32_t w = lane; w < (uint32_t)kCells / 32; w += 32) {
-                const uint4* src = reinterpret_cast<const uint4*>(g_cells + 32 * w);
-                uint32_t bits = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint4 v = __ldcg(src + q);
-                    const uint32_t x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) bits |= (((x[j] >> 15) & 1u) | ((x[j] >> 30) & 2u)) << (8 * q + 2 * j);
-                }
-                g_bits[w] = bits;
+            #pragma unroll 2
+            for (uint32_t k = 0; k < (uint32_t)kCells / 256; ++k) {
+                const uint32_t q = lane + 32 * k;
+                const uint4 v = reinterpret_cast<const uint4*>(cells_s)[q];
+                reinterpret_cast<uint4*>(g_cells)[q] = v;
+                const uint32_t b8 = ((v.x >> 15) & 1u) | ((v.x >> 30) & 2u) | (((v.y >> 15) & 1u) << 2) | (((v.y >> 30) & 2u) << 2) |
+                                    (((v.z >> 15) & 1u) << 4) | (((v.z >> 30) & 2u) << 4) | (((v.w >> 15) & 1u) << 6) | (((v.w >> 30) & 2u) << 6);
+                const uint32_t w = b8 | (__shfl_down_sync(0xffffffffu, b8, 1) << 8) | (__shfl_down_sync(0xffffffffu, b8, 2) << 16) | (__shfl_down_sync(0xffffffffu, b8, 3) << 24);
+                if ((lane & 3) == 0) g_bits[q >> 2] = w;
             }
         }
+        if (lane == 1) *reinterpret_cast<uint4*>(g_cells + kCells) = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);      // the sentinel: always clean
         if (METHOD == 1) for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = k < nsurv ? val[k] : 0.0;
         else for (uint32_t k = lane; k < (uint32_t)kValSlots; k += 32) g_val[k] = 0.0;
         if (lane == 0) {
