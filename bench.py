@@ -584,6 +584,7 @@ def main():
                                  "kernel_ms": {"k1_step3": c3.ms_score_step[1] / 3, "k1_step4": c3.ms_score_step[2] / 3, "k0": c3.ms_prepare / 3, "k2+k4": c3.ms_shuffle / 3}}
                 g.close()
                 configs["C4"] = run_c4(a, mk_params, sp, tgt, prot, rank, quiet=True)
+                configs["F1_mgf"] = run_mgf(a, mk_params, sp, pinned)
             configs["C5_shard"] = run_c5_shard(a, mk_params, pinned, rank, world, timed, total_over_ranks, gather_psms, size_gather_buffers)
         except Exception as e:                     # the headline line must survive a failing side config
             configs["error"] = repr(e)[:300]
@@ -627,6 +628,38 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_mgf(a, mk_params, sp, pinned):
+    """MGF text -> CSR arrays on the device (pq_parse_mgf_device; text in pinned host memory, the upload is inside the time)
+    and text -> loaded spectra (pq_load_mgf), on the text of the first 200 000 spectra of the workload; the host-threaded parser beside it."""
+    import torch
+    from pepquery_b200 import Search, host, synth
+    n = min(200000, len(sp["prec_mz"]))
+    end = int(sp["peak_off"][n])
+    sub = {"prec_mz": sp["prec_mz"][:n], "charge": sp["charge"][:n], "peak_off": sp["peak_off"][:n + 1], "mz": sp["mz"][:end], "inten": sp["inten"][:end]}
+    text = synth.mgf_text(sub, out=lambda nb: pinned((nb + 7) // 8).view(np.uint8)[:nb])
+    gb = text.nbytes / 1e9
+    g = Search(mk_params(1))
+    ptr = lambda t: t.ctypes.data_as(C.c_void_p)
+    ns, npk = C.c_int64(0), C.c_uint64(0)
+    td = []
+    for it in range(4):
+        t = text if it % 2 == 0 else text[:text.nbytes - 1]          # (a repeated call on the same text would return the cached parse)
+        t0 = time.perf_counter()
+        rc = g.L.pq_parse_mgf_device(g.h, ptr(t), C.c_uint64(t.nbytes), C.byref(ns), C.byref(npk), None, None, None, None, None)
+        torch.cuda.synchronize()
+        td.append(time.perf_counter() - t0)
+        if rc != 0:
+            raise RuntimeError("pq_parse_mgf_device rc %d" % rc)
+    tl = []
+    for it in range(3):
+        t0 = time.perf_counter(); g.load_mgf(text); torch.cuda.synchronize(); tl.append(time.perf_counter() - t0)
+    t0 = time.perf_counter(); host.parse_mgf(bytes(text)); th = time.perf_counter() - t0
+    g.close()
+    return {"workload": "MGF text of %d spectra (%.2f GB, TITLE/PEPMASS/CHARGE + '%%.4f %%.2f' peak lines), pinned host memory" % (n, gb),
+            "device_parse_GBps": gb / min(td[1:]), "device_parse_ms": 1e3 * min(td[1:]), "load_mgf_GBps": gb / min(tl[1:]), "load_mgf_ms": 1e3 * min(tl[1:]),
+            "host_parse_GBps": gb / th, "spectra": int(ns.value), "peaks": int(npk.value)}
 
 
 def run_small_config(a, mk_params, pinned, gather_psms, size_gather_buffers, timed):

@@ -630,7 +630,7 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
                 end_c = last ? (uint32_t)kCells - 1u : (uint32_t)(ecell[k + 1] & 0x7FFFu);          // inclusive
                 vb = k | (ec & kCellClean); ve = k;
             }
-            const bool wide = end_c + 1u > first_c + 24u;              // a long stretch of the axis without events: the whole warp fills it
+            const bool wide = end_c + 1u > first_c + 64u;              // a long stretch of the axis without events: the whole warp fills it
             if (!wide) {
                 #pragma unroll 1
                 for (uint32_t c = first_c; c <= end_c; ++c) cells_s[c] = (uint16_t)((c < end_c || last) ? vb : ve);
