@@ -88,7 +88,8 @@ typedef struct pq_params {
     int32_t hc;                 /* CParameter.unrestrictedSearchWithEqualAndBetterScore (-hc)          */
     int32_t n_random;           /* CParameter.nRandomPeptides (-n), reference default 10000            */
     int32_t enzyme;             /* -e index of pg/DatabaseInput.java:145-267: 1 Trypsin (default) ... 17
-                                   LysargiNase; 0 = NoEnzyme (unspecific digestion) is not supported      */
+                                   LysargiNase; 0 = NoEnzyme: unspecific digestion, every stretch of a protein
+                                   within the length and mass bounds (max_missed is not used then)        */
     int32_t max_missed;         /* CParameter.maxMissedCleavages, default 2                            */
     int32_t min_len, max_len;   /* 7 / 45                                                              */
     double  min_mass, max_mass; /* 500 / 10000 (digest mass window)                                    */

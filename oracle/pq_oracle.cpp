@@ -777,13 +777,18 @@ static void digest_protein(const Params& P, std::string prot, std::set<std::stri
     };
     const auto& E = kEnzymes[(P.p.enzyme >= 1 && P.p.enzyme <= 17) ? P.p.enzyme : 1];
     auto in = [](const char* set, char c) { return strchr(set, c) != nullptr && c != 0; };
+    // enzyme 0 = NoEnzyme (pg/DatabaseInput.java:117-121,149-156): CleavageParameter.unSpecific — every stretch of the protein whose mass
+    // lies in the digest window is a peptide (A14: compomics' unspecific iterator; missed cleavages play no role); the length filter
+    // of DigestProteinWorker.java:96 then keeps min_len .. max_len residues
+    const bool unspecific = P.p.enzyme == 0;
     std::vector<int> starts; starts.push_back(0);
     for (int i = 0; i < n - 1; ++i)
-        if ((in(E.before, prot[i]) && !in(E.restrict_after, prot[i + 1])) || in(E.after, prot[i + 1])) starts.push_back(i + 1);
+        if (unspecific || (in(E.before, prot[i]) && !in(E.restrict_after, prot[i + 1])) || in(E.after, prot[i + 1])) starts.push_back(i + 1);
     starts.push_back(n);
     int ns = (int)starts.size() - 1;
+    const int max_joined = unspecific ? P.p.max_len - 1 : P.p.max_missed;
     for (int i = 0; i < ns; ++i) {
-        for (int mc = 0; mc <= P.p.max_missed && i + mc < ns; ++mc) {
+        for (int mc = 0; mc <= max_joined && i + mc < ns; ++mc) {
             int a = starts[i], e = starts[i + mc + 1];
             int len = e - a;
             if (len <= 0) continue;

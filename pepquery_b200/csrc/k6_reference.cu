@@ -405,11 +405,13 @@ bool digest_reference_on_device(cudaStream_t st, const pq_params& P, const Codes
     RB(cudaStreamSynchronize(st));
     k6_set_u32<<<1, 1, 0, st>>>(T.starts.as<uint32_t>() + n_seg, n);          // (no host-to-device copy here: the copy engine may be busy with the spectra)
     // candidate peptides
-    const uint32_t per = (uint32_t)P.max_missed + 1;
+    // NoEnzyme (enzyme 0, pg/DatabaseInput.java:117-121): unspecific digestion — every residue starts a piece and a peptide is any
+    // run of up to max_len pieces, i.e. every stretch of the protein that passes the length and mass filters
+    const uint32_t per = P.enzyme == 0 ? (uint32_t)std::max(P.max_len, 1) : (uint32_t)P.max_missed + 1;
     const uint64_t n_slots64 = (uint64_t)n_seg * per;
     if (n_slots64 >= 0x7fffff00ull) { err = "too many digestion candidates"; return false; }
     const uint32_t n_slots = (uint32_t)n_slots64;
-    DigestCfg dc; dc.max_missed = P.max_missed; dc.min_len = P.min_len; dc.max_len = P.max_len; dc.min_mass = P.min_mass; dc.max_mass = P.max_mass;
+    DigestCfg dc; dc.max_missed = (int32_t)per - 1; dc.min_len = P.min_len; dc.max_len = P.max_len; dc.min_mass = P.min_mass; dc.max_mass = P.max_mass;
     for (int i = 0; i < 26; ++i) dc.residue_mass[i] = codes.residue_mass[i];
     RB(d_flags.reserve((size_t)n_slots + 64)); RB(d_cand.reserve(((size_t)n_slots + 2) * 4));
     k6_candidate_flags<<<(n_slots + 255) / 256, 256, 0, st>>>(T.starts.as<uint32_t>(), n_seg, d_first.as<uint8_t>(), d_res, dc, d_flags.as<uint8_t>());

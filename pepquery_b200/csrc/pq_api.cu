@@ -394,7 +394,7 @@ int32_t pq_create(const pq_params* params, pq_ctx** out) {
     if (params->n_isotope < 1 || params->n_isotope > PQ_MAX_ISOTOPE) return fail(nullptr, PQ_ERR_BAD_ARG, "n_isotope out of range");
     { bool has0 = false; for (int i = 0; i < params->n_isotope; ++i) has0 |= params->isotope[i] == 0; if (!has0) return fail(nullptr, PQ_ERR_BAD_ARG, "isotope error list must contain 0 (CParameter.java:436-446)"); }
     if (!(params->itol > 0) || !(params->tol >= 0)) return fail(nullptr, PQ_ERR_BAD_ARG, "tolerances must be positive");
-    { EnzymeRule er; if (!enzyme_rule(params->enzyme, er)) return fail(nullptr, PQ_ERR_UNSUPPORTED, "enzyme must be 1..17 (pg/DatabaseInput.java:145-267); 0 = NoEnzyme (unspecific digestion) is not supported"); }
+    { EnzymeRule er; if (!enzyme_rule(params->enzyme, er)) return fail(nullptr, PQ_ERR_UNSUPPORTED, "enzyme must be 0..17 (pg/DatabaseInput.java:145-267)"); }
     if (params->max_len > kMaxLen) return fail(nullptr, PQ_ERR_UNSUPPORTED, "max_len > 60");
     ctx = new pq_ctx();
     ctx->P = *params;

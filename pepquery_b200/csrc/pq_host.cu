@@ -200,11 +200,11 @@ void Codes::decode_row(const uint8_t* row, std::string& seq, FormRec& out) const
 bool enzyme_rule(int32_t index, EnzymeRule& out) {
     struct Def { const char* after; const char* before; const char* block; };
     static const Def defs[18] = {
-        {"", "", ""},            // 0 NoEnzyme
+        {"ABCDEFGHIJKLMNOPQRSTUVWXYZ", "", ""},      // 0 NoEnzyme: unspecific digestion, every residue ends a piece (K6 then joins up to max_len of them)
         {"RK", "", "P"}, {"RK", "", ""}, {"R", "", "P"}, {"R", "", ""}, {"", "R", ""}, {"E", "", ""}, {"K", "", "P"}, {"K", "", ""},
         {"", "K", ""}, {"", "D", ""}, {"", "DE", ""}, {"FYWL", "", "P"}, {"FYWL", "", ""}, {"FL", "", ""}, {"M", "", ""},
         {"", "AFILMV", ""}, {"", "RK", ""}};
-    if (index < 1 || index > 17) return false;
+    if (index < 0 || index > 17) return false;
     auto mask = [](const char* s) { uint32_t m = 0; for (; *s; ++s) m |= 1u << (*s - 'A'); return m; };
     out.cut_after = mask(defs[index].after); out.cut_before = mask(defs[index].before); out.block_next = mask(defs[index].block);
     return true;

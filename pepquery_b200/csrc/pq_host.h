@@ -49,7 +49,7 @@ struct Codes {
 // (x in cut_after and y not in block_next) or (y in cut_before).  pg/DatabaseInput.java:145-267 lists 17 enzymes
 // (index = the -e option); compomics Enzyme.isCleavageSite applies the rule (A10).
 struct EnzymeRule { uint32_t cut_after, cut_before, block_next; };
-bool enzyme_rule(int32_t index, EnzymeRule& out);          // false: unknown index or 0 (NoEnzyme, unspecific: not supported)
+bool enzyme_rule(int32_t index, EnzymeRule& out);          // false: unknown index; 0 = NoEnzyme (unspecific digestion: every residue ends a piece)
 
 // The reference table as K6 builds it on the device (k6_reference.cu).  rows/mass point at the table's DevBufs.
 struct RefDeviceTable {

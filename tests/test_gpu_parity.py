@@ -378,9 +378,18 @@ def test_enzymes(data, enzyme):
     assert g.counters().reference_forms > 1000
 
 
-def test_enzyme_zero_is_refused():
+def test_no_enzyme_is_unspecific_digestion():
+    """-e 0 (NoEnzyme, pg/DatabaseInput.java:117-121): every stretch of a protein within the length and mass bounds is a reference
+    peptide.  A small database (the candidate count is residues x lengths); table, Step 3 and Step 4 against the oracle."""
+    prot = synth.proteins(40)
+    tgt = synth.targets(30)
+    sp = synth.spectra(400, tgt, prot)
+    p = _abi.default_params(n_random=30, enzyme=0, min_len=7, max_len=20)
+    g, o, got = full_compare(p, sp, tgt, prot)
+    off, res = prot
+    assert g.counters().reference_sequences > 5 * int(off[-1])            # ~14 lengths per start position
     with pytest.raises(PepQueryError) as e:
-        Search(_abi.default_params(enzyme=0))
+        Search(_abi.default_params(enzyme=18))
     assert e.value.code == _abi.PQ_ERR_UNSUPPORTED
 
 

@@ -222,6 +222,28 @@ def test_enzyme_table(enzyme):
     assert set(o.reference_sequences()) == want and len(want) > 50
 
 
+def test_no_enzyme_is_every_substring():
+    """-e 0 (NoEnzyme, pg/DatabaseInput.java:117-121, CleavageParameter.unSpecific): every stretch of a protein within the length
+    bounds (the mass window opened wide here), I -> L folded, '*' dropped, minus the targets."""
+    from pepquery_b200 import synth
+    poff, pres = synth.proteins(3)
+    prots = [bytes(pres[poff[i]:poff[i + 1]]).decode() for i in range(len(poff) - 1)]
+    o = pq_oracle.Oracle(_abi.default_params(enzyme=0, min_len=7, max_len=12, min_mass=0.0, max_mass=1e9))
+    o.load_spectra(dict(prec_mz=np.array([500.0]), charge=np.array([2], dtype=np.int32), peak_off=np.array([0, 0], dtype=np.uint64),
+                        mz=np.zeros(0), inten=np.zeros(0)))
+    o.set_targets(np.array([0, 8], dtype=np.uint32), np.frombuffer(b"AAAAAAAK", dtype=np.uint8).copy())
+    o.build_reference(poff, pres)
+    want = set()
+    for pr in prots:
+        pr = pr.upper().replace("*", "").replace("I", "L")
+        for a in range(len(pr)):
+            for ln in range(7, 13):
+                if a + ln <= len(pr):
+                    want.add(pr[a:a + ln])
+    want.discard("AAAAAAAK")
+    assert set(o.reference_sequences()) == want and len(want) > 1000
+
+
 def test_oracle_regression_fixture():
     """The oracle must keep reproducing its committed outputs (tests/golden/oracle_vectors.json, tools/make_golden.py)."""
     from pepquery_b200 import synth
