@@ -136,7 +136,7 @@ struct pq_ctx {
     PeptideTable ref_super; uint32_t super_rows = 0; bool super_ready = false;
     bool pending_step[5] = {false, false, false, false, false};   // [2..4]: results of that step are already in the PSM table
     bool pending_ref = false;                                      // pq_build_reference(NULL) only has to cut the table out of the superset
-    cudaStream_t st_part = nullptr;
+    cudaStream_t st_part = nullptr, st_part2 = nullptr;      // search at load: the parts alternate between two streams
     // targeted PSM list (SpectraInput.pep2targeted_spectra)
     DevBuf tg_keys, tg_listed, tg_canon, tg_seen, tg_best, tg_type; uint32_t n_targeted = 0; std::vector<uint32_t> tg_pos;     // tg_pos[i] = position of pair i in the sorted keys
     TargetedView targeted_view() const {
@@ -404,7 +404,8 @@ int32_t pq_create(const pq_params* params, pq_ctx** out) {
     if (cudaSetDevice(params->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->st_aux, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->st_part, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->st_part, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->st_part2, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx; return fail(nullptr, PQ_ERR_CUDA, "cannot initialise device");
     }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->uev0); cudaEventCreate(&ctx->uev1);
@@ -459,6 +460,7 @@ int32_t pq_destroy(pq_ctx* ctx) {
     if (ctx->targets_ev) cudaEventDestroy(ctx->targets_ev);
     cudaStream_t st = ctx->st, st_copy = ctx->st_copy, st_aux = ctx->st_aux;
     if (ctx->st_part) { cudaStreamSynchronize(ctx->st_part); cudaStreamDestroy(ctx->st_part); }
+    if (ctx->st_part2) { cudaStreamSynchronize(ctx->st_part2); cudaStreamDestroy(ctx->st_part2); }
     delete ctx;
     if (st) cudaStreamDestroy(st);
     if (st_copy) cudaStreamDestroy(st_copy);
@@ -601,7 +603,7 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
     // whatever goes wrong from here on, the context ends up without spectra and with nothing in flight
     auto fail_load = [&](int32_t code, const std::string& msg) -> int32_t {
         if (early.th.joinable()) early.th.join();
-        cudaStreamSynchronize(ctx->st_part);
+        cudaStreamSynchronize(ctx->st_part); cudaStreamSynchronize(ctx->st_part2);
         cudaStreamSynchronize(sc); cudaStreamSynchronize(st); cudaStreamSynchronize(ctx->st_aux); cudaGetLastError();
         ctx->nS = 0; ctx->nCaller = 0; ctx->nZero = 0; ctx->max_peaks = 0; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0; ctx->prepared_at_load = false;
         ctx->residency = 0; ctx->n_resident = 0; ctx->cnt.spectra_loaded = 0; ctx->cnt.spectra_usable = 0; ctx->host_spectra_valid = false;
@@ -1553,7 +1555,8 @@ int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan) {
     mk.mark("shuffles for all forms");
     // ---- the Step-2 jobs by part ----
     const uint32_t n_jobs = plan.n_jobs;
-    const uint32_t chunks_per_part = 4;
+    uint32_t chunks_per_part = 6;      // measured at C2 size: 2 -> 48.4 ms end to end, 4 -> 44.4, 6 -> 43.7, 8 -> 43.6 (every part costs ~40 small launches and five host round trips)
+    if (const char* e = getenv("PQ_CHUNKS_PER_PART")) { int v = atoi(e); if (v > 0) chunks_per_part = (uint32_t)v; }
     const uint32_t part_spectra = plan.chunk_spectra * chunks_per_part;
     const uint32_t n_parts = (plan.n_res + part_spectra - 1) / part_spectra;
     if (ctx->parts.size() < n_parts) ctx->parts.resize(n_parts);
@@ -1586,75 +1589,79 @@ int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan) {
     for (uint32_t p = 0; p < n_parts; ++p) {
         pq_ctx::PartBufs& B = ctx->parts[p];
         B.n_psm = 0; B.n_seg = 0; B.nh3 = 0;
+        // the parts alternate between two streams: while this thread waits for the small results of part p (hit count, segment count,
+        // candidate totals), the Step-4 launch of part p - 1 is still running on the other stream
+        cudaStream_t sq = (p & 1u) && !getenv("PQ_ONE_PART_STREAM") ? ctx->st_part2 : sp_;
         const uint32_t j0 = first[p], nj = first[p + 1] - first[p];
         // the part is complete when K0 has finished its last chunk
         const size_t last_chunk = std::min<size_t>((size_t)(p + 1) * chunks_per_part, plan.n_chunks) - 1;
-        CU(cudaStreamWaitEvent(sp_, (*plan.k0_done)[last_chunk], 0));
+        CU(cudaStreamWaitEvent(sq, (*plan.k0_done)[last_chunk], 0));
         if (!nj) continue;
         if (pcand[p] > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-2 candidates for one launch");
         CU(B.scal.reserve(256));
-        CU(cudaMemsetAsync(B.scal.p, 0, 256, sp_));
+        CU(cudaMemsetAsync(B.scal.p, 0, 256, sq));
         uint32_t* scal = B.scal.as<uint32_t>();
         // ---- Step 2 ----
-        ScoreIO io2{sp_, ctx->jobs.as<Job>() + j0, &B.results, &B.hits, &B.hit_count, scal + 12, false};
+        ScoreIO io2{sq, ctx->jobs.as<Job>() + j0, &B.results, &B.hits, &B.hit_count, scal + 12, false};
         int32_t rc = run_score_io(ctx, io2, kJobTargets, nj, T.pred.as<int32_t>(), T.rows.as<uint8_t>(), T.mass.as<double>(), (uint32_t)std::max<unsigned long long>(pcand[p], 1), 1);
         if (rc) return rc;
         uint32_t nh = 0;
-        CU(cudaMemcpyAsync(&nh, B.hit_count.p, 4, cudaMemcpyDeviceToHost, sp_));
-        CU(cudaStreamSynchronize(sp_));
-        ctx->cnt.other_kernel_launches += (uint64_t)launch_job_counters(ctx->jobs.as<Job>() + j0, B.results.as<JobResult>(), nj, sp.npeaks, 0, ctx->d_counters.as<DevCounters>(), sp_);
+        CU(cudaMemcpyAsync(&nh, B.hit_count.p, 4, cudaMemcpyDeviceToHost, sq));
+        CU(cudaStreamSynchronize(sq));
+        ctx->cnt.other_kernel_launches += (uint64_t)launch_job_counters(ctx->jobs.as<Job>() + j0, B.results.as<JobResult>(), nj, sp.npeaks, 0, ctx->d_counters.as<DevCounters>(), sq);
         if (!nh) continue;
         CU(B.psm.reserve((size_t)nh * sizeof(DevPsm))); CU(B.seg_start.reserve(((size_t)nh + 2) * 4));
         {
             std::string err; int launches = 0;
             if (!psm_table_from_hits(B.hits.as<Hit>(), nh, sp, T.mass.as<double>(), T.rows.as<uint8_t>(), A, B.key_a, B.key_b, B.idx_a, B.idx_b, B.head, B.tmp,
-                                     B.psm.as<DevPsm>(), B.seg_start.as<uint32_t>(), scal, nullptr, sp_, &launches, err))
+                                     B.psm.as<DevPsm>(), B.seg_start.as<uint32_t>(), scal, nullptr, sq, &launches, err))
                 return fail(ctx, PQ_ERR_CUDA, "psm table: " + err);
             ctx->cnt.other_kernel_launches += (uint64_t)launches;
         }
         uint32_t nseg = 0;
-        CU(cudaMemcpyAsync(&nseg, scal, 4, cudaMemcpyDeviceToHost, sp_));
-        CU(cudaMemcpyAsync(&B.s_first, &B.psm.as<DevPsm>()[0].spectrum_sorted, 4, cudaMemcpyDeviceToHost, sp_));
-        CU(cudaMemcpyAsync(&B.s_last, &B.psm.as<DevPsm>()[nh - 1].spectrum_sorted, 4, cudaMemcpyDeviceToHost, sp_));
-        CU(cudaStreamSynchronize(sp_));
+        CU(cudaMemcpyAsync(&nseg, scal, 4, cudaMemcpyDeviceToHost, sq));
+        CU(cudaMemcpyAsync(&B.s_first, &B.psm.as<DevPsm>()[0].spectrum_sorted, 4, cudaMemcpyDeviceToHost, sq));
+        CU(cudaMemcpyAsync(&B.s_last, &B.psm.as<DevPsm>()[nh - 1].spectrum_sorted, 4, cudaMemcpyDeviceToHost, sq));
+        CU(cudaStreamSynchronize(sq));
         B.n_psm = nh; B.n_seg = nseg;
         // ---- Step 3 (superset table) ----
         CU(B.agg.reserve((size_t)nseg * sizeof(SegAgg)));
         if (ctx->super_rows == 0) {
-            CU(cudaMemsetAsync(B.agg.p, 0, (size_t)nseg * sizeof(SegAgg), sp_));
+            CU(cudaMemsetAsync(B.agg.p, 0, (size_t)nseg * sizeof(SegAgg), sq));
         } else {
             const uint32_t nj3 = nseg * (uint32_t)ctx->P.n_isotope;
             CU(B.jobs.reserve((size_t)nj3 * sizeof(Job)));
             unsigned long long* d_total = reinterpret_cast<unsigned long long*>(scal + 16);
             ctx->cnt.other_kernel_launches += (uint64_t)launch_step3_jobs(B.psm.as<DevPsm>(), B.seg_start.as<uint32_t>(), nseg, S.mass.as<double>(), ctx->super_rows, W,
-                                                                          ctx->s_mass.as<double>(), B.jobs.as<Job>(), B.agg.as<SegAgg>(), d_total, sp_);
+                                                                          ctx->s_mass.as<double>(), B.jobs.as<Job>(), B.agg.as<SegAgg>(), d_total, sq);
             unsigned long long cand3 = 0;
-            CU(cudaMemcpyAsync(&cand3, d_total, 8, cudaMemcpyDeviceToHost, sp_));
-            CU(cudaStreamSynchronize(sp_));
+            CU(cudaMemcpyAsync(&cand3, d_total, 8, cudaMemcpyDeviceToHost, sq));
+            CU(cudaStreamSynchronize(sq));
             if (cand3 > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-3 candidates for one launch");
-            ScoreIO io3{sp_, B.jobs.as<Job>(), &B.results, &B.hits, &B.hit_count, scal + 12, false};
+            ScoreIO io3{sq, B.jobs.as<Job>(), &B.results, &B.hits, &B.hit_count, scal + 12, false};
             rc = run_score_io(ctx, io3, kJobCompetitors, nj3, S.pred.as<int32_t>(), S.rows.as<uint8_t>(), S.mass.as<double>(), (uint32_t)std::max<unsigned long long>(cand3, 1), 1, &S);
             if (rc) return rc;
-            int k = launch_job_counters(B.jobs.as<Job>(), B.results.as<JobResult>(), nj3, sp.npeaks, 1, ctx->d_counters.as<DevCounters>(), sp_);
-            k += launch_step3_aggregate(B.results.as<JobResult>(), nseg, ctx->P.n_isotope, B.seg_start.as<uint32_t>(), B.psm.as<DevPsm>(), B.agg.as<SegAgg>(), sp_);
+            int k = launch_job_counters(B.jobs.as<Job>(), B.results.as<JobResult>(), nj3, sp.npeaks, 1, ctx->d_counters.as<DevCounters>(), sq);
+            k += launch_step3_aggregate(B.results.as<JobResult>(), nseg, ctx->P.n_isotope, B.seg_start.as<uint32_t>(), B.psm.as<DevPsm>(), B.agg.as<SegAgg>(), sq);
             ctx->cnt.other_kernel_launches += (uint64_t)k;
             uint32_t nh3 = 0;
-            CU(cudaMemcpyAsync(&nh3, B.hit_count.p, 4, cudaMemcpyDeviceToHost, sp_));
-            CU(cudaStreamSynchronize(sp_));
-            if (nh3) { CU(B.hits3.reserve((size_t)nh3 * sizeof(Hit))); CU(cudaMemcpyAsync(B.hits3.p, B.hits.p, (size_t)nh3 * sizeof(Hit), cudaMemcpyDeviceToDevice, sp_)); }
+            CU(cudaMemcpyAsync(&nh3, B.hit_count.p, 4, cudaMemcpyDeviceToHost, sq));
+            CU(cudaStreamSynchronize(sq));
+            if (nh3) { CU(B.hits3.reserve((size_t)nh3 * sizeof(Hit))); CU(cudaMemcpyAsync(B.hits3.p, B.hits.p, (size_t)nh3 * sizeof(Hit), cudaMemcpyDeviceToDevice, sq)); }
             B.nh3 = nh3;
         }
         // ---- Step 4 ----
         CU(B.valid_flag.reserve((size_t)nh + 64));
-        ctx->cnt.other_kernel_launches += (uint64_t)launch_valid_flags(B.psm.as<DevPsm>(), nh, B.valid_flag.as<uint8_t>(), scal + 5, sp_);
+        ctx->cnt.other_kernel_launches += (uint64_t)launch_valid_flags(B.psm.as<DevPsm>(), nh, B.valid_flag.as<uint8_t>(), scal + 5, sq);
         uint32_t n_valid = 0;
-        CU(cudaMemcpyAsync(&n_valid, scal + 5, 4, cudaMemcpyDeviceToHost, sp_));
-        CU(cudaStreamSynchronize(sp_));
+        CU(cudaMemcpyAsync(&n_valid, scal + 5, 4, cudaMemcpyDeviceToHost, sq));
+        CU(cudaStreamSynchronize(sq));
         Step4Work W4{&B.valid_flag, &B.list, &B.order, &B.keys, &B.keys2, &B.jobs, &B.results, &B.hits, &B.hit_count, &B.tmp, scal + 4, scal + 12};
-        rc = step4_score(ctx, sp_, B.psm.as<DevPsm>(), nh, n_valid, W4, false);
+        rc = step4_score(ctx, sq, B.psm.as<DevPsm>(), nh, n_valid, W4, false);
         if (rc) return rc;
         N += nh; NS += nseg; NH3 += B.nh3;
     }
+    CU(cudaStreamSynchronize(ctx->st_part2));
     mk.mark("parts queued");
     // ---- merge ----
     ctx->n_psm = 0; ctx->n_seg = 0; ctx->nh3 = 0; ctx->comp3_ready = false; ctx->comp3_n = 0;
