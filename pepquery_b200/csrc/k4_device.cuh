@@ -54,6 +54,9 @@ __device__ inline int32_t predict_peaks(const uint8_t* __restrict__ row, const M
         int c = s % maxc + 1; int q = s / maxc; int l = q % (nloss + 1); int t = q / (nloss + 1);
         double m = t ? y[k] : b[k];
         if (l > 0) m = __dsub_rn(m, loss[l - 1]);
+        // (m + c p) / c: for c = 1 and 2 — all MVH ever asks for — c p and the division are exact, so no divide sequence is needed
+        if (c == 1) return __dadd_rn(m, kProton);
+        if (c == 2) return __dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5);
         return __ddiv_rn(__dadd_rn(m, __dmul_rn((double)c, kProton)), (double)c);
     };
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
