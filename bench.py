@@ -340,7 +340,7 @@ def main():
         cap = torch.tensor([n], device="cuda", dtype=torch.int64)
         if world > 1:
             dist.all_reduce(cap, op=dist.ReduceOp.MAX)
-        cap = int(cap.item()); cap = cap + cap // 4 + 1024
+        cap = int(cap.item()); cap = cap + cap // 16 + 1024
         gbuf["cap"] = cap
         gbuf["pin_psm"] = torch.empty(HDR + cap * REC, dtype=torch.uint8, pin_memory=True).numpy()
         gbuf["pin_comp"] = torch.empty(max(1, cap) * 32 + 4096, dtype=torch.uint8, pin_memory=True).numpy()
@@ -371,11 +371,16 @@ def main():
         work.wait()
         if rank == 0:
             stride = HDR + gbuf["cap"] * REC
-            for r in range(world):
-                gbuf["host"][r * stride:(r + 1) * stride].copy_(gbuf["recv"][r], non_blocking=True)
-            torch.cuda.synchronize()
+            for r in range(world):                 # the headers first (one short wait), then exactly the records each rank sent
+                gbuf["host"][r * stride:r * stride + HDR].copy_(gbuf["recv"][r][:HDR], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
             hv = gbuf["host"].numpy()
-            return int(sum(int(hv[r * stride:r * stride + 8].view(np.int64)[0]) for r in range(world)))
+            counts = [int(hv[r * stride:r * stride + 8].view(np.int64)[0]) for r in range(world)]
+            for r in range(world):
+                used = HDR + counts[r] * REC
+                gbuf["host"][r * stride + HDR:r * stride + used].copy_(gbuf["recv"][r][HDR:used], non_blocking=True)
+            torch.cuda.synchronize()
+            return int(sum(counts))
         torch.cuda.synchronize()
         return 0
 

@@ -20,8 +20,10 @@ __global__ void k4_predict_kernel(const uint8_t* __restrict__ rows, uint32_t n_r
     if (r >= n_rows) return;
     const uint8_t* row = rows + (size_t)r * kRowBytes;
     dev::Extra ex; ex.site = -1; ex.delta = 0.0;
-    out[2 * (size_t)r] = dev::predict_peaks(row, M, itol, 1, ex);          // precursor charge 2: fragment charge 1 only
-    out[2 * (size_t)r + 1] = dev::predict_peaks(row, M, itol, 2, ex);
+    double b[kMaxLen], y[kMaxLen], loss[dev::kMaxLoss]; int nloss;
+    dev::predict_ladders(row, M, ex, b, y, loss, nloss);                    // one ladder walk for both charge sets
+    out[2 * (size_t)r] = dev::predict_count(b, y, (int)row[0], loss, nloss, itol, 1);          // precursor charge 2: fragment charge 1 only
+    out[2 * (size_t)r + 1] = dev::predict_count(b, y, (int)row[0], loss, nloss, itol, 2);
 }
 
 }  // namespace
