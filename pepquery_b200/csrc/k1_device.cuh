@@ -491,13 +491,14 @@ __device__ __forceinline__ bool below_score_bound(const uint32_t* codes, const B
 
 // The same decision from the row's cell lists (k_cells.cuh): K2 walked the ladder once when it wrote the row; here every
 // (ion, fragment charge) is one 2-byte entry — the byte offset of its cell in the staged spectrum's table, whose top bit says
-// "nothing can be claimed in this cell".  Whole 16-byte units of eight entries; slots that are no ion point at the always-clean
-// sentinel entry and are subtracted by count.
+// "nothing can be claimed in this cell" — K1 spreads those bits into a byte per cell once per job, so the test is one byte
+// load.  Whole 16-byte units of eight entries; slots that are no ion point at the always-clean sentinel cell behind that table.
 // Both sides at once: the b and the y unit of the same index are loaded together (and two indices per trip), so four 16-byte
 // loads are in flight per thread instead of one — the lists come from L2, the pass is latency-bound otherwise.
-__device__ __forceinline__ uint2 count_clean_lists(const uint4* __restrict__ pb, const uint4* __restrict__ py, size_t stride, uint32_t n_units, uint32_t cells_s) {
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }   // zero-extended
+__device__ __forceinline__ uint2 count_clean_lists(const uint4* __restrict__ pb, const uint4* __restrict__ py, size_t stride, uint32_t n_units, uint32_t cflag_s) {
     uint32_t cb = 0, cy = 0;
-    auto flag = [&](uint32_t e) -> uint32_t { return lds_u16(cells_s + e) >> 15; };
+    auto flag = [&](uint32_t e) -> uint32_t { return lds_u8(cflag_s + e); };      // the CTA's byte table: 1 = nothing can be claimed in that cell
     auto unit = [&](const uint4& q) -> uint32_t {
         return flag(q.x & 0xFFFFu) + flag(q.x >> 16) + flag(q.y & 0xFFFFu) + flag(q.y >> 16) + flag(q.z & 0xFFFFu) + flag(q.z >> 16) + flag(q.w & 0xFFFFu) + flag(q.w >> 16);
     };
@@ -511,12 +512,11 @@ __device__ __forceinline__ uint2 count_clean_lists(const uint4* __restrict__ pb,
 // n_units = streams read x units per stream; n_side = ions x charges of one side; the rest of the 8 * n_units slots are sentinel slots
 template <int METHOD>
 __device__ __forceinline__ bool below_score_bound_lists(const uint4* __restrict__ row_lists, size_t stride, uint32_t chunks_side, uint32_t n_units, uint32_t n_side,
-                                                        const BlobView& B, const double* log10_fact, double cutoff, const double* ln_fact, int32_t predicted) {
+                                                        const BlobView& B, uint32_t cflag_s, const double* log10_fact, double cutoff, const double* ln_fact, int32_t predicted) {
     if (!(cutoff > 0.0)) return false;
     const int pre = bound_precheck<METHOD>(B, predicted);
     if (pre >= 0) return pre != 0;
-    const uint32_t cells_s = smem_addr(B.cells);
-    const uint2 clean = count_clean_lists(row_lists, row_lists + (size_t)chunks_side * stride, stride, n_units, cells_s);
+    const uint2 clean = count_clean_lists(row_lists, row_lists + (size_t)chunks_side * stride, stride, n_units, cflag_s);
     const uint32_t slots = 8u * n_units;                          // the sentinel slots count as clean, so whatever is not clean is an ion that may match
     const uint32_t nb = slots - clean.x, ny = slots - clean.y;
     (void)n_side;

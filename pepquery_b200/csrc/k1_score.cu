@@ -73,6 +73,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     __shared__ uint32_t s_job[2];
     constexpr uint32_t kSurvCap = BLOCK == 256 ? 1024 : 2 * BLOCK;      // only the Step-4 configuration (BLOCK 256) pays for a long list
     __shared__ uint16_t s_surv[kSurvCap];         // bounded Step 4: candidates the score bound could not decide (index within the job)
+    __shared__ __align__(16) uint8_t s_cflag[BLOCK == 256 ? kCells + 16 : 16];      // Step-4 count pass: one byte per cell of the job's spectrum, 1 = nothing can be claimed (+ the list sentinel)
     __shared__ uint32_t s_nsurv;
     const bool bounded = L.kind == kJobShuffles && !cfg.score_all && !cfg.check_window;
     auto fetch = [&](uint32_t slot) {           // thread 0: take the next job and start its TMA into `slot`
@@ -134,6 +135,17 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
                 }
             }
             if (tid == 0) s_nsurv = 0;
+            if (BLOCK == 256 && job_lists) {
+                // the clean flags of the staged cell table, one byte per cell: a list entry then costs a byte load and an add
+                const uint4* src = reinterpret_cast<const uint4*>(B.cells);
+                for (uint32_t q = tid; q < (uint32_t)kCells / 8; q += BLOCK) {
+                    const uint4 v = src[q];
+                    const uint32_t lo = ((v.x >> 15) & 1u) | ((v.x >> 23) & 0x100u) | (((v.y >> 15) & 1u) << 16) | (((v.y >> 31) & 1u) << 24);
+                    const uint32_t hi = ((v.z >> 15) & 1u) | ((v.z >> 23) & 0x100u) | (((v.w >> 15) & 1u) << 16) | (((v.w >> 31) & 1u) << 24);
+                    reinterpret_cast<uint2*>(s_cflag)[q] = make_uint2(lo, hi);
+                }
+                if (tid < 4) reinterpret_cast<uint32_t*>(s_cflag + kCells)[tid] = 0x01010101u;
+            }
             __syncthreads();
             // jobs whose whole candidate list fits the survivor list (the usual case: -n 1000) run the count pass without a
             // barrier; longer jobs drain the list in rounds of BLOCK, 2048 candidates at a time
@@ -144,7 +156,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
                     int32_t pred = 0;
                     if (METHOD == 2) pred = L.row_pred[2 * ((size_t)J.cand_begin + c) + (J.charge == 2 ? 0 : 1)];
                     bool below;
-                    if (job_lists) below = below_score_bound_lists<METHOD>(job_lists + c, list_stride, list_chunks, list_units, list_n, B, s_l10, J.ref_score, L.ln_fact, pred);
+                    if (job_lists) below = below_score_bound_lists<METHOD>(job_lists + c, list_stride, list_chunks, list_units, list_n, B, smem_addr(s_cflag), s_l10, J.ref_score, L.ln_fact, pred);
                     else { load_row(J.cand_begin + c); below = below_score_bound<BLOCK, TS, METHOD>(codes, B, s_tab, s_nt, s_ct, J.charge, s_l10, J.ref_score, L.ln_fact, pred); }
                     if (below) ++n_bound;
                     else s_surv[atomicAdd(&s_nsurv, 1u)] = (uint16_t)(c - s0);

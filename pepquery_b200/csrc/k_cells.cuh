@@ -9,9 +9,10 @@
 //
 // One row's lists = 2 sides x nch_max charge streams x U 16-byte units of eight u16 entries, U = ceil((L - 1) / 8):
 //   side 0 (b ions) | side 1 (y ions); inside a side: stream of charge 1, of charge 2, of charge 3; slot k - 1 of a stream = ion k,
-//   entry = byte offset of its cell in BlobLayout::cells = 2 * cell_filter(m/z).  Slots that are no ion (k < charge: A6, fragment
-//   charge c needs c <= ion number; the padding of the last unit) hold kCellSentinel, the always-clean entry behind the table, so a
-//   reader counts whole units and subtracts the known number of such slots.
+//   entry = the ion's cell, cell_filter(m/z).  K1 turns the staged spectrum's clean flags into a byte per cell (1 = nothing can be
+//   claimed) once per job, so an entry costs one byte load and an add.  Slots that are no ion (k < charge: A6, fragment charge c
+//   needs c <= ion number; the padding of the last unit) hold kListSentinel, an always-clean extra cell behind that byte table, so a
+//   reader counts whole units and needs no length.
 // A job with nch = precursor charge - 1 fragment charges reads the first nch streams of each side.
 // The rows of one peptide form are stored unit-major: unit u of row k at base + u * stride + k (stride = rows reserved for the
 // form), so the 32 rows a warp of K1 (one thread per row) reads, and a warp of K2 writes, are 512 contiguous bytes per unit.
@@ -21,6 +22,7 @@
 namespace pq {
 
 constexpr int kListMaxCharge = 3;       // fragment charges held in the lists (precursor charge <= 4); above: K1 walks the ladder
+constexpr uint32_t kListSentinel = kCells;      // entry of a slot that is no ion: the always-clean cell behind K1's byte table
 
 PQ_HD uint32_t list_entries(int L, int nch) {      // ions x charges of one side for nch fragment charges
     uint32_t t = 0;
@@ -37,7 +39,7 @@ __device__ __forceinline__ void write_cell_lists(const uint8_t* row, const ModTa
                                                  uint32_t chunks_side, size_t stride) {
     const int L = (int)row[0], Lm1 = L - 1;
     const uint32_t U = list_stream_units(L);
-    constexpr unsigned long long kSent4 = 0x0001000100010001ull * (unsigned long long)kCellSentinel;
+    constexpr unsigned long long kSent4 = 0x0001000100010001ull * (unsigned long long)kListSentinel;
     for (int side = 0; side < 2; ++side) {
         uint4* out = dst + (size_t)side * chunks_side * stride;
         unsigned long long lo[kListMaxCharge], hi[kListMaxCharge];
@@ -49,9 +51,9 @@ __device__ __forceinline__ void write_cell_lists(const uint8_t* row, const ModTa
             acc = __dadd_rn(__dadd_rn(acc, M->aa[code]), M->delta[code]);
             const double m = side == 0 ? acc : __dadd_rn(acc, kWater);
             uint32_t e[kListMaxCharge];
-            e[0] = 2u * cell_filter(__dadd_rn(m, kProton));
-            e[1] = k >= 2 ? 2u * cell_filter(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5)) : kCellSentinel;
-            e[2] = k >= 3 ? 2u * cell_filter(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0)) : kCellSentinel;
+            e[0] = cell_filter(__dadd_rn(m, kProton));
+            e[1] = k >= 2 ? cell_filter(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5)) : kListSentinel;
+            e[2] = k >= 3 ? cell_filter(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0)) : kListSentinel;
             const int j = (k - 1) & 7, s = 16 * (j & 3);
 #pragma unroll
             for (int c = 0; c < kListMaxCharge; ++c) {
