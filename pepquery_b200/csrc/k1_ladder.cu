@@ -153,29 +153,37 @@ __device__ __forceinline__ PairScore score_ladder(const uint4* __restrict__ lad,
         }
     };
     const uint64_t high = nch > kLadderCharges && Lm1 > 3 ? ((~0ull >> (64 - Lm1)) & ~7ull) : 0ull;      // charges >= 4 are not in the lists: every ion k >= 4 is looked at
+    // ONE loop over both sides (all b ions, then all y ions): a warp runs as long as its busiest lane, and the busiest lane of the
+    // combined work is less busy than the busiest b lane plus the busiest y lane
+    const double* pmb = reinterpret_cast<const double*>(lad);
+    const double* pmy = reinterpret_cast<const double*>(lad + (size_t)PM);
+    uint64_t tb = M.b[0] | M.b[1] | M.b[2] | high, ty = M.y[0] | M.y[1] | M.y[2] | high;
+    auto next = [&](int& side, int& b, double& m) {           // the next ion to look at and its mass (the load is issued here)
+        side = tb ? 0 : 1;
+        const uint64_t t = tb ? tb : ty;
+        b = __ffsll((long long)t) - 1;
+        m = __ldg((side ? pmy : pmb) + b);
+        if (tb) tb &= tb - 1; else ty &= ty - 1;
+    };
+    int side_n = 0, b_n = 0; double m_n = 0.0;
+    bool more = (tb | ty) != 0ull;
+    if (more) next(side_n, b_n, m_n);
 #pragma unroll 1
-    for (int side = 0; side < 2; ++side) {
-        const double* pm = reinterpret_cast<const double*>(lad + (size_t)side * PM);
+    while (more) {
+        const int side = side_n, b = b_n; const double m = m_n;
+        more = (tb | ty) != 0ull;
+        if (more) next(side_n, b_n, m_n);
+        const int k = b + 1;
         const uint64_t d1 = side ? M.y[0] : M.b[0], d2 = side ? M.y[1] : M.b[1], d3 = side ? M.y[2] : M.b[2];
-        uint64_t todo = d1 | d2 | d3 | high;
-        int b_next = todo ? __ffsll((long long)todo) - 1 : 0;
-        double m_next = todo ? __ldg(pm + b_next) : 0.0;
-#pragma unroll 1
-        while (todo) {
-            const int b = b_next; const double m = m_next;
-            todo &= todo - 1;
-            if (todo) { b_next = __ffsll((long long)todo) - 1; m_next = __ldg(pm + b_next); }
-            const int k = b + 1;
-            if ((d1 >> b) & 1ull) claim(match_ion<METHOD>(B, __dadd_rn(m, kProton), itol), side == 0);
-            if ((d2 >> b) & 1ull) claim(match_ion<METHOD>(B, __dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5), itol), side == 0);
-            if ((d3 >> b) & 1ull) claim(match_ion<METHOD>(B, __ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0), itol), side == 0);
-            if (nch > kLadderCharges && k >= 4) {
-                double t = __dmul_rn(__dadd_rn(m, 4.0 * kProton), 0.25);
+        if ((d1 >> b) & 1ull) claim(match_ion<METHOD>(B, __dadd_rn(m, kProton), itol), side == 0);
+        if ((d2 >> b) & 1ull) claim(match_ion<METHOD>(B, __dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5), itol), side == 0);
+        if ((d3 >> b) & 1ull) claim(match_ion<METHOD>(B, __ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0), itol), side == 0);
+        if (nch > kLadderCharges && k >= 4) {
+            double t = __dmul_rn(__dadd_rn(m, 4.0 * kProton), 0.25);
+            if (ion_may_match(B, t)) claim(match_ion<METHOD>(B, t, itol), side == 0);
+            for (int c = 5; c <= nch && c <= k; ++c) {
+                t = __ddiv_rn(__dadd_rn(m, __dmul_rn((double)c, kProton)), (double)c);
                 if (ion_may_match(B, t)) claim(match_ion<METHOD>(B, t, itol), side == 0);
-                for (int c = 5; c <= nch && c <= k; ++c) {
-                    t = __ddiv_rn(__dadd_rn(m, __dmul_rn((double)c, kProton)), (double)c);
-                    if (ion_may_match(B, t)) claim(match_ion<METHOD>(B, t, itol), side == 0);
-                }
             }
         }
     }

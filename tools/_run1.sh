@@ -1,1 +1,3 @@
-ncu --set full --clock-control none --import-source on -k regex:'k1_score_kernel|k1_ladder_kernel' -s 2 -c 2 -f -o gpurun_out/prof_r2m python bench.py --steps 1 --warmup 1 --no-cpu --e2e-steps 0 --no-configs > gpurun_out/ncu_f_r2m.log 2>&1; echo "ncu full rc=$?"
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "ladder or default_search or golden or random_config or mvh or parameter_variations" 2>&1 | tail -3
+run() { python bench.py --no-cpu --e2e-steps 0 --steps 3 --no-configs 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1 value %.4g  ms/step %.2f'%(d['value'], d['ms_per_step'])); print({k: round(v,2) for k,v in d['kernel_ms_per_step'].items()})"; }
+run merged
