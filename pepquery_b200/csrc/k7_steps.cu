@@ -10,7 +10,7 @@
 //           StatisticScoreWorker per still-valid PSM, p = (nRand+1)/(N+1) (pg/StatisticScoreWorker.java:56-58);
 //           group order and round count of generateRandomPeptidesFast (pg/PeptideInput.java:387-424)
 //                                                                                        -> k7_flag_valid / k7_shuffle_plans /
-//                                                                                           k7_shuffle_layout / k7_step4_*
+//                                                                                           k7_layout_seqs / k7_layout_forms / k7_step4_*
 //   rank    RankPSM.RankPSMCompare (pg/RankPSM.java:107-149), CParameter.passed_psm_validation (pg/CParameter.java:913-940)
 //                                                                                        -> k7_rank
 #include <cub/cub.cuh>
@@ -229,64 +229,73 @@ __global__ void k7_shuffle_plans(const uint8_t* __restrict__ seq_flag, TargetAux
     plans[s] = S;
 }
 
-// Single CTA: compacts the flagged sequences / forms and lays out their shuffle rows (exclusive scans).
+// Compacts the flagged sequences / forms and lays out their shuffle rows (exclusive scans).  Every CTA owns kLayoutThreads entries:
+// it first sums what the entries before its own contribute (a strided read of flags and counts: a few thousand words), then scans
+// its own — no CTA waits for another (as ONE CTA walking all chunks this took 0.7 ms at 10 k sequences / 15 k forms).
 constexpr int kLayoutThreads = 1024;
 struct Tri { uint32_t n, rows; unsigned long long units; };
 struct AddTri { __device__ Tri operator()(const Tri& a, const Tri& b) const { return Tri{a.n + b.n, a.rows + b.rows, a.units + b.units}; } };
 __global__ void __launch_bounds__(kLayoutThreads)
-k7_shuffle_layout(const uint8_t* __restrict__ seq_flag, const uint32_t* __restrict__ form_flag, const uint8_t* __restrict__ valid_flag, uint32_t n_psm,
-                  const ShuffleSeq* __restrict__ plans, TargetAux A, uint32_t* __restrict__ seq_slot, uint32_t* __restrict__ form_slot,
-                  uint32_t* __restrict__ row_base, ShuffleSeq* __restrict__ seqs, ShuffleForm* __restrict__ forms, ShuffleTotals* __restrict__ totals) {
+k7_layout_seqs(const uint8_t* __restrict__ seq_flag, const ShuffleSeq* __restrict__ plans, uint32_t n_seq, uint32_t* __restrict__ seq_slot,
+               ShuffleSeq* __restrict__ seqs, ShuffleTotals* __restrict__ totals) {
     typedef cub::BlockScan<uint2, kLayoutThreads> Scan;
-    __shared__ typename Scan::TempStorage tmp;
+    typedef cub::BlockReduce<uint2, kLayoutThreads> Reduce;
+    __shared__ union { typename Scan::TempStorage scan; typename Reduce::TempStorage red; } tmp;
     __shared__ uint2 carry;
     struct Add { __device__ uint2 operator()(const uint2& a, const uint2& b) const { return make_uint2(a.x + b.x, a.y + b.y); } };
-    if (threadIdx.x == 0) carry = make_uint2(0u, 0u);
+    const uint32_t base = blockIdx.x * kLayoutThreads;
+    uint2 before = make_uint2(0u, 0u);
+    for (uint32_t s = threadIdx.x; s < base; s += kLayoutThreads) if (seq_flag[s]) { before.x += 1u; before.y += plans[s].num; }
+    before = Reduce(tmp.red).Reduce(before, Add());
+    if (threadIdx.x == 0) carry = before;
     __syncthreads();
-    for (uint32_t base = 0; base < A.n_seq; base += kLayoutThreads) {
-        uint32_t s = base + threadIdx.x;
-        bool f = s < A.n_seq && seq_flag[s];
-        uint2 v = make_uint2(f ? 1u : 0u, f ? plans[s].num : 0u), ex, tot;
-        Scan(tmp).ExclusiveScan(v, ex, make_uint2(0u, 0u), Add(), tot);
-        uint2 c = carry;
-        if (s < A.n_seq) seq_slot[s] = c.x + ex.x;
-        if (f) { ShuffleSeq S = plans[s]; S.out_base = c.y + ex.y; seqs[c.x + ex.x] = S; }
-        __syncthreads();
-        if (threadIdx.x == 0) carry = make_uint2(c.x + tot.x, c.y + tot.y);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { totals->n_seqs = carry.x; totals->raw_rows = carry.y; }
-    __syncthreads();
-    // forms: slot, first shuffle row, first cell-list unit (k_cells.cuh)
+    const uint2 c = carry;
+    const uint32_t s = base + threadIdx.x;
+    const bool f = s < n_seq && seq_flag[s];
+    uint2 v = make_uint2(f ? 1u : 0u, f ? plans[s].num : 0u), ex, tot;
+    Scan(tmp.scan).ExclusiveScan(v, ex, make_uint2(0u, 0u), Add(), tot);
+    if (s < n_seq) seq_slot[s] = c.x + ex.x;
+    if (f) { ShuffleSeq S = plans[s]; S.out_base = c.y + ex.y; seqs[c.x + ex.x] = S; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { totals->n_seqs = c.x + tot.x; totals->raw_rows = c.y + tot.y; }
+}
+// forms: slot, first shuffle row, first cell-list unit (k_cells.cuh)
+__global__ void __launch_bounds__(kLayoutThreads)
+k7_layout_forms(const uint32_t* __restrict__ form_flag, const ShuffleSeq* __restrict__ plans, TargetAux A, const uint32_t* __restrict__ seq_slot,
+                uint32_t* __restrict__ form_slot, uint32_t* __restrict__ row_base, ShuffleForm* __restrict__ forms, ShuffleTotals* __restrict__ totals) {
     typedef cub::BlockScan<Tri, kLayoutThreads> ScanTri;
-    __shared__ typename ScanTri::TempStorage tmp3;
-    __shared__ Tri carry3;
-    if (threadIdx.x == 0) carry3 = Tri{0u, 0u, 0ull};
-    __syncthreads();
-    for (uint32_t base = 0; base < A.n_forms; base += kLayoutThreads) {
-        uint32_t fi = base + threadIdx.x;
+    typedef cub::BlockReduce<Tri, kLayoutThreads> ReduceTri;
+    __shared__ union { typename ScanTri::TempStorage scan; typename ReduceTri::TempStorage red; } tmp;
+    __shared__ Tri carry;
+    auto entry = [&](uint32_t fi, uint32_t& nch_out, int32_t& sq_out, uint32_t& len_out, uint32_t& chunks_out) -> Tri {
         const uint32_t nch = fi < A.n_forms ? form_flag[fi] : 0u;
         const bool f = nch != 0u;
-        int32_t sq = f ? A.seq_of_form[fi] : 0;
+        const int32_t sq = f ? A.seq_of_form[fi] : 0;
         const uint32_t num = f ? plans[sq].num : 0u, len = f ? plans[sq].len : 0u;
         const uint32_t lch = min(nch, (uint32_t)kListMaxCharge), chunks = f ? list_chunks_side((int)len, (int)lch) : 0u;
-        Tri v{f ? 1u : 0u, num, (unsigned long long)num * (2ull * chunks)}, ex, tot;
-        ScanTri(tmp3).ExclusiveScan(v, ex, Tri{0u, 0u, 0ull}, AddTri(), tot);
-        Tri c = carry3;
-        if (fi < A.n_forms) { form_slot[fi] = c.n + ex.n; row_base[fi] = c.rows + ex.rows; }
-        if (f) {
-            ShuffleForm F;
-            F.seq_slot = seq_slot[sq]; F.row_base = c.rows + ex.rows; F.n_mods = A.form_mods[fi].n_mods;
-            for (int i = 0; i < PQ_MAX_FORM_MODS; ++i) F.mod[i] = A.form_mods[fi].mod[i];
-            F.len = len; F.list_nch = lch; F.list_chunks = chunks; F.list_rows = num; F.list_base = c.units + ex.units;
-            forms[c.n + ex.n] = F;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry3 = Tri{c.n + tot.n, c.rows + tot.rows, c.units + tot.units};
-        __syncthreads();
+        nch_out = lch; sq_out = sq; len_out = len; chunks_out = chunks;
+        return Tri{f ? 1u : 0u, num, (unsigned long long)num * (2ull * chunks)};
+    };
+    const uint32_t base = blockIdx.x * kLayoutThreads;
+    Tri before{0u, 0u, 0ull};
+    for (uint32_t fi = threadIdx.x; fi < base; fi += kLayoutThreads) { uint32_t a, l, ch; int32_t q; const Tri t = entry(fi, a, q, l, ch); before = AddTri()(before, t); }
+    before = ReduceTri(tmp.red).Reduce(before, AddTri());
+    if (threadIdx.x == 0) carry = before;
+    __syncthreads();
+    const Tri c = carry;
+    const uint32_t fi = base + threadIdx.x;
+    uint32_t lch, len, chunks; int32_t sq;
+    const Tri v = entry(fi, lch, sq, len, chunks);
+    Tri ex, tot;
+    ScanTri(tmp.scan).ExclusiveScan(v, ex, Tri{0u, 0u, 0ull}, AddTri(), tot);
+    if (fi < A.n_forms) { form_slot[fi] = c.n + ex.n; row_base[fi] = c.rows + ex.rows; }
+    if (v.n) {
+        ShuffleForm F;
+        F.seq_slot = seq_slot[sq]; F.row_base = c.rows + ex.rows; F.n_mods = A.form_mods[fi].n_mods;
+        for (int i = 0; i < PQ_MAX_FORM_MODS; ++i) F.mod[i] = A.form_mods[fi].mod[i];
+        F.len = len; F.list_nch = lch; F.list_chunks = chunks; F.list_rows = v.rows; F.list_base = c.units + ex.units;
+        forms[c.n + ex.n] = F;
     }
-    if (threadIdx.x == 0) { totals->n_forms = carry3.n; totals->out_rows = carry3.rows; totals->list_units = carry3.units; }       // totals->n_valid: counted by k7_flag_valid
-    (void)valid_flag; (void)n_psm;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { totals->n_forms = c.n + tot.n; totals->out_rows = c.rows + tot.rows; totals->list_units = c.units + tot.units; }       // totals->n_valid: counted by k7_flag_valid
 }
 
 __global__ void k7_psm_form_keys(const DevPsm* __restrict__ psms, const uint32_t* __restrict__ list, uint32_t n, uint32_t* __restrict__ keys) {
@@ -616,7 +625,9 @@ int launch_shuffle_plans(const uint8_t* seq_flag, const TargetAux& A, int32_t n_
 }
 int launch_shuffle_layout(const uint8_t* seq_flag, const uint32_t* form_flag, const uint8_t* valid_flag, uint32_t n_psm, const ShuffleSeq* plans, const TargetAux& A,
                           uint32_t* seq_slot, uint32_t* form_slot, uint32_t* row_base, ShuffleSeq* seqs, ShuffleForm* forms, ShuffleTotals* totals, cudaStream_t st) {
-    k7_shuffle_layout<<<1, kLayoutThreads, 0, st>>>(seq_flag, form_flag, valid_flag, n_psm, plans, A, seq_slot, form_slot, row_base, seqs, forms, totals);
+    (void)valid_flag; (void)n_psm;
+    if (A.n_seq) k7_layout_seqs<<<(A.n_seq + kLayoutThreads - 1) / kLayoutThreads, kLayoutThreads, 0, st>>>(seq_flag, plans, A.n_seq, seq_slot, seqs, totals);
+    if (A.n_forms) k7_layout_forms<<<(A.n_forms + kLayoutThreads - 1) / kLayoutThreads, kLayoutThreads, 0, st>>>(form_flag, plans, A, seq_slot, form_slot, row_base, forms, totals);
     return 1;
 }
 int launch_psm_form_keys(const DevPsm* psms, const uint32_t* list, uint32_t n, uint32_t* keys, cudaStream_t st) {
