@@ -52,8 +52,8 @@ __device__ __forceinline__ void write_cell_lists(const uint8_t* row, const ModTa
             const double m = side == 0 ? acc : __dadd_rn(acc, kWater);
             uint32_t e[kListMaxCharge];
             e[0] = cell_filter(__dadd_rn(m, kProton));
-            e[1] = k >= 2 ? cell_filter(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5)) : kListSentinel;
-            e[2] = k >= 3 ? cell_filter(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0)) : kListSentinel;
+            e[1] = (nch_max >= 2 && k >= 2) ? cell_filter(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5)) : kListSentinel;
+            e[2] = (nch_max >= 3 && k >= 3) ? cell_filter(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0)) : kListSentinel;      // (the only real divide: skipped when no PSM of the form needs charge 3)
             const int j = (k - 1) & 7, s = 16 * (j & 3);
 #pragma unroll
             for (int c = 0; c < kListMaxCharge; ++c) {
