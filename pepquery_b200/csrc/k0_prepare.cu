@@ -401,14 +401,20 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
             for (uint32_t i = lane; i < P; i += 32) W.aux[W.ord[i]] = (uint16_t)i;
             __syncwarp();
             if (count_kept(W.keep, P, lane) > 7) {
+                double tic = 0.0;
+                if (lane == 0) for (uint32_t f = 0; f < P; ++f) if (W.keep[W.aux[f]]) tic = __dadd_rn(tic, W.in[f]);   // list order = file order
+                tic = __shfl_sync(0xffffffffu, tic, 0);
+                // the quotients I / TIC by every lane (the ~30-instruction divide was the bulk of the serial walk); lane 0 then adds
+                // them in the reference's order (descending intensity), which is what decides the cut
+                #pragma unroll 1
+                for (uint32_t k = lane; k < P; k += 32) { const uint32_t f = W.ordI[k]; W.db[k] = W.keep[W.aux[f]] ? __ddiv_rn(W.in[f], tic) : 0.0; }
+                __syncwarp();
                 if (lane == 0) {
-                    double tic = 0.0;
-                    for (uint32_t f = 0; f < P; ++f) if (W.keep[W.aux[f]]) tic = __dadd_rn(tic, W.in[f]);   // list order = file order
                     double rel = 0.0;
                     for (uint32_t k = P; k-- > 0;) {
                         uint32_t f = W.ordI[k]; uint32_t pos = W.aux[f];
                         if (!W.keep[pos]) continue;
-                        rel = __dadd_rn(rel, __ddiv_rn(W.in[f], tic));
+                        rel = __dadd_rn(rel, W.db[k]);
                         if (!(rel <= 0.95)) W.keep[pos] = 0;
                     }
                 }
