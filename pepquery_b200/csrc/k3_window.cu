@@ -7,6 +7,8 @@
 // (spectrum, isotope error); K1 applies the exact bucket + tolerance predicate to every row of the run.
 #include <cstdlib>
 
+#include <algorithm>
+
 #include "pq_internal.h"
 
 namespace pq {
@@ -139,6 +141,28 @@ __global__ void k_wait_chunk(const uint32_t* flag, uint32_t expected) {
         __nanosleep(500);
     }
 }
+
+// Candidate-first from PAGEABLE caller arrays: host threads pack the needed spectra (gather order) into a page-locked ring, the chunk
+// goes up with one copy, k_scatter_staged puts every spectrum in its place of the mass-sorted CSR and k_set_flag releases the chunk.
+__global__ void k_gather_sources(const int32_t* __restrict__ list, int32_t n, const int32_t* __restrict__ caller, const uint32_t* __restrict__ npeaks,
+                                 int32_t* __restrict__ src, uint64_t* __restrict__ cnt) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { cnt[i] = 0; return; }
+    const int32_t s = list[i];
+    src[i] = caller[s]; cnt[i] = npeaks[s];
+}
+__global__ void __launch_bounds__(256)
+k_scatter_staged(const int32_t* __restrict__ list, int32_t n, const uint64_t* __restrict__ g_off /* stream offsets of these entries (+ one) */, uint64_t base,
+                 const uint64_t* __restrict__ off_out, const double* __restrict__ st_mz, const double* __restrict__ st_in, double* __restrict__ mz_out, double* __restrict__ in_out) {
+    const int lane = threadIdx.x & 31;
+    const int32_t warps = (int32_t)((gridDim.x * blockDim.x) >> 5);
+    for (int32_t w = (int32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < n; w += warps) {
+        const uint64_t a = g_off[w] - base, cnt = g_off[w + 1] - g_off[w], b = off_out[list[w]];
+        for (uint64_t k = lane; k < cnt; k += 32) { mz_out[b + k] = st_mz[a + k]; in_out[b + k] = st_in[a + k]; }
+    }
+}
+__global__ void k_set_flag(uint32_t* flag, uint32_t v) { __threadfence(); atomicExch(flag, v); }
 
 // full-upload path: peaks arrive in caller order chunk by chunk, so the copy is driven by the virtual id
 // (inv[v] = mass-sorted position of virtual spectrum v; src = the caller spectrum whose peaks it has)
@@ -309,6 +333,16 @@ int launch_gather_peaks_chunked(const int32_t* list, int32_t n_list, int32_t chu
     *n_ctas = (uint32_t)grid;
     k_gather_peaks_chunked<<<grid, 128, 0, st>>>(list, n_list, chunk, caller, off_in, off_out, h_mz, h_in, mz_out, in_out, chunk_done);
     return 1;
+}
+int launch_gather_sources(const int32_t* list, int32_t n, const int32_t* caller, const uint32_t* npeaks, int32_t* src, uint64_t* cnt, cudaStream_t st) {
+    k_gather_sources<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(list, n, caller, npeaks, src, cnt);
+    return 1;
+}
+int launch_scatter_staged(const int32_t* list, int32_t n, const uint64_t* g_off, uint64_t base, const uint64_t* off_out, const double* st_mz, const double* st_in,
+                          double* mz_out, double* in_out, uint32_t* flag, uint32_t flag_value, cudaStream_t st) {
+    if (n > 0) k_scatter_staged<<<std::min((n + 7) / 8, 148 * 8), 256, 0, st>>>(list, n, g_off, base, off_out, st_mz, st_in, mz_out, in_out);
+    k_set_flag<<<1, 1, 0, st>>>(flag, flag_value);
+    return 2;
 }
 int launch_wait_chunk(const uint32_t* flag, uint32_t expected, cudaStream_t st) {
     k_wait_chunk<<<1, 1, 0, st>>>(flag, expected);

@@ -1,6 +1,7 @@
 // pq_api.cu — the C ABI of libpepquery_b200.so (include/pepquery_b200.h): context, device residency, step drivers.
 // No CPU fallback: every scoring entry point launches CUDA kernels or fails.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -97,6 +98,8 @@ struct pq_ctx {
     DevBuf gather_list;                      // candidate-first: the resident spectra (sorted positions) in caller order
     DevBuf k0_counters;                      // work hand-out words of the per-chunk K0 launches
     DevBuf chunk_done;                       // candidate-first gather: CTAs that have finished upload chunk c
+    // candidate-first from pageable caller arrays: page-locked packing ring (two chunks), its device twin, what to pack
+    void* pack_host = nullptr; size_t pack_host_cap = 0; DevBuf pack_dev, pack_src, pack_cnt, pack_off; cudaEvent_t pack_ev[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> k0_ev;           // K0 of upload chunk c has finished
     DevBuf d_zero;                           // caller indices of the charge-less spectra, ascending
     // tables
@@ -177,6 +180,8 @@ int32_t generate_shuffles(pq_ctx* ctx, cudaStream_t st, bool all, ShuffleTotals&
 // arrive in (gather_list, chunks of chunk_spectra, one K0-done event per chunk) and how many chunks make a part.
 struct LoadPlan {
     uint32_t n_jobs; unsigned long long cand; uint32_t n_res; uint32_t chunk_spectra; size_t n_chunks; const std::vector<cudaEvent_t>* k0_done;
+    // chunks whose K0-done event a second thread has recorded so far (pageable caller arrays), null = all recorded; and its failure flag
+    const std::atomic<size_t>* issued = nullptr; const std::atomic<bool>* failed = nullptr;
 };
 
 int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan);
@@ -451,6 +456,8 @@ int32_t pq_destroy(pq_ctx* ctx) {
     if (ctx->mgf_host) cudaFreeHost(ctx->mgf_host);
     for (cudaEvent_t e : ctx->mgf.ev) cudaEventDestroy(e);
     if (ctx->stage_host) { cudaFreeHost(ctx->stage_host); cudaEventDestroy(ctx->stage_ev[0]); cudaEventDestroy(ctx->stage_ev[1]); }
+    if (ctx->pack_host) cudaFreeHost(ctx->pack_host);
+    for (cudaEvent_t e : ctx->pack_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
     if (ctx->uev0) cudaEventDestroy(ctx->uev0);
     if (ctx->uev1) cudaEventDestroy(ctx->uev1);
@@ -600,9 +607,12 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
     // database and the shuffles of every target form — is queued by a helper thread (both have host round trips for their sizes)
     // while this thread sets up the upload: by the time the first spectra have arrived and are prepared, it is done.
     struct EarlyWork { std::thread th; int32_t rc = PQ_OK; std::string err; uint64_t launches = 0, d2h = 0; bool digest = false, shuffles = false; } early;
+    // cf_staged: a second thread packs, uploads and scatters the needed spectra chunk by chunk and queues each chunk's K0 behind it
+    struct Stager { std::thread th; std::string err; uint64_t launches = 0; std::atomic<size_t> issued{0}; std::atomic<bool> failed{false}; } stager;
     // whatever goes wrong from here on, the context ends up without spectra and with nothing in flight
     auto fail_load = [&](int32_t code, const std::string& msg) -> int32_t {
         if (early.th.joinable()) early.th.join();
+        if (stager.th.joinable()) stager.th.join();
         cudaStreamSynchronize(ctx->st_part); cudaStreamSynchronize(ctx->st_part2);
         cudaStreamSynchronize(sc); cudaStreamSynchronize(st); cudaStreamSynchronize(ctx->st_aux); cudaGetLastError();
         ctx->nS = 0; ctx->nCaller = 0; ctx->nZero = 0; ctx->max_peaks = 0; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0; ctx->prepared_at_load = false;
@@ -637,7 +647,10 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
     const void* d_h_mz = peaks_on_device ? mz : dev_ptr(mz); const void* d_h_in = peaks_on_device ? inten : dev_ptr(inten);      // (the MGF parser left the peaks in ld[3] / ld[4])
     const bool pinned_all = d_h_mz && d_h_in;                     // only the peak arrays are read in place; the precursor arrays are copied
     const bool want_cf = ctx->P.candidate_first != 0 && getenv("PQ_LOAD_FULL") == nullptr;
-    const bool cf = want_cf && ctx->have_targets && !ctx->targets.seqs.empty() && pinned_all;
+    // candidate-first needs the targets; the peaks are then gathered by a kernel from page-locked caller arrays, or — pageable arrays —
+    // packed by host threads into a page-locked ring and scattered on the device (cf_staged)
+    const bool cf_staged = want_cf && ctx->have_targets && !ctx->targets.seqs.empty() && !pinned_all && !peaks_on_device && getenv("PQ_PAGEABLE_FULL") == nullptr;
+    const bool cf = want_cf && ctx->have_targets && !ctx->targets.seqs.empty() && (pinned_all || cf_staged);
     const bool digest_here = ctx->ref_staged && !ctx->ref_digested && ctx->have_targets;
     if (digest_here && !cf) {   // full upload: the target keys of a staged reference digest go up before the copy engine fills with spectra
         std::string err;        // (candidate-first moves the peaks with a kernel: the keys go up on the digest's own stream, later)
@@ -800,13 +813,88 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
             if (trace) { cudaEventCreate(&tr0); cudaEventRecord(tr0, sc); }
             // one gather launch for the whole upload (its CTAs stay resident, chunk_done[c] counts the CTAs that have finished chunk c);
             // PQ_GATHER_PER_CHUNK: one launch per chunk, ordered by events (the earlier form, for A/B runs)
-            const bool one_gather = getenv("PQ_GATHER_PER_CHUNK") == nullptr && !trace_env;
+            const bool one_gather = cf_staged || (getenv("PQ_GATHER_PER_CHUNK") == nullptr && !trace_env);
             uint32_t gather_ctas = 0;
-            if (one_gather)
+            if (cf_staged) {
+                // what to pack: caller spectrum and peak count of every gather-list entry, and where each entry starts in the packed stream
+                CL(ctx->pack_src.reserve((size_t)n_res * 4 + 64)); CL(ctx->pack_cnt.reserve(((size_t)n_res + 2) * 8)); CL(ctx->pack_off.reserve(((size_t)n_res + 2) * 8));
+                k_launch += launch_gather_sources(ctx->gather_list.as<int32_t>(), (int32_t)n_res, ctx->s_caller.as<int32_t>(), ctx->s_npeaks.as<uint32_t>(),
+                                                  ctx->pack_src.as<int32_t>(), ctx->pack_cnt.as<uint64_t>(), st);
+                rc = scan_exclusive(ctx, ctx->pack_cnt.as<uint64_t>(), ctx->pack_off.as<uint64_t>(), (int)n_res + 1);
+                if (rc) return fail_load(rc, ctx->err);
+                std::vector<int32_t> h_src(n_res);
+                CL(cudaMemcpyAsync(h_src.data(), ctx->pack_src.p, (size_t)n_res * 4, cudaMemcpyDeviceToHost, st));
+                CL(cudaStreamSynchronize(st));
+                ctx->cnt.d2h_bytes += (uint64_t)n_res * 4;
+                // chunk sizes (peaks) -> ring of two chunks, page-locked on the host and its twin on the device
+                std::vector<uint64_t> chunk_first(nck + 1, 0);       // stream offset (peaks) of the first entry of every chunk
+                uint64_t max_chunk = 0;
+                for (size_t c = 0; c < nck; ++c) {
+                    const uint32_t a = (uint32_t)(c * chunk_spectra), cnt = std::min(chunk_spectra, n_res - a);
+                    uint64_t sum = 0;
+                    for (uint32_t i = a; i < a + cnt; ++i) sum += off[h_src[i] + 1] - off[h_src[i]];
+                    chunk_first[c + 1] = chunk_first[c] + sum; max_chunk = std::max(max_chunk, sum);
+                }
+                const size_t slot_bytes = (size_t)std::max<uint64_t>(max_chunk, 1) * 16;
+                if (ctx->pack_host_cap < 2 * slot_bytes) {
+                    if (ctx->pack_host) { cudaFreeHost(ctx->pack_host); ctx->pack_host = nullptr; ctx->pack_host_cap = 0; }
+                    CL(cudaHostAlloc(&ctx->pack_host, 2 * slot_bytes + (slot_bytes >> 2), cudaHostAllocDefault)); ctx->pack_host_cap = 2 * slot_bytes + (slot_bytes >> 2);
+                }
+                CL(ctx->pack_dev.reserve(2 * slot_bytes));
+                for (cudaEvent_t& e : ctx->pack_ev) if (!e) CL(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                int n_threads = 6;
+                if (const char* e = getenv("PQ_PACK_THREADS")) { int v = atoi(e); if (v > 0) n_threads = v; }
+                n_threads = std::max(1, std::min(n_threads, (int)std::thread::hardware_concurrency()));
+                const size_t half = slot_bytes / 16;                   // peaks per slot: [m/z of the chunk | intensities of the chunk]
+                // (No spinning wait kernels here: this producer needs the host to launch its copies, and a thread that sits in a device-wide
+                // synchronisation — cudaFree of a growing buffer — while a wait kernel spins would block those launches for ever.  Events
+                // instead: this thread records chunk c's event, then makes the compute stream wait for it, queues K0 and says so in `issued`.)
+                stager.th = std::thread([ctx, st, sc, sp, pc, eager, stream_search, nck, chunk_spectra, n_res, h_src = std::move(h_src), chunk_first, off, mz, inten, slot_bytes, half, n_threads, &stager]() {
+                    cudaSetDevice(ctx->P.device);
+                    struct Fail { Stager* s; ~Fail() { if (!s->err.empty()) s->failed.store(true, std::memory_order_release); } } fail_guard{&stager};
+                    for (size_t c = 0; c < nck; ++c) {
+                        const uint32_t a = (uint32_t)(c * chunk_spectra), cnt = std::min(chunk_spectra, n_res - a);
+                        const size_t slot = c & 1;
+                        if (c >= 2 && cudaEventSynchronize(ctx->pack_ev[slot]) != cudaSuccess) { stager.err = "pack ring: event"; return; }      // the slot's previous chunk has been scattered
+                        double* h_mz = reinterpret_cast<double*>(static_cast<uint8_t*>(ctx->pack_host) + slot * slot_bytes);
+                        double* h_in = h_mz + half;
+                        const uint64_t base = chunk_first[c], peaks = chunk_first[c + 1] - chunk_first[c];
+                        // host threads copy contiguous runs of entries; the offsets follow from a prefix over the chunk
+                        std::vector<uint64_t> pos(cnt + 1, 0);
+                        for (uint32_t i = 0; i < cnt; ++i) pos[i + 1] = pos[i] + (off[h_src[a + i] + 1] - off[h_src[a + i]]);
+                        auto work = [&](int t) {
+                            const uint32_t lo = (uint32_t)((uint64_t)cnt * t / n_threads), hi = (uint32_t)((uint64_t)cnt * (t + 1) / n_threads);
+                            for (uint32_t i = lo; i < hi; ++i) {
+                                const uint64_t so = off[h_src[a + i]], k = pos[i + 1] - pos[i];
+                                memcpy(h_mz + pos[i], mz + so, (size_t)k * 8); memcpy(h_in + pos[i], inten + so, (size_t)k * 8);
+                            }
+                        };
+                        std::vector<std::thread> pool;
+                        for (int t = 1; t < n_threads; ++t) pool.emplace_back(work, t);
+                        work(0);
+                        for (auto& t : pool) t.join();
+                        double* d_mz = reinterpret_cast<double*>(ctx->pack_dev.as<uint8_t>() + slot * slot_bytes);
+                        double* d_in = d_mz + half;
+                        if (peaks) {
+                            if (cudaMemcpyAsync(d_mz, h_mz, (size_t)peaks * 8, cudaMemcpyHostToDevice, sc) != cudaSuccess ||
+                                cudaMemcpyAsync(d_in, h_in, (size_t)peaks * 8, cudaMemcpyHostToDevice, sc) != cudaSuccess) { stager.err = "pack ring: copy"; return; }
+                        }
+                        stager.launches += (uint64_t)launch_scatter_staged(ctx->gather_list.as<int32_t>() + a, (int32_t)cnt, ctx->pack_off.as<uint64_t>() + a, base, ctx->s_off.as<uint64_t>(),
+                                                                            d_mz, d_in, ctx->s_mz.as<double>(), ctx->s_in.as<double>(), ctx->chunk_done.as<uint32_t>() + c, 1u, sc);
+                        if (cudaEventRecord(ctx->pack_ev[slot], sc) != cudaSuccess || cudaEventRecord(ctx->chunk_ev[c], sc) != cudaSuccess ||
+                            cudaStreamWaitEvent(st, ctx->chunk_ev[c], 0) != cudaSuccess) { stager.err = "pack ring: record"; return; }
+                        if (eager)
+                            stager.launches += (uint64_t)launch_prepare(sp, ctx->gather_list.as<int32_t>() + a, (int32_t)cnt, pc, ctx->blobs.as<uint8_t>(), ctx->blob_off.as<uint64_t>(),
+                                                                         ctx->blob_len.as<uint32_t>(), ctx->max_peaks, st, 0, ctx->prep_id.as<int32_t>(), 0, ctx->k0_counters.as<uint32_t>() + 4 * c);
+                        if (stream_search && cudaEventRecord(ctx->k0_ev[c], st) != cudaSuccess) { stager.err = "pack ring: K0 event"; return; }
+                        stager.issued.store(c + 1, std::memory_order_release);
+                    }
+                });
+            } else if (one_gather)
                 k_launch += launch_gather_peaks_chunked(ctx->gather_list.as<int32_t>(), (int32_t)n_res, (int32_t)chunk_spectra, ctx->s_caller.as<int32_t>(), in_off.as<uint64_t>(),
                                                         ctx->s_off.as<uint64_t>(), static_cast<const double*>(d_h_mz), static_cast<const double*>(d_h_in),
                                                         ctx->s_mz.as<double>(), ctx->s_in.as<double>(), ctx->chunk_done.as<uint32_t>(), &gather_ctas, sc);
-            for (size_t c = 0; c < nck; ++c) {
+            for (size_t c = 0; c < nck && !cf_staged; ++c) {
                 const uint32_t a = (uint32_t)(c * chunk_spectra), cnt = std::min(chunk_spectra, n_res - a);
                 if (one_gather) k_launch += launch_wait_chunk(ctx->chunk_done.as<uint32_t>() + c, gather_ctas, st);
                 else {
@@ -844,6 +932,7 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
         if (stream_search && n_res) {
             // Steps 2-4 part by part while the rest of the spectra are still arriving
             LoadPlan plan{hj.njobs, hj.cand, n_res, chunk_spectra_cf, n_chunks_cf, &ctx->k0_ev};
+            if (cf_staged) { plan.issued = &stager.issued; plan.failed = &stager.failed; }
             ctx->cnt.other_kernel_launches += (uint64_t)k_launch; k_launch = 0;
             rc = search_at_load(ctx, plan);
             if (rc) return fail_load(rc, ctx->err);
@@ -927,6 +1016,9 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
     mk.mark("digest (staged reference)");
     // targets given before the spectra: their table is built while the peaks are on their way (device work, a few launches)
     if (ctx->have_targets && !cf) { int32_t rc = finalize_targets(ctx); if (rc) return fail_load(rc, ctx->err); }
+    if (stager.th.joinable()) stager.th.join();
+    if (!stager.err.empty()) return fail_load(PQ_ERR_CUDA, stager.err);
+    ctx->cnt.other_kernel_launches += stager.launches;
     CL(cudaStreamSynchronize(st)); CL(cudaStreamSynchronize(sc));
     mk.mark("wait for the upload");
 #undef CL
@@ -1595,6 +1687,12 @@ int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan) {
         const uint32_t j0 = first[p], nj = first[p + 1] - first[p];
         // the part is complete when K0 has finished its last chunk
         const size_t last_chunk = std::min<size_t>((size_t)(p + 1) * chunks_per_part, plan.n_chunks) - 1;
+        if (plan.issued) {                       // a second thread records these events: wait (on the host) until this one has been recorded
+            while (plan.issued->load(std::memory_order_acquire) <= last_chunk) {
+                if (plan.failed && plan.failed->load(std::memory_order_acquire)) return fail(ctx, PQ_ERR_CUDA, "the upload of the spectra failed");
+                std::this_thread::yield();
+            }
+        }
         CU(cudaStreamWaitEvent(sq, (*plan.k0_done)[last_chunk], 0));
         if (!nj) continue;
         if (pcand[p] > 0xfffffff0ull) return fail(ctx, PQ_ERR_UNSUPPORTED, "too many Step-2 candidates for one launch");

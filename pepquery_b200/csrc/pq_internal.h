@@ -196,6 +196,10 @@ int launch_gather_peaks_chunked(const int32_t* list, int32_t n_list, int32_t chu
                                 const double* h_mz, const double* h_in, double* mz_out, double* in_out, uint32_t* chunk_done /* zeroed, one word per chunk */,
                                 uint32_t* n_ctas, cudaStream_t st);
 int launch_wait_chunk(const uint32_t* flag, uint32_t expected, cudaStream_t st);      // the stream goes on once *flag >= expected
+// candidate-first from pageable caller arrays: what to pack (caller spectrum + peak count per gather-list entry), and a packed chunk into the CSR
+int launch_gather_sources(const int32_t* list, int32_t n, const int32_t* caller, const uint32_t* npeaks, int32_t* src, uint64_t* cnt /* [n + 1] */, cudaStream_t st);
+int launch_scatter_staged(const int32_t* list, int32_t n, const uint64_t* g_off, uint64_t base, const uint64_t* off_out, const double* st_mz, const double* st_in,
+                          double* mz_out, double* in_out, uint32_t* flag, uint32_t flag_value, cudaStream_t st);
 int launch_invert_order(int64_t n, const int32_t* order, int32_t* inv, cudaStream_t st);
 int launch_gather_peaks_by_virtual(int64_t first, int64_t count, int64_t n, const int32_t* zero_idx, const int32_t* inv, const uint64_t* off_in,
                                    const uint64_t* off_out, const double* mz_in, const double* in_in, double* mz_out, double* in_out, cudaStream_t st);

@@ -977,6 +977,45 @@ def test_candidate_first_load(data, method, at_load, chunk, monkeypatch):
     assert_psms_equal(got4, o2.psms())
 
 
+@pytest.mark.parametrize("method,chunk,threads,staged_db", [(1, None, None, True), (1, "97", "3", True), (2, "1000", "1", False)])
+def test_candidate_first_load_from_pageable_buffers(data, method, chunk, threads, staged_db, monkeypatch):
+    """Targets before the spectra + PAGEABLE peak arrays (what a JVM hands over unless it registers its memory): the needed spectra
+    are packed by host threads into a page-locked ring, uploaded chunk by chunk and scattered into the CSR on the device.  Same
+    records, detail rows and byte counts as the gather from pinned arrays; with the database staged the search runs inside the load."""
+    prot, tgt, sp = data
+    keep = []
+    spp = _pinned_copy(sp, keep)
+    if chunk:
+        monkeypatch.setenv("PQ_LOAD_CHUNK_SPECTRA", chunk)
+    if threads:
+        monkeypatch.setenv("PQ_PACK_THREADS", threads)
+    p = _abi.default_params(n_random=60, score_method=method)
+
+    def search(buffers):
+        g = Search(p)
+        g.set_targets(*tgt)
+        if staged_db:
+            g.stage_reference(*prot)
+        g.load_spectra(buffers)
+        g.step2()
+        if staged_db:
+            g.build_reference()
+        else:
+            g.build_reference(*prot)
+        g.step3(); g.step4(); g.rank()
+        return g.psms(), np.sort(g.competitors(3), order=["spectrum", "ref_form"]), g.counters()
+    got_p, comp_p, c_p = search(sp)              # numpy arrays: pageable
+    got_q, comp_q, c_q = search(spp)             # the same values in page-locked memory
+    assert got_p.tobytes() == got_q.tobytes() and comp_p.tobytes() == comp_q.tobytes()
+    assert c_p.spectra_prepared == c_q.spectra_prepared and 0 < c_p.spectra_prepared < c_p.spectra_loaded
+    total_bytes = 16 * int(sp["peak_off"][-1])
+    assert abs(int(c_p.h2d_bytes) - int(c_q.h2d_bytes)) < 64 and c_p.h2d_bytes < total_bytes      # only the needed peaks crossed, either way
+    assert_psms_equal(got_p, run_oracle(p, sp, tgt, prot).psms())
+    monkeypatch.setenv("PQ_PAGEABLE_FULL", "1")   # the full chunked upload through the copy engine: same records
+    got_f, comp_f, c_f = search(sp)
+    assert got_f.tobytes() == got_p.tobytes() and comp_f.tobytes() == comp_p.tobytes() and c_f.h2d_bytes >= total_bytes
+
+
 @pytest.mark.parametrize("mode", ["full", "candidate_first"])
 @pytest.mark.parametrize("method", [1, 2])
 def test_spectra_without_a_charge(data, mode, method):
