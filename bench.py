@@ -15,7 +15,7 @@ Keys of the JSON line (rank 0): see the task contract.
   value             pairs/s with inputs resident in HBM (Step 4 decides shuffles by their score bound where it can)
   value_all_scored  the same with every shuffle scored in full (pq_params.score_all_shuffles)
   e2e               the same metric through the C ABI from HOST (pinned) buffers, H2D/D2H and the reference-table build inside the
-                    timed region; e2e.pageable: the same from pageable buffers (full chunked upload)
+                    timed region; e2e.pageable: the same from pageable buffers (needed spectra packed into a page-locked ring by host threads)
   roofline          the Step-4 K1 launch: physical DRAM traffic against the measured HBM peak, and warp-instruction issue rate
                     against the issue peak (the resource that binds); the algorithmic-bytes figure of SURVEY.md §8d beside them
   configs           driver-visible numbers of the other BASELINE.json configs (C1, C3, C4, one mass shard of C5)
@@ -528,11 +528,12 @@ def main():
         g, e2e = e2e_arm(sp, a.e2e_steps, a.e2e_warmup)
         e2e["buffers"] = "pinned host arrays: candidate-first upload (pq_params.candidate_first)"
         g.close()
-        # the same call sequence from pageable buffers (what a JVM hands over unless it registers its off-heap memory): full chunked upload
+        # the same call sequence from pageable buffers (what a JVM hands over unless it registers its off-heap memory): candidate-first through a host-packed page-locked ring
         if world == 1:
             spg = {k: np.array(v) for k, v in sp.items()}
             g, pg = e2e_arm(spg, 2, 1)
             e2e["pageable"] = {k: pg[k] for k in ("value", "unit", "ms_per_step", "steps", "h2d_bytes_per_step")}
+            e2e["pageable"]["buffers"] = "pageable host arrays: the needed spectra packed by host threads into a page-locked ring, uploaded chunk by chunk"
             g.close(); del spg
         # Informational (not `value`): the same end-to-end step with TWO searches in flight, each in its own context driven by its
         # own host thread — what a sweep over many spectrum files does: one search uploads while the other computes.
