@@ -637,9 +637,16 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
                 vb = k | (ec & kCellClean); ve = k;
             }
             const bool wide = end_c + 1u > first_c + 64u;              // a long stretch of the axis without events: the whole warp fills it
-            if (!wide) {
+            if (!wide && first_c <= end_c) {
+                // [first_c, eb) holds vb, two cells per store once aligned; cell end_c holds ve unless the stretch ends the table
+                const uint32_t eb = last ? end_c + 1u : end_c;
+                uint32_t c = first_c;
+                if ((c & 1u) && c < eb) cells_s[c++] = (uint16_t)vb;
+                const uint32_t vv = vb | (vb << 16);
                 #pragma unroll 1
-                for (uint32_t c = first_c; c <= end_c; ++c) cells_s[c] = (uint16_t)((c < end_c || last) ? vb : ve);
+                for (; c + 2 <= eb; c += 2) *reinterpret_cast<uint32_t*>(cells_s + c) = vv;
+                if (c < eb) cells_s[c] = (uint16_t)vb;
+                if (!last) cells_s[end_c] = (uint16_t)ve;
             }
             uint32_t todo = __ballot_sync(0xffffffffu, wide);
             #pragma unroll 1

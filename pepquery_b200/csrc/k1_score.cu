@@ -20,9 +20,6 @@
 #ifndef K1_MIN_BLOCKS
 #define K1_MIN_BLOCKS 4
 #endif
-#ifndef K1S_MIN_BLOCKS
-#define K1S_MIN_BLOCKS 7       // Step-2 scatter kernel (72 registers; 10 resident CTAs at 48 registers spill and measured 1.72 vs 1.57 ms)
-#endif
 
 namespace pq {
 
@@ -240,7 +237,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
 // Here every THREAD takes its own job and reads that spectrum's blob straight from global memory (L2): no staging, all
 // lanes busy, latency hidden by occupancy.  Same pair scorer, same results.
 template <int BLOCK, int METHOD>
-__global__ void __launch_bounds__(BLOCK, K1S_MIN_BLOCKS)
+__global__ void __launch_bounds__(BLOCK)      // (72 registers, 7 resident CTAs; forcing 10 CTAs at 48 registers measured 1.72 vs 1.57 ms)
 k1_scatter_kernel(ScoreLaunch L, ScoreConfig cfg) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* codes_all = reinterpret_cast<uint32_t*>(smem);                                            // [16][BLOCK]
