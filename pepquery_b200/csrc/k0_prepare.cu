@@ -655,7 +655,15 @@ k0_prepare_kernel(SpectraView sp, const int32_t* __restrict__ list, int32_t n_li
                 todo &= todo - 1;
                 const uint32_t f = __shfl_sync(0xffffffffu, first_c, src), e = __shfl_sync(0xffffffffu, end_c, src);
                 const uint32_t b = __shfl_sync(0xffffffffu, vb, src), v = __shfl_sync(0xffffffffu, ve, src), l = __shfl_sync(0xffffffffu, last, src);
-                for (uint32_t c = f + lane; c <= e; c += 32) cells_s[c] = (uint16_t)((c < e || l) ? b : v);
+                // [f, eb) holds b, two cells per lane and trip; cell e holds v unless the stretch ends the table
+                const uint32_t eb = l ? e + 1u : e, c0 = f + (f & 1u);
+                const uint32_t bb = b | (b << 16);
+                for (uint32_t c = c0 + 2u * lane; c + 2u <= eb; c += 64u) *reinterpret_cast<uint32_t*>(cells_s + c) = bb;
+                if (lane == 0) {
+                    if ((f & 1u) && f < eb) cells_s[f] = (uint16_t)b;
+                    if (eb > c0 && ((eb - c0) & 1u)) cells_s[eb - 1u] = (uint16_t)b;
+                    if (!l) cells_s[e] = (uint16_t)v;
+                }
             }
         }
         __syncwarp();
