@@ -33,7 +33,7 @@ __host__ __device__ __forceinline__ uint32_t lad_cl_units(int Lm1) { return (uin
 // front, [pm b][pm y][cl b c1..c3][cl y c1..c3]
 constexpr int kFillBlock = 128;
 __global__ void __launch_bounds__(kFillBlock)
-k_ladder_fill(const uint8_t* __restrict__ rows, uint32_t n, uint32_t stride, const ModTable* __restrict__ M, uint4* __restrict__ out) {
+k_ladder_fill(const uint8_t* __restrict__ rows, uint32_t n, uint32_t stride, const ModTable* __restrict__ M, uint4* __restrict__ out, uint8_t* __restrict__ len_out) {
     __shared__ uint32_t s_codes[16][kFillBlock];
     __shared__ double2 s_tab[kMaxCodes];
     __shared__ double s_nt[kMaxTermCodes], s_ct[kMaxTermCodes];
@@ -50,6 +50,7 @@ k_ladder_fill(const uint8_t* __restrict__ rows, uint32_t n, uint32_t stride, con
     if (i >= n) return;
     const uint32_t head = s_codes[0][tid];
     const int L = (int)(head & 0xFFu), Lm1 = L - 1;
+    len_out[i] = (uint8_t)L;                 // the lengths once more, one byte per row: a warp of K1 reads 32 of them from one sector
     if (Lm1 <= 0) return;
     auto residue = [&](int idx) -> uint32_t { return (s_codes[1 + (idx >> 2)][tid] >> (8 * (idx & 3))) & 0xFFu; };      // 0-based residue
     const uint32_t PM = lad_pm_units(Lm1), U = lad_cl_units(Lm1);
@@ -248,7 +249,7 @@ k1_ladder_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstag
             if (c >= J.cand_count) continue;
             const uint32_t row = J.cand_begin + c;
             if (!in_window(L.row_mass[row], J.mass, va, cfg)) continue;                // DBSearchWorker.java:38-52
-            const int Lm1 = (int)L.rows[(size_t)row * kRowBytes] - 1;
+            const int Lm1 = (int)L.lad_len[row] - 1;
             int32_t pred = 0;
             if (METHOD == 2) pred = L.row_pred[2 * (size_t)row + (J.charge == 2 ? 0 : 1)];
             const PairScore ps = score_ladder<BLOCK, METHOD>(L.lad + (size_t)row * L.lad_stride, Lm1, B, J.charge, itol, s_l10, L.ln_fact, pred, usedw);
@@ -323,15 +324,16 @@ int launch_score_ladder(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream
 
 // Builds the ladder tables of a row table (n rows of 64 bytes, none longer than max_len residues): one slot of `stride` 16-byte
 // units per row.  Returns the stride through *stride_units.
-bool build_row_ladders(cudaStream_t st, const uint8_t* rows, uint32_t n, int max_len, const ModTable* mods, DevBuf& lad, uint32_t* stride_units, uint64_t* launches,
-                       std::string& err) {
+bool build_row_ladders(cudaStream_t st, const uint8_t* rows, uint32_t n, int max_len, const ModTable* mods, DevBuf& lad, DevBuf& lad_len, uint32_t* stride_units,
+                       uint64_t* launches, std::string& err) {
     const int Lm1 = std::max(std::min(max_len, (int)kMaxLen) - 1, 1);
     const uint32_t stride = 2u * lad_pm_units(Lm1) + 2u * (uint32_t)kLadderCharges * lad_cl_units(Lm1);
     *stride_units = stride;
     if (n == 0) return true;
     cudaError_t e = lad.reserve((size_t)n * stride * 16);
+    if (e == cudaSuccess) e = lad_len.reserve((size_t)n + 64);
     if (e != cudaSuccess) { err = std::string("ladder tables: ") + cudaGetErrorString(e); return false; }
-    k_ladder_fill<<<(n + kFillBlock - 1) / kFillBlock, kFillBlock, 0, st>>>(rows, n, stride, mods, lad.as<uint4>());
+    k_ladder_fill<<<(n + kFillBlock - 1) / kFillBlock, kFillBlock, 0, st>>>(rows, n, stride, mods, lad.as<uint4>(), lad_len.as<uint8_t>());
     e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("ladder tables: ") + cudaGetErrorString(e); return false; }
     if (launches) *launches += 1;

@@ -41,7 +41,7 @@ struct PeptideTable {               // a mass-sorted candidate table resident on
     std::vector<FormRec> forms;     // mass ascending
     DevBuf rows, mass, pred, mask;
     bool have_mask = false;
-    DevBuf lad; uint32_t lad_stride = 0;   // precomputed fragment ladders of the rows (k1_ladder.cu), built before the first Step 3 over this table
+    DevBuf lad, lad_len; uint32_t lad_stride = 0;   // precomputed fragment ladders of the rows (k1_ladder.cu), built before the first Step 3 over this table
     bool have_lad = false;
     std::vector<double> h_mass;     // host copy for range searches
     RefDeviceTable dev;             // device-built table (reference only)
@@ -244,7 +244,7 @@ int32_t run_score_io(pq_ctx* ctx, const ScoreIO& io, JobKind kind, uint32_t n_jo
     L.results = io.results->as<JobResult>(); L.hits = io.hits->as<Hit>(); L.hit_count = io.hit_count->as<uint32_t>();
     L.hit_capacity = hit_capacity; L.max_blob_bytes = ctx->max_blob; L.job_counter = io.job_counter;
     if (kind == kJobTargets) L.tgt = ctx->targeted_view();
-    if (kind == kJobCompetitors && ladders && ladders->have_lad) { L.lad = ladders->lad.as<uint4>(); L.lad_stride = ladders->lad_stride; }
+    if (kind == kJobCompetitors && ladders && ladders->have_lad) { L.lad = ladders->lad.as<uint4>(); L.lad_stride = ladders->lad_stride; L.lad_len = ladders->lad_len.as<uint8_t>(); }
     if (kind == kJobShuffles && ctx->have_lists) { L.sh_forms = ctx->sh_forms.as<ShuffleForm>(); L.form_slot = ctx->sh_form_slot.as<uint32_t>(); L.lists = ctx->sh_lists.as<uint4>(); }
     ScoreConfig cfg = score_config(ctx, check_window);
     if (kind == kJobTargets && ctx->P.library_mode) cfg.no_bucket = 1;
@@ -270,8 +270,8 @@ int32_t ensure_ladders(pq_ctx* ctx, PeptideTable& T, const uint8_t* rows, uint32
     bool ok;
     if (T.lad.reserve(16) != cudaSuccess) return fail(ctx, PQ_ERR_NOMEM, "ladder tables");
     const int max_len = std::max(ctx->P.max_len, 1);      // reference rows come from the digest: min_len .. max_len residues
-    if (timed) { Timer t(ctx, &ctx->cnt.ms_ladder); ok = build_row_ladders(st, rows, n_rows, max_len, ctx->d_mods.as<ModTable>(), T.lad, &T.lad_stride, &launches, err); }
-    else ok = build_row_ladders(st, rows, n_rows, max_len, ctx->d_mods.as<ModTable>(), T.lad, &T.lad_stride, &launches, err);
+    if (timed) { Timer t(ctx, &ctx->cnt.ms_ladder); ok = build_row_ladders(st, rows, n_rows, max_len, ctx->d_mods.as<ModTable>(), T.lad, T.lad_len, &T.lad_stride, &launches, err); }
+    else ok = build_row_ladders(st, rows, n_rows, max_len, ctx->d_mods.as<ModTable>(), T.lad, T.lad_len, &T.lad_stride, &launches, err);
     if (!ok) return fail(ctx, PQ_ERR_CUDA, "ladder tables: " + err);
     ctx->cnt.other_kernel_launches += launches;
     T.have_lad = true;

@@ -126,6 +126,7 @@ struct ScoreLaunch {
     TargetedView tgt;                                      // Step 2: targeted PSM list
     // Step 3: precomputed fragment ladders of the candidate rows (k1_ladder.cu); null = walk the ladder per pair
     const uint4* lad; uint32_t lad_stride;                 // row r at lad + r * lad_stride (16-byte units)
+    const uint8_t* lad_len;                                // peptide length of every row (one byte each)
     // Step 5
     double ptm_delta; int32_t ptm_position; int32_t ptm_residue_code;
 };
@@ -137,8 +138,8 @@ int launch_prepare(const SpectraView& sp, const int32_t* list, int32_t n_list, c
 int launch_score(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st);
 int launch_score_ladder(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st);      // Step 3 over rows with precomputed ladders (k1_ladder.cu)
 // the ladder tables of a row table whose peptides have at most max_len residues: one fixed-size slot per row
-bool build_row_ladders(cudaStream_t st, const uint8_t* rows, uint32_t n, int max_len, const ModTable* mods, DevBuf& lad, uint32_t* stride_units, uint64_t* launches,
-                       std::string& err);
+bool build_row_ladders(cudaStream_t st, const uint8_t* rows, uint32_t n, int max_len, const ModTable* mods, DevBuf& lad, DevBuf& lad_len, uint32_t* stride_units,
+                       uint64_t* launches, std::string& err);
 
 // Step-2 window enumeration on device: for every usable spectrum x isotope error, the run of target rows whose mass
 // can fall in the precursor window.  Fills jobs (capacity n_spectra * n_isotope) and returns the count through d_n_jobs.
