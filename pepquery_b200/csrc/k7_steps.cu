@@ -460,13 +460,13 @@ __global__ void k7_merge_hits(const Hit* __restrict__ in, uint32_t n, uint32_t r
     Hit h = in[i]; h.cand -= row_off; out[i] = h;
 }
 // Step-2 jobs of a search at load: key = (part of the job's spectrum, charge, first target row, rows); rank_in_upload[s] = position of
-// sorted spectrum s in the order the upload brings the spectra over, part = rank / part_spectra
-__global__ void k7_part_job_keys(const Job* __restrict__ jobs, uint32_t n, const uint32_t* __restrict__ rank_in_upload, uint32_t part_spectra,
+// sorted spectrum s in the order the upload brings the spectra over, part = (rank + shift) / part_spectra (shift > 0: a shorter first part)
+__global__ void k7_part_job_keys(const Job* __restrict__ jobs, uint32_t n, const uint32_t* __restrict__ rank_in_upload, uint32_t part_spectra, uint32_t shift,
                                  uint64_t* __restrict__ key, uint32_t* __restrict__ idx) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Job& J = jobs[i];
-    uint64_t part = rank_in_upload[J.spectrum] / part_spectra, z = (uint64_t)min(max(J.charge, 0), 15);
+    uint64_t part = (rank_in_upload[J.spectrum] + shift) / part_spectra, z = (uint64_t)min(max(J.charge, 0), 15);
     key[i] = (part << 52) | (z << 48) | ((uint64_t)(J.cand_begin & 0xFFFFFFFFFFull) << 8) | (uint64_t)min(J.cand_count, 255u);
     idx[i] = i;
 }
@@ -517,9 +517,9 @@ int launch_merge_hits(const Hit* in, uint32_t n, uint32_t row_off, Hit* out, cud
     k7_merge_hits<<<blocks(n), 256, 0, st>>>(in, n, row_off, out);
     return 1;
 }
-int launch_part_job_keys(const Job* jobs, uint32_t n, const uint32_t* rank_in_upload, uint32_t part_spectra, uint64_t* key, uint32_t* idx, cudaStream_t st) {
+int launch_part_job_keys(const Job* jobs, uint32_t n, const uint32_t* rank_in_upload, uint32_t part_spectra, uint32_t shift, uint64_t* key, uint32_t* idx, cudaStream_t st) {
     if (!n) return 0;
-    k7_part_job_keys<<<blocks(n), 256, 0, st>>>(jobs, n, rank_in_upload, part_spectra, key, idx);
+    k7_part_job_keys<<<blocks(n), 256, 0, st>>>(jobs, n, rank_in_upload, part_spectra, shift, key, idx);
     return 1;
 }
 int launch_part_bounds(const uint64_t* sorted_key, uint32_t n, uint32_t n_parts, uint32_t* first, cudaStream_t st) {

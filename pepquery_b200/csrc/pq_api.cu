@@ -140,6 +140,7 @@ struct pq_ctx {
     bool pending_step[5] = {false, false, false, false, false};   // [2..4]: results of that step are already in the PSM table
     bool pending_ref = false;                                      // pq_build_reference(NULL) only has to cut the table out of the superset
     cudaStream_t st_part = nullptr, st_part2 = nullptr;      // search at load: the parts alternate between two streams
+    cudaStream_t st_shuf = nullptr; cudaEvent_t shuf_ev = nullptr; bool shuf_pending = false;      // the shuffles of every target form, generated beside the upload; Step 4 of a part waits for shuf_ev
     // targeted PSM list (SpectraInput.pep2targeted_spectra)
     DevBuf tg_keys, tg_listed, tg_canon, tg_seen, tg_best, tg_type; uint32_t n_targeted = 0; std::vector<uint32_t> tg_pos;     // tg_pos[i] = position of pair i in the sorted keys
     TargetedView targeted_view() const {
@@ -406,11 +407,19 @@ int32_t pq_create(const pq_params* params, pq_ctx** out) {
     memset(&ctx->cnt, 0, sizeof ctx->cnt);
     std::string err;
     if (!ctx->codes.init(*params, err)) { delete ctx; return fail(nullptr, PQ_ERR_UNSUPPORTED, err); }
-    if (cudaSetDevice(params->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->st_aux, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->st_part, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->st_part2, cudaStreamNonBlocking) != cudaSuccess) {
+    // Search at load: the spectrum preparation (st), the gather (st_copy) and the reference table (st_aux) gate every part, so their
+    // CTAs are dispatched ahead of the waiting CTAs of the parts' own kernels (st_part / st_part2); the shuffle generation (st_shuf),
+    // which only Step 4 of the first part waits for, fills what is left.
+    int prio_lo = 0, prio_hi = 0;
+    if (cudaSetDevice(params->device) == cudaSuccess && !getenv("PQ_NO_PRIORITY")) cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    const int prio_mid = prio_hi < prio_lo ? std::min(prio_hi + 1, prio_lo - 1 > prio_hi ? prio_lo - 1 : prio_lo) : prio_lo;
+    if (cudaSetDevice(params->device) != cudaSuccess || cudaStreamCreateWithPriority(&ctx->st, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->st_copy, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->st_aux, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->st_part, cudaStreamNonBlocking, prio_mid) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->st_part2, cudaStreamNonBlocking, prio_mid) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->st_shuf, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->shuf_ev, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx; return fail(nullptr, PQ_ERR_CUDA, "cannot initialise device");
     }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1); cudaEventCreate(&ctx->uev0); cudaEventCreate(&ctx->uev1);
@@ -468,6 +477,8 @@ int32_t pq_destroy(pq_ctx* ctx) {
     cudaStream_t st = ctx->st, st_copy = ctx->st_copy, st_aux = ctx->st_aux;
     if (ctx->st_part) { cudaStreamSynchronize(ctx->st_part); cudaStreamDestroy(ctx->st_part); }
     if (ctx->st_part2) { cudaStreamSynchronize(ctx->st_part2); cudaStreamDestroy(ctx->st_part2); }
+    if (ctx->st_shuf) { cudaStreamSynchronize(ctx->st_shuf); cudaStreamDestroy(ctx->st_shuf); }
+    if (ctx->shuf_ev) cudaEventDestroy(ctx->shuf_ev);
     delete ctx;
     if (st) cudaStreamDestroy(st);
     if (st_copy) cudaStreamDestroy(st_copy);
@@ -613,7 +624,7 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
     auto fail_load = [&](int32_t code, const std::string& msg) -> int32_t {
         if (early.th.joinable()) early.th.join();
         if (stager.th.joinable()) stager.th.join();
-        cudaStreamSynchronize(ctx->st_part); cudaStreamSynchronize(ctx->st_part2);
+        cudaStreamSynchronize(ctx->st_part); cudaStreamSynchronize(ctx->st_part2); cudaStreamSynchronize(ctx->st_shuf);
         cudaStreamSynchronize(sc); cudaStreamSynchronize(st); cudaStreamSynchronize(ctx->st_aux); cudaGetLastError();
         ctx->nS = 0; ctx->nCaller = 0; ctx->nZero = 0; ctx->max_peaks = 0; ctx->step_done = 0; reset_psm_state(ctx); ctx->n_prepared = 0; ctx->prepared_at_load = false;
         ctx->residency = 0; ctx->n_resident = 0; ctx->cnt.spectra_loaded = 0; ctx->cnt.spectra_usable = 0; ctx->host_spectra_valid = false;
@@ -675,12 +686,13 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
                 early.launches += l; early.digest = true;
             }
             if (need_shuffles) {
-                if (cudaStreamWaitEvent(ctx->st_part, ctx->targets_ev, 0) != cudaSuccess) { early.rc = PQ_ERR_CUDA; early.err = "early shuffles: stream wait"; return; }
+                if (cudaStreamWaitEvent(ctx->st_shuf, ctx->targets_ev, 0) != cudaSuccess) { early.rc = PQ_ERR_CUDA; early.err = "early shuffles: stream wait"; return; }
                 pq_counters c; memset(&c, 0, sizeof c);
                 ShuffleTotals tot; memset(&tot, 0, sizeof tot);
-                const int32_t rc = generate_shuffles(ctx, ctx->st_part, true, tot, false, &c);      // on the parts' stream: their Step 4 is ordered behind it
+                const int32_t rc = generate_shuffles(ctx, ctx->st_shuf, true, tot, false, &c);      // a stream of its own: only Step 4 of a part waits for it (shuf_ev), Steps 2 and 3 do not
                 early.launches += c.other_kernel_launches; early.d2h += c.d2h_bytes;
                 if (rc) { early.rc = rc; return; }
+                if (cudaEventRecord(ctx->shuf_ev, ctx->st_shuf) != cudaSuccess) { early.rc = PQ_ERR_CUDA; early.err = "early shuffles: event"; return; }
                 early.shuffles = true;
             }
         });
@@ -927,7 +939,10 @@ static int32_t load_spectra_impl(pq_ctx* ctx, int64_t n, const double* prec_mz, 
         if (early.rc) return fail_load(early.rc, early.err.empty() ? ctx->err : early.err);
         ctx->cnt.other_kernel_launches += early.launches; ctx->cnt.d2h_bytes += early.d2h;
         if (early.digest) ctx->ref_digested = true;
-        if (early.shuffles) { ctx->shuffles_all = true; ctx->shuffles_epoch = ctx->targets_epoch; }
+        if (early.shuffles) {
+            ctx->shuffles_all = true; ctx->shuffles_epoch = ctx->targets_epoch; ctx->shuf_pending = true;
+            CL(cudaStreamWaitEvent(st, ctx->shuf_ev, 0));      // whatever is queued on the main stream from here on sees the shuffles
+        }
         mk.mark("early work joined");
         if (stream_search && n_res) {
             // Steps 2-4 part by part while the rest of the spectra are still arriving
@@ -1603,6 +1618,36 @@ int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan) {
     PeptideTable& T = ctx->targets; PeptideTable& R = ctx->reference; PeptideTable& S = ctx->ref_super;
     const int64_t nv = ctx->nS;
     SpectraView sp = ctx->view();
+    // ---- the Step-2 jobs by part: queued first (they need nothing of the reference), read back once the reference table is on its way ----
+    const uint32_t n_jobs = plan.n_jobs;
+    uint32_t chunks_per_part = 6;      // measured at C2 size: 2 -> 48.4 ms end to end, 4 -> 44.4, 6 -> 43.7, 8 -> 43.6 (every part costs ~40 small launches and five host round trips)
+    if (const char* e = getenv("PQ_CHUNKS_PER_PART")) { int v = atoi(e); if (v > 0) chunks_per_part = (uint32_t)v; }
+    // the first part is shorter: the reference table and the jobs are ready well before six chunks have arrived (4 -> 41.4 ms, 6 -> 42.4 ms when every part has that size)
+    uint32_t first_chunks = std::min<uint32_t>(4, chunks_per_part);
+    if (const char* e = getenv("PQ_FIRST_PART_CHUNKS")) { int v = atoi(e); if (v > 0) first_chunks = std::min<uint32_t>((uint32_t)v, chunks_per_part); }
+    const uint32_t shift_chunks = chunks_per_part - first_chunks;
+    const uint32_t part_spectra = plan.chunk_spectra * chunks_per_part, part_shift = plan.chunk_spectra * shift_chunks;
+    const uint32_t n_parts = (plan.n_res + part_shift + part_spectra - 1) / part_spectra;
+    if (ctx->parts.size() < n_parts) ctx->parts.resize(n_parts);
+    std::vector<uint32_t> first(n_parts + 1, 0); std::vector<unsigned long long> pcand(n_parts, 0);
+    int k_parts = 0; uint32_t* d_first = nullptr; unsigned long long* d_pc = nullptr;
+    if (n_jobs) {
+        CU(ctx->up_rank.reserve((size_t)nv * 4 + 64)); CU(ctx->part_first.reserve(((size_t)n_parts + 2) * 16));
+        CU(ctx->k_key_a.reserve((size_t)n_jobs * 8)); CU(ctx->k_key_b.reserve((size_t)n_jobs * 8)); CU(ctx->k_idx_a.reserve((size_t)n_jobs * 4)); CU(ctx->k_idx_b.reserve((size_t)n_jobs * 4));
+        CU(ctx->jobs2.reserve((size_t)n_jobs * sizeof(Job)));
+        k_parts = launch_scatter_rank(ctx->gather_list.as<int32_t>(), plan.n_res, ctx->up_rank.as<uint32_t>(), sp_);
+        k_parts += launch_fix_job_blobs(ctx->jobs.as<Job>(), n_jobs, ctx->prep_id.as<int32_t>(), sp_);
+        k_parts += launch_part_job_keys(ctx->jobs.as<Job>(), n_jobs, ctx->up_rank.as<uint32_t>(), part_spectra, part_shift, ctx->k_key_a.as<uint64_t>(), ctx->k_idx_a.as<uint32_t>(), sp_);
+        int32_t rc = sort_pairs_on(ctx, sp_, ctx->parts[0].tmp, ctx->k_key_a.as<uint64_t>(), ctx->k_key_b.as<uint64_t>(), ctx->k_idx_a.as<uint32_t>(), ctx->k_idx_b.as<uint32_t>(), (int)n_jobs, 64);
+        if (rc) return rc;
+        k_parts += launch_gather_jobs(ctx->jobs.as<Job>(), ctx->k_idx_b.as<uint32_t>(), n_jobs, ctx->jobs2.as<Job>(), sp_);
+        std::swap(ctx->jobs, ctx->jobs2);
+        d_first = ctx->part_first.as<uint32_t>();
+        d_pc = reinterpret_cast<unsigned long long*>(ctx->part_first.as<uint8_t>() + ((size_t)n_parts + 2) * 8);
+        CU(cudaMemsetAsync(d_pc, 0, (size_t)n_parts * 8, sp_));
+        k_parts += launch_part_bounds(ctx->k_key_b.as<uint64_t>(), n_jobs, n_parts, d_first, sp_);
+        k_parts += launch_part_cand(ctx->jobs.as<Job>(), n_jobs, ctx->k_key_b.as<uint64_t>(), d_pc, sp_);
+    }
     // ---- reference: digest (if not done), superset expansion over the resident mass range ----
     if (!ctx->ref_digested) {
         std::string err;
@@ -1645,34 +1690,11 @@ int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan) {
     }
     CU(cudaStreamSynchronize(sa));
     mk.mark("shuffles for all forms");
-    // ---- the Step-2 jobs by part ----
-    const uint32_t n_jobs = plan.n_jobs;
-    uint32_t chunks_per_part = 6;      // measured at C2 size: 2 -> 48.4 ms end to end, 4 -> 44.4, 6 -> 43.7, 8 -> 43.6 (every part costs ~40 small launches and five host round trips)
-    if (const char* e = getenv("PQ_CHUNKS_PER_PART")) { int v = atoi(e); if (v > 0) chunks_per_part = (uint32_t)v; }
-    const uint32_t part_spectra = plan.chunk_spectra * chunks_per_part;
-    const uint32_t n_parts = (plan.n_res + part_spectra - 1) / part_spectra;
-    if (ctx->parts.size() < n_parts) ctx->parts.resize(n_parts);
-    std::vector<uint32_t> first(n_parts + 1, 0); std::vector<unsigned long long> pcand(n_parts, 0);
     if (n_jobs) {
-        CU(ctx->up_rank.reserve((size_t)nv * 4 + 64)); CU(ctx->part_first.reserve(((size_t)n_parts + 2) * 16));
-        CU(ctx->k_key_a.reserve((size_t)n_jobs * 8)); CU(ctx->k_key_b.reserve((size_t)n_jobs * 8)); CU(ctx->k_idx_a.reserve((size_t)n_jobs * 4)); CU(ctx->k_idx_b.reserve((size_t)n_jobs * 4));
-        CU(ctx->jobs2.reserve((size_t)n_jobs * sizeof(Job)));
-        int k = launch_scatter_rank(ctx->gather_list.as<int32_t>(), plan.n_res, ctx->up_rank.as<uint32_t>(), sp_);
-        k += launch_fix_job_blobs(ctx->jobs.as<Job>(), n_jobs, ctx->prep_id.as<int32_t>(), sp_);
-        k += launch_part_job_keys(ctx->jobs.as<Job>(), n_jobs, ctx->up_rank.as<uint32_t>(), part_spectra, ctx->k_key_a.as<uint64_t>(), ctx->k_idx_a.as<uint32_t>(), sp_);
-        int32_t rc = sort_pairs_on(ctx, sp_, ctx->scan_tmp, ctx->k_key_a.as<uint64_t>(), ctx->k_key_b.as<uint64_t>(), ctx->k_idx_a.as<uint32_t>(), ctx->k_idx_b.as<uint32_t>(), (int)n_jobs, 64);
-        if (rc) return rc;
-        k += launch_gather_jobs(ctx->jobs.as<Job>(), ctx->k_idx_b.as<uint32_t>(), n_jobs, ctx->jobs2.as<Job>(), sp_);
-        std::swap(ctx->jobs, ctx->jobs2);
-        uint32_t* d_first = ctx->part_first.as<uint32_t>();
-        unsigned long long* d_pc = reinterpret_cast<unsigned long long*>(ctx->part_first.as<uint8_t>() + ((size_t)n_parts + 2) * 8);
-        CU(cudaMemsetAsync(d_pc, 0, (size_t)n_parts * 8, sp_));
-        k += launch_part_bounds(ctx->k_key_b.as<uint64_t>(), n_jobs, n_parts, d_first, sp_);
-        k += launch_part_cand(ctx->jobs.as<Job>(), n_jobs, ctx->k_key_b.as<uint64_t>(), d_pc, sp_);
         CU(cudaMemcpyAsync(first.data(), d_first, ((size_t)n_parts + 1) * 4, cudaMemcpyDeviceToHost, sp_));
         CU(cudaMemcpyAsync(pcand.data(), d_pc, (size_t)n_parts * 8, cudaMemcpyDeviceToHost, sp_));
         CU(cudaStreamSynchronize(sp_));
-        ctx->cnt.other_kernel_launches += (uint64_t)k + 3;
+        ctx->cnt.other_kernel_launches += (uint64_t)k_parts + 3;
     }
     mk.mark("jobs by part");
     WindowConfig W = window_config(ctx, false);
@@ -1686,7 +1708,7 @@ int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan) {
         cudaStream_t sq = (p & 1u) && !getenv("PQ_ONE_PART_STREAM") ? ctx->st_part2 : sp_;
         const uint32_t j0 = first[p], nj = first[p + 1] - first[p];
         // the part is complete when K0 has finished its last chunk
-        const size_t last_chunk = std::min<size_t>((size_t)(p + 1) * chunks_per_part, plan.n_chunks) - 1;
+        const size_t last_chunk = std::min<size_t>((size_t)(p + 1) * chunks_per_part - shift_chunks, plan.n_chunks) - 1;
         if (plan.issued) {                       // a second thread records these events: wait (on the host) until this one has been recorded
             while (plan.issued->load(std::memory_order_acquire) <= last_chunk) {
                 if (plan.failed && plan.failed->load(std::memory_order_acquire)) return fail(ctx, PQ_ERR_CUDA, "the upload of the spectra failed");
@@ -1755,11 +1777,13 @@ int32_t search_at_load(pq_ctx* ctx, const LoadPlan& plan) {
         CU(cudaMemcpyAsync(&n_valid, scal + 5, 4, cudaMemcpyDeviceToHost, sq));
         CU(cudaStreamSynchronize(sq));
         Step4Work W4{&B.valid_flag, &B.list, &B.order, &B.keys, &B.keys2, &B.jobs, &B.results, &B.hits, &B.hit_count, &B.tmp, scal + 4, scal + 12};
+        if (ctx->shuf_pending) CU(cudaStreamWaitEvent(sq, ctx->shuf_ev, 0));
         rc = step4_score(ctx, sq, B.psm.as<DevPsm>(), nh, n_valid, W4, false);
         if (rc) return rc;
         N += nh; NS += nseg; NH3 += B.nh3;
     }
     CU(cudaStreamSynchronize(ctx->st_part2));
+    if (ctx->shuf_pending) { CU(cudaStreamSynchronize(ctx->st_shuf)); ctx->shuf_pending = false; }
     mk.mark("parts queued");
     // ---- merge ----
     ctx->n_psm = 0; ctx->n_seg = 0; ctx->nh3 = 0; ctx->comp3_ready = false; ctx->comp3_n = 0;

@@ -267,7 +267,7 @@ int launch_merge_psms(const DevPsm* in, uint32_t n, uint32_t seg_off, DevPsm* ou
 int launch_merge_segs(const uint32_t* seg_start_in, const SegAgg* agg_in, uint32_t n_seg, uint32_t psm_off, uint32_t row_off, uint32_t* seg_start_out, SegAgg* agg_out,
                       uint32_t end_value, int last, cudaStream_t st);
 int launch_merge_hits(const Hit* in, uint32_t n, uint32_t row_off, Hit* out, cudaStream_t st);
-int launch_part_job_keys(const Job* jobs, uint32_t n, const uint32_t* rank_in_upload, uint32_t part_spectra, uint64_t* key, uint32_t* idx, cudaStream_t st);
+int launch_part_job_keys(const Job* jobs, uint32_t n, const uint32_t* rank_in_upload, uint32_t part_spectra, uint32_t shift, uint64_t* key, uint32_t* idx, cudaStream_t st);
 int launch_part_bounds(const uint64_t* sorted_key, uint32_t n, uint32_t n_parts, uint32_t* first, cudaStream_t st);
 int launch_part_cand(const Job* jobs, uint32_t n, const uint64_t* sorted_key, unsigned long long* cand, cudaStream_t st);
 int launch_window_rows(const double* mass, uint32_t n, double lo, double hi, uint32_t* ab, cudaStream_t st);
