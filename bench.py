@@ -471,11 +471,18 @@ def main():
         issue = {"warp_inst_per_launch": prof["warp_inst_per_launch"], "warp_inst_per_pair": prof["warp_inst_per_launch"] / max(k1_pairs, 1),
                  "inst_per_s": ips, "peak": ipeak, "peak_is": "%d SMs x 4 schedulers x %.0f MHz (one warp instruction per scheduler and cycle)" % (sm_count, sm_mhz),
                  "frac": ips / ipeak, "ncu_issue_active_pct": prof.get("issue_active_pct")}
+        if prof.get("lsu_wavefronts_per_launch"):
+            # the L1 / shared-memory data pipe: one wavefront per SM and cycle; the count pass is a byte look-up per fragment cell in shared memory
+            wps = prof["lsu_wavefronts_per_launch"] / (k1_ms / 1e3); wpeak = sm_count * sm_mhz * 1e6
+            issue["lsu_data_pipe"] = {"wavefronts_per_launch": prof["lsu_wavefronts_per_launch"], "shared_memory_share": prof["lsu_wavefronts_shared_per_launch"] / prof["lsu_wavefronts_per_launch"],
+                                      "wavefronts_per_s": wps, "peak": wpeak, "peak_is": "%d SMs x %.0f MHz (one L1/shared-memory wavefront per SM and cycle)" % (sm_count, sm_mhz),
+                                      "frac": wps / wpeak, "ncu_pct": prof.get("lsu_wavefronts_pct")}
     alg = (k1_bytes / 1e9) / (k1_ms / 1e3) if k1_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "kernel": "k1_score_kernel<256,%d> (Step 4, one launch per step)" % a.method, "peak_source": peak_src,
                 "ms_per_launch": k1_ms, "pairs_per_launch": k1_pairs,
-                "issue": issue, "binding": "issue slots (warp-instruction issue), not HBM" if issue else None,
+                "issue": issue, "binding": ("the L1/shared-memory data pipe (issue.lsu_data_pipe.frac) and warp-instruction issue slots (issue.frac), not HBM" if issue and issue.get("lsu_data_pipe")
+                                            else "issue slots (warp-instruction issue), not HBM") if issue else None,
                 "algorithmic": {"bytes_per_launch": k1_bytes, "GBps": alg, "x_hbm_peak": alg / peak,
                                 "note": "SURVEY.md 8d accounting: sum over pairs of 16*P_s+96 bytes, as if every pair re-read its spectrum.  The kernel stages a "
                                         "spectrum once per ~1000 shuffles, so this figure is NOT a roofline fraction (it exceeds 1); achieved/frac above are "
