@@ -324,6 +324,11 @@ int32_t pq_reset_counters(pq_ctx* ctx);
  * which = 0 records the start event, 1 the stop event; elapsed = stop - start after synchronising the stop event. */
 int32_t pq_event_record(pq_ctx* ctx, int32_t which);
 int32_t pq_event_elapsed_ms(pq_ctx* ctx, double* ms);
+/* Device self-test of an arithmetic shortcut of the kernels (diagnostic; no reference counterpart).
+ * which = 1: the three-operation RN(x / 3) the kernels use for the m/z of triply charged fragments against the IEEE division, over
+ * n doubles (pseudo-random significands and exponents from `seed`, magnitudes 2^-8 .. 2^16, plus their neighbours in ulps).
+ * *mismatches = how many differed (must be 0). */
+int32_t pq_selftest(pq_ctx* ctx, int32_t which, uint64_t n, uint64_t seed, uint64_t* mismatches);
 
 /* Host-side text front end: single-pass MGF parser into CSR buffers.  Two-call pattern:
  * first call with NULL outputs returns the required sizes. */

@@ -248,7 +248,7 @@ __device__ __forceinline__ PairScore score_pair_n(const uint32_t* codes /* this 
     auto ion = [&](double m, int k) {
         push(__dadd_rn(m, kProton));
         if (nch >= 2 && k >= 2) push(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5));
-        if (nch >= 3 && k >= 3) push(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0));
+        if (nch >= 3 && k >= 3) push(div3_rn(__dadd_rn(m, __dmul_rn(3.0, kProton))));
         if (NCH == 0) {
             if (nch >= 4 && k >= 4) push(__dmul_rn(__dadd_rn(m, 4.0 * kProton), 0.25));
             for (int c = 5; c <= nch && c <= k; ++c) {
@@ -345,7 +345,7 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
     auto ion = [&](double m, int k) -> uint32_t {                        // any ion number (A6: charge c needs c <= k)
         uint32_t c = clean(__dadd_rn(m, kProton));
         if (nch >= 2 && k >= 2) c += clean(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5));
-        if (nch >= 3 && k >= 3) c += clean(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0));
+        if (nch >= 3 && k >= 3) c += clean(div3_rn(__dadd_rn(m, __dmul_rn(3.0, kProton))));
         if (NCH == 0) {
             if (nch >= 4 && k >= 4) c += clean(__dmul_rn(__dadd_rn(m, 4.0 * kProton), 0.25));
             for (int f = 5; f <= nch && f <= k; ++f) c += clean(__ddiv_rn(__dadd_rn(m, __dmul_rn((double)f, kProton)), (double)f));
@@ -356,7 +356,7 @@ __device__ __forceinline__ uint32_t count_possible_n(const uint32_t* codes, cons
         if (NCH == 0) return ion(m, k);
         uint32_t c = clean(__dadd_rn(m, kProton));
         if (NCH >= 2) c += clean(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5));
-        if (NCH >= 3) c += clean(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0));
+        if (NCH >= 3) c += clean(div3_rn(__dadd_rn(m, __dmul_rn(3.0, kProton))));
         return c;
     };
     // ion / charge combinations of one series: sum over k = 1..L-1 of min(nch, k)

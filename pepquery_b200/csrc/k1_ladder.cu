@@ -55,39 +55,38 @@ k_ladder_fill(const uint8_t* __restrict__ rows, uint32_t n, uint32_t stride, con
     auto residue = [&](int idx) -> uint32_t { return (s_codes[1 + (idx >> 2)][tid] >> (8 * (idx & 3))) & 0xFFu; };      // 0-based residue
     const uint32_t PM = lad_pm_units(Lm1), U = lad_cl_units(Lm1);
     uint4* base = out + (size_t)i * stride;
-    constexpr unsigned long long kSent4 = 0x0001000100010001ull * (unsigned long long)kCellSentinel;
+    constexpr uint32_t kSent2 = 0x00010001u * kCellSentinel;
     for (int side = 0; side < 2; ++side) {
         double2* pm = reinterpret_cast<double2*>(base + (size_t)side * PM);
         uint4* cl = base + 2 * (size_t)PM + (size_t)side * kLadderCharges * U;
         double acc = side == 0 ? s_nt[(head >> 8) & 0xFFu] : s_ct[(head >> 16) & 0xFFu];
-        unsigned long long lo[kLadderCharges], hi[kLadderCharges];
-#pragma unroll
-        for (int c = 0; c < kLadderCharges; ++c) { lo[c] = kSent4; hi[c] = kSent4; }
         double prev = 0.0;
-        for (int k = 1; k <= Lm1; ++k) {
-            const double2 t = s_tab[residue(side == 0 ? k - 1 : L - k)];
-            acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
-            const double m = side == 0 ? acc : __dadd_rn(acc, kWater);
-            if (k & 1) { prev = m; if (k == Lm1) pm[(k - 1) >> 1] = make_double2(m, 0.0); }
-            else pm[(k - 1) >> 1] = make_double2(prev, m);
-            const int j = (k - 1) & 7;
-            uint32_t e[kLadderCharges];
-            e[0] = 2u * cell_filter(__dadd_rn(m, kProton));
-            e[1] = k >= 2 ? 2u * cell_filter(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5)) : kCellSentinel;
-            e[2] = k >= 3 ? 2u * cell_filter(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0)) : kCellSentinel;
+        for (uint32_t u = 0; u < U; ++u) {      // a unit (eight ions) at a time: every slot of the packed words is a compile-time position
+            uint32_t w[kLadderCharges][4];
 #pragma unroll
-            for (int c = 0; c < kLadderCharges; ++c) {
-                const int s = 16 * (j & 3);
-                if (j < 4) lo[c] = (lo[c] & ~(0xFFFFull << s)) | ((unsigned long long)e[c] << s);
-                else hi[c] = (hi[c] & ~(0xFFFFull << s)) | ((unsigned long long)e[c] << s);
-            }
-            if (j == 7 || k == Lm1) {
+            for (int c = 0; c < kLadderCharges; ++c) { w[c][0] = kSent2; w[c][1] = kSent2; w[c][2] = kSent2; w[c][3] = kSent2; }
+            auto ion = [&](int k, auto slot) {
+                constexpr int J = decltype(slot)::value;
+                const double2 t = s_tab[residue(side == 0 ? k - 1 : L - k)];
+                acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+                const double m = side == 0 ? acc : __dadd_rn(acc, kWater);
+                if (!(J & 1)) { prev = m; if (k == Lm1) pm[(k - 1) >> 1] = make_double2(m, 0.0); }      // ion k sits in slot (k - 1) & 7: odd k = even slot
+                else pm[(k - 1) >> 1] = make_double2(prev, m);
+                unit_put<J>(w[0], 2u * cell_filter(__dadd_rn(m, kProton)));
+                if (k >= 2) unit_put<J>(w[1], 2u * cell_filter(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5)));
+                if (k >= 3) unit_put<J>(w[2], 2u * cell_filter(div3_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)))));
+            };
+            const int k0 = 8 * (int)u + 1;
+            if (k0 + 0 <= Lm1) ion(k0 + 0, std::integral_constant<int, 0>());
+            if (k0 + 1 <= Lm1) ion(k0 + 1, std::integral_constant<int, 1>());
+            if (k0 + 2 <= Lm1) ion(k0 + 2, std::integral_constant<int, 2>());
+            if (k0 + 3 <= Lm1) ion(k0 + 3, std::integral_constant<int, 3>());
+            if (k0 + 4 <= Lm1) ion(k0 + 4, std::integral_constant<int, 4>());
+            if (k0 + 5 <= Lm1) ion(k0 + 5, std::integral_constant<int, 5>());
+            if (k0 + 6 <= Lm1) ion(k0 + 6, std::integral_constant<int, 6>());
+            if (k0 + 7 <= Lm1) ion(k0 + 7, std::integral_constant<int, 7>());
 #pragma unroll
-                for (int c = 0; c < kLadderCharges; ++c) {
-                    cl[(size_t)c * U + ((k - 1) >> 3)] = make_uint4((uint32_t)lo[c], (uint32_t)(lo[c] >> 32), (uint32_t)hi[c], (uint32_t)(hi[c] >> 32));
-                    lo[c] = kSent4; hi[c] = kSent4;
-                }
-            }
+            for (int c = 0; c < kLadderCharges; ++c) cl[(size_t)c * U + u] = make_uint4(w[c][0], w[c][1], w[c][2], w[c][3]);
         }
     }
 }
@@ -178,7 +177,7 @@ __device__ __forceinline__ PairScore score_ladder(const uint4* __restrict__ lad,
         const uint64_t d1 = side ? M.y[0] : M.b[0], d2 = side ? M.y[1] : M.b[1], d3 = side ? M.y[2] : M.b[2];
         if ((d1 >> b) & 1ull) claim(match_ion<METHOD>(B, __dadd_rn(m, kProton), itol), side == 0);
         if ((d2 >> b) & 1ull) claim(match_ion<METHOD>(B, __dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5), itol), side == 0);
-        if ((d3 >> b) & 1ull) claim(match_ion<METHOD>(B, __ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0), itol), side == 0);
+        if ((d3 >> b) & 1ull) claim(match_ion<METHOD>(B, div3_rn(__dadd_rn(m, __dmul_rn(3.0, kProton))), itol), side == 0);
         if (nch > kLadderCharges && k >= 4) {
             double t = __dmul_rn(__dadd_rn(m, 4.0 * kProton), 0.25);
             if (ion_may_match(B, t)) claim(match_ion<METHOD>(B, t, itol), side == 0);

@@ -254,6 +254,11 @@ __global__ void k2_place_mods(const ShuffleSeq* __restrict__ seqs, const Shuffle
                               const ShuffleMods* __restrict__ M, const uint8_t* __restrict__ raw,
                               const uint32_t* __restrict__ kept_index, const uint32_t* __restrict__ kept_count,
                               uint8_t* __restrict__ rows, const ModTable* __restrict__ table, uint4* __restrict__ lists) {
+    __shared__ double2 s_tab[kMaxCodes];
+    __shared__ double s_nt[kMaxTermCodes], s_ct[kMaxTermCodes];
+    for (int i = threadIdx.x; i < kMaxCodes; i += blockDim.x) s_tab[i] = make_double2(table->aa[i], table->delta[i]);
+    for (int i = threadIdx.x; i < kMaxTermCodes; i += blockDim.x) { s_nt[i] = table->nterm[i]; s_ct[i] = table->cterm[i]; }
+    __syncthreads();
     const uint32_t f = blockIdx.x;
     if (f >= n_forms) return;
     const ShuffleForm& F = forms[f];
@@ -310,7 +315,7 @@ __global__ void k2_place_mods(const ShuffleSeq* __restrict__ seqs, const Shuffle
         dst[0] = make_uint4(w[0], w[1], w[2], w[3]); dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
         dst[2] = make_uint4(w[8], w[9], w[10], w[11]); dst[3] = make_uint4(w[12], w[13], w[14], w[15]);
         // the spectrum-independent half of K1's Step-4 count pass: the cell of every (ion, fragment charge) of this row (k_cells.cuh)
-        if (lists) write_cell_lists(b, table, (int)F.list_nch, lists + F.list_base + k, F.list_chunks, (size_t)F.list_rows);
+        if (lists) write_cell_lists(b, s_tab, s_nt, s_ct, (int)F.list_nch, lists + F.list_base + k, F.list_chunks, (size_t)F.list_rows);
     }
 }
 

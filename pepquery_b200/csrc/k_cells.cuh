@@ -17,6 +17,8 @@
 // The rows of one peptide form are stored unit-major: unit u of row k at base + u * stride + k (stride = rows reserved for the
 // form), so the 32 rows a warp of K1 (one thread per row) reads, and a warp of K2 writes, are 512 contiguous bytes per unit.
 #pragma once
+#include <type_traits>
+
 #include "pq_common.h"
 
 namespace pq {
@@ -33,40 +35,48 @@ PQ_HD uint32_t list_stream_units(int L) { return L > 1 ? (uint32_t)(L - 1 + 7) >
 PQ_HD uint32_t list_chunks_side(int L, int nch_max) { return (uint32_t)nch_max * list_stream_units(L); }
 
 #ifdef __CUDACC__
-// Writes both sides of one row's lists: one ladder walk per side, every charge of an ion from the same running sum.
-// `row` = the 64 row bytes (any address space), M = the search's residue table.
-__device__ __forceinline__ void write_cell_lists(const uint8_t* row, const ModTable* __restrict__ M, int nch_max, uint4* __restrict__ dst /* unit 0 of this row */,
-                                                 uint32_t chunks_side, size_t stride) {
+// entry e into slot J (a compile-time number, 0..7) of a unit held as four 32-bit words
+template <int J> __device__ __forceinline__ void unit_put(uint32_t (&w)[4], uint32_t e) {
+    if (J & 1) w[J >> 1] = (w[J >> 1] & 0x0000FFFFu) | (e << 16);
+    else w[J >> 1] = (w[J >> 1] & 0xFFFF0000u) | e;
+}
+
+// Writes both sides of one row's lists: one ladder walk per side, every charge of an ion from the same running sum, a unit (eight
+// ions) at a time so that every slot of the packed words is a compile-time position.
+// `row` = the 64 row bytes, tab[code] = {residue mass, modification mass}, nt / ct = terminal masses (any address space).
+__device__ __forceinline__ void write_cell_lists(const uint8_t* row, const double2* tab, const double* nt, const double* ct, int nch_max,
+                                                 uint4* __restrict__ dst /* unit 0 of this row */, uint32_t chunks_side, size_t stride) {
     const int L = (int)row[0], Lm1 = L - 1;
     const uint32_t U = list_stream_units(L);
-    constexpr unsigned long long kSent4 = 0x0001000100010001ull * (unsigned long long)kListSentinel;
+    constexpr uint32_t kSent2 = 0x00010001u * kListSentinel;
     for (int side = 0; side < 2; ++side) {
         uint4* out = dst + (size_t)side * chunks_side * stride;
-        unsigned long long lo[kListMaxCharge], hi[kListMaxCharge];
+        double acc = side == 0 ? nt[row[1]] : ct[row[2]];
+        for (uint32_t u = 0; u < U; ++u) {
+            uint32_t w[kListMaxCharge][4];
 #pragma unroll
-        for (int c = 0; c < kListMaxCharge; ++c) { lo[c] = kSent4; hi[c] = kSent4; }
-        double acc = side == 0 ? M->nterm[row[1]] : M->cterm[row[2]];
-        for (int k = 1; k <= Lm1; ++k) {
-            const uint32_t code = row[kRowHeader + (side == 0 ? k - 1 : L - k)];
-            acc = __dadd_rn(__dadd_rn(acc, M->aa[code]), M->delta[code]);
-            const double m = side == 0 ? acc : __dadd_rn(acc, kWater);
-            uint32_t e[kListMaxCharge];
-            e[0] = cell_filter(__dadd_rn(m, kProton));
-            e[1] = (nch_max >= 2 && k >= 2) ? cell_filter(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5)) : kListSentinel;
-            e[2] = (nch_max >= 3 && k >= 3) ? cell_filter(__ddiv_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)), 3.0)) : kListSentinel;      // (the only real divide: skipped when no PSM of the form needs charge 3)
-            const int j = (k - 1) & 7, s = 16 * (j & 3);
+            for (int c = 0; c < kListMaxCharge; ++c) { w[c][0] = kSent2; w[c][1] = kSent2; w[c][2] = kSent2; w[c][3] = kSent2; }
+            auto ion = [&](int k, auto slot) {
+                constexpr int J = decltype(slot)::value;
+                const double2 t = tab[row[kRowHeader + (side == 0 ? k - 1 : L - k)]];
+                acc = __dadd_rn(__dadd_rn(acc, t.x), t.y);
+                const double m = side == 0 ? acc : __dadd_rn(acc, kWater);
+                unit_put<J>(w[0], cell_filter(__dadd_rn(m, kProton)));
+                if (nch_max >= 2 && k >= 2) unit_put<J>(w[1], cell_filter(__dmul_rn(__dadd_rn(m, 2.0 * kProton), 0.5)));
+                if (nch_max >= 3 && k >= 3) unit_put<J>(w[2], cell_filter(div3_rn(__dadd_rn(m, __dmul_rn(3.0, kProton)))));      // skipped when no PSM of the form needs charge 3
+            };
+            const int k0 = 8 * (int)u + 1;
+            if (k0 + 0 <= Lm1) ion(k0 + 0, std::integral_constant<int, 0>());
+            if (k0 + 1 <= Lm1) ion(k0 + 1, std::integral_constant<int, 1>());
+            if (k0 + 2 <= Lm1) ion(k0 + 2, std::integral_constant<int, 2>());
+            if (k0 + 3 <= Lm1) ion(k0 + 3, std::integral_constant<int, 3>());
+            if (k0 + 4 <= Lm1) ion(k0 + 4, std::integral_constant<int, 4>());
+            if (k0 + 5 <= Lm1) ion(k0 + 5, std::integral_constant<int, 5>());
+            if (k0 + 6 <= Lm1) ion(k0 + 6, std::integral_constant<int, 6>());
+            if (k0 + 7 <= Lm1) ion(k0 + 7, std::integral_constant<int, 7>());
 #pragma unroll
-            for (int c = 0; c < kListMaxCharge; ++c) {
-                if (j < 4) lo[c] = (lo[c] & ~(0xFFFFull << s)) | ((unsigned long long)e[c] << s);
-                else hi[c] = (hi[c] & ~(0xFFFFull << s)) | ((unsigned long long)e[c] << s);
-            }
-            if (j == 7 || k == Lm1) {
-#pragma unroll
-                for (int c = 0; c < kListMaxCharge; ++c) {
-                    if (c < nch_max) out[((size_t)c * U + (uint32_t)((k - 1) >> 3)) * stride] = make_uint4((uint32_t)lo[c], (uint32_t)(lo[c] >> 32), (uint32_t)hi[c], (uint32_t)(hi[c] >> 32));
-                    lo[c] = kSent4; hi[c] = kSent4;
-                }
-            }
+            for (int c = 0; c < kListMaxCharge; ++c)
+                if (c < nch_max) out[((size_t)c * U + u) * stride] = make_uint4(w[c][0], w[c][1], w[c][2], w[c][3]);
         }
     }
 }

@@ -500,6 +500,39 @@ int32_t pq_event_elapsed_ms(pq_ctx* ctx, double* ms) {
     *ms = f;
     return PQ_OK;
 }
+namespace pq { namespace {
+__global__ void k_selftest_div3(uint64_t n, uint64_t seed, unsigned long long* bad) {
+    unsigned long long local = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (i + 1);            // splitmix64
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        const uint64_t frac = z & 0xFFFFFFFFFFFFFull, ex = 1023 - 8 + (z >> 52) % 24;
+        const double x = __longlong_as_double((long long)((ex << 52) | frac));
+        for (int d = -2; d <= 2; ++d) {                                  // the value and its neighbours
+            const double v = __longlong_as_double(__double_as_longlong(x) + d);
+            if (__double_as_longlong(div3_rn(v)) != __double_as_longlong(__ddiv_rn(v, 3.0))) ++local;
+        }
+        const double y = __dmul_rn(3.0, x);                              // multiples of three (exact quotients) and what lies beside them
+        for (int d = -1; d <= 1; ++d) {
+            const double v = __longlong_as_double(__double_as_longlong(y) + d);
+            if (__double_as_longlong(div3_rn(v)) != __double_as_longlong(__ddiv_rn(v, 3.0))) ++local;
+        }
+    }
+    if (local) atomicAdd(bad, local);
+}
+} }
+int32_t pq_selftest(pq_ctx* ctx, int32_t which, uint64_t n, uint64_t seed, uint64_t* mismatches) {
+    if (!ctx || !mismatches || which != 1) return PQ_ERR_BAD_ARG;
+    cudaSetDevice(ctx->P.device);
+    CU(ctx->scratch.reserve(64));
+    CU(cudaMemsetAsync(ctx->scratch.p, 0, 8, ctx->st));
+    if (n) pq::k_selftest_div3<<<148 * 8, 256, 0, ctx->st>>>(n, seed, ctx->scratch.as<unsigned long long>());
+    unsigned long long bad = 0;
+    CU(cudaMemcpyAsync(&bad, ctx->scratch.p, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    *mismatches = bad;
+    return PQ_OK;
+}
 int32_t pq_get_counters(pq_ctx* ctx, pq_counters* out) {
     if (!ctx || !out) return PQ_ERR_BAD_ARG;
     cudaSetDevice(ctx->P.device);

@@ -59,7 +59,7 @@ EXPORTS = ["pq_version", "pq_last_error", "pq_default_params", "pq_create", "pq_
            "pq_step2_match_targets", "pq_step3_competitors", "pq_step4_shuffles", "pq_rank_and_validate",
            "pq_step5_ptm", "pq_get_psms", "pq_get_delta_scores", "pq_export_psms_device", "pq_get_competitors", "pq_get_shuffles", "pq_score_pairs",
            "pq_find_in_proteome", "pq_get_counters", "pq_reset_counters", "pq_event_record", "pq_event_elapsed_ms", "pq_parse_mgf",
-           "pq_read_ms_library"]
+           "pq_read_ms_library", "pq_selftest"]
 
 
 def _p(a):
@@ -285,6 +285,12 @@ class Search:
         ms = C.c_double()
         self._ck(self.L.pq_event_elapsed_ms(self.h, C.byref(ms)))
         return ms.value
+
+    def selftest(self, which, n, seed=1):
+        """Device self-test of an arithmetic shortcut (pq_selftest): number of mismatches, must be 0."""
+        bad = C.c_uint64()
+        self._ck(self.L.pq_selftest(self.h, C.c_int32(which), C.c_uint64(n), C.c_uint64(seed), C.byref(bad)))
+        return bad.value
 
     # -- the reference's names -------------------------------------------------------------------------------------
     def readMSMSfast(self, spectra, target_off, target_res):

@@ -1226,3 +1226,12 @@ def test_mgf_text_parsed_on_the_device(data):
         with pytest.raises(PepQueryError) as ei:
             g.load_mgf(bad)
         assert ei.value.code == _abi.PQ_ERR_BAD_ARG
+
+
+def test_divide_by_three_shortcut_is_the_ieee_division():
+    """The three-operation RN(x / 3) of the kernels (pq_common.h div3_rn: the m/z of triply charged fragments in K1, K2's cell lists and
+    the ladder tables) against __ddiv_rn on the device: 8 values around each of 2^26 pseudo-random doubles, no mismatch."""
+    g = Search(_abi.default_params())
+    assert g.selftest(1, 1 << 26, seed=2022) == 0
+    assert g.selftest(1, 1 << 20, seed=7) == 0
+    g.close()
