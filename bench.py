@@ -479,7 +479,7 @@ def main():
                                       "frac": wps / wpeak, "ncu_pct": prof.get("lsu_wavefronts_pct")}
     alg = (k1_bytes / 1e9) / (k1_ms / 1e3) if k1_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "kernel": "k1_score_kernel<256,%d> (Step 4, one launch per step)" % a.method, "peak_source": peak_src,
+                "kernel": "k1_score_kernel<128,%d> (Step 4, one launch per step)" % a.method, "peak_source": peak_src,
                 "ms_per_launch": k1_ms, "pairs_per_launch": k1_pairs,
                 "issue": issue, "binding": ("the L1/shared-memory data pipe (issue.lsu_data_pipe.frac) and warp-instruction issue slots (issue.frac), not HBM" if issue and issue.get("lsu_data_pipe")
                                             else "issue slots (warp-instruction issue), not HBM") if issue else None,

@@ -32,13 +32,13 @@ template <int BLOCK, int METHOD>
 __host__ __device__ constexpr size_t kFixedSmem() {      // without the residue table, which follows it (its size is a launch parameter)
     return ((size_t)16 * BLOCK * 4 + (size_t)(2 * kMaxTermCodes + 130) * 8 + (METHOD == 2 ? (size_t)10 * BLOCK * 4 : 0) + 127) & ~(size_t)127;
 }
-// Copies of every residue-table entry: the Step-4 configuration (BLOCK 256) is bound by shared-memory bandwidth (ncu: 0.77
+// Copies of every residue-table entry: the Step-4 configuration (BLOCK 128 / 256) is bound by shared-memory bandwidth (ncu: 0.77
 // wavefronts per cycle and SM, 41 % of them bank conflicts of the random 16-byte table look-ups); with 8 copies, copy
 // lane & 7, a quarter-warp's look-ups are conflict-free.
-template <int BLOCK> __host__ __device__ constexpr int kTabCopies() { return BLOCK == 256 ? 8 : 1; }
+template <int BLOCK> __host__ __device__ constexpr int kTabCopies() { return BLOCK >= 128 ? 8 : 1; }
 
 template <int BLOCK, int METHOD>
-__global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? K1_MIN_BLOCKS : (BLOCK == 64 ? 11 : 1))
+__global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? K1_MIN_BLOCKS : (BLOCK == 128 ? 2 * K1_MIN_BLOCKS : (BLOCK == 64 ? 11 : 1)))
 k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage, uint32_t tab_bytes, uint32_t n_codes) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -71,9 +71,9 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     // Jobs are handed out by an atomic counter (in list order, so neighbouring CTAs share table rows in L2); the next
     // job's blob is already in flight (second stage) while the current one is scored.
     __shared__ uint32_t s_job[2];
-    constexpr uint32_t kSurvCap = BLOCK == 256 ? 1024 : 2 * BLOCK;      // only the Step-4 configuration (BLOCK 256) pays for a long list
+    constexpr uint32_t kSurvCap = BLOCK >= 128 ? 1024 : 2 * BLOCK;      // only the Step-4 configurations (BLOCK 128 / 256) pay for a long list
     __shared__ uint16_t s_surv[kSurvCap];         // bounded Step 4: candidates the score bound could not decide (index within the job)
-    __shared__ __align__(16) uint8_t s_cflag[BLOCK == 256 ? kCells + 16 : 16];      // Step-4 count pass: one byte per cell of the job's spectrum, 1 = nothing can be claimed (+ the list sentinel)
+    __shared__ __align__(16) uint8_t s_cflag[BLOCK >= 128 ? kCells + 16 : 16];      // Step-4 count pass: one byte per cell of the job's spectrum, 1 = nothing can be claimed (+ the list sentinel)
     __shared__ uint32_t s_nsurv;
     const bool bounded = L.kind == kJobShuffles && !cfg.score_all && !cfg.check_window;
     auto fetch = [&](uint32_t slot) {           // thread 0: take the next job and start its TMA into `slot`
@@ -135,7 +135,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
                 }
             }
             if (tid == 0) s_nsurv = 0;
-            if (BLOCK == 256 && job_lists) {
+            if (BLOCK >= 128 && job_lists) {
                 // the clean flags of the staged cell table, one byte per cell: a list entry then costs a byte load and an add
                 const uint4* src = reinterpret_cast<const uint4*>(B.cells);
                 for (uint32_t q = tid; q < (uint32_t)kCells / 8; q += BLOCK) {
@@ -355,7 +355,13 @@ int launch_block(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) 
 int launch_score(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) {
     if (L.n_jobs == 0) return 0;
     switch (L.kind) {
-        case kJobShuffles: return launch_block<256>(L, cfg, st);
+        case kJobShuffles: {
+            // CTAs of 128 threads, one blob stage: the ~40 undecided shuffles of a job keep two of FOUR warps busy instead of two of eight,
+            // and eight CTAs per SM hide the blob load of the next job (C2 size: 96 threads 8.85 ms, 128 7.85, 160 8.1, 192 8.3, 256 with
+            // two stages 8.6; PQ_STEP4_BLOCK=256 selects the latter)
+            const char* e = getenv("PQ_STEP4_BLOCK");
+            return e && atoi(e) == 256 ? launch_block<256>(L, cfg, st) : launch_block<128>(L, cfg, st);
+        }
         case kJobCompetitors:
             if (L.lad && !getenv("PQ_STEP3_WALK")) return launch_score_ladder(L, cfg, st);
             return launch_block<64>(L, cfg, st);

@@ -1,4 +1,4 @@
-"""profiles/k1_step4_profile.json from an `ncu --set full` capture of bench.py's Step-4 K1 launch (k1_score_kernel<256, METHOD>):
+"""profiles/k1_step4_profile.json from an `ncu --set full` capture of bench.py's Step-4 K1 launch (k1_score_kernel<128, METHOD>; <256, METHOD> with PQ_STEP4_BLOCK=256):
 DRAM bytes, warp instructions and issue utilisation of ONE launch.  bench.py divides the first two by the launch time it measures live.
 
     python tools/make_step4_profile.py gpurun_out/prof_TAG.ncu-rep profiles/TAG_k1_ncu_full.txt"""
@@ -9,8 +9,8 @@ out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[0]
 col = {h: i for i, h in enumerate(hdr)}
-pick = [r for r in rows[2:] if "k1_score_kernel<256" in r[col["Kernel Name"]].replace("(int)", "")]
-assert pick, "no k1_score_kernel<256, ...> launch in the capture"
+pick = [r for r in rows[2:] if "k1_score_kernel<128" in r[col["Kernel Name"]].replace("(int)", "") or "k1_score_kernel<256" in r[col["Kernel Name"]].replace("(int)", "")]
+assert pick, "no k1_score_kernel<128 / 256, ...> launch in the capture"
 r = pick[-1]
 unit = {h: rows[1][i] for h, i in col.items()}
 
