@@ -32,6 +32,11 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  : "memory");
 }
 
+// pulls a global range towards L2 (no destination in the SM): the bulk copy that follows finds it there
+__device__ __forceinline__ void prefetch_l2_bulk(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 struct BlobView {
     const double* ev; const uint16_t* ans; const double* pmz; const double* pin; const uint16_t* pcode; const double* val; const uint16_t* cells; const uint32_t* cbits;
     uint32_t E; uint32_t nsurv; uint32_t flags; int32_t cls[4];

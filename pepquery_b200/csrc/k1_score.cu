@@ -65,6 +65,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     __syncthreads();
 
     const double itol = cfg.itol;
+    const bool prefetch = cfg.prefetch_next != 0;
     uint32_t* codes = codes_all + tid;
     uint32_t* usedw = usedw_all + tid;
 
@@ -76,8 +77,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
     __shared__ __align__(16) uint8_t s_cflag[BLOCK >= 128 ? kCells + 16 : 16];      // Step-4 count pass: one byte per cell of the job's spectrum, 1 = nothing can be claimed (+ the list sentinel)
     __shared__ uint32_t s_nsurv;
     const bool bounded = L.kind == kJobShuffles && !cfg.score_all && !cfg.check_window;
-    auto fetch = [&](uint32_t slot) {           // thread 0: take the next job and start its TMA into `slot`
-        uint32_t nj = atomicAdd(L.job_counter, 1u);
+    auto load = [&](uint32_t slot, uint32_t nj) {      // thread 0: start the TMA of job nj into `slot`
         s_job[slot] = nj;
         if (nj < L.n_jobs) {
             const Job& Jn = L.jobs[nj];
@@ -86,13 +86,21 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
             tma_load_1d(stage0 + (size_t)stage_bytes * slot, L.blobs + L.blob_off[Jn.blob], bytes, &s_bar[slot]);
         }
     };
+    auto fetch = [&](uint32_t slot) { load(slot, atomicAdd(L.job_counter, 1u)); };      // take the next job and start its TMA
+    // one stage: the next job is taken while the current one is scored and its blob pulled towards L2, so the copy that starts when
+    // the stage is free again comes from L2 instead of HBM
+    uint32_t next_job = 0xFFFFFFFFu;                   // (thread 0 only)
+    auto claim = [&]() {
+        next_job = atomicAdd(L.job_counter, 1u);
+        if (next_job < L.n_jobs) { const Job& Jn = L.jobs[next_job]; prefetch_l2_bulk(L.blobs + L.blob_off[Jn.blob], L.blob_len[Jn.blob]); }
+    };
     if (tid == 0) fetch(0);
     __syncthreads();
     uint32_t job = s_job[0];
     for (uint32_t it = 0; job < L.n_jobs; ++it) {
         const uint32_t cur = nstage == 2 ? (it & 1u) : 0u;
         const uint32_t parity = nstage == 2 ? ((it >> 1) & 1u) : (it & 1u);
-        if (nstage == 2 && tid == 0) fetch(cur ^ 1u);
+        if (tid == 0) { if (nstage == 2) fetch(cur ^ 1u); else if (prefetch) claim(); }
         const Job J = L.jobs[job];
         mbar_wait(&s_bar[cur], parity);
         const BlobView B = view_blob(stage0 + (size_t)stage_bytes * cur);
@@ -226,7 +234,7 @@ k1_score_kernel(ScoreLaunch L, ScoreConfig cfg, uint32_t stage_bytes, int nstage
             }
             JobResult R; R.n_in_window = a; R.n_better = b; R.best_score = bs; R.best_cand = bc; R.pad = nb;
             L.results[job] = R;
-            if (nstage == 1) fetch(0);
+            if (nstage == 1) { if (prefetch) load(0, next_job); else fetch(0); }
         }
         __syncthreads();
         job = s_job[nstage == 2 ? (cur ^ 1u) : 0u];

@@ -222,6 +222,7 @@ ScoreConfig score_config(const pq_ctx* c, int check_window) {
     s.check_window = check_window;
     s.score_all = c->P.score_all_shuffles || getenv("PQ_SCORE_ALL_SHUFFLES") != nullptr;
     s.no_bucket = 0;
+    s.prefetch_next = getenv("PQ_NO_BLOB_PREFETCH") ? 0 : 1;
     return s;
 }
 

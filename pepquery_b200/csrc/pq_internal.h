@@ -94,6 +94,7 @@ struct ScoreConfig {
     int32_t mvh_bins;
     int32_t check_window;     // candidates must pass the bucket + tolerance predicate (Steps 2, 3, 5)
     int32_t score_all;        // Step 4: compute every shuffle's score in full (no upper-bound decision)
+    int32_t prefetch_next;    // one-stage K1 jobs: take the next job early and pull its blob towards L2 (off: PQ_NO_BLOB_PREFETCH)
     int32_t no_bucket;        // Step 2 of a library search: only |mass error| <= tol, no +-1 rule on the 0.1-Da buckets (MsLibrarySearchWorker.java:118-120)
 };
 
