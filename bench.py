@@ -71,18 +71,21 @@ def workload_name(a, world=1):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe: start before, kill after).
+    The process is started ahead of the timed region (its start-up — driver queries of several 10 ms — was seen to cost the first
+    timed steps ~1 ms each when it began inside); only the samples whose own time stamps fall inside the region are used."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.lines = []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -93,30 +96,44 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def region_begin(self):
+        self.t0 = time.time()
+
+    def region_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _stamp(txt):
+        import datetime
+        try:
+            return datetime.datetime.strptime(txt.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                rows.append((self._stamp(f[0]), float(f[2]), float(f[3]), [nm for k, nm in enumerate(names) if f[6 + k].lower().startswith("active")]))
             except ValueError:
                 continue
-            for k, nm in enumerate(names):
-                if f[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
+        inside = [r for r in rows if r[0] is not None and self.t0 is not None and self.t0 - 0.03 <= r[0] <= (self.t1 or 1e18) + 0.03]
+        use = inside if inside else rows[-3:]          # a region shorter than the sampling period: the samples next to it
+        sm = [r[1] for r in use]; mx = [r[2] for r in use]; reasons = set(x for r in use for x in r[3])
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_inside_region": len(inside)}
 
 
 def java_probe():
@@ -407,7 +424,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    def resident_run(params, steps, warm):
+    def resident_run(params, steps, warm, before_warmup=None):
         """Spectra, targets and the reference table resident; one step = Steps 2 (incl. K0) + 3 + 4 + rank + results to the host."""
         g = Search(params)
         g.load_spectra(sp); g.set_targets(*tgt); g.step2(); g.build_reference(*prot)
@@ -419,6 +436,9 @@ def main():
         g.step3(); g.step4(); g.rank()
         g.ms_ladder_once = g.counters().ms_ladder        # fragment-ladder tables of the reference rows: built with the table, not per step
         size_gather_buffers(g)
+        if before_warmup:
+            before_warmup()                     # the clock sampler starts here: its start-up falls into the warm-up steps
+            time.sleep(0.25)
         for _ in range(max(warm, 1)):
             step()
         g.reset_counters()
@@ -432,11 +452,12 @@ def main():
     # spectrum preparation (K0) stays inside the timed Step 2, so prepare_at_load is off here; the end-to-end arm below uses the
     # library defaults (candidate-first upload, K0 chunk by chunk under it)
     warm = max(a.warmup, 3)
-    g, step, ms_host_reference = resident_run(mk_params(0), a.steps, warm)
     clocks = ClockSampler(local)
+    g, step, ms_host_reference = resident_run(mk_params(0), a.steps, warm, before_warmup=clocks.start)
     barrier()
-    clocks.start()
+    clocks.region_begin()
     t_max, t_mine, n_psm_total = timed(step, a.steps, g)
+    clocks.region_end()
     clk = clocks.stop()
     c = g.counters()
     pairs_step = (c.pairs_step2 + c.pairs_step3 + c.pairs_step4) / a.steps

@@ -74,8 +74,30 @@ def source(rep, pattern, top=40):
     return s
 
 
+def step_shares(path):
+    """Per-kernel shares of ONE resident step of `bench.py --steps 1 --warmup 1 --no-cpu --e2e-steps 0 --no-configs`: the last step whose
+    Step-4 launch took < 15 ms (the all-scored arm takes > 30 ms), from its k_enumerate_targets to the kernel before the next load
+    (k_virtual_meta) or the next step."""
+    _, rows = launches(path)
+    names = [r['Kernel Name'].split('(')[0] for r in rows]
+    s4 = [i for i, n in enumerate(names) if ('k1_score_kernel<128' in n or 'k1_score_kernel<256' in n) and float(rows[i]['Metric Value']) < 15e6]
+    e = s4[-1]
+    a = max(i for i, n in enumerate(names) if 'k_enumerate_targets' in n and i < e)
+    b = min([i for i, n in enumerate(names) if ('k_enumerate_targets' in n or 'k_virtual_meta' in n) and i > e] + [len(rows)])
+    agg = collections.OrderedDict()
+    for r in rows[a:b]:
+        k = r['Kernel Name'].split('(')[0][-70:]
+        v = agg.setdefault(k, [0, 0.0]); v[0] += 1; v[1] += float(r['Metric Value'])
+    tot = sum(v[1] for v in agg.values())
+    out = "one resident step (bench.py --steps 1 --warmup 1 --no-cpu --e2e-steps 0 --no-configs under ncu, launches %d..%d): %d launches, %.3f ms device time (cold-cache, serialised: compare shares)\n" % (a, b - 1, b - a, tot / 1e6)
+    for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
+        out += "%-72s n=%3d %9.3f ms %5.1f%%\n" % (k, v[0], v[1] / 1e6, 100 * v[1] / tot)
+    return out
+
+
 if __name__ == "__main__":
     cmd = sys.argv[1]
     if cmd == "launches": print(launches(sys.argv[2])[0])
+    elif cmd == "step-shares": print(step_shares(sys.argv[2]), end="")
     elif cmd == "raw": print(raw(sys.argv[2]))
     elif cmd == "source": print(source(sys.argv[2], sys.argv[3]))
