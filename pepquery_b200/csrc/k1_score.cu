@@ -368,6 +368,7 @@ int launch_score(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) 
             // and eight CTAs per SM hide the blob load of the next job (C2 size: 96 threads 8.85 ms, 128 7.85, 160 8.1, 192 8.3, 256 with
             // two stages 8.6; PQ_STEP4_BLOCK=256 selects the latter)
             const char* e = getenv("PQ_STEP4_BLOCK");
+            if (cfg.score_all && !e) return launch_block<256>(L, cfg, st);      // every shuffle scored in full: all warps busy anyway, two stages win (32.3 vs 35.0 ms)
             return e && atoi(e) == 256 ? launch_block<256>(L, cfg, st) : launch_block<128>(L, cfg, st);
         }
         case kJobCompetitors:
