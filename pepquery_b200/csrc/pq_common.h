@@ -163,7 +163,8 @@ PQ_HD double ddiv(double a, double b) {
 // ion).  r = RN(1/3) = (1/3)(1 - 2^-54); q0 = RN(x r) is within 1.5 ulp of x/3; rem = x - 3 q0 is exact (a multiple of ulp(q0) below
 // 5 ulp); q0 + rem r = x/3 - (rem/3) 2^-54, i.e. x/3 moved by less than 2^-53 ulp, and x/3 is never closer than ulp/6 to a rounding
 // boundary (a midpoint times 3 needs 55 bits, so x - 3 * midpoint is a non-zero multiple of ulp/2): the final rounding returns
-// RN(x/3), the double __ddiv_rn(x, 3.0) returns (tests compare the two on the device).
+// RN(x/3), the double __ddiv_rn(x, 3.0) returns (tests: pq_selftest compares the two on the device; tests/test_oracle_pins.py replays
+// the three operations in exact rational arithmetic).
 __device__ __forceinline__ double div3_rn(double x) {
     const double r = 0.33333333333333331;
     const double q0 = __dmul_rn(x, r);

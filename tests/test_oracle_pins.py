@@ -318,3 +318,41 @@ def test_novelty_filter_against_python_substring_search():
     off, res, want = synth.planted_targets(prot, np.random.default_rng(5))
     got = pq_oracle.find_in_proteome(off, res, prot[0], prot[1])
     assert np.array_equal(got, want) and 40 < want.sum() < len(want)
+
+
+def test_divide_by_three_shortcut_in_exact_arithmetic():
+    """pq_common.h div3_rn — RN(x r), one exact remainder, one fused correction with r = RN(1/3) — returns RN(x / 3).  Replayed with
+    exact rationals (float(Fraction) rounds to nearest-even once, which is what a fused multiply-add does) on random significands over
+    the exponents fragment masses can have, on the neighbours of multiples of three, and on the extremes of the significand."""
+    from fractions import Fraction
+    import random
+    import struct
+
+    r = 0.33333333333333331
+    assert r == float(Fraction(1, 3)) and Fraction(r) == Fraction(2 ** 54 - 1, 3 * 2 ** 54)
+
+    def fma(a, b, c):
+        return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+    def div3(x):
+        q0 = float(Fraction(x) * Fraction(r))
+        rem = fma(-3.0, q0, x)
+        assert Fraction(rem) == Fraction(x) - 3 * Fraction(q0)          # the remainder is exact
+        return fma(rem, r, q0)
+
+    def nudge(x, d):
+        return struct.unpack("<d", struct.pack("<q", struct.unpack("<q", struct.pack("<d", x))[0] + d))[0]
+
+    rnd = random.Random(2022)
+    xs = []
+    for _ in range(30000):
+        x = rnd.random() + 1.0
+        xs.append(x * 2.0 ** rnd.randint(-8, 15))
+    for _ in range(10000):
+        y = 3.0 * float(rnd.randint(1, 2 ** 52))
+        xs += [nudge(y, -1), y, nudge(y, 1)]
+    for e in range(-8, 16):
+        for m in (1.0, nudge(1.0, 1), nudge(2.0, -1), 1.5, nudge(1.5, -1), nudge(1.5, 1)):
+            xs.append(m * 2.0 ** e)
+    for x in xs:
+        assert div3(x) == float(Fraction(x) / 3), x
