@@ -1,6 +1,7 @@
 // k1_score.cu — K1: the pair scorer.  One CTA owns one job (= one prepared spectrum x a run of candidate peptide
-// rows); the spectrum blob is staged into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier,
-// double-buffered across jobs); one THREAD scores one (peptide, spectrum) pair.
+// rows); the spectrum blob is staged into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier; the next
+// job is taken early and its blob pulled towards L2 meanwhile, or — 256-thread configuration — loaded into a second
+// stage); one THREAD scores one (peptide, spectrum) pair.
 //
 // Replaces the body of PeptideSearchMT.scorePeptide2Spectrum (pg/PeptideSearchMT.java:1144-1251):
 //   annotator   JMatch.getSpectrumAnnotation (PSMMatch/JMatch.java:388-466) -> compomics PeptideSpectrumAnnotator
@@ -334,8 +335,8 @@ int launch_kernel(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st)
     const uint32_t n_codes = kTabCopies<BLOCK>() > 1 ? std::min<uint32_t>(std::max<uint32_t>(L.n_codes, 26u), (uint32_t)kMaxCodes) : (uint32_t)kMaxCodes;
     const uint32_t tab_bytes = (n_codes * (uint32_t)kTabCopies<BLOCK>() * 16u + 127u) & ~127u;
     const size_t tail = kFixedSmem<BLOCK, METHOD>() + tab_bytes;
-    // Shuffle jobs (~1000 pairs each) hide the blob load behind a second stage; target / competitor jobs are short, there
-    // one stage and more resident CTAs win (measured: Step 2 9.1 -> 5.4 ms, Step 3 18.7 -> 13.4 ms).
+    // 256-thread shuffle jobs (~1000 pairs each) hide the blob load behind a second stage; everywhere else one stage and more
+    // resident CTAs win (measured: Step 2 9.1 -> 5.4 ms, Step 3 18.7 -> 13.4 ms, Step 4 with 128 threads 9.1 -> 7.85 ms).
     int nstage = BLOCK == 256 ? 2 : 1;
     if ((size_t)stage * 2 + tail > 100 * 1024) nstage = 1;
     if (const char* e = getenv("PQ_K1_STAGES")) nstage = atoi(e) == 1 ? 1 : (atoi(e) == 2 ? 2 : nstage);
@@ -365,7 +366,7 @@ int launch_score(const ScoreLaunch& L, const ScoreConfig& cfg, cudaStream_t st) 
     switch (L.kind) {
         case kJobShuffles: {
             // CTAs of 128 threads, one blob stage: the ~40 undecided shuffles of a job keep two of FOUR warps busy instead of two of eight,
-            // and eight CTAs per SM hide the blob load of the next job (C2 size: 96 threads 8.85 ms, 128 7.85, 160 8.1, 192 8.3, 256 with
+            // and seven CTAs per SM (shared memory) hide the blob load of the next job (C2 size: 96 threads 8.85 ms, 128 7.85, 160 8.1, 192 8.3, 256 with
             // two stages 8.6; PQ_STEP4_BLOCK=256 selects the latter)
             const char* e = getenv("PQ_STEP4_BLOCK");
             if (cfg.score_all && !e) return launch_block<256>(L, cfg, st);      // every shuffle scored in full: all warps busy anyway, two stages win (32.3 vs 35.0 ms)
